@@ -1,0 +1,171 @@
+/*
+ * mogpe_b200 -- C-ABI of the B200-native hot path of aidanscannell/mogpe.
+ *
+ * The reference has no FFI/plugin interface: its hot path is Python methods calling GPflow / TFP / TF
+ * (SURVEY.md 8b).  This header is the boundary a replacement sits behind: the Python classes in
+ * mogpe_b200/ (same names and signatures as the reference's) call these entry points through ctypes
+ * with plain device/host pointers and sizes -- no framework types cross it.  Each entry point names
+ * the reference code it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - float64 everywhere (reference: tf.keras.backend.set_floatx("float64"),
+ *     mogpe/keras/mixture_of_experts/mosvgpe.py:13).
+ *   - X [N, D], Y [N, F] row-major (reference convention).
+ *   - "group" = one (inducing inputs Z, kernel) pair: Kuu, its Cholesky factor and A = L^-1 Kuf are per
+ *     group.  "latent" = one latent GP (one q_mu column + one q_sqrt matrix) and belongs to a group.
+ *     Latent order: expert k output f -> k*F + f  (P_e = K*F of them), then the G gating latents.
+ *   - Parameters cross the boundary in CONSTRAINED space in one packed buffer (mogpe_param_layout);
+ *     gradients come back in the same layout.  The host chains softplus / FillTriangular Jacobians
+ *     (reference: gpflow Parameter transforms).
+ *   - All inducing dimensions are padded to Mp (mogpe_layout.Mp); padded rows/cols are ignored on input
+ *     and zero in gradients.
+ *   - Standard-normal draws are explicit inputs (RNG parity with TF is impossible);
+ *     mogpe_fill_normal generates them on the device for production use.
+ *   - Ownership: the caller owns every buffer; the handle owns only scratch.  Errors: integer status,
+ *     text via mogpe_last_error.  A handle is bound to one device; calls on a handle are serialised by
+ *     the caller; work is enqueued on the caller's stream.
+ */
+#ifndef MOGPE_B200_H
+#define MOGPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOGPE_MAX_GROUPS 64
+#define MOGPE_MAX_LATENTS 64
+#define MOGPE_MAX_SAMPLES 16
+
+typedef enum {
+  MOGPE_OK = 0,
+  MOGPE_ERR_INVALID = 1,
+  MOGPE_ERR_CUDA = 2,
+  MOGPE_ERR_UNSUPPORTED = 3,
+  MOGPE_ERR_NCCL = 4
+} mogpe_status;
+
+/* bound ids: mogpe/keras/mixture_of_experts/mosvgpe.py:83-107 ; mogpe/mixture_of_experts/svgp.py:102-124 */
+enum { MOGPE_BOUND_FURTHER_GATING = 0, MOGPE_BOUND_TIGHT = 1, MOGPE_BOUND_FURTHER = 2 };
+/* API flavour selects the documented numerical quirks */
+enum { MOGPE_FLAVOUR_KERAS = 0, MOGPE_FLAVOUR_LEGACY = 1 };
+
+typedef struct mogpe_desc {
+  int32_t input_dim;      /* D */
+  int32_t output_dim;     /* F */
+  int32_t num_experts;    /* K */
+  int32_t num_gating;     /* G: 1 = Bernoulli gating (K must be 2), else Softmax with G == K */
+  int32_t num_groups;     /* Q */
+  int32_t num_latents;    /* P = K*F + G */
+  int32_t max_batch;      /* largest N passed to the ELBO call; predict streams in chunks of this */
+  int32_t flavour;        /* MOGPE_FLAVOUR_* */
+  int32_t device;         /* CUDA device ordinal */
+  int32_t reserved;
+  double jitter;          /* gpflow default_jitter() = 1e-6 */
+  const int32_t* group_num_inducing; /* [Q] true M per group */
+  const int32_t* latent_group;       /* [P] */
+} mogpe_desc;
+
+/* Offsets (in doubles) into the packed parameter / gradient buffer. */
+typedef struct mogpe_layout {
+  int64_t lengthscales; /* [Q, D]        kernel lengthscales (ARD; host broadcasts scalars) */
+  int64_t variance;     /* [Q]           kernel variance */
+  int64_t Z;            /* [Q, Mp, D]    inducing inputs */
+  int64_t q_mu;         /* [P, Mp] */
+  int64_t q_sqrt;       /* [P, Mp, Mp]   lower-triangular */
+  int64_t mean_c;       /* [P]           Constant mean function (0 for Zero) */
+  int64_t noise;        /* [K*F]         Gaussian likelihood variance per expert output */
+  int64_t total;
+  int32_t Mp;
+  int32_t reserved;
+} mogpe_layout;
+
+typedef struct mogpe_handle mogpe_handle;
+
+/* Replaces the construction of the gpflow SVGP objects inside SVGPExpert / SVGPGatingNetwork
+ * (mogpe/keras/experts.py:54-65, mogpe/keras/gating_networks.py:108-119). */
+mogpe_status mogpe_create(const mogpe_desc* desc, mogpe_handle** out);
+void mogpe_destroy(mogpe_handle* h);
+const char* mogpe_last_error(const mogpe_handle* h); /* h may be NULL: last create error */
+mogpe_status mogpe_param_layout(const mogpe_handle* h, mogpe_layout* out);
+
+/* Minibatch ELBO, forward and (if grads != NULL) backward.
+ * Replaces MixtureOfSVGPExperts.maximum_log_likelihood_objective / elbo / lower_bound_* and the
+ * GradientTape in train_step (mogpe/keras/mixture_of_experts/mosvgpe.py:57-274;
+ * mogpe/mixture_of_experts/svgp.py:67-469), including everything they call in experts.py,
+ * gating_networks.py, gps.py and GPflow (conditional, gauss_kl, likelihoods).
+ *
+ *   X [N, D], Y [N, F], params, grads: device pointers.
+ *   eps_u [P, S, Mp]  draws for u ~ q(u) of inducing-sampled latents (others ignored; may be NULL when
+ *                     no latent is inducing-sampled under `bound`)
+ *   eps_h [S, N, G]   marginal gating draws (further_gating, further)
+ *   eps_f [S, N, K*F] marginal expert draws (further)
+ *   scale             num_data / N, or 1.0 when num_data is None (mosvgpe.py:309-316)
+ *   out   [4] device: {elbo, variational expectation (scaled), KL gating, KL experts}
+ */
+mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, const double* Y, int32_t N,
+                                const double* params, const double* eps_u, const double* eps_h,
+                                const double* eps_f, int32_t bound, int32_t num_samples, double scale,
+                                double* out, double* grads, void* cuda_stream);
+
+/* Same call with HOST X / Y / eps (pinned or pageable) and a host result: copies in, runs, copies the
+ * 4 result doubles out and synchronises the stream.  params / grads stay device-resident (model state).
+ * This is the end-to-end entry the Python train_step uses for host-side data. */
+mogpe_status mogpe_elbo_fwd_bwd_host(mogpe_handle* h, const double* X_host, const double* Y_host, int32_t N,
+                                     const double* params, const double* eps_u_host,
+                                     const double* eps_h_host, const double* eps_f_host, int32_t bound,
+                                     int32_t num_samples, double scale, double* out_host, double* grads,
+                                     void* cuda_stream);
+
+/* Prediction.  Replaces predict_y / predict_experts_f / predict_experts_y / predict_mixing_probs
+ * (mogpe/keras/mixture_of_experts/base.py:65-77, mosvgpe.py:276-290, keras/gating_networks.py:173-249;
+ * mogpe/mixture_of_experts/base.py:58-115, mogpe/experts/svgp.py:171-227,
+ * mogpe/gating_networks/svgp.py:49-105).  Any output pointer may be NULL.
+ *   f_mean, f_var [N, P]  marginal q(f) per latent (with the q_sqrt term, no sampling)
+ *   mix_probs [N, K]      Bernoulli: analytic probit; Softmax: mean over eps_mc [R, N, K] draws
+ *   y_mean, y_var [N, F]  mixture mean / variance (flavour-specific formula)
+ * X and outputs are device pointers; N is streamed in chunks of max_batch. */
+mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const double* params, double* f_mean,
+                           double* f_var, double* mix_probs, double* y_mean, double* y_var,
+                           const double* eps_mc, int32_t num_mc, void* cuda_stream);
+
+/* Counter-based N(0,1) generator (Philox4x32-10 + Box-Muller) for the eps_* inputs.  Stand-in for the
+ * tf.random / tfd sampling inside the reference's bounds (mogpe/keras/gps.py:29, gpflow sample_mvn). */
+mogpe_status mogpe_fill_normal(mogpe_handle* h, double* dst, int64_t n, uint64_t seed, uint64_t offset,
+                               void* cuda_stream);
+
+/* Data-parallel gradient sum (north_star: one allreduce per step over NVLink).  The unique id is
+ * created on rank 0 and distributed by the caller (torch.distributed / MPI / file). */
+mogpe_status mogpe_nccl_unique_id(char out[128]);
+mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int32_t rank, int32_t world_size);
+mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_t n, void* cuda_stream);
+
+/* Device memory helpers so the Python host needs no tensor framework. */
+mogpe_status mogpe_malloc(int32_t device, int64_t bytes, void** out);
+mogpe_status mogpe_free(int32_t device, void* p);
+mogpe_status mogpe_malloc_host(int64_t bytes, void** out); /* pinned */
+mogpe_status mogpe_free_host(void* p);
+mogpe_status mogpe_memcpy_h2d(int32_t device, void* dst, const void* src, int64_t bytes, void* cuda_stream);
+mogpe_status mogpe_memcpy_d2h(int32_t device, void* dst, const void* src, int64_t bytes, void* cuda_stream);
+mogpe_status mogpe_memset_zero(int32_t device, void* dst, int64_t bytes, void* cuda_stream);
+mogpe_status mogpe_stream_sync(int32_t device, void* cuda_stream);
+
+/* Test hook: copy a named intermediate of the last call to the host (Kuu, L, Linv, Kuf, A, ...).
+ * Returns the element count in *n_out; copies min(capacity, count) doubles. */
+mogpe_status mogpe_debug_copy(mogpe_handle* h, const char* name, double* dst_host, int64_t capacity,
+                              int64_t* n_out);
+
+/* Test hook: batched FP64 GEMM on the library's DMMA kernel, C = alpha*op(A)*op(B) + beta*C (row-major,
+ * device pointers, dims multiples of 64).  kmode: bit0 left-lower, bit1 left-upper, bit2 right-lower,
+ * bit3 right-upper (restricts the k range per tile); tril_out: only lower-triangular tiles are produced. */
+mogpe_status mogpe_debug_gemm(int32_t device, const double* A, const double* B, double* C, int32_t batch,
+                              int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, int32_t kmode,
+                              int32_t tril_out, double alpha, double beta, void* cuda_stream);
+
+const char* mogpe_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOGPE_B200_H */

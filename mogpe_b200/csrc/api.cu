@@ -1,0 +1,769 @@
+// C-ABI implementation: handle, workspace and the kernel schedule of the ELBO forward/backward and of
+// prediction.  See include/mogpe_b200.h for the contract and DESIGN.md for the schedule.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mogpe_b200.h"
+#include "gemm_f64.cuh"
+#include "kernels.cuh"
+#include "lik.cuh"
+#include "model_dev.cuh"
+
+using namespace mogpe;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct mogpe_handle {
+  mogpe_desc desc;
+  std::vector<int32_t> group_M, latent_group;
+  int device = 0;
+  int Mp = 0, Bp = 0, Pe = 0;
+  Layout lo{};
+  ModelDev md_host{};
+  ModelDev* d_md = nullptr;
+  int cur_bound = -100, cur_S = -1;
+  // workspace (doubles)
+  double *Kuu = nullptr, *L = nullptr, *Linv = nullptr;            // [Q][Mp][Mp]
+  double *Lbar = nullptr, *T1 = nullptr, *T2 = nullptr;            // [Q][Mp][Mp]
+  double *Kuf = nullptr, *A = nullptr, *Abar = nullptr, *W = nullptr;  // [Q][Mp][Bp]
+  double* LTA = nullptr;                                           // [P][Mp][Bp]
+  double* Sc = nullptr;                                            // [P][Mp][Mp]
+  double *V = nullptr, *dV = nullptr;                              // [NVcap][Mp]
+  double *mean = nullptr, *dmean = nullptr;                        // [NVcap][Bp]
+  double *var0ss = nullptr, *varq = nullptr, *dfvar = nullptr;     // [Q|P][Bp]
+  int NVcap = 0;
+  int *d_lta_latent = nullptr, *d_lta_group = nullptr, *d_latent_group = nullptr;
+  // host-entry staging
+  double *stage_dev = nullptr, *stage_host = nullptr, *out_dev = nullptr, *out_host_pinned = nullptr;
+  size_t stage_cap = 0;
+  // NCCL (dlopen'ed)
+  void* nccl_lib = nullptr;
+  void* nccl_comm = nullptr;
+  std::string err;
+};
+
+#define H_FAIL(h, code, ...)              \
+  do {                                    \
+    char _b[512];                         \
+    snprintf(_b, sizeof(_b), __VA_ARGS__); \
+    (h)->err = _b;                        \
+    return code;                          \
+  } while (0)
+
+#define H_CUDA(h, expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) H_FAIL(h, MOGPE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+  return cudaMalloc((void**)p, n * sizeof(T));
+}
+
+extern "C" const char* mogpe_version(void) { return "mogpe_b200 0.1 (sm_100a, fp64 DMMA)"; }
+
+extern "C" const char* mogpe_last_error(const mogpe_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static void free_ws(mogpe_handle* h) {
+  double** ptrs[] = {&h->Kuu, &h->L, &h->Linv, &h->Lbar, &h->T1, &h->T2, &h->Kuf, &h->A, &h->Abar, &h->W,
+                     &h->LTA, &h->Sc, &h->V, &h->dV, &h->mean, &h->dmean, &h->var0ss, &h->varq, &h->dfvar,
+                     &h->stage_dev, &h->out_dev};
+  for (auto p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  if (h->d_md) cudaFree(h->d_md);
+  if (h->d_lta_latent) cudaFree(h->d_lta_latent);
+  if (h->d_lta_group) cudaFree(h->d_lta_group);
+  if (h->d_latent_group) cudaFree(h->d_latent_group);
+  if (h->stage_host) cudaFreeHost(h->stage_host);
+  if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
+}
+
+extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
+  if (!d || !out) {
+    g_create_error = "null argument";
+    return MOGPE_ERR_INVALID;
+  }
+  auto bad = [&](const char* m) {
+    g_create_error = m;
+    return MOGPE_ERR_INVALID;
+  };
+  if (d->input_dim < 1 || d->input_dim > 16) return bad("input_dim must be in [1, 16]");
+  if (d->output_dim < 1) return bad("output_dim must be >= 1");
+  if (d->num_experts < 2) return bad("num_experts must be >= 2");
+  if (!(d->num_gating == 1 && d->num_experts == 2) && d->num_gating != d->num_experts)
+    return bad("num_gating must be 1 (Bernoulli, K = 2) or equal to num_experts (Softmax)");
+  if (d->num_latents != d->num_experts * d->output_dim + d->num_gating) return bad("num_latents != K*F + G");
+  if (d->num_latents > MAXP || d->num_groups > MAXQ || d->num_groups < 1) return bad("too many latents / groups");
+  if (d->max_batch < 1) return bad("max_batch must be >= 1");
+  if (!d->group_num_inducing || !d->latent_group) return bad("null group_num_inducing / latent_group");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count <= d->device) {
+    g_create_error = "no CUDA device " + std::to_string(d->device) + " (this library has no CPU fallback)";
+    return MOGPE_ERR_CUDA;
+  }
+  auto* h = new mogpe_handle();
+  h->desc = *d;
+  h->device = d->device;
+  h->group_M.assign(d->group_num_inducing, d->group_num_inducing + d->num_groups);
+  h->latent_group.assign(d->latent_group, d->latent_group + d->num_latents);
+  h->desc.group_num_inducing = h->group_M.data();
+  h->desc.latent_group = h->latent_group.data();
+  int Mmax = 0;
+  for (int g = 0; g < d->num_groups; g++) {
+    if (h->group_M[g] < 1) {
+      delete h;
+      return bad("group_num_inducing must be >= 1");
+    }
+    Mmax = std::max(Mmax, h->group_M[g]);
+  }
+  for (int l = 0; l < d->num_latents; l++)
+    if (h->latent_group[l] < 0 || h->latent_group[l] >= d->num_groups) {
+      delete h;
+      return bad("latent_group out of range");
+    }
+  h->Mp = round_up(Mmax, 64);
+  h->Bp = round_up(d->max_batch, 128);
+  h->Pe = d->num_experts * d->output_dim;
+  const long long Q = d->num_groups, P = d->num_latents, Mp = h->Mp, D = d->input_dim;
+  Layout& lo = h->lo;
+  lo.ls = 0;
+  lo.kvar = lo.ls + Q * D;
+  lo.Z = lo.kvar + Q;
+  lo.q_mu = lo.Z + Q * Mp * D;
+  lo.q_sqrt = lo.q_mu + P * Mp;
+  // keep the big matrices 16-byte aligned for vector access
+  if (lo.q_sqrt % 2) lo.q_sqrt++;
+  lo.mean_c = lo.q_sqrt + P * Mp * Mp;
+  lo.noise = lo.mean_c + P;
+  lo.total = lo.noise + h->Pe;
+
+  ModelDev& md = h->md_host;
+  memset(&md, 0, sizeof(md));
+  md.D = d->input_dim;
+  md.F = d->output_dim;
+  md.K = d->num_experts;
+  md.G = d->num_gating;
+  md.Q = d->num_groups;
+  md.P = d->num_latents;
+  md.Pe = h->Pe;
+  md.Mp = h->Mp;
+  md.flavour = d->flavour;
+  for (int g = 0; g < md.Q; g++) md.group_M[g] = h->group_M[g];
+  for (int l = 0; l < md.P; l++) md.latent_group[l] = h->latent_group[l];
+
+  cudaError_t e = cudaSetDevice(h->device);
+  const size_t mm = (size_t)Q * Mp * Mp, mb = (size_t)Q * Mp * h->Bp;
+  if (e == cudaSuccess) e = dalloc(&h->d_md, 1);
+  if (e == cudaSuccess) e = dalloc(&h->Kuu, mm);
+  if (e == cudaSuccess) e = dalloc(&h->L, mm);
+  if (e == cudaSuccess) e = dalloc(&h->Linv, mm);
+  if (e == cudaSuccess) e = dalloc(&h->Lbar, mm);
+  if (e == cudaSuccess) e = dalloc(&h->T1, mm);
+  if (e == cudaSuccess) e = dalloc(&h->T2, mm);
+  if (e == cudaSuccess) e = dalloc(&h->Kuf, mb);
+  if (e == cudaSuccess) e = dalloc(&h->A, mb);
+  if (e == cudaSuccess) e = dalloc(&h->Abar, mb);
+  if (e == cudaSuccess) e = dalloc(&h->W, mb);
+  if (e == cudaSuccess) e = dalloc(&h->LTA, (size_t)P * Mp * h->Bp);
+  if (e == cudaSuccess) e = dalloc(&h->Sc, (size_t)P * Mp * Mp);
+  if (e == cudaSuccess) e = dalloc(&h->var0ss, (size_t)Q * h->Bp);
+  if (e == cudaSuccess) e = dalloc(&h->varq, (size_t)P * h->Bp);
+  if (e == cudaSuccess) e = dalloc(&h->dfvar, (size_t)P * h->Bp);
+  if (e == cudaSuccess) e = dalloc(&h->d_lta_latent, (size_t)MAXP);
+  if (e == cudaSuccess) e = dalloc(&h->d_lta_group, (size_t)MAXP);
+  if (e == cudaSuccess) e = dalloc(&h->d_latent_group, (size_t)MAXP);
+  if (e == cudaSuccess) e = dalloc(&h->out_dev, 8);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->out_host_pinned, 8 * sizeof(double));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->d_latent_group, md.latent_group, sizeof(int) * MAXP, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->varq, 0, (size_t)P * h->Bp * sizeof(double));
+  if (e == cudaSuccess && 8 * Mp * sizeof(double) > 48 * 1024)
+    e = cudaFuncSetAttribute(a_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * Mp * sizeof(double)));
+  if (e != cudaSuccess) {
+    g_create_error = std::string("workspace allocation failed: ") + cudaGetErrorString(e);
+    free_ws(h);
+    delete h;
+    return MOGPE_ERR_CUDA;
+  }
+  *out = h;
+  return MOGPE_OK;
+}
+
+extern "C" void mogpe_destroy(mogpe_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->nccl_comm && h->nccl_lib) {
+    typedef int (*destroy_t)(void*);
+    auto fn = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");
+    if (fn) fn(h->nccl_comm);
+  }
+  free_ws(h);
+  delete h;
+}
+
+extern "C" mogpe_status mogpe_param_layout(const mogpe_handle* h, mogpe_layout* out) {
+  if (!h || !out) return MOGPE_ERR_INVALID;
+  out->lengthscales = h->lo.ls;
+  out->variance = h->lo.kvar;
+  out->Z = h->lo.Z;
+  out->q_mu = h->lo.q_mu;
+  out->q_sqrt = h->lo.q_sqrt;
+  out->mean_c = h->lo.mean_c;
+  out->noise = h->lo.noise;
+  out->total = h->lo.total;
+  out->Mp = h->Mp;
+  out->reserved = 0;
+  return MOGPE_OK;
+}
+
+// ---- call-mode setup: which latents are inducing-sampled / marginal under (bound, S) -------------
+static mogpe_status set_mode(mogpe_handle* h, int bound, int S, cudaStream_t st) {
+  if (h->cur_bound == bound && h->cur_S == S) return MOGPE_OK;
+  ModelDev& md = h->md_host;
+  md.S = S;
+  md.bound = bound;
+  int nv = 0, nlta = 0;
+  for (int l = 0; l < md.P; l++) {
+    const bool expert = l < md.Pe;
+    bool inducing;
+    if (bound == MOGPE_BOUND_FURTHER_GATING) inducing = expert;
+    else if (bound == MOGPE_BOUND_TIGHT) inducing = true;
+    else inducing = false;  // further, predict (-1)
+    md.R[l] = inducing ? S : 1;
+    md.marg[l] = inducing ? 0 : 1;
+    md.voff[l] = nv;
+    for (int r = 0; r < md.R[l]; r++) md.vec_latent[nv + r] = l;
+    nv += md.R[l];
+    md.lta_slot[l] = -1;
+    if (md.marg[l]) {
+      md.lta_slot[l] = nlta;
+      md.lta_latent[nlta] = l;
+      md.lta_group[nlta] = md.latent_group[l];
+      nlta++;
+    }
+  }
+  md.NV = nv;
+  md.nlta = nlta;
+  int pos = 0, lp = 0;
+  for (int g = 0; g < md.Q; g++) {
+    md.gvec_begin[g] = pos;
+    md.glat_begin[g] = lp;
+    for (int l = 0; l < md.P; l++)
+      if (md.latent_group[l] == g) {
+        md.glat[lp++] = l;
+        for (int r = 0; r < md.R[l]; r++) md.gvec[pos++] = md.voff[l] + r;
+      }
+  }
+  md.gvec_begin[md.Q] = pos;
+  md.glat_begin[md.Q] = lp;
+  if (nv > h->NVcap) {
+    for (double** p : {&h->V, &h->dV, &h->mean, &h->dmean}) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
+    H_CUDA(h, dalloc(&h->V, (size_t)nv * h->Mp));
+    H_CUDA(h, dalloc(&h->dV, (size_t)nv * h->Mp));
+    H_CUDA(h, dalloc(&h->mean, (size_t)nv * h->Bp));
+    H_CUDA(h, dalloc(&h->dmean, (size_t)nv * h->Bp));
+    h->NVcap = nv;
+  }
+  // synchronous small uploads (mode changes are rare: once per (bound, S))
+  H_CUDA(h, cudaStreamSynchronize(st));
+  H_CUDA(h, cudaMemcpy(h->d_md, &md, sizeof(ModelDev), cudaMemcpyHostToDevice));
+  H_CUDA(h, cudaMemcpy(h->d_lta_latent, md.lta_latent, sizeof(int) * MAXP, cudaMemcpyHostToDevice));
+  H_CUDA(h, cudaMemcpy(h->d_lta_group, md.lta_group, sizeof(int) * MAXP, cudaMemcpyHostToDevice));
+  h->cur_bound = bound;
+  h->cur_S = S;
+  return MOGPE_OK;
+}
+
+static GemmParams gp_init() {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.alpha = 1.0;
+  return p;
+}
+
+// Kuu -> L -> Linv for every group, and the clean q_sqrt copies.
+static mogpe_status factorise(mogpe_handle* h, const double* params, cudaStream_t st) {
+  const int Q = h->md_host.Q, P = h->md_host.P, Mp = h->Mp;
+  kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
+  for (int j = 0; j < Mp / 32; j++)
+    chol_step_kernel<<<dim3(Mp / 32 - j, Q), 256, 0, st>>>(h->Kuu, h->L, Mp, j);
+  trinv_kernel<<<dim3(Mp / 32, Q), 256, 0, st>>>(h->L, h->Linv, Mp);
+  prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->Sc);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+// Kuf, A = Linv Kuf, LTA_l = S_l^T A for marginal latents, for columns [0, Bp) of the current chunk.
+static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const double* X, int N, int Bc,
+                                    cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, Mp = h->Mp, D = md.D;
+  kuf_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, (32 * D + 32) * sizeof(double), st>>>(h->d_md, params, h->lo, X, N, h->Bp,
+                                                                                      h->Kuf);
+  H_CUDA(h, cudaGetLastError());
+  {
+    GemmParams p = gp_init();
+    p.A = h->Linv; p.sA = (long long)Mp * Mp; p.lda = Mp;
+    p.B = h->Kuf;  p.sB = (long long)Mp * h->Bp; p.ldb = h->Bp;
+    p.C = h->A;    p.sC = (long long)Mp * h->Bp; p.ldc = h->Bp;
+    p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_LOWER;
+    H_CUDA(h, launch_gemm(p, Q, false, false, st));
+  }
+  if (md.nlta > 0) {
+    GemmParams p = gp_init();
+    p.A = h->Sc;  p.sA = (long long)Mp * Mp; p.lda = Mp; p.mapA = h->d_lta_latent;
+    p.B = h->A;   p.sB = (long long)Mp * h->Bp; p.ldb = h->Bp; p.mapB = h->d_lta_group;
+    p.C = h->LTA; p.sC = (long long)Mp * h->Bp; p.ldc = h->Bp;
+    p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_UPPER;
+    H_CUDA(h, launch_gemm(p, md.nlta, true, false, st));
+    col_sumsq_kernel<<<dim3(Bc / 128, md.nlta), 128, 0, st>>>(h->d_md, h->LTA, h->Bp, h->varq);
+  }
+  a_stats_kernel<<<dim3(Bc / 128, Q), 128, 8 * Mp * sizeof(double), st>>>(h->d_md, params, h->lo, h->A, h->V, h->Bp,
+                                                                          h->var0ss, h->mean);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+static int lik_block(int slots) {
+  int b = 128;
+  while (b > 32 && (size_t)slots * b * sizeof(double) > 160 * 1024) b >>= 1;
+  return b;
+}
+
+extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, const double* Y, int32_t N,
+                                           const double* params, const double* eps_u, const double* eps_h,
+                                           const double* eps_f, int32_t bound, int32_t S, double scale, double* out,
+                                           double* grads, void* cuda_stream) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (!X || !Y || !params || !out) H_FAIL(h, MOGPE_ERR_INVALID, "null X / Y / params / out");
+  if (N < 1 || N > h->desc.max_batch) H_FAIL(h, MOGPE_ERR_INVALID, "N=%d outside [1, max_batch=%d]", N, h->desc.max_batch);
+  if (S < 1 || S > MOGPE_MAX_SAMPLES) H_FAIL(h, MOGPE_ERR_INVALID, "num_samples=%d outside [1, %d]", S, MOGPE_MAX_SAMPLES);
+  if (bound < 0 || bound > 2) H_FAIL(h, MOGPE_ERR_INVALID, "unknown bound id %d", bound);
+  const ModelDev& md = h->md_host;
+  if (bound == MOGPE_BOUND_TIGHT && md.G > 1)
+    H_FAIL(h, MOGPE_ERR_UNSUPPORTED,
+           "tight bound with Softmax gating needs the Monte-Carlo likelihood expectation (not implemented)");
+  if ((bound == MOGPE_BOUND_FURTHER_GATING || bound == MOGPE_BOUND_TIGHT) && !eps_u)
+    H_FAIL(h, MOGPE_ERR_INVALID, "eps_u is required for bound %d", bound);
+  if ((bound == MOGPE_BOUND_FURTHER_GATING || bound == MOGPE_BOUND_FURTHER) && !eps_h)
+    H_FAIL(h, MOGPE_ERR_INVALID, "eps_h is required for bound %d", bound);
+  if (bound == MOGPE_BOUND_FURTHER && !eps_f) H_FAIL(h, MOGPE_ERR_INVALID, "eps_f is required for the further bound");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  H_CUDA(h, cudaSetDevice(h->device));
+  mogpe_status rc = set_mode(h, bound, S, st);
+  if (rc != MOGPE_OK) return rc;
+  const int Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;  // Bp: leading dimension of every [.., n] buffer
+  const int Bc = round_up(N, 128);                       // columns in use this call
+  const Layout& lo = h->lo;
+
+  H_CUDA(h, cudaMemsetAsync(out, 0, 4 * sizeof(double), st));
+  if (grads) H_CUDA(h, cudaMemsetAsync(grads, 0, lo.total * sizeof(double), st));
+
+  // ---------------- forward ----------------
+  rc = factorise(h, params, st);
+  if (rc != MOGPE_OK) return rc;
+  make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, st>>>(h->d_md, params, lo, h->Sc, eps_u, S, h->V);
+  rc = conditional_fwd(h, params, X, N, Bc, st);
+  if (rc != MOGPE_OK) return rc;
+
+  LikArgs la;
+  la.md = h->d_md; la.params = params; la.lo = lo; la.mean = h->mean; la.var0ss = h->var0ss; la.varq = h->varq;
+  la.Y = Y; la.eps_h = eps_h; la.eps_f = eps_f; la.N = N; la.Bp = Bp; la.scale = scale;
+  la.dmean = h->dmean; la.dfvar = h->dfvar; la.out = out; la.grads = grads;
+  {
+    const int slots = 4 * S * md.K + md.Pe;
+    const int blk = lik_block(slots);
+    const size_t smem = (size_t)slots * blk * sizeof(double);
+    static size_t lik_smem_set = 0;
+    if (smem > lik_smem_set) {
+      H_CUDA(h, cudaFuncSetAttribute(lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+      lik_smem_set = smem;
+    }
+    lik_kernel<<<Bc / blk, blk, smem, st>>>(la);
+    H_CUDA(h, cudaGetLastError());
+  }
+  kl_kernel<<<P, 256, 0, st>>>(h->d_md, params, lo, out, grads);
+  finish_elbo_kernel<<<1, 1, 0, st>>>(out);
+  H_CUDA(h, cudaGetLastError());
+  if (!grads) return MOGPE_OK;
+
+  // ---------------- backward ----------------
+  // (a) q_sqrt gradient of marginal latents: Sbar_l = tril(A (2 LTA_l diag(dfvar_l))^T); scaling fused in the
+  //     epilogue via alpha and into the B operand... done as: Sbar_l = 2 * tril(A_g diag(dfvar_l) LTA_l^T)
+  //     => scale LTA in place first (it is also the B operand of Abar += S_l dLTA_l).
+  build_abar_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, 0, st>>>(h->d_md, h->A, h->V, h->dmean, h->dfvar, Bp, h->Abar);
+  dV_kernel<<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, h->A, h->dmean, Bp, Bc, h->dV);
+  H_CUDA(h, cudaGetLastError());
+  if (md.nlta > 0) {
+    // Abar[g(l)] += S_l (2 LTA_l diag(dfvar_l))   -- column scaling fused into the B-operand load
+    // latents of one group are accumulated one launch at a time (C is read-modify-write)
+    for (int slot = 0; slot < md.nlta; slot++) {
+      const int l = md.lta_latent[slot], g = md.latent_group[l];
+      GemmParams p = gp_init();
+      p.A = h->Sc + (long long)l * Mp * Mp; p.lda = Mp;
+      p.B = h->LTA + (long long)slot * Mp * Bp; p.ldb = Bp;
+      p.C = h->Abar + (long long)g * Mp * Bp; p.ldc = Bp;
+      p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_LOWER;
+      p.alpha = 2.0; p.beta = 1.0;
+      p.colscale = h->dfvar + (long long)l * Bp;
+      H_CUDA(h, launch_gemm(p, 1, false, false, st));
+    }
+  }
+  {  // W = Linv^T Abar  (= Kuf-bar)
+    GemmParams p = gp_init();
+    p.A = h->Linv; p.sA = (long long)Mp * Mp; p.lda = Mp;
+    p.B = h->Abar; p.sB = (long long)Mp * Bp; p.ldb = Bp;
+    p.C = h->W;    p.sC = (long long)Mp * Bp; p.ldc = Bp;
+    p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_UPPER;
+    H_CUDA(h, launch_gemm(p, Q, true, false, st));
+  }
+  {  // Lbar = -tril(W A^T)
+    GemmParams p = gp_init();
+    p.A = h->W; p.sA = (long long)Mp * Bp; p.lda = Bp;
+    p.B = h->A; p.sB = (long long)Mp * Bp; p.ldb = Bp;
+    p.C = h->Lbar; p.sC = (long long)Mp * Mp; p.ldc = Mp;
+    p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = -1.0;
+    H_CUDA(h, launch_gemm(p, Q, false, true, st));
+  }
+  if (md.nlta > 0) {
+    // Sbar_l = 2 tril(A_g diag(dfvar_l) LTA_l^T): scale LTA in place (column scaling), then NT GEMM
+    // (uses the TB = true path, so the scaling is applied by a tiny elementwise pass instead of colscale)
+    // -> fused: C = A_g * (LTA_l * diag)^T ; we pre-scale W-free buffer: reuse Kuf? Keep it simple: scale LTA.
+    scale_cols_kernel<<<dim3(Bc / 128, Mp / 32, md.nlta), 128, 0, st>>>(h->d_md, h->LTA, h->dfvar, Bp);
+    GemmParams p = gp_init();
+    p.A = h->A;   p.sA = (long long)Mp * Bp; p.lda = Bp; p.mapA = h->d_lta_group;
+    p.B = h->LTA; p.sB = (long long)Mp * Bp; p.ldb = Bp;
+    p.C = grads + lo.q_sqrt; p.sC = (long long)Mp * Mp; p.ldc = Mp; p.mapC = h->d_lta_latent;
+    p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = 2.0; p.beta = 1.0;
+    H_CUDA(h, launch_gemm(p, md.nlta, false, true, st));
+  }
+  q_grads_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, lo, h->dV, eps_u, S, grads);
+  // Cholesky backward: Phi = tril(L^T Lbar) with halved diagonal; Kb = Linv^T Phi Linv (symmetrised in kuu_grad)
+  {
+    GemmParams p = gp_init();
+    p.A = h->L; p.sA = (long long)Mp * Mp; p.lda = Mp;
+    p.B = h->Lbar; p.sB = (long long)Mp * Mp; p.ldb = Mp;
+    p.C = h->T1; p.sC = (long long)Mp * Mp; p.ldc = Mp;
+    p.M = Mp; p.N = Mp; p.K = Mp; p.kmode = KM_LEFT_UPPER | KM_RIGHT_LOWER; p.tril_out = 1;
+    H_CUDA(h, launch_gemm(p, Q, true, false, st));
+    // tril_out skips the strictly-upper tiles: clear them once (T1 upper tiles are never written)
+    halve_diag_kernel<<<Q, 256, 0, st>>>(h->T1, Mp);
+  }
+  {
+    GemmParams p = gp_init();
+    p.A = h->Linv; p.sA = (long long)Mp * Mp; p.lda = Mp;
+    p.B = h->T1; p.sB = (long long)Mp * Mp; p.ldb = Mp;
+    p.C = h->T2; p.sC = (long long)Mp * Mp; p.ldc = Mp;
+    p.M = Mp; p.N = Mp; p.K = Mp; p.kmode = KM_LEFT_UPPER | KM_RIGHT_LOWER;
+    H_CUDA(h, launch_gemm(p, Q, true, false, st));
+  }
+  {
+    GemmParams p = gp_init();
+    p.A = h->T2; p.sA = (long long)Mp * Mp; p.lda = Mp;
+    p.B = h->Linv; p.sB = (long long)Mp * Mp; p.ldb = Mp;
+    p.C = h->Lbar; p.sC = (long long)Mp * Mp; p.ldc = Mp;  // reuse Lbar as Kb
+    p.M = Mp; p.N = Mp; p.K = Mp; p.kmode = KM_RIGHT_LOWER;
+    H_CUDA(h, launch_gemm(p, Q, false, false, st));
+  }
+  kuu_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
+  kuf_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+
+static mogpe_status ensure_stage(mogpe_handle* h, size_t doubles) {
+  if (doubles <= h->stage_cap) return MOGPE_OK;
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  if (h->stage_host) cudaFreeHost(h->stage_host);
+  h->stage_dev = nullptr;
+  h->stage_host = nullptr;
+  H_CUDA(h, dalloc(&h->stage_dev, doubles));
+  H_CUDA(h, cudaMallocHost((void**)&h->stage_host, doubles * sizeof(double)));
+  h->stage_cap = doubles;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_elbo_fwd_bwd_host(mogpe_handle* h, const double* X_host, const double* Y_host, int32_t N,
+                                                const double* params, const double* eps_u_host,
+                                                const double* eps_h_host, const double* eps_f_host, int32_t bound,
+                                                int32_t S, double scale, double* out_host, double* grads,
+                                                void* cuda_stream) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (!X_host || !Y_host || !out_host) H_FAIL(h, MOGPE_ERR_INVALID, "null host X / Y / out");
+  if (N < 1 || N > h->desc.max_batch) H_FAIL(h, MOGPE_ERR_INVALID, "N=%d outside [1, max_batch=%d]", N, h->desc.max_batch);
+  if (S < 1 || S > MOGPE_MAX_SAMPLES) H_FAIL(h, MOGPE_ERR_INVALID, "num_samples=%d outside [1, %d]", S, MOGPE_MAX_SAMPLES);
+  const ModelDev& md = h->md_host;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  H_CUDA(h, cudaSetDevice(h->device));
+  const size_t nx = (size_t)N * md.D, ny = (size_t)N * md.F;
+  const size_t nu = eps_u_host ? (size_t)md.P * S * h->Mp : 0;
+  const size_t nh = eps_h_host ? (size_t)S * N * md.G : 0;
+  const size_t nf = eps_f_host ? (size_t)S * N * md.Pe : 0;
+  const size_t total = nx + ny + nu + nh + nf;
+  mogpe_status rc = ensure_stage(h, total);
+  if (rc != MOGPE_OK) return rc;
+  // one pinned staging buffer, one H2D copy
+  double* hp = h->stage_host;
+  size_t off = 0;
+  auto put = [&](const double* src, size_t n) {
+    if (n) memcpy(hp + off, src, n * sizeof(double));
+    const size_t o = off;
+    off += n;
+    return o;
+  };
+  const size_t ox = put(X_host, nx), oy = put(Y_host, ny), ou = put(eps_u_host, nu), oh = put(eps_h_host, nh),
+               of = put(eps_f_host, nf);
+  H_CUDA(h, cudaMemcpyAsync(h->stage_dev, hp, total * sizeof(double), cudaMemcpyHostToDevice, st));
+  const double* d = h->stage_dev;
+  rc = mogpe_elbo_fwd_bwd(h, d + ox, d + oy, N, params, nu ? d + ou : nullptr, nh ? d + oh : nullptr,
+                          nf ? d + of : nullptr, bound, S, scale, h->out_dev, grads, cuda_stream);
+  if (rc != MOGPE_OK) return rc;
+  H_CUDA(h, cudaMemcpyAsync(h->out_host_pinned, h->out_dev, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  H_CUDA(h, cudaStreamSynchronize(st));
+  memcpy(out_host, h->out_host_pinned, 4 * sizeof(double));
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const double* params,
+                                      double* f_mean, double* f_var, double* mix_probs, double* y_mean, double* y_var,
+                                      const double* eps_mc, int32_t num_mc, void* cuda_stream) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (!X || !params || N < 1) H_FAIL(h, MOGPE_ERR_INVALID, "null X / params or N < 1");
+  const ModelDev& md = h->md_host;
+  if (md.G > 1 && (mix_probs || y_mean || y_var) && (!eps_mc || num_mc < 1))
+    H_FAIL(h, MOGPE_ERR_INVALID,
+           "Softmax gating: mixing probabilities are a Monte-Carlo mean (gpflow Softmax.predict_mean_and_var); "
+           "pass eps_mc [num_mc, N, K]");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  H_CUDA(h, cudaSetDevice(h->device));
+  mogpe_status rc = set_mode(h, -1, 1, st);
+  if (rc != MOGPE_OK) return rc;
+  rc = factorise(h, params, st);
+  if (rc != MOGPE_OK) return rc;
+  const int Mp = h->Mp;
+  make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, st>>>(h->d_md, params, h->lo, h->Sc, nullptr, 1, h->V);
+  const int chunk_max = h->desc.max_batch;
+  for (int64_t n0 = 0; n0 < N; n0 += chunk_max) {
+    const int nc = (int)std::min<int64_t>(chunk_max, N - n0);
+    const int Bc = round_up(nc, 128);
+    rc = conditional_fwd(h, params, X + n0 * md.D, nc, Bc, st);
+    if (rc != MOGPE_OK) return rc;
+    PredArgs pa;
+    pa.md = h->d_md; pa.params = params; pa.lo = h->lo; pa.mean = h->mean; pa.var0ss = h->var0ss; pa.varq = h->varq;
+    pa.n0 = (int)n0; pa.nchunk = nc; pa.Bp = h->Bp; pa.Ntot = N; pa.eps_mc = eps_mc; pa.num_mc = num_mc;
+    pa.f_mean = f_mean; pa.f_var = f_var; pa.mix = mix_probs; pa.y_mean = y_mean; pa.y_var = y_var;
+    const int blk = 128;
+    predict_out_kernel<<<(nc + blk - 1) / blk, blk, (size_t)2 * md.K * blk * sizeof(double), st>>>(pa);
+    H_CUDA(h, cudaGetLastError());
+  }
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_fill_normal(mogpe_handle* h, double* dst, int64_t n, uint64_t seed, uint64_t offset,
+                                          void* cuda_stream) {
+  if (!h || !dst || n < 0) return MOGPE_ERR_INVALID;
+  if (offset % 2) H_FAIL(h, MOGPE_ERR_INVALID, "offset must be even (normals are generated in pairs)");
+  if (n == 0) return MOGPE_OK;
+  H_CUDA(h, cudaSetDevice(h->device));
+  const long long pairs = (n + 1) / 2;
+  fill_normal_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(dst, n, seed, offset);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+// ---- NCCL through dlopen (the library must load on boxes without NCCL) ---------------------------
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, char[128], int) = nullptr;  // ncclUniqueId passed by value (128 bytes)
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct UniqueId {
+  char internal[128];
+};
+NcclApi g_nccl;
+bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) {
+    err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+    return false;
+  }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.AllReduce || !dlsym(lib, "ncclCommInitRank")) {
+    err = "libnccl is missing ncclGetUniqueId / ncclCommInitRank / ncclAllReduce";
+    return false;
+  }
+  g_nccl.lib = lib;
+  return true;
+}
+}  // namespace
+
+extern "C" mogpe_status mogpe_nccl_unique_id(char out[128]) {
+  std::string err;
+  if (!out) return MOGPE_ERR_INVALID;
+  if (!load_nccl(err)) {
+    g_create_error = err;
+    return MOGPE_ERR_NCCL;
+  }
+  int rc = g_nccl.GetUniqueId(out);
+  if (rc != 0) {
+    g_create_error = std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return MOGPE_ERR_NCCL;
+  }
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int32_t rank, int32_t world) {
+  if (!h || !id) return MOGPE_ERR_INVALID;
+  std::string err;
+  if (!load_nccl(err)) H_FAIL(h, MOGPE_ERR_NCCL, "%s", err.c_str());
+  H_CUDA(h, cudaSetDevice(h->device));
+  typedef int (*init_t)(void**, int, UniqueId, int);
+  auto fn = (init_t)dlsym(g_nccl.lib, "ncclCommInitRank");
+  UniqueId uid;
+  memcpy(uid.internal, id, 128);
+  int rc = fn(&h->nccl_comm, world, uid, rank);
+  if (rc != 0) H_FAIL(h, MOGPE_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  h->nccl_lib = g_nccl.lib;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_t n, void* cuda_stream) {
+  if (!h || !buf || n < 0) return MOGPE_ERR_INVALID;
+  if (!h->nccl_comm) H_FAIL(h, MOGPE_ERR_NCCL, "mogpe_comm_init has not been called on this handle");
+  H_CUDA(h, cudaSetDevice(h->device));
+  // ncclFloat64 = 8, ncclSum = 0
+  int rc = g_nccl.AllReduce(buf, buf, (size_t)n, 8, 0, h->nccl_comm, (cudaStream_t)cuda_stream);
+  if (rc != 0) H_FAIL(h, MOGPE_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return MOGPE_OK;
+}
+
+// ---- memory helpers -------------------------------------------------------------------------------
+#define G_CUDA(expr)                                                    \
+  do {                                                                  \
+    cudaError_t _e = (expr);                                            \
+    if (_e != cudaSuccess) {                                            \
+      g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e); \
+      return MOGPE_ERR_CUDA;                                            \
+    }                                                                   \
+  } while (0)
+
+extern "C" mogpe_status mogpe_malloc(int32_t device, int64_t bytes, void** out) {
+  if (!out || bytes < 0) return MOGPE_ERR_INVALID;
+  G_CUDA(cudaSetDevice(device));
+  G_CUDA(cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 16)));
+  return MOGPE_OK;
+}
+extern "C" mogpe_status mogpe_free(int32_t device, void* p) {
+  if (!p) return MOGPE_OK;
+  G_CUDA(cudaSetDevice(device));
+  G_CUDA(cudaFree(p));
+  return MOGPE_OK;
+}
+extern "C" mogpe_status mogpe_malloc_host(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return MOGPE_ERR_INVALID;
+  G_CUDA(cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 16)));
+  return MOGPE_OK;
+}
+extern "C" mogpe_status mogpe_free_host(void* p) {
+  if (!p) return MOGPE_OK;
+  G_CUDA(cudaFreeHost(p));
+  return MOGPE_OK;
+}
+extern "C" mogpe_status mogpe_memcpy_h2d(int32_t device, void* dst, const void* src, int64_t bytes, void* st) {
+  G_CUDA(cudaSetDevice(device));
+  G_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)st));
+  return MOGPE_OK;
+}
+extern "C" mogpe_status mogpe_memcpy_d2h(int32_t device, void* dst, const void* src, int64_t bytes, void* st) {
+  G_CUDA(cudaSetDevice(device));
+  G_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)st));
+  G_CUDA(cudaStreamSynchronize((cudaStream_t)st));
+  return MOGPE_OK;
+}
+extern "C" mogpe_status mogpe_memset_zero(int32_t device, void* dst, int64_t bytes, void* st) {
+  G_CUDA(cudaSetDevice(device));
+  G_CUDA(cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)st));
+  return MOGPE_OK;
+}
+extern "C" mogpe_status mogpe_stream_sync(int32_t device, void* st) {
+  G_CUDA(cudaSetDevice(device));
+  G_CUDA(cudaStreamSynchronize((cudaStream_t)st));
+  return MOGPE_OK;
+}
+
+// ---- test hooks -----------------------------------------------------------------------------------
+extern "C" mogpe_status mogpe_debug_copy(mogpe_handle* h, const char* name, double* dst, int64_t cap, int64_t* n_out) {
+  if (!h || !name || !n_out) return MOGPE_ERR_INVALID;
+  const ModelDev& md = h->md_host;
+  const long long Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;
+  const double* src = nullptr;
+  long long n = 0;
+  std::string s(name);
+  if (s == "Kuu") src = h->Kuu, n = Q * Mp * Mp;
+  else if (s == "L") src = h->L, n = Q * Mp * Mp;
+  else if (s == "Linv") src = h->Linv, n = Q * Mp * Mp;
+  else if (s == "Kb") src = h->Lbar, n = Q * Mp * Mp;
+  else if (s == "T1") src = h->T1, n = Q * Mp * Mp;
+  else if (s == "T2") src = h->T2, n = Q * Mp * Mp;
+  else if (s == "Kuf") src = h->Kuf, n = Q * Mp * Bp;
+  else if (s == "A") src = h->A, n = Q * Mp * Bp;
+  else if (s == "Abar") src = h->Abar, n = Q * Mp * Bp;
+  else if (s == "W") src = h->W, n = Q * Mp * Bp;
+  else if (s == "LTA") src = h->LTA, n = (long long)md.nlta * Mp * Bp;
+  else if (s == "Sc") src = h->Sc, n = P * Mp * Mp;
+  else if (s == "V") src = h->V, n = (long long)md.NV * Mp;
+  else if (s == "dV") src = h->dV, n = (long long)md.NV * Mp;
+  else if (s == "mean") src = h->mean, n = (long long)md.NV * Bp;
+  else if (s == "dmean") src = h->dmean, n = (long long)md.NV * Bp;
+  else if (s == "var0ss") src = h->var0ss, n = Q * Bp;
+  else if (s == "varq") src = h->varq, n = P * Bp;
+  else if (s == "dfvar") src = h->dfvar, n = P * Bp;
+  else H_FAIL(h, MOGPE_ERR_INVALID, "unknown intermediate '%s'", name);
+  *n_out = n;
+  H_CUDA(h, cudaSetDevice(h->device));
+  H_CUDA(h, cudaDeviceSynchronize());
+  if (dst && cap > 0)
+    H_CUDA(h, cudaMemcpy(dst, src, (size_t)std::min<long long>(cap, n) * sizeof(double), cudaMemcpyDeviceToHost));
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_debug_gemm(int32_t device, const double* A, const double* B, double* C, int32_t batch,
+                                         int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,
+                                         int32_t kmode, int32_t tril_out, double alpha, double beta, void* st) {
+  G_CUDA(cudaSetDevice(device));
+  GemmParams p = gp_init();
+  p.A = A; p.sA = (long long)M * K; p.lda = transA ? M : K;
+  p.B = B; p.sB = (long long)K * N; p.ldb = transB ? K : N;
+  p.C = C; p.sC = (long long)M * N; p.ldc = N;
+  p.M = M; p.N = N; p.K = K; p.kmode = kmode; p.tril_out = tril_out; p.alpha = alpha; p.beta = beta;
+  G_CUDA(launch_gemm(p, batch, transA != 0, transB != 0, (cudaStream_t)st));
+  return MOGPE_OK;
+}

@@ -1,0 +1,248 @@
+// Batched FP64 GEMM on the sm_100a DMMA pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4).
+//
+// tcgen05.mma has no f64 kind, so the FP64 tensor path on B200 is the warp-level DMMA; measured issue
+// peak on this pool: 37.0 TFLOP/s (tools/fp64_probe.cu), cuBLAS DGEMM 35.4.
+//
+// C[M,N] = alpha * opA(A)[M,K] * opB(B)[K,N] + beta * C, all row-major in memory:
+//   TA == false: A(m,k) = A[m*lda + k]      TA == true: A(m,k) = A[k*lda + m]
+//   TB == false: B(k,n) = B[k*ldb + n]      TB == true: B(k,n) = B[n*ldb + k]
+// Tiles keep the orientation they have in memory, so every global read is a 16-byte cp.async along the
+// contiguous axis, and the row pitches (+4 doubles) make every DMMA fragment read bank-conflict free.
+// Triangular operands restrict the k range per tile (kmode) instead of multiplying zeros.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mogpe {
+
+enum : int { KM_LEFT_LOWER = 1, KM_LEFT_UPPER = 2, KM_RIGHT_LOWER = 4, KM_RIGHT_UPPER = 8 };
+
+struct GemmParams {
+  const double* A;
+  const double* B;
+  double* C;
+  long long sA, sB, sC;  // batch strides in elements
+  const int* mapA;       // optional batch -> index maps (device), nullptr = identity
+  const int* mapB;
+  const int* mapC;
+  int lda, ldb, ldc;
+  int M, N, K;
+  int kmode;
+  int tril_out;  // 1: only tiles with col0 <= row0 are produced; elements above the diagonal are zeroed
+  double alpha, beta;
+  // optional fused column scaling of the B operand: B(k,n) *= colscale[batch_map*scs + n]  (TB == false only)
+  const double* colscale;
+  long long scs;
+  const int* mapS;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+struct GemmCfg {
+  static constexpr int WARPS_M = BM / WM;
+  static constexpr int WARPS_N = BN / WN;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int MI = WM / 8;
+  static constexpr int NI = WN / 8;
+  // smem tile shapes follow the memory orientation
+  static constexpr int A_ROWS = TA ? BK : BM;
+  static constexpr int A_COLS = TA ? BM : BK;
+  static constexpr int A_LD = A_COLS + 4;
+  static constexpr int B_ROWS = TB ? BN : BK;
+  static constexpr int B_COLS = TB ? BK : BN;
+  static constexpr int B_LD = B_COLS + 4;
+  static constexpr int A_ELEMS = A_ROWS * A_LD;
+  static constexpr int B_ELEMS = B_ROWS * B_LD;
+  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
+};
+
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+__global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::THREADS)
+    gemm_dmma_kernel(const GemmParams p) {
+  using Cfg = GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>;
+  extern __shared__ __align__(16) double smem[];
+
+  const int batch = blockIdx.z;
+  // heavier (lower) row blocks first for lower-triangular left operands
+  const int brow = (p.kmode & KM_LEFT_LOWER) ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
+  const int bcol = blockIdx.x;
+  const int row0 = brow * BM, col0 = bcol * BN;
+  if (p.tril_out && col0 > row0 + BM - 1) {
+    // strictly-upper tile of a lower-triangular result: exact zeros (consumers read whole tiles)
+    if (p.beta == 0.0) {
+      double* Cz = p.C + (long long)(p.mapC ? p.mapC[batch] : batch) * p.sC;
+      for (int t = threadIdx.x; t < BM * BN; t += blockDim.x)
+        Cz[(long long)(row0 + t / BN) * p.ldc + col0 + (t % BN)] = 0.0;
+    }
+    return;
+  }
+
+  int k_begin = 0, k_end = p.K;
+  if (p.kmode & KM_LEFT_LOWER) k_end = min(k_end, row0 + BM);
+  if (p.kmode & KM_LEFT_UPPER) k_begin = max(k_begin, row0);
+  if (p.kmode & KM_RIGHT_LOWER) k_begin = max(k_begin, col0);
+  if (p.kmode & KM_RIGHT_UPPER) k_end = min(k_end, col0 + BN);
+  k_begin = (k_begin / BK) * BK;
+  const int nk = (k_end > k_begin) ? (k_end - k_begin + BK - 1) / BK : 0;
+
+  const double* __restrict__ Ab = p.A + (long long)(p.mapA ? p.mapA[batch] : batch) * p.sA;
+  const double* __restrict__ Bb = p.B + (long long)(p.mapB ? p.mapB[batch] : batch) * p.sB;
+  double* __restrict__ Cb = p.C + (long long)(p.mapC ? p.mapC[batch] : batch) * p.sC;
+  const double* __restrict__ Sb =
+      p.colscale ? p.colscale + (long long)(p.mapS ? p.mapS[batch] : batch) * p.scs : nullptr;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm0 = (warp / Cfg::WARPS_N) * WM;
+  const int wn0 = (warp % Cfg::WARPS_N) * WN;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; i++)
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto load_stage = [&](int stage, int kt) {
+    double* As = smem + stage * Cfg::STAGE_ELEMS;
+    double* Bs = As + Cfg::A_ELEMS;
+    const int k0 = k_begin + kt * BK;
+    // A tile: A_ROWS x A_COLS doubles, 2 doubles per cp.async
+    constexpr int A_CH = Cfg::A_COLS / 2;
+    for (int c = tid; c < Cfg::A_ROWS * A_CH; c += Cfg::THREADS) {
+      const int r = c / A_CH, cc = (c % A_CH) * 2;
+      const double* g = TA ? (Ab + (long long)(k0 + r) * p.lda + row0 + cc)
+                           : (Ab + (long long)(row0 + r) * p.lda + k0 + cc);
+      cp_async16(As + r * Cfg::A_LD + cc, g);
+    }
+    constexpr int B_CH = Cfg::B_COLS / 2;
+    for (int c = tid; c < Cfg::B_ROWS * B_CH; c += Cfg::THREADS) {
+      const int r = c / B_CH, cc = (c % B_CH) * 2;
+      const double* g = TB ? (Bb + (long long)(col0 + r) * p.ldb + k0 + cc)
+                           : (Bb + (long long)(k0 + r) * p.ldb + col0 + cc);
+      cp_async16(Bs + r * Cfg::B_LD + cc, g);
+    }
+  };
+
+  // per-thread column scales for its NI fragment columns (fused dLTA = 2 * LTA * dvar scaling)
+  double cs[Cfg::NI];
+#pragma unroll
+  for (int j = 0; j < Cfg::NI; j++) cs[j] = 1.0;
+  if (Sb) {
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; j++) cs[j] = TB ? 1.0 : Sb[col0 + wn0 + j * 8 + lr];
+  }
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nk) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < nk; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = kt + STAGES - 1;
+      if (nxt < nk) load_stage(nxt % STAGES, nxt);
+      cp_async_commit();
+    }
+    const double* As = smem + (kt % STAGES) * Cfg::STAGE_ELEMS;
+    const double* Bs = As + Cfg::A_ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; kk++) {
+      double af[Cfg::MI], bf[Cfg::NI];
+      const int k = kk * 4 + lc;
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; i++) {
+        const int m = wm0 + i * 8 + lr;
+        af[i] = TA ? As[k * Cfg::A_LD + m] : As[m * Cfg::A_LD + k];
+      }
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; j++) {
+        const int n = wn0 + j * 8 + lr;
+        bf[j] = (TB ? Bs[n * Cfg::B_LD + k] : Bs[k * Cfg::B_LD + n]) * cs[j];
+      }
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; i++)
+#pragma unroll
+        for (int j = 0; j < Cfg::NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: thread owns (row = lr, cols = 2*lc, 2*lc+1) of each 8x8 fragment
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; i++) {
+    const int r = row0 + wm0 + i * 8 + lr;
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; j++) {
+      const int c = col0 + wn0 + j * 8 + lc * 2;
+      double2* dst = reinterpret_cast<double2*>(Cb + (long long)r * p.ldc + c);
+      double2 v;
+      v.x = p.alpha * acc[i][j][0];
+      v.y = p.alpha * acc[i][j][1];
+      if (p.beta != 0.0) {
+        const double2 o = *dst;
+        v.x += p.beta * o.x;
+        v.y += p.beta * o.y;
+      }
+      if (p.tril_out) {
+        if (c > r) v.x = 0.0;
+        if (c + 1 > r) v.y = 0.0;
+      }
+      *dst = v;
+    }
+  }
+}
+
+// ---- host-side dispatch ------------------------------------------------------------------------
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+inline cudaError_t launch_gemm_cfg(const GemmParams& p, int batch, cudaStream_t st) {
+  using Cfg = GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>;
+  auto kern = gemm_dmma_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(p.N / BN, p.M / BM, batch);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <bool TA, bool TB>
+inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st) {
+  // large tile when the problem fills the machine with 128x128 tiles, else 64x64
+  const bool big = (p.M % 128 == 0) && (p.N % 128 == 0) &&
+                   ((long long)(p.M / 128) * (p.N / 128) * batch >= 296 || p.tril_out == 0 && p.N >= 2048);
+  if (big) return launch_gemm_cfg<128, 128, 16, 64, 32, TA, TB, 3>(p, batch, st);
+  return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 4>(p, batch, st);
+}
+
+inline cudaError_t launch_gemm(const GemmParams& p, int batch, bool ta, bool tb, cudaStream_t st) {
+  if (p.M % 64 || p.N % 64 || p.K % 16) return cudaErrorInvalidValue;
+  if (!ta && !tb) return launch_gemm_t<false, false>(p, batch, st);
+  if (ta && !tb) return launch_gemm_t<true, false>(p, batch, st);
+  if (!ta && tb) return launch_gemm_t<false, true>(p, batch, st);
+  return launch_gemm_t<true, true>(p, batch, st);
+}
+
+}  // namespace mogpe

@@ -1,0 +1,586 @@
+// Kernel matrices, factorisation, streaming reductions and gradient kernels (FP64).
+// Every kernel is batched over the Q kernel groups / P latent GPs of the model.
+#pragma once
+#include "model_dev.cuh"
+
+namespace mogpe {
+
+// ------------------------------------------------------------------------------------------------
+// SquaredExponential Kuu (+ jitter), padded with the identity.
+// Expanded squared-distance form |z/l|^2 + |z'/l|^2 - 2 (z/l).(z'/l) as gpflow's square_distance.
+// grid (Mp/16, Mp/16, Q), block (16,16)
+// ------------------------------------------------------------------------------------------------
+__global__ void kuu_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
+                           double jitter, double* __restrict__ Kuu) {
+  const int g = blockIdx.z, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+  const double* ls = params + lo.ls + (long long)g * D;
+  const double* Z = params + lo.Z + (long long)g * Mp * D;
+  double v;
+  if (i < Mg && j < Mg) {
+    double si = 0, sj = 0, dot = 0;
+    for (int d = 0; d < D; d++) {
+      const double a = Z[i * D + d] / ls[d], b = Z[j * D + d] / ls[d];
+      si += a * a;
+      sj += b * b;
+      dot += a * b;
+    }
+    const double r2 = -2.0 * dot + (si + sj);
+    v = params[lo.kvar + g] * exp(-0.5 * r2);
+    if (i == j) v += jitter;
+  } else {
+    v = (i == j) ? 1.0 : 0.0;
+  }
+  Kuu[((long long)g * Mp + i) * Mp + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kuf[g][m][n] = k(z_m, x_n); zero for padded rows / columns.  X streamed coalesced, Z staged in smem.
+// grid (Bp/128, Mp/32, Q), block 128.  Dynamic smem: 32*(D+1) doubles.
+// ------------------------------------------------------------------------------------------------
+__global__ void kuf_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
+                           const double* __restrict__ X, int N, int Bp, double* __restrict__ Kuf) {
+  extern __shared__ double zs[];  // [32][D] scaled Z rows, then [32] squared norms
+  const int g = blockIdx.z, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
+  const int m0 = blockIdx.y * 32;
+  const double* ls = params + lo.ls + (long long)g * D;
+  const double* Z = params + lo.Z + (long long)g * Mp * D;
+  double* zn = zs + 32 * D;
+  for (int t = threadIdx.x; t < 32 * D; t += blockDim.x) {
+    const int r = t / D, d = t % D;
+    zs[t] = (m0 + r < Mg) ? Z[(m0 + r) * D + d] / ls[d] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = 0;
+    for (int d = 0; d < D; d++) s += zs[threadIdx.x * D + d] * zs[threadIdx.x * D + d];
+    zn[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const double kv = params[lo.kvar + g];
+  double xs[8];
+  double xn = 0;
+  const bool valid = n < N;
+  // D <= 8 fast path keeps x in registers; larger D re-reads X (L1-resident)
+  if (D <= 8) {
+    for (int d = 0; d < D; d++) {
+      xs[d] = valid ? X[(long long)n * D + d] / ls[d] : 0.0;
+      xn += xs[d] * xs[d];
+    }
+  } else {
+    for (int d = 0; d < D; d++) {
+      const double a = valid ? X[(long long)n * D + d] / ls[d] : 0.0;
+      xn += a * a;
+    }
+  }
+  double* out = Kuf + ((long long)g * Mp + m0) * Bp + n;
+  for (int r = 0; r < 32; r++) {
+    double v = 0.0;
+    if (valid && m0 + r < Mg) {
+      double dot = 0;
+      if (D <= 8) {
+        for (int d = 0; d < D; d++) dot += zs[r * D + d] * xs[d];
+      } else {
+        for (int d = 0; d < D; d++) dot += zs[r * D + d] * (X[(long long)n * D + d] / ls[d]);
+      }
+      const double r2 = -2.0 * dot + (zn[r] + xn);
+      v = kv * exp(-0.5 * r2);
+    }
+    out[(long long)r * Bp] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked left-looking Cholesky, one launch per 32-wide block column j.
+// CTA (i - j, g) produces L[i-block, j-block]; every CTA recomputes the (cheap) diagonal factor.
+// Reads Kuu, writes L (separate buffers: no read/write race on the diagonal block).
+// grid (Mp/32 - j, Q), block 256.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chol_step_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
+                                                         int Mp, int j) {
+  __shared__ double Li[32][33], Lj[32][33], Dg[32][33], Cg[32][33];
+  const int g = blockIdx.y, i = j + blockIdx.x;
+  const double* Kg = Kuu + (long long)g * Mp * Mp;
+  double* Lg = L + (long long)g * Mp * Mp;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double accC[2][2] = {{0, 0}, {0, 0}}, accD[2][2] = {{0, 0}, {0, 0}};
+  for (int kc = 0; kc < j; kc++) {
+    for (int t = tid; t < 1024; t += 256) {
+      const int r = t >> 5, c = t & 31;
+      Li[r][c] = Lg[(long long)(i * 32 + r) * Mp + kc * 32 + c];
+      Lj[r][c] = Lg[(long long)(j * 32 + r) * Mp + kc * 32 + c];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) {
+      const double a0 = Li[ty * 2][k], a1 = Li[ty * 2 + 1][k];
+      const double d0 = Lj[ty * 2][k], d1 = Lj[ty * 2 + 1][k];
+      const double b0 = Lj[tx * 2][k], b1 = Lj[tx * 2 + 1][k];
+      accC[0][0] += a0 * b0; accC[0][1] += a0 * b1; accC[1][0] += a1 * b0; accC[1][1] += a1 * b1;
+      accD[0][0] += d0 * b0; accD[0][1] += d0 * b1; accD[1][0] += d1 * b0; accD[1][1] += d1 * b1;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int r = ty * 2 + a, c = tx * 2 + b;
+      Dg[r][c] = Kg[(long long)(j * 32 + r) * Mp + j * 32 + c] - accD[a][b];
+      Cg[r][c] = Kg[(long long)(i * 32 + r) * Mp + j * 32 + c] - accC[a][b];
+    }
+  __syncthreads();
+  if (tid < 32) {  // unblocked factorisation of the 32x32 diagonal block by one warp
+    const int lane = tid;
+    for (int c = 0; c < 32; c++) {
+      const double d = sqrt(Dg[c][c]);
+      __syncwarp();
+      if (lane == c) Dg[c][c] = d;
+      if (lane > c) Dg[lane][c] /= d;
+      __syncwarp();
+      if (lane > c) {
+        const double lc = Dg[lane][c];
+        for (int cc = c + 1; cc <= lane; cc++) Dg[lane][cc] -= lc * Dg[cc][c];
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (i == j) {
+    for (int t = tid; t < 1024; t += 256) {
+      const int r = t >> 5, c = t & 31;
+      Lg[(long long)(j * 32 + r) * Mp + j * 32 + c] = (c <= r) ? Dg[r][c] : 0.0;
+    }
+  } else {
+    if (tid < 32) {  // X * Ljj^T = C, one row per thread
+      const int r = tid;
+      for (int c = 0; c < 32; c++) {
+        double s = Cg[r][c];
+        for (int t = 0; t < c; t++) s -= Cg[r][t] * Dg[c][t];
+        Cg[r][c] = s / Dg[c][c];
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < 1024; t += 256) {
+      const int r = t >> 5, c = t & 31;
+      Lg[(long long)(i * 32 + r) * Mp + j * 32 + c] = Cg[r][c];
+      Lg[(long long)(j * 32 + r) * Mp + i * 32 + c] = 0.0;  // mirrored upper block
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Linv = L^-1 by block columns: X[j,j] = Ljj^-1, X[i,j] = -Lii^-1 sum_{k=j}^{i-1} L[i,k] X[k,j].
+// grid (Mp/32, Q), block 256.  The explicit inverse turns every later solve into a DMMA GEMM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trinv_kernel(const double* __restrict__ L, double* __restrict__ Linv, int Mp) {
+  __shared__ double Lb[32][33], Xb[32][33], Rb[32][33], Ld[32][33];
+  const int g = blockIdx.y, j = blockIdx.x, nb = Mp / 32;
+  const double* Lg = L + (long long)g * Mp * Mp;
+  double* Xg = Linv + (long long)g * Mp * Mp;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int i = 0; i < j; i++)  // zero blocks above the diagonal
+    for (int t = tid; t < 1024; t += 256) Xg[(long long)(i * 32 + (t >> 5)) * Mp + j * 32 + (t & 31)] = 0.0;
+  for (int i = j; i < nb; i++) {
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    for (int k = j; k < i; k++) {
+      for (int t = tid; t < 1024; t += 256) {
+        const int r = t >> 5, c = t & 31;
+        Lb[r][c] = Lg[(long long)(i * 32 + r) * Mp + k * 32 + c];
+        Xb[r][c] = Xg[(long long)(k * 32 + r) * Mp + j * 32 + c];
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < 32; kk++) {
+        const double a0 = Lb[ty * 2][kk], a1 = Lb[ty * 2 + 1][kk];
+        const double b0 = Xb[kk][tx * 2], b1 = Xb[kk][tx * 2 + 1];
+        acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+      }
+      __syncthreads();
+    }
+    for (int t = tid; t < 1024; t += 256) {
+      const int r = t >> 5, c = t & 31;
+      Ld[r][c] = Lg[(long long)(i * 32 + r) * Mp + i * 32 + c];
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int r = ty * 2 + a, c = tx * 2 + b;
+        Rb[r][c] = (i == j) ? ((r == c) ? 1.0 : 0.0) : -acc[a][b];
+      }
+    __syncthreads();
+    if (tid < 32) {  // forward substitution Lii y = Rb[:, c], one column per thread
+      const int c = tid;
+      for (int r = 0; r < 32; r++) {
+        double s = Rb[r][c];
+        for (int t = 0; t < r; t++) s -= Ld[r][t] * Rb[t][c];
+        Rb[r][c] = s / Ld[r][r];
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < 1024; t += 256) {
+      const int r = t >> 5, c = t & 31;
+      Xg[(long long)(i * 32 + r) * Mp + j * 32 + c] = Rb[r][c];
+    }
+    __syncthreads();  // X[i,j] visible to this CTA's later block products
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Clean, padded lower-triangular copy of q_sqrt (GEMM operands must hold exact zeros above the diagonal)
+// grid (Mp/16, Mp/16, P), block (16,16)
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_qsqrt_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
+                                  double* __restrict__ Sc) {
+  const int l = blockIdx.z, Mp = md->Mp, Mg = md->group_M[md->latent_group[l]];
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+  const long long idx = ((long long)l * Mp + i) * Mp + j;
+  Sc[idx] = (i < Mg && j <= i) ? params[lo.q_sqrt + idx] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mean vectors: V[v][m] = q_mu[l][m] (+ sum_{k<=m} S_l[m][k] eps_u[l][r][k] for inducing-sampled latents)
+// (TFP MultivariateNormalTriL.sample, mogpe/keras/gps.py:20-29).  One warp per (vector, row m).
+// grid (Mp/8, NV), block 256
+// ------------------------------------------------------------------------------------------------
+__global__ void make_V_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
+                              const double* __restrict__ Sc, const double* __restrict__ eps_u, int S,
+                              double* __restrict__ V) {
+  const int v = blockIdx.y, Mp = md->Mp;
+  const int l = md->vec_latent[v], r = v - md->voff[l];
+  const int Mg = md->group_M[md->latent_group[l]];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  double s = 0.0;
+  const bool sampled = (md->R[l] == S) && !md->marg[l] && eps_u != nullptr;
+  if (m < Mg && sampled) {
+    const double* row = Sc + ((long long)l * Mp + m) * Mp;
+    const double* e = eps_u + ((long long)l * S + r) * Mp;
+    for (int k = lane; k <= m; k += 32) s += row[k] * e[k];
+  }
+  s = warp_sum(s);
+  if (lane == 0) V[(long long)v * Mp + m] = (m < Mg) ? params[lo.q_mu + (long long)l * Mp + m] + s : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One streaming pass over A[g] ([Mp, Bp], n contiguous): column sums of squares and the means
+// mean[v][n] = sum_m A[m][n] V[v][m] + c_l for up to 8 vectors of the group per pass (warp-free: one
+// column per thread, coalesced across the warp).
+// grid (Bp/128, Q), block 128, dynamic smem 8*Mp doubles
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) a_stats_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                      Layout lo, const double* __restrict__ A,
+                                                      const double* __restrict__ V, int Bp,
+                                                      double* __restrict__ var0ss, double* __restrict__ mean) {
+  extern __shared__ double vs[];  // [8][Mp]
+  const int g = blockIdx.y, Mp = md->Mp;
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const double* Ag = A + (long long)g * Mp * Bp + n;
+  const int vb = md->gvec_begin[g], ve = md->gvec_begin[g + 1];
+  bool first = true;
+  for (int v0 = vb; v0 < ve || first; v0 += 8) {
+    const int nv = min(8, ve - v0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nv * Mp; t += 128) vs[t] = V[(long long)md->gvec[v0 + t / Mp] * Mp + (t % Mp)];
+    __syncthreads();
+    double ss = 0, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < Mp; m++) {
+      const double a = Ag[(long long)m * Bp];
+      ss += a * a;
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (q < nv) acc[q] += a * vs[q * Mp + m];
+    }
+    if (first) var0ss[(long long)g * Bp + n] = ss;
+    for (int q = 0; q < nv; q++) {
+      const int v = md->gvec[v0 + q];
+      mean[(long long)v * Bp + n] = acc[q] + params[lo.mean_c + md->vec_latent[v]];
+    }
+    first = false;
+  }
+}
+
+// varq[l][n] = sum_m LTA[slot][m][n]^2.   grid (Bp/128, nlta), block 128
+__global__ void __launch_bounds__(128) col_sumsq_kernel(const ModelDev* __restrict__ md, const double* __restrict__ LTA,
+                                                        int Bp, double* __restrict__ varq) {
+  const int slot = blockIdx.y, Mp = md->Mp, l = md->lta_latent[slot];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const double* p = LTA + (long long)slot * Mp * Bp + n;
+  double ss = 0;
+  for (int m = 0; m < Mp; m++) {
+    const double a = p[(long long)m * Bp];
+    ss += a * a;
+  }
+  varq[(long long)l * Bp + n] = ss;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KL terms (Appendix A.5, whitened gauss_kl) and their gradients w.r.t. q_mu, q_sqrt.
+// One CTA per latent.  out[2] += KL of gating latents, out[3] += KL of expert latents.
+// grad convention: gradient of the ELBO (= data term - KL).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kl_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                 Layout lo, double* __restrict__ out, double* __restrict__ grads) {
+  __shared__ double red[8];
+  const int l = blockIdx.x, Mp = md->Mp, Mg = md->group_M[md->latent_group[l]];
+  const double* qm = params + lo.q_mu + (long long)l * Mp;
+  const double* S = params + lo.q_sqrt + (long long)l * Mp * Mp;
+  double acc = 0;
+  for (int m = threadIdx.x; m < Mg; m += 256) {
+    acc += qm[m] * qm[m] - 1.0 - log(S[(long long)m * Mp + m] * S[(long long)m * Mp + m]);
+    if (grads) grads[lo.q_mu + (long long)l * Mp + m] -= qm[m];
+  }
+  for (long long t = threadIdx.x; t < (long long)Mg * Mg; t += 256) {
+    const int i = t / Mg, j = t % Mg;
+    if (j <= i) {
+      const double s = S[(long long)i * Mp + j];
+      acc += s * s;
+      if (grads) grads[lo.q_sqrt + ((long long)l * Mp + i) * Mp + j] -= (i == j) ? (s - 1.0 / s) : s;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < 8; w++) s += red[w];
+    atomicAdd(out + (l >= md->Pe ? 2 : 3), 0.5 * s);
+  }
+}
+
+__global__ void finish_elbo_kernel(double* out) { out[0] = out[1] - out[2] - out[3]; }
+
+// ------------------------------------------------------------------------------------------------
+// Backward: Abar[g][m][n] = -2 A[m][n] sum_{l in g} dfvar[l][n] + sum_{v in g} V[v][m] dmean[v][n]
+// grid (Bp/128, Mp/32, Q), block 128
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) build_abar_kernel(const ModelDev* __restrict__ md, const double* __restrict__ A,
+                                                         const double* __restrict__ V,
+                                                         const double* __restrict__ dmean,
+                                                         const double* __restrict__ dfvar, int Bp,
+                                                         double* __restrict__ Abar) {
+  __shared__ double vs[32 * 33];
+  const int g = blockIdx.z, Mp = md->Mp, m0 = blockIdx.y * 32;
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  double dv = 0;
+  for (int q = md->glat_begin[g]; q < md->glat_begin[g + 1]; q++) dv += dfvar[(long long)md->glat[q] * Bp + n];
+  double acc[32];
+  const double* Ag = A + ((long long)g * Mp + m0) * Bp + n;
+#pragma unroll
+  for (int r = 0; r < 32; r++) acc[r] = -2.0 * dv * Ag[(long long)r * Bp];
+  const int vb = md->gvec_begin[g], ve = md->gvec_begin[g + 1];
+  for (int v0 = vb; v0 < ve; v0 += 32) {
+    const int nv = min(32, ve - v0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nv * 32; t += 128) {
+      const int q = t / 32, r = t % 32;
+      vs[q * 33 + r] = V[(long long)md->gvec[v0 + q] * Mp + m0 + r];
+    }
+    __syncthreads();
+    for (int q = 0; q < nv; q++) {
+      const double dm = dmean[(long long)md->gvec[v0 + q] * Bp + n];
+#pragma unroll
+      for (int r = 0; r < 32; r++) acc[r] += vs[q * 33 + r] * dm;
+    }
+  }
+  double* out = Abar + ((long long)g * Mp + m0) * Bp + n;
+#pragma unroll
+  for (int r = 0; r < 32; r++) out[(long long)r * Bp] = acc[r];
+}
+
+// dV[v][m] = sum_n A[g][m][n] dmean[v][n].  One warp per row m, up to 8 vectors per pass.
+// grid (Mp/8, Q), block 256
+__global__ void __launch_bounds__(256) dV_kernel(const ModelDev* __restrict__ md, const double* __restrict__ A,
+                                                 const double* __restrict__ dmean, int Bp, int Bc, double* __restrict__ dV) {
+  const int g = blockIdx.y, Mp = md->Mp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  const double* row = A + ((long long)g * Mp + m) * Bp;
+  const int vb = md->gvec_begin[g], ve = md->gvec_begin[g + 1];
+  for (int v0 = vb; v0 < ve; v0 += 8) {
+    const int nv = min(8, ve - v0);
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int n = lane; n < Bc; n += 32) {
+      const double a = row[n];
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (q < nv) acc[q] += a * dmean[(long long)md->gvec[v0 + q] * Bp + n];
+    }
+    for (int q = 0; q < nv; q++) {
+      const double s = warp_sum(acc[q]);
+      if (lane == 0) dV[(long long)md->gvec[v0 + q] * Mp + m] = s;
+    }
+  }
+}
+
+// grads.q_mu[l][m] += sum_r dV[v(l,r)][m];  grads.q_sqrt[l][m][k] += sum_s dV[v(l,s)][m] eps_u[l][s][k] (k <= m)
+// for inducing-sampled latents.   grid (Mp/16, Mp/16, P), block (16,16)
+__global__ void q_grads_kernel(const ModelDev* __restrict__ md, Layout lo, const double* __restrict__ dV,
+                               const double* __restrict__ eps_u, int S, double* __restrict__ grads) {
+  const int l = blockIdx.z, Mp = md->Mp, Mg = md->group_M[md->latent_group[l]];
+  const int m = blockIdx.y * 16 + threadIdx.y, k = blockIdx.x * 16 + threadIdx.x;
+  if (m >= Mg || k > m) return;
+  const int R = md->R[l], v0 = md->voff[l];
+  if (k == 0) {
+    double s = 0;
+    for (int r = 0; r < R; r++) s += dV[(long long)(v0 + r) * Mp + m];
+    grads[lo.q_mu + (long long)l * Mp + m] += s;
+  }
+  if (!md->marg[l] && eps_u != nullptr) {
+    double s = 0;
+    for (int r = 0; r < R; r++) s += dV[(long long)(v0 + r) * Mp + m] * eps_u[((long long)l * S + r) * Mp + k];
+    grads[lo.q_sqrt + ((long long)l * Mp + m) * Mp + k] += s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel-hyperparameter and Z gradients from Kuf-bar (= W): E = W .* Kuf,
+//   dZ[m,d]  = -sum_n E (z_md - x_nd) / l_d^2 ;  dl_d = sum_mn E (z_md - x_nd)^2 / l_d^3 ; dvar = sum E / var
+// One warp per row m (coalesced over n).  grid (Mp/8, Q), block 256.  D <= 16.
+// ------------------------------------------------------------------------------------------------
+template <int DMAX>
+__global__ void __launch_bounds__(256) kuf_grad_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                       Layout lo, const double* __restrict__ X, int N, int Bp,
+                                                       const double* __restrict__ W, const double* __restrict__ Kuf,
+                                                       double* __restrict__ grads) {
+  const int g = blockIdx.y, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= Mg) return;
+  const double* ls = params + lo.ls + (long long)g * D;
+  const double* z = params + lo.Z + ((long long)g * Mp + m) * D;
+  const double* w = W + ((long long)g * Mp + m) * Bp;
+  const double* kf = Kuf + ((long long)g * Mp + m) * Bp;
+  double zz[DMAX], a1[DMAX], a2[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) {
+    zz[d] = d < D ? z[d] : 0.0;
+    a1[d] = a2[d] = 0.0;
+  }
+  double se = 0;
+  for (int n = lane; n < N; n += 32) {
+    const double e = w[n] * kf[n];
+    se += e;
+#pragma unroll
+    for (int d = 0; d < DMAX; d++)
+      if (d < D) {
+        const double df = zz[d] - X[(long long)n * D + d];
+        a1[d] += e * df;
+        a2[d] += e * df * df;
+      }
+  }
+  se = warp_sum(se);
+  if (lane == 0) atomicAdd(grads + lo.kvar + g, se / params[lo.kvar + g]);
+#pragma unroll
+  for (int d = 0; d < DMAX; d++)
+    if (d < D) {
+      const double s1 = warp_sum(a1[d]), s2 = warp_sum(a2[d]);
+      if (lane == 0) {
+        const double l = ls[d];
+        atomicAdd(grads + lo.Z + ((long long)g * Mp + m) * D + d, -s1 / (l * l));
+        atomicAdd(grads + lo.ls + (long long)g * D + d, s2 / (l * l * l));
+      }
+    }
+}
+
+// Same for Kuu with the symmetrised Kuu-bar = (Kb + Kb^T)/2 (Kb = L^-T Phi L^-1 from the Cholesky
+// backward).  Both triangles of Kuu depend on Z, so row m collects the (m, m') and (m', m) terms.
+template <int DMAX>
+__global__ void __launch_bounds__(256) kuu_grad_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                       Layout lo, double jitter, const double* __restrict__ Kb,
+                                                       const double* __restrict__ Kuu, double* __restrict__ grads) {
+  const int g = blockIdx.y, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= Mg) return;
+  const double* ls = params + lo.ls + (long long)g * D;
+  const double* Zg = params + lo.Z + (long long)g * Mp * D;
+  const double* kb = Kb + (long long)g * Mp * Mp;
+  const double* ku = Kuu + (long long)g * Mp * Mp;
+  double zz[DMAX], a1[DMAX], a2[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) {
+    zz[d] = d < D ? Zg[m * D + d] : 0.0;
+    a1[d] = a2[d] = 0.0;
+  }
+  double se = 0;
+  for (int j = lane; j < Mg; j += 32) {
+    const double kbs = 0.5 * (kb[(long long)m * Mp + j] + kb[(long long)j * Mp + m]);
+    const double kv = ku[(long long)m * Mp + j] - (j == m ? jitter : 0.0);
+    const double e = kbs * kv;
+    se += e;
+#pragma unroll
+    for (int d = 0; d < DMAX; d++)
+      if (d < D) {
+        const double df = zz[d] - Zg[j * D + d];
+        a1[d] += e * df;
+        a2[d] += e * df * df;
+      }
+  }
+  se = warp_sum(se);
+  if (lane == 0) atomicAdd(grads + lo.kvar + g, se / params[lo.kvar + g]);
+#pragma unroll
+  for (int d = 0; d < DMAX; d++)
+    if (d < D) {
+      const double s1 = warp_sum(a1[d]), s2 = warp_sum(a2[d]);
+      if (lane == 0) {
+        const double l = ls[d];
+        atomicAdd(grads + lo.Z + ((long long)g * Mp + m) * D + d, -2.0 * s1 / (l * l));
+        atomicAdd(grads + lo.ls + (long long)g * D + d, s2 / (l * l * l));
+      }
+    }
+}
+
+// LTA[slot][m][n] *= dfvar[lta_latent[slot]][n].   grid (Bp/128, Mp/32, nlta), block 128
+__global__ void scale_cols_kernel(const ModelDev* md, double* LTA, const double* dfvar, int Bp) {
+  const int slot = blockIdx.z, Mp = md->Mp, l = md->lta_latent[slot];
+  const int n = blockIdx.x * 128 + threadIdx.x, m0 = blockIdx.y * 32;
+  const double s = dfvar[(long long)l * Bp + n];
+  double* p = LTA + ((long long)slot * Mp + m0) * Bp + n;
+#pragma unroll 8
+  for (int r = 0; r < 32; r++) p[(long long)r * Bp] *= s;
+}
+
+// Phi: halve the diagonal of a (already lower-triangular) matrix batch.  grid (Q), block 256
+__global__ void halve_diag_kernel(double* __restrict__ P, int Mp) {
+  double* p = P + (long long)blockIdx.x * Mp * Mp;
+  for (int i = threadIdx.x; i < Mp; i += blockDim.x) p[(long long)i * Mp + i] *= 0.5;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller standard normals (counter-based: element i depends only on seed, offset+i)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__global__ void fill_normal_kernel(double* __restrict__ dst, long long n, unsigned long long seed,
+                                   unsigned long long offset) {
+  const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = pair * 2;
+  if (i >= n) return;
+  const unsigned long long ctr = offset / 2 + pair;
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x6d6f6770u, 0x65623230u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  // two 53-bit uniforms in (0, 1]
+  const double u1 = ((double)(((unsigned long long)c[0] << 21) ^ (c[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(((unsigned long long)c[2] << 21) ^ (c[3] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(u1));
+  double s, co;
+  sincospi(2.0 * u2, &s, &co);
+  dst[i] = rad * co;
+  if (i + 1 < n) dst[i + 1] = rad * s;
+}
+
+}  // namespace mogpe

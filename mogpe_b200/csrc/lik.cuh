@@ -1,0 +1,445 @@
+// Fused gating / expert-likelihood / mixture log-sum pass: one thread per data point computes the
+// per-point variational expectation AND its adjoints w.r.t. every latent mean / variance in one sweep.
+//
+// Reference semantics:
+//   further_gating: experts via inducing samples (variance without q_sqrt), gating via marginal h samples
+//   tight:          gating also via inducing samples + analytic Bernoulli expectation
+//   further:        experts and gating via marginal samples; density scale = noise variance
+// The reference evaluates log(sum_k p_k pi_k) in probability space; this kernel evaluates the same
+// quantity in log space (log-sum-exp), equal to rounding wherever the reference is finite (quirk 6).
+#pragma once
+#include "model_dev.cuh"
+
+namespace mogpe {
+
+#define MOGPE_LOG_2PI 1.8378770664093454835606594728112
+#define MOGPE_INV_SQRT2 0.70710678118654752440084436210485
+#define MOGPE_INV_SQRT_2PI 0.39894228040143267793994605993438
+
+// gpflow.likelihoods.utils.inv_probit with its 1e-3 jitter (quirk 3)
+__device__ __forceinline__ double inv_probit(double x) {
+  return 0.5 * (1.0 + erf(x * MOGPE_INV_SQRT2)) * (1.0 - 2e-3) + 1e-3;
+}
+__device__ __forceinline__ double inv_probit_grad(double x) {
+  return (1.0 - 2e-3) * MOGPE_INV_SQRT_2PI * exp(-0.5 * x * x);
+}
+
+struct LikArgs {
+  const ModelDev* md;
+  const double* params;
+  Layout lo;
+  const double* mean;    // [NV][Bp]
+  const double* var0ss;  // [Q][Bp]
+  const double* varq;    // [P][Bp]
+  const double* Y;       // [N][F]
+  const double* eps_h;   // [S][N][G]
+  const double* eps_f;   // [S][N][Pe]
+  int N, Bp;
+  double scale;
+  double* dmean;  // [NV][Bp]
+  double* dfvar;  // [P][Bp]
+  double* out;    // out[1] += scaled data term
+  double* grads;  // nullable
+};
+
+// per-thread scratch in shared memory, laid out [slot][thread] (conflict-free)
+struct Scratch {
+  double* base;
+  int stride;
+  __device__ __forceinline__ double& operator()(int slot) const { return base[slot * stride]; }
+};
+
+// Gating log-probabilities for sample s -> lpi[k] (K entries), marginal-sample mode.
+// Also used in backward to recompute pi.
+__device__ __forceinline__ void gating_forward_sample(const ModelDev* md, const LikArgs& a, int n, int s, bool valid,
+                                                      const Scratch& lpi, int lpi0) {
+  const int G = md->G, K = md->K, Pe = md->Pe;
+  const bool keras = md->flavour == MOGPE_FLAVOUR_KERAS;
+  if (G == 1) {
+    const int l = Pe, g = md->latent_group[l];
+    double hm = 0, hv = 1, e = 0;
+    if (valid) {
+      hm = a.mean[(long long)md->voff[l] * a.Bp + n];
+      hv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n] + a.varq[(long long)l * a.Bp + n];
+      e = a.eps_h[((long long)s * a.N + n)];
+    }
+    const double sd = keras ? sqrt(hv) : hv;
+    const double h = hm + sd * e;
+    const double p0 = inv_probit(h);
+    const double p1 = keras ? inv_probit(-h) : 1.0 - p0;
+    lpi(lpi0 + 0) = log(p0);
+    lpi(lpi0 + 1) = log(p1);
+  } else {
+    double mx = -1e300;
+    for (int k = 0; k < K; k++) {
+      const int l = Pe + k, g = md->latent_group[l];
+      double h = 0;
+      if (valid) {
+        const double hm = a.mean[(long long)md->voff[l] * a.Bp + n];
+        const double hv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n] + a.varq[(long long)l * a.Bp + n];
+        const double sd = keras ? sqrt(hv) : hv;
+        h = hm + sd * a.eps_h[((long long)s * a.N + n) * G + k];
+      }
+      lpi(lpi0 + k) = h;
+      mx = fmax(mx, h);
+    }
+    double se = 0;
+    for (int k = 0; k < K; k++) se += exp(lpi(lpi0 + k) - mx);
+    const double lse = mx + log(se);
+    for (int k = 0; k < K; k++) lpi(lpi0 + k) -= lse;
+  }
+}
+
+// Backward of gating_forward_sample given dlpi[k] (adjoints of log pi_k for sample s).
+__device__ __forceinline__ void gating_backward_sample(const ModelDev* md, const LikArgs& a, int n, int s,
+                                                       const Scratch& lpi, int lpi0, const Scratch& dlpi, int d0) {
+  const int G = md->G, K = md->K, Pe = md->Pe;
+  const bool keras = md->flavour == MOGPE_FLAVOUR_KERAS;
+  if (G == 1) {
+    const int l = Pe, g = md->latent_group[l];
+    const double hm = a.mean[(long long)md->voff[l] * a.Bp + n];
+    const double hv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n] + a.varq[(long long)l * a.Bp + n];
+    const double e = a.eps_h[((long long)s * a.N + n)];
+    const double sd = keras ? sqrt(hv) : hv;
+    const double h = hm + sd * e;
+    const double gp = inv_probit_grad(h);
+    const double p0 = exp(lpi(lpi0 + 0)), p1 = exp(lpi(lpi0 + 1));
+    const double dh = dlpi(d0 + 0) * gp / p0 - dlpi(d0 + 1) * gp / p1;
+    a.dmean[(long long)md->voff[l] * a.Bp + n] += dh;
+    a.dfvar[(long long)l * a.Bp + n] += dh * e * (keras ? 0.5 / sd : 1.0);
+  } else {
+    double sd_all = 0;
+    for (int k = 0; k < K; k++) sd_all += dlpi(d0 + k);
+    for (int k = 0; k < K; k++) {
+      const int l = Pe + k, g = md->latent_group[l];
+      const double hv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n] + a.varq[(long long)l * a.Bp + n];
+      const double sd = keras ? sqrt(hv) : hv;
+      const double e = a.eps_h[((long long)s * a.N + n) * G + k];
+      const double dh = dlpi(d0 + k) - exp(lpi(lpi0 + k)) * sd_all;
+      a.dmean[(long long)md->voff[l] * a.Bp + n] += dh;
+      a.dfvar[(long long)l * a.Bp + n] += dh * e * (keras ? 0.5 / sd : 1.0);
+    }
+  }
+}
+
+// grid (Bp/blockDim), dynamic smem = (4*S*K + K*F)*blockDim doubles.  Threads n >= N write zero adjoints
+// (the padded columns feed the B-long GEMMs of the backward pass).
+__global__ void lik_kernel(const LikArgs a) {
+  extern __shared__ double sm[];
+  const ModelDev* md = a.md;
+  const int S = md->S, K = md->K, F = md->F, G = md->G, Pe = md->Pe, P = md->P;
+  const int bound = md->bound;
+  const bool keras = md->flavour == MOGPE_FLAVOUR_KERAS;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = n < a.N;
+  const int SK = S * K;
+  Scratch lp{sm + threadIdx.x, (int)blockDim.x};  // slots: [0,SK) lp, [SK,2SK) lpi, [2SK,3SK) dlp, [3SK,4SK) dlpi
+  const int LP = 0, LPI = SK, DLP = 2 * SK, DLPI = 3 * SK, DN = 4 * SK;  // DN: Pe noise-gradient slots
+  const bool want = a.grads != nullptr;
+
+  // zero this column's adjoints
+  for (int v = 0; v < md->NV; v++) a.dmean[(long long)v * a.Bp + n] = 0.0;
+  for (int l = 0; l < P; l++) a.dfvar[(long long)l * a.Bp + n] = 0.0;
+
+  double val = 0.0;
+  const double w_sample = a.scale;
+
+  if (bound == MOGPE_BOUND_FURTHER && !keras) {
+    // ---- legacy "further" (mogpe/mixture_of_experts/svgp.py:232-330): per-output mixture log_prob, one
+    // sample index shared by gating and experts; f, h sampled with scale = variance (quirk 2).
+    const double w = w_sample / S;
+    for (int s = 0; s < S; s++) {
+      gating_forward_sample(md, a, n, s, valid, lp, LPI);
+      for (int k = 0; k < K; k++) lp(DLPI + k) = 0.0;
+      for (int f = 0; f < F; f++) {
+        double mx = -1e300;
+        for (int k = 0; k < K; k++) {
+          const int l = k * F + f, g = md->latent_group[l];
+          double ln = 0;
+          if (valid) {
+            const double fm = a.mean[(long long)md->voff[l] * a.Bp + n];
+            const double fv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n] + a.varq[(long long)l * a.Bp + n];
+            const double fs = fm + fv * a.eps_f[((long long)s * a.N + n) * Pe + l];
+            const double sc = a.params[a.lo.noise + l];
+            const double z = (a.Y[(long long)n * F + f] - fs) / sc;
+            ln = -0.5 * z * z - log(sc) - 0.5 * MOGPE_LOG_2PI;
+          }
+          lp(LP + k) = ln + lp(LPI + k);
+          mx = fmax(mx, lp(LP + k));
+        }
+        double se = 0;
+        for (int k = 0; k < K; k++) se += exp(lp(LP + k) - mx);
+        const double lse = mx + log(se);
+        if (valid) val += w * lse;
+        if (want && valid) {
+          for (int k = 0; k < K; k++) {
+            const int l = k * F + f, g = md->latent_group[l];
+            const double r = w * exp(lp(LP + k) - lse);
+            const double fm = a.mean[(long long)md->voff[l] * a.Bp + n];
+            const double fv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n] + a.varq[(long long)l * a.Bp + n];
+            const double e = a.eps_f[((long long)s * a.N + n) * Pe + l];
+            const double fs = fm + fv * e;
+            const double sc = a.params[a.lo.noise + l];
+            const double z = (a.Y[(long long)n * F + f] - fs) / sc;
+            const double dmu = r * z / sc;
+            a.dmean[(long long)md->voff[l] * a.Bp + n] += dmu;
+            a.dfvar[(long long)l * a.Bp + n] += dmu * e;
+            lp(DN + l) = (s == 0 ? 0.0 : lp(DN + l)) + r * (z * z - 1.0) / sc;  // dnoise
+            lp(DLPI + k) += r;
+          }
+        }
+      }
+      if (want && valid) gating_backward_sample(md, a, n, s, lp, LPI, lp, DLPI);
+    }
+    if (want) {
+      for (int l = 0; l < Pe; l++) {
+        const double s = warp_sum(valid ? lp(DN + l) : 0.0);
+        if ((threadIdx.x & 31) == 0) atomicAdd(a.grads + a.lo.noise + l, s);
+      }
+    }
+  } else {
+    // ---- S x S structure: log sum_k p_k[s1] pi_k[s2], mean over (s1, s2)
+    // 1. expert log densities lp[s][k]
+    for (int s = 0; s < S; s++)
+      for (int k = 0; k < K; k++) {
+        double acc = 0;
+        if (valid)
+          for (int f = 0; f < F; f++) {
+            const int l = k * F + f, g = md->latent_group[l];
+            const double fvar0 = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n];
+            double mu, sc;
+            if (bound != MOGPE_BOUND_FURTHER) {
+              mu = a.mean[(long long)(md->voff[l] + s) * a.Bp + n];
+              const double yv = fvar0 + a.params[a.lo.noise + l];
+              sc = keras ? yv : sqrt(yv);  // quirk 1
+            } else {  // keras further: f_s = mean + sqrt(var) eps, scale = noise variance
+              const double fv = fvar0 + a.varq[(long long)l * a.Bp + n];
+              mu = a.mean[(long long)md->voff[l] * a.Bp + n] + sqrt(fv) * a.eps_f[((long long)s * a.N + n) * Pe + l];
+              sc = a.params[a.lo.noise + l];
+            }
+            const double z = (a.Y[(long long)n * F + f] - mu) / sc;
+            acc += -0.5 * z * z - log(sc) - 0.5 * MOGPE_LOG_2PI;
+          }
+        lp(LP + s * K + k) = acc;
+        lp(DLP + s * K + k) = 0.0;
+        lp(DLPI + s * K + k) = 0.0;
+      }
+    // 2. gating log probabilities lpi[s][k]
+    if (bound == MOGPE_BOUND_TIGHT) {
+      // inducing-sampled gating + analytic Bernoulli expectation (keras/gating_networks.py:159-171,243-244)
+      const int l = Pe, g = md->latent_group[l];
+      for (int s = 0; s < S; s++) {
+        double t = 0;
+        if (valid) {
+          const double hm = a.mean[(long long)(md->voff[l] + s) * a.Bp + n];
+          const double hv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n];
+          t = hm / sqrt(1.0 + hv);
+        }
+        const double p0 = inv_probit(t);
+        const double p1 = keras ? inv_probit(-t) : 1.0 - p0;
+        lp(LPI + s * K + 0) = log(p0);
+        lp(LPI + s * K + 1) = log(p1);
+      }
+    } else {
+      for (int s = 0; s < S; s++) gating_forward_sample(md, a, n, s, valid, lp, LPI + s * K);
+    }
+    // 3. marginalise the indicator, average samples
+    const double w = w_sample / ((double)S * S);
+    for (int s1 = 0; s1 < S; s1++)
+      for (int s2 = 0; s2 < S; s2++) {
+        double mx = -1e300;
+        for (int k = 0; k < K; k++) mx = fmax(mx, lp(LP + s1 * K + k) + lp(LPI + s2 * K + k));
+        double se = 0;
+        for (int k = 0; k < K; k++) se += exp(lp(LP + s1 * K + k) + lp(LPI + s2 * K + k) - mx);
+        const double lse = mx + log(se);
+        if (valid) val += w * lse;
+        if (want)
+          for (int k = 0; k < K; k++) {
+            const double r = w * exp(lp(LP + s1 * K + k) + lp(LPI + s2 * K + k) - lse);
+            lp(DLP + s1 * K + k) += r;
+            lp(DLPI + s2 * K + k) += r;
+          }
+      }
+    // 4. backward through the expert densities
+    if (want) {
+      for (int k = 0; k < K; k++)
+        for (int f = 0; f < F; f++) {
+          const int l = k * F + f, g = md->latent_group[l];
+          double dnoise = 0;
+          if (valid) {
+            const double fvar0 = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n];
+            const double y = a.Y[(long long)n * F + f];
+            if (bound != MOGPE_BOUND_FURTHER) {
+              const double yv = fvar0 + a.params[a.lo.noise + l];
+              const double sc = keras ? yv : sqrt(yv);
+              double dyv = 0;
+              for (int s = 0; s < S; s++) {
+                const double mu = a.mean[(long long)(md->voff[l] + s) * a.Bp + n];
+                const double z = (y - mu) / sc;
+                const double d = lp(DLP + s * K + k);
+                a.dmean[(long long)(md->voff[l] + s) * a.Bp + n] += d * z / sc;
+                dyv += d * (z * z - 1.0) / sc * (keras ? 1.0 : 0.5 / sc);
+              }
+              a.dfvar[(long long)l * a.Bp + n] += dyv;
+              dnoise = dyv;
+            } else {
+              const double fv = fvar0 + a.varq[(long long)l * a.Bp + n];
+              const double sf = sqrt(fv), sc = a.params[a.lo.noise + l];
+              const double fm = a.mean[(long long)md->voff[l] * a.Bp + n];
+              double dfm = 0, dfv = 0;
+              for (int s = 0; s < S; s++) {
+                const double e = a.eps_f[((long long)s * a.N + n) * Pe + l];
+                const double z = (y - (fm + sf * e)) / sc;
+                const double d = lp(DLP + s * K + k);
+                const double dmu = d * z / sc;
+                dfm += dmu;
+                dfv += dmu * e * 0.5 / sf;
+                dnoise += d * (z * z - 1.0) / sc;
+              }
+              a.dmean[(long long)md->voff[l] * a.Bp + n] += dfm;
+              a.dfvar[(long long)l * a.Bp + n] += dfv;
+            }
+          }
+          dnoise = warp_sum(dnoise);
+          if ((threadIdx.x & 31) == 0) atomicAdd(a.grads + a.lo.noise + l, dnoise);
+        }
+      // 5. backward through the gating
+      if (valid) {
+        if (bound == MOGPE_BOUND_TIGHT) {
+          const int l = Pe, g = md->latent_group[l];
+          const double hv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n];
+          const double rs = rsqrt(1.0 + hv);
+          double dhv = 0;
+          for (int s = 0; s < S; s++) {
+            const double hm = a.mean[(long long)(md->voff[l] + s) * a.Bp + n];
+            const double t = hm * rs;
+            const double gp = inv_probit_grad(t);
+            const double p0 = exp(lp(LPI + s * K + 0)), p1 = exp(lp(LPI + s * K + 1));
+            const double dt = lp(DLPI + s * K + 0) * gp / p0 - lp(DLPI + s * K + 1) * gp / p1;
+            a.dmean[(long long)(md->voff[l] + s) * a.Bp + n] += dt * rs;
+            dhv += dt * (-0.5) * hm * rs * rs * rs;
+          }
+          a.dfvar[(long long)l * a.Bp + n] += dhv;
+        } else {
+          for (int s = 0; s < S; s++) gating_backward_sample(md, a, n, s, lp, LPI + s * K, lp, DLPI + s * K);
+        }
+      }
+    }
+  }
+
+  // data term
+  val = warp_sum(val);
+  if ((threadIdx.x & 31) == 0) atomicAdd(a.out + 1, val);
+
+  // mean-function constants and kernel variance (through k(x,x) = variance) gradients
+  if (want) {
+    for (int l = 0; l < P; l++) {
+      double dc = 0;
+      for (int r = 0; r < md->R[l]; r++) dc += a.dmean[(long long)(md->voff[l] + r) * a.Bp + n];
+      dc = warp_sum(dc);
+      const double dk = warp_sum(a.dfvar[(long long)l * a.Bp + n]);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(a.grads + a.lo.mean_c + l, dc);
+        atomicAdd(a.grads + a.lo.kvar + md->latent_group[l], dk);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prediction outputs (Appendix A.6-A.7).  One thread per test point.
+// ------------------------------------------------------------------------------------------------
+struct PredArgs {
+  const ModelDev* md;
+  const double* params;
+  Layout lo;
+  const double* mean;    // [P][Bp]  (R = 1 for every latent)
+  const double* var0ss;  // [Q][Bp]
+  const double* varq;    // [P][Bp]
+  int n0, nchunk, Bp;
+  long long Ntot;
+  const double* eps_mc;  // [R][Ntot][K] or null
+  int num_mc;
+  double* f_mean;  // [Ntot][P] or null
+  double* f_var;
+  double* mix;     // [Ntot][K] or null
+  double* y_mean;  // [Ntot][F] or null
+  double* y_var;
+};
+
+__global__ void predict_out_kernel(const PredArgs a) {
+  extern __shared__ double sm[];
+  const ModelDev* md = a.md;
+  const int K = md->K, F = md->F, G = md->G, Pe = md->Pe, P = md->P;
+  const bool keras = md->flavour == MOGPE_FLAVOUR_KERAS;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nchunk) return;
+  const long long n = (long long)a.n0 + i;
+  Scratch pi{sm + threadIdx.x, (int)blockDim.x};  // K slots: mixing probs; K more: softmax scratch
+  auto fmean = [&](int l) { return a.mean[(long long)md->voff[l] * a.Bp + i]; };
+  auto fvar = [&](int l) {
+    const int g = md->latent_group[l];
+    return a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + i] + a.varq[(long long)l * a.Bp + i];
+  };
+  if (a.f_mean)
+    for (int l = 0; l < P; l++) a.f_mean[n * P + l] = fmean(l);
+  if (a.f_var)
+    for (int l = 0; l < P; l++) a.f_var[n * P + l] = fvar(l);
+  if (!a.mix && !a.y_mean && !a.y_var) return;
+  if (G == 1) {
+    const double t = fmean(Pe) / sqrt(1.0 + fvar(Pe));
+    const double p0 = inv_probit(t);
+    pi(0) = p0;
+    pi(1) = keras ? inv_probit(-t) : 1.0 - p0;
+  } else {
+    // gpflow Softmax.predict_mean_and_var: Monte-Carlo mean of softmax(mu + sqrt(v) eps) over num_mc draws
+    for (int k = 0; k < K; k++) pi(k) = 0.0;
+    for (int r = 0; r < a.num_mc; r++) {
+      double mx = -1e300;
+      for (int k = 0; k < K; k++) {
+        const double h = fmean(Pe + k) + sqrt(fvar(Pe + k)) * a.eps_mc[((long long)r * a.Ntot + n) * K + k];
+        pi(K + k) = h;
+        mx = fmax(mx, h);
+      }
+      double se = 0;
+      for (int k = 0; k < K; k++) {
+        pi(K + k) = exp(pi(K + k) - mx);
+        se += pi(K + k);
+      }
+      for (int k = 0; k < K; k++) pi(k) += pi(K + k) / se;
+    }
+    for (int k = 0; k < K; k++) pi(k) /= (double)a.num_mc;
+  }
+  if (a.mix)
+    for (int k = 0; k < K; k++) a.mix[n * K + k] = pi(k);
+  if (a.y_mean || a.y_var) {
+    for (int f = 0; f < F; f++) {
+      double mean = 0;
+      for (int k = 0; k < K; k++) mean += pi(k) * fmean(k * F + f);
+      double var;
+      if (keras) {  // tfd.Mixture of MVNDiag(scale_diag = y_var): component stddev is y_var (quirk 1)
+        double e2 = 0, m2 = 0;
+        for (int k = 0; k < K; k++) {
+          const int l = k * F + f;
+          const double yv = fvar(l) + a.params[a.lo.noise + l], mu = fmean(l);
+          e2 += pi(k) * yv * yv;
+          m2 += pi(k) * mu * mu;
+        }
+        var = e2 + m2 - mean * mean;
+      } else {  // MixtureSameFamily: law of total variance, centred
+        double e2 = 0, c2 = 0;
+        for (int k = 0; k < K; k++) {
+          const int l = k * F + f;
+          const double d = fmean(l) - mean;
+          e2 += pi(k) * (fvar(l) + a.params[a.lo.noise + l]);
+          c2 += pi(k) * d * d;
+        }
+        var = e2 + c2;
+      }
+      if (a.y_mean) a.y_mean[n * F + f] = mean;
+      if (a.y_var) a.y_var[n * F + f] = var;
+    }
+  }
+}
+
+}  // namespace mogpe

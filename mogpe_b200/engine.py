@@ -1,0 +1,272 @@
+"""Host-side engine: packs the parameters of K SVGP experts + one SVGP gating network into the layout of
+include/mogpe_b200.h and drives the CUDA library.  Everything numerical happens on the device; this
+module only moves parameters / gradients between the model objects and the packed buffers.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .device import DeviceBuffer, as_view
+
+DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
+
+
+@dataclass
+class GPBlock:
+    """Constrained-space parameters of one SVGP: shared Z, one kernel shared by all L latents or
+    L separate kernels (gpflow SeparateIndependent + shared inducing variables)."""
+
+    Z: np.ndarray  # [M, D]
+    lengthscales: List[np.ndarray]  # per kernel: scalar () or [D]
+    variances: List[float]
+    q_mu: np.ndarray  # [M, L]
+    q_sqrt: np.ndarray  # [L, M, M]
+    mean_c: Optional[np.ndarray] = None  # [L] or None (Zero mean function)
+    noise: Optional[np.ndarray] = None  # [L] Gaussian likelihood variance (experts only)
+
+    @property
+    def M(self):
+        return self.Z.shape[0]
+
+    @property
+    def L(self):
+        return self.q_mu.shape[1]
+
+
+@dataclass
+class GPGrads:
+    Z: np.ndarray
+    lengthscales: List[np.ndarray]
+    variances: List[np.ndarray]
+    q_mu: np.ndarray
+    q_sqrt: np.ndarray
+    mean_c: np.ndarray
+    noise: Optional[np.ndarray]
+
+
+@dataclass
+class ElboResult:
+    elbo: float
+    var_exp: float
+    kl_gating: float
+    kl_experts: float
+    experts: Optional[List[GPGrads]] = None  # d ELBO / d (constrained parameter)
+    gating: Optional[GPGrads] = None
+    flat_grads: Optional[DeviceBuffer] = field(default=None, repr=False)
+
+
+class Engine:
+    def __init__(self, experts: List[GPBlock], gating: GPBlock, flavour="keras", max_batch=1024, device=0,
+                 jitter=DEFAULT_JITTER):
+        self.lib = _lib.load()
+        self.flavour = flavour
+        self.device = device
+        self.K = len(experts)
+        self.D = int(experts[0].Z.shape[1])
+        self.F = int(experts[0].L)
+        self.G = int(gating.L)
+        for e in experts:
+            if e.L != self.F or e.Z.shape[1] != self.D:
+                raise ValueError("all experts must share input_dim and num_latent_gps")
+        if gating.Z.shape[1] != self.D:
+            raise ValueError("gating network input_dim differs from the experts'")
+        if not ((self.G == 1 and self.K == 2) or self.G == self.K):
+            raise ValueError(f"gating network with {self.G} function(s) cannot gate {self.K} experts")
+        # groups: one per (GP, kernel)
+        self.blocks_meta = []  # per GP: (first_group, n_groups, first_latent, L, M)
+        group_M, latent_group = [], []
+        for gp in list(experts) + [gating]:
+            nk = len(gp.lengthscales)
+            if nk not in (1, gp.L):
+                raise ValueError("a GP needs 1 shared kernel or one kernel per latent")
+            g0, l0 = len(group_M), len(latent_group)
+            group_M += [gp.M] * nk
+            latent_group += [g0 + (0 if nk == 1 else l) for l in range(gp.L)]
+            self.blocks_meta.append((g0, nk, l0, gp.L, gp.M))
+        self.Q, self.P, self.Pe = len(group_M), len(latent_group), self.K * self.F
+        self._gm = (C.c_int32 * self.Q)(*group_M)
+        self._lg = (C.c_int32 * self.P)(*latent_group)
+        self.max_batch = int(max_batch)
+        desc = _lib.Desc(self.D, self.F, self.K, self.G, self.Q, self.P, self.max_batch,
+                         _lib.FLAVOUR_IDS[flavour], device, 0, jitter, self._gm, self._lg)
+        h = C.c_void_p()
+        _lib.check(self.lib.mogpe_create(C.byref(desc), C.byref(h)))
+        self.h = h
+        lo = _lib.Layout()
+        _lib.check(self.lib.mogpe_param_layout(self.h, C.byref(lo)), self.h)
+        self.lo = lo
+        self.Mp = lo.Mp
+        self.params = DeviceBuffer((lo.total,), device)
+        self.grads = DeviceBuffer((lo.total,), device)
+        self.out = DeviceBuffer((4,), device)
+        self._eps_cache = {}
+        self.set_params(experts, gating)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mogpe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- packing ---------------------------------------------------------------------------------
+    def pack(self, experts: List[GPBlock], gating: GPBlock) -> np.ndarray:
+        lo, Mp, D = self.lo, self.Mp, self.D
+        flat = np.zeros(lo.total)
+        ls = flat[lo.lengthscales:lo.lengthscales + self.Q * D].reshape(self.Q, D)
+        kv = flat[lo.variance:lo.variance + self.Q]
+        Z = flat[lo.Z:lo.Z + self.Q * Mp * D].reshape(self.Q, Mp, D)
+        qm = flat[lo.q_mu:lo.q_mu + self.P * Mp].reshape(self.P, Mp)
+        qs = flat[lo.q_sqrt:lo.q_sqrt + self.P * Mp * Mp].reshape(self.P, Mp, Mp)
+        mc = flat[lo.mean_c:lo.mean_c + self.P]
+        nz = flat[lo.noise:lo.noise + self.Pe]
+        for gp, (g0, nk, l0, L, M) in zip(list(experts) + [gating], self.blocks_meta):
+            for i in range(nk):
+                ls[g0 + i] = np.broadcast_to(np.asarray(gp.lengthscales[i], dtype=np.float64), (D,))
+                kv[g0 + i] = float(gp.variances[i])
+                Z[g0 + i, :M] = gp.Z
+            qm[l0:l0 + L, :M] = np.asarray(gp.q_mu).T
+            qs[l0:l0 + L, :M, :M] = np.tril(np.asarray(gp.q_sqrt))
+            if gp.mean_c is not None:
+                mc[l0:l0 + L] = np.broadcast_to(np.asarray(gp.mean_c, dtype=np.float64).reshape(-1), (L,))
+            if gp.noise is not None:
+                nz[l0:l0 + L] = np.broadcast_to(np.asarray(gp.noise, dtype=np.float64).reshape(-1), (L,))
+        return flat
+
+    def set_params(self, experts, gating):
+        self._ls_shapes = [[np.shape(ls) for ls in gp.lengthscales] for gp in list(experts) + [gating]]
+        self.params.copy_from(self.pack(experts, gating))
+
+    def unpack_grads(self, flat: np.ndarray):
+        lo, Mp, D = self.lo, self.Mp, self.D
+        ls = flat[lo.lengthscales:lo.lengthscales + self.Q * D].reshape(self.Q, D)
+        kv = flat[lo.variance:lo.variance + self.Q]
+        Z = flat[lo.Z:lo.Z + self.Q * Mp * D].reshape(self.Q, Mp, D)
+        qm = flat[lo.q_mu:lo.q_mu + self.P * Mp].reshape(self.P, Mp)
+        qs = flat[lo.q_sqrt:lo.q_sqrt + self.P * Mp * Mp].reshape(self.P, Mp, Mp)
+        mc = flat[lo.mean_c:lo.mean_c + self.P]
+        nz = flat[lo.noise:lo.noise + self.Pe]
+        out = []
+        for bi, (g0, nk, l0, L, M) in enumerate(self.blocks_meta):
+            gl = []
+            for i in range(nk):
+                shp = self._ls_shapes[bi][i]
+                gl.append(ls[g0 + i].sum() if shp == () else ls[g0 + i].copy())
+            out.append(GPGrads(
+                Z=Z[g0:g0 + nk, :M].sum(0),
+                lengthscales=gl,
+                variances=[kv[g0 + i].copy() for i in range(nk)],
+                q_mu=qm[l0:l0 + L, :M].T.copy(),
+                q_sqrt=np.tril(qs[l0:l0 + L, :M, :M]),
+                mean_c=mc[l0:l0 + L].copy(),
+                noise=nz[l0:l0 + L].copy() if bi < self.K else None,
+            ))
+        return out[:-1], out[-1]
+
+    # ---- eps helpers ---------------------------------------------------------------------------------
+    def pack_eps_u(self, eps_u_experts, eps_u_gating, S):
+        """[K][S, F, M_k] (+ gating [S, G, M_g]) -> [P, S, Mp] zero padded."""
+        flat = np.zeros((self.P, S, self.Mp))
+        srcs = list(eps_u_experts) if eps_u_experts is not None else [None] * self.K
+        srcs.append(eps_u_gating)
+        for e, (g0, nk, l0, L, M) in zip(srcs, self.blocks_meta):
+            if e is not None:
+                flat[l0:l0 + L, :, :M] = np.transpose(np.asarray(e, dtype=np.float64), (1, 0, 2))
+        return flat
+
+    def pack_eps_f(self, eps_f):
+        """[S, N, F, K] -> [S, N, K*F] (latent order k*F + f)."""
+        e = np.asarray(eps_f, dtype=np.float64)
+        return np.ascontiguousarray(np.transpose(e, (0, 1, 3, 2)).reshape(e.shape[0], e.shape[1], self.Pe))
+
+    def _dev(self, name, arr):
+        """Upload a host array into a cached device buffer; pass device tensors through."""
+        if arr is None:
+            return None, None
+        v = as_view(arr)
+        if v.on_device:
+            return v.ptr, v
+        n = int(np.prod(v.shape))
+        buf = self._eps_cache.get(name)
+        if buf is None or buf.size < n:
+            buf = DeviceBuffer((n,), self.device, zero=False)
+            self._eps_cache[name] = buf
+        _lib.check(self.lib.mogpe_memcpy_h2d(self.device, buf.ptr, v.ptr, n * 8, None))
+        return buf.ptr, (buf, v)
+
+    def fill_normal(self, buf: DeviceBuffer, seed: int, offset: int = 0, count=None, stream=None):
+        _lib.check(self.lib.mogpe_fill_normal(self.h, buf.ptr, buf.size if count is None else count, seed, offset, stream), self.h)
+
+    # ---- the hot path ----------------------------------------------------------------------------------
+    def elbo(self, X, Y, bound="further_gating", num_samples=1, scale=1.0, eps_u=None, eps_h=None, eps_f=None,
+             want_grads=True, unpack=True, stream=None) -> ElboResult:
+        """eps_u [P, S, Mp], eps_h [S, N, G], eps_f [S, N, K*F] (already in library layout)."""
+        xv, yv = as_view(X), as_view(Y)
+        N = int(xv.shape[0])
+        if len(xv.shape) != 2 or xv.shape[1] != self.D:
+            raise ValueError(f"X must be [N, {self.D}], got {xv.shape}")
+        if tuple(yv.shape) != (N, self.F):
+            raise ValueError(f"Y must be [{N}, {self.F}], got {tuple(yv.shape)}")
+        b = _lib.BOUND_IDS[bound]
+        gptr = self.grads.ptr if want_grads else None
+        host_path = (not xv.on_device) and (not yv.on_device) and all(
+            e is None or not as_view(e).on_device for e in (eps_u, eps_h, eps_f))
+        if host_path:
+            out = np.zeros(4)
+            ev = [None if e is None else as_view(e) for e in (eps_u, eps_h, eps_f)]
+            _lib.check(self.lib.mogpe_elbo_fwd_bwd_host(
+                self.h, xv.ptr, yv.ptr, N, self.params.ptr, *[None if e is None else e.ptr for e in ev],
+                b, num_samples, float(scale), out.ctypes.data, gptr, stream), self.h)
+        else:
+            keep = []
+            ptrs = []
+            for name, e in (("X", X), ("Y", Y), ("eps_u", eps_u), ("eps_h", eps_h), ("eps_f", eps_f)):
+                p, k = self._dev(name, e)
+                ptrs.append(p)
+                keep.append(k)
+            _lib.check(self.lib.mogpe_elbo_fwd_bwd(
+                self.h, ptrs[0], ptrs[1], N, self.params.ptr, ptrs[2], ptrs[3], ptrs[4],
+                b, num_samples, float(scale), self.out.ptr, gptr, stream), self.h)
+            out = self.out.numpy()
+        res = ElboResult(*[float(v) for v in out])
+        if want_grads:
+            res.flat_grads = self.grads
+            if unpack:
+                res.experts, res.gating = self.unpack_grads(self.grads.numpy())
+        return res
+
+    def predict(self, X, want=("f_mean", "f_var", "mix_probs", "y_mean", "y_var"), eps_mc=None, stream=None):
+        """-> dict of numpy arrays (f_mean/f_var [N, P], mix_probs [N, K], y_mean/y_var [N, F])."""
+        xv = as_view(X)
+        N = int(xv.shape[0])
+        if len(xv.shape) != 2 or xv.shape[1] != self.D:
+            raise ValueError(f"X must be [N, {self.D}], got {xv.shape}")
+        xp, keep = self._dev("Xp", X)
+        shapes = {"f_mean": (N, self.P), "f_var": (N, self.P), "mix_probs": (N, self.K),
+                  "y_mean": (N, self.F), "y_var": (N, self.F)}
+        bufs = {k: DeviceBuffer(shapes[k], self.device, zero=False) for k in want}
+        num_mc = 0
+        mp = None
+        if eps_mc is not None:
+            e = np.ascontiguousarray(eps_mc, dtype=np.float64)
+            if e.shape[1:] != (N, self.K):
+                raise ValueError(f"eps_mc must be [R, {N}, {self.K}]")
+            num_mc = e.shape[0]
+            mp, keep2 = self._dev("eps_mc", e)
+        args = [bufs[k].ptr if k in bufs else None for k in ("f_mean", "f_var", "mix_probs", "y_mean", "y_var")]
+        _lib.check(self.lib.mogpe_predict(self.h, xp, N, self.params.ptr, *args, mp, num_mc, stream), self.h)
+        return {k: b.numpy() for k, b in bufs.items()}
+
+    def debug(self, name):
+        n = C.c_int64()
+        _lib.check(self.lib.mogpe_debug_copy(self.h, name.encode(), None, 0, C.byref(n)), self.h)
+        out = np.empty(n.value)
+        _lib.check(self.lib.mogpe_debug_copy(self.h, name.encode(), out.ctypes.data, n.value, C.byref(n)), self.h)
+        return out

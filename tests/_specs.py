@@ -49,7 +49,8 @@ def make_spec(seed=0, N=24, D=2, F=1, K=2, M=8, S=1, flavour="keras", bound="fur
     if noise_lo is None:
         # "further" uses the noise *variance* as the density scale (quirk 2): keep it large enough that the
         # reference's probability-space evaluation (quirk 6) stays finite on these seeds
-        noise_lo = 0.5 if bound == "further" else 1e-2
+        # (the keras flavour also uses y_var itself as the scale of the expert density, quirk 1)
+        noise_lo = 0.5 if bound == "further" else (0.3 if flavour == "keras" else 1e-2)
     experts = [
         make_gp(rng, X, Ms[k], F, F if separate_kernels else 1, ard, mean_c, True, noise_lo=noise_lo)
         for k in range(K)

@@ -1,0 +1,249 @@
+"""GPU parity tests of the CUDA library (through the C-ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): ELBO / predictions 1e-8 relative, gradients 1e-6 relative (float64).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests._specs import BOUNDS, FLAVOURS, make_spec
+
+pytestmark = pytest.mark.gpu
+
+RTOL_VALUE = 1e-8
+RTOL_GRAD = 1e-6
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (128, 256, 192), (256, 1024, 128), (512, 4096, 512)])
+def test_dmma_gemm_matches_numpy(ta, tb, M, N, K):
+    import torch
+    from mogpe_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(M + N + K + ta * 2 + tb)
+    batch = 3
+    A = rng.standard_normal((batch, K, M) if ta else (batch, M, K))
+    B = rng.standard_normal((batch, N, K) if tb else (batch, K, N))
+    C0 = rng.standard_normal((batch, M, N))
+    dA, dB, dC = (torch.as_tensor(x, device="cuda") for x in (A, B, C0))
+    _lib.check(lib.mogpe_debug_gemm(0, dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), batch, M, N, K, ta, tb, 0, 0, 1.5, 0.5, None))
+    torch.cuda.synchronize()
+    opA = np.swapaxes(A, 1, 2) if ta else A
+    opB = np.swapaxes(B, 1, 2) if tb else B
+    ref = 1.5 * opA @ opB + 0.5 * C0
+    assert _rel(dC.cpu().numpy(), ref) < 1e-13
+
+
+@pytest.mark.parametrize("size", [128, 256, 512])
+def test_dmma_gemm_triangular_modes(size):
+    import torch
+    from mogpe_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(size)
+    M = size
+    T = np.tril(rng.standard_normal((2, M, M)))
+    R = rng.standard_normal((2, M, 1024))
+    out = torch.zeros((2, M, 1024), dtype=torch.float64, device="cuda")
+    dT, dR = torch.as_tensor(T, device="cuda"), torch.as_tensor(R, device="cuda")
+    # left lower: T @ R
+    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dR.data_ptr(), out.data_ptr(), 2, M, 1024, M, 0, 0, 1, 0, 1.0, 0.0, None))
+    assert _rel(out.cpu().numpy(), T @ R) < 1e-13
+    # left upper (transposed lower): T^T @ R
+    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dR.data_ptr(), out.data_ptr(), 2, M, 1024, M, 1, 0, 2, 0, 1.0, 0.0, None))
+    assert _rel(out.cpu().numpy(), np.swapaxes(T, 1, 2) @ R) < 1e-13
+    # tril output of an NT product over a long k
+    W = rng.standard_normal((2, M, 2048))
+    A = rng.standard_normal((2, M, 2048))
+    o2 = torch.full((2, M, M), 7.0, dtype=torch.float64, device="cuda")
+    dW, dA = torch.as_tensor(W, device="cuda"), torch.as_tensor(A, device="cuda")
+    _lib.check(lib.mogpe_debug_gemm(0, dW.data_ptr(), dA.data_ptr(), o2.data_ptr(), 2, M, M, 2048, 0, 1, 0, 1, -1.0, 0.0, None))
+    assert _rel(o2.cpu().numpy(), -np.tril(W @ np.swapaxes(A, 1, 2))) < 1e-13
+    # right lower: R2 @ T  and left-upper x right-lower: T^T @ T2
+    R2 = rng.standard_normal((2, M, M))
+    o3 = torch.zeros((2, M, M), dtype=torch.float64, device="cuda")
+    dR2 = torch.as_tensor(R2, device="cuda")
+    _lib.check(lib.mogpe_debug_gemm(0, dR2.data_ptr(), dT.data_ptr(), o3.data_ptr(), 2, M, M, M, 0, 0, 4, 0, 1.0, 0.0, None))
+    assert _rel(o3.cpu().numpy(), R2 @ T) < 1e-13
+    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dT.data_ptr(), o3.data_ptr(), 2, M, M, M, 1, 0, 2 | 4, 0, 1.0, 0.0, None))
+    assert _rel(o3.cpu().numpy(), np.swapaxes(T, 1, 2) @ T) < 1e-13
+
+
+def _check_intermediates(eng, spec, X):
+    """Kuu, L, Linv, Kuf, A of every group against numpy (A via solve_triangular, as the reference does)."""
+    from scipy.linalg import solve_triangular
+
+    from oracle import ref_numpy as rn
+
+    Mp, Bp = eng.Mp, ((eng.max_batch + 127) // 128) * 128
+    Q = eng.Q
+    Kuu = eng.debug("Kuu").reshape(Q, Mp, Mp)
+    L = eng.debug("L").reshape(Q, Mp, Mp)
+    Linv = eng.debug("Linv").reshape(Q, Mp, Mp)
+    Kuf = eng.debug("Kuf").reshape(Q, Mp, Bp)
+    A = eng.debug("A").reshape(Q, Mp, Bp)
+    N = X.shape[0]
+    g = 0
+    worst = {}
+    for gp in spec["experts"] + [spec["gating"]]:
+        Z = np.asarray(gp["Z"])
+        M = Z.shape[0]
+        for kern in gp["kernels"]:
+            K_ref = rn.rbf_K(kern, Z) + 1e-6 * np.eye(M)
+            L_ref = np.linalg.cholesky(K_ref)
+            Kuf_ref = rn.rbf_K(kern, Z, X)
+            A_ref = solve_triangular(L_ref, Kuf_ref, lower=True)
+            for name, got, ref in (("Kuu", Kuu[g, :M, :M], K_ref), ("L", L[g, :M, :M], L_ref),
+                                   ("Linv", Linv[g, :M, :M], np.linalg.inv(L_ref)),
+                                   ("Kuf", Kuf[g, :M, :N], Kuf_ref), ("A", A[g, :M, :N], A_ref)):
+                worst[name] = max(worst.get(name, 0.0), _rel(got, ref))
+            # padding: identity / zeros
+            assert np.array_equal(L[g, M:, M:], np.eye(Mp - M))
+            assert not np.any(L[g, M:, :M]) and not np.any(Kuf[g, M:, :]) and not np.any(A[g, M:, :N])
+            assert not np.any(np.triu(L[g], 1)) and not np.any(np.triu(Linv[g], 1))
+            g += 1
+    return worst
+
+
+@pytest.mark.parametrize("M,N", [(8, 24), (70, 300), (200, 1000)])
+def test_factorisation_and_conditional_intermediates(M, N):
+    from tests._engine_helpers import engine_from_spec, run_engine_elbo
+
+    spec, X, Y, eps = make_spec(seed=M, N=N, D=2, F=1, K=2, M=M, separate_kernels=False)
+    eng = engine_from_spec(spec, max_batch=N)
+    run_engine_elbo(eng, spec, X, Y, eps, want_grads=False)
+    worst = _check_intermediates(eng, spec, X)
+    assert worst["Kuu"] < 1e-14 and worst["Kuf"] < 1e-13, worst
+    # conditioning of Kuu (jitter 1e-6) amplifies rounding in L / L^-1 / A; 1e-9 is far inside the ELBO budget
+    assert worst["L"] < 1e-9 and worst["A"] < 1e-8, worst
+
+
+CASES = [
+    # K, F, S, M, N, D, separate kernels
+    (2, 1, 1, 8, 24, 2, False),
+    (2, 2, 2, 20, 100, 3, True),
+    (3, 1, 2, 33, 130, 1, False),
+    (3, 2, 3, 70, 257, 2, True),
+]
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+@pytest.mark.parametrize("bound", BOUNDS)
+@pytest.mark.parametrize("case", CASES)
+def test_elbo_and_gradients_match_oracle(flavour, bound, case):
+    from oracle import ref_numpy as rn
+    from oracle import ref_torch as rt
+    from tests._engine_helpers import engine_from_spec, engine_grads_named, oracle_grads_constrained, run_engine_elbo
+
+    K, F, S, M, N, D, sep = case
+    if bound == "tight" and K > 2:
+        pytest.skip("Softmax tight bound is Monte-Carlo in the reference; not implemented (MOGPE_ERR_UNSUPPORTED)")
+    spec, X, Y, eps = make_spec(seed=100 + K + F + S, N=N, D=D, F=F, K=K, M=M, S=S, flavour=flavour, bound=bound,
+                                num_data=10 * N, separate_kernels=sep, gating_mean_c=0.2)
+    eng = engine_from_spec(spec, max_batch=N)
+    res = run_engine_elbo(eng, spec, X, Y, eps)
+    ref = rn.elbo(spec, X, Y, eps)
+    assert np.isfinite(ref)
+    assert abs(res.elbo - ref) <= RTOL_VALUE * abs(ref), (res.elbo, ref)
+    assert abs(res.elbo - (res.var_exp - res.kl_gating - res.kl_experts)) <= 1e-12 * abs(ref)
+    val, grads_u = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    want = oracle_grads_constrained(spec, grads_u)
+    got = engine_grads_named(res, spec)
+    bad = {}
+    for name, g_ref in want.items():
+        r = _rel(got[name], g_ref)
+        scale = max(1.0, float(np.max(np.abs(g_ref))))
+        if np.max(np.abs(np.asarray(got[name]) - g_ref)) > RTOL_GRAD * scale:
+            bad[name] = r
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("device_inputs", [False, True])
+def test_host_and_device_entry_points_agree(device_inputs):
+    from tests._engine_helpers import engine_from_spec, run_engine_elbo
+
+    spec, X, Y, eps = make_spec(seed=5, N=200, D=2, F=1, K=2, M=16, S=2)
+    eng = engine_from_spec(spec, max_batch=256)
+    a = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=device_inputs)
+    b = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=not device_inputs)
+    assert a.elbo == pytest.approx(b.elbo, rel=1e-13)
+    np.testing.assert_allclose(a.gating.q_sqrt, b.gating.q_sqrt, rtol=1e-10, atol=1e-14)
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+@pytest.mark.parametrize("K,F,sep", [(2, 1, False), (2, 2, True), (3, 2, True)])
+def test_predict_matches_oracle(flavour, K, F, sep):
+    from oracle import ref_numpy as rn
+    from tests._engine_helpers import engine_from_spec
+
+    N = 333
+    spec, X, Y, eps = make_spec(seed=9 + K, N=N, D=2, F=F, K=K, M=25, flavour=flavour, separate_kernels=sep)
+    eng = engine_from_spec(spec, max_batch=128)  # forces 3 chunks
+    eps_mc = np.random.default_rng(3).standard_normal((17, N, K)) if K > 2 else None
+    out = eng.predict(X, eps_mc=eps_mc)
+    pi = rn.predict_mixing_probs(spec, X, eps_mc)
+    ym, yv = rn.predict_y(spec, X, eps_mc)
+    assert _rel(out["mix_probs"], pi) < RTOL_VALUE
+    assert _rel(out["y_mean"], ym) < RTOL_VALUE
+    assert _rel(out["y_var"], yv) < RTOL_VALUE
+    l = 0
+    for gp in spec["experts"] + [spec["gating"]]:
+        fm, fv = rn.predict_f(gp, X)
+        L = fm.shape[1]
+        assert _rel(out["f_mean"][:, l:l + L], fm) < RTOL_VALUE
+        assert _rel(out["f_var"][:, l:l + L], fv) < RTOL_VALUE
+        l += L
+
+
+def test_different_inducing_counts_per_gp():
+    from oracle import ref_numpy as rn
+    from tests._engine_helpers import engine_from_spec, run_engine_elbo
+
+    spec, X, Y, eps = make_spec(seed=21, N=150, D=1, F=1, K=2, M=12, M_experts=[6, 7], M_gating=40, S=2, num_data=1000)
+    eng = engine_from_spec(spec, max_batch=150)
+    res = run_engine_elbo(eng, spec, X, Y, eps)
+    ref = rn.elbo(spec, X, Y, eps)
+    assert abs(res.elbo - ref) <= RTOL_VALUE * abs(ref)
+
+
+def test_fill_normal_is_standard_normal_and_reproducible():
+    from mogpe_b200.device import DeviceBuffer
+    from tests._engine_helpers import engine_from_spec
+
+    spec, X, Y, eps = make_spec(seed=1, N=16, M=4)
+    eng = engine_from_spec(spec, max_batch=16)
+    buf = DeviceBuffer((200001,), zero=True)
+    eng.fill_normal(buf, seed=1234, offset=0)
+    a = buf.numpy()
+    eng.fill_normal(buf, seed=1234, offset=0)
+    assert np.array_equal(a, buf.numpy())
+    assert abs(a.mean()) < 0.01 and abs(a.std() - 1.0) < 0.01
+    from scipy import stats
+
+    assert stats.kstest(a, "norm").pvalue > 1e-4
+    # counter-based: a window at an even offset reproduces the same stream
+    eng.fill_normal(buf, seed=1234, offset=1000, count=500)
+    assert np.array_equal(buf.numpy()[:500], a[1000:1500])
+
+
+def test_invalid_arguments_raise():
+    from mogpe_b200._lib import MogpeError
+    from tests._engine_helpers import engine_from_spec, run_engine_elbo
+
+    spec, X, Y, eps = make_spec(seed=2, N=32, M=4, K=3)
+    eng = engine_from_spec(spec, max_batch=16)
+    with pytest.raises(MogpeError):
+        run_engine_elbo(eng, spec, X, Y, eps)  # N > max_batch
+    spec["bound"] = "tight"
+    eng = engine_from_spec(spec, max_batch=32)
+    with pytest.raises(MogpeError, match="Softmax"):
+        run_engine_elbo(eng, spec, X, Y, eps)
+    with pytest.raises(ValueError):
+        eng.elbo(X[:, :1].repeat(3, 1), Y)
