@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""Benchmark of the mogpe hot path: minibatch ELBO forward+backward of MixtureOfSVGPExperts.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one synthetic minibatch: draw the Monte-Carlo normals on the
+device, ELBO forward + full backward (gradients of every kernel / inducing / variational parameter), and
+for N > 1 one NCCL all-reduce of the packed gradient buffer.  Prints ONE JSON line (rank 0).
+
+Workloads (per-GPU batch fixed -> weak scaling):
+  C1 mcycle-like  D=1 F=1 K=2 G=1 M=32   batch 16
+  C2 artificial   D=1 F=1 K=3 G=3 M=128  batch 8192
+  C3 quadcopter   D=2 F=2 K=2 G=1 M=256  batch 16384
+  C4 (default)    D=4 F=1 K=8 G=8 M=512  batch 8192 per GPU (65536 global on 8 GPUs)  <- BASELINE.json metric
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C1": dict(D=1, F=1, K=2, M=32, batch=16, num_data=93, sep=False, cpu_rows=16),
+    "C2": dict(D=1, F=1, K=3, M=128, batch=8192, num_data=100_000, sep=False, cpu_rows=8192),
+    "C3": dict(D=2, F=2, K=2, M=256, batch=16384, num_data=1_000_000, sep=True, cpu_rows=4096),
+    "C4": dict(D=4, F=1, K=8, M=512, batch=8192, num_data=10_000_000, sep=False, cpu_rows=2048),
+}
+BOUND, FLAVOUR, S = "further_gating", "keras", 1
+FP64_TENSOR_PEAK_TFLOPS = 37.0  # measured DMMA issue peak on this pool (profiles/fp64_probe_r01.log)
+
+
+def logu(rng, lo, hi, size=None):
+    return np.exp(rng.uniform(np.log(lo), np.log(hi), size))
+
+
+def synth_model(wl, seed=3):
+    """Model parameters in the oracle's spec format: l, var ~ LogU(0.3, 3), noise ~ LogU(0.3, 1)
+    (kept where the reference's probability-space ELBO is finite), q_mu ~ N(0,1), q_sqrt = tril(0.1 N) + I,
+    Z = M data-like rows."""
+    rng = np.random.default_rng(seed)
+    D, F, K, M = wl["D"], wl["F"], wl["K"], wl["M"]
+    G = 1 if K == 2 else K
+
+    def gp(L, nk, expert):
+        d = {
+            "Z": rng.standard_normal((M, D)),
+            "kernels": [{"lengthscales": logu(rng, 0.3, 3.0, D), "variance": float(logu(rng, 0.3, 3.0))} for _ in range(nk)],
+            "q_mu": rng.standard_normal((M, L)),
+            "q_sqrt": np.tril(0.1 * rng.standard_normal((L, M, M))) + np.eye(M)[None],
+            "mean_c": 0.1 * rng.standard_normal(L) if expert else None,
+        }
+        if expert:
+            d["noise_variance"] = logu(rng, 0.3, 1.0, L)
+        return d
+
+    experts = [gp(F, F if wl["sep"] else 1, True) for _ in range(K)]
+    gating = gp(G, 1, False)
+    return {"flavour": FLAVOUR, "bound": BOUND, "num_samples": S, "num_data": wl["num_data"],
+            "experts": experts, "gating": gating}
+
+
+def synth_batch(wl, n, seed):
+    rng = np.random.default_rng(seed)
+    D, F, K = wl["D"], wl["F"], wl["K"]
+    X = rng.standard_normal((n, D))
+    regime = rng.integers(0, K, n)
+    Y = np.stack([np.sin((1 + f) * X.sum(-1) + regime) + 0.1 * (1 + regime) * rng.standard_normal(n) for f in range(F)], -1)
+    return np.ascontiguousarray(X), np.ascontiguousarray(Y)
+
+
+def blocks_from_spec(spec):
+    from mogpe_b200.engine import GPBlock
+
+    def blk(g, expert):
+        L = np.asarray(g["q_mu"]).shape[1]
+        return GPBlock(Z=np.asarray(g["Z"], float), lengthscales=[np.asarray(k["lengthscales"], float) for k in g["kernels"]],
+                       variances=[float(k["variance"]) for k in g["kernels"]], q_mu=np.asarray(g["q_mu"], float),
+                       q_sqrt=np.asarray(g["q_sqrt"], float),
+                       mean_c=None if g.get("mean_c") is None else np.asarray(g["mean_c"], float),
+                       noise=np.broadcast_to(np.asarray(g["noise_variance"], float).reshape(-1), (L,)).copy() if expert else None)
+
+    return [blk(g, True) for g in spec["experts"]], blk(spec["gating"], False)
+
+
+def step_flops(wl, B):
+    """Algorithmic FLOPs of one fwd+bwd step (BASELINE.md work model; FMA = 2)."""
+    F, K, M = wl["F"], wl["K"], wl["M"]
+    G = 1 if K == 2 else K
+    Pe, Pg = K * F, G
+    return Pe * (4.0 * M * M * B + 8.0 * M**3 / 3.0) + Pg * (8.0 * M * M * B + 8.0 * M**3 / 3.0)
+
+
+# ---- the CPU arm: the restated reference (oracle/ref_torch.py) ------------------------------------------
+def run_cpu_reference(wl, spec, steps, warmup, rows):
+    import torch
+
+    from oracle import ref_torch as rt
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = rt.MixtureOfSVGPExperts(spec)
+    X, Y = synth_batch(wl, rows, seed=1000)
+    rng = np.random.default_rng(11)
+    K, F, M = wl["K"], wl["F"], wl["M"]
+    G = 1 if K == 2 else K
+    eps = {"u_experts": [rng.standard_normal((S, F, M)) for _ in range(K)], "h": rng.standard_normal((S, rows, G))}
+    for _ in range(warmup):
+        model.elbo_and_grads(X, Y, eps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.elbo_and_grads(X, Y, eps)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return {"value": rows / dt, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} fwd+bwd steps of {rows} rows of workload (same model, torch float64 autograd "
+                      f"following the reference's per-expert op sequence), {dt * 1e3:.1f} ms/step"}, dt
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = args.steps, max(args.warmup, 3 if args.impl == "ours" else 0)
+    K = wl["K"]
+    G = 1 if K == 2 else K
+    cfg = {"workload": f"{args.workload}: D={wl['D']} F={wl['F']} K={K} G={G} M={wl['M']} S={S} "
+                       f"bound={BOUND} flavour={FLAVOUR}, batch {wl['batch']}/GPU (global {wl['batch'] * world}), "
+                       f"num_data={wl['num_data']}",
+           "batch_per_gpu": wl["batch"], "global_batch": wl["batch"] * world, "M": wl["M"], "K": K, "D": wl["D"],
+           "l2": "per-step working set (A, Kuf, W, ... = 4*Q*M*B*8 B) is far larger than the 126 MB L2 for C2-C4; "
+                 "minibatches cycle through a 4-batch pool",
+           "parallelism": f"dp{world}: minibatch rows sharded, params replicated, one NCCL all-reduce of grads"}
+    spec = synth_model(wl)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rows = wl["cpu_rows"]
+        cb, dt = run_cpu_reference(wl, spec, max(1, steps), min(warmup, 2), rows)
+        line = {"impl": "reference", "metric": "elbo_fwd_bwd_points_per_sec", "value": cb["value"], "unit": "points/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 2), "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "restated reference (torch-CPU float64, oracle/ref_torch.py): TensorFlow/GPflow/TFP are not "
+                        "installable here, so the reference's own code cannot run"}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from mogpe_b200.device import DeviceBuffer
+    from mogpe_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = wl["batch"]
+    experts, gating = blocks_from_spec(spec)
+    eng = Engine(experts, gating, flavour=FLAVOUR, max_batch=B, device=local_rank)
+    eng.set_seed(1234 + rank)
+    if world > 1:
+        ids = [Engine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.init_data_parallel(rank, world, ids[0])
+    scale = wl["num_data"] / float(B * world)
+    pool = 4
+    host_batches = [synth_batch(wl, B, seed=100 + rank * pool + i) for i in range(pool)]
+    dev_batches = [(DeviceBuffer.from_numpy(x, local_rank), DeviceBuffer.from_numpy(y, local_rank)) for x, y in host_batches]
+    pinned = []
+    for x, y in host_batches:
+        px = torch.from_numpy(x).pin_memory()
+        py = torch.from_numpy(y).pin_memory()
+        pinned.append((px, py, px.numpy(), py.numpy()))
+
+    def step(i):
+        x, y = dev_batches[i % pool]
+        eng.elbo(x, y, BOUND, S, scale, want_grads=True, unpack=False, readback=False)
+        if world > 1:
+            eng.allreduce(eng.gbuf)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    eng.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop() if sampler else None
+    elbo_val = eng.gbuf.numpy(offset=eng.lo.total, count=4)
+
+    # end to end through the host-facing entry: pinned host X/Y -> H2D -> step -> D2H of the result
+    def e2e_step(i):
+        _, _, xn, yn = pinned[i % pool]
+        r = eng.elbo(xn, yn, BOUND, S, scale, want_grads=True, unpack=False)
+        if world > 1:
+            eng.allreduce(eng.gbuf)
+            torch.cuda.synchronize()
+        return r
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pts = float(B * world * steps)
+    value = pts / (ms * 1e-3)
+    gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) * 1e-12 if prof["gemm_ms"] > 0 else None
+    line = {
+        "metric": "elbo_fwd_bwd_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "steps_per_sec": steps / (ms * 1e-3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg, "clocks": clocks,
+        "e2e": {"value": pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(B * (wl["D"] + wl["F"]) * 8), "d2h_bytes_per_step": 32,
+                "api": "Engine.elbo(X_host, Y_host) -> mogpe_elbo_fwd_bwd_host (pinned X/Y, H2D + D2H inside)"},
+        "gpu_launches": int(prof["all_launches"]),
+        "roofline": {
+            "bound": "tensor", "kernel": "mogpe::gemm_dmma_kernel (all instances: A=Linv*Kuf, S^T*A, Linv^T*Abar, W*A^T, ...)",
+            "achieved": gemm_tflops, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+            "frac": None if gemm_tflops is None else gemm_tflops / FP64_TENSOR_PEAK_TFLOPS,
+            "peak_source": "measured FP64 DMMA issue peak of this pool's B200 (profiles/fp64_probe_r01.log; cuBLAS DGEMM "
+                           "reaches 35.4); MEASURED_PEAKS.json holds only HBM and bf16 figures",
+            "gemm_ms_per_step": prof["gemm_ms"] / steps, "gemm_share_of_step": prof["gemm_ms"] / ms,
+            "gemm_launches_per_step": prof["gemm_launches"] / steps,
+            "step_model_tflops": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12,
+            "traffic": None,
+        },
+        "elbo_last_step": float(elbo_val[0]),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = run_cpu_reference(wl, spec, 3, 1, wl["cpu_rows"])
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,16 @@ mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const do
                            double* f_var, double* mix_probs, double* y_mean, double* y_var,
                            const double* eps_mc, int32_t num_mc, void* cuda_stream);
 
+/* Library-owned random stream.  When an eps_* pointer that `bound` needs is NULL, the library draws it on
+ * the device from Philox(seed, counter) -- as the reference draws inside tf.random / tfd -- and advances the
+ * counter.  mogpe_debug_copy("eps_u" | "eps_h" | "eps_f") returns the draws of the last call so the oracle
+ * can replay them. */
+mogpe_status mogpe_set_seed(mogpe_handle* h, uint64_t seed);
+
+/* Data-parallel ranks each evaluate the KL terms redundantly; with weight 1/world_size the all-reduced
+ * ELBO and gradients equal the single-process ones. Default 1. */
+mogpe_status mogpe_set_kl_weight(mogpe_handle* h, double w);
+
 /* Counter-based N(0,1) generator (Philox4x32-10 + Box-Muller) for the eps_* inputs.  Stand-in for the
  * tf.random / tfd sampling inside the reference's bounds (mogpe/keras/gps.py:29, gpflow sample_mvn). */
 mogpe_status mogpe_fill_normal(mogpe_handle* h, double* dst, int64_t n, uint64_t seed, uint64_t offset,
@@ -150,6 +160,14 @@ mogpe_status mogpe_memcpy_h2d(int32_t device, void* dst, const void* src, int64_
 mogpe_status mogpe_memcpy_d2h(int32_t device, void* dst, const void* src, int64_t bytes, void* cuda_stream);
 mogpe_status mogpe_memset_zero(int32_t device, void* dst, int64_t bytes, void* cuda_stream);
 mogpe_status mogpe_stream_sync(int32_t device, void* cuda_stream);
+
+/* Measurement hooks (bench.py roofline): with profiling on, every DMMA GEMM launch is bracketed by CUDA
+ * events on the caller's stream.  mogpe_profile_read synchronises, returns the accumulated GEMM device
+ * time (ms), the algorithmic FLOPs of those launches, their count, and the count of ALL kernels this
+ * handle launched since the last read, then resets the counters. */
+mogpe_status mogpe_profile_enable(mogpe_handle* h, int32_t on);
+mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches,
+                                int64_t* all_launches);
 
 /* Test hook: copy a named intermediate of the last call to the host (Kuu, L, Linv, Kuf, A, ...).
  * Returns the element count in *n_out; copies min(capacity, count) doubles. */

@@ -51,6 +51,10 @@ _PROTOS = {
     "mogpe_elbo_fwd_bwd_host": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_double, _P, _P, _P]),
     "mogpe_predict": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "mogpe_fill_normal": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
+    "mogpe_set_seed": (C.c_int, [_P, C.c_uint64]),
+    "mogpe_set_kl_weight": (C.c_int, [_P, C.c_double]),
+    "mogpe_profile_enable": (C.c_int, [_P, C.c_int32]),
+    "mogpe_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mogpe_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "mogpe_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int32]),
     "mogpe_allreduce_sum": (C.c_int, [_P, _P, C.c_int64, _P]),

@@ -44,6 +44,20 @@ struct mogpe_handle {
   // host-entry staging
   double *stage_dev = nullptr, *stage_host = nullptr, *out_dev = nullptr, *out_host_pinned = nullptr;
   size_t stage_cap = 0;
+  // library-owned random stream
+  uint64_t seed = 0x6d6f677065ULL, rng_counter = 0;
+  double *eps_u_int = nullptr, *eps_h_int = nullptr, *eps_f_int = nullptr;
+  size_t eps_u_cap = 0, eps_h_cap = 0, eps_f_cap = 0;
+  const double *last_eps_u = nullptr, *last_eps_h = nullptr, *last_eps_f = nullptr;
+  long long last_nu = 0, last_nh = 0, last_nf = 0;
+  double kl_weight = 1.0;
+  // measurement
+  bool prof = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  double prof_flops = 0;
+  long long gemm_launches = 0, all_launches = 0;
+  cudaStream_t prof_stream = nullptr;
   // NCCL (dlopen'ed)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
@@ -78,7 +92,7 @@ extern "C" const char* mogpe_last_error(const mogpe_handle* h) { return h ? h->e
 static void free_ws(mogpe_handle* h) {
   double** ptrs[] = {&h->Kuu, &h->L, &h->Linv, &h->Lbar, &h->T1, &h->T2, &h->Kuf, &h->A, &h->Abar, &h->W,
                      &h->LTA, &h->Sc, &h->V, &h->dV, &h->mean, &h->dmean, &h->var0ss, &h->varq, &h->dfvar,
-                     &h->stage_dev, &h->out_dev};
+                     &h->stage_dev, &h->out_dev, &h->eps_u_int, &h->eps_h_int, &h->eps_f_int};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -89,6 +103,8 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_latent_group) cudaFree(h->d_latent_group);
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
+  for (auto e : h->ev) cudaEventDestroy(e);
+  h->ev.clear();
 }
 
 extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
@@ -297,6 +313,31 @@ static GemmParams gp_init() {
   return p;
 }
 
+// GEMM launch through the handle: counts launches and, with profiling on, brackets it with CUDA events.
+// `flops` is the ALGORITHMIC work of the operation (triangular operands counted as triangular).
+static cudaError_t hgemm(mogpe_handle* h, const GemmParams& p, int batch, bool ta, bool tb, cudaStream_t st,
+                         double flops) {
+  h->gemm_launches++;
+  h->all_launches++;
+  if (!h->prof) return launch_gemm(p, batch, ta, tb, st);
+  if (h->ev_used + 2 > h->ev.size()) {
+    for (int i = 0; i < 64; i++) {
+      cudaEvent_t e;
+      cudaError_t ce = cudaEventCreate(&e);
+      if (ce != cudaSuccess) return ce;
+      h->ev.push_back(e);
+    }
+  }
+  h->prof_stream = st;
+  cudaEventRecord(h->ev[h->ev_used], st);
+  cudaError_t rc = launch_gemm(p, batch, ta, tb, st);
+  cudaEventRecord(h->ev[h->ev_used + 1], st);
+  h->ev_used += 2;
+  h->prof_flops += flops;
+  return rc;
+}
+#define KCOUNT(h, n) ((h)->all_launches += (n))
+
 // Kuu -> L -> Linv for every group, and the clean q_sqrt copies.
 static mogpe_status factorise(mogpe_handle* h, const double* params, cudaStream_t st) {
   const int Q = h->md_host.Q, P = h->md_host.P, Mp = h->Mp;
@@ -305,6 +346,7 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, cudaStream_
     chol_step_kernel<<<dim3(Mp / 32 - j, Q), 256, 0, st>>>(h->Kuu, h->L, Mp, j);
   trinv_kernel<<<dim3(Mp / 32, Q), 256, 0, st>>>(h->L, h->Linv, Mp);
   prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->Sc);
+  KCOUNT(h, 3 + Mp / 32);
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
 }
@@ -323,7 +365,7 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
     p.B = h->Kuf;  p.sB = (long long)Mp * h->Bp; p.ldb = h->Bp;
     p.C = h->A;    p.sC = (long long)Mp * h->Bp; p.ldc = h->Bp;
     p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_LOWER;
-    H_CUDA(h, launch_gemm(p, Q, false, false, st));
+    H_CUDA(h, hgemm(h, p, Q, false, false, st, (double)Q * Mp * Mp * Bc));
   }
   if (md.nlta > 0) {
     GemmParams p = gp_init();
@@ -331,9 +373,11 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
     p.B = h->A;   p.sB = (long long)Mp * h->Bp; p.ldb = h->Bp; p.mapB = h->d_lta_group;
     p.C = h->LTA; p.sC = (long long)Mp * h->Bp; p.ldc = h->Bp;
     p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_UPPER;
-    H_CUDA(h, launch_gemm(p, md.nlta, true, false, st));
+    H_CUDA(h, hgemm(h, p, md.nlta, true, false, st, (double)md.nlta * Mp * Mp * Bc));
+    KCOUNT(h, 1);
     col_sumsq_kernel<<<dim3(Bc / 128, md.nlta), 128, 0, st>>>(h->d_md, h->LTA, h->Bp, h->varq);
   }
+  KCOUNT(h, 2);  // kuf + a_stats
   a_stats_kernel<<<dim3(Bc / 128, Q), 128, 8 * Mp * sizeof(double), st>>>(h->d_md, params, h->lo, h->A, h->V, h->Bp,
                                                                           h->var0ss, h->mean);
   H_CUDA(h, cudaGetLastError());
@@ -359,15 +403,38 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   if (bound == MOGPE_BOUND_TIGHT && md.G > 1)
     H_FAIL(h, MOGPE_ERR_UNSUPPORTED,
            "tight bound with Softmax gating needs the Monte-Carlo likelihood expectation (not implemented)");
-  if ((bound == MOGPE_BOUND_FURTHER_GATING || bound == MOGPE_BOUND_TIGHT) && !eps_u)
-    H_FAIL(h, MOGPE_ERR_INVALID, "eps_u is required for bound %d", bound);
-  if ((bound == MOGPE_BOUND_FURTHER_GATING || bound == MOGPE_BOUND_FURTHER) && !eps_h)
-    H_FAIL(h, MOGPE_ERR_INVALID, "eps_h is required for bound %d", bound);
-  if (bound == MOGPE_BOUND_FURTHER && !eps_f) H_FAIL(h, MOGPE_ERR_INVALID, "eps_f is required for the further bound");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   H_CUDA(h, cudaSetDevice(h->device));
   mogpe_status rc = set_mode(h, bound, S, st);
   if (rc != MOGPE_OK) return rc;
+  {
+    // draws the caller did not supply come from the library-owned Philox stream
+    const bool need_u = bound == MOGPE_BOUND_FURTHER_GATING || bound == MOGPE_BOUND_TIGHT;
+    const bool need_h = bound == MOGPE_BOUND_FURTHER_GATING || bound == MOGPE_BOUND_FURTHER;
+    const bool need_f = bound == MOGPE_BOUND_FURTHER;
+    auto draw = [&](const double*& eps, bool need, double*& buf, size_t& cap, size_t n) -> mogpe_status {
+      if (eps || !need) return MOGPE_OK;
+      if (n > cap) {
+        if (buf) cudaFree(buf);
+        buf = nullptr;
+        H_CUDA(h, dalloc(&buf, n));
+        cap = n;
+      }
+      const long long pairs = ((long long)n + 1) / 2;
+      fill_normal_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(buf, (long long)n, h->seed, h->rng_counter);
+      KCOUNT(h, 1);
+      h->rng_counter += (n + 1) / 2 * 2;
+      eps = buf;
+      return MOGPE_OK;
+    };
+    const size_t nu = (size_t)md.P * S * h->Mp, nh = (size_t)S * N * md.G, nf = (size_t)S * N * md.Pe;
+    if ((rc = draw(eps_u, need_u, h->eps_u_int, h->eps_u_cap, nu)) != MOGPE_OK) return rc;
+    if ((rc = draw(eps_h, need_h, h->eps_h_int, h->eps_h_cap, nh)) != MOGPE_OK) return rc;
+    if ((rc = draw(eps_f, need_f, h->eps_f_int, h->eps_f_cap, nf)) != MOGPE_OK) return rc;
+    h->last_eps_u = eps_u; h->last_nu = need_u ? (long long)nu : 0;
+    h->last_eps_h = eps_h; h->last_nh = need_h ? (long long)nh : 0;
+    h->last_eps_f = eps_f; h->last_nf = need_f ? (long long)nf : 0;
+  }
   const int Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;  // Bp: leading dimension of every [.., n] buffer
   const int Bc = round_up(N, 128);                       // columns in use this call
   const Layout& lo = h->lo;
@@ -379,6 +446,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   rc = factorise(h, params, st);
   if (rc != MOGPE_OK) return rc;
   make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, st>>>(h->d_md, params, lo, h->Sc, eps_u, S, h->V);
+  KCOUNT(h, 4);  // make_V, lik, kl, finish
   rc = conditional_fwd(h, params, X, N, Bc, st);
   if (rc != MOGPE_OK) return rc;
 
@@ -398,7 +466,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     lik_kernel<<<Bc / blk, blk, smem, st>>>(la);
     H_CUDA(h, cudaGetLastError());
   }
-  kl_kernel<<<P, 256, 0, st>>>(h->d_md, params, lo, out, grads);
+  kl_kernel<<<P, 256, 0, st>>>(h->d_md, params, lo, h->kl_weight, out, grads);
   finish_elbo_kernel<<<1, 1, 0, st>>>(out);
   H_CUDA(h, cudaGetLastError());
   if (!grads) return MOGPE_OK;
@@ -409,6 +477,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   //     => scale LTA in place first (it is also the B operand of Abar += S_l dLTA_l).
   build_abar_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, 0, st>>>(h->d_md, h->A, h->V, h->dmean, h->dfvar, Bp, h->Abar);
   dV_kernel<<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, h->A, h->dmean, Bp, Bc, h->dV);
+  KCOUNT(h, 6);  // build_abar, dV, q_grads, halve_diag, kuu_grad, kuf_grad
   H_CUDA(h, cudaGetLastError());
   if (md.nlta > 0) {
     // Abar[g(l)] += S_l (2 LTA_l diag(dfvar_l))   -- column scaling fused into the B-operand load
@@ -422,7 +491,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
       p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_LOWER;
       p.alpha = 2.0; p.beta = 1.0;
       p.colscale = h->dfvar + (long long)l * Bp;
-      H_CUDA(h, launch_gemm(p, 1, false, false, st));
+      H_CUDA(h, hgemm(h, p, 1, false, false, st, (double)Mp * Mp * Bc));
     }
   }
   {  // W = Linv^T Abar  (= Kuf-bar)
@@ -431,7 +500,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.B = h->Abar; p.sB = (long long)Mp * Bp; p.ldb = Bp;
     p.C = h->W;    p.sC = (long long)Mp * Bp; p.ldc = Bp;
     p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_UPPER;
-    H_CUDA(h, launch_gemm(p, Q, true, false, st));
+    H_CUDA(h, hgemm(h, p, Q, true, false, st, (double)Q * Mp * Mp * Bc));
   }
   {  // Lbar = -tril(W A^T)
     GemmParams p = gp_init();
@@ -439,7 +508,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.B = h->A; p.sB = (long long)Mp * Bp; p.ldb = Bp;
     p.C = h->Lbar; p.sC = (long long)Mp * Mp; p.ldc = Mp;
     p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = -1.0;
-    H_CUDA(h, launch_gemm(p, Q, false, true, st));
+    H_CUDA(h, hgemm(h, p, Q, false, true, st, (double)Q * Mp * Mp * Bc));
   }
   if (md.nlta > 0) {
     // Sbar_l = 2 tril(A_g diag(dfvar_l) LTA_l^T): scale LTA in place (column scaling), then NT GEMM
@@ -451,7 +520,8 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.B = h->LTA; p.sB = (long long)Mp * Bp; p.ldb = Bp;
     p.C = grads + lo.q_sqrt; p.sC = (long long)Mp * Mp; p.ldc = Mp; p.mapC = h->d_lta_latent;
     p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = 2.0; p.beta = 1.0;
-    H_CUDA(h, launch_gemm(p, md.nlta, false, true, st));
+    H_CUDA(h, hgemm(h, p, md.nlta, false, true, st, (double)md.nlta * Mp * Mp * Bc));
+    KCOUNT(h, 1);
   }
   q_grads_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, lo, h->dV, eps_u, S, grads);
   // Cholesky backward: Phi = tril(L^T Lbar) with halved diagonal; Kb = Linv^T Phi Linv (symmetrised in kuu_grad)
@@ -461,7 +531,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.B = h->Lbar; p.sB = (long long)Mp * Mp; p.ldb = Mp;
     p.C = h->T1; p.sC = (long long)Mp * Mp; p.ldc = Mp;
     p.M = Mp; p.N = Mp; p.K = Mp; p.kmode = KM_LEFT_UPPER | KM_RIGHT_LOWER; p.tril_out = 1;
-    H_CUDA(h, launch_gemm(p, Q, true, false, st));
+    H_CUDA(h, hgemm(h, p, Q, true, false, st, (double)Q * Mp * Mp * Mp / 3.0));
     // tril_out skips the strictly-upper tiles: clear them once (T1 upper tiles are never written)
     halve_diag_kernel<<<Q, 256, 0, st>>>(h->T1, Mp);
   }
@@ -471,7 +541,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.B = h->T1; p.sB = (long long)Mp * Mp; p.ldb = Mp;
     p.C = h->T2; p.sC = (long long)Mp * Mp; p.ldc = Mp;
     p.M = Mp; p.N = Mp; p.K = Mp; p.kmode = KM_LEFT_UPPER | KM_RIGHT_LOWER;
-    H_CUDA(h, launch_gemm(p, Q, true, false, st));
+    H_CUDA(h, hgemm(h, p, Q, true, false, st, (double)Q * Mp * Mp * Mp * 2.0 / 3.0));
   }
   {
     GemmParams p = gp_init();
@@ -479,7 +549,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.B = h->Linv; p.sB = (long long)Mp * Mp; p.ldb = Mp;
     p.C = h->Lbar; p.sC = (long long)Mp * Mp; p.ldc = Mp;  // reuse Lbar as Kb
     p.M = Mp; p.N = Mp; p.K = Mp; p.kmode = KM_RIGHT_LOWER;
-    H_CUDA(h, launch_gemm(p, Q, false, false, st));
+    H_CUDA(h, hgemm(h, p, Q, false, false, st, (double)Q * Mp * Mp * Mp));
   }
   kuu_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
   kuf_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
@@ -559,6 +629,7 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
   if (rc != MOGPE_OK) return rc;
   const int Mp = h->Mp;
   make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, st>>>(h->d_md, params, h->lo, h->Sc, nullptr, 1, h->V);
+  KCOUNT(h, 1);
   const int chunk_max = h->desc.max_batch;
   for (int64_t n0 = 0; n0 < N; n0 += chunk_max) {
     const int nc = (int)std::min<int64_t>(chunk_max, N - n0);
@@ -570,6 +641,7 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
     pa.n0 = (int)n0; pa.nchunk = nc; pa.Bp = h->Bp; pa.Ntot = N; pa.eps_mc = eps_mc; pa.num_mc = num_mc;
     pa.f_mean = f_mean; pa.f_var = f_var; pa.mix = mix_probs; pa.y_mean = y_mean; pa.y_var = y_var;
     const int blk = 128;
+    KCOUNT(h, 1);
     predict_out_kernel<<<(nc + blk - 1) / blk, blk, (size_t)2 * md.K * blk * sizeof(double), st>>>(pa);
     H_CUDA(h, cudaGetLastError());
   }
@@ -665,6 +737,50 @@ extern "C" mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_
   return MOGPE_OK;
 }
 
+extern "C" mogpe_status mogpe_set_seed(mogpe_handle* h, uint64_t seed) {
+  if (!h) return MOGPE_ERR_INVALID;
+  h->seed = seed;
+  h->rng_counter = 0;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_set_kl_weight(mogpe_handle* h, double w) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (!(w > 0.0) || w > 1.0) H_FAIL(h, MOGPE_ERR_INVALID, "kl weight must be in (0, 1]");
+  h->kl_weight = w;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_profile_enable(mogpe_handle* h, int32_t on) {
+  if (!h) return MOGPE_ERR_INVALID;
+  h->prof = on != 0;
+  h->ev_used = 0;
+  h->prof_flops = 0;
+  h->gemm_launches = h->all_launches = 0;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, double* gemm_flops,
+                                           int64_t* gemm_launches, int64_t* all_launches) {
+  if (!h) return MOGPE_ERR_INVALID;
+  H_CUDA(h, cudaSetDevice(h->device));
+  H_CUDA(h, cudaStreamSynchronize(h->prof_stream));
+  double ms = 0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float t = 0;
+    H_CUDA(h, cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+    ms += t;
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = h->prof_flops;
+  if (gemm_launches) *gemm_launches = h->gemm_launches;
+  if (all_launches) *all_launches = h->all_launches;
+  h->ev_used = 0;
+  h->prof_flops = 0;
+  h->gemm_launches = h->all_launches = 0;
+  return MOGPE_OK;
+}
+
 // ---- memory helpers -------------------------------------------------------------------------------
 #define G_CUDA(expr)                                                    \
   do {                                                                  \
@@ -746,11 +862,14 @@ extern "C" mogpe_status mogpe_debug_copy(mogpe_handle* h, const char* name, doub
   else if (s == "var0ss") src = h->var0ss, n = Q * Bp;
   else if (s == "varq") src = h->varq, n = P * Bp;
   else if (s == "dfvar") src = h->dfvar, n = P * Bp;
+  else if (s == "eps_u") src = h->last_eps_u, n = h->last_nu;
+  else if (s == "eps_h") src = h->last_eps_h, n = h->last_nh;
+  else if (s == "eps_f") src = h->last_eps_f, n = h->last_nf;
   else H_FAIL(h, MOGPE_ERR_INVALID, "unknown intermediate '%s'", name);
   *n_out = n;
   H_CUDA(h, cudaSetDevice(h->device));
   H_CUDA(h, cudaDeviceSynchronize());
-  if (dst && cap > 0)
+  if (dst && cap > 0 && n > 0 && src)
     H_CUDA(h, cudaMemcpy(dst, src, (size_t)std::min<long long>(cap, n) * sizeof(double), cudaMemcpyDeviceToHost));
   return MOGPE_OK;
 }

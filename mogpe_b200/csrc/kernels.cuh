@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(128) col_sumsq_kernel(const ModelDev* __restri
 // grad convention: gradient of the ELBO (= data term - KL).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kl_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
-                                                 Layout lo, double* __restrict__ out, double* __restrict__ grads) {
+                                                 Layout lo, double klw, double* __restrict__ out, double* __restrict__ grads) {
   __shared__ double red[8];
   const int l = blockIdx.x, Mp = md->Mp, Mg = md->group_M[md->latent_group[l]];
   const double* qm = params + lo.q_mu + (long long)l * Mp;
@@ -330,14 +330,14 @@ __global__ void __launch_bounds__(256) kl_kernel(const ModelDev* __restrict__ md
   double acc = 0;
   for (int m = threadIdx.x; m < Mg; m += 256) {
     acc += qm[m] * qm[m] - 1.0 - log(S[(long long)m * Mp + m] * S[(long long)m * Mp + m]);
-    if (grads) grads[lo.q_mu + (long long)l * Mp + m] -= qm[m];
+    if (grads) grads[lo.q_mu + (long long)l * Mp + m] -= klw * qm[m];
   }
   for (long long t = threadIdx.x; t < (long long)Mg * Mg; t += 256) {
     const int i = t / Mg, j = t % Mg;
     if (j <= i) {
       const double s = S[(long long)i * Mp + j];
       acc += s * s;
-      if (grads) grads[lo.q_sqrt + ((long long)l * Mp + i) * Mp + j] -= (i == j) ? (s - 1.0 / s) : s;
+      if (grads) grads[lo.q_sqrt + ((long long)l * Mp + i) * Mp + j] -= klw * ((i == j) ? (s - 1.0 / s) : s);
     }
   }
   acc = warp_sum(acc);
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256) kl_kernel(const ModelDev* __restrict__ md
   if (threadIdx.x == 0) {
     double s = 0;
     for (int w = 0; w < 8; w++) s += red[w];
-    atomicAdd(out + (l >= md->Pe ? 2 : 3), 0.5 * s);
+    atomicAdd(out + (l >= md->Pe ? 2 : 3), 0.5 * klw * s);
   }
 }
 

@@ -100,8 +100,10 @@ class Engine:
         self.lo = lo
         self.Mp = lo.Mp
         self.params = DeviceBuffer((lo.total,), device)
-        self.grads = DeviceBuffer((lo.total,), device)
-        self.out = DeviceBuffer((4,), device)
+        # gradients and the 4 result scalars share one buffer so data-parallel ranks sum both in ONE all-reduce
+        self.gbuf = DeviceBuffer((lo.total + 4,), device)
+        self.grads_ptr = self.gbuf.ptr
+        self.out_ptr = self.gbuf.ptr + lo.total * 8
         self._eps_cache = {}
         self.set_params(experts, gating)
 
@@ -206,8 +208,10 @@ class Engine:
 
     # ---- the hot path ----------------------------------------------------------------------------------
     def elbo(self, X, Y, bound="further_gating", num_samples=1, scale=1.0, eps_u=None, eps_h=None, eps_f=None,
-             want_grads=True, unpack=True, stream=None) -> ElboResult:
-        """eps_u [P, S, Mp], eps_h [S, N, G], eps_f [S, N, K*F] (already in library layout)."""
+             want_grads=True, unpack=True, readback=True, stream=None) -> ElboResult:
+        """eps_u [P, S, Mp], eps_h [S, N, G], eps_f [S, N, K*F] (already in library layout); any eps left None
+        is drawn by the library's own Philox stream.  readback=False (device inputs only) leaves the result
+        in self.gbuf and returns None without synchronising."""
         xv, yv = as_view(X), as_view(Y)
         N = int(xv.shape[0])
         if len(xv.shape) != 2 or xv.shape[1] != self.D:
@@ -215,7 +219,7 @@ class Engine:
         if tuple(yv.shape) != (N, self.F):
             raise ValueError(f"Y must be [{N}, {self.F}], got {tuple(yv.shape)}")
         b = _lib.BOUND_IDS[bound]
-        gptr = self.grads.ptr if want_grads else None
+        gptr = self.grads_ptr if want_grads else None
         host_path = (not xv.on_device) and (not yv.on_device) and all(
             e is None or not as_view(e).on_device for e in (eps_u, eps_h, eps_f))
         if host_path:
@@ -233,13 +237,15 @@ class Engine:
                 keep.append(k)
             _lib.check(self.lib.mogpe_elbo_fwd_bwd(
                 self.h, ptrs[0], ptrs[1], N, self.params.ptr, ptrs[2], ptrs[3], ptrs[4],
-                b, num_samples, float(scale), self.out.ptr, gptr, stream), self.h)
-            out = self.out.numpy()
+                b, num_samples, float(scale), self.out_ptr, gptr, stream), self.h)
+            out = self.gbuf.numpy(offset=self.lo.total, count=4) if readback else None
+        if out is None:
+            return None
         res = ElboResult(*[float(v) for v in out])
         if want_grads:
-            res.flat_grads = self.grads
+            res.flat_grads = self.gbuf
             if unpack:
-                res.experts, res.gating = self.unpack_grads(self.grads.numpy())
+                res.experts, res.gating = self.unpack_grads(self.gbuf.numpy(count=self.lo.total))
         return res
 
     def predict(self, X, want=("f_mean", "f_var", "mix_probs", "y_mean", "y_var"), eps_mc=None, stream=None):
@@ -263,6 +269,35 @@ class Engine:
         args = [bufs[k].ptr if k in bufs else None for k in ("f_mean", "f_var", "mix_probs", "y_mean", "y_var")]
         _lib.check(self.lib.mogpe_predict(self.h, xp, N, self.params.ptr, *args, mp, num_mc, stream), self.h)
         return {k: b.numpy() for k, b in bufs.items()}
+
+    # ---- random stream / data parallel / measurement hooks ------------------------------------------------
+    def set_seed(self, seed: int):
+        _lib.check(self.lib.mogpe_set_seed(self.h, int(seed)), self.h)
+
+    def init_data_parallel(self, rank: int, world_size: int, unique_id: bytes):
+        """Join an NCCL communicator (id from Engine.nccl_unique_id() on rank 0, distributed by the caller) and
+        weight the redundantly computed KL terms by 1/world_size so that the all-reduced sums are exact."""
+        _lib.check(self.lib.mogpe_comm_init(self.h, unique_id, rank, world_size), self.h)
+        _lib.check(self.lib.mogpe_set_kl_weight(self.h, 1.0 / world_size), self.h)
+        self.world_size = world_size
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().mogpe_nccl_unique_id(buf))
+        return buf.raw
+
+    def allreduce(self, buf: DeviceBuffer, count=None, stream=None):
+        _lib.check(self.lib.mogpe_allreduce_sum(self.h, buf.ptr, buf.size if count is None else count, stream), self.h)
+
+    def profile(self, on=True):
+        _lib.check(self.lib.mogpe_profile_enable(self.h, 1 if on else 0), self.h)
+
+    def profile_read(self):
+        ms, fl = C.c_double(), C.c_double()
+        ng, na = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.mogpe_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(ng), C.byref(na)), self.h)
+        return {"gemm_ms": ms.value, "gemm_flops": fl.value, "gemm_launches": ng.value, "all_launches": na.value}
 
     def debug(self, name):
         n = C.c_int64()
