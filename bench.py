@@ -62,7 +62,7 @@ def synth_model(wl, seed=3):
         return d
 
     experts = [gp(F, F if wl["sep"] else 1, True) for _ in range(K)]
-    gating = gp(G, 1, False)
+    gating = gp(G, G, False)  # G separate gating kernels + shared Z ("3 RBF kernels, shared Z")
     return {"flavour": FLAVOUR, "bound": BOUND, "num_samples": S, "num_data": wl["num_data"],
             "experts": experts, "gating": gating}
 

@@ -176,10 +176,13 @@ mogpe_status mogpe_debug_copy(mogpe_handle* h, const char* name, double* dst_hos
 
 /* Test hook: batched FP64 GEMM on the library's DMMA kernel, C = alpha*op(A)*op(B) + beta*C (row-major,
  * device pointers, dims multiples of 64).  kmode: bit0 left-lower, bit1 left-upper, bit2 right-lower,
- * bit3 right-upper (restricts the k range per tile); tril_out: only lower-triangular tiles are produced. */
+ * bit3 right-upper (restricts the k range per tile); tril_out: only lower-triangular tiles are produced;
+ * cfg: tile configuration id (-1 = automatic). */
 mogpe_status mogpe_debug_gemm(int32_t device, const double* A, const double* B, double* C, int32_t batch,
                               int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, int32_t kmode,
-                              int32_t tril_out, double alpha, double beta, void* cuda_stream);
+                              int32_t tril_out, double alpha, double beta, int32_t cfg, void* cuda_stream);
+/* Test/tuning hook: force a GEMM tile configuration for all later launches (-1 = automatic). */
+mogpe_status mogpe_debug_set_gemm_cfg(int32_t cfg);
 
 const char* mogpe_version(void);
 

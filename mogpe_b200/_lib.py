@@ -68,7 +68,8 @@ _PROTOS = {
     "mogpe_stream_sync": (C.c_int, [C.c_int32, _P]),
     "mogpe_debug_copy": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "mogpe_debug_gemm": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _P]),
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _P]),
+    "mogpe_debug_set_gemm_cfg": (C.c_int, [C.c_int32]),
     "mogpe_version": (C.c_char_p, []),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)

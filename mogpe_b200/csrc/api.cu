@@ -5,6 +5,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,6 +43,10 @@ struct mogpe_handle {
   double *var0ss = nullptr, *varq = nullptr, *dfvar = nullptr;     // [Q|P][Bp]
   int NVcap = 0;
   int *d_lta_latent = nullptr, *d_lta_group = nullptr, *d_latent_group = nullptr;
+  // rounds of the Abar accumulation: round r holds the r-th marginal latent of every group
+  int *d_round_latent = nullptr, *d_round_slot = nullptr, *d_round_group = nullptr;  // [MAXP rounds][MAXP]
+  int n_rounds = 0;
+  int round_count[MAXP] = {0};
   // host-entry staging
   double *stage_dev = nullptr, *stage_host = nullptr, *out_dev = nullptr, *out_host_pinned = nullptr;
   size_t stage_cap = 0;
@@ -101,6 +107,9 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_lta_latent) cudaFree(h->d_lta_latent);
   if (h->d_lta_group) cudaFree(h->d_lta_group);
   if (h->d_latent_group) cudaFree(h->d_latent_group);
+  if (h->d_round_latent) cudaFree(h->d_round_latent);
+  if (h->d_round_slot) cudaFree(h->d_round_slot);
+  if (h->d_round_group) cudaFree(h->d_round_group);
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
   for (auto e : h->ev) cudaEventDestroy(e);
@@ -201,11 +210,16 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (e == cudaSuccess) e = dalloc(&h->d_lta_latent, (size_t)MAXP);
   if (e == cudaSuccess) e = dalloc(&h->d_lta_group, (size_t)MAXP);
   if (e == cudaSuccess) e = dalloc(&h->d_latent_group, (size_t)MAXP);
+  if (e == cudaSuccess) e = dalloc(&h->d_round_latent, (size_t)MAXP * MAXP);
+  if (e == cudaSuccess) e = dalloc(&h->d_round_slot, (size_t)MAXP * MAXP);
+  if (e == cudaSuccess) e = dalloc(&h->d_round_group, (size_t)MAXP * MAXP);
   if (e == cudaSuccess) e = dalloc(&h->out_dev, 8);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->out_host_pinned, 8 * sizeof(double));
   if (e == cudaSuccess)
     e = cudaMemcpy(h->d_latent_group, md.latent_group, sizeof(int) * MAXP, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(h->varq, 0, (size_t)P * h->Bp * sizeof(double));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(chol_inv_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM_BYTES);
   if (e == cudaSuccess && 8 * Mp * sizeof(double) > 48 * 1024)
     e = cudaFuncSetAttribute(a_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * Mp * sizeof(double)));
   if (e != cudaSuccess) {
@@ -301,6 +315,22 @@ static mogpe_status set_mode(mogpe_handle* h, int bound, int S, cudaStream_t st)
   H_CUDA(h, cudaMemcpy(h->d_md, &md, sizeof(ModelDev), cudaMemcpyHostToDevice));
   H_CUDA(h, cudaMemcpy(h->d_lta_latent, md.lta_latent, sizeof(int) * MAXP, cudaMemcpyHostToDevice));
   H_CUDA(h, cudaMemcpy(h->d_lta_group, md.lta_group, sizeof(int) * MAXP, cudaMemcpyHostToDevice));
+  {
+    std::vector<int> rl(MAXP * MAXP, 0), rs(MAXP * MAXP, 0), rg(MAXP * MAXP, 0), seen(MAXQ, 0);
+    h->n_rounds = 0;
+    for (int r = 0; r < MAXP; r++) h->round_count[r] = 0;
+    for (int slot = 0; slot < md.nlta; slot++) {
+      const int l = md.lta_latent[slot], g = md.latent_group[l], r = seen[g]++;
+      const int pos = h->round_count[r]++;
+      rl[r * MAXP + pos] = l;
+      rs[r * MAXP + pos] = slot;
+      rg[r * MAXP + pos] = g;
+      h->n_rounds = std::max(h->n_rounds, r + 1);
+    }
+    H_CUDA(h, cudaMemcpy(h->d_round_latent, rl.data(), sizeof(int) * MAXP * MAXP, cudaMemcpyHostToDevice));
+    H_CUDA(h, cudaMemcpy(h->d_round_slot, rs.data(), sizeof(int) * MAXP * MAXP, cudaMemcpyHostToDevice));
+    H_CUDA(h, cudaMemcpy(h->d_round_group, rg.data(), sizeof(int) * MAXP * MAXP, cudaMemcpyHostToDevice));
+  }
   h->cur_bound = bound;
   h->cur_S = S;
   return MOGPE_OK;
@@ -334,6 +364,7 @@ static cudaError_t hgemm(mogpe_handle* h, const GemmParams& p, int batch, bool t
   cudaEventRecord(h->ev[h->ev_used + 1], st);
   h->ev_used += 2;
   h->prof_flops += flops;
+  if (getenv("MOGPE_DEBUG_PROF")) fprintf(stderr, "gemm M=%d N=%d K=%d batch=%d ta=%d tb=%d kmode=%d tril=%d flops=%.4g\n", p.M, p.N, p.K, batch, ta, tb, p.kmode, p.tril_out, flops);
   return rc;
 }
 #define KCOUNT(h, n) ((h)->all_launches += (n))
@@ -343,10 +374,9 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, cudaStream_
   const int Q = h->md_host.Q, P = h->md_host.P, Mp = h->Mp;
   kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
   for (int j = 0; j < Mp / 32; j++)
-    chol_step_kernel<<<dim3(Mp / 32 - j, Q), 256, 0, st>>>(h->Kuu, h->L, Mp, j);
-  trinv_kernel<<<dim3(Mp / 32, Q), 256, 0, st>>>(h->L, h->Linv, Mp);
+    chol_inv_step_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, j);
   prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->Sc);
-  KCOUNT(h, 3 + Mp / 32);
+  KCOUNT(h, 2 + Mp / 32);
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
 }
@@ -466,7 +496,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     lik_kernel<<<Bc / blk, blk, smem, st>>>(la);
     H_CUDA(h, cudaGetLastError());
   }
-  kl_kernel<<<P, 256, 0, st>>>(h->d_md, params, lo, h->kl_weight, out, grads);
+  kl_kernel<<<dim3(Mp / 8, P), 256, 0, st>>>(h->d_md, params, lo, h->kl_weight, out, grads);
   finish_elbo_kernel<<<1, 1, 0, st>>>(out);
   H_CUDA(h, cudaGetLastError());
   if (!grads) return MOGPE_OK;
@@ -476,22 +506,24 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   //     epilogue via alpha and into the B operand... done as: Sbar_l = 2 * tril(A_g diag(dfvar_l) LTA_l^T)
   //     => scale LTA in place first (it is also the B operand of Abar += S_l dLTA_l).
   build_abar_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, 0, st>>>(h->d_md, h->A, h->V, h->dmean, h->dfvar, Bp, h->Abar);
-  dV_kernel<<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, h->A, h->dmean, Bp, Bc, h->dV);
+  H_CUDA(h, cudaMemsetAsync(h->dV, 0, (size_t)md.NV * Mp * sizeof(double), st));
+  dV_kernel<<<dim3((Bc + 1023) / 1024, Mp / 32, Q), 256, 0, st>>>(h->d_md, h->A, h->dmean, Bp, Bc, h->dV);
   KCOUNT(h, 6);  // build_abar, dV, q_grads, halve_diag, kuu_grad, kuf_grad
   H_CUDA(h, cudaGetLastError());
   if (md.nlta > 0) {
-    // Abar[g(l)] += S_l (2 LTA_l diag(dfvar_l))   -- column scaling fused into the B-operand load
-    // latents of one group are accumulated one launch at a time (C is read-modify-write)
-    for (int slot = 0; slot < md.nlta; slot++) {
-      const int l = md.lta_latent[slot], g = md.latent_group[l];
+    // Abar[g(l)] += S_l (2 LTA_l diag(dfvar_l))   -- column scaling fused into the B-operand load.
+    // C is read-modify-write, so latents sharing a group go in successive rounds; each round is one batched
+    // launch over the groups that still have a marginal latent left.
+    for (int round = 0; round < h->n_rounds; round++) {
+      const int nb = h->round_count[round];
       GemmParams p = gp_init();
-      p.A = h->Sc + (long long)l * Mp * Mp; p.lda = Mp;
-      p.B = h->LTA + (long long)slot * Mp * Bp; p.ldb = Bp;
-      p.C = h->Abar + (long long)g * Mp * Bp; p.ldc = Bp;
+      p.A = h->Sc;    p.sA = (long long)Mp * Mp; p.lda = Mp; p.mapA = h->d_round_latent + round * MAXP;
+      p.B = h->LTA;   p.sB = (long long)Mp * Bp; p.ldb = Bp; p.mapB = h->d_round_slot + round * MAXP;
+      p.C = h->Abar;  p.sC = (long long)Mp * Bp; p.ldc = Bp; p.mapC = h->d_round_group + round * MAXP;
       p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_LOWER;
       p.alpha = 2.0; p.beta = 1.0;
-      p.colscale = h->dfvar + (long long)l * Bp;
-      H_CUDA(h, hgemm(h, p, 1, false, false, st, (double)Mp * Mp * Bc));
+      p.colscale = h->dfvar; p.scs = Bp; p.mapS = h->d_round_latent + round * MAXP;
+      H_CUDA(h, hgemm(h, p, nb, false, false, st, (double)nb * Mp * Mp * Bc));
     }
   }
   {  // W = Linv^T Abar  (= Kuf-bar)
@@ -874,15 +906,21 @@ extern "C" mogpe_status mogpe_debug_copy(mogpe_handle* h, const char* name, doub
   return MOGPE_OK;
 }
 
+extern "C" mogpe_status mogpe_debug_set_gemm_cfg(int32_t cfg) {
+  gemm_cfg_override() = cfg;
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_debug_gemm(int32_t device, const double* A, const double* B, double* C, int32_t batch,
                                          int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,
-                                         int32_t kmode, int32_t tril_out, double alpha, double beta, void* st) {
+                                         int32_t kmode, int32_t tril_out, double alpha, double beta, int32_t cfg,
+                                         void* st) {
   G_CUDA(cudaSetDevice(device));
   GemmParams p = gp_init();
   p.A = A; p.sA = (long long)M * K; p.lda = transA ? M : K;
   p.B = B; p.sB = (long long)K * N; p.ldb = transB ? K : N;
   p.C = C; p.sC = (long long)M * N; p.ldc = N;
   p.M = M; p.N = N; p.K = K; p.kmode = kmode; p.tril_out = tril_out; p.alpha = alpha; p.beta = beta;
-  G_CUDA(launch_gemm(p, batch, transA != 0, transB != 0, (cudaStream_t)st));
+  G_CUDA(launch_gemm(p, batch, transA != 0, transB != 0, (cudaStream_t)st, cfg));
   return MOGPE_OK;
 }

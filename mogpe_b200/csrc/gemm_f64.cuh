@@ -72,10 +72,40 @@ struct GemmCfg {
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
 };
 
+// One k-tile (BK deep) of MMAs for row-fragment range [I0, I1) of this warp.  TRIL: compile-time pattern
+// "quarter(j) <= quarter(i)" used on the diagonal tiles of a lower-triangular RESULT.  Everything is a
+// compile-time constant, so the DMMA stream has no predicates and ptxas can software-pipeline the LDS.
+template <class Cfg, int BK, bool TA, bool TB, int I0, int I1, bool TRIL>
+__device__ __forceinline__ void mma_ktile(const double* __restrict__ As, const double* __restrict__ Bs,
+                                          double (&acc)[Cfg::MI][Cfg::NI][2], const double (&cs)[Cfg::NI], int wr,
+                                          int wc, int lr, int lc) {
+#pragma unroll
+  for (int kk = 0; kk < BK / 4; kk++) {
+    double af[Cfg::MI], bf[Cfg::NI];
+    const int k = kk * 4 + lc;
+#pragma unroll
+    for (int i = I0; i < I1; i++) {
+      const int m = (i * Cfg::WARPS_M + wr) * 8 + lr;
+      af[i] = TA ? As[k * Cfg::A_LD + m] : As[m * Cfg::A_LD + k];
+    }
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; j++) {
+      const int n = (j * Cfg::WARPS_N + wc) * 8 + lr;
+      bf[j] = (TB ? Bs[n * Cfg::B_LD + k] : Bs[k * Cfg::B_LD + n]) * cs[j];
+    }
+#pragma unroll
+    for (int i = I0; i < I1; i++)
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; j++)
+        if (!TRIL || (j / (Cfg::NI / 4)) <= (i / (Cfg::MI / 4))) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+}
+
 template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::THREADS)
     gemm_dmma_kernel(const GemmParams p) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>;
+  static_assert(Cfg::MI % 4 == 0 && Cfg::NI % 4 == 0, "fragment quarters");
   extern __shared__ __align__(16) double smem[];
 
   const int batch = blockIdx.z;
@@ -109,8 +139,11 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int wm0 = (warp / Cfg::WARPS_N) * WM;
-  const int wn0 = (warp % Cfg::WARPS_N) * WN;
+  // 8-row / 8-column fragments are INTERLEAVED across the warp grid: fragment i of warp-row wr covers tile rows
+  // (i*WARPS_M + wr)*8 .. +7, so fragment quarter q = [q*MI/4, (q+1)*MI/4) covers tile rows [q*BM/4, (q+1)*BM/4)
+  // for EVERY warp.  Skipping the quarters that lie in the zero half of a triangular operand (or above the
+  // diagonal of a triangular result) then shortens all warps equally instead of idling half of them.
+  const int wr = warp / Cfg::WARPS_N, wc = warp % Cfg::WARPS_N;
   const int lr = lane >> 2, lc = lane & 3;
 
   double acc[Cfg::MI][Cfg::NI][2];
@@ -146,7 +179,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
   for (int j = 0; j < Cfg::NI; j++) cs[j] = 1.0;
   if (Sb) {
 #pragma unroll
-    for (int j = 0; j < Cfg::NI; j++) cs[j] = TB ? 1.0 : Sb[col0 + wn0 + j * 8 + lr];
+    for (int j = 0; j < Cfg::NI; j++) cs[j] = TB ? 1.0 : Sb[col0 + (j * Cfg::WARPS_N + wc) * 8 + lr];
   }
 
 #pragma unroll
@@ -155,6 +188,10 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
     cp_async_commit();
   }
 
+  const bool left_lower = p.kmode & KM_LEFT_LOWER, left_upper = p.kmode & KM_LEFT_UPPER;
+  const bool tril_diag = p.tril_out && row0 == col0 && BM == BN;
+  constexpr int QR = BM / 4;  // rows per fragment quarter
+  constexpr int Q1 = Cfg::MI / 4, Q2 = Cfg::MI / 2, Q3 = 3 * Cfg::MI / 4, Q4 = Cfg::MI;
   for (int kt = 0; kt < nk; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
@@ -165,24 +202,27 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
     }
     const double* As = smem + (kt % STAGES) * Cfg::STAGE_ELEMS;
     const double* Bs = As + Cfg::A_ELEMS;
-#pragma unroll
-    for (int kk = 0; kk < BK / 4; kk++) {
-      double af[Cfg::MI], bf[Cfg::NI];
-      const int k = kk * 4 + lc;
-#pragma unroll
-      for (int i = 0; i < Cfg::MI; i++) {
-        const int m = wm0 + i * 8 + lr;
-        af[i] = TA ? As[k * Cfg::A_LD + m] : As[m * Cfg::A_LD + k];
-      }
-#pragma unroll
-      for (int j = 0; j < Cfg::NI; j++) {
-        const int n = wn0 + j * 8 + lr;
-        bf[j] = (TB ? Bs[n * Cfg::B_LD + k] : Bs[k * Cfg::B_LD + n]) * cs[j];
-      }
-#pragma unroll
-      for (int i = 0; i < Cfg::MI; i++)
-#pragma unroll
-        for (int j = 0; j < Cfg::NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    // quarters [q0, q1) of the row fragments that can hold non-zeros of the left operand in this k-tile
+    const int d = k_begin + kt * BK - row0;  // k-tile start relative to the tile's first row
+    int q0 = 0, q1 = 4;
+    if (left_lower && d > 0) q0 = min(3, d / QR);                  // A(m,k) = 0 for k > m
+    if (left_upper) q1 = max(1, min(4, (d + BK - 1) / QR + 1));    // A(m,k) = 0 for k < m
+    if (tril_diag) {
+      mma_ktile<Cfg, BK, TA, TB, 0, Q4, true>(As, Bs, acc, cs, wr, wc, lr, lc);
+    } else if (q0 == 0 && q1 == 4) {
+      mma_ktile<Cfg, BK, TA, TB, 0, Q4, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+    } else if (q0 == 1) {
+      mma_ktile<Cfg, BK, TA, TB, Q1, Q4, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+    } else if (q0 == 2) {
+      mma_ktile<Cfg, BK, TA, TB, Q2, Q4, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+    } else if (q0 == 3) {
+      mma_ktile<Cfg, BK, TA, TB, Q3, Q4, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+    } else if (q1 == 1) {
+      mma_ktile<Cfg, BK, TA, TB, 0, Q1, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+    } else if (q1 == 2) {
+      mma_ktile<Cfg, BK, TA, TB, 0, Q2, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+    } else {
+      mma_ktile<Cfg, BK, TA, TB, 0, Q3, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     }
   }
   cp_async_wait<0>();
@@ -190,10 +230,10 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
   // epilogue: thread owns (row = lr, cols = 2*lc, 2*lc+1) of each 8x8 fragment
 #pragma unroll
   for (int i = 0; i < Cfg::MI; i++) {
-    const int r = row0 + wm0 + i * 8 + lr;
+    const int r = row0 + (i * Cfg::WARPS_M + wr) * 8 + lr;
 #pragma unroll
     for (int j = 0; j < Cfg::NI; j++) {
-      const int c = col0 + wn0 + j * 8 + lc * 2;
+      const int c = col0 + (j * Cfg::WARPS_N + wc) * 8 + lc * 2;
       double2* dst = reinterpret_cast<double2*>(Cb + (long long)r * p.ldc + c);
       double2 v;
       v.x = p.alpha * acc[i][j][0];
@@ -228,21 +268,38 @@ inline cudaError_t launch_gemm_cfg(const GemmParams& p, int batch, cudaStream_t 
   return cudaGetLastError();
 }
 
+// Tile configurations (BM, BN, BK, WM, WN, stages).  cfg < 0: automatic choice.
+inline int& gemm_cfg_override() {
+  static int v = -1;
+  return v;
+}
+
 template <bool TA, bool TB>
-inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st) {
-  // large tile when the problem fills the machine with 128x128 tiles, else 64x64
-  const bool big = (p.M % 128 == 0) && (p.N % 128 == 0) &&
-                   ((long long)(p.M / 128) * (p.N / 128) * batch >= 296 || p.tril_out == 0 && p.N >= 2048);
-  if (big) return launch_gemm_cfg<128, 128, 16, 64, 32, TA, TB, 3>(p, batch, st);
+inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st, int cfg) {
+  if (cfg < 0) cfg = gemm_cfg_override();
+  if (cfg < 0) {
+    // measured on B200 (tools/gemm_bench.py, profiles/gemm_sweep_r01.txt): 64x128 tiles (2 CTAs/SM, 16 warps)
+    // are fastest for the [M x M] x [M x B] products, 64x64 for triangular results and M^3 products
+    cfg = (!p.tril_out && p.N % 128 == 0 && p.N >= 1024) ? 2 : 1;
+  }
+  const bool ok128 = (p.M % 128 == 0) && (p.N % 128 == 0);
+  switch (cfg) {
+    case 0: if (ok128) return launch_gemm_cfg<128, 128, 16, 64, 32, TA, TB, 3>(p, batch, st); break;
+    case 2: if (p.N % 128 == 0) return launch_gemm_cfg<64, 128, 16, 32, 32, TA, TB, 4>(p, batch, st); break;
+    case 3: if (p.M % 128 == 0) return launch_gemm_cfg<128, 64, 16, 32, 32, TA, TB, 4>(p, batch, st); break;
+    case 4: if (ok128) return launch_gemm_cfg<128, 128, 16, 32, 32, TA, TB, 3>(p, batch, st); break;
+    case 5: if (ok128) return launch_gemm_cfg<128, 128, 16, 64, 32, TA, TB, 4>(p, batch, st); break;
+    default: break;
+  }
   return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 4>(p, batch, st);
 }
 
-inline cudaError_t launch_gemm(const GemmParams& p, int batch, bool ta, bool tb, cudaStream_t st) {
+inline cudaError_t launch_gemm(const GemmParams& p, int batch, bool ta, bool tb, cudaStream_t st, int cfg = -1) {
   if (p.M % 64 || p.N % 64 || p.K % 16) return cudaErrorInvalidValue;
-  if (!ta && !tb) return launch_gemm_t<false, false>(p, batch, st);
-  if (ta && !tb) return launch_gemm_t<true, false>(p, batch, st);
-  if (!ta && tb) return launch_gemm_t<false, true>(p, batch, st);
-  return launch_gemm_t<true, true>(p, batch, st);
+  if (!ta && !tb) return launch_gemm_t<false, false>(p, batch, st, cfg);
+  if (ta && !tb) return launch_gemm_t<true, false>(p, batch, st, cfg);
+  if (!ta && tb) return launch_gemm_t<false, true>(p, batch, st, cfg);
+  return launch_gemm_t<true, true>(p, batch, st, cfg);
 }
 
 }  // namespace mogpe

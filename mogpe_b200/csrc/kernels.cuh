@@ -92,139 +92,157 @@ __global__ void kuf_kernel(const ModelDev* __restrict__ md, const double* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// Blocked left-looking Cholesky, one launch per 32-wide block column j.
-// CTA (i - j, g) produces L[i-block, j-block]; every CTA recomputes the (cheap) diagonal factor.
-// Reads Kuu, writes L (separate buffers: no read/write race on the diagonal block).
-// grid (Mp/32 - j, Q), block 256.
+// Blocked left-looking Cholesky FUSED with the triangular inverse, one launch per 32-wide block column j.
+// Per group, Mp/32 CTAs:
+//   b <  j : Linv[j, b] = -Ljj^-1 sum_{k=b}^{j-1} L[j,k] Linv[k,b]      (row block j of L^-1 is complete now)
+//   b == j : L[j,j] = chol(D),  Linv[j,j] = Ljj^-1
+//   b >  j : L[b, j] = (Kuu[b,j] - sum_{k<j} L[b,k] L[j,k]^T) Ljj^-T
+// with D = Kuu[j,j] - sum_{k<j} L[j,k] L[j,k]^T recomputed by every CTA (cheap, avoids a second launch).
+// The explicit inverse turns every later triangular solve into a DMMA GEMM.
+// Reads Kuu, writes L / Linv (separate buffers: no read/write race on the diagonal block).
+// grid (Mp/32, Q), block 256.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) chol_step_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
-                                                         int Mp, int j) {
-  __shared__ double Li[32][33], Lj[32][33], Dg[32][33], Cg[32][33];
-  const int g = blockIdx.y, i = j + blockIdx.x;
+constexpr int CHOL_CH = 64;  // k-chunk of the block products
+constexpr size_t CHOL_SMEM_BYTES = (32 * (CHOL_CH + 1) + CHOL_CH * 33 + 2 * 32 * 33) * sizeof(double);
+static_assert(CHOL_CH * 33 >= 32 * (CHOL_CH + 1), "Pb must fit in the Pc region");
+
+// In-place Cholesky of a 32x32 block in shared memory by 256 threads (lower triangle valid on exit).
+__device__ __forceinline__ void chol32_smem(double (*Dg)[33], int tid) {
+  for (int c = 0; c < 32; c++) {
+    __syncthreads();
+    const double d = sqrt(Dg[c][c]);
+    __syncthreads();
+    if (tid == 0) Dg[c][c] = d;
+    if (tid > c && tid < 32) Dg[tid][c] /= d;
+    __syncthreads();
+    // trailing update: element (r, cc), c < cc <= r < 32
+    for (int t = tid; t < 1024; t += 256) {
+      const int r = t >> 5, cc = t & 31;
+      if (cc > c && cc <= r) Dg[r][cc] -= Dg[r][c] * Dg[cc][c];
+    }
+  }
+  __syncthreads();
+}
+
+// Solve T x = b for 32 right-hand sides held as columns of Rb (in place), T lower-triangular 32x32 in smem.
+// 256 threads = 32 columns x 8 lanes; the dot product over earlier rows is split over the 8 lanes.
+__device__ __forceinline__ void trsm32_lower_cols(const double (*T)[33], double (*Rb)[33], int tid) {
+  const int c = tid >> 3, sub = tid & 7;
+  for (int r = 0; r < 32; r++) {
+    double s = 0;
+    for (int t = sub; t < r; t += 8) s += T[r][t] * Rb[t][c];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    __syncthreads();
+    if (sub == 0) Rb[r][c] = (Rb[r][c] - s) / T[r][r];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) chol_inv_step_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
+                                                             double* __restrict__ Linv, int Mp, int j) {
+  // dynamic smem (CHOL_SMEM_BYTES): Pa | Pb/Pc (never live together) | Dg | Cg
+  extern __shared__ double chol_smem[];
+  double(*Pa)[CHOL_CH + 1] = reinterpret_cast<double(*)[CHOL_CH + 1]>(chol_smem);
+  double(*Pb)[CHOL_CH + 1] = reinterpret_cast<double(*)[CHOL_CH + 1]>(chol_smem + 32 * (CHOL_CH + 1));
+  double(*Pc)[33] = reinterpret_cast<double(*)[33]>(chol_smem + 32 * (CHOL_CH + 1));  // Linv[k, b] chunk (k rows)
+  double(*Dg)[33] = reinterpret_cast<double(*)[33]>(chol_smem + 32 * (CHOL_CH + 1) + CHOL_CH * 33);
+  double(*Cg)[33] = Dg + 32;
+  const int g = blockIdx.y, b = blockIdx.x;
   const double* Kg = Kuu + (long long)g * Mp * Mp;
   double* Lg = L + (long long)g * Mp * Mp;
+  double* Xg = Linv + (long long)g * Mp * Mp;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double accC[2][2] = {{0, 0}, {0, 0}}, accD[2][2] = {{0, 0}, {0, 0}};
-  for (int kc = 0; kc < j; kc++) {
-    for (int t = tid; t < 1024; t += 256) {
-      const int r = t >> 5, c = t & 31;
-      Li[r][c] = Lg[(long long)(i * 32 + r) * Mp + kc * 32 + c];
-      Lj[r][c] = Lg[(long long)(j * 32 + r) * Mp + kc * 32 + c];
+  const int kend = j * 32;
+  // ---- D (all CTAs) and C (b > j): products over k < j*32 of rows of L
+  for (int k0 = 0; k0 < kend; k0 += CHOL_CH) {
+    const int kw = min(CHOL_CH, kend - k0);
+    for (int t = tid; t < 32 * CHOL_CH; t += 256) {
+      const int r = t / CHOL_CH, c = t % CHOL_CH;
+      const bool in = c < kw;
+      Pa[r][c] = in ? Lg[(long long)(j * 32 + r) * Mp + k0 + c] : 0.0;
+      if (b > j) Pb[r][c] = in ? Lg[(long long)(b * 32 + r) * Mp + k0 + c] : 0.0;
     }
     __syncthreads();
 #pragma unroll 8
-    for (int k = 0; k < 32; k++) {
-      const double a0 = Li[ty * 2][k], a1 = Li[ty * 2 + 1][k];
-      const double d0 = Lj[ty * 2][k], d1 = Lj[ty * 2 + 1][k];
-      const double b0 = Lj[tx * 2][k], b1 = Lj[tx * 2 + 1][k];
-      accC[0][0] += a0 * b0; accC[0][1] += a0 * b1; accC[1][0] += a1 * b0; accC[1][1] += a1 * b1;
+    for (int k = 0; k < CHOL_CH; k++) {
+      const double d0 = Pa[ty * 2][k], d1 = Pa[ty * 2 + 1][k];
+      const double b0 = Pa[tx * 2][k], b1 = Pa[tx * 2 + 1][k];
       accD[0][0] += d0 * b0; accD[0][1] += d0 * b1; accD[1][0] += d1 * b0; accD[1][1] += d1 * b1;
+      if (b > j) {
+        const double a0 = Pb[ty * 2][k], a1 = Pb[ty * 2 + 1][k];
+        accC[0][0] += a0 * b0; accC[0][1] += a0 * b1; accC[1][0] += a1 * b0; accC[1][1] += a1 * b1;
+      }
     }
     __syncthreads();
+  }
+  // ---- R (b < j): sum_{k = b*32}^{j*32} L[j, k] Linv[k, b-block]
+  if (b < j) {
+    for (int k0 = b * 32; k0 < kend; k0 += CHOL_CH) {
+      const int kw = min(CHOL_CH, kend - k0);
+      for (int t = tid; t < 32 * CHOL_CH; t += 256) {
+        const int r = t / CHOL_CH, c = t % CHOL_CH;
+        Pa[r][c] = (c < kw) ? Lg[(long long)(j * 32 + r) * Mp + k0 + c] : 0.0;
+      }
+      for (int t = tid; t < CHOL_CH * 32; t += 256) {
+        const int r = t >> 5, c = t & 31;
+        Pc[r][c] = (r < kw) ? Xg[(long long)(k0 + r) * Mp + b * 32 + c] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < CHOL_CH; k++) {
+        const double a0 = Pa[ty * 2][k], a1 = Pa[ty * 2 + 1][k];
+        const double b0 = Pc[k][tx * 2], b1 = Pc[k][tx * 2 + 1];
+        accC[0][0] += a0 * b0; accC[0][1] += a0 * b1; accC[1][0] += a1 * b0; accC[1][1] += a1 * b1;
+      }
+      __syncthreads();
+    }
   }
 #pragma unroll
   for (int a = 0; a < 2; a++)
 #pragma unroll
-    for (int b = 0; b < 2; b++) {
-      const int r = ty * 2 + a, c = tx * 2 + b;
-      Dg[r][c] = Kg[(long long)(j * 32 + r) * Mp + j * 32 + c] - accD[a][b];
-      Cg[r][c] = Kg[(long long)(i * 32 + r) * Mp + j * 32 + c] - accC[a][b];
+    for (int c2 = 0; c2 < 2; c2++) {
+      const int r = ty * 2 + a, c = tx * 2 + c2;
+      Dg[r][c] = Kg[(long long)(j * 32 + r) * Mp + j * 32 + c] - accD[a][c2];
+      if (b > j) Cg[r][c] = Kg[(long long)(b * 32 + r) * Mp + j * 32 + c] - accC[a][c2];
+      else if (b < j) Cg[r][c] = -accC[a][c2];
+      else Cg[r][c] = (r == c) ? 1.0 : 0.0;
     }
-  __syncthreads();
-  if (tid < 32) {  // unblocked factorisation of the 32x32 diagonal block by one warp
-    const int lane = tid;
-    for (int c = 0; c < 32; c++) {
-      const double d = sqrt(Dg[c][c]);
-      __syncwarp();
-      if (lane == c) Dg[c][c] = d;
-      if (lane > c) Dg[lane][c] /= d;
-      __syncwarp();
-      if (lane > c) {
-        const double lc = Dg[lane][c];
-        for (int cc = c + 1; cc <= lane; cc++) Dg[lane][cc] -= lc * Dg[cc][c];
-      }
-      __syncwarp();
+  chol32_smem(Dg, tid);
+  if (b > j) {
+    // X Ljj^T = C  <=>  Ljj X^T = C^T : transpose C in place, solve columns, write back transposed
+    __syncthreads();
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int t = tid + q * 256;
+      v[q] = Cg[t & 31][t >> 5];
     }
-  }
-  __syncthreads();
-  if (i == j) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int t = tid + q * 256;
+      Cg[t >> 5][t & 31] = v[q];
+    }
+    __syncthreads();
+    trsm32_lower_cols(Dg, Cg, tid);
     for (int t = tid; t < 1024; t += 256) {
       const int r = t >> 5, c = t & 31;
-      Lg[(long long)(j * 32 + r) * Mp + j * 32 + c] = (c <= r) ? Dg[r][c] : 0.0;
+      Lg[(long long)(b * 32 + r) * Mp + j * 32 + c] = Cg[c][r];
+      Lg[(long long)(j * 32 + r) * Mp + b * 32 + c] = 0.0;   // mirrored upper block of L
+      Xg[(long long)(j * 32 + r) * Mp + b * 32 + c] = 0.0;   // and of Linv
     }
   } else {
-    if (tid < 32) {  // X * Ljj^T = C, one row per thread
-      const int r = tid;
-      for (int c = 0; c < 32; c++) {
-        double s = Cg[r][c];
-        for (int t = 0; t < c; t++) s -= Cg[r][t] * Dg[c][t];
-        Cg[r][c] = s / Dg[c][c];
-      }
-    }
+    // Ljj Y = Cg  (Cg = I -> Ljj^-1 ;  Cg = -R -> Linv[j, b])
     __syncthreads();
+    trsm32_lower_cols(Dg, Cg, tid);
     for (int t = tid; t < 1024; t += 256) {
       const int r = t >> 5, c = t & 31;
-      Lg[(long long)(i * 32 + r) * Mp + j * 32 + c] = Cg[r][c];
-      Lg[(long long)(j * 32 + r) * Mp + i * 32 + c] = 0.0;  // mirrored upper block
+      Xg[(long long)(j * 32 + r) * Mp + b * 32 + c] = Cg[r][c];
+      if (b == j) Lg[(long long)(j * 32 + r) * Mp + j * 32 + c] = (c <= r) ? Dg[r][c] : 0.0;
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Linv = L^-1 by block columns: X[j,j] = Ljj^-1, X[i,j] = -Lii^-1 sum_{k=j}^{i-1} L[i,k] X[k,j].
-// grid (Mp/32, Q), block 256.  The explicit inverse turns every later solve into a DMMA GEMM.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trinv_kernel(const double* __restrict__ L, double* __restrict__ Linv, int Mp) {
-  __shared__ double Lb[32][33], Xb[32][33], Rb[32][33], Ld[32][33];
-  const int g = blockIdx.y, j = blockIdx.x, nb = Mp / 32;
-  const double* Lg = L + (long long)g * Mp * Mp;
-  double* Xg = Linv + (long long)g * Mp * Mp;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int i = 0; i < j; i++)  // zero blocks above the diagonal
-    for (int t = tid; t < 1024; t += 256) Xg[(long long)(i * 32 + (t >> 5)) * Mp + j * 32 + (t & 31)] = 0.0;
-  for (int i = j; i < nb; i++) {
-    double acc[2][2] = {{0, 0}, {0, 0}};
-    for (int k = j; k < i; k++) {
-      for (int t = tid; t < 1024; t += 256) {
-        const int r = t >> 5, c = t & 31;
-        Lb[r][c] = Lg[(long long)(i * 32 + r) * Mp + k * 32 + c];
-        Xb[r][c] = Xg[(long long)(k * 32 + r) * Mp + j * 32 + c];
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int kk = 0; kk < 32; kk++) {
-        const double a0 = Lb[ty * 2][kk], a1 = Lb[ty * 2 + 1][kk];
-        const double b0 = Xb[kk][tx * 2], b1 = Xb[kk][tx * 2 + 1];
-        acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
-      }
-      __syncthreads();
-    }
-    for (int t = tid; t < 1024; t += 256) {
-      const int r = t >> 5, c = t & 31;
-      Ld[r][c] = Lg[(long long)(i * 32 + r) * Mp + i * 32 + c];
-    }
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-      for (int b = 0; b < 2; b++) {
-        const int r = ty * 2 + a, c = tx * 2 + b;
-        Rb[r][c] = (i == j) ? ((r == c) ? 1.0 : 0.0) : -acc[a][b];
-      }
-    __syncthreads();
-    if (tid < 32) {  // forward substitution Lii y = Rb[:, c], one column per thread
-      const int c = tid;
-      for (int r = 0; r < 32; r++) {
-        double s = Rb[r][c];
-        for (int t = 0; t < r; t++) s -= Ld[r][t] * Rb[t][c];
-        Rb[r][c] = s / Ld[r][r];
-      }
-    }
-    __syncthreads();
-    for (int t = tid; t < 1024; t += 256) {
-      const int r = t >> 5, c = t & 31;
-      Xg[(long long)(i * 32 + r) * Mp + j * 32 + c] = Rb[r][c];
-    }
-    __syncthreads();  // X[i,j] visible to this CTA's later block products
   }
 }
 
@@ -318,35 +336,38 @@ __global__ void __launch_bounds__(128) col_sumsq_kernel(const ModelDev* __restri
 
 // ------------------------------------------------------------------------------------------------
 // KL terms (Appendix A.5, whitened gauss_kl) and their gradients w.r.t. q_mu, q_sqrt.
-// One CTA per latent.  out[2] += KL of gating latents, out[3] += KL of expert latents.
-// grad convention: gradient of the ELBO (= data term - KL).
+// grid (Mp/8, P), block 256: one warp per row of q_sqrt (coalesced).  out[2] += KL of gating latents,
+// out[3] += KL of expert latents.  grad convention: gradient of the ELBO (= data term - KL).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kl_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
                                                  Layout lo, double klw, double* __restrict__ out, double* __restrict__ grads) {
   __shared__ double red[8];
-  const int l = blockIdx.x, Mp = md->Mp, Mg = md->group_M[md->latent_group[l]];
-  const double* qm = params + lo.q_mu + (long long)l * Mp;
-  const double* S = params + lo.q_sqrt + (long long)l * Mp * Mp;
+  const int l = blockIdx.y, Mp = md->Mp, Mg = md->group_M[md->latent_group[l]];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
   double acc = 0;
-  for (int m = threadIdx.x; m < Mg; m += 256) {
-    acc += qm[m] * qm[m] - 1.0 - log(S[(long long)m * Mp + m] * S[(long long)m * Mp + m]);
-    if (grads) grads[lo.q_mu + (long long)l * Mp + m] -= klw * qm[m];
-  }
-  for (long long t = threadIdx.x; t < (long long)Mg * Mg; t += 256) {
-    const int i = t / Mg, j = t % Mg;
-    if (j <= i) {
-      const double s = S[(long long)i * Mp + j];
+  if (i < Mg) {
+    const double* row = params + lo.q_sqrt + ((long long)l * Mp + i) * Mp;
+    double* grow = grads ? grads + lo.q_sqrt + ((long long)l * Mp + i) * Mp : nullptr;
+    for (int j = lane; j <= i; j += 32) {
+      const double s = row[j];
       acc += s * s;
-      if (grads) grads[lo.q_sqrt + ((long long)l * Mp + i) * Mp + j] -= klw * ((i == j) ? (s - 1.0 / s) : s);
+      if (j == i) acc -= 1.0 + log(s * s);
+      if (grow) grow[j] -= klw * ((i == j) ? (s - 1.0 / s) : s);
+    }
+    if (lane == 0) {
+      const double q = params[lo.q_mu + (long long)l * Mp + i];
+      acc += q * q;
+      if (grads) grads[lo.q_mu + (long long)l * Mp + i] -= klw * q;
     }
   }
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  if (lane == 0) red[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0;
     for (int w = 0; w < 8; w++) s += red[w];
-    atomicAdd(out + (l >= md->Pe ? 2 : 3), 0.5 * klw * s);
+    if (s != 0.0) atomicAdd(out + (l >= md->Pe ? 2 : 3), 0.5 * klw * s);
   }
 }
 
@@ -390,28 +411,41 @@ __global__ void __launch_bounds__(128) build_abar_kernel(const ModelDev* __restr
   for (int r = 0; r < 32; r++) out[(long long)r * Bp] = acc[r];
 }
 
-// dV[v][m] = sum_n A[g][m][n] dmean[v][n].  One warp per row m, up to 8 vectors per pass.
-// grid (Mp/8, Q), block 256
+// dV[v][m] += sum_n A[g][m][n] dmean[v][n] (dV zero-initialised).  CTA = (1024-column slab, 32 rows, group):
+// thread (cx, ry) streams 4 columns x 8 rows... each warp reads full 256-byte row segments (coalesced),
+// reduces over its columns with shuffles and adds one atomic per (row, vector).  Up to 8 vectors per pass.
+// grid (ceil(Bc/1024), Mp/32, Q), block 256
 __global__ void __launch_bounds__(256) dV_kernel(const ModelDev* __restrict__ md, const double* __restrict__ A,
                                                  const double* __restrict__ dmean, int Bp, int Bc, double* __restrict__ dV) {
-  const int g = blockIdx.y, Mp = md->Mp;
+  const int g = blockIdx.z, Mp = md->Mp, m0 = blockIdx.y * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + warp;
-  const double* row = A + ((long long)g * Mp + m) * Bp;
+  const int n0 = blockIdx.x * 1024, n1 = min(Bc, n0 + 1024);
   const int vb = md->gvec_begin[g], ve = md->gvec_begin[g + 1];
   for (int v0 = vb; v0 < ve; v0 += 8) {
     const int nv = min(8, ve - v0);
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int n = lane; n < Bc; n += 32) {
-      const double a = row[n];
+    // warp w owns rows m0 + 4w .. m0 + 4w + 3
+    double acc[4][8];
 #pragma unroll
-      for (int q = 0; q < 8; q++)
-        if (q < nv) acc[q] += a * dmean[(long long)md->gvec[v0 + q] * Bp + n];
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int q = 0; q < 8; q++) acc[r][q] = 0.0;
+    for (int n = n0 + lane; n < n1; n += 32) {
+      double dm[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) dm[q] = (q < nv) ? dmean[(long long)md->gvec[v0 + q] * Bp + n] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const double a = A[((long long)g * Mp + m0 + warp * 4 + r) * Bp + n];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[r][q] += a * dm[q];
+      }
     }
-    for (int q = 0; q < nv; q++) {
-      const double s = warp_sum(acc[q]);
-      if (lane == 0) dV[(long long)md->gvec[v0 + q] * Mp + m] = s;
-    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      for (int q = 0; q < nv; q++) {
+        const double s = warp_sum(acc[r][q]);
+        if (lane == 0) atomicAdd(dV + (long long)md->gvec[v0 + q] * Mp + m0 + warp * 4 + r, s);
+      }
   }
 }
 

@@ -20,9 +20,10 @@ def _rel(a, b):
     return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
 
 
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(64, 64, 64), (128, 256, 192), (256, 1024, 128), (512, 4096, 512)])
-def test_dmma_gemm_matches_numpy(ta, tb, M, N, K):
+def test_dmma_gemm_matches_numpy(ta, tb, M, N, K, cfg):
     import torch
     from mogpe_b200 import _lib
 
@@ -33,7 +34,7 @@ def test_dmma_gemm_matches_numpy(ta, tb, M, N, K):
     B = rng.standard_normal((batch, N, K) if tb else (batch, K, N))
     C0 = rng.standard_normal((batch, M, N))
     dA, dB, dC = (torch.as_tensor(x, device="cuda") for x in (A, B, C0))
-    _lib.check(lib.mogpe_debug_gemm(0, dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), batch, M, N, K, ta, tb, 0, 0, 1.5, 0.5, None))
+    _lib.check(lib.mogpe_debug_gemm(0, dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), batch, M, N, K, ta, tb, 0, 0, 1.5, 0.5, cfg, None))
     torch.cuda.synchronize()
     opA = np.swapaxes(A, 1, 2) if ta else A
     opB = np.swapaxes(B, 1, 2) if tb else B
@@ -41,8 +42,9 @@ def test_dmma_gemm_matches_numpy(ta, tb, M, N, K):
     assert _rel(dC.cpu().numpy(), ref) < 1e-13
 
 
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("size", [128, 256, 512])
-def test_dmma_gemm_triangular_modes(size):
+def test_dmma_gemm_triangular_modes(size, cfg):
     import torch
     from mogpe_b200 import _lib
 
@@ -54,25 +56,25 @@ def test_dmma_gemm_triangular_modes(size):
     out = torch.zeros((2, M, 1024), dtype=torch.float64, device="cuda")
     dT, dR = torch.as_tensor(T, device="cuda"), torch.as_tensor(R, device="cuda")
     # left lower: T @ R
-    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dR.data_ptr(), out.data_ptr(), 2, M, 1024, M, 0, 0, 1, 0, 1.0, 0.0, None))
+    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dR.data_ptr(), out.data_ptr(), 2, M, 1024, M, 0, 0, 1, 0, 1.0, 0.0, cfg, None))
     assert _rel(out.cpu().numpy(), T @ R) < 1e-13
     # left upper (transposed lower): T^T @ R
-    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dR.data_ptr(), out.data_ptr(), 2, M, 1024, M, 1, 0, 2, 0, 1.0, 0.0, None))
+    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dR.data_ptr(), out.data_ptr(), 2, M, 1024, M, 1, 0, 2, 0, 1.0, 0.0, cfg, None))
     assert _rel(out.cpu().numpy(), np.swapaxes(T, 1, 2) @ R) < 1e-13
     # tril output of an NT product over a long k
     W = rng.standard_normal((2, M, 2048))
     A = rng.standard_normal((2, M, 2048))
     o2 = torch.full((2, M, M), 7.0, dtype=torch.float64, device="cuda")
     dW, dA = torch.as_tensor(W, device="cuda"), torch.as_tensor(A, device="cuda")
-    _lib.check(lib.mogpe_debug_gemm(0, dW.data_ptr(), dA.data_ptr(), o2.data_ptr(), 2, M, M, 2048, 0, 1, 0, 1, -1.0, 0.0, None))
+    _lib.check(lib.mogpe_debug_gemm(0, dW.data_ptr(), dA.data_ptr(), o2.data_ptr(), 2, M, M, 2048, 0, 1, 0, 1, -1.0, 0.0, cfg, None))
     assert _rel(o2.cpu().numpy(), -np.tril(W @ np.swapaxes(A, 1, 2))) < 1e-13
     # right lower: R2 @ T  and left-upper x right-lower: T^T @ T2
     R2 = rng.standard_normal((2, M, M))
     o3 = torch.zeros((2, M, M), dtype=torch.float64, device="cuda")
     dR2 = torch.as_tensor(R2, device="cuda")
-    _lib.check(lib.mogpe_debug_gemm(0, dR2.data_ptr(), dT.data_ptr(), o3.data_ptr(), 2, M, M, M, 0, 0, 4, 0, 1.0, 0.0, None))
+    _lib.check(lib.mogpe_debug_gemm(0, dR2.data_ptr(), dT.data_ptr(), o3.data_ptr(), 2, M, M, M, 0, 0, 4, 0, 1.0, 0.0, cfg, None))
     assert _rel(o3.cpu().numpy(), R2 @ T) < 1e-13
-    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dT.data_ptr(), o3.data_ptr(), 2, M, M, M, 1, 0, 2 | 4, 0, 1.0, 0.0, None))
+    _lib.check(lib.mogpe_debug_gemm(0, dT.data_ptr(), dT.data_ptr(), o3.data_ptr(), 2, M, M, M, 1, 0, 2 | 4, 0, 1.0, 0.0, cfg, None))
     assert _rel(o3.cpu().numpy(), np.swapaxes(T, 1, 2) @ T) < 1e-13
 
 
