@@ -130,6 +130,18 @@ mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const do
                            double* f_var, double* mix_probs, double* y_mean, double* y_var,
                            const double* eps_mc, int32_t num_mc, void* cuda_stream);
 
+/* Conditional given inducing samples u_s ~ q(u) for EVERY latent (mogpe/keras/gps.py:14-50,
+ * mogpe/gps/svgp.py:130-152: SVGPExpert.predict_f(num_inducing_samples=S), SVGPGatingNetwork.predict_h(...)).
+ *   eps_u [P, S, Mp] (NULL -> library stream); f_mean [S, N, P] includes the mean function;
+ *   f_var [N, P] is the same for every sample (no q_sqrt term).  N <= max_batch. */
+mogpe_status mogpe_predict_f_inducing_samples(mogpe_handle* h, const double* X, int32_t N, const double* params,
+                                              const double* eps_u, int32_t num_samples, double* f_mean,
+                                              double* f_var, void* cuda_stream);
+
+/* prior_kl of every latent GP (gpflow gauss_kl, whitened; mogpe/keras/experts.py:205-207,
+ * mogpe/keras/gating_networks.py:251-253, mogpe/experts/svgp.py:161-169).  kl [P] device. */
+mogpe_status mogpe_prior_kl(mogpe_handle* h, const double* params, double* kl, void* cuda_stream);
+
 /* Library-owned random stream.  When an eps_* pointer that `bound` needs is NULL, the library draws it on
  * the device from Philox(seed, counter) -- as the reference draws inside tf.random / tfd -- and advances the
  * counter.  mogpe_debug_copy("eps_u" | "eps_h" | "eps_f") returns the draws of the last call so the oracle

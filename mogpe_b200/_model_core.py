@@ -1,0 +1,285 @@
+"""Shared machinery of the two API flavours: SVGP parameter containers -> Engine, gradient chaining to the
+unconstrained variables, light-weight distribution objects, Adam.
+
+The reference evaluates everything through GPflow/TFP on the CPU; here every conditional, bound and
+prediction goes through mogpe_b200.engine.Engine (CUDA).  What stays on the host is parameter bookkeeping
+and O(N*K) post-processing of returned predictions (distribution objects for metrics / plotting callers).
+"""
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .device import as_view
+from .engine import Engine, GPBlock, GPGrads
+from .gpflow_lite import SVGP, Constant, Gaussian, Parameter
+
+LOG_2PI = math.log(2.0 * math.pi)
+
+
+def svgp_to_block(gp: SVGP, is_expert: bool) -> GPBlock:
+    L = gp.num_latent_gps
+    mean_c = None
+    if isinstance(gp.mean_function, Constant):
+        mean_c = np.broadcast_to(np.asarray(gp.mean_function.c.numpy(), dtype=np.float64).reshape(-1), (L,)).copy()
+    noise = None
+    if is_expert:
+        if not isinstance(gp.likelihood, Gaussian):
+            raise NotImplementedError("experts need a Gaussian likelihood (the reference supports no other)")
+        noise = np.broadcast_to(np.asarray(gp.likelihood.variance.numpy(), dtype=np.float64).reshape(-1), (L,)).copy()
+    return GPBlock(
+        Z=gp.Z.numpy(),
+        lengthscales=[k.lengthscales.numpy() for k in gp.latent_kernel_list],
+        variances=[float(k.variance.numpy()) for k in gp.latent_kernel_list],
+        q_mu=gp.q_mu.numpy(),
+        q_sqrt=gp.q_sqrt.numpy(),
+        mean_c=mean_c,
+        noise=noise,
+    )
+
+
+def accumulate_param_grads(acc: Dict[int, np.ndarray], gp: SVGP, g: GPGrads, is_expert: bool):
+    """Chain constrained-space gradients to the unconstrained variables and ACCUMULATE per
+    Parameter object: the reference fixture puts the same expert in the list twice (tests/keras/test_keras.py:84)."""
+
+    def add(p: Parameter, grad_constrained):
+        gu = p.chain_grad(grad_constrained)
+        acc[id(p)] = acc.get(id(p), 0.0) + gu
+
+    add(gp.Z, g.Z)
+    for k, gl, gv in zip(gp.latent_kernel_list, g.lengthscales, g.variances):
+        add(k.lengthscales, np.asarray(gl))
+        add(k.variance, np.asarray(gv))
+    add(gp.q_mu, g.q_mu)
+    add(gp.q_sqrt, g.q_sqrt)
+    if isinstance(gp.mean_function, Constant):
+        c = gp.mean_function.c
+        gc = g.mean_c if c.unconstrained.size == g.mean_c.size else np.sum(g.mean_c)
+        add(c, np.asarray(gc))
+    if is_expert:
+        v = gp.likelihood.variance
+        gn = g.noise if v.unconstrained.size == g.noise.size else np.sum(g.noise)
+        add(v, np.asarray(gn))
+
+
+class MixtureCore:
+    """Owns the Engine for a list of expert SVGPs + one gating SVGP."""
+
+    def __init__(self, expert_gps: List[SVGP], gating_gp: SVGP, flavour: str, device: int = 0):
+        self.expert_gps, self.gating_gp, self.flavour, self.device = list(expert_gps), gating_gp, flavour, device
+        self.engine: Optional[Engine] = None
+        self.seed = 0
+        self.default_batch = 1024
+
+    # -- engine lifecycle ---------------------------------------------------------------------------------
+    def _blocks(self):
+        return [svgp_to_block(g, True) for g in self.expert_gps], svgp_to_block(self.gating_gp, False)
+
+    def ensure_engine(self, batch: int) -> Engine:
+        experts, gating = self._blocks()
+        if self.engine is None or batch > self.engine.max_batch:
+            if self.engine is not None:
+                self.engine.close()
+            self.engine = Engine(experts, gating, flavour=self.flavour, max_batch=max(batch, self.default_batch),
+                                 device=self.device)
+            self.engine.set_seed(self.seed)
+        else:
+            self.engine.set_params(experts, gating)
+        return self.engine
+
+    def set_seed(self, seed: int):
+        self.seed = int(seed)
+        if self.engine is not None:
+            self.engine.set_seed(self.seed)
+
+    @property
+    def trainable_parameters(self) -> List[Parameter]:
+        seen, out = set(), []
+        for gp in self.expert_gps + [self.gating_gp]:
+            for p in gp.trainable_parameters:
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    out.append(p)
+        return out
+
+    # -- hot path ---------------------------------------------------------------------------------------------
+    def elbo(self, X, Y, bound, num_samples, num_data, eps=None, want_grads=False):
+        """-> (ElboResult, {id(param): d ELBO / d unconstrained}).  eps: optional explicit draws in the oracle's
+        format {"u_experts": [K][S, F, M], "u_gating": [S, G, M], "h": [S, N, G], "f": [S, N, F, K]}."""
+        xv = as_view(X)
+        N = int(xv.shape[0])
+        eng = self.ensure_engine(N)
+        scale = 1.0 if num_data is None else float(num_data) / N
+        eps_u = eps_h = eps_f = None
+        if eps is not None:
+            if eps.get("u_experts") is not None or eps.get("u_gating") is not None:
+                eps_u = eng.pack_eps_u(eps.get("u_experts"), eps.get("u_gating") if bound == "tight" else None, num_samples)
+            if eps.get("h") is not None and bound != "tight":
+                eps_h = np.ascontiguousarray(eps["h"], dtype=np.float64)
+            if eps.get("f") is not None and bound == "further":
+                eps_f = eng.pack_eps_f(eps["f"])
+        res = eng.elbo(X, Y, bound, num_samples, scale, eps_u, eps_h, eps_f, want_grads=want_grads)
+        grads = None
+        if want_grads:
+            grads = {}
+            for gp, g in zip(self.expert_gps, res.experts):
+                accumulate_param_grads(grads, gp, g, True)
+            accumulate_param_grads(grads, self.gating_gp, res.gating, False)
+        return res, grads
+
+    def predict(self, Xnew, want, eps_mc=None, rng=None):
+        xv = as_view(Xnew)
+        N = int(xv.shape[0])
+        eng = self.ensure_engine(min(N, max(self.default_batch, 65536)))
+        need_pi = any(w in want for w in ("mix_probs", "y_mean", "y_var"))
+        if eng.G > 1 and need_pi and eps_mc is None:
+            # gpflow Softmax.predict_mean_and_var: 100 Monte-Carlo draws from the global RNG
+            rng = rng or np.random.default_rng(self.seed)
+            eps_mc = rng.standard_normal((100, N, eng.K))
+        return eng.predict(Xnew, want=want, eps_mc=eps_mc)
+
+    def latent_slices(self):
+        """-> per GP (experts..., gating): slice into the latent axis of f_mean / f_var."""
+        out, l = [], 0
+        for gp in self.expert_gps + [self.gating_gp]:
+            out.append(slice(l, l + gp.num_latent_gps))
+            l += gp.num_latent_gps
+        return out
+
+
+# ---- distributions returned to callers (metrics / plotting) -------------------------------------------------------
+class Normal:
+    """Stand-in for tfd.Normal / tfd.MultivariateNormalDiag(loc, scale) with the methods the reference's callers
+    use.  `event_ndims` = 1 reduces log_prob over the last axis (MultivariateNormalDiag)."""
+
+    def __init__(self, loc, scale, event_ndims=0):
+        self.loc, self.scale, self.event_ndims = np.asarray(loc), np.asarray(scale), event_ndims
+
+    def mean(self):
+        return self.loc
+
+    def stddev(self):
+        return np.abs(self.scale)
+
+    def variance(self):
+        return self.scale**2
+
+    def log_prob(self, y):
+        z = (np.asarray(y) - self.loc) / self.scale
+        lp = -0.5 * z * z - np.log(np.abs(self.scale)) - 0.5 * LOG_2PI
+        return lp.sum(-1) if self.event_ndims else lp
+
+    def prob(self, y):
+        return np.exp(self.log_prob(y))
+
+    def sample(self, n=None, rng=None):
+        rng = rng or np.random.default_rng()
+        shape = self.loc.shape if n is None else (n,) + self.loc.shape
+        return self.loc + self.scale * rng.standard_normal(shape)
+
+    @property
+    def batch_shape(self):
+        return self.loc.shape[:-1] if self.event_ndims else self.loc.shape
+
+
+class Categorical:
+    def __init__(self, probs):
+        self.probs = np.asarray(probs)
+
+    def probs_parameter(self):
+        return self.probs
+
+    def sample(self, n=None, rng=None):
+        rng = rng or np.random.default_rng()
+        c = np.cumsum(self.probs, -1)
+        u = rng.random(self.probs.shape[:-1] if n is None else (n,) + self.probs.shape[:-1])
+        return (u[..., None] > c).sum(-1)
+
+
+class MixtureDistribution:
+    """Stand-in for the tfd.Mixture (Keras flavour) / tfd.MixtureSameFamily (legacy) returned by predict_y.
+    mean() and variance() are the device-computed values (flavour-exact)."""
+
+    def __init__(self, mixing_probs, locs, scales, mean, variance):
+        self.mixing_probs = np.asarray(mixing_probs)  # [N, K]
+        self.locs, self.scales = np.asarray(locs), np.asarray(scales)  # [N, F, K]
+        self._mean, self._variance = np.asarray(mean), np.asarray(variance)  # [N, F]
+
+    def mean(self):
+        return self._mean
+
+    def variance(self):
+        return self._variance
+
+    def stddev(self):
+        return np.sqrt(self._variance)
+
+    def log_prob(self, y, joint_over_outputs=True):
+        """Keras flavour (joint_over_outputs): log sum_k pi_k prod_f N(y_f; mu_kf, s_kf) -> [N];
+        legacy MixtureSameFamily over Normal: per output -> [N, F]."""
+        y = np.asarray(y)[..., None]
+        z = (y - self.locs) / self.scales
+        lp = -0.5 * z * z - np.log(np.abs(self.scales)) - 0.5 * LOG_2PI  # [N, F, K]
+        if joint_over_outputs:
+            w = lp.sum(-2) + np.log(self.mixing_probs)
+        else:
+            w = lp + np.log(self.mixing_probs)[..., None, :]
+        m = w.max(-1, keepdims=True)
+        return (m + np.log(np.exp(w - m).sum(-1, keepdims=True)))[..., 0]
+
+    def prob(self, y, **kw):
+        return np.exp(self.log_prob(y, **kw))
+
+    def sample(self, n=1, rng=None):
+        rng = rng or np.random.default_rng()
+        N, F, K = self.locs.shape
+        k = Categorical(self.mixing_probs).sample(n, rng)  # [n, N]
+        idx = np.broadcast_to(k[..., None, None], (n, N, F, 1))
+        loc = np.take_along_axis(np.broadcast_to(self.locs, (n, N, F, K)), idx, -1)[..., 0]
+        sc = np.take_along_axis(np.broadcast_to(self.scales, (n, N, F, K)), idx, -1)[..., 0]
+        return loc + sc * rng.standard_normal((n, N, F))
+
+
+# ---- optimiser (the reference uses tf.optimizers.Adam everywhere) ----------------------------
+class Adam:
+    """TF-default Adam (beta_1 = 0.9, beta_2 = 0.999, epsilon = 1e-7) over Parameter.unconstrained arrays."""
+
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta_1, beta_2, epsilon
+        self.t = 0
+        self.m: Dict[int, np.ndarray] = {}
+        self.v: Dict[int, np.ndarray] = {}
+
+    def apply_gradients(self, grads_and_vars):
+        """grads of the LOSS w.r.t. the unconstrained variables, as tf.optimizers.Adam.apply_gradients."""
+        self.t += 1
+        lr_t = self.lr * math.sqrt(1.0 - self.b2**self.t) / (1.0 - self.b1**self.t)
+        for g, p in grads_and_vars:
+            if g is None:
+                continue
+            g = np.asarray(g, dtype=np.float64).reshape(p.unconstrained.shape)
+            m = self.m.get(id(p))
+            if m is None:
+                m = self.m[id(p)] = np.zeros_like(p.unconstrained)
+                self.v[id(p)] = np.zeros_like(p.unconstrained)
+            v = self.v[id(p)]
+            m += (1.0 - self.b1) * (g - m)
+            v += (1.0 - self.b2) * (g * g - v)
+            p.assign_unconstrained(p.unconstrained - lr_t * m / (np.sqrt(v) + self.eps))
+
+
+class MeanTracker:
+    """tf.keras.metrics.Mean."""
+
+    def __init__(self, name="loss"):
+        self.name, self.total, self.count = name, 0.0, 0
+
+    def update_state(self, v):
+        self.total += float(v)
+        self.count += 1
+
+    def result(self):
+        return self.total / max(1, self.count)
+
+    def reset_states(self):
+        self.total, self.count = 0.0, 0

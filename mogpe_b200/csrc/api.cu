@@ -680,6 +680,61 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
   return MOGPE_OK;
 }
 
+extern "C" mogpe_status mogpe_predict_f_inducing_samples(mogpe_handle* h, const double* X, int32_t N,
+                                                         const double* params, const double* eps_u, int32_t S,
+                                                         double* f_mean, double* f_var, void* cuda_stream) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (!X || !params) H_FAIL(h, MOGPE_ERR_INVALID, "null X / params");
+  if (N < 1 || N > h->desc.max_batch) H_FAIL(h, MOGPE_ERR_INVALID, "N=%d outside [1, max_batch=%d]", N, h->desc.max_batch);
+  if (S < 1 || S > MOGPE_MAX_SAMPLES) H_FAIL(h, MOGPE_ERR_INVALID, "num_samples=%d outside [1, %d]", S, MOGPE_MAX_SAMPLES);
+  const ModelDev& md = h->md_host;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  H_CUDA(h, cudaSetDevice(h->device));
+  mogpe_status rc = set_mode(h, MOGPE_BOUND_TIGHT, S, st);  // "tight" = every latent inducing-sampled
+  if (rc != MOGPE_OK) return rc;
+  if (!eps_u) {
+    const size_t nu = (size_t)md.P * S * h->Mp;
+    if (nu > h->eps_u_cap) {
+      if (h->eps_u_int) cudaFree(h->eps_u_int);
+      h->eps_u_int = nullptr;
+      H_CUDA(h, dalloc(&h->eps_u_int, nu));
+      h->eps_u_cap = nu;
+    }
+    const long long pairs = ((long long)nu + 1) / 2;
+    fill_normal_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(h->eps_u_int, (long long)nu, h->seed, h->rng_counter);
+    h->rng_counter += (nu + 1) / 2 * 2;
+    eps_u = h->eps_u_int;
+    h->last_eps_u = eps_u;
+    h->last_nu = (long long)nu;
+    KCOUNT(h, 1);
+  }
+  rc = factorise(h, params, st);
+  if (rc != MOGPE_OK) return rc;
+  make_V_kernel<<<dim3(h->Mp / 8, md.NV), 256, 0, st>>>(h->d_md, params, h->lo, h->Sc, eps_u, S, h->V);
+  rc = conditional_fwd(h, params, X, N, round_up(N, 128), st);
+  if (rc != MOGPE_OK) return rc;
+  inducing_out_kernel<<<(N + 127) / 128, 128, 0, st>>>(h->d_md, params, h->lo, h->mean, h->var0ss, N, h->Bp, f_mean, f_var);
+  KCOUNT(h, 2);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_prior_kl(mogpe_handle* h, const double* params, double* kl, void* cuda_stream) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (!params || !kl) H_FAIL(h, MOGPE_ERR_INVALID, "null params / kl");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  H_CUDA(h, cudaSetDevice(h->device));
+  if (h->cur_bound == -100) {  // the device model description is uploaded by the first mode set
+    mogpe_status rc = set_mode(h, -1, 1, st);
+    if (rc != MOGPE_OK) return rc;
+  }
+  H_CUDA(h, cudaMemsetAsync(kl, 0, sizeof(double) * h->md_host.P, st));
+  kl_per_latent_kernel<<<dim3(h->Mp / 8, h->md_host.P), 256, 0, st>>>(h->d_md, params, h->lo, kl);
+  KCOUNT(h, 1);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_fill_normal(mogpe_handle* h, double* dst, int64_t n, uint64_t seed, uint64_t offset,
                                           void* cuda_stream) {
   if (!h || !dst || n < 0) return MOGPE_ERR_INVALID;

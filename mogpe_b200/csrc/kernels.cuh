@@ -371,6 +371,52 @@ __global__ void __launch_bounds__(256) kl_kernel(const ModelDev* __restrict__ md
   }
 }
 
+// per-latent KL (same arithmetic as kl_kernel, no gradients): kl[l] += ...   grid (Mp/8, P), block 256
+__global__ void __launch_bounds__(256) kl_per_latent_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                            Layout lo, double* __restrict__ kl) {
+  __shared__ double red[8];
+  const int l = blockIdx.y, Mp = md->Mp, Mg = md->group_M[md->latent_group[l]];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  double acc = 0;
+  if (i < Mg) {
+    const double* row = params + lo.q_sqrt + ((long long)l * Mp + i) * Mp;
+    for (int j = lane; j <= i; j += 32) {
+      const double s = row[j];
+      acc += s * s;
+      if (j == i) acc -= 1.0 + log(s * s);
+    }
+    if (lane == 0) {
+      const double q = params[lo.q_mu + (long long)l * Mp + i];
+      acc += q * q;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < 8; w++) s += red[w];
+    if (s != 0.0) atomicAdd(kl + l, 0.5 * s);
+  }
+}
+
+// f_mean[s][n][l] = mean[voff[l] + s][n] ; f_var[n][l] = kvar[g] - var0ss[g][n]   (all latents inducing-sampled)
+// grid (ceil(N/128)), block 128
+__global__ void inducing_out_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
+                                    const double* __restrict__ mean, const double* __restrict__ var0ss, int N, int Bp,
+                                    double* __restrict__ f_mean, double* __restrict__ f_var) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= N) return;
+  const int P = md->P, S = md->S;
+  for (int l = 0; l < P; l++) {
+    const int g = md->latent_group[l];
+    if (f_var) f_var[(long long)n * P + l] = params[lo.kvar + g] - var0ss[(long long)g * Bp + n];
+    if (f_mean)
+      for (int s = 0; s < S; s++) f_mean[((long long)s * N + n) * P + l] = mean[(long long)(md->voff[l] + s) * Bp + n];
+  }
+}
+
 __global__ void finish_elbo_kernel(double* out) { out[0] = out[1] - out[2] - out[3]; }
 
 // ------------------------------------------------------------------------------------------------

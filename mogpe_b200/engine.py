@@ -299,6 +299,25 @@ class Engine:
         _lib.check(self.lib.mogpe_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(ng), C.byref(na)), self.h)
         return {"gemm_ms": ms.value, "gemm_flops": fl.value, "gemm_launches": ng.value, "all_launches": na.value}
 
+    def predict_f_inducing_samples(self, X, num_samples, eps_u=None, stream=None):
+        """-> f_mean [S, N, P], f_var [N, P] (mogpe/keras/gps.py:14-50); eps_u [P, S, Mp] or None (library stream)."""
+        xv = as_view(X)
+        N = int(xv.shape[0])
+        if len(xv.shape) != 2 or xv.shape[1] != self.D:
+            raise ValueError(f"X must be [N, {self.D}], got {xv.shape}")
+        xp, keep = self._dev("Xp", X)
+        ep, keep2 = self._dev("eps_u", eps_u)
+        fm = DeviceBuffer((num_samples, N, self.P), self.device, zero=False)
+        fv = DeviceBuffer((N, self.P), self.device, zero=False)
+        _lib.check(self.lib.mogpe_predict_f_inducing_samples(self.h, xp, N, self.params.ptr, ep, num_samples, fm.ptr, fv.ptr, stream), self.h)
+        return fm.numpy(), fv.numpy()
+
+    def prior_kl(self, stream=None):
+        """-> KL of every latent GP [P]."""
+        kl = DeviceBuffer((self.P,), self.device)
+        _lib.check(self.lib.mogpe_prior_kl(self.h, self.params.ptr, kl.ptr, stream), self.h)
+        return kl.numpy()
+
     def debug(self, name):
         n = C.c_int64()
         _lib.check(self.lib.mogpe_debug_copy(self.h, name.encode(), None, 0, C.byref(n)), self.h)

@@ -1,0 +1,161 @@
+"""GPU parity of the drop-in Python API (both flavours) against the oracle: what a user of the reference calls."""
+import numpy as np
+import pytest
+
+from tests._specs import BOUNDS, FLAVOURS, make_spec
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+@pytest.mark.parametrize("bound", BOUNDS)
+@pytest.mark.parametrize("K,F,sep", [(2, 1, False), (2, 2, True), (3, 1, True)])
+def test_objective_and_unconstrained_gradients(flavour, bound, K, F, sep):
+    from oracle import ref_torch as rt
+    from tests._model_helpers import model_from_spec, oracle_grads_in_model_order
+
+    if bound == "tight" and K > 2:
+        pytest.skip("Softmax tight bound is Monte-Carlo in the reference; not implemented")
+    spec, X, Y, eps = make_spec(seed=40 + K + F, N=90, D=2, F=F, K=K, M=14, S=2, flavour=flavour, bound=bound,
+                                num_data=900, separate_kernels=sep, gating_mean_c=-0.1)
+    model = model_from_spec(spec)
+    val = model.maximum_log_likelihood_objective((X, Y), eps=eps)
+    ref, grads_u = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    assert abs(val - ref) <= 1e-8 * abs(ref)
+    val2, grads = model.elbo_and_gradients((X, Y), eps=eps)
+    assert val2 == pytest.approx(val, rel=1e-12)
+    want = oracle_grads_in_model_order(spec, model, grads_u)
+    for p, g, w in zip(model.trainable_variables, grads, want):
+        w = np.asarray(w)
+        assert np.max(np.abs(np.asarray(g).reshape(w.shape) - w)) <= 1e-6 * max(1.0, np.max(np.abs(w))), p.name
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+@pytest.mark.parametrize("K", [2, 3])
+def test_predict_surface(flavour, K):
+    from oracle import ref_numpy as rn
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=60 + K, N=70, D=1, F=2, K=K, M=9, flavour=flavour, separate_kernels=True)
+    model = model_from_spec(spec)
+    eps_mc = np.random.default_rng(0).standard_normal((23, 70, K)) if K > 2 else None
+    dist = model.predict_y(X, eps_mc=eps_mc)
+    ym, yv = rn.predict_y(spec, X, eps_mc)
+    assert _rel(dist.mean(), ym) < 1e-8 and _rel(dist.variance(), yv) < 1e-8
+    pi = rn.predict_mixing_probs(spec, X, eps_mc)
+    assert _rel(model.gating_network.predict_mixing_probs(X, eps_mc=eps_mc), pi) < 1e-8
+    mu_ref, var_ref = rn.predict_experts_y(spec, X)
+    if flavour == "keras":
+        mean, var = model(X) if K == 2 else (dist.mean(), dist.variance())
+        assert _rel(mean, ym) < 1e-8
+        mus, vs = model.predict_experts_y(X)
+        e0 = model.experts_list[0]
+        d0 = e0.predict_dist(X)
+        assert _rel(d0.mean(), mu_ref[..., 0]) < 1e-8 and _rel(d0.stddev(), var_ref[..., 0]) < 1e-8  # quirk 1
+        kl = e0.prior_kl()
+        gate_kl = model.gating_network.prior_kl()
+        h_mean, h_var = model.gating_network.predict_h(X)
+        assert h_mean.shape == (70, K) and (K > 2 or np.array_equal(h_mean[:, 1], -h_mean[:, 0]))
+    else:
+        mus, vs = model.experts.predict_ys(X)
+        kl = model.experts.prior_kls()[0]
+        gate_kl = model.gating_network.prior_kl()
+        assert model.predict_mixing_probs(X, eps_mc=eps_mc).shape == (70, K)
+        fm, fv = model.experts.predict_fs(X)
+        assert fm.shape == (70, 2, K)
+    assert _rel(mus, mu_ref) < 1e-8 and _rel(vs, var_ref) < 1e-8
+    assert kl == pytest.approx(rn.prior_kl(spec["experts"][0]), rel=1e-10)
+    assert gate_kl == pytest.approx(rn.prior_kl(spec["gating"]), rel=1e-10)
+    # log_prob used by the reference's NLPD metric (training/metrics.py:9-16)
+    assert np.all(np.isfinite(dist.log_prob(Y, joint_over_outputs=(flavour == "keras"))))
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+def test_predict_f_given_inducing_samples(flavour):
+    from oracle import ref_numpy as rn
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=71, N=50, D=2, F=2, K=2, M=11, S=3, flavour=flavour, separate_kernels=True)
+    model = model_from_spec(spec)
+    expert = model.experts_list[1] if flavour == "keras" else model.experts.experts_list[1]
+    mean, var = expert.predict_f(X, num_inducing_samples=3, eps_u=eps["u_experts"][1])
+    m_ref, v_ref = rn.predict_f_given_inducing_samples(spec["experts"][1], X, eps["u_experts"][1])
+    assert mean.shape == (3, 50, 2) and _rel(mean, m_ref) < 1e-8 and _rel(var, v_ref) < 1e-8
+
+
+def test_reference_fixture_with_aliased_expert_accumulates_gradients():
+    """tests/keras/test_keras.py fixture: same expert twice, shared kernel / mean / Z between expert and gate."""
+    import copy
+
+    from oracle import ref_numpy as rn
+    from tests.test_host_cpu import _reference_fixture_model
+
+    model = _reference_fixture_model()
+    N, M = 5, 4
+    X, Y = np.ones((N, 2)), np.ones((N, 1))
+    eps = {"u_experts": [np.full((1, 1, M), 0.3)] * 2, "h": np.full((1, N, 1), -0.2)}
+    kern = {"lengthscales": [3.0, 3.0], "variance": 10.0}
+    gp = {"Z": np.ones((M, 2)), "kernels": [kern], "q_mu": np.zeros((M, 1)), "q_sqrt": np.eye(M)[None].copy(),
+          "mean_c": [-2.0], "noise_variance": [3.0]}
+    gate = copy.deepcopy(gp)
+    del gate["noise_variance"]
+    spec = {"flavour": "keras", "bound": "further_gating", "num_samples": 1, "num_data": None,
+            "experts": [gp, copy.deepcopy(gp)], "gating": gate}
+    ref = rn.elbo(spec, X, Y, eps)
+    val, grads = model.elbo_and_gradients((X, Y), eps=eps)
+    assert abs(val - ref) <= 1e-8 * abs(ref)
+    # finite differences on the shared likelihood variance: both experts' contributions must be summed
+    p = model.experts_list[0].gp.likelihood.variance
+    idx = [id(v) for v in model.trainable_variables].index(id(p))
+    u0 = p.unconstrained.copy()
+    h = 1e-5
+    p.assign_unconstrained(u0 + h)
+    vp = model.maximum_log_likelihood_objective((X, Y), eps=eps)
+    p.assign_unconstrained(u0 - h)
+    vm = model.maximum_log_likelihood_objective((X, Y), eps=eps)
+    p.assign_unconstrained(u0)
+    assert float(np.asarray(grads[idx]).reshape(-1)[0]) == pytest.approx((vp - vm) / (2 * h), rel=1e-5)
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+def test_training_reduces_the_loss(flavour):
+    from mogpe_b200._model_core import Adam
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=80, N=128, D=1, F=1, K=2, M=10, S=1, flavour=flavour, num_data=128)
+    model = model_from_spec(spec)
+    model.set_seed(1)
+    model.compile(optimizer=Adam(learning_rate=0.01))
+    first = model.test_step((X, Y), eps=eps)["loss"] if flavour == "keras" else model.training_loss((X, Y), eps=eps)
+    if flavour == "keras":
+        hist = model.fit(X, Y, epochs=30, batch_size=32)
+        assert len(hist["loss"]) == 30
+    else:
+        for _ in range(120):
+            logs = model.train_step((X, Y))
+        assert "loss" in logs
+    last = -model.maximum_log_likelihood_objective((X, Y), eps=eps)
+    assert np.isfinite(last) and last < first - 1.0, (first, last)
+
+
+def test_library_random_stream_replays_through_the_oracle():
+    """eps left to the library's Philox stream: dump the draws and replay them in the oracle."""
+    from oracle import ref_numpy as rn
+    from tests._engine_helpers import engine_from_spec
+
+    spec, X, Y, eps = make_spec(seed=90, N=64, D=2, F=1, K=2, M=8, S=2, num_data=640)
+    eng = engine_from_spec(spec, max_batch=64)
+    eng.set_seed(77)
+    res = eng.elbo(X, Y, "further_gating", 2, 10.0, want_grads=False)
+    eu = eng.debug("eps_u").reshape(eng.P, 2, eng.Mp)
+    eh = eng.debug("eps_h").reshape(2, 64, 1)
+    replay = {"u_experts": [np.transpose(eu[k:k + 1, :, :8], (1, 0, 2)) for k in range(2)], "h": eh}
+    ref = rn.elbo(spec, X, Y, replay)
+    assert abs(res.elbo - ref) <= 1e-8 * abs(ref)
+    res2 = eng.elbo(X, Y, "further_gating", 2, 10.0, want_grads=False)
+    assert res2.elbo != res.elbo  # the stream advances

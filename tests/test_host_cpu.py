@@ -1,0 +1,179 @@
+"""CPU-only tests of the host side: bijectors / Parameter bookkeeping, parameter collection with aliasing,
+the C-ABI library loads and exports every symbol the header declares, loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mogpe_b200 import _lib
+from mogpe_b200 import gpflow_lite as gl
+from oracle import ref_numpy as rn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "mogpe_b200.h")).read()
+    declared = set(re.findall(r"\b(mogpe_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mogpe_status"}
+    lib = _lib.load()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in lib.mogpe_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tests._engine_helpers import engine_from_spec
+    from tests._specs import make_spec
+
+    spec, X, Y, eps = make_spec()
+    with pytest.raises(_lib.MogpeError, match="no CPU fallback"):
+        engine_from_spec(spec, 32)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mogpe_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle's", "").replace("the oracle", ""), os.path.join(dirpath, f)
+
+
+def test_bijectors_match_oracle_definitions():
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(7) * 3
+    pos = gl.positive(lower=1e-6)
+    np.testing.assert_allclose(pos.forward(u), 1e-6 + rn.softplus(u), rtol=1e-15)
+    np.testing.assert_allclose(pos.inverse(pos.forward(u)), u, rtol=1e-10, atol=1e-12)
+    x = rng.standard_normal((2, 15))
+    tri = gl.triangular()
+    np.testing.assert_array_equal(tri.forward(x), rn.fill_triangular(x))
+    np.testing.assert_array_equal(tri.inverse(tri.forward(x)), x)
+    np.testing.assert_array_equal(tri.forward(np.arange(1.0, 7.0)), [[4, 0, 0], [6, 5, 0], [3, 2, 1]])  # TFP docs example
+    # chain rule: finite differences through the bijector
+    g = rng.standard_normal(7)
+    h = 1e-6
+    fd = (pos.forward(u + h) - pos.forward(u - h)) / (2 * h) * g
+    np.testing.assert_allclose(pos.chain_grad(u, g), fd, rtol=1e-6)
+    G = np.tril(rng.standard_normal((2, 5, 5)))
+    gu = tri.chain_grad(x, G)
+    np.testing.assert_allclose(np.sum(gu * x), np.sum(G * tri.forward(x)), rtol=1e-12)  # linear map: <J^T G, x> = <G, J x>
+
+
+def test_parameter_roundtrip_and_errors():
+    p = gl.Parameter([0.5, 2.0], transform=gl.positive())
+    np.testing.assert_allclose(p.numpy(), [0.5, 2.0], rtol=1e-14)
+    p.assign([1.0, 3.0])
+    np.testing.assert_allclose(p.numpy(), [1.0, 3.0], rtol=1e-14)
+    with pytest.raises(ValueError):
+        gl.Parameter(-1.0, transform=gl.positive())
+    with pytest.raises(ValueError):
+        gl.Gaussian(variance=1e-7)  # below the 1e-6 lower bound (mogpe/gps/likelihoods.py:21)
+    with pytest.raises(NotImplementedError):
+        gl.SVGP(gl.RBF(), gl.Gaussian(), np.zeros((3, 1)), q_diag=True)
+    with pytest.raises(NotImplementedError):
+        gl.SVGP(gl.RBF(), gl.Gaussian(), np.zeros((3, 1)), whiten=False)
+    with pytest.raises(ValueError):
+        gl.SVGP(gl.RBF(), gl.Gaussian(), np.zeros((3, 1)), q_mu=np.zeros((4, 1)))
+
+
+def _reference_fixture_model():
+    """tests/keras/test_keras.py:16-108 of the reference: shared kernel / mean / inducing objects, the same
+    expert placed in the list twice."""
+    from mogpe_b200.keras import MixtureOfSVGPExperts, SVGPExpert, SVGPGatingNetwork
+
+    kern = gl.RBF(lengthscales=2 * [3.0], variance=10.0)
+    lik = gl.Gaussian(variance=3.0, variance_lower_bound=1e-6)
+    mean = gl.Constant(c=-2.0)
+    iv = gl.InducingPoints(np.ones((4, 2)))
+    expert = SVGPExpert(kernel=kern, likelihood=lik, mean_function=mean, inducing_variable=iv, num_latent_gps=1,
+                        q_diag=False, q_mu=None, q_sqrt=None, whiten=True)
+    gating = SVGPGatingNetwork(kernel=kern, mean_function=mean, inducing_variable=iv, q_diag=False, q_mu=None,
+                               q_sqrt=None, whiten=True)
+    return MixtureOfSVGPExperts(experts_list=[expert for _ in range(2)], gating_network=gating)
+
+
+def test_reference_fixture_constructs_and_dedupes_aliased_parameters():
+    model = _reference_fixture_model()
+    assert model.num_experts == 2 and model.gating_network.num_experts == 2
+    assert model.bound == "further_gating" and model.num_samples == 1 and model.num_data is None
+    names = sorted(p.name for p in model.trainable_variables)
+    # kernel (2) + likelihood (1) + Z (1) + c (1) shared; q_mu/q_sqrt of the one expert and of the gating net
+    assert names == sorted(["variance", "lengthscales", "variance", "Z", "c", "q_mu", "q_sqrt", "q_mu", "q_sqrt"])
+    assert np.array_equal(model.experts_list[0].gp.q_sqrt.numpy()[0], np.eye(4))
+    with pytest.raises(AssertionError):
+        from mogpe_b200.keras import MixtureOfSVGPExperts
+
+        MixtureOfSVGPExperts(model.experts_list + model.experts_list[:1], model.gating_network)  # 3 experts, Bernoulli gate
+
+
+def test_gating_likelihood_is_inferred_from_kernel_type():
+    from mogpe_b200.keras import SVGPGatingNetwork
+
+    iv = gl.InducingPoints(np.zeros((3, 1)))
+    assert isinstance(SVGPGatingNetwork(gl.RBF(), iv).gp.likelihood, gl.Bernoulli)
+    g3 = SVGPGatingNetwork(gl.SeparateIndependent([gl.RBF() for _ in range(3)]), iv)
+    assert isinstance(g3.gp.likelihood, gl.Softmax) and g3.num_experts == 3 and g3.num_gating_gps == 3
+    g4 = SVGPGatingNetwork(gl.SharedIndependent(gl.RBF(), 4), iv)
+    assert g4.num_experts == 4 and len(g4.gp.latent_kernel_list) == 1
+
+
+def test_legacy_constructors_and_validation():
+    from mogpe_b200.experts import SVGPExpert, SVGPExperts
+    from mogpe_b200.gating_networks import SVGPGatingNetwork
+    from mogpe_b200.mixture_of_experts import MixtureOfSVGPExperts
+
+    Z = np.linspace(-1, 1, 6)[:, None]
+    experts = SVGPExperts([SVGPExpert(gl.RBF(), gl.Gaussian(0.1), Z.copy()) for _ in range(2)])
+    with pytest.raises(AttributeError):
+        SVGPGatingNetwork(gl.RBF(), gl.Gaussian(), Z.copy(), None)
+    gate = SVGPGatingNetwork(gl.RBF(), gl.Bernoulli(), Z.copy(), None)
+    model = MixtureOfSVGPExperts(gate, experts, num_data=100, num_samples=2, bound="further")
+    assert model.num_experts == 2 and len(experts.noise_variances()) == 2
+    assert len(model.trainable_variables) == 2 * 6 + 5  # per expert: kernel(2) lik Z q_mu q_sqrt; gate: kernel(2) Z q_mu q_sqrt
+    u = experts.experts_list[0].sample_inducing_points(3, eps_u=np.zeros((3, 1, 6)))
+    assert u.shape == (3, 6, 1) and not np.any(u)
+    model.bound = "tight_2"
+    with pytest.raises(NotImplementedError):
+        model._bound_name()
+    with pytest.raises(RuntimeError):
+        SVGPExpert(gl.RBF(), gl.Gaussian(0.1), Z.copy()).predict_f(Z)  # not attached to a model
+
+
+def test_adam_matches_tf_defaults_on_a_quadratic():
+    from mogpe_b200._model_core import Adam
+
+    p = gl.Parameter(np.array([1.0, -2.0]))
+    opt = Adam(learning_rate=0.1)
+    m = v = np.zeros(2)
+    x = np.array([1.0, -2.0])
+    for t in range(1, 6):
+        g = 2 * x
+        opt.apply_gradients([(2 * p.unconstrained, p)])
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        x = x - 0.1 * np.sqrt(1 - 0.999**t) / (1 - 0.9**t) * m / (np.sqrt(v) + 1e-7)
+        np.testing.assert_allclose(p.unconstrained, x, rtol=1e-12)
+
+
+def test_mixture_distribution_matches_tfp_formulas():
+    from mogpe_b200._model_core import MixtureDistribution
+
+    rng = np.random.default_rng(1)
+    pi = rng.dirichlet(np.ones(3), 5)
+    mu, sd = rng.standard_normal((5, 2, 3)), rng.uniform(0.5, 2.0, (5, 2, 3))
+    mean = (pi[:, None] * mu).sum(-1)
+    var = (pi[:, None] * sd**2).sum(-1) + (pi[:, None] * mu**2).sum(-1) - mean**2
+    d = MixtureDistribution(pi, mu, sd, mean, var)
+    y = rng.standard_normal((5, 2))
+    joint = np.log(sum(pi[:, k] * np.prod(np.exp(-0.5 * ((y - mu[..., k]) / sd[..., k]) ** 2) / (sd[..., k] * np.sqrt(2 * np.pi)), -1)
+                       for k in range(3)))
+    np.testing.assert_allclose(d.log_prob(y), joint, rtol=1e-12)
+    assert d.sample(4, rng).shape == (4, 5, 2)
