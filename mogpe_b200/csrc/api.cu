@@ -373,10 +373,10 @@ static cudaError_t hgemm(mogpe_handle* h, const GemmParams& p, int batch, bool t
 static mogpe_status factorise(mogpe_handle* h, const double* params, cudaStream_t st) {
   const int Q = h->md_host.Q, P = h->md_host.P, Mp = h->Mp;
   kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
-  for (int j = 0; j < Mp / 32; j++)
+  for (int j = -1; j < Mp / 32; j++)
     chol_inv_step_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, j);
   prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->Sc);
-  KCOUNT(h, 2 + Mp / 32);
+  KCOUNT(h, 3 + Mp / 32);
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
 }
@@ -583,8 +583,13 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.M = Mp; p.N = Mp; p.K = Mp; p.kmode = KM_RIGHT_LOWER;
     H_CUDA(h, hgemm(h, p, Q, false, false, st, (double)Q * Mp * Mp * Mp));
   }
-  kuu_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
-  kuf_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+  if (md.D <= 4) {
+    kuu_grad_kernel<4><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
+    kuf_grad_kernel<4><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+  } else {
+    kuu_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
+    kuf_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+  }
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
 }

@@ -102,147 +102,202 @@ __global__ void kuf_kernel(const ModelDev* __restrict__ md, const double* __rest
 // Reads Kuu, writes L / Linv (separate buffers: no read/write race on the diagonal block).
 // grid (Mp/32, Q), block 256.
 // ------------------------------------------------------------------------------------------------
-constexpr int CHOL_CH = 64;  // k-chunk of the block products
-constexpr size_t CHOL_SMEM_BYTES = (32 * (CHOL_CH + 1) + CHOL_CH * 33 + 2 * 32 * 33) * sizeof(double);
-static_assert(CHOL_CH * 33 >= 32 * (CHOL_CH + 1), "Pb must fit in the Pc region");
+constexpr int CHOL_CH = 128;          // k-chunk of the block products (one cp.async round trip each)
+constexpr int CHOL_PA = CHOL_CH + 4;  // row pitch = 4 (mod 16) doubles: conflict-free DMMA fragment reads
+constexpr int CHOL_PC = 36;
+constexpr size_t CHOL_SMEM_BYTES = (32 * CHOL_PA + CHOL_CH * CHOL_PC + 2 * 32 * 33) * sizeof(double);
+static_assert(CHOL_CH * CHOL_PC >= 32 * CHOL_PA, "Pb must fit in the Pc region");
 
-// In-place Cholesky of a 32x32 block in shared memory by 256 threads (lower triangle valid on exit).
-__device__ __forceinline__ void chol32_smem(double (*Dg)[33], int tid) {
+__device__ __forceinline__ void cp_async16_k(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all_k() { asm volatile("cp.async.wait_all;\n" ::); }
+
+__device__ __forceinline__ void dmma884_k(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Cholesky of a 32x32 block held in shared memory, by ONE warp: lane r keeps row r in registers, pivots and
+// multipliers travel by shuffles (no block barriers on the sequential critical path).  rdiag[c] = 1 / L[c][c].
+__device__ __forceinline__ void chol32_warp(double (*Dg)[33], double* rdiag, int lane) {
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) a[c] = Dg[lane][c];
+#pragma unroll
   for (int c = 0; c < 32; c++) {
-    __syncthreads();
-    const double d = sqrt(Dg[c][c]);
-    __syncthreads();
-    if (tid == 0) Dg[c][c] = d;
-    if (tid > c && tid < 32) Dg[tid][c] /= d;
-    __syncthreads();
-    // trailing update: element (r, cc), c < cc <= r < 32
-    for (int t = tid; t < 1024; t += 256) {
-      const int r = t >> 5, cc = t & 31;
-      if (cc > c && cc <= r) Dg[r][cc] -= Dg[r][c] * Dg[cc][c];
+    const double piv = __shfl_sync(0xffffffffu, a[c], c);
+    const double rs = rsqrt(piv);  // NaN for a non-positive pivot (not positive definite): propagates to the ELBO
+    a[c] = (lane == c) ? piv * rs : a[c] * rs;  // rows above the pivot hold junk in column c; never read
+    if (lane == c) rdiag[c] = rs;
+#pragma unroll
+    for (int cc = c + 1; cc < 32; cc++) {
+      const double lcc = __shfl_sync(0xffffffffu, a[c], cc);  // L[cc][c]
+      a[cc] -= a[c] * lcc;
     }
   }
-  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 32; c++) Dg[lane][c] = (c <= lane) ? a[c] : 0.0;
 }
 
-// Solve T x = b for 32 right-hand sides held as columns of Rb (in place), T lower-triangular 32x32 in smem.
-// 256 threads = 32 columns x 8 lanes; the dot product over earlier rows is split over the 8 lanes.
-__device__ __forceinline__ void trsm32_lower_cols(const double (*T)[33], double (*Rb)[33], int tid) {
-  const int c = tid >> 3, sub = tid & 7;
+// Solve T y = b for the 32 columns of Rb in place (T lower-triangular 32x32 in smem), ONE warp, lane = column.
+// Right-looking: once y[r] is known it is eliminated from all later rows (independent FMAs).
+__device__ __forceinline__ void trsm32_cols_warp(const double (*T)[33], const double* rdiag, double (*Rb)[33], int lane) {
+  double y[32];
+#pragma unroll
+  for (int r = 0; r < 32; r++) y[r] = Rb[r][lane];
+#pragma unroll
   for (int r = 0; r < 32; r++) {
-    double s = 0;
-    for (int t = sub; t < r; t += 8) s += T[r][t] * Rb[t][c];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    __syncthreads();
-    if (sub == 0) Rb[r][c] = (Rb[r][c] - s) / T[r][r];
-    __syncthreads();
+    y[r] *= rdiag[r];
+#pragma unroll
+    for (int rr = r + 1; rr < 32; rr++) y[rr] -= T[rr][r] * y[r];
   }
+#pragma unroll
+  for (int r = 0; r < 32; r++) Rb[r][lane] = y[r];
 }
 
-__global__ void __launch_bounds__(256) chol_inv_step_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
-                                                             double* __restrict__ Linv, int Mp, int j) {
-  // dynamic smem (CHOL_SMEM_BYTES): Pa | Pb/Pc (never live together) | Dg | Cg
-  extern __shared__ double chol_smem[];
-  double(*Pa)[CHOL_CH + 1] = reinterpret_cast<double(*)[CHOL_CH + 1]>(chol_smem);
-  double(*Pb)[CHOL_CH + 1] = reinterpret_cast<double(*)[CHOL_CH + 1]>(chol_smem + 32 * (CHOL_CH + 1));
-  double(*Pc)[33] = reinterpret_cast<double(*)[33]>(chol_smem + 32 * (CHOL_CH + 1));  // Linv[k, b] chunk (k rows)
-  double(*Dg)[33] = reinterpret_cast<double(*)[33]>(chol_smem + 32 * (CHOL_CH + 1) + CHOL_CH * 33);
+// Step j of the fused Cholesky + inverse (launch j = -1 .. Mp/32 - 1), grid (Mp/32, Q), block 256.
+//   B-part, CTA b != j (j >= 0): one 32x32 block product on the DMMA pipe, then a 32x32x32 multiply with the
+//     already-known Ljj^-1 -- no triangular solve:
+//        b > j : L[b,j]    = (Kuu[b,j] - sum_{k<j} L[b,k] L[j,k]^T) Ljj^-T
+//        b < j : Linv[j,b] = -Ljj^-1 sum_{k=b}^{j-1} L[j,k] Linv[k,b]
+//   A-part (look-ahead), CTA b == j+1: it already streams row block j+1 of L for its B-part, so it accumulates
+//     sum_{k<j} L[j+1,k] L[j+1,k]^T in the same sweep, adds the outer product of the block it just produced,
+//     factors the NEXT diagonal block and inverts it (one warp, registers + shuffles).
+// The 32x32 outputs are split over the 8 warps (fragment row i = warp/2, fragment columns 2*(warp%2) + {0,1}):
+// no cross-warp reduction, deterministic, 8 accumulator registers per product.
+// The only sequential work per launch is one block product + one 32x32 factor/invert by ONE CTA per group.
+__global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
+                                                                double* __restrict__ Linv, int Mp, int j) {
+  extern __shared__ __align__(16) double chol_smem[];  // Pa | Pb/Pc (never live together) | Dg | Cg
+  __shared__ double rdiag[32];
+  double(*Pa)[CHOL_PA] = reinterpret_cast<double(*)[CHOL_PA]>(chol_smem);
+  double(*Pb)[CHOL_PA] = reinterpret_cast<double(*)[CHOL_PA]>(chol_smem + 32 * CHOL_PA);
+  double(*Pc)[CHOL_PC] = reinterpret_cast<double(*)[CHOL_PC]>(chol_smem + 32 * CHOL_PA);  // Linv[k, b] chunk (k rows)
+  double(*Dg)[33] = reinterpret_cast<double(*)[33]>(chol_smem + 32 * CHOL_PA + CHOL_CH * CHOL_PC);
   double(*Cg)[33] = Dg + 32;
-  const int g = blockIdx.y, b = blockIdx.x;
+  const int g = blockIdx.y, nb = Mp / 32;
+  const int b = (blockIdx.x + j + 1) % nb;  // the look-ahead CTA (critical path) is scheduled first
   const double* Kg = Kuu + (long long)g * Mp * Mp;
   double* Lg = L + (long long)g * Mp * Mp;
   double* Xg = Linv + (long long)g * Mp * Mp;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const int d = j + 1;
+  const bool do_b = (j >= 0) && (b != j), do_a = (b == d) && (d < nb);
+  if (!do_b && !do_a) return;
+  const int fi = warp >> 1, fq0 = (warp & 1) * 2;  // this warp's output fragments
   double accC[2][2] = {{0, 0}, {0, 0}}, accD[2][2] = {{0, 0}, {0, 0}};
-  const int kend = j * 32;
-  // ---- D (all CTAs) and C (b > j): products over k < j*32 of rows of L
-  for (int k0 = 0; k0 < kend; k0 += CHOL_CH) {
-    const int kw = min(CHOL_CH, kend - k0);
-    for (int t = tid; t < 32 * CHOL_CH; t += 256) {
-      const int r = t / CHOL_CH, c = t % CHOL_CH;
-      const bool in = c < kw;
-      Pa[r][c] = in ? Lg[(long long)(j * 32 + r) * Mp + k0 + c] : 0.0;
-      if (b > j) Pb[r][c] = in ? Lg[(long long)(b * 32 + r) * Mp + k0 + c] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < CHOL_CH; k++) {
-      const double d0 = Pa[ty * 2][k], d1 = Pa[ty * 2 + 1][k];
-      const double b0 = Pa[tx * 2][k], b1 = Pa[tx * 2 + 1][k];
-      accD[0][0] += d0 * b0; accD[0][1] += d0 * b1; accD[1][0] += d1 * b0; accD[1][1] += d1 * b1;
+
+  if (do_b) {
+    const int kend = j * 32, kbeg = (b > j) ? 0 : b * 32;
+    for (int k0 = kbeg; k0 < kend; k0 += CHOL_CH) {
+      const int kw = min(CHOL_CH, kend - k0);  // multiple of 32
+      for (int t = tid; t < 32 * (kw / 2); t += 256) {
+        const int r = t / (kw / 2), c = (t % (kw / 2)) * 2;
+        cp_async16_k(&Pa[r][c], Lg + (long long)(j * 32 + r) * Mp + k0 + c);
+        if (b > j) cp_async16_k(&Pb[r][c], Lg + (long long)(b * 32 + r) * Mp + k0 + c);
+      }
+      if (b < j)
+        for (int t = tid; t < kw * 16; t += 256) {
+          const int r = t >> 4, c = (t & 15) * 2;
+          cp_async16_k(&Pc[r][c], Xg + (long long)(k0 + r) * Mp + b * 32 + c);
+        }
+      cp_async_wait_all_k();
+      __syncthreads();
       if (b > j) {
-        const double a0 = Pb[ty * 2][k], a1 = Pb[ty * 2 + 1][k];
-        accC[0][0] += a0 * b0; accC[0][1] += a0 * b1; accC[1][0] += a1 * b0; accC[1][1] += a1 * b1;
-      }
-    }
-    __syncthreads();
-  }
-  // ---- R (b < j): sum_{k = b*32}^{j*32} L[j, k] Linv[k, b-block]
-  if (b < j) {
-    for (int k0 = b * 32; k0 < kend; k0 += CHOL_CH) {
-      const int kw = min(CHOL_CH, kend - k0);
-      for (int t = tid; t < 32 * CHOL_CH; t += 256) {
-        const int r = t / CHOL_CH, c = t % CHOL_CH;
-        Pa[r][c] = (c < kw) ? Lg[(long long)(j * 32 + r) * Mp + k0 + c] : 0.0;
-      }
-      for (int t = tid; t < CHOL_CH * 32; t += 256) {
-        const int r = t >> 5, c = t & 31;
-        Pc[r][c] = (r < kw) ? Xg[(long long)(k0 + r) * Mp + b * 32 + c] : 0.0;
+#pragma unroll 4
+        for (int k = lc; k < kw; k += 4) {  // C += L[b,k] L[j,k]^T ; look-ahead: D += L[b,k] L[b,k]^T
+          const double a = Pb[fi * 8 + lr][k];
+          dmma884_k(accC[0][0], accC[0][1], a, Pa[fq0 * 8 + lr][k]);
+          dmma884_k(accC[1][0], accC[1][1], a, Pa[(fq0 + 1) * 8 + lr][k]);
+          if (do_a) {
+            dmma884_k(accD[0][0], accD[0][1], a, Pb[fq0 * 8 + lr][k]);
+            dmma884_k(accD[1][0], accD[1][1], a, Pb[(fq0 + 1) * 8 + lr][k]);
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int k = lc; k < kw; k += 4) {  // R += L[j,k] Linv[k,b]
+          const double a = Pa[fi * 8 + lr][k];
+          dmma884_k(accC[0][0], accC[0][1], a, Pc[k][fq0 * 8 + lr]);
+          dmma884_k(accC[1][0], accC[1][1], a, Pc[k][(fq0 + 1) * 8 + lr]);
+        }
       }
       __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int r = fi * 8 + lr, c = (fq0 + u) * 8 + lc * 2;
+      const double2 base = (b > j) ? *reinterpret_cast<const double2*>(Kg + (long long)(b * 32 + r) * Mp + j * 32 + c)
+                                   : make_double2(0.0, 0.0);
+      Cg[r][c] = base.x - accC[u][0];
+      Cg[r][c + 1] = base.y - accC[u][1];
+    }
+    for (int t = tid; t < 1024; t += 256)
+      Dg[t >> 5][t & 31] = Xg[(long long)(j * 32 + (t >> 5)) * Mp + j * 32 + (t & 31)];  // Ljj^-1 (previous launch)
+    __syncthreads();
+    double o[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int t = tid + u * 256, r = t >> 5, c = t & 31;
+      double sum = 0;
+      if (b > j) {
 #pragma unroll 8
-      for (int k = 0; k < CHOL_CH; k++) {
-        const double a0 = Pa[ty * 2][k], a1 = Pa[ty * 2 + 1][k];
-        const double b0 = Pc[k][tx * 2], b1 = Pc[k][tx * 2 + 1];
-        accC[0][0] += a0 * b0; accC[0][1] += a0 * b1; accC[1][0] += a1 * b0; accC[1][1] += a1 * b1;
+        for (int q = 0; q < 32; q++) sum += Cg[r][q] * Dg[c][q];  // C Ljj^-T
+      } else {
+#pragma unroll 8
+        for (int q = 0; q < 32; q++) sum += Dg[r][q] * Cg[q][c];  // Ljj^-1 (-R)
       }
-      __syncthreads();
+      o[u] = sum;
     }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int t = tid + u * 256, r = t >> 5, c = t & 31;
+      if (b > j) {
+        Lg[(long long)(b * 32 + r) * Mp + j * 32 + c] = o[u];
+        Lg[(long long)(j * 32 + r) * Mp + b * 32 + c] = 0.0;   // mirrored upper block of L
+        Xg[(long long)(j * 32 + r) * Mp + b * 32 + c] = 0.0;   // and of Linv
+        Cg[r][c] = o[u];                                        // keep L[b,j] for the look-ahead
+      } else {
+        Xg[(long long)(j * 32 + r) * Mp + b * 32 + c] = o[u];
+      }
+    }
+    if (!do_a) return;
+    __syncthreads();
   }
+
+  // ---- A-part: D = Kuu[d,d] - sum_{k<j*32} L[d,k] L[d,k]^T (accD) - L[d,j] L[d,j]^T (block just produced, in Cg)
 #pragma unroll
-  for (int a = 0; a < 2; a++)
-#pragma unroll
-    for (int c2 = 0; c2 < 2; c2++) {
-      const int r = ty * 2 + a, c = tx * 2 + c2;
-      Dg[r][c] = Kg[(long long)(j * 32 + r) * Mp + j * 32 + c] - accD[a][c2];
-      if (b > j) Cg[r][c] = Kg[(long long)(b * 32 + r) * Mp + j * 32 + c] - accC[a][c2];
-      else if (b < j) Cg[r][c] = -accC[a][c2];
-      else Cg[r][c] = (r == c) ? 1.0 : 0.0;
+  for (int u = 0; u < 2; u++) {
+    const int r = fi * 8 + lr, c = (fq0 + u) * 8 + lc * 2;
+    const double2 base = *reinterpret_cast<const double2*>(Kg + (long long)(d * 32 + r) * Mp + d * 32 + c);
+    double s0 = 0, s1 = 0;
+    if (j >= 0) {
+#pragma unroll 8
+      for (int q = 0; q < 32; q++) {
+        s0 += Cg[r][q] * Cg[c][q];
+        s1 += Cg[r][q] * Cg[c + 1][q];
+      }
     }
-  chol32_smem(Dg, tid);
-  if (b > j) {
-    // X Ljj^T = C  <=>  Ljj X^T = C^T : transpose C in place, solve columns, write back transposed
-    __syncthreads();
-    double v[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int t = tid + q * 256;
-      v[q] = Cg[t & 31][t >> 5];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int t = tid + q * 256;
-      Cg[t >> 5][t & 31] = v[q];
-    }
-    __syncthreads();
-    trsm32_lower_cols(Dg, Cg, tid);
-    for (int t = tid; t < 1024; t += 256) {
-      const int r = t >> 5, c = t & 31;
-      Lg[(long long)(b * 32 + r) * Mp + j * 32 + c] = Cg[c][r];
-      Lg[(long long)(j * 32 + r) * Mp + b * 32 + c] = 0.0;   // mirrored upper block of L
-      Xg[(long long)(j * 32 + r) * Mp + b * 32 + c] = 0.0;   // and of Linv
-    }
-  } else {
-    // Ljj Y = Cg  (Cg = I -> Ljj^-1 ;  Cg = -R -> Linv[j, b])
-    __syncthreads();
-    trsm32_lower_cols(Dg, Cg, tid);
-    for (int t = tid; t < 1024; t += 256) {
-      const int r = t >> 5, c = t & 31;
-      Xg[(long long)(j * 32 + r) * Mp + b * 32 + c] = Cg[r][c];
-      if (b == j) Lg[(long long)(j * 32 + r) * Mp + j * 32 + c] = (c <= r) ? Dg[r][c] : 0.0;
-    }
+    Dg[r][c] = base.x - accD[u][0] - s0;
+    Dg[r][c + 1] = base.y - accD[u][1] - s1;
+  }
+  __syncthreads();
+  for (int t = tid; t < 1024; t += 256) Cg[t >> 5][t & 31] = ((t >> 5) == (t & 31)) ? 1.0 : 0.0;
+  __syncthreads();
+  if (tid < 32) {
+    chol32_warp(Dg, rdiag, tid);
+    __syncwarp();
+    trsm32_cols_warp(Dg, rdiag, Cg, tid);  // Ldd Y = I
+  }
+  __syncthreads();
+  for (int t = tid; t < 1024; t += 256) {
+    const int r = t >> 5, c = t & 31;
+    Lg[(long long)(d * 32 + r) * Mp + d * 32 + c] = Dg[r][c];
+    Xg[(long long)(d * 32 + r) * Mp + d * 32 + c] = Cg[r][c];
   }
 }
 
@@ -304,6 +359,7 @@ __global__ void __launch_bounds__(128) a_stats_kernel(const ModelDev* __restrict
     for (int t = threadIdx.x; t < nv * Mp; t += 128) vs[t] = V[(long long)md->gvec[v0 + t / Mp] * Mp + (t % Mp)];
     __syncthreads();
     double ss = 0, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
     for (int m = 0; m < Mp; m++) {
       const double a = Ag[(long long)m * Bp];
       ss += a * a;
@@ -327,9 +383,12 @@ __global__ void __launch_bounds__(128) col_sumsq_kernel(const ModelDev* __restri
   const int n = blockIdx.x * 128 + threadIdx.x;
   const double* p = LTA + (long long)slot * Mp * Bp + n;
   double ss = 0;
-  for (int m = 0; m < Mp; m++) {
-    const double a = p[(long long)m * Bp];
-    ss += a * a;
+  for (int m = 0; m < Mp; m += 8) {
+    double a[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) a[u] = p[(long long)(m + u) * Bp];
+#pragma unroll
+    for (int u = 0; u < 8; u++) ss += a[u] * a[u];
   }
   varq[(long long)l * Bp + n] = ss;
 }
@@ -540,16 +599,25 @@ __global__ void __launch_bounds__(256) kuf_grad_kernel(const ModelDev* __restric
     a1[d] = a2[d] = 0.0;
   }
   double se = 0;
-  for (int n = lane; n < N; n += 32) {
-    const double e = w[n] * kf[n];
-    se += e;
+  for (int n0 = lane; n0 < N; n0 += 128) {  // 4 independent elements per lane in flight
+    double e[4];
 #pragma unroll
-    for (int d = 0; d < DMAX; d++)
-      if (d < D) {
-        const double df = zz[d] - X[(long long)n * D + d];
-        a1[d] += e * df;
-        a2[d] += e * df * df;
-      }
+    for (int u = 0; u < 4; u++) {
+      const int n = n0 + u * 32;
+      e[u] = (n < N) ? w[n] * kf[n] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int n = min(n0 + u * 32, N - 1);
+      se += e[u];
+#pragma unroll
+      for (int d = 0; d < DMAX; d++)
+        if (d < D) {
+          const double df = zz[d] - X[(long long)n * D + d];
+          a1[d] += e[u] * df;
+          a2[d] += e[u] * df * df;
+        }
+    }
   }
   se = warp_sum(se);
   if (lane == 0) atomicAdd(grads + lo.kvar + g, se / params[lo.kvar + g]);
