@@ -278,9 +278,10 @@ template <bool TA, bool TB>
 inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st, int cfg) {
   if (cfg < 0) cfg = gemm_cfg_override();
   if (cfg < 0) {
-    // measured on B200 (tools/gemm_bench.py, profiles/gemm_sweep_r01.txt): 64x128 tiles (2 CTAs/SM, 16 warps)
-    // are fastest for the [M x M] x [M x B] products, 64x64 for triangular results and M^3 products
-    cfg = (!p.tril_out && p.N % 128 == 0 && p.N >= 1024) ? 2 : 1;
+    // measured on B200 (tools/gemm_bench.py, profiles/gemm_sweep_r01.txt): 64x64 tiles win everywhere because
+    // 4 CTAs/SM (16 warps with independent barriers) keep the DMMA pipe fed; BK = 32 with 3 stages is best for the
+    // long-K products with a triangular result and for the M^3 products, BK = 16 with 2 stages for [M x M] x [M x B]
+    cfg = (p.K % 32 == 0 && (p.tril_out || p.N < 1024)) ? 11 : 7;
   }
   const bool ok128 = (p.M % 128 == 0) && (p.N % 128 == 0);
   switch (cfg) {
@@ -289,6 +290,12 @@ inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st
     case 3: if (p.M % 128 == 0) return launch_gemm_cfg<128, 64, 16, 32, 32, TA, TB, 4>(p, batch, st); break;
     case 4: if (ok128) return launch_gemm_cfg<128, 128, 16, 32, 32, TA, TB, 3>(p, batch, st); break;
     case 5: if (ok128) return launch_gemm_cfg<128, 128, 16, 64, 32, TA, TB, 4>(p, batch, st); break;
+    case 6: return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 3>(p, batch, st);
+    case 7: return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 2>(p, batch, st);
+    case 8: if (p.N % 128 == 0 && p.K % 32 == 0) return launch_gemm_cfg<64, 128, 32, 32, 32, TA, TB, 2>(p, batch, st); break;
+    case 9: if (p.N % 128 == 0) return launch_gemm_cfg<64, 128, 16, 32, 32, TA, TB, 3>(p, batch, st); break;
+    case 10: if (p.K % 32 == 0) return launch_gemm_cfg<64, 64, 32, 32, 32, TA, TB, 2>(p, batch, st); break;
+    case 11: if (p.K % 32 == 0) return launch_gemm_cfg<64, 64, 32, 32, 32, TA, TB, 3>(p, batch, st); break;
     default: break;
   }
   return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 4>(p, batch, st);
