@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -41,6 +42,7 @@ struct mogpe_handle {
   double *V = nullptr, *dV = nullptr;                              // [NVcap][Mp]
   double *mean = nullptr, *dmean = nullptr;                        // [NVcap][Bp]
   double *var0ss = nullptr, *varq = nullptr, *dfvar = nullptr;     // [Q|P][Bp]
+  double *ss_part = nullptr, *lta_part = nullptr, *dot_part = nullptr;  // [Q|P|NVcap][Mp/64][Bp] epilogue partials
   int NVcap = 0;
   int *d_lta_latent = nullptr, *d_lta_group = nullptr, *d_latent_group = nullptr;
   // rounds of the Abar accumulation: round r holds the r-th marginal latent of every group
@@ -98,7 +100,8 @@ extern "C" const char* mogpe_last_error(const mogpe_handle* h) { return h ? h->e
 static void free_ws(mogpe_handle* h) {
   double** ptrs[] = {&h->Kuu, &h->L, &h->Linv, &h->Lbar, &h->T1, &h->T2, &h->Kuf, &h->A, &h->Abar, &h->W,
                      &h->LTA, &h->Sc, &h->V, &h->dV, &h->mean, &h->dmean, &h->var0ss, &h->varq, &h->dfvar,
-                     &h->stage_dev, &h->out_dev, &h->eps_u_int, &h->eps_h_int, &h->eps_f_int};
+                     &h->stage_dev, &h->out_dev, &h->eps_u_int, &h->eps_h_int, &h->eps_f_int, &h->ss_part, &h->lta_part,
+                     &h->dot_part};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -207,6 +210,8 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (e == cudaSuccess) e = dalloc(&h->var0ss, (size_t)Q * h->Bp);
   if (e == cudaSuccess) e = dalloc(&h->varq, (size_t)P * h->Bp);
   if (e == cudaSuccess) e = dalloc(&h->dfvar, (size_t)P * h->Bp);
+  if (e == cudaSuccess) e = dalloc(&h->ss_part, (size_t)Q * (Mp / 64) * h->Bp);
+  if (e == cudaSuccess) e = dalloc(&h->lta_part, (size_t)P * (Mp / 64) * h->Bp);
   if (e == cudaSuccess) e = dalloc(&h->d_lta_latent, (size_t)MAXP);
   if (e == cudaSuccess) e = dalloc(&h->d_lta_group, (size_t)MAXP);
   if (e == cudaSuccess) e = dalloc(&h->d_latent_group, (size_t)MAXP);
@@ -300,7 +305,7 @@ static mogpe_status set_mode(mogpe_handle* h, int bound, int S, cudaStream_t st)
   md.gvec_begin[md.Q] = pos;
   md.glat_begin[md.Q] = lp;
   if (nv > h->NVcap) {
-    for (double** p : {&h->V, &h->dV, &h->mean, &h->dmean}) {
+    for (double** p : {&h->V, &h->dV, &h->mean, &h->dmean, &h->dot_part}) {
       if (*p) cudaFree(*p);
       *p = nullptr;
     }
@@ -308,6 +313,7 @@ static mogpe_status set_mode(mogpe_handle* h, int bound, int S, cudaStream_t st)
     H_CUDA(h, dalloc(&h->dV, (size_t)nv * h->Mp));
     H_CUDA(h, dalloc(&h->mean, (size_t)nv * h->Bp));
     H_CUDA(h, dalloc(&h->dmean, (size_t)nv * h->Bp));
+    H_CUDA(h, dalloc(&h->dot_part, (size_t)nv * (h->Mp / 64) * h->Bp));
     h->NVcap = nv;
   }
   // synchronous small uploads (mode changes are rare: once per (bound, S))
@@ -345,11 +351,14 @@ static GemmParams gp_init() {
 
 // GEMM launch through the handle: counts launches and, with profiling on, brackets it with CUDA events.
 // `flops` is the ALGORITHMIC work of the operation (triangular operands counted as triangular).
+// [M x M] x [M x B] products with fused column statistics always use this configuration (BM = GEMM_STAT_BM = 64)
+constexpr int STAT_CFG = 7;
+
 static cudaError_t hgemm(mogpe_handle* h, const GemmParams& p, int batch, bool ta, bool tb, cudaStream_t st,
-                         double flops) {
+                         double flops, int cfg = -1) {
   h->gemm_launches++;
   h->all_launches++;
-  if (!h->prof) return launch_gemm(p, batch, ta, tb, st);
+  if (!h->prof) return launch_gemm(p, batch, ta, tb, st, cfg);
   if (h->ev_used + 2 > h->ev.size()) {
     for (int i = 0; i < 64; i++) {
       cudaEvent_t e;
@@ -360,7 +369,7 @@ static cudaError_t hgemm(mogpe_handle* h, const GemmParams& p, int batch, bool t
   }
   h->prof_stream = st;
   cudaEventRecord(h->ev[h->ev_used], st);
-  cudaError_t rc = launch_gemm(p, batch, ta, tb, st);
+  cudaError_t rc = launch_gemm(p, batch, ta, tb, st, cfg);
   cudaEventRecord(h->ev[h->ev_used + 1], st);
   h->ev_used += 2;
   h->prof_flops += flops;
@@ -395,7 +404,11 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
     p.B = h->Kuf;  p.sB = (long long)Mp * h->Bp; p.ldb = h->Bp;
     p.C = h->A;    p.sC = (long long)Mp * h->Bp; p.ldc = h->Bp;
     p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_LOWER;
-    H_CUDA(h, hgemm(h, p, Q, false, false, st, (double)Q * Mp * Mp * Bc));
+    // fused epilogue: per-row-block partials of sum_m A^2 and of the means A^T V (no second pass over A)
+    p.stat_ss = h->ss_part; p.stat_dot = h->dot_part; p.statV = h->V; p.ldstat = h->Bp;
+    p.statvec_begin = reinterpret_cast<const int*>(reinterpret_cast<const char*>(h->d_md) + offsetof(ModelDev, gvec_begin));
+    p.statvec = reinterpret_cast<const int*>(reinterpret_cast<const char*>(h->d_md) + offsetof(ModelDev, gvec));
+    H_CUDA(h, hgemm(h, p, Q, false, false, st, (double)Q * Mp * Mp * Bc, STAT_CFG));
   }
   if (md.nlta > 0) {
     GemmParams p = gp_init();
@@ -403,13 +416,13 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
     p.B = h->A;   p.sB = (long long)Mp * h->Bp; p.ldb = h->Bp; p.mapB = h->d_lta_group;
     p.C = h->LTA; p.sC = (long long)Mp * h->Bp; p.ldc = h->Bp;
     p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_UPPER;
-    H_CUDA(h, hgemm(h, p, md.nlta, true, false, st, (double)md.nlta * Mp * Mp * Bc));
-    KCOUNT(h, 1);
-    col_sumsq_kernel<<<dim3(Bc / 128, md.nlta), 128, 0, st>>>(h->d_md, h->LTA, h->Bp, h->varq);
+    p.stat_ss = h->lta_part; p.ldstat = h->Bp;  // sum_m LTA^2 partials
+    H_CUDA(h, hgemm(h, p, md.nlta, true, false, st, (double)md.nlta * Mp * Mp * Bc, STAT_CFG));
   }
-  KCOUNT(h, 2);  // kuf + a_stats
-  a_stats_kernel<<<dim3(Bc / 128, Q), 128, 8 * Mp * sizeof(double), st>>>(h->d_md, params, h->lo, h->A, h->V, h->Bp,
-                                                                          h->var0ss, h->mean);
+  KCOUNT(h, 2);  // kuf + stats_finish
+  stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + md.nlta), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, h->dot_part,
+                                                                           h->lta_part, Mp / GEMM_STAT_BM, h->Bp, h->var0ss,
+                                                                           h->mean, h->varq);
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
 }
@@ -505,10 +518,9 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   // (a) q_sqrt gradient of marginal latents: Sbar_l = tril(A (2 LTA_l diag(dfvar_l))^T); scaling fused in the
   //     epilogue via alpha and into the B operand... done as: Sbar_l = 2 * tril(A_g diag(dfvar_l) LTA_l^T)
   //     => scale LTA in place first (it is also the B operand of Abar += S_l dLTA_l).
-  build_abar_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, 0, st>>>(h->d_md, h->A, h->V, h->dmean, h->dfvar, Bp, h->Abar);
   H_CUDA(h, cudaMemsetAsync(h->dV, 0, (size_t)md.NV * Mp * sizeof(double), st));
-  dV_kernel<<<dim3((Bc + 1023) / 1024, Mp / 32, Q), 256, 0, st>>>(h->d_md, h->A, h->dmean, Bp, Bc, h->dV);
-  KCOUNT(h, 6);  // build_abar, dV, q_grads, halve_diag, kuu_grad, kuf_grad
+  build_abar_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, 0, st>>>(h->d_md, h->A, h->V, h->dmean, h->dfvar, Bp, h->Abar, h->dV);
+  KCOUNT(h, 5);  // build_abar (+dV), q_grads, halve_diag, kuu_grad, kuf_grad
   H_CUDA(h, cudaGetLastError());
   if (md.nlta > 0) {
     // Abar[g(l)] += S_l (2 LTA_l diag(dfvar_l))   -- column scaling fused into the B-operand load.
@@ -543,17 +555,14 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     H_CUDA(h, hgemm(h, p, Q, false, true, st, (double)Q * Mp * Mp * Bc));
   }
   if (md.nlta > 0) {
-    // Sbar_l = 2 tril(A_g diag(dfvar_l) LTA_l^T): scale LTA in place (column scaling), then NT GEMM
-    // (uses the TB = true path, so the scaling is applied by a tiny elementwise pass instead of colscale)
-    // -> fused: C = A_g * (LTA_l * diag)^T ; we pre-scale W-free buffer: reuse Kuf? Keep it simple: scale LTA.
-    scale_cols_kernel<<<dim3(Bc / 128, Mp / 32, md.nlta), 128, 0, st>>>(h->d_md, h->LTA, h->dfvar, Bp);
+    // Sbar_l = 2 tril(A_g diag(dfvar_l) LTA_l^T): diag(dfvar_l) is applied to the A-operand fragments per k
     GemmParams p = gp_init();
     p.A = h->A;   p.sA = (long long)Mp * Bp; p.lda = Bp; p.mapA = h->d_lta_group;
     p.B = h->LTA; p.sB = (long long)Mp * Bp; p.ldb = Bp;
     p.C = grads + lo.q_sqrt; p.sC = (long long)Mp * Mp; p.ldc = Mp; p.mapC = h->d_lta_latent;
     p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = 2.0; p.beta = 1.0;
+    p.kscale = h->dfvar; p.sks = Bp; p.mapK = h->d_lta_latent;
     H_CUDA(h, hgemm(h, p, md.nlta, false, true, st, (double)md.nlta * Mp * Mp * Bc));
-    KCOUNT(h, 1);
   }
   q_grads_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, lo, h->dV, eps_u, S, grads);
   // Cholesky backward: Phi = tril(L^T Lbar) with halved diagonal; Kb = Linv^T Phi Linv (symmetrised in kuu_grad)
@@ -585,10 +594,10 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   }
   if (md.D <= 4) {
     kuu_grad_kernel<4><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
-    kuf_grad_kernel<4><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+    kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
   } else {
     kuu_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
-    kuf_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+    kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
   }
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;

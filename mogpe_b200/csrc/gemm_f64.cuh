@@ -34,6 +34,22 @@ struct GemmParams {
   const double* colscale;
   long long scs;
   const int* mapS;
+  // optional fused per-k scaling of the A operand: A(m,k) *= kscale[batch_map*sks + k]  (fuses diag(dvar) into
+  // Sbar = 2 tril(A diag(dvar) LTA^T) without a separate pass over LTA)
+  const double* kscale;
+  long long sks;
+  const int* mapK;
+  // optional fused column statistics of the RESULT tile (deterministic: one partial per row block, summed later):
+  //   stat_ss [batch][M/BM][ldstat]      += sum over the tile's rows of C(m,n)^2
+  //   stat_dot[v][M/BM][ldstat] (v = statvec_begin[batch] .. statvec_begin[batch+1], index via statvec[])
+  //                                        = sum_m C(m,n) * statV[vec][m]
+  double* stat_ss;
+  double* stat_dot;
+  const double* statV;      // [NV][M]
+  const int* statvec_begin; // [batch + 1] (indexed by mapped C batch)
+  const int* statvec;       // vector ids
+  int ldstat;
+  int stat_rowblocks;       // M / BM of the launch (set by the launcher)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -68,25 +84,30 @@ struct GemmCfg {
   static constexpr int B_LD = B_COLS + 4;
   static constexpr int A_ELEMS = A_ROWS * A_LD;
   static constexpr int B_ELEMS = B_ROWS * B_LD;
-  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS + BK;  // + BK per-k scales
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
+  // resident CTAs per SM the register allocation must allow (64x64 tiles: 4 CTAs = 16 warps keep the DMMA pipe fed)
+  static constexpr int MIN_CTAS = (BM * BN <= 4096) ? 4 : ((BM * BN <= 8192) ? 2 : 1);
 };
 
 // One k-tile (BK deep) of MMAs for row-fragment range [I0, I1) of this warp.  TRIL: compile-time pattern
 // "quarter(j) <= quarter(i)" used on the diagonal tiles of a lower-triangular RESULT.  Everything is a
 // compile-time constant, so the DMMA stream has no predicates and ptxas can software-pipeline the LDS.
-template <class Cfg, int BK, bool TA, bool TB, int I0, int I1, bool TRIL>
+template <class Cfg, int BK, bool TA, bool TB, int I0, int I1, bool TRIL, bool KS>
 __device__ __forceinline__ void mma_ktile(const double* __restrict__ As, const double* __restrict__ Bs,
                                           double (&acc)[Cfg::MI][Cfg::NI][2], const double (&cs)[Cfg::NI], int wr,
                                           int wc, int lr, int lc) {
+  const double* __restrict__ Ks = Bs + Cfg::B_ELEMS;
 #pragma unroll
   for (int kk = 0; kk < BK / 4; kk++) {
     double af[Cfg::MI], bf[Cfg::NI];
     const int k = kk * 4 + lc;
+    const double sk = KS ? Ks[k] : 1.0;
 #pragma unroll
     for (int i = I0; i < I1; i++) {
       const int m = (i * Cfg::WARPS_M + wr) * 8 + lr;
       af[i] = TA ? As[k * Cfg::A_LD + m] : As[m * Cfg::A_LD + k];
+      if (KS) af[i] *= sk;
     }
 #pragma unroll
     for (int j = 0; j < Cfg::NI; j++) {
@@ -101,8 +122,9 @@ __device__ __forceinline__ void mma_ktile(const double* __restrict__ As, const d
   }
 }
 
-template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
-__global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::THREADS)
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES, bool STATS>
+__global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::THREADS,
+                                  GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::MIN_CTAS)
     gemm_dmma_kernel(const GemmParams p) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>;
   static_assert(Cfg::MI % 4 == 0 && Cfg::NI % 4 == 0, "fragment quarters");
@@ -136,6 +158,8 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
   double* __restrict__ Cb = p.C + (long long)(p.mapC ? p.mapC[batch] : batch) * p.sC;
   const double* __restrict__ Sb =
       p.colscale ? p.colscale + (long long)(p.mapS ? p.mapS[batch] : batch) * p.scs : nullptr;
+  const double* __restrict__ Kb =
+      p.kscale ? p.kscale + (long long)(p.mapK ? p.mapK[batch] : batch) * p.sks : nullptr;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -171,6 +195,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
                            : (Bb + (long long)(k0 + r) * p.ldb + col0 + cc);
       cp_async16(Bs + r * Cfg::B_LD + cc, g);
     }
+    if (Kb && tid < BK / 2) cp_async16(Bs + Cfg::B_ELEMS + tid * 2, Kb + k0 + tid * 2);
   };
 
   // per-thread column scales for its NI fragment columns (fused dLTA = 2 * LTA * dvar scaling)
@@ -207,25 +232,73 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
     int q0 = 0, q1 = 4;
     if (left_lower && d > 0) q0 = min(3, d / QR);                  // A(m,k) = 0 for k > m
     if (left_upper) q1 = max(1, min(4, (d + BK - 1) / QR + 1));    // A(m,k) = 0 for k < m
-    if (tril_diag) {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q4, true>(As, Bs, acc, cs, wr, wc, lr, lc);
+    if (Kb) {  // per-k scaled products are triangular-result products (no left-operand structure)
+      if (tril_diag) mma_ktile<Cfg, BK, TA, TB, 0, Q4, true, true>(As, Bs, acc, cs, wr, wc, lr, lc);
+      else mma_ktile<Cfg, BK, TA, TB, 0, Q4, false, true>(As, Bs, acc, cs, wr, wc, lr, lc);
+    } else if (tril_diag) {
+      mma_ktile<Cfg, BK, TA, TB, 0, Q4, true, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q0 == 0 && q1 == 4) {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q4, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q4, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q0 == 1) {
-      mma_ktile<Cfg, BK, TA, TB, Q1, Q4, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, Q1, Q4, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q0 == 2) {
-      mma_ktile<Cfg, BK, TA, TB, Q2, Q4, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, Q2, Q4, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q0 == 3) {
-      mma_ktile<Cfg, BK, TA, TB, Q3, Q4, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, Q3, Q4, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q1 == 1) {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q1, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q1, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q1 == 2) {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q2, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q2, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q3, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q3, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     }
   }
   cp_async_wait<0>();
+
+  if (STATS && p.stat_ss) {
+    // column statistics of this tile: reduce over the thread's MI row fragments, then over the 8 lanes that share a
+    // column pair (lane bits 2..4), then over the warp rows through shared memory; one plain store per column.
+    __syncthreads();  // all warps are done with the operand tiles: reuse them as scratch
+    double* red = smem;  // [WARPS_M][BN] per quantity
+    const int cb = p.mapC ? p.mapC[batch] : batch;
+    const int vb = p.statvec_begin ? p.statvec_begin[cb] : 0, ve = p.statvec_begin ? p.statvec_begin[cb + 1] : 0;
+    for (int qi = -1; qi < ve - vb; qi++) {
+      const double* vv = (qi >= 0) ? p.statV + (long long)p.statvec[vb + qi] * p.M + row0 : nullptr;
+      double w[Cfg::MI];
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; i++) w[i] = vv ? vv[(i * Cfg::WARPS_M + wr) * 8 + lr] : 0.0;
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; j++) {
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int i = 0; i < Cfg::MI; i++) {
+          const double c0 = p.alpha * acc[i][j][0], c1 = p.alpha * acc[i][j][1];
+          s0 += (qi < 0) ? c0 * c0 : c0 * w[i];
+          s1 += (qi < 0) ? c1 * c1 : c1 * w[i];
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lr == 0) {
+          const int c = (j * Cfg::WARPS_N + wc) * 8 + lc * 2;
+          red[wr * BN + c] = s0;
+          red[wr * BN + c + 1] = s1;
+        }
+      }
+      __syncthreads();
+      for (int c = tid; c < BN; c += Cfg::THREADS) {
+        double t = 0;
+#pragma unroll
+        for (int q = 0; q < Cfg::WARPS_M; q++) t += red[q * BN + c];
+        double* dst = (qi < 0) ? p.stat_ss + ((long long)cb * p.stat_rowblocks + brow) * p.ldstat
+                               : p.stat_dot + ((long long)p.statvec[vb + qi] * p.stat_rowblocks + brow) * p.ldstat;
+        dst[col0 + c] = t;
+      }
+      __syncthreads();
+    }
+  }
 
   // epilogue: thread owns (row = lr, cols = 2*lc, 2*lc+1) of each 8x8 fragment
 #pragma unroll
@@ -253,10 +326,10 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
 }
 
 // ---- host-side dispatch ------------------------------------------------------------------------
-template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES, bool STATS = false>
 inline cudaError_t launch_gemm_cfg(const GemmParams& p, int batch, cudaStream_t st) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>;
-  auto kern = gemm_dmma_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>;
+  auto kern = gemm_dmma_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES, STATS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -264,7 +337,9 @@ inline cudaError_t launch_gemm_cfg(const GemmParams& p, int batch, cudaStream_t 
     attr_set = true;
   }
   dim3 grid(p.N / BN, p.M / BM, batch);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  GemmParams q = p;
+  q.stat_rowblocks = p.M / BM;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(q);
   return cudaGetLastError();
 }
 
@@ -284,6 +359,7 @@ inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st
     cfg = (p.K % 32 == 0 && (p.tril_out || p.N < 1024)) ? 11 : 7;
   }
   const bool ok128 = (p.M % 128 == 0) && (p.N % 128 == 0);
+  if (p.stat_ss) return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 2, true>(p, batch, st);  // BM = GEMM_STAT_BM
   switch (cfg) {
     case 0: if (ok128) return launch_gemm_cfg<128, 128, 16, 64, 32, TA, TB, 3>(p, batch, st); break;
     case 2: if (p.N % 128 == 0) return launch_gemm_cfg<64, 128, 16, 32, 32, TA, TB, 4>(p, batch, st); break;
@@ -300,6 +376,10 @@ inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st
   }
   return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 4>(p, batch, st);
 }
+
+// Row blocks per matrix that the automatic configuration will use for an [M x M] x [M x B] product with fused
+// column statistics (every configuration chosen for those products has BM = 64).
+constexpr int GEMM_STAT_BM = 64;
 
 inline cudaError_t launch_gemm(const GemmParams& p, int batch, bool ta, bool tb, cudaStream_t st, int cfg = -1) {
   if (p.M % 64 || p.N % 64 || p.K % 16) return cudaErrorInvalidValue;

@@ -376,6 +376,38 @@ __global__ void __launch_bounds__(128) a_stats_kernel(const ModelDev* __restrict
   }
 }
 
+// Sum the per-row-block partial column statistics written by the GEMM epilogues (deterministic order):
+//   var0ss[g][n] = sum_rb ss_part[g][rb][n];  mean[v][n] = sum_rb dot_part[v][rb][n] + c_latent(v);
+//   varq[l][n] = sum_rb lta_part[slot(l)][rb][n].     grid (Bc/128, Q + NV + nlta), block 128
+__global__ void __launch_bounds__(128) stats_finish_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                           Layout lo, const double* __restrict__ ss_part,
+                                                           const double* __restrict__ dot_part,
+                                                           const double* __restrict__ lta_part, int rbn, int Bp,
+                                                           double* __restrict__ var0ss, double* __restrict__ mean,
+                                                           double* __restrict__ varq) {
+  const int n = blockIdx.x * 128 + threadIdx.x, Q = md->Q, NV = md->NV;
+  int y = blockIdx.y;
+  const double* src;
+  double* dst;
+  double add = 0.0;
+  if (y < Q) {
+    src = ss_part + (long long)y * rbn * Bp;
+    dst = var0ss + (long long)y * Bp;
+  } else if (y < Q + NV) {
+    y -= Q;
+    src = dot_part + (long long)y * rbn * Bp;
+    dst = mean + (long long)y * Bp;
+    add = params[lo.mean_c + md->vec_latent[y]];
+  } else {
+    y -= Q + NV;
+    src = lta_part + (long long)y * rbn * Bp;
+    dst = varq + (long long)md->lta_latent[y] * Bp;
+  }
+  double t = 0;
+  for (int rb = 0; rb < rbn; rb++) t += src[(long long)rb * Bp + n];
+  dst[n] = t + add;
+}
+
 // varq[l][n] = sum_m LTA[slot][m][n]^2.   grid (Bp/128, nlta), block 128
 __global__ void __launch_bounds__(128) col_sumsq_kernel(const ModelDev* __restrict__ md, const double* __restrict__ LTA,
                                                         int Bp, double* __restrict__ varq) {
@@ -480,78 +512,60 @@ __global__ void finish_elbo_kernel(double* out) { out[0] = out[1] - out[2] - out
 
 // ------------------------------------------------------------------------------------------------
 // Backward: Abar[g][m][n] = -2 A[m][n] sum_{l in g} dfvar[l][n] + sum_{v in g} V[v][m] dmean[v][n]
-// grid (Bp/128, Mp/32, Q), block 128
+// and, in the same pass over A, dV[v][m] += sum_n A[g][m][n] dmean[v][n] (dV zero-initialised): the products
+// are transposed through shared memory, reduced per row by one warp and added with one atomic per (row, vector)
+// per CTA.   grid (Bc/128, Mp/32, Q), block 128
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) build_abar_kernel(const ModelDev* __restrict__ md, const double* __restrict__ A,
                                                          const double* __restrict__ V,
                                                          const double* __restrict__ dmean,
                                                          const double* __restrict__ dfvar, int Bp,
-                                                         double* __restrict__ Abar) {
+                                                         double* __restrict__ Abar, double* __restrict__ dV) {
   __shared__ double vs[32 * 33];
+  __shared__ double pr[32][129];
   const int g = blockIdx.z, Mp = md->Mp, m0 = blockIdx.y * 32;
-  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x * 128 + tid;
   double dv = 0;
   for (int q = md->glat_begin[g]; q < md->glat_begin[g + 1]; q++) dv += dfvar[(long long)md->glat[q] * Bp + n];
-  double acc[32];
+  double a[32], acc[32];
   const double* Ag = A + ((long long)g * Mp + m0) * Bp + n;
 #pragma unroll
-  for (int r = 0; r < 32; r++) acc[r] = -2.0 * dv * Ag[(long long)r * Bp];
+  for (int r = 0; r < 32; r++) {
+    a[r] = Ag[(long long)r * Bp];
+    acc[r] = -2.0 * dv * a[r];
+  }
   const int vb = md->gvec_begin[g], ve = md->gvec_begin[g + 1];
   for (int v0 = vb; v0 < ve; v0 += 32) {
     const int nv = min(32, ve - v0);
     __syncthreads();
-    for (int t = threadIdx.x; t < nv * 32; t += 128) {
+    for (int t = tid; t < nv * 32; t += 128) {
       const int q = t / 32, r = t % 32;
       vs[q * 33 + r] = V[(long long)md->gvec[v0 + q] * Mp + m0 + r];
     }
     __syncthreads();
     for (int q = 0; q < nv; q++) {
-      const double dm = dmean[(long long)md->gvec[v0 + q] * Bp + n];
+      const int vec = md->gvec[v0 + q];
+      const double dm = dmean[(long long)vec * Bp + n];
 #pragma unroll
-      for (int r = 0; r < 32; r++) acc[r] += vs[q * 33 + r] * dm;
+      for (int r = 0; r < 32; r++) {
+        acc[r] += vs[q * 33 + r] * dm;
+        pr[r][tid] = a[r] * dm;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < 8; rr++) {
+        const int row = warp * 8 + rr;
+        double sum = (pr[row][lane] + pr[row][lane + 32]) + (pr[row][lane + 64] + pr[row][lane + 96]);
+        sum = warp_sum(sum);
+        if (lane == 0) atomicAdd(dV + (long long)vec * Mp + m0 + row, sum);
+      }
+      __syncthreads();
     }
   }
   double* out = Abar + ((long long)g * Mp + m0) * Bp + n;
 #pragma unroll
   for (int r = 0; r < 32; r++) out[(long long)r * Bp] = acc[r];
-}
-
-// dV[v][m] += sum_n A[g][m][n] dmean[v][n] (dV zero-initialised).  CTA = (1024-column slab, 32 rows, group):
-// thread (cx, ry) streams 4 columns x 8 rows... each warp reads full 256-byte row segments (coalesced),
-// reduces over its columns with shuffles and adds one atomic per (row, vector).  Up to 8 vectors per pass.
-// grid (ceil(Bc/1024), Mp/32, Q), block 256
-__global__ void __launch_bounds__(256) dV_kernel(const ModelDev* __restrict__ md, const double* __restrict__ A,
-                                                 const double* __restrict__ dmean, int Bp, int Bc, double* __restrict__ dV) {
-  const int g = blockIdx.z, Mp = md->Mp, m0 = blockIdx.y * 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * 1024, n1 = min(Bc, n0 + 1024);
-  const int vb = md->gvec_begin[g], ve = md->gvec_begin[g + 1];
-  for (int v0 = vb; v0 < ve; v0 += 8) {
-    const int nv = min(8, ve - v0);
-    // warp w owns rows m0 + 4w .. m0 + 4w + 3
-    double acc[4][8];
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int q = 0; q < 8; q++) acc[r][q] = 0.0;
-    for (int n = n0 + lane; n < n1; n += 32) {
-      double dm[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) dm[q] = (q < nv) ? dmean[(long long)md->gvec[v0 + q] * Bp + n] : 0.0;
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const double a = A[((long long)g * Mp + m0 + warp * 4 + r) * Bp + n];
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc[r][q] += a * dm[q];
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-      for (int q = 0; q < nv; q++) {
-        const double s = warp_sum(acc[r][q]);
-        if (lane == 0) atomicAdd(dV + (long long)md->gvec[v0 + q] * Mp + m0 + warp * 4 + r, s);
-      }
-  }
 }
 
 // grads.q_mu[l][m] += sum_r dV[v(l,r)][m];  grads.q_sqrt[l][m][k] += sum_s dV[v(l,s)][m] eps_u[l][s][k] (k <= m)
@@ -577,60 +591,73 @@ __global__ void q_grads_kernel(const ModelDev* __restrict__ md, Layout lo, const
 // ------------------------------------------------------------------------------------------------
 // Kernel-hyperparameter and Z gradients from Kuf-bar (= W): E = W .* Kuf,
 //   dZ[m,d]  = -sum_n E (z_md - x_nd) / l_d^2 ;  dl_d = sum_mn E (z_md - x_nd)^2 / l_d^3 ; dvar = sum E / var
-// One warp per row m (coalesced over n).  grid (Mp/8, Q), block 256.  D <= 16.
+// One warp per ROWS rows m (coalesced over n; x_n is loaded once for the ROWS rows).
+// grid (Mp/(8*ROWS), Q), block 256.  D <= DMAX.
 // ------------------------------------------------------------------------------------------------
-template <int DMAX>
+template <int DMAX, int ROWS>
 __global__ void __launch_bounds__(256) kuf_grad_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
                                                        Layout lo, const double* __restrict__ X, int N, int Bp,
                                                        const double* __restrict__ W, const double* __restrict__ Kuf,
                                                        double* __restrict__ grads) {
   const int g = blockIdx.y, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + warp;
-  if (m >= Mg) return;
+  const int m0 = (blockIdx.x * 8 + warp) * ROWS;
+  if (m0 >= Mg) return;
   const double* ls = params + lo.ls + (long long)g * D;
-  const double* z = params + lo.Z + ((long long)g * Mp + m) * D;
-  const double* w = W + ((long long)g * Mp + m) * Bp;
-  const double* kf = Kuf + ((long long)g * Mp + m) * Bp;
-  double zz[DMAX], a1[DMAX], a2[DMAX];
+  double zz[ROWS][DMAX], a1[ROWS][DMAX], a2[ROWS][DMAX], se[ROWS];
 #pragma unroll
-  for (int d = 0; d < DMAX; d++) {
-    zz[d] = d < D ? z[d] : 0.0;
-    a1[d] = a2[d] = 0.0;
-  }
-  double se = 0;
-  for (int n0 = lane; n0 < N; n0 += 128) {  // 4 independent elements per lane in flight
-    double e[4];
+  for (int r = 0; r < ROWS; r++) {
+    se[r] = 0.0;
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int n = n0 + u * 32;
-      e[u] = (n < N) ? w[n] * kf[n] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int n = min(n0 + u * 32, N - 1);
-      se += e[u];
-#pragma unroll
-      for (int d = 0; d < DMAX; d++)
-        if (d < D) {
-          const double df = zz[d] - X[(long long)n * D + d];
-          a1[d] += e[u] * df;
-          a2[d] += e[u] * df * df;
-        }
+    for (int d = 0; d < DMAX; d++) {
+      zz[r][d] = (d < D && m0 + r < Mg) ? params[lo.Z + ((long long)g * Mp + m0 + r) * D + d] : 0.0;
+      a1[r][d] = a2[r][d] = 0.0;
     }
   }
-  se = warp_sum(se);
-  if (lane == 0) atomicAdd(grads + lo.kvar + g, se / params[lo.kvar + g]);
+  const double* w = W + ((long long)g * Mp + m0) * Bp;
+  const double* kf = Kuf + ((long long)g * Mp + m0) * Bp;
+#pragma unroll(8 / ROWS)
+  for (int n = lane; n < N; n += 32) {
+    double x[DMAX], e[ROWS];
 #pragma unroll
-  for (int d = 0; d < DMAX; d++)
-    if (d < D) {
-      const double s1 = warp_sum(a1[d]), s2 = warp_sum(a2[d]);
-      if (lane == 0) {
-        const double l = ls[d];
-        atomicAdd(grads + lo.Z + ((long long)g * Mp + m) * D + d, -s1 / (l * l));
-        atomicAdd(grads + lo.ls + (long long)g * D + d, s2 / (l * l * l));
+    for (int r = 0; r < ROWS; r++) e[r] = w[(long long)r * Bp + n] * kf[(long long)r * Bp + n];  // rows >= Mg: Kuf = 0
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) x[d] = (d < D) ? X[(long long)n * D + d] : 0.0;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      se[r] += e[r];
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) {
+        const double df = zz[r][d] - x[d];
+        a1[r][d] += e[r] * df;
+        a2[r][d] += e[r] * df * df;
       }
     }
+  }
+  double dkv = 0.0, dls[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) dls[d] = 0.0;
+#pragma unroll
+  for (int r = 0; r < ROWS; r++) {
+    dkv += warp_sum(se[r]);
+#pragma unroll
+    for (int d = 0; d < DMAX; d++)
+      if (d < D) {
+        const double s1 = warp_sum(a1[r][d]);
+        dls[d] += warp_sum(a2[r][d]);
+        if (lane == 0 && m0 + r < Mg) {
+          const double l = ls[d];
+          atomicAdd(grads + lo.Z + ((long long)g * Mp + m0 + r) * D + d, -s1 / (l * l));
+        }
+      }
+  }
+  if (lane == 0) {
+    atomicAdd(grads + lo.kvar + g, dkv / params[lo.kvar + g]);
+    for (int d = 0; d < D && d < DMAX; d++) {
+      const double l = ls[d];
+      atomicAdd(grads + lo.ls + (long long)g * D + d, dls[d] / (l * l * l));
+    }
+  }
 }
 
 // Same for Kuu with the symmetrised Kuu-bar = (Kb + Kb^T)/2 (Kb = L^-T Phi L^-1 from the Cholesky
@@ -679,16 +706,6 @@ __global__ void __launch_bounds__(256) kuu_grad_kernel(const ModelDev* __restric
         atomicAdd(grads + lo.ls + (long long)g * D + d, s2 / (l * l * l));
       }
     }
-}
-
-// LTA[slot][m][n] *= dfvar[lta_latent[slot]][n].   grid (Bp/128, Mp/32, nlta), block 128
-__global__ void scale_cols_kernel(const ModelDev* md, double* LTA, const double* dfvar, int Bp) {
-  const int slot = blockIdx.z, Mp = md->Mp, l = md->lta_latent[slot];
-  const int n = blockIdx.x * 128 + threadIdx.x, m0 = blockIdx.y * 32;
-  const double s = dfvar[(long long)l * Bp + n];
-  double* p = LTA + ((long long)slot * Mp + m0) * Bp + n;
-#pragma unroll 8
-  for (int r = 0; r < 32; r++) p[(long long)r * Bp] *= s;
 }
 
 // Phi: halve the diagonal of a (already lower-triangular) matrix batch.  grid (Q), block 256
