@@ -93,7 +93,7 @@ struct GemmCfg {
 // One k-tile (BK deep) of MMAs for row-fragment range [I0, I1) of this warp.  TRIL: compile-time pattern
 // "quarter(j) <= quarter(i)" used on the diagonal tiles of a lower-triangular RESULT.  Everything is a
 // compile-time constant, so the DMMA stream has no predicates and ptxas can software-pipeline the LDS.
-template <class Cfg, int BK, bool TA, bool TB, int I0, int I1, bool TRIL, bool KS>
+template <class Cfg, int BK, bool TA, bool TB, int I0, int I1, bool TRIL, bool KS, bool CS>
 __device__ __forceinline__ void mma_ktile(const double* __restrict__ As, const double* __restrict__ Bs,
                                           double (&acc)[Cfg::MI][Cfg::NI][2], const double (&cs)[Cfg::NI], int wr,
                                           int wc, int lr, int lc) {
@@ -112,7 +112,8 @@ __device__ __forceinline__ void mma_ktile(const double* __restrict__ As, const d
 #pragma unroll
     for (int j = 0; j < Cfg::NI; j++) {
       const int n = (j * Cfg::WARPS_N + wc) * 8 + lr;
-      bf[j] = (TB ? Bs[n * Cfg::B_LD + k] : Bs[k * Cfg::B_LD + n]) * cs[j];
+      bf[j] = TB ? Bs[n * Cfg::B_LD + k] : Bs[k * Cfg::B_LD + n];
+      if (CS) bf[j] *= cs[j];  // only instantiated for scaled launches: a DMUL shares the FP64 pipe with DMMA
     }
 #pragma unroll
     for (int i = I0; i < I1; i++)
@@ -122,7 +123,7 @@ __device__ __forceinline__ void mma_ktile(const double* __restrict__ As, const d
   }
 }
 
-template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES, bool STATS>
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES, bool STATS, bool SCALE>
 __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::THREADS,
                                   GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::MIN_CTAS)
     gemm_dmma_kernel(const GemmParams p) {
@@ -195,14 +196,14 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
                            : (Bb + (long long)(k0 + r) * p.ldb + col0 + cc);
       cp_async16(Bs + r * Cfg::B_LD + cc, g);
     }
-    if (Kb && tid < BK / 2) cp_async16(Bs + Cfg::B_ELEMS + tid * 2, Kb + k0 + tid * 2);
+    if (SCALE && Kb && tid < BK / 2) cp_async16(Bs + Cfg::B_ELEMS + tid * 2, Kb + k0 + tid * 2);
   };
 
   // per-thread column scales for its NI fragment columns (fused dLTA = 2 * LTA * dvar scaling)
   double cs[Cfg::NI];
 #pragma unroll
   for (int j = 0; j < Cfg::NI; j++) cs[j] = 1.0;
-  if (Sb) {
+  if (SCALE && Sb) {
 #pragma unroll
     for (int j = 0; j < Cfg::NI; j++) cs[j] = TB ? 1.0 : Sb[col0 + (j * Cfg::WARPS_N + wc) * 8 + lr];
   }
@@ -232,25 +233,25 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
     int q0 = 0, q1 = 4;
     if (left_lower && d > 0) q0 = min(3, d / QR);                  // A(m,k) = 0 for k > m
     if (left_upper) q1 = max(1, min(4, (d + BK - 1) / QR + 1));    // A(m,k) = 0 for k < m
-    if (Kb) {  // per-k scaled products are triangular-result products (no left-operand structure)
-      if (tril_diag) mma_ktile<Cfg, BK, TA, TB, 0, Q4, true, true>(As, Bs, acc, cs, wr, wc, lr, lc);
-      else mma_ktile<Cfg, BK, TA, TB, 0, Q4, false, true>(As, Bs, acc, cs, wr, wc, lr, lc);
+    if (SCALE && Kb) {  // per-k scaled products are triangular-result products (no left-operand structure)
+      if (tril_diag) mma_ktile<Cfg, BK, TA, TB, 0, Q4, true, true, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      else mma_ktile<Cfg, BK, TA, TB, 0, Q4, false, true, false>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (tril_diag) {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q4, true, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q4, true, false, SCALE>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q0 == 0 && q1 == 4) {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q4, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q4, false, false, SCALE>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q0 == 1) {
-      mma_ktile<Cfg, BK, TA, TB, Q1, Q4, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, Q1, Q4, false, false, SCALE>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q0 == 2) {
-      mma_ktile<Cfg, BK, TA, TB, Q2, Q4, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, Q2, Q4, false, false, SCALE>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q0 == 3) {
-      mma_ktile<Cfg, BK, TA, TB, Q3, Q4, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, Q3, Q4, false, false, SCALE>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q1 == 1) {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q1, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q1, false, false, SCALE>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else if (q1 == 2) {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q2, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q2, false, false, SCALE>(As, Bs, acc, cs, wr, wc, lr, lc);
     } else {
-      mma_ktile<Cfg, BK, TA, TB, 0, Q3, false, false>(As, Bs, acc, cs, wr, wc, lr, lc);
+      mma_ktile<Cfg, BK, TA, TB, 0, Q3, false, false, SCALE>(As, Bs, acc, cs, wr, wc, lr, lc);
     }
   }
   cp_async_wait<0>();
@@ -326,10 +327,11 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
 }
 
 // ---- host-side dispatch ------------------------------------------------------------------------
-template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES, bool STATS = false>
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES, bool STATS = false, bool SCALE = false>
 inline cudaError_t launch_gemm_cfg(const GemmParams& p, int batch, cudaStream_t st) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>;
-  auto kern = gemm_dmma_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES, STATS>;
+  if (!SCALE && (p.colscale || p.kscale)) return cudaErrorInvalidValue;  // scaled launches use the dedicated paths
+  auto kern = gemm_dmma_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES, STATS, SCALE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -360,6 +362,8 @@ inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st
   }
   const bool ok128 = (p.M % 128 == 0) && (p.N % 128 == 0);
   if (p.stat_ss) return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 2, true>(p, batch, st);  // BM = GEMM_STAT_BM
+  if (p.kscale) return launch_gemm_cfg<64, 64, 32, 32, 32, TA, TB, 3, false, true>(p, batch, st);
+  if (p.colscale) return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 2, false, true>(p, batch, st);
   switch (cfg) {
     case 0: if (ok128) return launch_gemm_cfg<128, 128, 16, 64, 32, TA, TB, 3>(p, batch, st); break;
     case 2: if (p.N % 128 == 0) return launch_gemm_cfg<64, 128, 16, 32, 32, TA, TB, 4>(p, batch, st); break;
