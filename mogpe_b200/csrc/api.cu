@@ -52,6 +52,10 @@ struct mogpe_handle {
   // host-entry staging
   double *stage_dev = nullptr, *stage_host = nullptr, *out_dev = nullptr, *out_host_pinned = nullptr;
   size_t stage_cap = 0;
+  // side stream: work that does not depend on the Cholesky chain (Kuf, q_sqrt prep, mean vectors; Kuf gradients in
+  // the backward) overlaps the latency-bound factorisation launches
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // library-owned random stream
   uint64_t seed = 0x6d6f677065ULL, rng_counter = 0;
   double *eps_u_int = nullptr, *eps_h_int = nullptr, *eps_f_int = nullptr;
@@ -117,6 +121,9 @@ static void free_ws(mogpe_handle* h) {
   if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
   for (auto e : h->ev) cudaEventDestroy(e);
   h->ev.clear();
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
 }
 
 extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
@@ -220,6 +227,9 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (e == cudaSuccess) e = dalloc(&h->d_round_group, (size_t)MAXP * MAXP);
   if (e == cudaSuccess) e = dalloc(&h->out_dev, 8);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->out_host_pinned, 8 * sizeof(double));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess)
     e = cudaMemcpy(h->d_latent_group, md.latent_group, sizeof(int) * MAXP, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(h->varq, 0, (size_t)P * h->Bp * sizeof(double));
@@ -379,24 +389,51 @@ static cudaError_t hgemm(mogpe_handle* h, const GemmParams& p, int batch, bool t
 #define KCOUNT(h, n) ((h)->all_launches += (n))
 
 // Kuu -> L -> Linv for every group, and the clean q_sqrt copies.
-static mogpe_status factorise(mogpe_handle* h, const double* params, cudaStream_t st) {
-  const int Q = h->md_host.Q, P = h->md_host.P, Mp = h->Mp;
+// fork / join of the side stream around a region of the caller's stream
+static cudaError_t side_fork(mogpe_handle* h, cudaStream_t st) {
+  cudaError_t e = cudaEventRecord(h->ev_fork, st);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+  return e;
+}
+static cudaError_t side_join(mogpe_handle* h, cudaStream_t st) {
+  cudaError_t e = cudaEventRecord(h->ev_join, h->side);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_join, 0);
+  return e;
+}
+
+static void launch_kuf(mogpe_handle* h, const double* params, const double* X, int N, int Bc, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  kuf_kernel<<<dim3(Bc / 128, h->Mp / 32, md.Q), 128, (32 * md.D + 32) * sizeof(double), st>>>(h->d_md, params, h->lo, X, N,
+                                                                                               h->Bp, h->Kuf);
+  KCOUNT(h, 1);
+}
+
+// Kuu -> L -> Linv for every group on the caller's stream.  Concurrently, on the side stream, everything that does
+// not depend on the factorisation: the clean q_sqrt copies, the mean vectors V (u-samples) and Kuf of the first
+// chunk.  The Cholesky chain is a sequence of short latency-bound launches that leave most SMs idle.
+static mogpe_status factorise(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X, int N,
+                              int Bc, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, P = md.P, Mp = h->Mp;
+  H_CUDA(h, side_fork(h, st));
+  prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, h->side>>>(h->d_md, params, h->lo, h->Sc);
+  make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, h->side>>>(h->d_md, params, h->lo, h->Sc, eps_u, S, h->V);
+  launch_kuf(h, params, X, N, Bc, h->side);
   kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
-  for (int j = -1; j < Mp / 32; j++)
+  for (int j = -1; j < Mp / 32; j++)  // launch j: block column j of L, block row j of L^-1, look-ahead factor of block j+1
     chol_inv_step_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, j);
-  prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->Sc);
-  KCOUNT(h, 3 + Mp / 32);
+  KCOUNT(h, 4 + Mp / 32);
   H_CUDA(h, cudaGetLastError());
+  H_CUDA(h, side_join(h, st));
   return MOGPE_OK;
 }
 
 // Kuf, A = Linv Kuf, LTA_l = S_l^T A for marginal latents, for columns [0, Bp) of the current chunk.
 static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const double* X, int N, int Bc,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, bool kuf_done) {
   const ModelDev& md = h->md_host;
-  const int Q = md.Q, Mp = h->Mp, D = md.D;
-  kuf_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, (32 * D + 32) * sizeof(double), st>>>(h->d_md, params, h->lo, X, N, h->Bp,
-                                                                                      h->Kuf);
+  const int Q = md.Q, Mp = h->Mp;
+  if (!kuf_done) launch_kuf(h, params, X, N, Bc, st);
   H_CUDA(h, cudaGetLastError());
   {
     GemmParams p = gp_init();
@@ -419,7 +456,7 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
     p.stat_ss = h->lta_part; p.ldstat = h->Bp;  // sum_m LTA^2 partials
     H_CUDA(h, hgemm(h, p, md.nlta, true, false, st, (double)md.nlta * Mp * Mp * Bc, STAT_CFG));
   }
-  KCOUNT(h, 2);  // kuf + stats_finish
+  KCOUNT(h, 1);  // stats_finish
   stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + md.nlta), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, h->dot_part,
                                                                            h->lta_part, Mp / GEMM_STAT_BM, h->Bp, h->var0ss,
                                                                            h->mean, h->varq);
@@ -486,11 +523,10 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   if (grads) H_CUDA(h, cudaMemsetAsync(grads, 0, lo.total * sizeof(double), st));
 
   // ---------------- forward ----------------
-  rc = factorise(h, params, st);
+  rc = factorise(h, params, eps_u, S, X, N, Bc, st);
   if (rc != MOGPE_OK) return rc;
-  make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, st>>>(h->d_md, params, lo, h->Sc, eps_u, S, h->V);
-  KCOUNT(h, 4);  // make_V, lik, kl, finish
-  rc = conditional_fwd(h, params, X, N, Bc, st);
+  KCOUNT(h, 3);  // lik, kl, finish
+  rc = conditional_fwd(h, params, X, N, Bc, st, true);
   if (rc != MOGPE_OK) return rc;
 
   LikArgs la;
@@ -546,6 +582,13 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_UPPER;
     H_CUDA(h, hgemm(h, p, Q, true, false, st, (double)Q * Mp * Mp * Bc));
   }
+  // Kuf-bar = W is complete: its kernel-hyperparameter / Z gradients only read W, Kuf, X -> side stream, overlapping
+  // the GEMMs of the Cholesky backward below (different gradient entries except kvar / ls, which are atomics)
+  H_CUDA(h, side_fork(h, st));
+  if (md.D <= 4)
+    kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q), 256, 0, h->side>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+  else
+    kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q), 256, 0, h->side>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
   {  // Lbar = -tril(W A^T)
     GemmParams p = gp_init();
     p.A = h->W; p.sA = (long long)Mp * Bp; p.lda = Bp;
@@ -592,13 +635,11 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.M = Mp; p.N = Mp; p.K = Mp; p.kmode = KM_RIGHT_LOWER;
     H_CUDA(h, hgemm(h, p, Q, false, false, st, (double)Q * Mp * Mp * Mp));
   }
-  if (md.D <= 4) {
+  if (md.D <= 4)
     kuu_grad_kernel<4><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
-    kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
-  } else {
+  else
     kuu_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
-    kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
-  }
+  H_CUDA(h, side_join(h, st));  // Kuf gradients (side stream, launched right after W was complete)
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
 }
@@ -671,16 +712,16 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
   H_CUDA(h, cudaSetDevice(h->device));
   mogpe_status rc = set_mode(h, -1, 1, st);
   if (rc != MOGPE_OK) return rc;
-  rc = factorise(h, params, st);
-  if (rc != MOGPE_OK) return rc;
-  const int Mp = h->Mp;
-  make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, st>>>(h->d_md, params, h->lo, h->Sc, nullptr, 1, h->V);
-  KCOUNT(h, 1);
   const int chunk_max = h->desc.max_batch;
+  {
+    const int nc0 = (int)std::min<int64_t>(chunk_max, N);
+    rc = factorise(h, params, nullptr, 1, X, nc0, round_up(nc0, 128), st);  // Kuf of the first chunk overlaps the chain
+    if (rc != MOGPE_OK) return rc;
+  }
   for (int64_t n0 = 0; n0 < N; n0 += chunk_max) {
     const int nc = (int)std::min<int64_t>(chunk_max, N - n0);
     const int Bc = round_up(nc, 128);
-    rc = conditional_fwd(h, params, X + n0 * md.D, nc, Bc, st);
+    rc = conditional_fwd(h, params, X + n0 * md.D, nc, Bc, st, n0 == 0);
     if (rc != MOGPE_OK) return rc;
     PredArgs pa;
     pa.md = h->d_md; pa.params = params; pa.lo = h->lo; pa.mean = h->mean; pa.var0ss = h->var0ss; pa.varq = h->varq;
@@ -722,10 +763,9 @@ extern "C" mogpe_status mogpe_predict_f_inducing_samples(mogpe_handle* h, const 
     h->last_nu = (long long)nu;
     KCOUNT(h, 1);
   }
-  rc = factorise(h, params, st);
+  rc = factorise(h, params, eps_u, S, X, N, round_up(N, 128), st);
   if (rc != MOGPE_OK) return rc;
-  make_V_kernel<<<dim3(h->Mp / 8, md.NV), 256, 0, st>>>(h->d_md, params, h->lo, h->Sc, eps_u, S, h->V);
-  rc = conditional_fwd(h, params, X, N, round_up(N, 128), st);
+  rc = conditional_fwd(h, params, X, N, round_up(N, 128), st, true);
   if (rc != MOGPE_OK) return rc;
   inducing_out_kernel<<<(N + 127) / 128, 128, 0, st>>>(h->d_md, params, h->lo, h->mean, h->var0ss, N, h->Bp, f_mean, f_var);
   KCOUNT(h, 2);

@@ -158,14 +158,30 @@ __device__ __forceinline__ void trsm32_cols_warp(const double (*T)[33], const do
   for (int r = 0; r < 32; r++) Rb[r][lane] = y[r];
 }
 
+// Solve x T^T = c for the 32 rows of Cb in place, ONE warp, lane = row.
+__device__ __forceinline__ void trsm32_rows_warp(const double (*T)[33], const double* rdiag, double (*Cb)[33], int lane) {
+  double x[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) x[c] = Cb[lane][c];
+#pragma unroll
+  for (int c = 0; c < 32; c++) {
+    x[c] *= rdiag[c];
+#pragma unroll
+    for (int cc = c + 1; cc < 32; cc++) x[cc] -= T[cc][c] * x[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c++) Cb[lane][c] = x[c];
+}
+
 // Step j of the fused Cholesky + inverse (launch j = -1 .. Mp/32 - 1), grid (Mp/32, Q), block 256.
-//   B-part, CTA b != j (j >= 0): one 32x32 block product on the DMMA pipe, then a 32x32x32 multiply with the
-//     already-known Ljj^-1 -- no triangular solve:
+//   B-part, CTA b != j (j >= 0): one 32x32 block product on the DMMA pipe, then a single-warp 32x32 triangular
+//     solve against Ljj (all CTAs in parallel):
 //        b > j : L[b,j]    = (Kuu[b,j] - sum_{k<j} L[b,k] L[j,k]^T) Ljj^-T
 //        b < j : Linv[j,b] = -Ljj^-1 sum_{k=b}^{j-1} L[j,k] Linv[k,b]
 //   A-part (look-ahead), CTA b == j+1: it already streams row block j+1 of L for its B-part, so it accumulates
-//     sum_{k<j} L[j+1,k] L[j+1,k]^T in the same sweep, adds the outer product of the block it just produced,
-//     factors the NEXT diagonal block and inverts it (one warp, registers + shuffles).
+//     sum_{k<j} L[j+1,k] L[j+1,k]^T in the same sweep, adds the outer product of the block it just produced and
+//     factors the NEXT diagonal block (one warp, registers + shuffles).  Its inverse Linv[j+1,j+1] is computed
+//     by CTA b == j+1 of the next launch, off the critical path.
 // The 32x32 outputs are split over the 8 warps (fragment row i = warp/2, fragment columns 2*(warp%2) + {0,1}):
 // no cross-warp reduction, deterministic, 8 accumulator registers per product.
 // The only sequential work per launch is one block product + one 32x32 factor/invert by ONE CTA per group.
@@ -185,13 +201,14 @@ __global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __r
   double* Xg = Linv + (long long)g * Mp * Mp;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int d = j + 1;
-  const bool do_b = (j >= 0) && (b != j), do_a = (b == d) && (d < nb);
+  // launch j also lets CTA b == j invert Ljj (factored by the previous launch): off the critical path
+  const bool do_b = (j >= 0), do_a = (b == d) && (d < nb);
   if (!do_b && !do_a) return;
   const int fi = warp >> 1, fq0 = (warp & 1) * 2;  // this warp's output fragments
   double accC[2][2] = {{0, 0}, {0, 0}}, accD[2][2] = {{0, 0}, {0, 0}};
 
   if (do_b) {
-    const int kend = j * 32, kbeg = (b > j) ? 0 : b * 32;
+    const int kend = (b == j) ? 0 : j * 32, kbeg = (b > j) ? 0 : b * 32;  // b == j: no product, Cg = I
     for (int k0 = kbeg; k0 < kend; k0 += CHOL_CH) {
       const int kw = min(CHOL_CH, kend - k0);  // multiple of 32
       for (int t = tid; t < 32 * (kw / 2); t += 256) {
@@ -232,25 +249,25 @@ __global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __r
       const int r = fi * 8 + lr, c = (fq0 + u) * 8 + lc * 2;
       const double2 base = (b > j) ? *reinterpret_cast<const double2*>(Kg + (long long)(b * 32 + r) * Mp + j * 32 + c)
                                    : make_double2(0.0, 0.0);
-      Cg[r][c] = base.x - accC[u][0];
-      Cg[r][c + 1] = base.y - accC[u][1];
+      Cg[r][c] = ((b == j && r == c) ? 1.0 : base.x) - accC[u][0];
+      Cg[r][c + 1] = ((b == j && r == c + 1) ? 1.0 : base.y) - accC[u][1];
     }
     for (int t = tid; t < 1024; t += 256)
-      Dg[t >> 5][t & 31] = Xg[(long long)(j * 32 + (t >> 5)) * Mp + j * 32 + (t & 31)];  // Ljj^-1 (previous launch)
+      Dg[t >> 5][t & 31] = Lg[(long long)(j * 32 + (t >> 5)) * Mp + j * 32 + (t & 31)];  // Ljj (previous launch)
+    if (tid < 32) rdiag[tid] = 1.0 / Lg[(long long)(j * 32 + tid) * Mp + j * 32 + tid];
+    __syncthreads();
+    // one warp solves against Ljj (every CTA in parallel; nothing waits for an explicit Ljj^-1):
+    //   b > j : X Ljj^T = C      b < j : Ljj Y = -R
+    if (tid < 32) {
+      if (b > j) trsm32_rows_warp(Dg, rdiag, Cg, tid);
+      else trsm32_cols_warp(Dg, rdiag, Cg, tid);
+    }
     __syncthreads();
     double o[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int t = tid + u * 256, r = t >> 5, c = t & 31;
-      double sum = 0;
-      if (b > j) {
-#pragma unroll 8
-        for (int q = 0; q < 32; q++) sum += Cg[r][q] * Dg[c][q];  // C Ljj^-T
-      } else {
-#pragma unroll 8
-        for (int q = 0; q < 32; q++) sum += Dg[r][q] * Cg[q][c];  // Ljj^-1 (-R)
-      }
-      o[u] = sum;
+      const int t = tid + u * 256;
+      o[u] = Cg[t >> 5][t & 31];
     }
     __syncthreads();
 #pragma unroll
@@ -286,18 +303,11 @@ __global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __r
     Dg[r][c + 1] = base.y - accD[u][1] - s1;
   }
   __syncthreads();
-  for (int t = tid; t < 1024; t += 256) Cg[t >> 5][t & 31] = ((t >> 5) == (t & 31)) ? 1.0 : 0.0;
-  __syncthreads();
-  if (tid < 32) {
-    chol32_warp(Dg, rdiag, tid);
-    __syncwarp();
-    trsm32_cols_warp(Dg, rdiag, Cg, tid);  // Ldd Y = I
-  }
+  if (tid < 32) chol32_warp(Dg, rdiag, tid);
   __syncthreads();
   for (int t = tid; t < 1024; t += 256) {
     const int r = t >> 5, c = t & 31;
     Lg[(long long)(d * 32 + r) * Mp + d * 32 + c] = Dg[r][c];
-    Xg[(long long)(d * 32 + r) * Mp + d * 32 + c] = Cg[r][c];
   }
 }
 
