@@ -163,6 +163,21 @@ mogpe_status mogpe_nccl_unique_id(char out[128]);
 mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int32_t rank, int32_t world_size);
 mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_t n, void* cuda_stream);
 
+/* Optimiser step on the device (reference: optimizer.apply_gradients in train_step,
+ * mogpe/keras/mixture_of_experts/mosvgpe.py:61-63, tf.optimizers.Adam with TF defaults).
+ *   var_rep [total] (host): for every entry of the packed buffer, the index of the representative entry of the
+ *     variable it belongs to (itself if untied), or -1 for entries that are not variables (padding, the strict upper
+ *     triangle of q_sqrt, non-trainable parameters).
+ *   u [total] (device): the unconstrained variables in the packed layout (lengthscales / variances / noise hold the
+ *     pre-softplus values; everything else is stored as is).
+ * mogpe_opt_transform writes params = T(u); mogpe_opt_adam_step chains `grads` (d ELBO / d constrained, as returned by
+ * mogpe_elbo_fwd_bwd) to the unconstrained variables, sums tied entries, applies one Adam step to loss = -ELBO and
+ * refreshes params.  t is the 1-based step count. */
+mogpe_status mogpe_opt_setup(mogpe_handle* h, const int32_t* var_rep, double noise_lower_bound);
+mogpe_status mogpe_opt_transform(mogpe_handle* h, double* u, double* params, void* cuda_stream);
+mogpe_status mogpe_opt_adam_step(mogpe_handle* h, double* u, double* params, const double* grads, double lr,
+                                 double beta1, double beta2, double epsilon, int64_t t, void* cuda_stream);
+
 /* Device memory helpers so the Python host needs no tensor framework. */
 mogpe_status mogpe_malloc(int32_t device, int64_t bytes, void** out);
 mogpe_status mogpe_free(int32_t device, void* p);

@@ -138,6 +138,94 @@ class MixtureCore:
             eps_mc = rng.standard_normal((100, N, eng.K))
         return eng.predict(Xnew, want=want, eps_mc=eps_mc)
 
+    # -- device-side training -------------------------------------------------------------------------
+    def _gps(self):
+        return self.expert_gps + [self.gating_gp]
+
+    def _packed_blocks(self, value_of, tri_of):
+        """GPBlocks whose arrays are produced by value_of(param) (q_sqrt: tri_of(param) -> [L, M, M])."""
+        blocks = []
+        for i, gp in enumerate(self._gps()):
+            is_expert = i < len(self.expert_gps)
+            L = gp.num_latent_gps
+            mean_c = None
+            if isinstance(gp.mean_function, Constant):
+                mean_c = np.broadcast_to(np.asarray(value_of(gp.mean_function.c), dtype=np.float64).reshape(-1), (L,)).copy()
+            noise = None
+            if is_expert:
+                noise = np.broadcast_to(np.asarray(value_of(gp.likelihood.variance), dtype=np.float64).reshape(-1), (L,)).copy()
+            blocks.append(GPBlock(
+                Z=np.asarray(value_of(gp.Z), dtype=np.float64),
+                lengthscales=[np.asarray(value_of(k.lengthscales), dtype=np.float64) for k in gp.latent_kernel_list],
+                variances=[float(np.asarray(value_of(k.variance))) for k in gp.latent_kernel_list],
+                q_mu=np.asarray(value_of(gp.q_mu), dtype=np.float64),
+                q_sqrt=np.asarray(tri_of(gp.q_sqrt), dtype=np.float64),
+                mean_c=mean_c, noise=noise))
+        return blocks[:-1], blocks[-1]
+
+    def setup_device_optimizer(self, batch: int):
+        """Build the variable map of the packed layout (ties: broadcast scalars, objects used twice) and upload the
+        unconstrained variables.  -> Engine."""
+        eng = self.ensure_engine(batch)
+        lowers = {float(g.likelihood.variance.transform.lower) for g in self.expert_gps}
+        if len(lowers) != 1:
+            raise NotImplementedError("experts with different Gaussian variance lower bounds need the host optimiser")
+        ids, next_id = {}, [1]
+
+        def ids_of(p):
+            if id(p) not in ids:
+                n = p.unconstrained.size
+                ids[id(p)] = (np.arange(next_id[0], next_id[0] + n, dtype=np.float64).reshape(p.unconstrained.shape), p)
+                next_id[0] += n
+            return ids[id(p)][0] if p.trainable else np.zeros(p.unconstrained.shape)
+
+        tri = lambda p: p.transform.forward(ids_of(p))  # FillTriangular of the id vector: ids land where the values do
+        flat_ids = eng.pack(*self._packed_blocks(ids_of, tri)).astype(np.int64)
+        uniq, first = np.unique(flat_ids, return_index=True)
+        first_of = dict(zip(uniq.tolist(), first.tolist()))
+        rep = np.full(flat_ids.shape, -1, dtype=np.int32)
+        nz = flat_ids > 0
+        rep[nz] = np.array([first_of[i] for i in flat_ids[nz].tolist()], dtype=np.int32)
+        self._var_positions = {pid: (np.array([first_of[int(i)] for i in arr.reshape(-1)], dtype=np.int64).reshape(arr.shape), p)
+                               for pid, (arr, p) in ids.items() if p.trainable}
+        eng.setup_optimizer(rep, lowers.pop())
+        u_blocks = self._packed_blocks(lambda p: p.unconstrained, lambda p: p.numpy())
+        eng.set_unconstrained(eng.pack(*u_blocks))
+        self._opt_engine = eng
+        return eng
+
+    def pull_variables(self):
+        """Copy the device-side unconstrained variables back into the Parameter objects."""
+        u = self._opt_engine.u.numpy()
+        for pos, p in self._var_positions.values():
+            p.assign_unconstrained(u[pos])
+
+    def fit_device(self, X, Y, bound, num_samples, num_data, optimizer, epochs, batch_size, shuffle, seed, tracker,
+                   verbose=0):
+        """Training loop with the whole step on the device: ELBO fwd+bwd -> bijector chain -> Adam -> params.
+        Only the minibatch (H2D) and 4 result scalars (D2H) cross the bus per step."""
+        X, Y = np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(Y, dtype=np.float64)
+        n = X.shape[0]
+        eng = self.setup_device_optimizer(min(batch_size, n))
+        rng = np.random.default_rng(seed)
+        history = {"loss": []}
+        for epoch in range(epochs):
+            tracker.reset_states()
+            order = rng.permutation(n) if shuffle else np.arange(n)
+            for s in range(0, n, batch_size):
+                idx = order[s:s + batch_size]
+                Xb, Yb = np.ascontiguousarray(X[idx]), np.ascontiguousarray(Y[idx])
+                scale = 1.0 if num_data is None else float(num_data) / len(idx)
+                res = eng.elbo(Xb, Yb, bound, num_samples, scale, want_grads=True, unpack=False)
+                optimizer.t += 1
+                eng.adam_step(optimizer.t, optimizer.lr, optimizer.b1, optimizer.b2, optimizer.eps)
+                tracker.update_state(-res.elbo)
+            history["loss"].append(tracker.result())
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - loss: {tracker.result():.4f}")
+        self.pull_variables()
+        return history
+
     def latent_slices(self):
         """-> per GP (experts..., gating): slice into the latent axis of f_mean / f_var."""
         out, l = [], 0

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
@@ -70,6 +71,10 @@ struct mogpe_handle {
   double prof_flops = 0;
   long long gemm_launches = 0, all_launches = 0;
   cudaStream_t prof_stream = nullptr;
+  // device-side optimiser
+  int* var_rep = nullptr;
+  double *opt_gu = nullptr, *opt_m = nullptr, *opt_v = nullptr;
+  double noise_lower = 1e-6;
   // NCCL (dlopen'ed)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
@@ -105,7 +110,7 @@ static void free_ws(mogpe_handle* h) {
   double** ptrs[] = {&h->Kuu, &h->L, &h->Linv, &h->Lbar, &h->T1, &h->T2, &h->Kuf, &h->A, &h->Abar, &h->W,
                      &h->LTA, &h->Sc, &h->V, &h->dV, &h->mean, &h->dmean, &h->var0ss, &h->varq, &h->dfvar,
                      &h->stage_dev, &h->out_dev, &h->eps_u_int, &h->eps_h_int, &h->eps_f_int, &h->ss_part, &h->lta_part,
-                     &h->dot_part};
+                     &h->dot_part, &h->opt_gu, &h->opt_m, &h->opt_v};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -117,6 +122,7 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_round_latent) cudaFree(h->d_round_latent);
   if (h->d_round_slot) cudaFree(h->d_round_slot);
   if (h->d_round_group) cudaFree(h->d_round_group);
+  if (h->var_rep) cudaFree(h->var_rep);
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
   for (auto e : h->ev) cudaEventDestroy(e);
@@ -919,6 +925,57 @@ extern "C" mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, dou
   h->ev_used = 0;
   h->prof_flops = 0;
   h->gemm_launches = h->all_launches = 0;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_opt_setup(mogpe_handle* h, const int32_t* var_rep, double noise_lower_bound) {
+  if (!h || !var_rep) return MOGPE_ERR_INVALID;
+  const long long n = h->lo.total;
+  for (long long i = 0; i < n; i++)
+    if (var_rep[i] >= n || (var_rep[i] >= 0 && var_rep[var_rep[i]] != var_rep[i]))
+      H_FAIL(h, MOGPE_ERR_INVALID, "var_rep[%lld] = %d is not a representative index", i, var_rep[i]);
+  H_CUDA(h, cudaSetDevice(h->device));
+  if (!h->var_rep) {
+    H_CUDA(h, dalloc(&h->var_rep, (size_t)n));
+    H_CUDA(h, dalloc(&h->opt_gu, (size_t)n));
+    H_CUDA(h, dalloc(&h->opt_m, (size_t)n));
+    H_CUDA(h, dalloc(&h->opt_v, (size_t)n));
+  }
+  H_CUDA(h, cudaMemcpy(h->var_rep, var_rep, sizeof(int) * n, cudaMemcpyHostToDevice));
+  H_CUDA(h, cudaMemset(h->opt_m, 0, sizeof(double) * n));
+  H_CUDA(h, cudaMemset(h->opt_v, 0, sizeof(double) * n));
+  h->noise_lower = noise_lower_bound;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_opt_transform(mogpe_handle* h, double* u, double* params, void* cuda_stream) {
+  if (!h || !u || !params) return MOGPE_ERR_INVALID;
+  if (!h->var_rep) H_FAIL(h, MOGPE_ERR_INVALID, "mogpe_opt_setup has not been called");
+  H_CUDA(h, cudaSetDevice(h->device));
+  const long long n = h->lo.total;
+  opt_transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(n, h->lo, h->var_rep, u,
+                                                                                           h->noise_lower, params);
+  KCOUNT(h, 1);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_opt_adam_step(mogpe_handle* h, double* u, double* params, const double* grads, double lr,
+                                            double beta1, double beta2, double epsilon, int64_t t, void* cuda_stream) {
+  if (!h || !u || !params || !grads) return MOGPE_ERR_INVALID;
+  if (!h->var_rep) H_FAIL(h, MOGPE_ERR_INVALID, "mogpe_opt_setup has not been called");
+  if (t < 1) H_FAIL(h, MOGPE_ERR_INVALID, "step count t must be >= 1");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  H_CUDA(h, cudaSetDevice(h->device));
+  const long long n = h->lo.total;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t));
+  H_CUDA(h, cudaMemsetAsync(h->opt_gu, 0, sizeof(double) * n, st));
+  opt_chain_kernel<<<blocks, 256, 0, st>>>(n, h->lo, u, grads, h->var_rep, h->opt_gu);
+  opt_adam_kernel<<<blocks, 256, 0, st>>>(n, h->var_rep, h->opt_gu, u, h->opt_m, h->opt_v, lr_t, beta1, beta2, epsilon);
+  opt_transform_kernel<<<blocks, 256, 0, st>>>(n, h->lo, h->var_rep, u, h->noise_lower, params);
+  KCOUNT(h, 3);
+  H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
 }
 

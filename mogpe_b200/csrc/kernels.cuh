@@ -725,6 +725,63 @@ __global__ void halve_diag_kernel(double* __restrict__ P, int Mp) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Device-side optimiser step: the reference's train_step applies tf.optimizers.Adam to the
+// UNCONSTRAINED variables (mosvgpe.py:57-69).  `u` holds them in the packed layout; positive parameters are
+// softplus-transformed (gpflow.utilities.positive; noise: + lower bound), q_sqrt's FillTriangular is a pure
+// permutation, so Adam (elementwise) acts on the lower-triangular entries in place.
+// var_rep[i] = index of the representative entry of the variable that packed entry i belongs to (-1: not a
+// variable).  Tied entries (a scalar lengthscale broadcast over D, an expert object used twice, ...) sum their
+// gradients into the representative, which is updated and broadcast back.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int param_kind(long long i, Layout lo) {  // 0 identity, 1 softplus, 2 softplus + noise lower bound
+  if (i < lo.Z) return 1;          // lengthscales, kernel variances
+  if (i >= lo.noise) return 2;     // Gaussian likelihood variances
+  return 0;                        // Z, q_mu, q_sqrt (lower triangle), mean_c
+}
+
+// gu[i] = dELBO/du_i (chain through the bijector); tied entries are accumulated into their representative
+__global__ void opt_chain_kernel(long long n, Layout lo, const double* __restrict__ u, const double* __restrict__ g,
+                                 const int* __restrict__ var_rep, double* __restrict__ gu) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int rep = var_rep[i];
+  if (rep < 0) return;
+  double v = g[i];
+  if (param_kind(i, lo) != 0) v *= 1.0 / (1.0 + exp(-u[i]));  // d softplus / du = sigmoid(u)
+  if (rep == i) atomicAdd(gu + i, v);
+  else atomicAdd(gu + rep, v);
+}
+
+// Adam (TF semantics: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); epsilon outside the sqrt) on loss = -ELBO
+__global__ void opt_adam_kernel(long long n, const int* __restrict__ var_rep, const double* __restrict__ gu,
+                                double* __restrict__ u, double* __restrict__ m, double* __restrict__ v, double lr_t,
+                                double b1, double b2, double eps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || var_rep[i] != i) return;
+  const double gl = -gu[i];
+  const double mi = m[i] + (1.0 - b1) * (gl - m[i]);
+  const double vi = v[i] + (1.0 - b2) * (gl * gl - v[i]);
+  m[i] = mi;
+  v[i] = vi;
+  u[i] -= lr_t * mi / (sqrt(vi) + eps);
+}
+
+// params[i] = T(u[rep(i)]) (and u of tied entries follows its representative); non-variables are left untouched
+__global__ void opt_transform_kernel(long long n, Layout lo, const int* __restrict__ var_rep, double* __restrict__ u,
+                                     double noise_lower, double* __restrict__ params) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int rep = var_rep[i];
+  if (rep < 0) return;
+  const double ui = u[rep];
+  if (rep != i) u[i] = ui;
+  const int kind = param_kind(i, lo);
+  double p = ui;
+  if (kind != 0) p = (ui > 0 ? ui : 0.0) + log1p(exp(-fabs(ui))) + (kind == 2 ? noise_lower : 0.0);  // stable softplus
+  params[i] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Philox4x32-10 + Box-Muller standard normals (counter-based: element i depends only on seed, offset+i)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {

@@ -299,6 +299,26 @@ class Engine:
         _lib.check(self.lib.mogpe_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(ng), C.byref(na)), self.h)
         return {"gemm_ms": ms.value, "gemm_flops": fl.value, "gemm_launches": ng.value, "all_launches": na.value}
 
+    # ---- device-side optimiser -------------------------------------------------------------------
+    def setup_optimizer(self, var_rep: np.ndarray, noise_lower: float = 1e-6):
+        """var_rep [total] int32: representative packed index of each entry's variable (-1: not a variable)."""
+        rep = np.ascontiguousarray(var_rep, dtype=np.int32)
+        if rep.shape != (self.lo.total,):
+            raise ValueError(f"var_rep must have {self.lo.total} entries")
+        _lib.check(self.lib.mogpe_opt_setup(self.h, rep.ctypes.data_as(C.POINTER(C.c_int32)), float(noise_lower)), self.h)
+        if getattr(self, "u", None) is None:
+            self.u = DeviceBuffer((self.lo.total,), self.device)
+
+    def set_unconstrained(self, u_flat: np.ndarray, stream=None):
+        """Upload the unconstrained variables and refresh params = T(u) on the device."""
+        self.u.copy_from(u_flat)
+        _lib.check(self.lib.mogpe_opt_transform(self.h, self.u.ptr, self.params.ptr, stream), self.h)
+
+    def adam_step(self, t: int, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, stream=None):
+        """One Adam step on loss = -ELBO from the gradients of the last elbo() call (all on the device)."""
+        _lib.check(self.lib.mogpe_opt_adam_step(self.h, self.u.ptr, self.params.ptr, self.grads_ptr, float(lr), float(beta_1),
+                                                float(beta_2), float(epsilon), int(t), stream), self.h)
+
     def predict_f_inducing_samples(self, X, num_samples, eps_u=None, stream=None):
         """-> f_mean [S, N, P], f_var [N, P] (mogpe/keras/gps.py:14-50); eps_u [P, S, Mp] or None (library stream)."""
         xv = as_view(X)

@@ -159,3 +159,28 @@ def test_library_random_stream_replays_through_the_oracle():
     assert abs(res.elbo - ref) <= 1e-8 * abs(ref)
     res2 = eng.elbo(X, Y, "further_gating", 2, 10.0, want_grads=False)
     assert res2.elbo != res.elbo  # the stream advances
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+def test_device_optimizer_matches_host_adam(flavour):
+    """fit(device_optimizer=True): bijector chain + Adam on the GPU == train_step's host Adam, step for step
+    (same library random stream), including tied variables (scalar lengthscale broadcast over D, shared noise)."""
+    from mogpe_b200._model_core import Adam
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=81, N=96, D=2, F=2, K=2, M=9, S=2, flavour=flavour, num_data=96, ard=False,
+                                separate_kernels=False, gating_mean_c=0.05)
+    a, b = model_from_spec(spec), model_from_spec(spec)
+    for m in (a, b):
+        m.set_seed(5)
+        m.compile(optimizer=Adam(learning_rate=0.02))
+    steps = 6
+    for _ in range(steps):
+        a.train_step((X, Y))                      # host: unpack grads, chain, numpy Adam, re-pack
+    b.fit(X, Y, epochs=steps, batch_size=96, shuffle=False)  # device: one batch per epoch = same 6 steps
+    assert len(a.trainable_variables) == len(b.trainable_variables)
+    for pa, pb in zip(a.trainable_variables, b.trainable_variables):
+        np.testing.assert_allclose(pb.unconstrained, pa.unconstrained, rtol=1e-9, atol=1e-11, err_msg=pa.name)
+    va = a.maximum_log_likelihood_objective((X, Y), eps=eps)
+    vb = b.maximum_log_likelihood_objective((X, Y), eps=eps)
+    assert va == pytest.approx(vb, rel=1e-9)
