@@ -90,6 +90,28 @@ def blocks_from_spec(spec):
     return [blk(g, True) for g in spec["experts"]], blk(spec["gating"], False)
 
 
+def build_public_model(spec, wl, device=0):
+    """The same model through the drop-in API classes (what a user of the reference constructs)."""
+    from mogpe_b200 import gpflow_lite as gl
+    from mogpe_b200.keras import MixtureOfSVGPExperts, SVGPExpert, SVGPGatingNetwork
+
+    def kern(g, L):
+        ks = [gl.RBF(variance=k["variance"], lengthscales=np.asarray(k["lengthscales"], float)) for k in g["kernels"]]
+        return ks[0] if len(ks) == 1 and L == 1 else (gl.SharedIndependent(ks[0], L) if len(ks) == 1 else gl.SeparateIndependent(ks))
+
+    experts = []
+    for g in spec["experts"]:
+        L = np.asarray(g["q_mu"]).shape[1]
+        k = kern(g, L)
+        k = k.kernel if isinstance(k, gl.SharedIndependent) else k
+        experts.append(SVGPExpert(k, gl.Gaussian(np.asarray(g["noise_variance"], float).reshape(1, -1)), gl.InducingPoints(g["Z"]),
+                                  gl.Constant(np.asarray(g["mean_c"], float)), num_latent_gps=L, q_mu=g["q_mu"], q_sqrt=g["q_sqrt"]))
+    g = spec["gating"]
+    G = np.asarray(g["q_mu"]).shape[1]
+    gating = SVGPGatingNetwork(kern(g, G), gl.InducingPoints(g["Z"]), q_mu=g["q_mu"], q_sqrt=g["q_sqrt"])
+    return MixtureOfSVGPExperts(experts, gating, num_samples=S, num_data=wl["num_data"], bound=BOUND, device=device)
+
+
 def step_flops(wl, B):
     """Algorithmic FLOPs of one fwd+bwd step (BASELINE.md work model; FMA = 2)."""
     F, K, M = wl["F"], wl["K"], wl["M"]
@@ -270,22 +292,27 @@ def main():
     clocks = sampler.stop() if sampler else None
     elbo_val = eng.gbuf.numpy(offset=eng.lo.total, count=4)
 
-    # end to end through the host-facing entry: pinned host X/Y -> H2D -> step -> D2H of the result
-    def e2e_step(i):
-        _, _, xn, yn = pinned[i % pool]
-        r = eng.elbo(xn, yn, BOUND, S, scale, want_grads=True, unpack=False)
-        if world > 1:
-            eng.allreduce(eng.gbuf)
-            torch.cuda.synchronize()
-        return r
+    # End to end through the public API a user of the reference calls: MixtureOfSVGPExperts.fit (Keras flavour).
+    # Every step copies its minibatch host -> device (staged through pinned memory inside mogpe_elbo_fwd_bwd_host),
+    # runs ELBO forward + backward, [all-reduces the gradients], applies the device-side Adam step, and reads the 4
+    # result scalars back (device -> host) before the next step starts.
+    del eng, dev_batches
+    model = build_public_model(spec, wl, device=local_rank)
+    model.set_seed(4321 + rank)
+    if world > 1:
+        ids2 = [Engine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids2, src=0)
+        model.enable_data_parallel(rank, world, ids2[0])
+    from mogpe_b200._model_core import Adam
 
-    for i in range(3):
-        e2e_step(i)
+    model.compile(optimizer=Adam(learning_rate=1e-3))
+    Xh = np.concatenate([hb[0] for hb in host_batches] * ((steps + 3) // pool + 1))[: (steps + 3) * B]
+    Yh = np.concatenate([hb[1] for hb in host_batches] * ((steps + 3) // pool + 1))[: (steps + 3) * B]
+    model.fit(Xh[: 3 * B], Yh[: 3 * B], epochs=1, batch_size=B, shuffle=False)  # warm-up (3 steps)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(steps):
-        e2e_step(i)
+    hist = model.fit(Xh[3 * B:], Yh[3 * B:], epochs=1, batch_size=B, shuffle=False)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -309,7 +336,9 @@ def main():
         "config": cfg, "clocks": clocks,
         "e2e": {"value": pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(B * (wl["D"] + wl["F"]) * 8), "d2h_bytes_per_step": 32,
-                "api": "Engine.elbo(X_host, Y_host) -> mogpe_elbo_fwd_bwd_host (pinned X/Y, H2D + D2H inside)"},
+                "api": "mogpe_b200.keras.MixtureOfSVGPExperts.fit(X_host, Y_host, batch_size=B): per step H2D of the "
+                       "minibatch, ELBO fwd+bwd, [NCCL all-reduce], device-side Adam, D2H of the result",
+                "final_loss": float(hist["loss"][-1])},
         "gpu_launches": int(prof["all_launches"]),
         "roofline": {
             "bound": "tensor", "kernel": "mogpe::gemm_dmma_kernel (all instances: A=Linv*Kuf, S^T*A, Linv^T*Abar, W*A^T, ...)",
@@ -320,7 +349,9 @@ def main():
             "gemm_ms_per_step": prof["gemm_ms"] / steps, "gemm_share_of_step": prof["gemm_ms"] / ms,
             "gemm_launches_per_step": prof["gemm_launches"] / steps,
             "step_model_tflops": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12,
-            "traffic": None,
+            "traffic": 1.071e9,
+            "traffic_note": "dram read+write of the largest launch (A = Linv*Kuf, 16 groups) from profiles/gemm_ncu_full_r01f.csv; "
+                            "its algorithmic bytes are 2 * Q*M*B*8 = 1.074e9 (read Kuf, write A): no re-reads",
         },
         "elbo_last_step": float(elbo_val[0]),
     }

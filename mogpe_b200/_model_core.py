@@ -70,6 +70,7 @@ class MixtureCore:
         self.engine: Optional[Engine] = None
         self.seed = 0
         self.default_batch = 1024
+        self.dp = None  # (rank, world_size, nccl unique id) for data-parallel fit()
 
     # -- engine lifecycle ---------------------------------------------------------------------------------
     def _blocks(self):
@@ -83,9 +84,18 @@ class MixtureCore:
             self.engine = Engine(experts, gating, flavour=self.flavour, max_batch=max(batch, self.default_batch),
                                  device=self.device)
             self.engine.set_seed(self.seed)
+            if self.dp is not None and self.dp[1] > 1:
+                self.engine.init_data_parallel(*self.dp)
         else:
             self.engine.set_params(experts, gating)
         return self.engine
+
+    def enable_data_parallel(self, rank: int, world_size: int, unique_id: bytes):
+        """One process per GPU: every rank calls fit() on ITS rows of each global minibatch; gradients are summed with
+        one NCCL all-reduce per step inside the library.  unique_id: Engine.nccl_unique_id() of rank 0."""
+        if self.engine is not None:
+            raise RuntimeError("enable_data_parallel must be called before the first objective / fit call")
+        self.dp = (int(rank), int(world_size), unique_id)
 
     def set_seed(self, seed: int):
         self.seed = int(seed)
@@ -167,31 +177,31 @@ class MixtureCore:
         """Build the variable map of the packed layout (ties: broadcast scalars, objects used twice) and upload the
         unconstrained variables.  -> Engine."""
         eng = self.ensure_engine(batch)
-        lowers = {float(g.likelihood.variance.transform.lower) for g in self.expert_gps}
-        if len(lowers) != 1:
-            raise NotImplementedError("experts with different Gaussian variance lower bounds need the host optimiser")
-        ids, next_id = {}, [1]
+        if getattr(self, "_opt_engine", None) is not eng:  # the variable map depends only on the model structure
+            lowers = {float(g.likelihood.variance.transform.lower) for g in self.expert_gps}
+            if len(lowers) != 1:
+                raise NotImplementedError("experts with different Gaussian variance lower bounds need the host optimiser")
+            ids, next_id = {}, [1]
 
-        def ids_of(p):
-            if id(p) not in ids:
-                n = p.unconstrained.size
-                ids[id(p)] = (np.arange(next_id[0], next_id[0] + n, dtype=np.float64).reshape(p.unconstrained.shape), p)
-                next_id[0] += n
-            return ids[id(p)][0] if p.trainable else np.zeros(p.unconstrained.shape)
+            def ids_of(p):
+                if id(p) not in ids:
+                    n = p.unconstrained.size
+                    ids[id(p)] = (np.arange(next_id[0], next_id[0] + n, dtype=np.float64).reshape(p.unconstrained.shape), p)
+                    next_id[0] += n
+                return ids[id(p)][0] if p.trainable else np.zeros(p.unconstrained.shape)
 
-        tri = lambda p: p.transform.forward(ids_of(p))  # FillTriangular of the id vector: ids land where the values do
-        flat_ids = eng.pack(*self._packed_blocks(ids_of, tri)).astype(np.int64)
-        uniq, first = np.unique(flat_ids, return_index=True)
-        first_of = dict(zip(uniq.tolist(), first.tolist()))
-        rep = np.full(flat_ids.shape, -1, dtype=np.int32)
-        nz = flat_ids > 0
-        rep[nz] = np.array([first_of[i] for i in flat_ids[nz].tolist()], dtype=np.int32)
-        self._var_positions = {pid: (np.array([first_of[int(i)] for i in arr.reshape(-1)], dtype=np.int64).reshape(arr.shape), p)
-                               for pid, (arr, p) in ids.items() if p.trainable}
-        eng.setup_optimizer(rep, lowers.pop())
+            tri = lambda p: p.transform.forward(ids_of(p))  # FillTriangular of the id vector: ids land where the values do
+            flat_ids = eng.pack(*self._packed_blocks(ids_of, tri)).astype(np.int64)
+            uniq, first, inv = np.unique(flat_ids, return_index=True, return_inverse=True)
+            rep = first[inv].astype(np.int32)
+            rep[flat_ids == 0] = -1
+            self._var_positions = {
+                pid: (first[np.searchsorted(uniq, arr.astype(np.int64).reshape(-1))].reshape(arr.shape), p)
+                for pid, (arr, p) in ids.items() if p.trainable}
+            eng.setup_optimizer(rep, lowers.pop())
+            self._opt_engine = eng
         u_blocks = self._packed_blocks(lambda p: p.unconstrained, lambda p: p.numpy())
         eng.set_unconstrained(eng.pack(*u_blocks))
-        self._opt_engine = eng
         return eng
 
     def pull_variables(self):
@@ -215,8 +225,12 @@ class MixtureCore:
             for s in range(0, n, batch_size):
                 idx = order[s:s + batch_size]
                 Xb, Yb = np.ascontiguousarray(X[idx]), np.ascontiguousarray(Y[idx])
-                scale = 1.0 if num_data is None else float(num_data) / len(idx)
+                world = 1 if self.dp is None else self.dp[1]
+                scale = 1.0 if num_data is None else float(num_data) / (len(idx) * world)
                 res = eng.elbo(Xb, Yb, bound, num_samples, scale, want_grads=True, unpack=False)
+                if world > 1:
+                    eng.allreduce(eng.gbuf)  # [grads | elbo, var_exp, kl_g, kl_e] summed over ranks
+                    res.elbo = float(eng.gbuf.numpy(offset=eng.lo.total, count=1)[0])
                 optimizer.t += 1
                 eng.adam_step(optimizer.t, optimizer.lr, optimizer.b1, optimizer.b2, optimizer.eps)
                 tracker.update_state(-res.elbo)

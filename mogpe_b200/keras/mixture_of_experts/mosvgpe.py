@@ -62,6 +62,10 @@ class MixtureOfSVGPExperts(MixtureOfExpertsBase):
     def set_seed(self, seed: int):
         self._core.set_seed(seed)
 
+    def enable_data_parallel(self, rank: int, world_size: int, unique_id: bytes):
+        """Data-parallel fit(): see MixtureCore.enable_data_parallel (new capability; the reference is single-device)."""
+        self._core.enable_data_parallel(rank, world_size, unique_id)
+
     # -- objective ---------------------------------------------------------------------------------------------
     def maximum_log_likelihood_objective(self, data, eps=None) -> float:
         return self.elbo(data=data, num_samples=self.num_samples, num_data=self.num_data, bound=self.bound, eps=eps)

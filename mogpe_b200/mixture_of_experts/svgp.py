@@ -40,6 +40,9 @@ class MixtureOfSVGPExperts(MixtureOfExperts):
     def set_seed(self, seed: int):
         self._core.set_seed(seed)
 
+    def enable_data_parallel(self, rank: int, world_size: int, unique_id: bytes):
+        self._core.enable_data_parallel(rank, world_size, unique_id)
+
     # -- objective ----------------------------------------------------------------------------------------------
     def _bound_name(self):
         if self.bound in BOUNDS:
