@@ -249,3 +249,21 @@ def test_invalid_arguments_raise():
         run_engine_elbo(eng, spec, X, Y, eps)
     with pytest.raises(ValueError):
         eng.elbo(X[:, :1].repeat(3, 1), Y)
+
+
+def test_large_inducing_count_m1024_predict_and_elbo():
+    """BASELINE config C5 uses M = 1024 (Mp = 1024: 32 Cholesky block steps, 16 GEMM row blocks)."""
+    from oracle import ref_numpy as rn
+    from tests._engine_helpers import engine_from_spec, run_engine_elbo
+
+    spec, X, Y, eps = make_spec(seed=31, N=1500, D=2, F=1, K=2, M=1024, S=1, num_data=15000)
+    eng = engine_from_spec(spec, max_batch=512)
+    out = eng.predict(X)  # 3 chunks
+    ym, yv = rn.predict_y(spec, X)
+    assert _rel(out["y_mean"], ym) < RTOL_VALUE and _rel(out["y_var"], yv) < RTOL_VALUE
+    assert _rel(out["mix_probs"], rn.predict_mixing_probs(spec, X)) < RTOL_VALUE
+    Xb, Yb = X[:512], Y[:512]
+    eps_b = {"u_experts": eps["u_experts"], "h": eps["h"][:, :512]}
+    res = run_engine_elbo(eng, spec, Xb, Yb, eps_b, want_grads=False)
+    ref = rn.elbo(spec, Xb, Yb, eps_b)
+    assert abs(res.elbo - ref) <= RTOL_VALUE * abs(ref)
