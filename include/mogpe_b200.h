@@ -142,6 +142,12 @@ mogpe_status mogpe_predict_f_inducing_samples(mogpe_handle* h, const double* X, 
  * mogpe/keras/gating_networks.py:251-253, mogpe/experts/svgp.py:161-169).  kl [P] device. */
 mogpe_status mogpe_prior_kl(mogpe_handle* h, const double* params, double* kl, void* cuda_stream);
 
+/* Monte-Carlo draws for the Softmax likelihood expectation inside the `tight` bound with G > 1 gating functions
+ * (gpflow Softmax.predict_mean_and_var: mean over num_mc draws of softmax(mu + sqrt(var) eps); the legacy flavour maps
+ * it over the S inducing samples, mogpe/mixture_of_experts/svgp.py:355-364).  eps_mc [S, num_mc, N, G] (device) is used
+ * by the next mogpe_elbo_fwd_bwd call(s); NULL -> drawn from the library stream each call.  Default num_mc = 100. */
+mogpe_status mogpe_set_mc(mogpe_handle* h, const double* eps_mc, int32_t num_mc);
+
 /* Library-owned random stream.  When an eps_* pointer that `bound` needs is NULL, the library draws it on
  * the device from Philox(seed, counter) -- as the reference draws inside tf.random / tfd -- and advances the
  * counter.  mogpe_debug_copy("eps_u" | "eps_h" | "eps_f") returns the draws of the last call so the oracle

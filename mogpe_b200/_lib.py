@@ -53,6 +53,7 @@ _PROTOS = {
     "mogpe_predict_f_inducing_samples": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     "mogpe_prior_kl": (C.c_int, [_P, _P, _P, _P]),
     "mogpe_fill_normal": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
+    "mogpe_set_mc": (C.c_int, [_P, _P, C.c_int32]),
     "mogpe_set_seed": (C.c_int, [_P, C.c_uint64]),
     "mogpe_set_kl_weight": (C.c_int, [_P, C.c_double]),
     "mogpe_profile_enable": (C.c_int, [_P, C.c_int32]),

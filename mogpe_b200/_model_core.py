@@ -128,6 +128,8 @@ class MixtureCore:
                 eps_h = np.ascontiguousarray(eps["h"], dtype=np.float64)
             if eps.get("f") is not None and bound == "further":
                 eps_f = eng.pack_eps_f(eps["f"])
+        if bound == "tight" and eng.G > 1:
+            eng.set_mc(None if eps is None else eps.get("mc"))
         res = eng.elbo(X, Y, bound, num_samples, scale, eps_u, eps_h, eps_f, want_grads=want_grads)
         grads = None
         if want_grads:

@@ -64,6 +64,12 @@ struct mogpe_handle {
   const double *last_eps_u = nullptr, *last_eps_h = nullptr, *last_eps_f = nullptr;
   long long last_nu = 0, last_nh = 0, last_nf = 0;
   double kl_weight = 1.0;
+  const double* eps_mc_user = nullptr;  // [S][num_mc][N][G] or null -> library stream
+  int num_mc = 100;
+  double* eps_mc_int = nullptr;
+  size_t eps_mc_cap = 0;
+  const double* last_eps_mc = nullptr;
+  long long last_nmc = 0;
   // measurement
   bool prof = false;
   std::vector<cudaEvent_t> ev;
@@ -110,7 +116,7 @@ static void free_ws(mogpe_handle* h) {
   double** ptrs[] = {&h->Kuu, &h->L, &h->Linv, &h->Lbar, &h->T1, &h->T2, &h->Kuf, &h->A, &h->Abar, &h->W,
                      &h->LTA, &h->Sc, &h->V, &h->dV, &h->mean, &h->dmean, &h->var0ss, &h->varq, &h->dfvar,
                      &h->stage_dev, &h->out_dev, &h->eps_u_int, &h->eps_h_int, &h->eps_f_int, &h->ss_part, &h->lta_part,
-                     &h->dot_part, &h->opt_gu, &h->opt_m, &h->opt_v};
+                     &h->dot_part, &h->opt_gu, &h->opt_m, &h->opt_v, &h->eps_mc_int};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -486,9 +492,6 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   if (S < 1 || S > MOGPE_MAX_SAMPLES) H_FAIL(h, MOGPE_ERR_INVALID, "num_samples=%d outside [1, %d]", S, MOGPE_MAX_SAMPLES);
   if (bound < 0 || bound > 2) H_FAIL(h, MOGPE_ERR_INVALID, "unknown bound id %d", bound);
   const ModelDev& md = h->md_host;
-  if (bound == MOGPE_BOUND_TIGHT && md.G > 1)
-    H_FAIL(h, MOGPE_ERR_UNSUPPORTED,
-           "tight bound with Softmax gating needs the Monte-Carlo likelihood expectation (not implemented)");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   H_CUDA(h, cudaSetDevice(h->device));
   mogpe_status rc = set_mode(h, bound, S, st);
@@ -517,6 +520,11 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     if ((rc = draw(eps_u, need_u, h->eps_u_int, h->eps_u_cap, nu)) != MOGPE_OK) return rc;
     if ((rc = draw(eps_h, need_h, h->eps_h_int, h->eps_h_cap, nh)) != MOGPE_OK) return rc;
     if ((rc = draw(eps_f, need_f, h->eps_f_int, h->eps_f_cap, nf)) != MOGPE_OK) return rc;
+    const double* eps_mc = h->eps_mc_user;
+    const bool need_mc = bound == MOGPE_BOUND_TIGHT && md.G > 1;
+    const size_t nmc = (size_t)S * h->num_mc * N * md.G;
+    if ((rc = draw(eps_mc, need_mc, h->eps_mc_int, h->eps_mc_cap, nmc)) != MOGPE_OK) return rc;
+    h->last_eps_mc = eps_mc; h->last_nmc = need_mc ? (long long)nmc : 0;
     h->last_eps_u = eps_u; h->last_nu = need_u ? (long long)nu : 0;
     h->last_eps_h = eps_h; h->last_nh = need_h ? (long long)nh : 0;
     h->last_eps_f = eps_f; h->last_nf = need_f ? (long long)nf : 0;
@@ -538,9 +546,10 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   LikArgs la;
   la.md = h->d_md; la.params = params; la.lo = lo; la.mean = h->mean; la.var0ss = h->var0ss; la.varq = h->varq;
   la.Y = Y; la.eps_h = eps_h; la.eps_f = eps_f; la.N = N; la.Bp = Bp; la.scale = scale;
+  la.eps_mc = h->last_eps_mc; la.num_mc = h->num_mc;
   la.dmean = h->dmean; la.dfvar = h->dfvar; la.out = out; la.grads = grads;
   {
-    const int slots = 4 * S * md.K + md.Pe;
+    const int slots = 4 * S * md.K + md.Pe + 6 * md.K;
     const int blk = lik_block(slots);
     const size_t smem = (size_t)slots * blk * sizeof(double);
     static size_t lik_smem_set = 0;
@@ -884,6 +893,14 @@ extern "C" mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_
   return MOGPE_OK;
 }
 
+extern "C" mogpe_status mogpe_set_mc(mogpe_handle* h, const double* eps_mc, int32_t num_mc) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (num_mc < 1) H_FAIL(h, MOGPE_ERR_INVALID, "num_mc must be >= 1");
+  h->eps_mc_user = eps_mc;
+  h->num_mc = num_mc;
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_set_seed(mogpe_handle* h, uint64_t seed) {
   if (!h) return MOGPE_ERR_INVALID;
   h->seed = seed;
@@ -1063,6 +1080,7 @@ extern "C" mogpe_status mogpe_debug_copy(mogpe_handle* h, const char* name, doub
   else if (s == "eps_u") src = h->last_eps_u, n = h->last_nu;
   else if (s == "eps_h") src = h->last_eps_h, n = h->last_nh;
   else if (s == "eps_f") src = h->last_eps_f, n = h->last_nf;
+  else if (s == "eps_mc") src = h->last_eps_mc, n = h->last_nmc;
   else H_FAIL(h, MOGPE_ERR_INVALID, "unknown intermediate '%s'", name);
   *n_out = n;
   H_CUDA(h, cudaSetDevice(h->device));

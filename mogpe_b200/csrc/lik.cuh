@@ -34,6 +34,8 @@ struct LikArgs {
   const double* Y;       // [N][F]
   const double* eps_h;   // [S][N][G]
   const double* eps_f;   // [S][N][Pe]
+  const double* eps_mc;  // [S][R][N][G] Softmax Monte-Carlo draws (tight bound, G > 1)
+  int num_mc;
   int N, Bp;
   double scale;
   double* dmean;  // [NV][Bp]
@@ -122,7 +124,7 @@ __device__ __forceinline__ void gating_backward_sample(const ModelDev* md, const
   }
 }
 
-// grid (Bp/blockDim), dynamic smem = (4*S*K + K*F)*blockDim doubles.  Threads n >= N write zero adjoints
+// grid (Bp/blockDim), dynamic smem = (4*S*K + K*F + 6*K)*blockDim doubles.  Threads n >= N write zero adjoints
 // (the padded columns feed the B-long GEMMs of the backward pass).
 __global__ void lik_kernel(const LikArgs a) {
   extern __shared__ double sm[];
@@ -225,7 +227,34 @@ __global__ void lik_kernel(const LikArgs a) {
         lp(DLPI + s * K + k) = 0.0;
       }
     // 2. gating log probabilities lpi[s][k]
-    if (bound == MOGPE_BOUND_TIGHT) {
+    if (bound == MOGPE_BOUND_TIGHT && G > 1) {
+      // inducing-sampled gating + Monte-Carlo Softmax expectation: pi_k = mean_r softmax_k(hm + sqrt(hv) eps_r)
+      const int HM = DN + Pe, SD = HM + K, PR = SD + K;  // scratch slots: hm[K], sd[K], p_r[K]
+      for (int s = 0; s < S; s++) {
+        for (int k = 0; k < K; k++) {
+          const int l = Pe + k, g = md->latent_group[l];
+          lp(HM + k) = valid ? a.mean[(long long)(md->voff[l] + s) * a.Bp + n] : 0.0;
+          lp(SD + k) = valid ? sqrt(a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n]) : 1.0;
+          lp(LPI + s * K + k) = 0.0;
+        }
+        for (int r = 0; r < a.num_mc; r++) {
+          double mx = -1e300;
+          for (int k = 0; k < K; k++) {
+            const double e = valid ? a.eps_mc[(((long long)s * a.num_mc + r) * a.N + n) * G + k] : 0.0;
+            const double h = lp(HM + k) + lp(SD + k) * e;
+            lp(PR + k) = h;
+            mx = fmax(mx, h);
+          }
+          double se = 0;
+          for (int k = 0; k < K; k++) {
+            lp(PR + k) = exp(lp(PR + k) - mx);
+            se += lp(PR + k);
+          }
+          for (int k = 0; k < K; k++) lp(LPI + s * K + k) += lp(PR + k) / se;
+        }
+        for (int k = 0; k < K; k++) lp(LPI + s * K + k) = log(lp(LPI + s * K + k) / (double)a.num_mc);
+      }
+    } else if (bound == MOGPE_BOUND_TIGHT) {
       // inducing-sampled gating + analytic Bernoulli expectation (keras/gating_networks.py:159-171,243-244)
       const int l = Pe, g = md->latent_group[l];
       for (int s = 0; s < S; s++) {
@@ -305,7 +334,48 @@ __global__ void lik_kernel(const LikArgs a) {
         }
       // 5. backward through the gating
       if (valid) {
-        if (bound == MOGPE_BOUND_TIGHT) {
+        if (bound == MOGPE_BOUND_TIGHT && G > 1) {
+          // d log pi_k = w_k d pi_k, w_k = dlpi_k / pi_k;  d pi_k / d h_j = mean_r p_rk (delta_kj - p_rj)
+          const int HM = DN + Pe, SD = HM + K, PR = SD + K, WK = PR + K, DH = WK + K, DS = DH + K;
+          for (int s = 0; s < S; s++) {
+            for (int k = 0; k < K; k++) {
+              const int l = Pe + k, g = md->latent_group[l];
+              lp(HM + k) = a.mean[(long long)(md->voff[l] + s) * a.Bp + n];
+              lp(SD + k) = sqrt(a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n]);
+              lp(WK + k) = lp(DLPI + s * K + k) / exp(lp(LPI + s * K + k));
+              lp(DH + k) = 0.0;
+              lp(DS + k) = 0.0;
+            }
+            for (int r = 0; r < a.num_mc; r++) {
+              const double* e = a.eps_mc + (((long long)s * a.num_mc + r) * a.N + n) * G;
+              double mx = -1e300;
+              for (int k = 0; k < K; k++) {
+                lp(PR + k) = lp(HM + k) + lp(SD + k) * e[k];
+                mx = fmax(mx, lp(PR + k));
+              }
+              double se = 0;
+              for (int k = 0; k < K; k++) {
+                lp(PR + k) = exp(lp(PR + k) - mx);
+                se += lp(PR + k);
+              }
+              double t = 0;
+              for (int k = 0; k < K; k++) {
+                lp(PR + k) /= se;
+                t += lp(WK + k) * lp(PR + k);
+              }
+              for (int k = 0; k < K; k++) {
+                const double dh = lp(PR + k) * (lp(WK + k) - t);
+                lp(DH + k) += dh;
+                lp(DS + k) += dh * e[k];
+              }
+            }
+            for (int k = 0; k < K; k++) {
+              const int l = Pe + k;
+              a.dmean[(long long)(md->voff[l] + s) * a.Bp + n] += lp(DH + k) / (double)a.num_mc;
+              a.dfvar[(long long)l * a.Bp + n] += lp(DS + k) / (double)a.num_mc * 0.5 / lp(SD + k);
+            }
+          }
+        } else if (bound == MOGPE_BOUND_TIGHT) {
           const int l = Pe, g = md->latent_group[l];
           const double hv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * a.Bp + n];
           const double rs = rsqrt(1.0 + hv);

@@ -207,6 +207,15 @@ class Engine:
         _lib.check(self.lib.mogpe_fill_normal(self.h, buf.ptr, buf.size if count is None else count, seed, offset, stream), self.h)
 
     # ---- the hot path ----------------------------------------------------------------------------------
+    def set_mc(self, eps_mc=None, num_mc=100):
+        """Softmax Monte-Carlo draws for the tight bound (G > 1): eps_mc [S, num_mc, N, G] or None (library stream)."""
+        ptr = None
+        if eps_mc is not None:
+            e = np.ascontiguousarray(eps_mc, dtype=np.float64)
+            num_mc = e.shape[1]
+            ptr, self._mc_keep = self._dev("eps_mc_elbo", e)
+        _lib.check(self.lib.mogpe_set_mc(self.h, ptr, int(num_mc)), self.h)
+
     def elbo(self, X, Y, bound="further_gating", num_samples=1, scale=1.0, eps_u=None, eps_h=None, eps_f=None,
              want_grads=True, unpack=True, readback=True, stream=None) -> ElboResult:
         """eps_u [P, S, Mp], eps_h [S, N, G], eps_f [S, N, K*F] (already in library layout); any eps left None

@@ -34,6 +34,8 @@ def run_engine_elbo(eng, spec, X, Y, eps, want_grads=True, device_inputs=False):
         eps_h = np.ascontiguousarray(eps["h"])
     elif b == "tight":
         eps_u = eng.pack_eps_u(eps["u_experts"], eps["u_gating"], S)
+        if eng.G > 1:
+            eng.set_mc(eps["mc"])  # Softmax likelihood expectation is Monte-Carlo: [S, R, N, G]
     else:
         eps_h = np.ascontiguousarray(eps["h"])
         eps_f = eng.pack_eps_f(eps["f"])

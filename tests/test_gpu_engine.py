@@ -145,10 +145,10 @@ def test_elbo_and_gradients_match_oracle(flavour, bound, case):
     from tests._engine_helpers import engine_from_spec, engine_grads_named, oracle_grads_constrained, run_engine_elbo
 
     K, F, S, M, N, D, sep = case
-    if bound == "tight" and K > 2:
-        pytest.skip("Softmax tight bound is Monte-Carlo in the reference; not implemented (MOGPE_ERR_UNSUPPORTED)")
     spec, X, Y, eps = make_spec(seed=100 + K + F + S, N=N, D=D, F=F, K=K, M=M, S=S, flavour=flavour, bound=bound,
                                 num_data=10 * N, separate_kernels=sep, gating_mean_c=0.2)
+    if bound == "tight" and K > 2:  # Softmax predict_mean_and_var is Monte-Carlo: explicit draws [S, R, N, K]
+        eps["mc"] = np.random.default_rng(17).standard_normal((S, 9, N, K))
     eng = engine_from_spec(spec, max_batch=N)
     res = run_engine_elbo(eng, spec, X, Y, eps)
     ref = rn.elbo(spec, X, Y, eps)
@@ -243,10 +243,9 @@ def test_invalid_arguments_raise():
     eng = engine_from_spec(spec, max_batch=16)
     with pytest.raises(MogpeError):
         run_engine_elbo(eng, spec, X, Y, eps)  # N > max_batch
-    spec["bound"] = "tight"
     eng = engine_from_spec(spec, max_batch=32)
     with pytest.raises(MogpeError, match="Softmax"):
-        run_engine_elbo(eng, spec, X, Y, eps)
+        eng.predict(X, want=("mix_probs",))  # Softmax mixing probabilities need Monte-Carlo draws
     with pytest.raises(ValueError):
         eng.elbo(X[:, :1].repeat(3, 1), Y)
 
