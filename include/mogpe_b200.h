@@ -43,7 +43,8 @@ typedef enum {
   MOGPE_ERR_INVALID = 1,
   MOGPE_ERR_CUDA = 2,
   MOGPE_ERR_UNSUPPORTED = 3,
-  MOGPE_ERR_NCCL = 4
+  MOGPE_ERR_NCCL = 4,
+  MOGPE_ERR_NUMERIC = 5 /* Cholesky of Kuu + jitter*I failed (not positive definite / NaN parameters) */
 } mogpe_status;
 
 /* bound ids: mogpe/keras/mixture_of_experts/mosvgpe.py:83-107 ; mogpe/mixture_of_experts/svgp.py:102-124 */
@@ -148,6 +149,12 @@ mogpe_status mogpe_prior_kl(mogpe_handle* h, const double* params, double* kl, v
  * by the next mogpe_elbo_fwd_bwd call(s); NULL -> drawn from the library stream each call.  Default num_mc = 100. */
 mogpe_status mogpe_set_mc(mogpe_handle* h, const double* eps_mc, int32_t num_mc);
 
+/* Numerical status of the calls issued since the last check (synchronises the stream).  The reference's
+ * tf.linalg.cholesky raises InvalidArgumentError when Kuu + jitter*I is not positive definite; here the factorisation
+ * records the first failing group and this call (made by the *_host entry and by the Python layer whenever it reads
+ * results back) returns MOGPE_ERR_NUMERIC with a message naming it. */
+mogpe_status mogpe_check_numerics(mogpe_handle* h, void* cuda_stream);
+
 /* Library-owned random stream.  When an eps_* pointer that `bound` needs is NULL, the library draws it on
  * the device from Philox(seed, counter) -- as the reference draws inside tf.random / tfd -- and advances the
  * counter.  mogpe_debug_copy("eps_u" | "eps_h" | "eps_f") returns the draws of the last call so the oracle
@@ -183,6 +190,11 @@ mogpe_status mogpe_opt_setup(mogpe_handle* h, const int32_t* var_rep, double noi
 mogpe_status mogpe_opt_transform(mogpe_handle* h, double* u, double* params, void* cuda_stream);
 mogpe_status mogpe_opt_adam_step(mogpe_handle* h, double* u, double* params, const double* grads, double lr,
                                  double beta1, double beta2, double epsilon, int64_t t, void* cuda_stream);
+
+/* Minibatch assembly from a device-resident data set (replaces the tf.data shuffle/batch pipeline of
+ * mogpe/training/utils.py:105-116): dst[i, :] = src[idx[i], :], src [N, cols], idx [n] int64, all device pointers. */
+mogpe_status mogpe_gather_rows(mogpe_handle* h, const double* src, const int64_t* idx, int64_t n, int32_t cols,
+                               double* dst, void* cuda_stream);
 
 /* Device memory helpers so the Python host needs no tensor framework. */
 mogpe_status mogpe_malloc(int32_t device, int64_t bytes, void** out);

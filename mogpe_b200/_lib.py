@@ -53,6 +53,7 @@ _PROTOS = {
     "mogpe_predict_f_inducing_samples": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     "mogpe_prior_kl": (C.c_int, [_P, _P, _P, _P]),
     "mogpe_fill_normal": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
+    "mogpe_check_numerics": (C.c_int, [_P, _P]),
     "mogpe_set_mc": (C.c_int, [_P, _P, C.c_int32]),
     "mogpe_set_seed": (C.c_int, [_P, C.c_uint64]),
     "mogpe_set_kl_weight": (C.c_int, [_P, C.c_double]),
@@ -64,6 +65,7 @@ _PROTOS = {
     "mogpe_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "mogpe_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int32]),
     "mogpe_allreduce_sum": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "mogpe_gather_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
     "mogpe_malloc": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(_P)]),
     "mogpe_free": (C.c_int, [C.c_int32, _P]),
     "mogpe_malloc_host": (C.c_int, [C.c_int64, C.POINTER(_P)]),

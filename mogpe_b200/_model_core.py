@@ -10,7 +10,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from .device import as_view
+from .device import DeviceBuffer, TensorView, as_view
 from .engine import Engine, GPBlock, GPGrads
 from .gpflow_lite import SVGP, Constant, Gaussian, Parameter
 
@@ -213,7 +213,7 @@ class MixtureCore:
             p.assign_unconstrained(u[pos])
 
     def fit_device(self, X, Y, bound, num_samples, num_data, optimizer, epochs, batch_size, shuffle, seed, tracker,
-                   verbose=0):
+                   verbose=0, device_data=False):
         """Training loop with the whole step on the device: ELBO fwd+bwd -> bijector chain -> Adam -> params.
         Only the minibatch (H2D) and 4 result scalars (D2H) cross the bus per step."""
         X, Y = np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(Y, dtype=np.float64)
@@ -221,12 +221,28 @@ class MixtureCore:
         eng = self.setup_device_optimizer(min(batch_size, n))
         rng = np.random.default_rng(seed)
         history = {"loss": []}
+        if device_data:
+            # the data set lives in HBM; each epoch uploads one permutation, each step gathers its rows
+            # on the device (no per-step host -> device copy of data)
+            Xd, Yd = DeviceBuffer.from_numpy(X, self.device), DeviceBuffer.from_numpy(Y, self.device)
+            idx_dev = DeviceBuffer((n,), self.device, zero=False)  # int64 bit pattern in an 8-byte slot
+            bmax = min(batch_size, n)
+            Xb_dev = DeviceBuffer((bmax, X.shape[1]), self.device, zero=False)
+            Yb_dev = DeviceBuffer((bmax, Y.shape[1]), self.device, zero=False)
         for epoch in range(epochs):
             tracker.reset_states()
             order = rng.permutation(n) if shuffle else np.arange(n)
+            if device_data:
+                idx_dev.copy_from(np.ascontiguousarray(order, dtype=np.int64).view(np.float64))
             for s in range(0, n, batch_size):
                 idx = order[s:s + batch_size]
-                Xb, Yb = np.ascontiguousarray(X[idx]), np.ascontiguousarray(Y[idx])
+                if device_data:
+                    eng.gather_rows(Xd, idx_dev.ptr + s * 8, len(idx), X.shape[1], Xb_dev)
+                    eng.gather_rows(Yd, idx_dev.ptr + s * 8, len(idx), Y.shape[1], Yb_dev)
+                    Xb = TensorView(Xb_dev.ptr, (len(idx), X.shape[1]), True, self.device, Xb_dev)
+                    Yb = TensorView(Yb_dev.ptr, (len(idx), Y.shape[1]), True, self.device, Yb_dev)
+                else:
+                    Xb, Yb = np.ascontiguousarray(X[idx]), np.ascontiguousarray(Y[idx])
                 world = 1 if self.dp is None else self.dp[1]
                 scale = 1.0 if num_data is None else float(num_data) / (len(idx) * world)
                 res = eng.elbo(Xb, Yb, bound, num_samples, scale, want_grads=True, unpack=False)

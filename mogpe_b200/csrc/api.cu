@@ -77,6 +77,7 @@ struct mogpe_handle {
   double prof_flops = 0;
   long long gemm_launches = 0, all_launches = 0;
   cudaStream_t prof_stream = nullptr;
+  int* d_fail = nullptr;  // 0 = ok, g + 1 = Cholesky of group g failed
   // device-side optimiser
   int* var_rep = nullptr;
   double *opt_gu = nullptr, *opt_m = nullptr, *opt_v = nullptr;
@@ -129,6 +130,7 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_round_slot) cudaFree(h->d_round_slot);
   if (h->d_round_group) cudaFree(h->d_round_group);
   if (h->var_rep) cudaFree(h->var_rep);
+  if (h->d_fail) cudaFree(h->d_fail);
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
   for (auto e : h->ev) cudaEventDestroy(e);
@@ -238,6 +240,8 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (e == cudaSuccess) e = dalloc(&h->d_round_slot, (size_t)MAXP * MAXP);
   if (e == cudaSuccess) e = dalloc(&h->d_round_group, (size_t)MAXP * MAXP);
   if (e == cudaSuccess) e = dalloc(&h->out_dev, 8);
+  if (e == cudaSuccess) e = dalloc(&h->d_fail, 1);
+  if (e == cudaSuccess) e = cudaMemset(h->d_fail, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->out_host_pinned, 8 * sizeof(double));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -433,7 +437,7 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, const doubl
   launch_kuf(h, params, X, N, Bc, h->side);
   kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
   for (int j = -1; j < Mp / 32; j++)  // launch j: block column j of L, block row j of L^-1, look-ahead factor of block j+1
-    chol_inv_step_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, j);
+    chol_inv_step_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, j, h->d_fail);
   KCOUNT(h, 4 + Mp / 32);
   H_CUDA(h, cudaGetLastError());
   H_CUDA(h, side_join(h, st));
@@ -710,7 +714,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd_host(mogpe_handle* h, const double* X
   H_CUDA(h, cudaMemcpyAsync(h->out_host_pinned, h->out_dev, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
   H_CUDA(h, cudaStreamSynchronize(st));
   memcpy(out_host, h->out_host_pinned, 4 * sizeof(double));
-  return MOGPE_OK;
+  return mogpe_check_numerics(h, cuda_stream);
 }
 
 extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const double* params,
@@ -893,6 +897,21 @@ extern "C" mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_
   return MOGPE_OK;
 }
 
+extern "C" mogpe_status mogpe_check_numerics(mogpe_handle* h, void* cuda_stream) {
+  if (!h) return MOGPE_ERR_INVALID;
+  H_CUDA(h, cudaSetDevice(h->device));
+  int flag = 0;
+  H_CUDA(h, cudaMemcpyAsync(&flag, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
+  H_CUDA(h, cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  if (flag != 0) {
+    H_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), (cudaStream_t)cuda_stream));
+    H_FAIL(h, MOGPE_ERR_NUMERIC,
+           "Cholesky decomposition was not successful: Kuu + jitter*I of kernel group %d is not positive definite "
+           "(or its parameters are NaN)", flag - 1);
+  }
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_set_mc(mogpe_handle* h, const double* eps_mc, int32_t num_mc) {
   if (!h) return MOGPE_ERR_INVALID;
   if (num_mc < 1) H_FAIL(h, MOGPE_ERR_INVALID, "num_mc must be >= 1");
@@ -992,6 +1011,19 @@ extern "C" mogpe_status mogpe_opt_adam_step(mogpe_handle* h, double* u, double* 
   opt_adam_kernel<<<blocks, 256, 0, st>>>(n, h->var_rep, h->opt_gu, u, h->opt_m, h->opt_v, lr_t, beta1, beta2, epsilon);
   opt_transform_kernel<<<blocks, 256, 0, st>>>(n, h->lo, h->var_rep, u, h->noise_lower, params);
   KCOUNT(h, 3);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_gather_rows(mogpe_handle* h, const double* src, const int64_t* idx, int64_t n, int32_t cols,
+                                          double* dst, void* cuda_stream) {
+  if (!h || !src || !idx || !dst || n < 0 || cols < 1) return MOGPE_ERR_INVALID;
+  if (n == 0) return MOGPE_OK;
+  H_CUDA(h, cudaSetDevice(h->device));
+  const long long total = (long long)n * cols;
+  gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+      src, reinterpret_cast<const long long*>(idx), (long long)n, cols, dst);
+  KCOUNT(h, 1);
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
 }

@@ -87,7 +87,7 @@ struct GemmCfg {
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS + BK;  // + BK per-k scales
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
   // resident CTAs per SM the register allocation must allow (64x64 tiles: 4 CTAs = 16 warps keep the DMMA pipe fed)
-  static constexpr int MIN_CTAS = (BM * BN <= 4096) ? 4 : ((BM * BN <= 8192) ? 2 : 1);
+  static constexpr int MIN_CTAS = (BM * BN <= 4096) ? (THREADS <= 128 ? 4 : 3) : ((BM * BN <= 8192) ? 2 : 1);
 };
 
 // One k-tile (BK deep) of MMAs for row-fragment range [I0, I1) of this warp.  TRIL: compile-time pattern
@@ -119,7 +119,7 @@ __device__ __forceinline__ void mma_ktile(const double* __restrict__ As, const d
     for (int i = I0; i < I1; i++)
 #pragma unroll
       for (int j = 0; j < Cfg::NI; j++)
-        if (!TRIL || (j / (Cfg::NI / 4)) <= (i / (Cfg::MI / 4))) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        if (!TRIL || (j * 4 / Cfg::NI) <= (i / (Cfg::MI / 4))) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
   }
 }
 
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
                                   GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::MIN_CTAS)
     gemm_dmma_kernel(const GemmParams p) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>;
-  static_assert(Cfg::MI % 4 == 0 && Cfg::NI % 4 == 0, "fragment quarters");
+  static_assert(Cfg::MI % 4 == 0, "fragment quarters");
   extern __shared__ __align__(16) double smem[];
 
   const int batch = blockIdx.z;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
   }
 
   const bool left_lower = p.kmode & KM_LEFT_LOWER, left_upper = p.kmode & KM_LEFT_UPPER;
-  const bool tril_diag = p.tril_out && row0 == col0 && BM == BN;
+  const bool tril_diag = p.tril_out && row0 == col0 && BM == BN && (Cfg::NI % 4 == 0);
   constexpr int QR = BM / 4;  // rows per fragment quarter
   constexpr int Q1 = Cfg::MI / 4, Q2 = Cfg::MI / 2, Q3 = 3 * Cfg::MI / 4, Q4 = Cfg::MI;
   for (int kt = 0; kt < nk; kt++) {
@@ -376,6 +376,12 @@ inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st
     case 9: if (p.N % 128 == 0) return launch_gemm_cfg<64, 128, 16, 32, 32, TA, TB, 3>(p, batch, st); break;
     case 10: if (p.K % 32 == 0) return launch_gemm_cfg<64, 64, 32, 32, 32, TA, TB, 2>(p, batch, st); break;
     case 11: if (p.K % 32 == 0) return launch_gemm_cfg<64, 64, 32, 32, 32, TA, TB, 3>(p, batch, st); break;
+    case 12: return launch_gemm_cfg<64, 64, 16, 32, 16, TA, TB, 2>(p, batch, st);      // 8 warps of 32x16
+    case 13: return launch_gemm_cfg<64, 64, 16, 32, 16, TA, TB, 3>(p, batch, st);
+    case 14: if (p.M % 128 == 0) return launch_gemm_cfg<128, 64, 16, 32, 32, TA, TB, 2>(p, batch, st); break;  // 8 warps
+    case 15: if (p.N % 128 == 0) return launch_gemm_cfg<64, 128, 16, 32, 32, TA, TB, 2>(p, batch, st); break;
+    case 16: if (p.K % 32 == 0) return launch_gemm_cfg<64, 64, 32, 32, 16, TA, TB, 2>(p, batch, st); break;
+    case 17: if (p.K % 32 == 0) return launch_gemm_cfg<64, 64, 32, 32, 32, TA, TB, 4>(p, batch, st); break;
     default: break;
   }
   return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 4>(p, batch, st);

@@ -122,14 +122,16 @@ __device__ __forceinline__ void dmma884_k(double& c0, double& c1, double a, doub
 
 // Cholesky of a 32x32 block held in shared memory, by ONE warp: lane r keeps row r in registers, pivots and
 // multipliers travel by shuffles (no block barriers on the sequential critical path).  rdiag[c] = 1 / L[c][c].
-__device__ __forceinline__ void chol32_warp(double (*Dg)[33], double* rdiag, int lane) {
+__device__ __forceinline__ void chol32_warp(double (*Dg)[33], double* rdiag, int lane, int* fail_flag, int fail_code) {
   double a[32];
+  bool bad = false;
 #pragma unroll
   for (int c = 0; c < 32; c++) a[c] = Dg[lane][c];
 #pragma unroll
   for (int c = 0; c < 32; c++) {
     const double piv = __shfl_sync(0xffffffffu, a[c], c);
-    const double rs = rsqrt(piv);  // NaN for a non-positive pivot (not positive definite): propagates to the ELBO
+    if (!(piv > 0.0)) bad = true;   // non-positive or NaN pivot: matrix is not positive definite
+    const double rs = rsqrt(piv);  // NaN for a non-positive pivot: also propagates to the ELBO
     a[c] = (lane == c) ? piv * rs : a[c] * rs;  // rows above the pivot hold junk in column c; never read
     if (lane == c) rdiag[c] = rs;
 #pragma unroll
@@ -140,6 +142,7 @@ __device__ __forceinline__ void chol32_warp(double (*Dg)[33], double* rdiag, int
   }
 #pragma unroll
   for (int c = 0; c < 32; c++) Dg[lane][c] = (c <= lane) ? a[c] : 0.0;
+  if (bad && lane == 0) atomicMax(fail_flag, fail_code);
 }
 
 // Solve T y = b for the 32 columns of Rb in place (T lower-triangular 32x32 in smem), ONE warp, lane = column.
@@ -186,7 +189,8 @@ __device__ __forceinline__ void trsm32_rows_warp(const double (*T)[33], const do
 // no cross-warp reduction, deterministic, 8 accumulator registers per product.
 // The only sequential work per launch is one block product + one 32x32 factor/invert by ONE CTA per group.
 __global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
-                                                                double* __restrict__ Linv, int Mp, int j) {
+                                                                double* __restrict__ Linv, int Mp, int j,
+                                                                int* __restrict__ fail_flag) {
   extern __shared__ __align__(16) double chol_smem[];  // Pa | Pb/Pc (never live together) | Dg | Cg
   __shared__ double rdiag[32];
   double(*Pa)[CHOL_PA] = reinterpret_cast<double(*)[CHOL_PA]>(chol_smem);
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __r
     Dg[r][c + 1] = base.y - accD[u][1] - s1;
   }
   __syncthreads();
-  if (tid < 32) chol32_warp(Dg, rdiag, tid);
+  if (tid < 32) chol32_warp(Dg, rdiag, tid, fail_flag, g + 1);  // flag = 1 + index of the failing group
   __syncthreads();
   for (int t = tid; t < 1024; t += 256) {
     const int r = t >> 5, c = t & 31;
@@ -722,6 +726,17 @@ __global__ void __launch_bounds__(256) kuu_grad_kernel(const ModelDev* __restric
 __global__ void halve_diag_kernel(double* __restrict__ P, int Mp) {
   double* p = P + (long long)blockIdx.x * Mp * Mp;
   for (int i = threadIdx.x; i < Mp; i += blockDim.x) p[(long long)i * Mp + i] *= 0.5;
+}
+
+// Minibatch assembly on the device (reference: tf.data shuffle + batch, mogpe/training/utils.py:105-116):
+// dst[i, :] = src[idx[i], :].   grid (ceil(n*C/256)), block 256
+__global__ void gather_rows_kernel(const double* __restrict__ src, const long long* __restrict__ idx, long long n, int C,
+                                   double* __restrict__ dst) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C) return;
+  const long long i = t / C;
+  const int c = (int)(t % C);
+  dst[t] = src[idx[i] * C + c];
 }
 
 // ------------------------------------------------------------------------------------------------

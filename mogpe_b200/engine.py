@@ -207,6 +207,14 @@ class Engine:
         _lib.check(self.lib.mogpe_fill_normal(self.h, buf.ptr, buf.size if count is None else count, seed, offset, stream), self.h)
 
     # ---- the hot path ----------------------------------------------------------------------------------
+    def gather_rows(self, src: DeviceBuffer, idx_dev_ptr: int, n: int, cols: int, dst: DeviceBuffer, stream=None):
+        """dst[i, :] = src[idx[i], :] on the device (idx: device pointer to n int64)."""
+        _lib.check(self.lib.mogpe_gather_rows(self.h, src.ptr, idx_dev_ptr, int(n), int(cols), dst.ptr, stream), self.h)
+
+    def check_numerics(self, stream=None):
+        """Raise MogpeError(MOGPE_ERR_NUMERIC) if a Cholesky factorisation failed since the last check."""
+        _lib.check(self.lib.mogpe_check_numerics(self.h, stream), self.h)
+
     def set_mc(self, eps_mc=None, num_mc=100):
         """Softmax Monte-Carlo draws for the tight bound (G > 1): eps_mc [S, num_mc, N, G] or None (library stream)."""
         ptr = None
@@ -248,6 +256,8 @@ class Engine:
                 self.h, ptrs[0], ptrs[1], N, self.params.ptr, ptrs[2], ptrs[3], ptrs[4],
                 b, num_samples, float(scale), self.out_ptr, gptr, stream), self.h)
             out = self.gbuf.numpy(offset=self.lo.total, count=4) if readback else None
+            if readback:
+                self.check_numerics(stream)
         if out is None:
             return None
         res = ElboResult(*[float(v) for v in out])
@@ -277,6 +287,7 @@ class Engine:
             mp, keep2 = self._dev("eps_mc", e)
         args = [bufs[k].ptr if k in bufs else None for k in ("f_mean", "f_var", "mix_probs", "y_mean", "y_var")]
         _lib.check(self.lib.mogpe_predict(self.h, xp, N, self.params.ptr, *args, mp, num_mc, stream), self.h)
+        self.check_numerics(stream)
         return {k: b.numpy() for k, b in bufs.items()}
 
     # ---- random stream / data parallel / measurement hooks ------------------------------------------------

@@ -114,18 +114,20 @@ class MixtureOfSVGPExperts(MixtureOfExpertsBase):
     def test_step(self, data, eps=None):
         return {"loss": -self.maximum_log_likelihood_objective(data, eps)}
 
-    def fit(self, X, Y, epochs=1, batch_size=32, shuffle=True, verbose=0, seed=0, device_optimizer=True):
+    def fit(self, X, Y, epochs=1, batch_size=32, shuffle=True, verbose=0, seed=0, device_optimizer=True,
+            device_data=False):
         """Minimal tf.keras.Model.fit: minibatches (last partial batch kept, as Keras does), per-epoch mean loss.
 
         device_optimizer=True (default, Adam only) keeps the variables, the bijector chain and Adam on the GPU for the
         whole loop and copies the variables back into the Parameter objects at the end; False runs train_step per
-        batch (gradients and Adam on the host, as the reference's eager loop)."""
+        batch (gradients and Adam on the host, as the reference's eager loop).  device_data=True additionally keeps the
+        data set in HBM and assembles every shuffled minibatch with a device gather (no per-step H2D)."""
         if self.optimizer is None:
             self.compile()
         if device_optimizer and isinstance(self.optimizer, Adam):
             bound = self.bound if self.bound in BOUNDS else "further_gating"
             return self._core.fit_device(X, Y, bound, self.num_samples, self.num_data, self.optimizer, epochs, batch_size,
-                                         shuffle, seed, self.loss_tracker, verbose)
+                                         shuffle, seed, self.loss_tracker, verbose, device_data)
         X, Y = np.asarray(X, dtype=np.float64), np.asarray(Y, dtype=np.float64)
         rng = np.random.default_rng(seed)
         history = {"loss": []}

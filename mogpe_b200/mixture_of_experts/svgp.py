@@ -104,14 +104,14 @@ class MixtureOfSVGPExperts(MixtureOfExperts):
         self.loss_tracker.update_state(-elbo)
         return {"loss": self.loss_tracker.result()}
 
-    def fit(self, X, Y, epochs=1, batch_size=32, shuffle=True, verbose=0, seed=0):
+    def fit(self, X, Y, epochs=1, batch_size=32, shuffle=True, verbose=0, seed=0, device_data=False):
         """Keras-style loop (the legacy class is a tf.keras.Model too) with the optimiser step on the device."""
         if self.optimizer is None:
             self.compile()
         if not isinstance(self.optimizer, Adam):
             raise NotImplementedError("fit() runs the device-side Adam; call train_step in your own loop otherwise")
         return self._core.fit_device(X, Y, self._bound_name(), self.num_samples, self.num_data, self.optimizer, epochs,
-                                     batch_size, shuffle, seed, self.loss_tracker, verbose)
+                                     batch_size, shuffle, seed, self.loss_tracker, verbose, device_data)
 
     # -- prediction -----------------------------------------------------------------------------------------------
     def __call__(self, Xnew, training: Optional[bool] = False):

@@ -184,3 +184,21 @@ def test_device_optimizer_matches_host_adam(flavour):
     va = a.maximum_log_likelihood_objective((X, Y), eps=eps)
     vb = b.maximum_log_likelihood_objective((X, Y), eps=eps)
     assert va == pytest.approx(vb, rel=1e-9)
+
+
+def test_device_resident_data_pipeline_matches_host_batches():
+    """fit(device_data=True): shuffled minibatches gathered on the device give the same training trajectory as
+    host-side slicing (same permutation stream, same library random stream)."""
+    from mogpe_b200._model_core import Adam
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=83, N=100, D=2, F=1, K=2, M=8, S=1, num_data=100)
+    a, b = model_from_spec(spec), model_from_spec(spec)
+    for m in (a, b):
+        m.set_seed(9)
+        m.compile(optimizer=Adam(learning_rate=0.01))
+    ha = a.fit(X, Y, epochs=3, batch_size=32, shuffle=True, seed=4)                    # 4 batches / epoch, last one ragged
+    hb = b.fit(X, Y, epochs=3, batch_size=32, shuffle=True, seed=4, device_data=True)
+    np.testing.assert_allclose(hb["loss"], ha["loss"], rtol=1e-10)
+    for pa, pb in zip(a.trainable_variables, b.trainable_variables):
+        np.testing.assert_allclose(pb.unconstrained, pa.unconstrained, rtol=1e-9, atol=1e-11, err_msg=pa.name)

@@ -266,3 +266,20 @@ def test_large_inducing_count_m1024_predict_and_elbo():
     res = run_engine_elbo(eng, spec, Xb, Yb, eps_b, want_grads=False)
     ref = rn.elbo(spec, Xb, Yb, eps_b)
     assert abs(res.elbo - ref) <= RTOL_VALUE * abs(ref)
+
+
+def test_cholesky_failure_is_reported_like_the_reference():
+    """tf.linalg.cholesky raises for a non positive-definite Kuu; we report MOGPE_ERR_NUMERIC naming the group."""
+    from mogpe_b200._lib import MogpeError
+    from tests._engine_helpers import engine_from_spec, run_engine_elbo
+
+    spec, X, Y, eps = make_spec(seed=3, N=40, D=1, K=2, M=6)
+    spec["gating"]["kernels"][0]["variance"] = float("nan")
+    eng = engine_from_spec(spec, max_batch=40)
+    with pytest.raises(MogpeError, match="Cholesky decomposition was not successful.*group 2"):
+        run_engine_elbo(eng, spec, X, Y, eps)
+    with pytest.raises(MogpeError, match="Cholesky"):
+        run_engine_elbo(eng, spec, X, Y, eps, device_inputs=True)
+    spec["gating"]["kernels"][0]["variance"] = 1.0
+    eng2 = engine_from_spec(spec, max_batch=40)
+    assert np.isfinite(run_engine_elbo(eng2, spec, X, Y, eps).elbo)
