@@ -1,0 +1,182 @@
+"""Config front-ends: the reference's TOML (legacy) and YAML/JSON (Keras) schemas build our models.
+CPU only (construction); the GPU test runs one objective through a TOML-built model."""
+import json
+import textwrap
+
+import numpy as np
+import pytest
+
+# same schema and values as the reference's examples/mcycle/configs/config_2_experts.toml (data, not code)
+TOML = textwrap.dedent('''
+    num_samples = 1
+    num_experts = 2
+    bound = "further_gating"
+    [[experts]]
+        whiten = true
+        [experts.mean_function]
+            name = "constant"
+            [experts.mean_function.params]
+                constant = 0.0
+        [experts.kernel]
+            name = "rbf"
+            [experts.kernel.params]
+                lengthscale = 10.0
+                variance = 0.1
+        [experts.likelihood]
+            name = "gaussian"
+            [experts.likelihood.params]
+                variance = 0.032
+        [experts.inducing_points]
+            num_inducing = 32
+            q_mu.mean = 0.0
+            q_mu.var = 2.0
+            q_sqrt = 1.0
+            q_diag = false
+    [[experts]]
+        [experts.kernel]
+            name = "rbf"
+            [experts.kernel.params]
+                lengthscale = 0.5
+                variance = 20.0
+        [experts.likelihood]
+            name = "gaussian"
+            [experts.likelihood.params]
+                variance = 0.9
+        [experts.inducing_points]
+            num_inducing = 32
+    [gating_network]
+        whiten = true
+        [gating_network.mean_function]
+            name = "zero"
+        [[gating_network.kernel]]
+            name = "rbf"
+            [gating_network.kernel.params]
+                lengthscale = 0.5
+                variance = 3.0
+        [gating_network.inducing_points]
+            num_inducing = 32
+            q_mu.mean = 0.0
+            q_mu.var = 2.0
+            q_sqrt = 2.0
+            inputs_trainable = false
+''')
+
+# same structure as the reference's examples/mcycle/notebooks/keras_configs/two_experts.yaml
+YAML = textwrap.dedent('''
+    class_name: MixtureOfSVGPExperts
+    config:
+      experts_list:
+      - class_name: SVGPExpert
+        config:
+          kernel: {class_name: SquaredExponential, config: {lengthscales: 10.0, variance: 1.0}}
+          likelihood: {class_name: Gaussian, config: {variance: 1.0}}
+          mean_function: {class_name: Constant, config: {c: 0.0}}
+          inducing_variable: {class_name: InducingPoints, config: {num_inducing: 10, input_dim: 1}}
+          num_latent_gps: 1
+      - class_name: SVGPExpert
+        config:
+          kernel: {class_name: SquaredExponential, config: {lengthscales: 1.0, variance: 1.0}}
+          likelihood: {class_name: Gaussian, config: {variance: 1.0}}
+          mean_function: {class_name: Constant, config: {c: 0.0}}
+          inducing_variable: {class_name: InducingPoints, config: {num_inducing: 10, input_dim: 1}}
+          num_latent_gps: 1
+      gating_network:
+        class_name: SVGPGatingNetwork
+        config:
+          kernel: {class_name: SquaredExponential, config: {lengthscales: 1.0, variance: 1.0}}
+          mean_function: {class_name: Zero, config: {output_dim: 1}}
+          inducing_variable: {class_name: InducingPoints, config: {num_inducing: 10, input_dim: 1}}
+    keras_version: 2.6.0
+    backend: tensorflow
+''')
+
+
+def _data(n=133):
+    rng = np.random.default_rng(0)
+    X = np.sort(rng.standard_normal((n, 1)), 0)
+    return X, np.sin(3 * X) + 0.1 * rng.standard_normal((n, 1))
+
+
+def test_toml_builds_the_legacy_model(tmp_path):
+    from mogpe_b200 import gpflow_lite as gl
+    from mogpe_b200.training import MixtureOfSVGPExperts_from_toml
+
+    p = tmp_path / "config_2_experts.toml"
+    p.write_text(TOML)
+    X, Y = _data()
+    model = MixtureOfSVGPExperts_from_toml(str(p), (X, Y), seed=1)
+    assert model.bound == "further_gating" and model.num_samples == 1 and model.num_data == 133 and model.num_experts == 2
+    e0, e1 = model.experts.experts_list
+    np.testing.assert_allclose(e0.kernel.lengthscales.numpy(), [10.0])
+    assert float(e0.kernel.variance.numpy()) == pytest.approx(0.1) and float(e0.likelihood.variance.numpy()) == pytest.approx(0.032)
+    assert isinstance(e0.mean_function, gl.Constant) and isinstance(e1.mean_function, gl.Zero)
+    assert e0.q_mu.numpy().shape == (32, 1) and e0.q_mu.numpy().std() > 1.0       # N(0, 2^2) initial noise
+    assert np.array_equal(e1.q_mu.numpy(), np.zeros((32, 1))) and np.array_equal(e1.q_sqrt.numpy()[0], np.eye(32))
+    assert not np.any(np.triu(e0.q_sqrt.numpy()[0], 1)) and np.all(np.diag(e0.q_sqrt.numpy()[0]) >= 0)
+    assert all(np.any(np.all(np.isclose(X, z), axis=1)) for z in e0.Z.numpy())    # Z = rows of X
+    g = model.gating_network
+    assert isinstance(g.likelihood, gl.Bernoulli) and g.num_gating_functions == 1 and not g.Z.trainable
+    assert g.Z not in model.trainable_variables and e0.Z in model.trainable_variables
+    model2 = MixtureOfSVGPExperts_from_toml(str(p), (X, Y), seed=1)
+    np.testing.assert_array_equal(model2.experts.experts_list[0].q_mu.numpy(), e0.q_mu.numpy())
+
+
+def test_toml_defaults_and_errors(tmp_path):
+    from mogpe_b200.training import MixtureOfSVGPExperts_from_toml
+
+    X, Y = _data(40)
+    bad = tmp_path / "bad.toml"
+    bad.write_text(TOML.replace('name = "rbf"', 'name = "cosine"', 1))
+    with pytest.raises(NotImplementedError, match="cosine"):
+        MixtureOfSVGPExperts_from_toml(str(bad), (X, Y))
+    nob = tmp_path / "nob.toml"
+    nob.write_text(TOML.replace('bound = "further_gating"\n', ""))
+    assert MixtureOfSVGPExperts_from_toml(str(nob), (X[:, :1].repeat(1, 1).repeat(4, 0), Y.repeat(4, 0))).bound == "further"
+    nok = tmp_path / "nok.toml"
+    nok.write_text(TOML.replace("num_experts = 2\n", ""))
+    with pytest.raises(NotImplementedError, match="num_experts"):
+        MixtureOfSVGPExperts_from_toml(str(nok), (X.repeat(4, 0), Y.repeat(4, 0)))
+
+
+def test_yaml_and_json_roundtrip(tmp_path):
+    from mogpe_b200 import gpflow_lite as gl
+    from mogpe_b200.keras import utils
+
+    y = tmp_path / "two_experts.yaml"
+    y.write_text(YAML)
+    model = utils.model_from_yaml(str(y), seed=0)
+    assert model.num_experts == 2 and model.bound == "further_gating" and model.num_samples == 1
+    assert model.experts_list[0].gp.Z.numpy().shape == (10, 1)
+    assert float(model.experts_list[0].gp.kernel.lengthscales.numpy()) == pytest.approx(10.0)
+    assert isinstance(model.gating_network.gp.likelihood, gl.Bernoulli)
+    X, Y = _data(50)
+    utils.sample_mosvgpe_inducing_inputs_from_data(X, model, seed=2)
+    assert all(np.any(np.isclose(X, z)) for z in model.gating_network.gp.Z.numpy())
+    # the reference's only test: deserialize(serialize(layer)) has the same type (tests/keras/test_keras.py:111-121)
+    for layer in [model, model.gating_network, model.experts_list[0], model.experts_list[0].gp.kernel,
+                  model.experts_list[0].gp.likelihood, model.experts_list[0].gp.mean_function,
+                  model.experts_list[0].gp.inducing_variable]:
+        cfg = utils.serialize(layer)
+        json.dumps(cfg, cls=utils.NumpyArrayEncoder)
+        assert type(utils.deserialize(cfg)) is type(layer)
+    j = tmp_path / "config.json"
+    utils.save_json_config(model, str(j))
+    loaded = utils.load_from_json_config(str(j))
+    for a, b in zip(model.trainable_variables, loaded.trainable_variables):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-15)
+
+
+@pytest.mark.gpu
+def test_toml_model_runs_on_the_gpu(tmp_path):
+    from mogpe_b200.training import MixtureOfSVGPExperts_from_toml
+
+    p = tmp_path / "c.toml"
+    p.write_text(TOML)
+    X, Y = _data()
+    model = MixtureOfSVGPExperts_from_toml(str(p), (X, Y), seed=1)
+    model.set_seed(0)
+    v = model.maximum_log_likelihood_objective((X[:16], Y[:16]))
+    assert np.isfinite(v)
+    hist = model.fit(X, Y, epochs=3, batch_size=16)
+    assert len(hist["loss"]) == 3 and np.all(np.isfinite(hist["loss"]))
+    assert model.predict_y(X).mean().shape == (133, 1)
