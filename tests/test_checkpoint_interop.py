@@ -106,6 +106,14 @@ def test_cuda_path_at_reference_trained_parameters():
     assert np.max(np.abs(dist.mean() - g["y_mean"])) <= 1e-8 * np.max(np.abs(g["y_mean"]))
     assert np.max(np.abs(dist.variance() - g["y_var"])) <= 1e-8 * np.max(np.abs(g["y_var"]))
     assert np.max(np.abs(model.predict_mixing_probs(X) - g["mix_probs"])) <= 1e-8
+    # the reference's metrics on top of predict_y (mogpe/training/metrics.py) at trained parameters: sane values
+    from mogpe_b200.training import metrics
+
+    nlpd, mae, rmse = (f(model, (X, Y)) for f in (metrics.negative_log_predictive_density, metrics.mean_absolute_error,
+                                                  metrics.root_mean_squared_error))
+    assert mae == pytest.approx(float(np.mean(np.abs(g["y_mean"] - Y))), rel=1e-8)
+    assert rmse == pytest.approx(float(np.sqrt(np.mean((g["y_mean"] - Y) ** 2))), rel=1e-8)
+    assert np.isfinite(nlpd) and nlpd < 0.5 and rmse < 0.5  # a trained model fits standardised data well
     fm, fv = model.experts.experts_list[0].predict_f(X)
     assert np.max(np.abs(fm - g["expert0/f_mean"])) <= 1e-8 * np.max(np.abs(g["expert0/f_mean"]))
     assert np.max(np.abs(fv - g["expert0/f_var"])) <= 1e-8 * np.max(np.abs(g["expert0/f_var"]))
