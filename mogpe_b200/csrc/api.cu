@@ -57,6 +57,8 @@ struct mogpe_handle {
   // the backward) overlaps the latency-bound factorisation launches
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_rows;  // ev_rows[i]: rows [64 i, 64 i + 64) of L^-1 are complete (Cholesky chain progress)
+  bool a_done_in_factorise = false;
   // library-owned random stream
   uint64_t seed = 0x6d6f677065ULL, rng_counter = 0;
   double *eps_u_int = nullptr, *eps_h_int = nullptr, *eps_f_int = nullptr;
@@ -135,6 +137,7 @@ static void free_ws(mogpe_handle* h) {
   if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
   for (auto e : h->ev) cudaEventDestroy(e);
   h->ev.clear();
+  for (auto e : h->ev_rows) cudaEventDestroy(e);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->side) cudaStreamDestroy(h->side);
@@ -405,6 +408,8 @@ static cudaError_t hgemm(mogpe_handle* h, const GemmParams& p, int batch, bool t
 #define KCOUNT(h, n) ((h)->all_launches += (n))
 
 // Kuu -> L -> Linv for every group, and the clean q_sqrt copies.
+static cudaError_t launch_a_gemm(mogpe_handle* h, int Bc, int row_base, int rows, cudaStream_t st);
+
 // fork / join of the side stream around a region of the caller's stream
 static cudaError_t side_fork(mogpe_handle* h, cudaStream_t st) {
   cudaError_t e = cudaEventRecord(h->ev_fork, st);
@@ -436,12 +441,48 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, const doubl
   make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, h->side>>>(h->d_md, params, h->lo, h->Sc, eps_u, S, h->V);
   launch_kuf(h, params, X, N, Bc, h->side);
   kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
-  for (int j = -1; j < Mp / 32; j++)  // launch j: block column j of L, block row j of L^-1, look-ahead factor of block j+1
+  // Launch j of the chain completes block row j of L^-1.  A = L^-1 Kuf only needs rows [64 i, 64 i + 64) of L^-1 for
+  // its row block i, so the A-GEMM is issued in 64-row slices on the side stream, each waiting for the chain launch
+  // that completes its rows: the DMMA work fills the SMs that the latency-bound chain leaves idle.
+  const int nslices = Mp / 64;
+  while ((int)h->ev_rows.size() < nslices) {
+    cudaEvent_t e;
+    H_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev_rows.push_back(e);
+  }
+  const bool pipeline = !h->prof;  // per-GEMM event timing needs the GEMMs alone on the device
+  for (int j = -1; j < Mp / 32; j++) {
     chol_inv_step_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, j, h->d_fail);
+    if (pipeline && j >= 0 && (j & 1)) {
+      const int i = j >> 1;
+      H_CUDA(h, cudaEventRecord(h->ev_rows[i], st));
+      H_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_rows[i], 0));
+      H_CUDA(h, launch_a_gemm(h, Bc, i * 64, 64, h->side));
+    }
+  }
+  h->a_done_in_factorise = pipeline;
   KCOUNT(h, 4 + Mp / 32);
   H_CUDA(h, cudaGetLastError());
   H_CUDA(h, side_join(h, st));
   return MOGPE_OK;
+}
+
+// A = Linv Kuf for result rows [row_base, row_base + rows) of every group, with the fused statistics epilogue
+// (per-row-block partials of sum_m A^2 and of the means A^T V: no second pass over A).
+static cudaError_t launch_a_gemm(mogpe_handle* h, int Bc, int row_base, int rows, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, Mp = h->Mp;
+  GemmParams p = gp_init();
+  p.A = h->Linv; p.sA = (long long)Mp * Mp; p.lda = Mp;
+  p.B = h->Kuf;  p.sB = (long long)Mp * h->Bp; p.ldb = h->Bp;
+  p.C = h->A;    p.sC = (long long)Mp * h->Bp; p.ldc = h->Bp;
+  p.M = rows; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_LOWER; p.row_base = row_base; p.M_total = Mp;
+  p.stat_ss = h->ss_part; p.stat_dot = h->dot_part; p.statV = h->V; p.ldstat = h->Bp;
+  p.statvec_begin = reinterpret_cast<const int*>(reinterpret_cast<const char*>(h->d_md) + offsetof(ModelDev, gvec_begin));
+  p.statvec = reinterpret_cast<const int*>(reinterpret_cast<const char*>(h->d_md) + offsetof(ModelDev, gvec));
+  // algorithmic FLOPs of the slice: rows x (row_base + rows/2 ...) ~ triangular part: sum over its rows of 2*k*Bc
+  const double flops = (double)Q * Bc * ((double)rows * (2.0 * row_base + rows));
+  return hgemm(h, p, Q, false, false, st, flops, STAT_CFG);
 }
 
 // Kuf, A = Linv Kuf, LTA_l = S_l^T A for marginal latents, for columns [0, Bp) of the current chunk.
@@ -451,18 +492,8 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
   const int Q = md.Q, Mp = h->Mp;
   if (!kuf_done) launch_kuf(h, params, X, N, Bc, st);
   H_CUDA(h, cudaGetLastError());
-  {
-    GemmParams p = gp_init();
-    p.A = h->Linv; p.sA = (long long)Mp * Mp; p.lda = Mp;
-    p.B = h->Kuf;  p.sB = (long long)Mp * h->Bp; p.ldb = h->Bp;
-    p.C = h->A;    p.sC = (long long)Mp * h->Bp; p.ldc = h->Bp;
-    p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_LOWER;
-    // fused epilogue: per-row-block partials of sum_m A^2 and of the means A^T V (no second pass over A)
-    p.stat_ss = h->ss_part; p.stat_dot = h->dot_part; p.statV = h->V; p.ldstat = h->Bp;
-    p.statvec_begin = reinterpret_cast<const int*>(reinterpret_cast<const char*>(h->d_md) + offsetof(ModelDev, gvec_begin));
-    p.statvec = reinterpret_cast<const int*>(reinterpret_cast<const char*>(h->d_md) + offsetof(ModelDev, gvec));
-    H_CUDA(h, hgemm(h, p, Q, false, false, st, (double)Q * Mp * Mp * Bc, STAT_CFG));
-  }
+  if (!(kuf_done && h->a_done_in_factorise)) H_CUDA(h, launch_a_gemm(h, Bc, 0, Mp, st));
+  h->a_done_in_factorise = false;
   if (md.nlta > 0) {
     GemmParams p = gp_init();
     p.A = h->Sc;  p.sA = (long long)Mp * Mp; p.lda = Mp; p.mapA = h->d_lta_latent;

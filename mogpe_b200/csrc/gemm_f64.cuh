@@ -49,7 +49,11 @@ struct GemmParams {
   const int* statvec_begin; // [batch + 1] (indexed by mapped C batch)
   const int* statvec;       // vector ids
   int ldstat;
-  int stat_rowblocks;       // M / BM of the launch (set by the launcher)
+  int stat_rowblocks;       // row blocks of the WHOLE matrix (M_total / BM), set by the launcher
+  // row slice: this launch produces rows [row_base, row_base + M) of a result with M_total rows (triangular k ranges
+  // and statistics row-block indices are absolute).  row_base must be a multiple of the row tile.
+  int row_base;
+  int M_total;              // 0 -> M
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
   // heavier (lower) row blocks first for lower-triangular left operands
   const int brow = (p.kmode & KM_LEFT_LOWER) ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
   const int bcol = blockIdx.x;
-  const int row0 = brow * BM, col0 = bcol * BN;
+  const int row0 = p.row_base + brow * BM, col0 = bcol * BN;
   if (p.tril_out && col0 > row0 + BM - 1) {
     // strictly-upper tile of a lower-triangular result: exact zeros (consumers read whole tiles)
     if (p.beta == 0.0) {
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
     const int cb = p.mapC ? p.mapC[batch] : batch;
     const int vb = p.statvec_begin ? p.statvec_begin[cb] : 0, ve = p.statvec_begin ? p.statvec_begin[cb + 1] : 0;
     for (int qi = -1; qi < ve - vb; qi++) {
-      const double* vv = (qi >= 0) ? p.statV + (long long)p.statvec[vb + qi] * p.M + row0 : nullptr;
+      const double* vv = (qi >= 0) ? p.statV + (long long)p.statvec[vb + qi] * (p.M_total ? p.M_total : p.M) + row0 : nullptr;
       double w[Cfg::MI];
 #pragma unroll
       for (int i = 0; i < Cfg::MI; i++) w[i] = vv ? vv[(i * Cfg::WARPS_M + wr) * 8 + lr] : 0.0;
@@ -293,8 +297,9 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
         double t = 0;
 #pragma unroll
         for (int q = 0; q < Cfg::WARPS_M; q++) t += red[q * BN + c];
-        double* dst = (qi < 0) ? p.stat_ss + ((long long)cb * p.stat_rowblocks + brow) * p.ldstat
-                               : p.stat_dot + ((long long)p.statvec[vb + qi] * p.stat_rowblocks + brow) * p.ldstat;
+        const int arb = row0 / BM;  // absolute row block
+        double* dst = (qi < 0) ? p.stat_ss + ((long long)cb * p.stat_rowblocks + arb) * p.ldstat
+                               : p.stat_dot + ((long long)p.statvec[vb + qi] * p.stat_rowblocks + arb) * p.ldstat;
         dst[col0 + c] = t;
       }
       __syncthreads();
@@ -340,7 +345,8 @@ inline cudaError_t launch_gemm_cfg(const GemmParams& p, int batch, cudaStream_t 
   }
   dim3 grid(p.N / BN, p.M / BM, batch);
   GemmParams q = p;
-  q.stat_rowblocks = p.M / BM;
+  q.stat_rowblocks = (p.M_total ? p.M_total : p.M) / BM;
+  if (p.row_base % BM) return cudaErrorInvalidValue;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(q);
   return cudaGetLastError();
 }
