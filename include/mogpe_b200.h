@@ -119,6 +119,16 @@ mogpe_status mogpe_elbo_fwd_bwd_host(mogpe_handle* h, const double* X_host, cons
                                      int32_t num_samples, double scale, double* out_host, double* grads,
                                      void* cuda_stream);
 
+/* Asynchronous variant for training loops: same as mogpe_elbo_fwd_bwd_host (library random stream for the draws), but it
+ * returns as soon as the work is enqueued.  X / Y are copied into one of a small ring of pinned staging slots (the call
+ * blocks only if the slot it needs is still in flight); the 4 result doubles are written to out_dev (device; NULL ->
+ * internal) and copied asynchronously into
+ * out_host_pinned (caller-owned pinned memory, mogpe_malloc_host) and are valid after the stream has been synchronised
+ * (mogpe_stream_sync / mogpe_check_numerics). */
+mogpe_status mogpe_elbo_fwd_bwd_host_async(mogpe_handle* h, const double* X_host, const double* Y_host, int32_t N,
+                                           const double* params, int32_t bound, int32_t num_samples, double scale,
+                                           double* out_dev, double* out_host_pinned, double* grads, void* cuda_stream);
+
 /* Prediction.  Replaces predict_y / predict_experts_f / predict_experts_y / predict_mixing_probs
  * (mogpe/keras/mixture_of_experts/base.py:65-77, mosvgpe.py:276-290, keras/gating_networks.py:173-249;
  * mogpe/mixture_of_experts/base.py:58-115, mogpe/experts/svgp.py:171-227,
@@ -203,6 +213,7 @@ mogpe_status mogpe_malloc_host(int64_t bytes, void** out); /* pinned */
 mogpe_status mogpe_free_host(void* p);
 mogpe_status mogpe_memcpy_h2d(int32_t device, void* dst, const void* src, int64_t bytes, void* cuda_stream);
 mogpe_status mogpe_memcpy_d2h(int32_t device, void* dst, const void* src, int64_t bytes, void* cuda_stream);
+mogpe_status mogpe_memcpy_d2h_async(int32_t device, void* dst_pinned, const void* src, int64_t bytes, void* cuda_stream);
 mogpe_status mogpe_memset_zero(int32_t device, void* dst, int64_t bytes, void* cuda_stream);
 mogpe_status mogpe_stream_sync(int32_t device, void* cuda_stream);
 

@@ -49,6 +49,7 @@ _PROTOS = {
     "mogpe_param_layout": (C.c_int, [_P, C.POINTER(Layout)]),
     "mogpe_elbo_fwd_bwd": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_double, _P, _P, _P]),
     "mogpe_elbo_fwd_bwd_host": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_double, _P, _P, _P]),
+    "mogpe_elbo_fwd_bwd_host_async": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P]),
     "mogpe_predict": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "mogpe_predict_f_inducing_samples": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     "mogpe_prior_kl": (C.c_int, [_P, _P, _P, _P]),
@@ -72,6 +73,7 @@ _PROTOS = {
     "mogpe_free_host": (C.c_int, [_P]),
     "mogpe_memcpy_h2d": (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),
     "mogpe_memcpy_d2h": (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),
+    "mogpe_memcpy_d2h_async": (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),
     "mogpe_memset_zero": (C.c_int, [C.c_int32, _P, C.c_int64, _P]),
     "mogpe_stream_sync": (C.c_int, [C.c_int32, _P]),
     "mogpe_debug_copy": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),

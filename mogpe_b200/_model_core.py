@@ -10,11 +10,17 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from .device import DeviceBuffer, TensorView, as_view
+from .device import DeviceBuffer, PinnedBuffer, TensorView, as_view
 from .engine import Engine, GPBlock, GPGrads
 from .gpflow_lite import SVGP, Constant, Gaussian, Parameter
 
 LOG_2PI = math.log(2.0 * math.pi)
+
+
+def _lib_check(status):
+    from . import _lib
+
+    _lib.check(status)
 
 
 def svgp_to_block(gp: SVGP, is_expert: bool) -> GPBlock:
@@ -229,29 +235,38 @@ class MixtureCore:
             bmax = min(batch_size, n)
             Xb_dev = DeviceBuffer((bmax, X.shape[1]), self.device, zero=False)
             Yb_dev = DeviceBuffer((bmax, Y.shape[1]), self.device, zero=False)
+        world = 1 if self.dp is None else self.dp[1]
+        steps_per_epoch = (n + batch_size - 1) // batch_size
+        results = PinnedBuffer(4 * steps_per_epoch)  # every step's {elbo, var_exp, kl_g, kl_e}, copied back asynchronously
+        lib = eng.lib
         for epoch in range(epochs):
             tracker.reset_states()
             order = rng.permutation(n) if shuffle else np.arange(n)
             if device_data:
                 idx_dev.copy_from(np.ascontiguousarray(order, dtype=np.int64).view(np.float64))
-            for s in range(0, n, batch_size):
+            for step_i, s in enumerate(range(0, n, batch_size)):
                 idx = order[s:s + batch_size]
+                scale = 1.0 if num_data is None else float(num_data) / (len(idx) * world)
+                out_ptr = results.ptr + 32 * step_i
                 if device_data:
                     eng.gather_rows(Xd, idx_dev.ptr + s * 8, len(idx), X.shape[1], Xb_dev)
                     eng.gather_rows(Yd, idx_dev.ptr + s * 8, len(idx), Y.shape[1], Yb_dev)
                     Xb = TensorView(Xb_dev.ptr, (len(idx), X.shape[1]), True, self.device, Xb_dev)
                     Yb = TensorView(Yb_dev.ptr, (len(idx), Y.shape[1]), True, self.device, Yb_dev)
+                    eng.elbo(Xb, Yb, bound, num_samples, scale, want_grads=True, unpack=False, readback=False)
                 else:
-                    Xb, Yb = np.ascontiguousarray(X[idx]), np.ascontiguousarray(Y[idx])
-                world = 1 if self.dp is None else self.dp[1]
-                scale = 1.0 if num_data is None else float(num_data) / (len(idx) * world)
-                res = eng.elbo(Xb, Yb, bound, num_samples, scale, want_grads=True, unpack=False)
+                    # host rows -> pinned staging ring -> device, nothing waits for the GPU
+                    eng.elbo_host_async(X[idx], Y[idx], bound, num_samples, scale, out_ptr)
                 if world > 1:
                     eng.allreduce(eng.gbuf)  # [grads | elbo, var_exp, kl_g, kl_e] summed over ranks
-                    res.elbo = float(eng.gbuf.numpy(offset=eng.lo.total, count=1)[0])
+                if device_data or world > 1:
+                    _lib_check(lib.mogpe_memcpy_d2h_async(eng.device, out_ptr, eng.out_ptr, 32, None))
                 optimizer.t += 1
                 eng.adam_step(optimizer.t, optimizer.lr, optimizer.b1, optimizer.b2, optimizer.eps)
-                tracker.update_state(-res.elbo)
+            eng.check_numerics()  # one synchronisation per epoch; raises if a Cholesky failed
+            losses = -results.array[0:4 * steps_per_epoch:4]
+            for v in losses:
+                tracker.update_state(v)
             history["loss"].append(tracker.result())
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs} - loss: {tracker.result():.4f}")

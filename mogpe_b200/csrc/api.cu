@@ -50,6 +50,14 @@ struct mogpe_handle {
   int *d_round_latent = nullptr, *d_round_slot = nullptr, *d_round_group = nullptr;  // [MAXP rounds][MAXP]
   int n_rounds = 0;
   int round_count[MAXP] = {0};
+  // async host entry: ring of pinned staging slots
+  static constexpr int RING = 4;
+  double* ring_host[RING] = {nullptr, nullptr, nullptr, nullptr};
+  double* ring_dev[RING] = {nullptr, nullptr, nullptr, nullptr};
+  double* ring_out[RING] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
+  size_t ring_cap = 0;
+  int ring_pos = 0;
   // host-entry staging
   double *stage_dev = nullptr, *stage_host = nullptr, *out_dev = nullptr, *out_host_pinned = nullptr;
   size_t stage_cap = 0;
@@ -133,6 +141,12 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_round_group) cudaFree(h->d_round_group);
   if (h->var_rep) cudaFree(h->var_rep);
   if (h->d_fail) cudaFree(h->d_fail);
+  for (int i = 0; i < mogpe_handle::RING; i++) {
+    if (h->ring_host[i]) cudaFreeHost(h->ring_host[i]);
+    if (h->ring_dev[i]) cudaFree(h->ring_dev[i]);
+    if (h->ring_out[i]) cudaFree(h->ring_out[i]);
+    if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+  }
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
   for (auto e : h->ev) cudaEventDestroy(e);
@@ -748,6 +762,47 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd_host(mogpe_handle* h, const double* X
   return mogpe_check_numerics(h, cuda_stream);
 }
 
+extern "C" mogpe_status mogpe_elbo_fwd_bwd_host_async(mogpe_handle* h, const double* X_host, const double* Y_host,
+                                                      int32_t N, const double* params, int32_t bound, int32_t S,
+                                                      double scale, double* out_dev, double* out_host_pinned,
+                                                      double* grads, void* cuda_stream) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (!X_host || !Y_host || !out_host_pinned) H_FAIL(h, MOGPE_ERR_INVALID, "null host X / Y / out");
+  if (N < 1 || N > h->desc.max_batch) H_FAIL(h, MOGPE_ERR_INVALID, "N=%d outside [1, max_batch=%d]", N, h->desc.max_batch);
+  const ModelDev& md = h->md_host;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  H_CUDA(h, cudaSetDevice(h->device));
+  const size_t nx = (size_t)N * md.D, ny = (size_t)N * md.F, need = (size_t)h->desc.max_batch * (md.D + md.F);
+  if (need > h->ring_cap) {
+    H_CUDA(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < mogpe_handle::RING; i++) {
+      if (h->ring_host[i]) cudaFreeHost(h->ring_host[i]);
+      if (h->ring_dev[i]) cudaFree(h->ring_dev[i]);
+      h->ring_host[i] = nullptr;
+      h->ring_dev[i] = nullptr;
+      H_CUDA(h, cudaMallocHost((void**)&h->ring_host[i], need * sizeof(double)));
+      H_CUDA(h, dalloc(&h->ring_dev[i], need));
+      if (!h->ring_out[i]) H_CUDA(h, dalloc(&h->ring_out[i], 4));
+      if (!h->ring_ev[i]) H_CUDA(h, cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+    }
+    h->ring_cap = need;
+  }
+  const int slot = h->ring_pos;
+  h->ring_pos = (h->ring_pos + 1) % mogpe_handle::RING;
+  // the slot was last used RING calls ago: wait until that step has consumed it (no-op unless the host runs far ahead)
+  H_CUDA(h, cudaEventSynchronize(h->ring_ev[slot]));
+  memcpy(h->ring_host[slot], X_host, nx * sizeof(double));
+  memcpy(h->ring_host[slot] + nx, Y_host, ny * sizeof(double));
+  H_CUDA(h, cudaMemcpyAsync(h->ring_dev[slot], h->ring_host[slot], (nx + ny) * sizeof(double), cudaMemcpyHostToDevice, st));
+  mogpe_status rc = mogpe_elbo_fwd_bwd(h, h->ring_dev[slot], h->ring_dev[slot] + nx, N, params, nullptr, nullptr, nullptr,
+                                       bound, S, scale, out_dev ? out_dev : h->ring_out[slot], grads, cuda_stream);
+  if (rc != MOGPE_OK) return rc;
+  H_CUDA(h, cudaMemcpyAsync(out_host_pinned, out_dev ? out_dev : h->ring_out[slot], 4 * sizeof(double),
+                            cudaMemcpyDeviceToHost, st));
+  H_CUDA(h, cudaEventRecord(h->ring_ev[slot], st));
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const double* params,
                                       double* f_mean, double* f_var, double* mix_probs, double* y_mean, double* y_var,
                                       const double* eps_mc, int32_t num_mc, void* cuda_stream) {
@@ -1100,6 +1155,11 @@ extern "C" mogpe_status mogpe_memcpy_d2h(int32_t device, void* dst, const void* 
   G_CUDA(cudaSetDevice(device));
   G_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)st));
   G_CUDA(cudaStreamSynchronize((cudaStream_t)st));
+  return MOGPE_OK;
+}
+extern "C" mogpe_status mogpe_memcpy_d2h_async(int32_t device, void* dst, const void* src, int64_t bytes, void* st) {
+  G_CUDA(cudaSetDevice(device));
+  G_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)st));
   return MOGPE_OK;
 }
 extern "C" mogpe_status mogpe_memset_zero(int32_t device, void* dst, int64_t bytes, void* st) {

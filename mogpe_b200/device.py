@@ -57,6 +57,28 @@ class DeviceBuffer:
             pass
 
 
+class PinnedBuffer:
+    """Page-locked host float64 buffer (cudaMallocHost) viewed as a numpy array."""
+
+    def __init__(self, n):
+        p = C.c_void_p()
+        _lib.check(_lib.load().mogpe_malloc_host(int(n) * 8, C.byref(p)))
+        self.ptr, self.size = p.value, int(n)
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_double)), shape=(self.size,))
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            _lib.load().mogpe_free_host(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 # ---- DLPack capsule parsing (dlpack.h, DLManagedTensor) -----------------------------------------------
 class _DLDevice(C.Structure):
     _fields_ = [("device_type", C.c_int32), ("device_id", C.c_int32)]

@@ -267,6 +267,15 @@ class Engine:
                 res.experts, res.gating = self.unpack_grads(self.gbuf.numpy(count=self.lo.total))
         return res
 
+    def elbo_host_async(self, X, Y, bound, num_samples, scale, out_pinned_ptr: int, stream=None):
+        """Enqueue one fwd+bwd step on host X / Y without synchronising; the 4 result doubles land in the pinned
+        buffer at out_pinned_ptr once the stream reaches them."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        _lib.check(self.lib.mogpe_elbo_fwd_bwd_host_async(self.h, X.ctypes.data, Y.ctypes.data, X.shape[0], self.params.ptr,
+                                                          _lib.BOUND_IDS[bound], num_samples, float(scale), self.out_ptr,
+                                                          out_pinned_ptr, self.grads_ptr, stream), self.h)
+
     def predict(self, X, want=("f_mean", "f_var", "mix_probs", "y_mean", "y_var"), eps_mc=None, stream=None):
         """-> dict of numpy arrays (f_mean/f_var [N, P], mix_probs [N, K], y_mean/y_var [N, F])."""
         xv = as_view(X)
