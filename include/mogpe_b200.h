@@ -49,6 +49,11 @@ typedef enum {
 
 /* bound ids: mogpe/keras/mixture_of_experts/mosvgpe.py:83-107 ; mogpe/mixture_of_experts/svgp.py:102-124 */
 enum { MOGPE_BOUND_FURTHER_GATING = 0, MOGPE_BOUND_TIGHT = 1, MOGPE_BOUND_FURTHER = 2 };
+/* Precision of the dense M x M x B products.  F64: FP64 DMMA everywhere (gpflow's default_float, results within 1e-8 of
+ * the reference).  TF32: mogpe_predict runs A = L^-1 Kuf and q_sqrt^T A as 3xTF32 products on the tcgen05 tensor cores
+ * (FP32-class accuracy, tolerance class 1e-4); kernel matrices, Cholesky, L^-1 and the predictive means stay FP64.
+ * mogpe_elbo_fwd_bwd always runs in FP64. */
+enum { MOGPE_PRECISION_F64 = 0, MOGPE_PRECISION_TF32 = 1 };
 /* API flavour selects the documented numerical quirks */
 enum { MOGPE_FLAVOUR_KERAS = 0, MOGPE_FLAVOUR_LEGACY = 1 };
 
@@ -62,7 +67,7 @@ typedef struct mogpe_desc {
   int32_t max_batch;      /* largest N passed to the ELBO call; predict streams in chunks of this */
   int32_t flavour;        /* MOGPE_FLAVOUR_* */
   int32_t device;         /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t precision;      /* MOGPE_PRECISION_*: arithmetic of the M x M x B products of mogpe_predict */
   double jitter;          /* gpflow default_jitter() = 1e-6 */
   const int32_t* group_num_inducing; /* [Q] true M per group */
   const int32_t* latent_group;       /* [P] */

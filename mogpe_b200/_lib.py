@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmogpe_b200.so")
 MOGPE_OK = 0
 BOUND_IDS = {"further_gating": 0, "tight": 1, "further": 2}
 FLAVOUR_IDS = {"keras": 0, "legacy": 1}
+PRECISION_IDS = {"float64": 0, "tf32": 1}
 MAX_SAMPLES = 16
 MAX_LATENTS = 64
 MAX_GROUPS = 64
@@ -27,7 +28,7 @@ class Desc(C.Structure):
     _fields_ = [
         ("input_dim", C.c_int32), ("output_dim", C.c_int32), ("num_experts", C.c_int32),
         ("num_gating", C.c_int32), ("num_groups", C.c_int32), ("num_latents", C.c_int32),
-        ("max_batch", C.c_int32), ("flavour", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32),
+        ("max_batch", C.c_int32), ("flavour", C.c_int32), ("device", C.c_int32), ("precision", C.c_int32),
         ("jitter", C.c_double),
         ("group_num_inducing", C.POINTER(C.c_int32)), ("latent_group", C.POINTER(C.c_int32)),
     ]

@@ -82,8 +82,16 @@ class MixtureCore:
     def _blocks(self):
         return [svgp_to_block(g, True) for g in self.expert_gps], svgp_to_block(self.gating_gp, False)
 
+    def _stamp(self):
+        """Identity + modification counters of every Parameter the engine's packed buffer is built from."""
+        return tuple((id(p), p.version, p.trainable) for gp in self._gps() for _, p in gp.parameters())
+
     def ensure_engine(self, batch: int) -> Engine:
+        stamp = self._stamp()
+        if self.engine is not None and batch <= self.engine.max_batch and stamp == getattr(self, "_engine_stamp", None):
+            return self.engine  # device parameters are already in sync with the Parameter objects
         experts, gating = self._blocks()
+        self._engine_stamp = stamp
         if self.engine is None or batch > self.engine.max_batch:
             if self.engine is not None:
                 self.engine.close()
@@ -186,6 +194,7 @@ class MixtureCore:
         unconstrained variables.  -> Engine."""
         eng = self.ensure_engine(batch)
         if getattr(self, "_opt_engine", None) is not eng:  # the variable map depends only on the model structure
+            self._opt_stamp = None
             lowers = {float(g.likelihood.variance.transform.lower) for g in self.expert_gps}
             if len(lowers) != 1:
                 raise NotImplementedError("experts with different Gaussian variance lower bounds need the host optimiser")
@@ -208,8 +217,10 @@ class MixtureCore:
                 for pid, (arr, p) in ids.items() if p.trainable}
             eng.setup_optimizer(rep, lowers.pop())
             self._opt_engine = eng
-        u_blocks = self._packed_blocks(lambda p: p.unconstrained, lambda p: p.numpy())
-        eng.set_unconstrained(eng.pack(*u_blocks))
+        if getattr(self, "_opt_stamp", None) != self._stamp():
+            u_blocks = self._packed_blocks(lambda p: p.unconstrained, lambda p: p.numpy())
+            eng.set_unconstrained(eng.pack(*u_blocks))
+            self._opt_stamp = self._stamp()
         return eng
 
     def pull_variables(self):
@@ -217,14 +228,20 @@ class MixtureCore:
         u = self._opt_engine.u.numpy()
         for pos, p in self._var_positions.values():
             p.assign_unconstrained(u[pos])
+        # the device holds exactly these variables (and params = T(u)): nothing to upload until a Parameter changes
+        self._engine_stamp = self._opt_stamp = self._stamp()
 
     def fit_device(self, X, Y, bound, num_samples, num_data, optimizer, epochs, batch_size, shuffle, seed, tracker,
                    verbose=0, device_data=False):
         """Training loop with the whole step on the device: ELBO fwd+bwd -> bijector chain -> Adam -> params.
         Only the minibatch (H2D) and 4 result scalars (D2H) cross the bus per step."""
+        import os, time
+        timing = os.environ.get("MOGPE_FIT_TIMING")
+        t_start = time.perf_counter()
         X, Y = np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(Y, dtype=np.float64)
         n = X.shape[0]
         eng = self.setup_device_optimizer(min(batch_size, n))
+        t_setup = time.perf_counter()
         rng = np.random.default_rng(seed)
         history = {"loss": []}
         if device_data:
@@ -270,7 +287,11 @@ class MixtureCore:
             history["loss"].append(tracker.result())
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs} - loss: {tracker.result():.4f}")
+        t_loop = time.perf_counter()
         self.pull_variables()
+        if timing:
+            print(f"fit timing: setup {1e3 * (t_setup - t_start):.1f} ms, loop {1e3 * (t_loop - t_setup):.1f} ms, "
+                  f"pull {1e3 * (time.perf_counter() - t_loop):.1f} ms", flush=True)
         return history
 
     def latent_slices(self):

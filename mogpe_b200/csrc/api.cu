@@ -16,6 +16,7 @@
 #include "../../include/mogpe_b200.h"
 #include "gemm_f64.cuh"
 #include "kernels.cuh"
+#include "kernels_tf32.cuh"
 #include "lik.cuh"
 #include "model_dev.cuh"
 
@@ -50,6 +51,15 @@ struct mogpe_handle {
   int *d_round_latent = nullptr, *d_round_slot = nullptr, *d_round_group = nullptr;  // [MAXP rounds][MAXP]
   int n_rounds = 0;
   int round_count[MAXP] = {0};
+  // TF32 mode (tcgen05 products on split FP32 planes, gemm_tf32.cuh); buffers are created on first use
+  int precision = MOGPE_PRECISION_F64;
+  int Mp32 = 0;                                   // inducing dimension padded to the 128-row UMMA tile
+  float *Linv32 = nullptr, *ST32 = nullptr;       // [Q | P][2][Mp32][Mp32]: L^-1 and tril(q_sqrt)^T, K-major hi / lo planes
+  float *KufT32 = nullptr, *AT32 = nullptr;       // [Q][2][Bp][Mp32]: Kuf^T and A^T planes (point index n = row)
+  double* alpha = nullptr;                        // [P][Mp32]: L^-T q_mu (FP64 means)
+  CUtensorMap tm_linv, tm_st, tm_kuf, tm_at;
+  bool t32_ready = false;
+  int* d_t32_err = nullptr;
   // async host entry: ring of pinned staging slots
   static constexpr int RING = 4;
   double* ring_host[RING] = {nullptr, nullptr, nullptr, nullptr};
@@ -141,6 +151,12 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_round_group) cudaFree(h->d_round_group);
   if (h->var_rep) cudaFree(h->var_rep);
   if (h->d_fail) cudaFree(h->d_fail);
+  if (h->Linv32) cudaFree(h->Linv32);
+  if (h->ST32) cudaFree(h->ST32);
+  if (h->KufT32) cudaFree(h->KufT32);
+  if (h->AT32) cudaFree(h->AT32);
+  if (h->alpha) cudaFree(h->alpha);
+  if (h->d_t32_err) cudaFree(h->d_t32_err);
   for (int i = 0; i < mogpe_handle::RING; i++) {
     if (h->ring_host[i]) cudaFreeHost(h->ring_host[i]);
     if (h->ring_dev[i]) cudaFree(h->ring_dev[i]);
@@ -174,6 +190,7 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (d->num_latents != d->num_experts * d->output_dim + d->num_gating) return bad("num_latents != K*F + G");
   if (d->num_latents > MAXP || d->num_groups > MAXQ || d->num_groups < 1) return bad("too many latents / groups");
   if (d->max_batch < 1) return bad("max_batch must be >= 1");
+  if (d->precision != MOGPE_PRECISION_F64 && d->precision != MOGPE_PRECISION_TF32) return bad("unknown precision");
   if (!d->group_num_inducing || !d->latent_group) return bad("null group_num_inducing / latent_group");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count <= d->device) {
@@ -200,8 +217,10 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
       delete h;
       return bad("latent_group out of range");
     }
+  h->precision = d->precision;
   h->Mp = round_up(Mmax, 64);
-  h->Bp = round_up(d->max_batch, 128);
+  h->Mp32 = round_up(h->Mp, t32::BM);
+  h->Bp = round_up(d->max_batch, h->precision == MOGPE_PRECISION_TF32 ? t32::BN : 128);
   h->Pe = d->num_experts * d->output_dim;
   const long long Q = d->num_groups, P = d->num_latents, Mp = h->Mp, D = d->input_dim;
   Layout& lo = h->lo;
@@ -447,13 +466,13 @@ static void launch_kuf(mogpe_handle* h, const double* params, const double* X, i
 // not depend on the factorisation: the clean q_sqrt copies, the mean vectors V (u-samples) and Kuf of the first
 // chunk.  The Cholesky chain is a sequence of short latency-bound launches that leave most SMs idle.
 static mogpe_status factorise(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X, int N,
-                              int Bc, cudaStream_t st) {
+                              int Bc, cudaStream_t st, bool fp64_products = true) {
   const ModelDev& md = h->md_host;
   const int Q = md.Q, P = md.P, Mp = h->Mp;
   H_CUDA(h, side_fork(h, st));
   prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, h->side>>>(h->d_md, params, h->lo, h->Sc);
   make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, h->side>>>(h->d_md, params, h->lo, h->Sc, eps_u, S, h->V);
-  launch_kuf(h, params, X, N, Bc, h->side);
+  if (fp64_products) launch_kuf(h, params, X, N, Bc, h->side);
   kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
   // Launch j of the chain completes block row j of L^-1.  A = L^-1 Kuf only needs rows [64 i, 64 i + 64) of L^-1 for
   // its row block i, so the A-GEMM is issued in 64-row slices on the side stream, each waiting for the chain launch
@@ -464,7 +483,7 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, const doubl
     H_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->ev_rows.push_back(e);
   }
-  const bool pipeline = !h->prof;  // per-GEMM event timing needs the GEMMs alone on the device
+  const bool pipeline = !h->prof && fp64_products;  // per-GEMM event timing needs the GEMMs alone on the device
   for (int j = -1; j < Mp / 32; j++) {
     chol_inv_step_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, j, h->d_fail);
     if (pipeline && j >= 0 && (j & 1)) {
@@ -803,6 +822,89 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd_host_async(mogpe_handle* h, const dou
   return MOGPE_OK;
 }
 
+// ---- TF32 mode (tcgen05 3xTF32 products; gemm_tf32.cuh, kernels_tf32.cuh) -----------------------------------------------
+static mogpe_status ensure_t32(mogpe_handle* h) {
+  if (h->t32_ready) return MOGPE_OK;
+  const ModelDev& md = h->md_host;
+  const size_t Q = md.Q, P = md.P, M32 = h->Mp32, Bp = h->Bp;
+  H_CUDA(h, dalloc(&h->Linv32, Q * 2 * M32 * M32));
+  H_CUDA(h, dalloc(&h->ST32, P * 2 * M32 * M32));
+  H_CUDA(h, dalloc(&h->KufT32, Q * 2 * Bp * M32));
+  H_CUDA(h, dalloc(&h->AT32, Q * 2 * Bp * M32));
+  H_CUDA(h, dalloc(&h->alpha, P * M32));
+  H_CUDA(h, dalloc(&h->d_t32_err, 1));
+  H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
+  if (!t32::make_map_kmajor(&h->tm_linv, h->Linv32, (int)Q, (int)M32, (int)M32, t32::BM) ||
+      !t32::make_map_kmajor(&h->tm_st, h->ST32, (int)P, (int)M32, (int)M32, t32::BM) ||
+      !t32::make_map_kmajor(&h->tm_kuf, h->KufT32, (int)Q, (int)Bp, (int)M32, t32::BN) ||
+      !t32::make_map_kmajor(&h->tm_at, h->AT32, (int)Q, (int)Bp, (int)M32, t32::BN))
+    H_FAIL(h, MOGPE_ERR_CUDA, "cuTensorMapEncodeTiled failed (TF32 mode needs a driver with TMA tensor maps)");
+  h->t32_ready = true;
+  return MOGPE_OK;
+}
+
+// After factorise(): split L^-1 and tril(q_sqrt)^T of the marginal latents into hi / lo planes, alpha = L^-T q_mu.
+static mogpe_status t32_prepare(mogpe_handle* h, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, Mp = h->Mp, M32 = h->Mp32;
+  t32::split_planes_kernel<<<dim3((M32 + 255) / 256, M32, Q), 256, 0, st>>>(h->Linv, Mp, Mp, (long long)Mp * Mp, Mp, h->Linv32,
+                                                                            M32, M32, 1);
+  if (md.nlta > 0)
+    t32::split_planes_T_kernel<<<dim3(M32 / 32, M32 / 32, md.nlta), dim3(32, 8), 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp,
+                                                                                         h->d_lta_latent, h->ST32, M32);
+  t32::alpha_kernel<<<dim3(M32 / 128, md.NV), 128, 0, st>>>(h->d_md, h->Linv, h->V, M32, h->alpha);
+  KCOUNT(h, 3);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+// One chunk of test points: Kuf^T planes + FP64 mean partials, then the two variance products on the tensor cores.
+static mogpe_status conditional_fwd_t32(mogpe_handle* h, const double* params, const double* X, int N, int Bc,
+                                        cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, M32 = h->Mp32, m_tiles = M32 / t32::BM;
+  const dim3 kg(Bc / 64, M32 / 128, Q);
+  if (md.D <= 2)
+    t32::kuf32_kernel<2><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->KufT32, h->alpha, h->dot_part, m_tiles);
+  else if (md.D <= 4)
+    t32::kuf32_kernel<4><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->KufT32, h->alpha, h->dot_part, m_tiles);
+  else if (md.D <= 8)
+    t32::kuf32_kernel<8><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->KufT32, h->alpha, h->dot_part, m_tiles);
+  else
+    t32::kuf32_kernel<16><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->KufT32, h->alpha, h->dot_part, m_tiles);
+  KCOUNT(h, 1);
+  H_CUDA(h, cudaGetLastError());
+  t32::Params p;
+  memset(&p, 0, sizeof(p));
+  p.m_tiles = m_tiles; p.K = M32; p.kmode = t32::K_LOWER;
+  p.ss_part = h->ss_part; p.ld_ss = h->Bp; p.err_flag = h->d_t32_err;
+  if (md.nlta > 0) {
+    p.out = h->AT32; p.out_batch_stride = (long long)2 * h->Bp * M32; p.out_plane_stride = (long long)h->Bp * M32; p.ldo = M32;
+  }
+  for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = g;
+  H_CUDA(h, t32::launch(h->tm_linv, h->tm_kuf, p, Bc / t32::BN, Q, st));  // A^T planes + sum_m A^2 partials
+  h->gemm_launches++;
+  KCOUNT(h, 1);
+  if (md.nlta > 0) {
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = m_tiles; p.K = M32; p.kmode = t32::K_UPPER;
+    p.ss_part = h->lta_part; p.ld_ss = h->Bp; p.err_flag = h->d_t32_err;
+    for (int slot = 0; slot < md.nlta; slot++) {
+      p.mapA[slot] = slot;                 // ST32 is stored per LTA slot
+      p.mapB[slot] = md.lta_group[slot];
+    }
+    H_CUDA(h, t32::launch(h->tm_st, h->tm_at, p, Bc / t32::BN, md.nlta, st));  // sum_m (q_sqrt^T A)^2 partials
+    h->gemm_launches++;
+    KCOUNT(h, 1);
+  }
+  KCOUNT(h, 1);  // stats_finish
+  stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + md.nlta), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, h->dot_part,
+                                                                           h->lta_part, m_tiles, h->Bp, h->var0ss, h->mean,
+                                                                           h->varq);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const double* params,
                                       double* f_mean, double* f_var, double* mix_probs, double* y_mean, double* y_var,
                                       const double* eps_mc, int32_t num_mc, void* cuda_stream) {
@@ -818,15 +920,22 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
   mogpe_status rc = set_mode(h, -1, 1, st);
   if (rc != MOGPE_OK) return rc;
   const int chunk_max = h->desc.max_batch;
+  const bool tf32 = h->precision == MOGPE_PRECISION_TF32;
   {
     const int nc0 = (int)std::min<int64_t>(chunk_max, N);
-    rc = factorise(h, params, nullptr, 1, X, nc0, round_up(nc0, 128), st);  // Kuf of the first chunk overlaps the chain
+    if (tf32) {
+      rc = ensure_t32(h);
+      if (rc != MOGPE_OK) return rc;
+    }
+    rc = factorise(h, params, nullptr, 1, X, nc0, round_up(nc0, 128), st, !tf32);  // Kuf of the first chunk overlaps the chain
+    if (rc == MOGPE_OK && tf32) rc = t32_prepare(h, st);
     if (rc != MOGPE_OK) return rc;
   }
   for (int64_t n0 = 0; n0 < N; n0 += chunk_max) {
     const int nc = (int)std::min<int64_t>(chunk_max, N - n0);
-    const int Bc = round_up(nc, 128);
-    rc = conditional_fwd(h, params, X + n0 * md.D, nc, Bc, st, n0 == 0);
+    const int Bc = round_up(nc, tf32 ? t32::BN : 128);
+    rc = tf32 ? conditional_fwd_t32(h, params, X + n0 * md.D, nc, Bc, st)
+              : conditional_fwd(h, params, X + n0 * md.D, nc, Bc, st, n0 == 0);
     if (rc != MOGPE_OK) return rc;
     PredArgs pa;
     pa.md = h->d_md; pa.params = params; pa.lo = h->lo; pa.mean = h->mean; pa.var0ss = h->var0ss; pa.varq = h->varq;

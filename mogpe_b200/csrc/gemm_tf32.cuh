@@ -371,12 +371,13 @@ inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
 
 // ---- FP64 -> hi / lo FP32 planes ---------------------------------------------------------------------------------
 // dst [batch][2][rows_p][cols_p] <- src [batch][rows][cols] (zero padded).  grid (ceil(cols_p/256), rows_p, batch)
+// lower_only: entries above the diagonal are written as zero whatever the source holds there.
 __global__ void split_planes_kernel(const double* __restrict__ src, int rows, int cols, long long src_batch_stride,
-                                    int src_ld, float* __restrict__ dst, int rows_p, int cols_p) {
+                                    int src_ld, float* __restrict__ dst, int rows_p, int cols_p, int lower_only) {
   const int c = blockIdx.x * 256 + threadIdx.x, r = blockIdx.y, b = blockIdx.z;
   if (c >= cols_p) return;
   double x = 0.0;
-  if (r < rows && c < cols) x = src[(long long)b * src_batch_stride + (long long)r * src_ld + c];
+  if (r < rows && c < cols && !(lower_only && c > r)) x = src[(long long)b * src_batch_stride + (long long)r * src_ld + c];
   const float hi = tf32_hi((float)x);
   const float lo = (float)(x - (double)hi);
   float* d = dst + ((long long)b * 2 * rows_p + r) * cols_p + c;

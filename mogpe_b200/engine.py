@@ -60,8 +60,13 @@ class ElboResult:
 
 class Engine:
     def __init__(self, experts: List[GPBlock], gating: GPBlock, flavour="keras", max_batch=1024, device=0,
-                 jitter=DEFAULT_JITTER):
+                 jitter=DEFAULT_JITTER, precision="float64"):
+        """precision: "float64" (gpflow default_float; FP64 DMMA) or "tf32" (predict runs its M x M x N products as 3xTF32
+        on the tcgen05 tensor cores, tolerance class 1e-4; the ELBO always runs in FP64)."""
         self.lib = _lib.load()
+        if precision not in _lib.PRECISION_IDS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISION_IDS)}")
+        self.precision = precision
         self.flavour = flavour
         self.device = device
         self.K = len(experts)
@@ -91,7 +96,7 @@ class Engine:
         self._lg = (C.c_int32 * self.P)(*latent_group)
         self.max_batch = int(max_batch)
         desc = _lib.Desc(self.D, self.F, self.K, self.G, self.Q, self.P, self.max_batch,
-                         _lib.FLAVOUR_IDS[flavour], device, 0, jitter, self._gm, self._lg)
+                         _lib.FLAVOUR_IDS[flavour], device, _lib.PRECISION_IDS[precision], jitter, self._gm, self._lg)
         h = C.c_void_p()
         _lib.check(self.lib.mogpe_create(C.byref(desc), C.byref(h)))
         self.h = h

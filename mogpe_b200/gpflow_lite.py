@@ -92,11 +92,25 @@ class Parameter:
     """gpflow.Parameter: stores the UNCONSTRAINED value (what the optimiser updates, as the reference's
     trainable_variables are) and exposes the constrained one."""
 
+    _clock = [0]  # global modification counter: lets the engine skip re-uploading parameters that did not change
+
     def __init__(self, value, transform=None, trainable=True, name=None):
         self.transform = transform or Identity()
         self.unconstrained = np.array(self.transform.inverse(np.asarray(value, dtype=DEFAULT_FLOAT)), dtype=DEFAULT_FLOAT)
         self.trainable = trainable
         self.name = name
+
+    @property
+    def unconstrained(self):
+        return self._u
+
+    @unconstrained.setter
+    def unconstrained(self, u):
+        u = np.array(u, dtype=DEFAULT_FLOAT)
+        u.flags.writeable = False  # every change goes through this setter (and bumps `version`)
+        self._u = u
+        Parameter._clock[0] += 1
+        self.version = Parameter._clock[0]
 
     def numpy(self):
         return self.transform.forward(self.unconstrained)

@@ -17,10 +17,10 @@ def block_from_gp(gp, is_expert):
     )
 
 
-def engine_from_spec(spec, max_batch):
+def engine_from_spec(spec, max_batch, precision="float64"):
     experts = [block_from_gp(g, True) for g in spec["experts"]]
     gating = block_from_gp(spec["gating"], False)
-    return Engine(experts, gating, flavour=spec["flavour"], max_batch=max_batch)
+    return Engine(experts, gating, flavour=spec["flavour"], max_batch=max_batch, precision=precision)
 
 
 def run_engine_elbo(eng, spec, X, Y, eps, want_grads=True, device_inputs=False):

@@ -11,13 +11,13 @@ def logu(rng, lo, hi, size=None):
     return np.exp(rng.uniform(np.log(lo), np.log(hi), size))
 
 
-def make_gp(rng, X, M, L, n_kernels, ard, mean_c, is_expert, noise_lo=1e-2, jitter_z=0.0):
+def make_gp(rng, X, M, L, n_kernels, ard, mean_c, is_expert, noise_lo=1e-2, jitter_z=0.0, ls_range=(0.3, 3.0)):
     N, D = X.shape
     idx = rng.choice(N, size=M, replace=N < M)
     Z = X[idx].copy() + jitter_z * rng.standard_normal((M, D))
     kernels = []
     for _ in range(n_kernels):
-        ls = logu(rng, 0.3, 3.0, D) if ard else float(logu(rng, 0.3, 3.0))
+        ls = logu(rng, ls_range[0], ls_range[1], D) if ard else float(logu(rng, ls_range[0], ls_range[1]))
         kernels.append({"lengthscales": ls, "variance": float(logu(rng, 0.3, 3.0))})
     gp = {
         "Z": Z,
@@ -40,7 +40,7 @@ def make_data(rng, N, D, F, K):
 
 def make_spec(seed=0, N=24, D=2, F=1, K=2, M=8, S=1, flavour="keras", bound="further_gating",
               num_data=None, separate_kernels=False, ard=True, mean_c=0.3, gating_mean_c=None,
-              M_gating=None, M_experts=None, noise_lo=None):
+              M_gating=None, M_experts=None, noise_lo=None, ls_range=(0.3, 3.0)):
     """-> spec, X, Y, eps (dict of explicit standard-normal draws)."""
     rng = np.random.default_rng(seed)
     X, Y = make_data(rng, N, D, F, K)
@@ -52,10 +52,11 @@ def make_spec(seed=0, N=24, D=2, F=1, K=2, M=8, S=1, flavour="keras", bound="fur
         # (the keras flavour also uses y_var itself as the scale of the expert density, quirk 1)
         noise_lo = 0.5 if bound == "further" else (0.3 if flavour == "keras" else 1e-2)
     experts = [
-        make_gp(rng, X, Ms[k], F, F if separate_kernels else 1, ard, mean_c, True, noise_lo=noise_lo)
+        make_gp(rng, X, Ms[k], F, F if separate_kernels else 1, ard, mean_c, True, noise_lo=noise_lo, ls_range=ls_range)
         for k in range(K)
     ]
-    gating = make_gp(rng, X, M_gating or M, G, G if (separate_kernels and G > 1) else 1, ard, gating_mean_c, False)
+    gating = make_gp(rng, X, M_gating or M, G, G if (separate_kernels and G > 1) else 1, ard, gating_mean_c, False,
+                     ls_range=ls_range)
     spec = {"flavour": flavour, "bound": bound, "num_samples": S, "num_data": num_data,
             "experts": experts, "gating": gating}
     eps = {

@@ -66,8 +66,8 @@ int main(int argc, char** argv) {
   CK(cudaMemset(O32, 0xff, (size_t)batch * 2 * rows * N * 4));
   const int a_rows = a_mn ? K : rows, a_cols = a_mn ? rows : K;
   t32::split_planes_kernel<<<dim3((a_cols + 255) / 256, a_rows, batch), 256>>>(dA, a_rows, a_cols, (long long)a_rows * a_cols,
-                                                                               a_cols, A32, a_rows, a_cols);
-  t32::split_planes_kernel<<<dim3((K + 255) / 256, N, batch), 256>>>(dB, N, K, (long long)K * N, K, B32, N, K);
+                                                                               a_cols, A32, a_rows, a_cols, 0);
+  t32::split_planes_kernel<<<dim3((K + 255) / 256, N, batch), 256>>>(dB, N, K, (long long)K * N, K, B32, N, K, 0);
   CK(cudaGetLastError());
   CUtensorMap mapA, mapB;
   bool ok = t32::make_map_kmajor(&mapA, A32, batch, rows, K, t32::BM);
