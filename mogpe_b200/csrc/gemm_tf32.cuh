@@ -14,8 +14,9 @@
 // Operand layout: BOTH operands K-major (tools/umma_probe.cu: on sm_100a kind::tf32 with an MN-major operand silently
 // produces zeros, profiles/umma_probe_r01.log), i.e. D[m][n] = sum_k Aop[m][k] * Bop[n][k] with k contiguous in memory
 // for both.  So Kuf and A are kept TRANSPOSED ([point n][inducing index k]) in this mode and q_sqrt^T is materialised.
-// Tile: D[128 x 256] per CTA (UMMA M = 128, N = 256, K = 8 per instruction), BK = 16 per pipeline stage, 4 stages:
-//   smem per stage: A [plane][128 rows][16 fp32], B [plane][256 rows][16 fp32], rows of 64 B, 64B-swizzled by TMA.
+// Tile: two D[128 x 256] row tiles per CTA (UMMA M = 128, N = 256, K = 8 per instruction) sharing one B stage, BK = 16 per
+// pipeline stage, 3 stages of 64 KB:  A0, A1 [plane][128 rows][16 fp32], B [plane][256 rows][16 fp32], rows of 64 B,
+// 64B-swizzled by TMA.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
 // (each reads its own 32-lane TMEM quarter).  Triangular operands shorten the k loop per row tile.
 // Epilogue: column sums of squares of the tile (butterfly transpose-reduce over the 32 lanes, then over the 4 warps)
@@ -29,16 +30,16 @@
 namespace mogpe {
 namespace t32 {
 
-constexpr int BM = 128, BN = 256, BK = 16, STAGES = 4, UK = 8;
+constexpr int BM = 128, BN = 256, BK = 16, STAGES = 3, UK = 8;
 constexpr int A_PLANE_BYTES = BM * BK * 4;          // 8 KB
 constexpr int B_PLANE_BYTES = BN * BK * 4;          // 16 KB
 constexpr int A_STAGE_BYTES = 2 * A_PLANE_BYTES;    // hi + lo
 constexpr int B_STAGE_BYTES = 2 * B_PLANE_BYTES;
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KB
-constexpr int RED_BYTES = 4 * BN * 4;                        // cross-warp column-sum scratch
+constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + B_STAGE_BYTES;  // two row tiles + one column tile: 64 KB
+constexpr int RED_BYTES = 2 * 4 * BN * 4;                    // cross-warp column-sum scratch, one per row tile
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RED_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;  // two 128 x 256 FP32 accumulators
 
 enum : int { K_FULL = 0, K_LOWER = 1, K_UPPER = 2 };
 
@@ -53,8 +54,6 @@ struct Params {
   double* ss_part;  // optional [batch][m_tiles][ld_ss]: column sums of squares of each row tile
   int ld_ss;
   int* err_flag;    // set to 1 if a barrier wait times out (the kernel traps instead of hanging)
-  int dbg_mode;     // debug: 1 = epilogue warps pre-fill the accumulator with row*1000+col and every MMA accumulates
-  uint32_t* dbg;    // debug: CTA (0,0,0) dumps its pipeline stages (STAGES * STAGE_BYTES) after the main loop
   int mapA[64], mapB[64];  // batch -> outermost tensor-map coordinate of the A / B operand
 };
 
@@ -146,36 +145,51 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // hi = x with the 13 low mantissa bits cleared (a TF32 number whether the tensor core truncates or rounds)
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-// grid (n_tiles, batch, m_tiles): the row tile comes from blockIdx.z so that, for triangular operands, the tiles with
-// the longest k loops are scheduled first.
+// One CTA = TWO adjacent row tiles (2p, 2p+1) x one 256-column tile: both accumulators (2 x 256 TMEM columns = all 512)
+// are fed from the same B stage, so the L2 -> shared-memory traffic per MMA is 2/3 of the one-tile version (the kernel
+// is bound by that traffic).  With a triangular operand the two tiles have k ranges that differ by 128: the loop runs
+// in the direction in which the SHORTER tile finishes first (ascending k for K_LOWER, descending for K_UPPER); its
+// accumulator is committed early and its epilogue overlaps the last 8 stages of the other tile.
+// grid (n_tiles, batch, m_pairs): the pair comes from blockIdx.z so that the longest k loops are scheduled first.
 __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                   const __grid_constant__ CUtensorMap mapB,
                                                                   const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 1024-byte aligned tile area (swizzle atoms)
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  float* red = reinterpret_cast<float*>(gbase + STAGES * STAGE_BYTES);  // [4][BN]
+  float* red = reinterpret_cast<float*>(gbase + STAGES * STAGE_BYTES);  // [2 tiles][4 warps][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + STAGES * STAGE_BYTES + RED_BYTES);
   uint64_t* full = bars;              // [STAGES] TMA -> MMA
   uint64_t* empty = bars + STAGES;    // [STAGES] MMA -> TMA
-  uint64_t* acc_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* acc_full = bars + 2 * STAGES;  // [2] accumulator of tile 0 / 1 complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, batch = blockIdx.y;
-  const int m_tile = (p.kmode == K_UPPER) ? (int)blockIdx.z : p.m_tiles - 1 - (int)blockIdx.z;
-  const int m0 = m_tile * BM, n0 = n_tile * BN;
-  int k_begin = 0, k_end = p.K;
-  if (p.kmode == K_LOWER) k_end = min(p.K, m0 + BM);
-  if (p.kmode == K_UPPER) k_begin = m0;
-  const int num_kb = (k_end - k_begin) / BK;
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int pair = (p.kmode == K_UPPER) ? (int)blockIdx.z : m_pairs - 1 - (int)blockIdx.z;
+  const int n0 = n_tile * BN;
+  const bool has1 = 2 * pair + 1 < p.m_tiles;
+  // k range [kb_t, ke_t) of each tile, and of the pair
+  int kb_t[2], ke_t[2];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    const int m0 = (2 * pair + t) * BM;
+    kb_t[t] = (p.kmode == K_UPPER) ? m0 : 0;
+    ke_t[t] = (p.kmode == K_LOWER) ? min(p.K, m0 + BM) : p.K;
+  }
+  if (!has1) { kb_t[1] = 0; ke_t[1] = 0; }
+  const int k_lo = has1 ? min(kb_t[0], kb_t[1]) : kb_t[0], k_hi = has1 ? max(ke_t[0], ke_t[1]) : ke_t[0];
+  const int num_kb = (k_hi - k_lo) / BK;
+  const bool descending = p.kmode == K_UPPER;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
@@ -198,128 +212,117 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
+        const int k0 = descending ? k_hi - (kb + 1) * BK : k_lo + kb * BK;
+        const bool use0 = k0 >= kb_t[0] && k0 < ke_t[0], use1 = k0 >= kb_t[1] && k0 < ke_t[1];
         mbar_wait(&empty[s], ph ^ 1, p.err_flag);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        const int k0 = k_begin + kb * BK;
-        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-        tma_load_4d(sa, &mapA, smem_u32(&full[s]), k0, m0, 0, ca);  // {k, m, plane, batch}
-        tma_load_4d(sb, &mapB, smem_u32(&full[s]), k0, n0, 0, cb);  // {k, n, plane, batch}
+        mbar_expect_tx(&full[s], B_STAGE_BYTES + (use0 ? A_STAGE_BYTES : 0) + (use1 ? A_STAGE_BYTES : 0));
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_STAGE_BYTES;
+        if (use0) tma_load_4d(sa, &mapA, smem_u32(&full[s]), k0, 2 * pair * BM, 0, ca);                        // {k, m, plane, batch}
+        if (use1) tma_load_4d(sa + A_STAGE_BYTES, &mapA, smem_u32(&full[s]), k0, (2 * pair + 1) * BM, 0, ca);
+        tma_load_4d(sb, &mapB, smem_u32(&full[s]), k0, n0, 0, cb);                                            // {k, n, plane, batch}
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    if (p.dbg_mode == 1 || p.dbg_mode == 3) {
-      asm volatile("bar.sync 2, 160;" ::: "memory");
-      tc_fence_after();
-    }
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
-      uint32_t acc = (p.dbg_mode == 1 || p.dbg_mode == 3) ? 1 : 0;
+      uint32_t acc[2] = {0, 0};
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
+        const int k0 = descending ? k_hi - (kb + 1) * BK : k_lo + kb * BK;
         mbar_wait(&full[s], ph, p.err_flag);
         tc_fence_after();
-        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_STAGE_BYTES;
 #pragma unroll
-        for (int j = 0; j < BK / UK; j++) {
-          uint64_t ad[2], bd[2];
+        for (int t = 0; t < 2; t++) {
+          if (!(k0 >= kb_t[t] && k0 < ke_t[t])) continue;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * BN);
 #pragma unroll
-          for (int pl = 0; pl < 2; pl++) {
-            // K-major, 64B swizzle: 8-row groups 512 B apart (SBO); the k-step advances the start address by 32 B
-            ad[pl] = make_smem_desc(sa + pl * A_PLANE_BYTES + j * UK * 4, 16, 8 * BK * 4, 4);
-            bd[pl] = make_smem_desc(sb + pl * B_PLANE_BYTES + j * UK * 4, 16, 8 * BK * 4, 4);
+          for (int j = 0; j < BK / UK; j++) {
+            uint64_t ad[2], bd[2];
+#pragma unroll
+            for (int pl = 0; pl < 2; pl++) {
+              // K-major, 64B swizzle: 8-row groups 512 B apart (SBO); the k-step advances the start address by 32 B
+              ad[pl] = make_smem_desc(sa + t * A_STAGE_BYTES + pl * A_PLANE_BYTES + j * UK * 4, 16, 8 * BK * 4, 4);
+              bd[pl] = make_smem_desc(sb + pl * B_PLANE_BYTES + j * UK * 4, 16, 8 * BK * 4, 4);
+            }
+            umma_tf32(d_tmem, ad[1], bd[0], idesc, acc[t]);  // lo * hi
+            acc[t] = 1;
+            umma_tf32(d_tmem, ad[0], bd[1], idesc, 1);       // hi * lo
+            umma_tf32(d_tmem, ad[0], bd[0], idesc, 1);       // hi * hi
           }
-          umma_tf32(tmem_base, ad[1], bd[0], idesc, acc);  // lo * hi
-          acc = 1;
-          umma_tf32(tmem_base, ad[0], bd[1], idesc, acc);  // hi * lo
-          umma_tf32(tmem_base, ad[0], bd[0], idesc, acc);  // hi * hi
         }
         umma_commit(&empty[s]);  // smem slot is free once these MMAs have read it
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const bool last = descending ? (k0 == kb_t[t]) : (k0 + BK == ke_t[t]);
+          if (last && ke_t[t] > kb_t[t]) umma_commit(&acc_full[t]);  // this tile's accumulator is complete
+        }
       }
-      umma_commit(acc_full);     // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
-    if (p.dbg_mode == 1 || p.dbg_mode == 3) {
-      for (int c = 0; c < BN / 32; c++) {
-        uint32_t r[32];
-        for (int i = 0; i < 32; i++) r[i] = __float_as_uint((float)((q * 32 + lane) * 1000 + c * 32 + i));
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-            ::"r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32)), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
-            "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
-            "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
-            "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-            "r"(r[31])
-            : "memory");
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      asm volatile("bar.sync 2, 160;" ::: "memory");
-    }
-    mbar_wait(acc_full, 0, p.err_flag);
-    if (p.dbg_mode >= 2) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < 4000000) {}
-    }
-    tc_fence_after();
-    float* ocol_hi = nullptr;  // element (n0, this thread's row m) of the transposed result
-    float* ocol_lo = nullptr;
-    if (p.out) {
-      ocol_hi = p.out + (long long)batch * p.out_batch_stride + (long long)n0 * p.ldo + (m0 + q * 32 + lane);
-      ocol_lo = ocol_hi + p.out_plane_stride;
-    }
+    const int t_first = descending ? 1 : 0;  // the tile with the shorter k range finishes first
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+    for (int it = 0; it < 2; it++) {
+      const int t = it == 0 ? t_first : 1 - t_first;
+      if (t == 1 && !has1) continue;
+      const int m_tile = 2 * pair + t, m0 = m_tile * BM;
+      mbar_wait(&acc_full[t], 0, p.err_flag);
+      tc_fence_after();
+      float* redt = red + t * 4 * BN;
+      float* ocol_hi = nullptr;  // element (n0, this thread's row m) of the transposed result
+      float* ocol_lo = nullptr;
       if (p.out) {
+        ocol_hi = p.out + (long long)batch * p.out_batch_stride + (long long)n0 * p.ldo + (m0 + q * 32 + lane);
+        ocol_lo = ocol_hi + p.out_plane_stride;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c * 32), v);
+        if (p.out) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) {  // one coalesced 128-byte store per warp and column
-          const float hi = tf32_hi(v[i]);
-          const long long o = (long long)(c * 32 + i) * p.ldo;
-          ocol_hi[o] = hi;
-          ocol_lo[o] = v[i] - hi;
+          for (int i = 0; i < 32; i++) {  // one coalesced 128-byte store per warp and column
+            const float hi = tf32_hi(v[i]);
+            const long long o = (long long)(c * 32 + i) * p.ldo;
+            ocol_hi[o] = hi;
+            ocol_lo[o] = v[i] - hi;
+          }
+        }
+        if (p.ss_part) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] *= v[i];
+          // butterfly transpose-reduce: after the last step lane c holds the sum over the warp's 32 rows of column c
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; i++) {
+              const float send = up ? v[i] : v[i + o];
+              const float keep = up ? v[i + o] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          redt[q * BN + c * 32 + lane] = v[0];
         }
       }
       if (p.ss_part) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        const int tt = threadIdx.x - 64;
+        double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] *= v[i];
-        // butterfly transpose-reduce: after the last step lane c holds the sum over the warp's 32 rows of column c
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          const bool up = (lane & o) != 0;
-#pragma unroll
-          for (int i = 0; i < o; i++) {
-            const float send = up ? v[i] : v[i + o];
-            const float keep = up ? v[i + o] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-          }
+        for (int u = 0; u < BN / 128; u++) {
+          const int col = tt + u * 128;
+          dst[col] = ((double)redt[col] + (double)redt[BN + col]) + ((double)redt[2 * BN + col] + (double)redt[3 * BN + col]);
         }
-        red[q * BN + c * 32 + lane] = v[0];
       }
     }
     tc_fence_before();
-    if (p.ss_part) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      const int t = threadIdx.x - 64;
-      double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
-#pragma unroll
-      for (int u = 0; u < BN / 128; u++) {
-        const int col = t + u * 128;
-        dst[col] = ((double)red[col] + (double)red[BN + col]) + ((double)red[2 * BN + col] + (double)red[3 * BN + col]);
-      }
-    }
   }
   __syncthreads();
-  if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(gbase);
-    for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 4; i += THREADS) p.dbg[i] = src[i];
-  }
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
@@ -365,7 +368,7 @@ inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tf32x3_kernel<<<dim3(n_tiles, batch, p.m_tiles), THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
+  gemm_tf32x3_kernel<<<dim3(n_tiles, batch, (p.m_tiles + 1) / 2), THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
   return cudaGetLastError();
 }
 

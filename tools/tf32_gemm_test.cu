@@ -84,14 +84,8 @@ int main(int argc, char** argv) {
   p.out = O32; p.out_batch_stride = (long long)2 * rows * N; p.out_plane_stride = (long long)rows * N; p.ldo = rows;  // [n][m]
   p.ss_part = ss; p.ld_ss = N; p.err_flag = err;
   for (int b = 0; b < batch; b++) { p.mapA[b] = batch - 1 - b; p.mapB[b] = b; }  // output b = A[batch-1-b] * B[b]
-  uint32_t* dbg;
-  CK(cudaMalloc(&dbg, t32::STAGES * t32::STAGE_BYTES));
-  CK(cudaMemset(dbg, 0xee, t32::STAGES * t32::STAGE_BYTES));
-  p.dbg = dbg;
-  p.dbg_mode = getenv("T32_DBG") ? atoi(getenv("T32_DBG")) : 0;
   CK(t32::launch(mapA, mapB, p, N / 256, batch, 0));
   cudaError_t se = cudaDeviceSynchronize();
-  p.dbg = nullptr;
   if (se != cudaSuccess) {
     printf("kernel failed: %s\n", cudaGetErrorString(se));
     return 4;
@@ -100,46 +94,6 @@ int main(int argc, char** argv) {
   std::vector<double> SS((size_t)batch * (rows / 128) * N);
   CK(cudaMemcpy(O.data(), O32, O.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(SS.data(), ss, SS.size() * 8, cudaMemcpyDeviceToHost));
-  if (K <= t32::STAGES * t32::BK) {
-    // verify the TMA-staged tiles of CTA (0,0,0): batch 0, n tile 0, m tile (kmode == 2 ? 0 : last)
-    std::vector<float> S(t32::STAGES * t32::STAGE_BYTES / 4);
-    CK(cudaMemcpy(S.data(), dbg, S.size() * 4, cudaMemcpyDeviceToHost));
-    const int m_tile = kmode == 2 ? 0 : rows / 128 - 1, ba = batch - 1;
-    long long badA = 0, badB = 0, nzA = 0, nzB = 0;
-    for (int st = 0; st < K / t32::BK; st++) {
-      const float* sa = S.data() + (size_t)st * t32::STAGE_BYTES / 4;
-      const float* sb = sa + t32::A_STAGE_BYTES / 4;
-      for (int kk = 0; kk < t32::BK; kk++) {
-        const int k = st * t32::BK + kk;
-        for (int mm = 0; mm < 128; mm++) {
-          const int m = m_tile * 128 + mm;
-          const double a = a_mn ? A[((size_t)ba * K + k) * rows + m] : A[((size_t)ba * rows + m) * K + k];
-          size_t byte;
-          if (a_mn) {  // [mblk][k][32] rows of 128 B, 16-byte chunk index ^= (row & 7)
-            const size_t rowi = (size_t)(mm / 32) * t32::BK + kk;
-            byte = rowi * 128 + ((((mm % 32) / 4) ^ (rowi & 7)) * 16) + (mm % 4) * 4;
-          } else {     // [m][16] rows of 64 B, Swizzle<2,4,3>: chunk bits [4,6) ^= address bits [7,9)
-            const size_t lin = (size_t)mm * 64 + kk * 4;
-            byte = lin ^ (((lin >> 7) & 3) << 4);
-          }
-          const float got = sa[byte / 4];
-          const float want = host_tf32_hi((float)a);
-          if (got != want) badA++;
-          if (got != 0) nzA++;
-        }
-        for (int nn = 0; nn < 256; nn++) {
-          const double bv = B[((size_t)0 * N + nn) * K + k];
-          const size_t lin = (size_t)nn * 64 + kk * 4;
-          const size_t byte = lin ^ (((lin >> 7) & 3) << 4);
-          const float got = sb[byte / 4];
-          const float want = host_tf32_hi((float)bv);
-          if (got != want) badB++;
-          if (got != 0) nzB++;
-        }
-      }
-    }
-    printf("staged tiles (hi planes): A mismatches %lld (nonzero %lld), B mismatches %lld (nonzero %lld)\n", badA, nzA, badB, nzB);
-  }
   double max_rel = 0, max_ss_rel = 0;
   int bad_printed = 0;
   for (int b = 0; b < batch && check; b++) {
