@@ -37,6 +37,19 @@ BOUND, FLAVOUR, S = "further_gating", "keras", 1
 FP64_TENSOR_PEAK_TFLOPS = 37.0  # measured DMMA issue peak on this pool (profiles/fp64_probe_r01.log)
 
 
+def _hbm_peak():
+    """Measured copy bandwidth of this pool's B200 (driver-written MEASURED_PEAKS.json), else the profiling recipe's
+    fallback."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6543.7
+
+
+HBM_PEAK_GBS = _hbm_peak()
+
+
 def logu(rng, lo, hi, size=None):
     return np.exp(rng.uniform(np.log(lo), np.log(hi), size))
 
@@ -300,6 +313,7 @@ def main():
     barrier()
     ms_prof = p0.elapsed_time(p1)
     prof = eng.profile_read()
+    stream_prof = eng.profile_read_streaming()
     eng.profile(False)
     clocks = sampler.stop() if sampler else None
     elbo_val = eng.gbuf.numpy(offset=eng.lo.total, count=4)
@@ -368,6 +382,13 @@ def main():
         },
         "elbo_last_step": float(elbo_val[0]),
     }
+    # HBM-bound streaming kernels, each timed alone with CUDA events in the profiled pass: algorithmic bytes
+    # / duration against the measured copy bandwidth
+    hbm = HBM_PEAK_GBS
+    line["roofline"]["streaming"] = {
+        k: {"us_per_step": 1e3 * ms_k / steps, "achieved": by / (ms_k * 1e-3) * 1e-9, "peak": hbm, "unit": "GB/s",
+            "frac": by / (ms_k * 1e-3) * 1e-9 / hbm}
+        for k, (ms_k, by) in stream_prof.items() if ms_k > 0}
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = run_cpu_reference(wl, spec, 3, 1, wl["cpu_rows"])
         line["cpu_baseline"] = cb

@@ -229,6 +229,9 @@ mogpe_status mogpe_stream_sync(int32_t device, void* cuda_stream);
 mogpe_status mogpe_profile_enable(mogpe_handle* h, int32_t on);
 mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches,
                                 int64_t* all_launches);
+/* Profiling mode also times the streaming kernels alone on the caller's stream: ms[4], bytes[4] for
+ * {kuf, lik, build_abar, kuf_grad} (accumulated since the last read; bytes = algorithmic bytes). */
+mogpe_status mogpe_profile_read_streaming(mogpe_handle* h, double* ms, double* bytes);
 
 /* Test hook: copy a named intermediate of the last call to the host (Kuu, L, Linv, Kuf, A, ...).
  * Returns the element count in *n_out; copies min(capacity, count) doubles. */

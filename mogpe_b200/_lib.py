@@ -61,6 +61,7 @@ _PROTOS = {
     "mogpe_set_kl_weight": (C.c_int, [_P, C.c_double]),
     "mogpe_profile_enable": (C.c_int, [_P, C.c_int32]),
     "mogpe_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mogpe_profile_read_streaming": (C.c_int, [_P, _P, _P]),
     "mogpe_opt_setup": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_double]),
     "mogpe_opt_transform": (C.c_int, [_P, _P, _P, _P]),
     "mogpe_opt_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, _P]),

@@ -97,6 +97,11 @@ struct mogpe_handle {
   double prof_flops = 0;
   long long gemm_launches = 0, all_launches = 0;
   cudaStream_t prof_stream = nullptr;
+  // streaming-kernel timers (profiling mode only): kuf, lik, build_abar, kuf_grad run alone on the caller's stream
+  static constexpr int NSK = 4;
+  std::vector<cudaEvent_t> sk_ev[NSK];
+  size_t sk_used[NSK] = {0, 0, 0, 0};
+  double sk_bytes[NSK] = {0, 0, 0, 0};
   int* d_fail = nullptr;  // 0 = ok, g + 1 = Cholesky of group g failed
   // device-side optimiser
   int* var_rep = nullptr;
@@ -167,6 +172,10 @@ static void free_ws(mogpe_handle* h) {
   if (h->out_host_pinned) cudaFreeHost(h->out_host_pinned);
   for (auto e : h->ev) cudaEventDestroy(e);
   h->ev.clear();
+  for (auto& v : h->sk_ev) {
+    for (auto e : v) cudaEventDestroy(e);
+    v.clear();
+  }
   for (auto e : h->ev_rows) cudaEventDestroy(e);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -440,6 +449,27 @@ static cudaError_t hgemm(mogpe_handle* h, const GemmParams& p, int batch, bool t
 }
 #define KCOUNT(h, n) ((h)->all_launches += (n))
 
+// Profiling mode: bracket one streaming kernel with CUDA events and count its ALGORITHMIC bytes.
+enum { SK_KUF = 0, SK_LIK = 1, SK_ABAR = 2, SK_KUF_GRAD = 3 };
+static void sk_begin(mogpe_handle* h, int id, cudaStream_t st) {
+  if (!h->prof) return;
+  auto& v = h->sk_ev[id];
+  if (h->sk_used[id] + 2 > v.size())
+    for (int i = 0; i < 32; i++) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      v.push_back(e);
+    }
+  cudaEventRecord(v[h->sk_used[id]], st);
+}
+static void sk_end(mogpe_handle* h, int id, cudaStream_t st, double bytes) {
+  if (!h->prof || h->sk_used[id] + 2 > h->sk_ev[id].size()) return;
+  cudaEventRecord(h->sk_ev[id][h->sk_used[id] + 1], st);
+  h->sk_used[id] += 2;
+  h->sk_bytes[id] += bytes;
+  h->prof_stream = st;
+}
+
 // Kuu -> L -> Linv for every group, and the clean q_sqrt copies.
 static cudaError_t launch_a_gemm(mogpe_handle* h, int Bc, int row_base, int rows, cudaStream_t st);
 
@@ -457,8 +487,18 @@ static cudaError_t side_join(mogpe_handle* h, cudaStream_t st) {
 
 static void launch_kuf(mogpe_handle* h, const double* params, const double* X, int N, int Bc, cudaStream_t st) {
   const ModelDev& md = h->md_host;
-  kuf_kernel<<<dim3(Bc / 128, h->Mp / 32, md.Q), 128, (32 * md.D + 32) * sizeof(double), st>>>(h->d_md, params, h->lo, X, N,
-                                                                                               h->Bp, h->Kuf);
+  sk_begin(h, SK_KUF, st);
+  const dim3 kg(Bc / 128, h->Mp / 32, md.Q);
+  if (md.D <= 2)
+    kuf_kernel<2><<<kg, 128, 32 * 3 * sizeof(double), st>>>(h->d_md, params, h->lo, X, N, h->Bp, h->Kuf);
+  else if (md.D <= 4)
+    kuf_kernel<4><<<kg, 128, 32 * 5 * sizeof(double), st>>>(h->d_md, params, h->lo, X, N, h->Bp, h->Kuf);
+  else if (md.D <= 8)
+    kuf_kernel<8><<<kg, 128, 32 * 9 * sizeof(double), st>>>(h->d_md, params, h->lo, X, N, h->Bp, h->Kuf);
+  else
+    kuf_kernel<16><<<kg, 128, 32 * 17 * sizeof(double), st>>>(h->d_md, params, h->lo, X, N, h->Bp, h->Kuf);
+  // algorithmic bytes: write Kuf [Q][M][N], read X [N][D] and Z [M][D] per group
+  sk_end(h, SK_KUF, st, 8.0 * md.Q * ((double)h->Mp * N + (double)N * md.D + (double)h->Mp * md.D));
   KCOUNT(h, 1);
 }
 
@@ -472,7 +512,7 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, const doubl
   H_CUDA(h, side_fork(h, st));
   prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, h->side>>>(h->d_md, params, h->lo, h->Sc);
   make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, h->side>>>(h->d_md, params, h->lo, h->Sc, eps_u, S, h->V);
-  if (fp64_products) launch_kuf(h, params, X, N, Bc, h->side);
+  if (fp64_products && !h->prof) launch_kuf(h, params, X, N, Bc, h->side);
   kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
   // Launch j of the chain completes block row j of L^-1.  A = L^-1 Kuf only needs rows [64 i, 64 i + 64) of L^-1 for
   // its row block i, so the A-GEMM is issued in 64-row slices on the side stream, each waiting for the chain launch
@@ -497,6 +537,7 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, const doubl
   KCOUNT(h, 4 + Mp / 32);
   H_CUDA(h, cudaGetLastError());
   H_CUDA(h, side_join(h, st));
+  if (fp64_products && h->prof) launch_kuf(h, params, X, N, Bc, st);  // timed alone on the caller's stream
   return MOGPE_OK;
 }
 
@@ -625,7 +666,10 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
       H_CUDA(h, cudaFuncSetAttribute(lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
       lik_smem_set = smem;
     }
+    sk_begin(h, SK_LIK, st);
     lik_kernel<<<Bc / blk, blk, smem, st>>>(la);
+    // algorithmic bytes: per point the means / variances of every latent in and their adjoints out, Y, draws
+    sk_end(h, SK_LIK, st, 8.0 * N * (2.0 * md.Pe + 2.0 * (md.P - md.Pe) + md.F + (double)S * md.G + 1.0));
     H_CUDA(h, cudaGetLastError());
   }
   kl_kernel<<<dim3(Mp / 8, P), 256, 0, st>>>(h->d_md, params, lo, h->kl_weight, out, grads);
@@ -638,7 +682,9 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   //     epilogue via alpha and into the B operand... done as: Sbar_l = 2 * tril(A_g diag(dfvar_l) LTA_l^T)
   //     => scale LTA in place first (it is also the B operand of Abar += S_l dLTA_l).
   H_CUDA(h, cudaMemsetAsync(h->dV, 0, (size_t)md.NV * Mp * sizeof(double), st));
+  sk_begin(h, SK_ABAR, st);
   build_abar_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, 0, st>>>(h->d_md, h->A, h->V, h->dmean, h->dfvar, Bp, h->Abar, h->dV);
+  sk_end(h, SK_ABAR, st, 8.0 * Q * 2.0 * Mp * N);  // read A, write Abar
   KCOUNT(h, 5);  // build_abar (+dV), q_grads, halve_diag, kuu_grad, kuf_grad
   H_CUDA(h, cudaGetLastError());
   if (md.nlta > 0) {
@@ -668,10 +714,15 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   // Kuf-bar = W is complete: its kernel-hyperparameter / Z gradients only read W, Kuf, X -> side stream, overlapping
   // the GEMMs of the Cholesky backward below (different gradient entries except kvar / ls, which are atomics)
   H_CUDA(h, side_fork(h, st));
-  if (md.D <= 4)
-    kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q), 256, 0, h->side>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
-  else
-    kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q), 256, 0, h->side>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+  {
+    cudaStream_t ks = h->prof ? st : h->side;  // profiling: alone on the caller's stream
+    sk_begin(h, SK_KUF_GRAD, ks);
+    if (md.D <= 4)
+      kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+    else
+      kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+    sk_end(h, SK_KUF_GRAD, ks, 8.0 * Q * (2.0 * Mp * N + (double)N * md.D));  // read W and Kuf, X
+  }
   {  // Lbar = -tril(W A^T)
     GemmParams p = gp_init();
     p.A = h->W; p.sA = (long long)Mp * Bp; p.lda = Bp;
@@ -1134,6 +1185,10 @@ extern "C" mogpe_status mogpe_profile_enable(mogpe_handle* h, int32_t on) {
   h->prof = on != 0;
   h->ev_used = 0;
   h->prof_flops = 0;
+  for (int i = 0; i < mogpe_handle::NSK; i++) {
+    h->sk_used[i] = 0;
+    h->sk_bytes[i] = 0;
+  }
   h->gemm_launches = h->all_launches = 0;
   return MOGPE_OK;
 }
@@ -1156,6 +1211,25 @@ extern "C" mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, dou
   h->ev_used = 0;
   h->prof_flops = 0;
   h->gemm_launches = h->all_launches = 0;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_profile_read_streaming(mogpe_handle* h, double* ms, double* bytes) {
+  if (!h || !ms || !bytes) return MOGPE_ERR_INVALID;
+  H_CUDA(h, cudaSetDevice(h->device));
+  H_CUDA(h, cudaStreamSynchronize(h->prof_stream));
+  for (int id = 0; id < mogpe_handle::NSK; id++) {
+    double t = 0;
+    for (size_t i = 0; i + 1 < h->sk_used[id]; i += 2) {
+      float e = 0;
+      H_CUDA(h, cudaEventElapsedTime(&e, h->sk_ev[id][i], h->sk_ev[id][i + 1]));
+      t += e;
+    }
+    ms[id] = t;
+    bytes[id] = h->sk_bytes[id];
+    h->sk_used[id] = 0;
+    h->sk_bytes[id] = 0;
+  }
   return MOGPE_OK;
 }
 

@@ -36,58 +36,55 @@ __global__ void kuu_kernel(const ModelDev* __restrict__ md, const double* __rest
 
 // ------------------------------------------------------------------------------------------------
 // Kuf[g][m][n] = k(z_m, x_n); zero for padded rows / columns.  X streamed coalesced, Z staged in smem.
-// grid (Bp/128, Mp/32, Q), block 128.  Dynamic smem: 32*(D+1) doubles.
+// grid (Bp/128, Mp/32, Q), block 128.  Dynamic smem: 32*(DMAX+1) doubles.
 // ------------------------------------------------------------------------------------------------
-__global__ void kuf_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
-                           const double* __restrict__ X, int N, int Bp, double* __restrict__ Kuf) {
-  extern __shared__ double zs[];  // [32][D] scaled Z rows, then [32] squared norms
+template <int DMAX>
+__global__ void __launch_bounds__(128) kuf_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                  Layout lo, const double* __restrict__ X, int N, int Bp,
+                                                  double* __restrict__ Kuf) {
+  extern __shared__ double zs[];  // [32][DMAX] scaled Z rows (zero beyond D / Mg), then [32] squared norms
   const int g = blockIdx.z, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
   const int m0 = blockIdx.y * 32;
   const double* ls = params + lo.ls + (long long)g * D;
   const double* Z = params + lo.Z + (long long)g * Mp * D;
-  double* zn = zs + 32 * D;
-  for (int t = threadIdx.x; t < 32 * D; t += blockDim.x) {
-    const int r = t / D, d = t % D;
-    zs[t] = (m0 + r < Mg) ? Z[(m0 + r) * D + d] / ls[d] : 0.0;
+  double* zn = zs + 32 * DMAX;
+  for (int t = threadIdx.x; t < 32 * DMAX; t += blockDim.x) {
+    const int r = t / DMAX, d = t % DMAX;
+    zs[t] = (d < D && m0 + r < Mg) ? Z[(m0 + r) * D + d] / ls[d] : 0.0;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
     double s = 0;
-    for (int d = 0; d < D; d++) s += zs[threadIdx.x * D + d] * zs[threadIdx.x * D + d];
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) s += zs[threadIdx.x * DMAX + d] * zs[threadIdx.x * DMAX + d];
     zn[threadIdx.x] = s;
   }
   __syncthreads();
   const int n = blockIdx.x * 128 + threadIdx.x;
   const double kv = params[lo.kvar + g];
-  double xs[8];
-  double xn = 0;
   const bool valid = n < N;
-  // D <= 8 fast path keeps x in registers; larger D re-reads X (L1-resident)
-  if (D <= 8) {
-    for (int d = 0; d < D; d++) {
-      xs[d] = valid ? X[(long long)n * D + d] / ls[d] : 0.0;
-      xn += xs[d] * xs[d];
-    }
-  } else {
-    for (int d = 0; d < D; d++) {
-      const double a = valid ? X[(long long)n * D + d] / ls[d] : 0.0;
-      xn += a * a;
-    }
+  double xs[DMAX];  // registers: every loop over d is fully unrolled
+  double xn = 0;
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) {
+    xs[d] = (valid && d < D) ? X[(long long)n * D + d] / ls[d] : 0.0;
+    xn += xs[d] * xs[d];
   }
   double* out = Kuf + ((long long)g * Mp + m0) * Bp + n;
-  for (int r = 0; r < 32; r++) {
-    double v = 0.0;
-    if (valid && m0 + r < Mg) {
+  // four rows per iteration: four independent exp chains in flight per thread (the chain is latency-bound otherwise)
+#pragma unroll 2
+  for (int r = 0; r < 32; r += 4) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
       double dot = 0;
-      if (D <= 8) {
-        for (int d = 0; d < D; d++) dot += zs[r * D + d] * xs[d];
-      } else {
-        for (int d = 0; d < D; d++) dot += zs[r * D + d] * (X[(long long)n * D + d] / ls[d]);
-      }
-      const double r2 = -2.0 * dot + (zn[r] + xn);
-      v = kv * exp(-0.5 * r2);
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) dot += zs[(r + u) * DMAX + d] * xs[d];
+      const double r2 = -2.0 * dot + (zn[r + u] + xn);
+      v[u] = kv * exp(-0.5 * r2);
     }
-    out[(long long)r * Bp] = v;
+#pragma unroll
+    for (int u = 0; u < 4; u++) out[(long long)(r + u) * Bp] = (valid && m0 + r + u < Mg) ? v[u] : 0.0;
   }
 }
 

@@ -333,6 +333,12 @@ class Engine:
         _lib.check(self.lib.mogpe_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(ng), C.byref(na)), self.h)
         return {"gemm_ms": ms.value, "gemm_flops": fl.value, "gemm_launches": ng.value, "all_launches": na.value}
 
+    def profile_read_streaming(self):
+        """-> {kernel: (ms, algorithmic bytes)} for the streaming kernels timed in profiling mode."""
+        ms, by = (C.c_double * 4)(), (C.c_double * 4)()
+        _lib.check(self.lib.mogpe_profile_read_streaming(self.h, ms, by), self.h)
+        return {k: (ms[i], by[i]) for i, k in enumerate(("kuf", "lik", "build_abar", "kuf_grad"))}
+
     # ---- device-side optimiser (SURVEY 8f-1) -------------------------------------------------------------------
     def setup_optimizer(self, var_rep: np.ndarray, noise_lower: float = 1e-6):
         """var_rep [total] int32: representative packed index of each entry's variable (-1: not a variable)."""
