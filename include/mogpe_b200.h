@@ -206,6 +206,23 @@ mogpe_status mogpe_opt_transform(mogpe_handle* h, double* u, double* params, voi
 mogpe_status mogpe_opt_adam_step(mogpe_handle* h, double* u, double* params, const double* grads, double lr,
                                  double beta1, double beta2, double epsilon, int64_t t, void* cuda_stream);
 
+/* One whole training step on the library's own stream: [copy the minibatch in from host memory through a pinned ring],
+ * ELBO forward + backward with draws from the library random stream, bijector chain, Adam (TF semantics, step count t),
+ * params = T(u), and an asynchronous copy of the 4 result doubles to out_host_pinned (nullable).  Replaces one iteration
+ * of the Keras fit loop / monitored_training_loop (mogpe/keras/mixture_of_experts/mosvgpe.py:57-69,
+ * mogpe/training/training_loops.py:28-30).  With use_graph != 0 the launches (~45 kernels) are captured into a CUDA graph the
+ * second time a given argument set is seen and replayed afterwards: the random-stream position and the Adam step count
+ * live on the device, so replays are exact continuations.  Small models are launch-bound; this removes the launch cost.
+ * use_graph: 0 = never, 1 = only when the step is launch-bound (Q M^2 B < 2e8), 2 = always.
+ * Nothing is synchronised: results are valid after mogpe_check_numerics / mogpe_stream_sync(device, NULL). */
+mogpe_status mogpe_train_step(mogpe_handle* h, const double* X, const double* Y, int32_t data_on_host, int32_t N,
+                              double* params, int32_t bound, int32_t num_samples, double scale, double* out,
+                              double* out_host_pinned, double* grads, double* u, double lr, double beta1, double beta2,
+                              double epsilon, int64_t t, int32_t use_graph);
+
+/* Number of captured training-step graphs and whether capture failed and was switched off (diagnostics / tests). */
+mogpe_status mogpe_graph_stats(mogpe_handle* h, int32_t* captured, int32_t* disabled);
+
 /* Minibatch assembly from a device-resident data set (replaces the tf.data shuffle/batch pipeline of
  * mogpe/training/utils.py:105-116): dst[i, :] = src[idx[i], :], src [N, cols], idx [n] int64, all device pointers. */
 mogpe_status mogpe_gather_rows(mogpe_handle* h, const double* src, const int64_t* idx, int64_t n, int32_t cols,

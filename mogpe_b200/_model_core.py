@@ -77,6 +77,8 @@ class MixtureCore:
         self.seed = 0
         self.default_batch = 1024
         self.dp = None  # (rank, world_size, nccl unique id) for data-parallel fit()
+        self.precision = "float64"
+        self.use_graphs = True  # fit(): replay each training step as one CUDA graph (single-GPU)
 
     # -- engine lifecycle ---------------------------------------------------------------------------------
     def _blocks(self):
@@ -96,7 +98,7 @@ class MixtureCore:
             if self.engine is not None:
                 self.engine.close()
             self.engine = Engine(experts, gating, flavour=self.flavour, max_batch=max(batch, self.default_batch),
-                                 device=self.device)
+                                 device=self.device, precision=self.precision)
             self.engine.set_seed(self.seed)
             if self.dp is not None and self.dp[1] > 1:
                 self.engine.init_data_parallel(*self.dp)
@@ -115,6 +117,20 @@ class MixtureCore:
         self.seed = int(seed)
         if self.engine is not None:
             self.engine.set_seed(self.seed)
+
+    def set_precision(self, precision: str):
+        """"float64" (default, gpflow's default_float) or "tf32": predict_* run their M x M x N products as 3xTF32 on the
+        tcgen05 tensor cores (FP32-class accuracy, ~4x the FP64 throughput at M = 1024); the ELBO always runs in FP64."""
+        from . import _lib
+
+        if precision not in _lib.PRECISION_IDS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISION_IDS)}")
+        if precision != self.precision:
+            self.precision = precision
+            if self.engine is not None:  # the workspace layout depends on the mode: rebuild on next use
+                self.engine.close()
+                self.engine = None
+                self._engine_stamp = self._opt_stamp = None
 
     @property
     def trainable_parameters(self) -> List[Parameter]:
@@ -265,6 +281,19 @@ class MixtureCore:
                 idx = order[s:s + batch_size]
                 scale = 1.0 if num_data is None else float(num_data) / (len(idx) * world)
                 out_ptr = results.ptr + 32 * step_i
+                if world == 1:
+                    # the whole step is one library call (one CUDA-graph launch once its argument set has been seen twice)
+                    optimizer.t += 1
+                    if device_data:
+                        eng.gather_rows(Xd, idx_dev.ptr + s * 8, len(idx), X.shape[1], Xb_dev)
+                        eng.gather_rows(Yd, idx_dev.ptr + s * 8, len(idx), Y.shape[1], Yb_dev)
+                        Xb = TensorView(Xb_dev.ptr, (len(idx), X.shape[1]), True, self.device, Xb_dev)
+                        Yb = TensorView(Yb_dev.ptr, (len(idx), Y.shape[1]), True, self.device, Yb_dev)
+                    else:
+                        Xb, Yb = X[idx], Y[idx]
+                    eng.train_step(Xb, Yb, bound, num_samples, scale, optimizer.t, optimizer.lr, optimizer.b1, optimizer.b2,
+                                   optimizer.eps, out_pinned_ptr=out_ptr, use_graph=self.use_graphs)
+                    continue
                 if device_data:
                     eng.gather_rows(Xd, idx_dev.ptr + s * 8, len(idx), X.shape[1], Xb_dev)
                     eng.gather_rows(Yd, idx_dev.ptr + s * 8, len(idx), Y.shape[1], Yb_dev)

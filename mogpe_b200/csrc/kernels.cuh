@@ -765,17 +765,28 @@ __global__ void opt_chain_kernel(long long n, Layout lo, const double* __restric
 }
 
 // Adam (TF semantics: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); epsilon outside the sqrt) on loss = -ELBO
+// lr_t_dev (optional): the bias-corrected step size computed on the device by train_step_prep_kernel (graph replay).
 __global__ void opt_adam_kernel(long long n, const int* __restrict__ var_rep, const double* __restrict__ gu,
                                 double* __restrict__ u, double* __restrict__ m, double* __restrict__ v, double lr_t,
-                                double b1, double b2, double eps) {
+                                double b1, double b2, double eps, const double* __restrict__ lr_t_dev) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || var_rep[i] != i) return;
+  if (lr_t_dev) lr_t = *lr_t_dev;
   const double gl = -gu[i];
   const double mi = m[i] + (1.0 - b1) * (gl - m[i]);
   const double vi = v[i] + (1.0 - b2) * (gl * gl - v[i]);
   m[i] = mi;
   v[i] = vi;
   u[i] -= lr_t * mi / (sqrt(vi) + eps);
+}
+
+// Graph-replayed training step: advance the device-side random-stream position and Adam step count, and derive the
+// bias-corrected step size.  state = {rng position, adam t}; one thread.
+__global__ void train_step_prep_kernel(unsigned long long* __restrict__ state, unsigned long long rng_consumed, double lr,
+                                       double b1, double b2, double* __restrict__ lr_t_dev) {
+  state[0] += rng_consumed;
+  const unsigned long long t = ++state[1];
+  *lr_t_dev = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
 }
 
 // params[i] = T(u[rep(i)]) (and u of tied entries follows its representative); non-variables are left untouched
@@ -803,11 +814,14 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
 
+// `base` (optional, device memory) is added to `offset`: launches captured in a CUDA graph keep the stream position on
+// the device so that replaying the graph continues the random stream (mogpe_train_step).
 __global__ void fill_normal_kernel(double* __restrict__ dst, long long n, unsigned long long seed,
-                                   unsigned long long offset) {
+                                   unsigned long long offset, const unsigned long long* __restrict__ base) {
   const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = pair * 2;
   if (i >= n) return;
+  if (base) offset += *base;
   const unsigned long long ctr = offset / 2 + pair;
   uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x6d6f6770u, 0x65623230u};
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);

@@ -359,6 +359,28 @@ class Engine:
         _lib.check(self.lib.mogpe_opt_adam_step(self.h, self.u.ptr, self.params.ptr, self.grads_ptr, float(lr), float(beta_1),
                                                 float(beta_2), float(epsilon), int(t), stream), self.h)
 
+    def train_step(self, X, Y, bound, num_samples, scale, t, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+                   out_pinned_ptr=None, use_graph=True):
+        """One fused training step (ELBO fwd+bwd -> Adam -> params) on the library's stream, replayed as a CUDA graph from
+        its third occurrence (use_graph: False / 0 never, True / 1 when the step is launch-bound, 2 always).
+        X / Y: host numpy arrays (staged through pinned memory) or device TensorViews."""
+        if isinstance(X, np.ndarray):
+            X = np.ascontiguousarray(X, dtype=np.float64)
+            Y = np.ascontiguousarray(Y, dtype=np.float64)
+            xp, yp, on_host, n = X.ctypes.data, Y.ctypes.data, 1, X.shape[0]
+        else:
+            xv, yv = as_view(X), as_view(Y)
+            xp, yp, on_host, n = xv.ptr, yv.ptr, 0, int(xv.shape[0])
+        _lib.check(self.lib.mogpe_train_step(self.h, xp, yp, on_host, n, self.params.ptr, _lib.BOUND_IDS[bound], num_samples,
+                                             float(scale), self.out_ptr, out_pinned_ptr, self.grads_ptr, self.u.ptr, float(lr),
+                                             float(beta_1), float(beta_2), float(epsilon), int(t), int(use_graph)), self.h)
+
+    def graph_stats(self):
+        """-> (captured training-step graphs, capture disabled after a failure)."""
+        n, d = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.mogpe_graph_stats(self.h, C.byref(n), C.byref(d)), self.h)
+        return n.value, bool(d.value)
+
     def predict_f_inducing_samples(self, X, num_samples, eps_u=None, stream=None):
         """-> f_mean [S, N, P], f_var [N, P] (mogpe/keras/gps.py:14-50); eps_u [P, S, Mp] or None (library stream)."""
         xv = as_view(X)

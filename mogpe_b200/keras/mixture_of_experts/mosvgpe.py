@@ -62,6 +62,10 @@ class MixtureOfSVGPExperts(MixtureOfExpertsBase):
     def set_seed(self, seed: int):
         self._core.set_seed(seed)
 
+    def set_precision(self, precision: str):
+        """"float64" (default) or "tf32" (prediction on the tcgen05 tensor cores; new capability)."""
+        self._core.set_precision(precision)
+
     def enable_data_parallel(self, rank: int, world_size: int, unique_id: bytes):
         """Data-parallel fit(): see MixtureCore.enable_data_parallel (new capability; the reference is single-device)."""
         self._core.enable_data_parallel(rank, world_size, unique_id)

@@ -40,6 +40,10 @@ class MixtureOfSVGPExperts(MixtureOfExperts):
     def set_seed(self, seed: int):
         self._core.set_seed(seed)
 
+    def set_precision(self, precision: str):
+        """"float64" (default) or "tf32" (prediction on the tcgen05 tensor cores; new capability)."""
+        self._core.set_precision(precision)
+
     def enable_data_parallel(self, rank: int, world_size: int, unique_id: bytes):
         self._core.enable_data_parallel(rank, world_size, unique_id)
 

@@ -202,3 +202,30 @@ def test_device_resident_data_pipeline_matches_host_batches():
     np.testing.assert_allclose(hb["loss"], ha["loss"], rtol=1e-10)
     for pa, pb in zip(a.trainable_variables, b.trainable_variables):
         np.testing.assert_allclose(pb.unconstrained, pa.unconstrained, rtol=1e-9, atol=1e-11, err_msg=pa.name)
+
+
+@pytest.mark.parametrize("device_data", [False, True])
+def test_graph_replayed_training_steps_match_direct_launches(device_data):
+    """fit() replays each step as one CUDA graph (mogpe_train_step); the trajectory must equal the directly launched one:
+    the random-stream position and the Adam step count live on the device and continue across replays, ragged last
+    batches get their own graph, and a predict call in the middle (call-mode change) does not disturb the replays."""
+    from mogpe_b200._model_core import Adam
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=85, N=100, D=2, F=1, K=2, M=8, S=2, num_data=100)
+    a, b = model_from_spec(spec), model_from_spec(spec)
+    for m in (a, b):
+        m.set_seed(11)
+        m.compile(optimizer=Adam(learning_rate=0.01))
+    a._core.use_graphs = False
+    ha = a.fit(X, Y, epochs=4, batch_size=32, shuffle=False, device_data=device_data)  # 3 full batches + one of 4 rows
+    hb = b.fit(X, Y, epochs=2, batch_size=32, shuffle=False, device_data=device_data)
+    b.predict_y(X[:10])
+    hb2 = b.fit(X, Y, epochs=2, batch_size=32, shuffle=False, device_data=device_data)
+    a.predict_y(X[:10])
+    np.testing.assert_allclose(hb["loss"] + hb2["loss"], ha["loss"], rtol=1e-10)
+    for pa, pb in zip(a.trainable_variables, b.trainable_variables):
+        np.testing.assert_allclose(pb.unconstrained, pa.unconstrained, rtol=1e-9, atol=1e-11, err_msg=pa.name)
+    captured, disabled = b._core.engine.graph_stats()
+    assert not disabled and captured >= 1
+    assert a._core.engine.graph_stats()[0] == 0

@@ -115,3 +115,28 @@ def test_unknown_precision_is_rejected():
     spec, X, Y, eps = make_spec(seed=5, N=20, D=2, F=1, K=2, M=8)
     with pytest.raises(ValueError):
         engine_from_spec(spec, max_batch=32, precision="bf16")
+
+
+@pytest.mark.parametrize("flavour", ["keras", "legacy"])
+def test_public_api_set_precision(flavour):
+    """model.set_precision("tf32") switches predict_y / predict_mixing_probs to the tcgen05 path and back; training
+    (fit / maximum_log_likelihood_objective) stays float64 in both modes."""
+    from oracle import ref_numpy as rn
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=61, N=300, D=2, F=1, K=2, M=40, flavour=flavour, ls_range=(0.15, 0.5))
+    model = model_from_spec(spec)
+    ym, yv = rn.predict_y(spec, X)
+    d64 = model.predict_y(X)
+    assert _rel(d64.mean(), ym) < RTOL_F64 and _rel(d64.variance(), yv) < RTOL_F64
+    model.set_precision("tf32")
+    d32 = model.predict_y(X)
+    assert _rel(d32.mean(), ym) < RTOL_TF32 and _rel(d32.variance(), yv) < RTOL_TF32
+    assert not np.array_equal(np.asarray(d32.variance()), np.asarray(d64.variance()))
+    val = model.maximum_log_likelihood_objective((X, Y), eps=eps)
+    assert abs(val - rn.elbo(spec, X, Y, eps)) <= RTOL_F64 * abs(val)
+    model.set_precision("float64")
+    d64b = model.predict_y(X)
+    assert np.array_equal(np.asarray(d64b.variance()), np.asarray(d64.variance()))
+    with pytest.raises(ValueError):
+        model.set_precision("fp8")
