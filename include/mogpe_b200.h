@@ -141,7 +141,11 @@ mogpe_status mogpe_elbo_fwd_bwd_host_async(mogpe_handle* h, const double* X_host
  *   f_mean, f_var [N, P]  marginal q(f) per latent (with the q_sqrt term, no sampling)
  *   mix_probs [N, K]      Bernoulli: analytic probit; Softmax: mean over eps_mc [R, N, K] draws
  *   y_mean, y_var [N, F]  mixture mean / variance (flavour-specific formula)
- * X and outputs are device pointers; N is streamed in chunks of max_batch. */
+ * X and outputs are device pointers; N is streamed in chunks of max_batch.
+ *   Softmax gating (G > 1): the mixing probabilities are gpflow's Monte-Carlo mean over num_mc draws; eps_mc [num_mc, N, K]
+ *   supplies them (parity tests), eps_mc == NULL takes them from the library random stream (generated per chunk on the
+ *   device, indexed by the global point index: independent of max_batch; this is what makes 1e8-point sweeps possible).
+ */
 mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const double* params, double* f_mean,
                            double* f_var, double* mix_probs, double* y_mean, double* y_var,
                            const double* eps_mc, int32_t num_mc, void* cuda_stream);

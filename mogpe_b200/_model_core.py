@@ -174,11 +174,11 @@ class MixtureCore:
         N = int(xv.shape[0])
         eng = self.ensure_engine(min(N, max(self.default_batch, 65536)))
         need_pi = any(w in want for w in ("mix_probs", "y_mean", "y_var"))
-        if eng.G > 1 and need_pi and eps_mc is None:
-            # gpflow Softmax.predict_mean_and_var: 100 Monte-Carlo draws from the global RNG
-            rng = rng or np.random.default_rng(self.seed)
+        if eng.G > 1 and need_pi and eps_mc is None and rng is not None:
+            # gpflow Softmax.predict_mean_and_var: 100 Monte-Carlo draws from the global RNG; an explicit numpy Generator
+            # reproduces that on the host, the default (rng None) draws them on the device from the library stream
             eps_mc = rng.standard_normal((100, N, eng.K))
-        return eng.predict(Xnew, want=want, eps_mc=eps_mc)
+        return eng.predict(Xnew, want=want, eps_mc=eps_mc, num_mc=100)
 
     # -- device-side training -------------------------------------------------------------------------
     def _gps(self):

@@ -153,7 +153,7 @@ static cudaError_t dalloc(T** p, size_t n) {
   return cudaMalloc((void**)p, n * sizeof(T));
 }
 
-extern "C" const char* mogpe_version(void) { return "mogpe_b200 0.1 (sm_100a, fp64 DMMA)"; }
+extern "C" const char* mogpe_version(void) { return "mogpe_b200 0.2 (sm_100a: fp64 DMMA, tf32 tcgen05)"; }
 
 extern "C" const char* mogpe_last_error(const mogpe_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -992,10 +992,12 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
   if (!h) return MOGPE_ERR_INVALID;
   if (!X || !params || N < 1) H_FAIL(h, MOGPE_ERR_INVALID, "null X / params or N < 1");
   const ModelDev& md = h->md_host;
-  if (md.G > 1 && (mix_probs || y_mean || y_var) && (!eps_mc || num_mc < 1))
+  const bool need_mc = md.G > 1 && (mix_probs || y_mean || y_var);
+  if (need_mc && num_mc < 1)
     H_FAIL(h, MOGPE_ERR_INVALID,
            "Softmax gating: mixing probabilities are a Monte-Carlo mean (gpflow Softmax.predict_mean_and_var); "
-           "pass eps_mc [num_mc, N, K]");
+           "pass num_mc >= 1 (and eps_mc [num_mc, N, K], or NULL for the library random stream)");
+  const bool lib_mc = need_mc && !eps_mc;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   H_CUDA(h, cudaSetDevice(h->device));
   mogpe_status rc = set_mode(h, -1, 1, st);
@@ -1021,12 +1023,29 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
     PredArgs pa;
     pa.md = h->d_md; pa.params = params; pa.lo = h->lo; pa.mean = h->mean; pa.var0ss = h->var0ss; pa.varq = h->varq;
     pa.n0 = (int)n0; pa.nchunk = nc; pa.Bp = h->Bp; pa.Ntot = N; pa.eps_mc = eps_mc; pa.num_mc = num_mc;
+    pa.mc_ld = N; pa.mc_n0 = 0;
+    if (lib_mc) {
+      // draws for this chunk from the library stream, indexed by the GLOBAL point index (chunking-independent)
+      const size_t need = (size_t)num_mc * chunk_max * md.K;
+      if (need > h->eps_mc_cap) {
+        h->graphs_dirty = true;
+        if (h->eps_mc_int) cudaFree(h->eps_mc_int);
+        h->eps_mc_int = nullptr;
+        H_CUDA(h, dalloc(&h->eps_mc_int, need));
+        h->eps_mc_cap = need;
+      }
+      fill_normal_mc_kernel<<<dim3((unsigned)(((long long)nc * md.K + 255) / 256), num_mc), 256, 0, st>>>(
+          h->eps_mc_int, nc, md.K, (long long)N, (long long)n0, h->seed, h->rng_counter);
+      KCOUNT(h, 1);
+      pa.eps_mc = h->eps_mc_int; pa.mc_ld = nc; pa.mc_n0 = n0;
+    }
     pa.f_mean = f_mean; pa.f_var = f_var; pa.mix = mix_probs; pa.y_mean = y_mean; pa.y_var = y_var;
     const int blk = 128;
     KCOUNT(h, 1);
     predict_out_kernel<<<(nc + blk - 1) / blk, blk, (size_t)2 * md.K * blk * sizeof(double), st>>>(pa);
     H_CUDA(h, cudaGetLastError());
   }
+  if (lib_mc) h->rng_counter += ((unsigned long long)num_mc * N * md.K + 1) / 2 * 2;
   return MOGPE_OK;
 }
 

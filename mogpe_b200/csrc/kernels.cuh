@@ -842,3 +842,31 @@ __global__ void fill_normal_kernel(double* __restrict__ dst, long long n, unsign
 }
 
 }  // namespace mogpe
+
+namespace mogpe {
+// Library-generated Softmax Monte-Carlo draws for one chunk of test points (gpflow Softmax.predict_mean_and_var draws
+// from the global RNG): dst[r][i][k], i in [0, nc), is element offset + ((r * Ntot) + n0 + i) * K + k of the Philox stream,
+// so the result does not depend on how the points are chunked.   grid (ceil(nc*K/256), R), block 256
+__global__ void fill_normal_mc_kernel(double* __restrict__ dst, int nc, int K, long long Ntot, long long n0,
+                                      unsigned long long seed, unsigned long long offset) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (j >= (long long)nc * K) return;
+  const unsigned long long e = offset + ((unsigned long long)r * Ntot + n0) * K + j;
+  const unsigned long long ctr = e >> 1;
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x6d6f6770u, 0x65623230u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int q = 0; q < 10; q++) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const double u1 = ((double)(((unsigned long long)c[0] << 21) ^ (c[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(((unsigned long long)c[2] << 21) ^ (c[3] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, co;
+  sincospi(2.0 * u2, &sn, &co);
+  dst[(long long)r * nc * K + j] = rad * ((e & 1) ? sn : co);
+}
+}  // namespace mogpe

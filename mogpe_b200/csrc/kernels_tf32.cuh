@@ -62,6 +62,9 @@ __global__ void __launch_bounds__(128) kuf32_kernel(const ModelDev* __restrict__
   const double* ls = params + lo.ls + (long long)g * D;
   const double* Z = params + lo.Z + (long long)g * Mp * D;
   const double kv = params[lo.kvar + g];
+  double il[DMAX];  // 1 / lengthscale: one FP64 division per thread instead of D per point
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) il[d] = d < D ? 1.0 / ls[d] : 0.0;
   double z[4][DMAX], zn[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(128) kuf32_kernel(const ModelDev* __restrict__
     zn[j] = 0.0;
 #pragma unroll
     for (int d = 0; d < DMAX; d++) {
-      z[j][d] = (d < D && k < Mg) ? Z[(long long)k * D + d] / ls[d] : 0.0;
+      z[j][d] = (d < D && k < Mg) ? Z[(long long)k * D + d] * il[d] : 0.0;
       zn[j] += z[j][d] * z[j][d];
     }
   }
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(128) kuf32_kernel(const ModelDev* __restrict__
     double x[DMAX], xn = 0.0;
 #pragma unroll
     for (int d = 0; d < DMAX; d++) {
-      x[d] = (valid && d < D) ? X[(long long)n * D + d] / ls[d] : 0.0;
+      x[d] = (valid && d < D) ? X[(long long)n * D + d] * il[d] : 0.0;
       xn += x[d] * x[d];
     }
     double kval[4];

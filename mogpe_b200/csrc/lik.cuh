@@ -428,7 +428,8 @@ struct PredArgs {
   const double* varq;    // [P][Bp]
   int n0, nchunk, Bp;
   long long Ntot;
-  const double* eps_mc;  // [R][Ntot][K] or null
+  const double* eps_mc;  // [R][mc_ld][K] (rows n - mc_n0) or null
+  long long mc_ld, mc_n0;
   int num_mc;
   double* f_mean;  // [Ntot][P] or null
   double* f_var;
@@ -467,7 +468,7 @@ __global__ void predict_out_kernel(const PredArgs a) {
     for (int r = 0; r < a.num_mc; r++) {
       double mx = -1e300;
       for (int k = 0; k < K; k++) {
-        const double h = fmean(Pe + k) + sqrt(fvar(Pe + k)) * a.eps_mc[((long long)r * a.Ntot + n) * K + k];
+        const double h = fmean(Pe + k) + sqrt(fvar(Pe + k)) * a.eps_mc[((long long)r * a.mc_ld + (n - a.mc_n0)) * K + k];
         pi(K + k) = h;
         mx = fmax(mx, h);
       }

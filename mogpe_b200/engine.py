@@ -281,8 +281,10 @@ class Engine:
                                                           _lib.BOUND_IDS[bound], num_samples, float(scale), self.out_ptr,
                                                           out_pinned_ptr, self.grads_ptr, stream), self.h)
 
-    def predict(self, X, want=("f_mean", "f_var", "mix_probs", "y_mean", "y_var"), eps_mc=None, stream=None):
-        """-> dict of numpy arrays (f_mean/f_var [N, P], mix_probs [N, K], y_mean/y_var [N, F])."""
+    def predict(self, X, want=("f_mean", "f_var", "mix_probs", "y_mean", "y_var"), eps_mc=None, stream=None, num_mc=100):
+        """-> dict of numpy arrays (f_mean/f_var [N, P], mix_probs [N, K], y_mean/y_var [N, F]).
+        Softmax gating: eps_mc [R, N, K] explicit Monte-Carlo draws, or None -> num_mc draws per point from the library's
+        random stream (generated on the device)."""
         xv = as_view(X)
         N = int(xv.shape[0])
         if len(xv.shape) != 2 or xv.shape[1] != self.D:
@@ -291,7 +293,7 @@ class Engine:
         shapes = {"f_mean": (N, self.P), "f_var": (N, self.P), "mix_probs": (N, self.K),
                   "y_mean": (N, self.F), "y_var": (N, self.F)}
         bufs = {k: DeviceBuffer(shapes[k], self.device, zero=False) for k in want}
-        num_mc = 0
+        num_mc = int(num_mc) if self.G > 1 else 0
         mp = None
         if eps_mc is not None:
             e = np.ascontiguousarray(eps_mc, dtype=np.float64)

@@ -245,7 +245,7 @@ def test_invalid_arguments_raise():
         run_engine_elbo(eng, spec, X, Y, eps)  # N > max_batch
     eng = engine_from_spec(spec, max_batch=32)
     with pytest.raises(MogpeError, match="Softmax"):
-        eng.predict(X, want=("mix_probs",))  # Softmax mixing probabilities need Monte-Carlo draws
+        eng.predict(X, want=("mix_probs",), num_mc=0)  # Softmax mixing probabilities need Monte-Carlo draws
     with pytest.raises(ValueError):
         eng.elbo(X[:, :1].repeat(3, 1), Y)
 
@@ -283,3 +283,25 @@ def test_cholesky_failure_is_reported_like_the_reference():
     spec["gating"]["kernels"][0]["variance"] = 1.0
     eng2 = engine_from_spec(spec, max_batch=40)
     assert np.isfinite(run_engine_elbo(eng2, spec, X, Y, eps).elbo)
+
+
+def test_predict_softmax_library_draws_are_chunking_independent_and_close_to_explicit_draws():
+    """eps_mc=None: the Softmax Monte-Carlo draws come from the library stream, indexed by the global point index, so the
+    result does not depend on max_batch; with many draws it converges to the explicit-draw estimate (both are unbiased
+    estimates of the same expectation)."""
+    from tests._engine_helpers import engine_from_spec
+
+    N, K = 500, 3
+    spec, X, Y, eps = make_spec(seed=31, N=N, D=2, F=1, K=K, M=20)
+    a, b = engine_from_spec(spec, max_batch=128), engine_from_spec(spec, max_batch=512)
+    for e in (a, b):
+        e.set_seed(7)
+    pa = a.predict(X, want=("mix_probs", "y_mean"), num_mc=64)
+    pb = b.predict(X, want=("mix_probs", "y_mean"), num_mc=64)
+    np.testing.assert_allclose(pa["mix_probs"], pb["mix_probs"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(pa["mix_probs"].sum(-1), 1.0, rtol=1e-12)
+    pa2 = a.predict(X, want=("mix_probs",), num_mc=64)  # the stream advances between calls
+    assert not np.array_equal(pa2["mix_probs"], pa["mix_probs"])
+    big = a.predict(X, want=("mix_probs",), num_mc=4000)["mix_probs"]
+    ref = a.predict(X, want=("mix_probs",), eps_mc=np.random.default_rng(0).standard_normal((4000, N, K)))["mix_probs"]
+    assert np.max(np.abs(big - ref)) < 0.03  # two independent 4000-draw estimates: std <= 0.5 / sqrt(4000) each

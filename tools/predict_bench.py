@@ -1,4 +1,4 @@
-"""predict_y / predict_mixing_probs throughput (BASELINE config C5 shape: K=8, G=8, D=4, M=1024; N scaled down).
+"""predict_y / predict_mixing_probs throughput (BASELINE config C5: K=8, G=8, D=4, M=1024, N up to 1e8).
 Test points are generated on the device; outputs stay on the device.  Usage: python tools/predict_bench.py [N] [M] [float64|tf32]"""
 import sys, time
 sys.path.insert(0, ".")
@@ -19,15 +19,11 @@ eng = Engine(experts, gating, flavour="keras", max_batch=65536, precision=precis
 lib = _lib.load()
 X = DeviceBuffer((N, 4), zero=False)
 eng.fill_normal(X, seed=4)
-R = 100
-eps_mc = DeviceBuffer((R, N, 8), zero=False) if N * R * 8 * 8 < 40e9 else None
-if eps_mc is None:
-    raise SystemExit("N too large to materialise the Softmax Monte-Carlo draws; use a smaller N")
-eng.fill_normal(eps_mc, seed=5)
+R = 100  # gpflow's Softmax Monte-Carlo draws per point, generated on the device from the library stream
 outs = {k: DeviceBuffer(s, zero=False) for k, s in (("y_mean", (N, 1)), ("y_var", (N, 1)), ("mix", (N, 8)))}
 def run():
     _lib.check(lib.mogpe_predict(eng.h, X.ptr, N, eng.params.ptr, None, None, outs["mix"].ptr, outs["y_mean"].ptr, outs["y_var"].ptr,
-                                 eps_mc.ptr, R, None), eng.h)
+                                 None, R, None), eng.h)
 run(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
