@@ -59,6 +59,12 @@ struct mogpe_handle {
   double* alpha = nullptr;                        // [P][Mp32]: L^-T q_mu (FP64 means)
   CUtensorMap tm_linv, tm_st, tm_kuf, tm_at;
   bool t32_ready = false;
+  // INT8 mode (integer-sliced FP64-accurate products, gemm_i8.cuh): byte planes and power-of-two scales
+  int8_t *Linv8 = nullptr, *ST8 = nullptr;        // [Q | P][NS][Mp32][Mp32]
+  int8_t *KufT8 = nullptr, *AT8 = nullptr;        // [Q][NS][Bp][Mp32]
+  double *linv_scale = nullptr, *st_scale = nullptr;      // [Q | P][Mp32] row scales
+  double *kuf_scale = nullptr, *aout_scale = nullptr;     // [Q] group scales
+  bool i8_ready = false;
   int* d_t32_err = nullptr;
   // graph-replayed training step (mogpe_train_step): launches are captured once per argument set and replayed
   struct GraphEntry {
@@ -182,6 +188,14 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_step_state) cudaFree(h->d_step_state);
   if (h->d_lr_t) cudaFree(h->d_lr_t);
   if (h->step_stage) cudaFree(h->step_stage);
+  if (h->Linv8) cudaFree(h->Linv8);
+  if (h->ST8) cudaFree(h->ST8);
+  if (h->KufT8) cudaFree(h->KufT8);
+  if (h->AT8) cudaFree(h->AT8);
+  if (h->linv_scale) cudaFree(h->linv_scale);
+  if (h->st_scale) cudaFree(h->st_scale);
+  if (h->kuf_scale) cudaFree(h->kuf_scale);
+  if (h->aout_scale) cudaFree(h->aout_scale);
   if (h->Linv32) cudaFree(h->Linv32);
   if (h->ST32) cudaFree(h->ST32);
   if (h->KufT32) cudaFree(h->KufT32);
@@ -225,7 +239,8 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (d->num_latents != d->num_experts * d->output_dim + d->num_gating) return bad("num_latents != K*F + G");
   if (d->num_latents > MAXP || d->num_groups > MAXQ || d->num_groups < 1) return bad("too many latents / groups");
   if (d->max_batch < 1) return bad("max_batch must be >= 1");
-  if (d->precision != MOGPE_PRECISION_F64 && d->precision != MOGPE_PRECISION_TF32) return bad("unknown precision");
+  if (d->precision != MOGPE_PRECISION_F64 && d->precision != MOGPE_PRECISION_TF32 && d->precision != MOGPE_PRECISION_INT8)
+    return bad("unknown precision");
   if (!d->group_num_inducing || !d->latent_group) return bad("null group_num_inducing / latent_group");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count <= d->device) {
@@ -255,7 +270,7 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   h->precision = d->precision;
   h->Mp = round_up(Mmax, 64);
   h->Mp32 = round_up(h->Mp, t32::BM);
-  h->Bp = round_up(d->max_batch, h->precision == MOGPE_PRECISION_TF32 ? t32::BN : 128);
+  h->Bp = round_up(d->max_batch, h->precision != MOGPE_PRECISION_F64 ? t32::BN : 128);
   h->Pe = d->num_experts * d->output_dim;
   const long long Q = d->num_groups, P = d->num_latents, Mp = h->Mp, D = d->input_dim;
   Layout& lo = h->lo;
@@ -986,6 +1001,103 @@ static mogpe_status conditional_fwd_t32(mogpe_handle* h, const double* params, c
   return MOGPE_OK;
 }
 
+// ---- INT8 mode (integer-sliced FP64-accurate products; gemm_i8.cuh) -----------------------------------------------------
+static mogpe_status ensure_i8(mogpe_handle* h) {
+  if (h->i8_ready) return MOGPE_OK;
+  const ModelDev& md = h->md_host;
+  const size_t Q = md.Q, P = md.P, M32 = h->Mp32, Bp = h->Bp, NS = oz::NS;
+  H_CUDA(h, dalloc(&h->Linv8, Q * NS * M32 * M32));
+  H_CUDA(h, dalloc(&h->ST8, P * NS * M32 * M32));
+  H_CUDA(h, dalloc(&h->KufT8, Q * NS * Bp * M32));
+  H_CUDA(h, dalloc(&h->AT8, Q * NS * Bp * M32));
+  H_CUDA(h, dalloc(&h->linv_scale, Q * M32));
+  H_CUDA(h, dalloc(&h->st_scale, P * M32));
+  H_CUDA(h, dalloc(&h->kuf_scale, Q));
+  H_CUDA(h, dalloc(&h->aout_scale, Q));
+  if (!h->alpha) H_CUDA(h, dalloc(&h->alpha, P * M32));
+  if (!h->d_t32_err) {
+    H_CUDA(h, dalloc(&h->d_t32_err, 1));
+    H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
+  }
+  if (!oz::make_map_i8(&h->tm_linv, h->Linv8, (int)Q, (int)M32, (int)M32, oz::BM) ||
+      !oz::make_map_i8(&h->tm_st, h->ST8, (int)P, (int)M32, (int)M32, oz::BM) ||
+      !oz::make_map_i8(&h->tm_kuf, h->KufT8, (int)Q, (int)Bp, (int)M32, oz::BN) ||
+      !oz::make_map_i8(&h->tm_at, h->AT8, (int)Q, (int)Bp, (int)M32, oz::BN))
+    H_FAIL(h, MOGPE_ERR_CUDA, "cuTensorMapEncodeTiled failed (INT8 mode needs a driver with TMA tensor maps)");
+  h->i8_ready = true;
+  return MOGPE_OK;
+}
+
+// After factorise(): row scales + byte planes of L^-1 and tril(q_sqrt)^T, group scales, alpha = L^-T q_mu.
+static mogpe_status i8_prepare(mogpe_handle* h, const double* params, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, Mp = h->Mp, M32 = h->Mp32;
+  oz::row_scale_kernel<<<dim3(M32, Q), 128, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1, h->linv_scale, M32);
+  oz::slice_square_kernel<<<dim3(M32 / 32, M32 / 32, Q), dim3(32, 8), 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1,
+                                                                              h->linv_scale, h->Linv8, M32);
+  if (md.nlta > 0) {
+    oz::row_scale_kernel<<<dim3(M32, md.nlta), 128, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0,
+                                                              h->st_scale, M32);
+    oz::slice_square_kernel<<<dim3(M32 / 32, M32 / 32, md.nlta), dim3(32, 8), 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp,
+                                                                                      h->d_lta_latent, 1, 0, h->st_scale,
+                                                                                      h->ST8, M32);
+  }
+  oz::group_scales_kernel<<<1, MAXQ, 0, st>>>(h->d_md, params, h->lo, h->kuf_scale, h->aout_scale);
+  t32::alpha_kernel<<<dim3(M32 / 128, md.NV), 128, 0, st>>>(h->d_md, h->Linv, h->V, M32, h->alpha);
+  KCOUNT(h, 6);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+static mogpe_status conditional_fwd_i8(mogpe_handle* h, const double* params, const double* X, int N, int Bc,
+                                       cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, M32 = h->Mp32, m_tiles = M32 / oz::BM;
+  const dim3 kg(Bc / 64, M32 / 128, Q);
+  if (md.D <= 2)
+    oz::kuf8_kernel<2><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, h->KufT8, h->alpha, h->dot_part, m_tiles);
+  else if (md.D <= 4)
+    oz::kuf8_kernel<4><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, h->KufT8, h->alpha, h->dot_part, m_tiles);
+  else if (md.D <= 8)
+    oz::kuf8_kernel<8><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, h->KufT8, h->alpha, h->dot_part, m_tiles);
+  else
+    oz::kuf8_kernel<16><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, h->KufT8, h->alpha, h->dot_part, m_tiles);
+  KCOUNT(h, 1);
+  H_CUDA(h, cudaGetLastError());
+  oz::Params p;
+  memset(&p, 0, sizeof(p));
+  p.m_tiles = m_tiles; p.K = M32; p.kmode = t32::K_LOWER;
+  p.a_scale = h->linv_scale; p.a_scale_stride = M32; p.b_scale = h->kuf_scale;
+  p.ss_part = h->ss_part; p.ld_ss = h->Bp; p.err_flag = h->d_t32_err;
+  if (md.nlta > 0) {
+    p.out = h->AT8; p.out_batch_stride = (long long)oz::NS * h->Bp * M32; p.out_plane_stride = (long long)h->Bp * M32; p.ldo = M32;
+    p.out_scale = h->aout_scale;
+  }
+  for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = g;
+  H_CUDA(h, oz::launch(h->tm_linv, h->tm_kuf, p, Bc / oz::BN, Q, st));  // A^T byte planes + sum_m A^2 partials
+  h->gemm_launches++;
+  KCOUNT(h, 1);
+  if (md.nlta > 0) {
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = m_tiles; p.K = M32; p.kmode = t32::K_UPPER;
+    p.a_scale = h->st_scale; p.a_scale_stride = M32; p.b_scale = h->aout_scale;
+    p.ss_part = h->lta_part; p.ld_ss = h->Bp; p.err_flag = h->d_t32_err;
+    for (int slot = 0; slot < md.nlta; slot++) {
+      p.mapA[slot] = slot;
+      p.mapB[slot] = md.lta_group[slot];
+    }
+    H_CUDA(h, oz::launch(h->tm_st, h->tm_at, p, Bc / oz::BN, md.nlta, st));  // sum_m (q_sqrt^T A)^2 partials
+    h->gemm_launches++;
+    KCOUNT(h, 1);
+  }
+  KCOUNT(h, 1);
+  stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + md.nlta), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, h->dot_part,
+                                                                           h->lta_part, m_tiles, h->Bp, h->var0ss, h->mean,
+                                                                           h->varq);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const double* params,
                                       double* f_mean, double* f_var, double* mix_probs, double* y_mean, double* y_var,
                                       const double* eps_mc, int32_t num_mc, void* cuda_stream) {
@@ -1003,21 +1115,22 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
   mogpe_status rc = set_mode(h, -1, 1, st);
   if (rc != MOGPE_OK) return rc;
   const int chunk_max = h->desc.max_batch;
-  const bool tf32 = h->precision == MOGPE_PRECISION_TF32;
+  const bool tf32 = h->precision == MOGPE_PRECISION_TF32, i8 = h->precision == MOGPE_PRECISION_INT8;
   {
     const int nc0 = (int)std::min<int64_t>(chunk_max, N);
-    if (tf32) {
-      rc = ensure_t32(h);
-      if (rc != MOGPE_OK) return rc;
-    }
-    rc = factorise(h, params, nullptr, 1, X, nc0, round_up(nc0, 128), st, !tf32);  // Kuf of the first chunk overlaps the chain
+    if (tf32) rc = ensure_t32(h);
+    if (i8) rc = ensure_i8(h);
+    if (rc != MOGPE_OK) return rc;
+    rc = factorise(h, params, nullptr, 1, X, nc0, round_up(nc0, 128), st, !tf32 && !i8);  // Kuf of the first chunk overlaps the chain
     if (rc == MOGPE_OK && tf32) rc = t32_prepare(h, st);
+    if (rc == MOGPE_OK && i8) rc = i8_prepare(h, params, st);
     if (rc != MOGPE_OK) return rc;
   }
   for (int64_t n0 = 0; n0 < N; n0 += chunk_max) {
     const int nc = (int)std::min<int64_t>(chunk_max, N - n0);
-    const int Bc = round_up(nc, tf32 ? t32::BN : 128);
+    const int Bc = round_up(nc, (tf32 || i8) ? t32::BN : 128);
     rc = tf32 ? conditional_fwd_t32(h, params, X + n0 * md.D, nc, Bc, st)
+         : i8 ? conditional_fwd_i8(h, params, X + n0 * md.D, nc, Bc, st)
               : conditional_fwd(h, params, X + n0 * md.D, nc, Bc, st, n0 == 0);
     if (rc != MOGPE_OK) return rc;
     PredArgs pa;

@@ -1,0 +1,367 @@
+// FP64-accurate batched GEMM on the sm_100a INT8 tensor cores (integer slicing, "Ozaki scheme"), for the same products as
+// gemm_tf32.cuh:   D[m][n] = sum_k Aop[m][k] * Bop[n][k],  both operands K-major.
+//
+// tcgen05.mma has no f64 kind and the FP64 DMMA pipe peaks at 37 TFLOP/s on this part, but kind::i8 multiplies signed bytes
+// with EXACT int32 accumulation in TMEM at 4.5 POP/s.  Every FP64 operand row is written as
+//      x = 2^e * sum_{p=0}^{NS-1} q_p * 2^(-7 (p + 1)),    q_p in [-64, 64]  (signed bytes),   |x| <= 2^(e-1)
+// (e: one power-of-two scale per operand row; successive round-to-nearest residuals), and the product is
+//      D[m][n] = 2^(ea[m] + eb[n]) * sum_{d=0}^{NS-1} 2^(-7 (d + 2)) * T_d[m][n],    T_d = sum_{i+j=d} sum_k qa_i[m][k] qb_j[n][k]
+// with every T_d an exact integer (|T_d| <= (d+1) K 2^12 << 2^31).  Only the slice pairs with i + j >= NS are dropped:
+// an error of ~ (NS+1) K 2^(-7 NS) relative to rowmax(A) * rowmax(B), i.e. 1e-13 for NS = 8, K = 1024 -- FP64-class, and
+// unlike a floating-point accumulation it does not grow with cancellation inside the sum.
+// Cost: NS (NS + 1) / 2 = 36 slice pairs per 32-wide k-step (INT8 K = 32 per instruction), issued as 12 wide MMAs (see the
+// MMA loop), against 4 DMMA k-steps of 8.
+//
+// Tile: D[128 x 64] per CTA, the NS accumulators T_0 .. T_7 occupy all 512 TMEM columns (8 x 64).  Pipeline stage = 64
+// k-values (64-byte rows, 64B swizzle): A [NS planes][128 rows][64 B] + B [NS][64 rows][64 B] = 96 KB, 2 stages; each stage
+// feeds 2 x 36 MMAs (>= 2300 tensor cycles), so two stages cover the TMA latency.  Same warp roles as gemm_tf32x3_kernel.
+// Epilogue: T_d -> FP64 (tcgen05.ld, 8 int->double conversions per element), row / column scales, column sums of squares in
+// FP64 (butterfly transpose-reduce), and optionally the tile re-sliced into NS byte planes, transposed ([n][m]), as the
+// B operand of the next product.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_tf32.cuh"  // mbarrier / TMA / descriptor helpers, tensor-map encoder
+
+namespace mogpe {
+namespace oz {
+
+constexpr int NS = 8;                 // byte slices per operand
+constexpr int BM = 128, BN = 64, BKB = 64, UKB = 32, STAGES = 2;
+constexpr int A_PLANE_BYTES = BM * BKB;            // 8 KB
+constexpr int B_PLANE_BYTES = BN * BKB;            // 4 KB
+constexpr int A_STAGE_BYTES = NS * A_PLANE_BYTES;  // 64 KB
+constexpr int B_STAGE_BYTES = NS * B_PLANE_BYTES;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int RED_BYTES = 4 * BN * 8;              // cross-warp column sums (FP64)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RED_BYTES + 1024 + 256;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = NS * BN;                 // 512
+
+struct Params {
+  int m_tiles;  // row tiles of 128
+  int K;        // reduction length (multiple of 64)
+  int kmode;    // t32::K_FULL / K_LOWER / K_UPPER
+  const double* a_scale;     // [A batches][m_tiles * 128]: 2^ea of each operand row
+  long long a_scale_stride;  // doubles per A batch
+  const double* b_scale;     // [B batches] (device): 2^eb, one scale for all rows of a B operand batch
+  int8_t* out;               // optional re-sliced TRANSPOSED result planes [batch][NS][n][ldo]
+  long long out_batch_stride, out_plane_stride;  // bytes
+  int ldo;
+  const double* out_scale;   // [batch] (device): 2^e of the re-sliced result (|D| / 2^e <= 1/2)
+  double* ss_part;           // optional [batch][m_tiles][ld_ss] column sums of squares per row tile
+  int ld_ss;
+  int* err_flag;
+  int mapA[64], mapB[64];
+};
+
+__device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
+  return (2u << 4)      // D = S32
+         | (1u << 7)    // A = signed int8
+         | (1u << 10)   // B = signed int8
+         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// Called by ALL lanes of the (converged) MMA warp: elect.sync picks the issuing lane, so the SASS is one predicated UTCIMMA
+// instead of the per-thread ELECT loop that a divergent `if (lane == 0)` region compiles to (these MMAs are only 32-48 cycles
+// long: the issue path must be short).
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(t32::smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32_i(uint32_t taddr, int* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// grid (m_tiles, n_tiles, batch): the row tiles of one column tile are neighbours in launch order (they share the B tile in L2)
+__global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                     const __grid_constant__ CUtensorMap mapB,
+                                                                     const __grid_constant__ Params p) {
+  using namespace t32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  double* red = reinterpret_cast<double*>(gbase + STAGES * STAGE_BYTES);  // [4][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + STAGES * STAGE_BYTES + RED_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y, batch = blockIdx.z;
+  const int m_tile = (p.kmode == K_UPPER) ? (int)blockIdx.x : p.m_tiles - 1 - (int)blockIdx.x;
+  const int m0 = m_tile * BM, n0 = n_tile * BN;
+  int k_begin = 0, k_end = p.K;
+  if (p.kmode == K_LOWER) k_end = min(p.K, m0 + BM);
+  if (p.kmode == K_UPPER) k_begin = m0 / BKB * BKB;
+  const int num_kb = (k_end - k_begin) / BKB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int ca = p.mapA[batch], cb = p.mapB[batch];
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1, p.err_flag);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        const int k0 = k_begin + kb * BKB;
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+        tma_load_4d(sa, &mapA, smem_u32(&full[s]), k0, m0, 0, ca);  // {k, m, slice, batch}: all NS planes in one copy
+        tma_load_4d(sb, &mapB, smem_u32(&full[s]), k0, n0, 0, cb);
+      }
+    }
+  } else if (warp == 1) {
+    // the whole warp runs the loop (converged); one elected lane issues
+    for (int kb = 0; kb < num_kb; kb++) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full[s], ph, p.err_flag);
+      tc_fence_after();
+      const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+      // K-major, 64B swizzle: 8-row groups 512 B apart; planes and the 32-byte k-step only move the start address field
+      const uint64_t ad0 = make_smem_desc(sa, 16, 8 * BKB, 4), bd0 = make_smem_desc(sb, 16, 8 * BKB, 4);
+      const uint32_t first = kb == 0 ? 0u : 1u;
+      // Slice i of A meets slices j = 0 .. NS-1-i of B, and pair (i, j) belongs to accumulator T_(i+j) = TMEM columns
+      // (i + j) * 64.  The B planes are contiguous in shared memory (plane j = rows 64 j .. 64 j + 63 of one tall K-major
+      // tile), so ONE wide MMA  A_i x [B_0; ...; B_(NS-1-i)]^T  with N = 64 (NS - i) columns starting at TMEM column 64 i
+      // covers all pairs of slice i (split in two when N > 256): 12 MMAs per k-step instead of 36, and A_i is read from
+      // shared memory once instead of NS - i times (the 36-MMA version was bound by that re-read, 63 instead of 32 cycles
+      // per 64 columns).  Slice 0 goes first and overwrites every accumulator on the very first k-step.
+#pragma unroll
+      for (int j = 0; j < BKB / UKB; j++) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          const uint64_t ad = ad0 + (uint64_t)((i * A_PLANE_BYTES + j * UKB) >> 4);
+#pragma unroll
+          for (int c0 = 0; c0 < BN * (NS - i); c0 += 256) {
+            const int n1 = BN * (NS - i) - c0 < 256 ? BN * (NS - i) - c0 : 256;
+            const uint64_t bd = bd0 + (uint64_t)((c0 * BKB + j * UKB) >> 4);
+            umma_i8(tmem_base + (uint32_t)(i * BN + c0), ad, bd, make_idesc_i8(n1), (j == 0 && i == 0) ? first : 1u);
+          }
+        }
+      }
+      __syncwarp();
+      umma_commit_elect(&empty[s]);
+    }
+    umma_commit_elect(acc_full);
+  } else {
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0, p.err_flag);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    // 2^(ea + eb) * 2^(-14): T_d carries 2^(-7 (d + 2))
+    const double rs = p.a_scale[(long long)p.mapA[batch] * p.a_scale_stride + row] * p.b_scale[p.mapB[batch]] * (1.0 / 16384.0);
+    int8_t* ocol = nullptr;
+    if (p.out) ocol = p.out + (long long)batch * p.out_batch_stride + (long long)n0 * p.ldo + row;
+    const double oinv = p.out ? 1.0 / p.out_scale[batch] : 0.0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      double v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = 0.0;
+      double w = 1.0;
+#pragma unroll 1
+      for (int d = 0; d < NS; d++) {
+        int t[32];
+        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), t);
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = fma((double)t[i], w, v[i]);
+        w *= 1.0 / 128.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] *= rs;
+      if (p.out) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          double r = v[i] * oinv;  // |r| <= 1/2
+          int8_t* o = ocol + (long long)(c * 32 + i) * p.ldo;
+#pragma unroll
+          for (int s = 0; s < NS; s++) {
+            const double tt = r * 128.0;
+            const int qv = __double2int_rn(tt);
+            r = tt - (double)qv;
+            o[(long long)s * p.out_plane_stride] = (int8_t)qv;
+          }
+        }
+      }
+      if (p.ss_part) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] *= v[i];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < o; i++) {
+            const double send = up ? v[i] : v[i + o];
+            const double keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        red[q * BN + c * 32 + lane] = v[0];
+      }
+    }
+    tc_fence_before();
+    if (p.ss_part) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int tt = threadIdx.x - 64;
+      if (tt < BN) {
+        double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
+        dst[tt] = (red[tt] + red[BN + tt]) + (red[2 * BN + tt] + red[3 * BN + tt]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// byte planes [batch][NS][rows][cols] (cols = k contiguous): box {64 k, box_rows, NS planes, 1}, 64B swizzle
+inline bool make_map_i8(CUtensorMap* map, const int8_t* ptr, int batch, int rows, int cols, int box_rows) {
+  t32::EncodeTiledFn fn = t32::encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)NS, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)cols, (cuuint64_t)rows * cols, (cuuint64_t)NS * rows * cols};
+  cuuint32_t box[4] = {BKB, (cuuint32_t)box_rows, NS, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& p, int n_tiles, int batch,
+                          cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gemm_i8_sliced_kernel<<<dim3(p.m_tiles, n_tiles, batch), THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
+  return cudaGetLastError();
+}
+
+// ---- slicing of FP64 operands -------------------------------------------------------------------------------------
+// 2^e with 2^(e-1) >= x (so that |x| / 2^e <= 1/2); 1 for x == 0
+__host__ __device__ inline double pow2_scale(double maxabs) {
+  if (!(maxabs > 0.0)) return 1.0;
+  int e;
+  frexp(maxabs, &e);          // maxabs = f * 2^e, f in [0.5, 1)
+  return ldexp(1.0, e + 1);   // maxabs < 2^e  ->  maxabs / 2^(e+1) < 1/2
+}
+
+__device__ __forceinline__ void slice8(double x, double inv_scale, int8_t* q) {
+  double r = x * inv_scale;
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const double t = r * 128.0;
+    const int v = __double2int_rn(t);
+    r = t - (double)v;
+    q[s] = (int8_t)v;
+  }
+}
+
+// Row scales of src(r, :) (or of src(:, r) when transposed): scale[b][r] = pow2_scale(max |.|), 1 for padded rows.
+// lower_only: entries above the diagonal of src are ignored (treated as zero).   grid (rows_p, batch), block 128
+__global__ void __launch_bounds__(128) row_scale_kernel(const double* __restrict__ src, int n, long long src_batch_stride,
+                                                        int src_ld, const int* __restrict__ map, int transposed,
+                                                        int lower_only, double* __restrict__ scale, int rows_p) {
+  __shared__ double red[4];
+  const int r = blockIdx.x, b = blockIdx.y, sb = map ? map[b] : b;
+  double m = 0.0;
+  if (r < n) {
+    const double* s = src + (long long)sb * src_batch_stride;
+    for (int c = threadIdx.x; c < n; c += 128) {
+      const int rr = transposed ? c : r, cc = transposed ? r : c;  // element (r, c) of the operand = src(rr, cc)
+      if (lower_only && cc > rr) continue;
+      m = fmax(m, fabs(s[(long long)rr * src_ld + cc]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) scale[(long long)b * rows_p + r] = pow2_scale(fmax(fmax(red[0], red[1]), fmax(red[2], red[3])));
+}
+
+// dst [batch][NS][n_p][n_p] byte planes of the operand (r, c) -> src(r, c) or src(c, r) (transposed), zero padded, each
+// row sliced against its own scale.   grid (n_p/32, n_p/32, batch), block (32, 8)
+__global__ void slice_square_kernel(const double* __restrict__ src, int n, long long src_batch_stride, int src_ld,
+                                    const int* __restrict__ map, int transposed, int lower_only,
+                                    const double* __restrict__ scale, int8_t* __restrict__ dst, int n_p) {
+  __shared__ double tile[32][33];
+  const int b = blockIdx.z, sb = map ? map[b] : b;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const double* s = src + (long long)sb * src_batch_stride;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    // coalesced read of src: operand rows r0.. / cols c0..  = src rows (transposed ? c0.. : r0..)
+    const int sr = (transposed ? c0 : r0) + j, sc = (transposed ? r0 : c0) + threadIdx.x;
+    double x = 0.0;
+    if (sr < n && sc < n && !(lower_only && sc > sr)) x = s[(long long)sr * src_ld + sc];
+    tile[j][threadIdx.x] = x;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    const double x = transposed ? tile[threadIdx.x][j] : tile[j][threadIdx.x];
+    int8_t qv[NS];
+    slice8(x, 1.0 / scale[(long long)b * n_p + r], qv);
+    int8_t* d = dst + ((long long)b * NS * n_p + r) * n_p + c;
+#pragma unroll
+    for (int p2 = 0; p2 < NS; p2++) d[(long long)p2 * n_p * n_p] = qv[p2];
+  }
+}
+
+}  // namespace oz
+}  // namespace mogpe

@@ -113,3 +113,93 @@ __global__ void __launch_bounds__(128) kuf32_kernel(const ModelDev* __restrict__
 
 }  // namespace t32
 }  // namespace mogpe
+
+// ---- INT8 (integer-sliced, FP64-accurate) mode: gemm_i8.cuh -------------------------------------------------------------
+#include "gemm_i8.cuh"
+
+namespace mogpe {
+namespace oz {
+
+// Per-group scales of the sliced operands: kuf_scale[g] = 2^e >= 2 kvar (|Kuf| <= kvar), a_scale[g] = 2^e >= 2 sqrt(kvar)
+// (sum_m A[m][n]^2 <= kvar, so |A| <= sqrt(kvar)).   one block, Q threads
+__global__ void group_scales_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
+                                    double* __restrict__ kuf_scale, double* __restrict__ a_scale) {
+  const int g = threadIdx.x;
+  if (g >= md->Q) return;
+  const double kv = params[lo.kvar + g];
+  kuf_scale[g] = pow2_scale(kv);
+  a_scale[g] = pow2_scale(sqrt(kv));
+}
+
+// Kuf^T in NS byte planes + the FP64 mean partials (same roles as t32::kuf32_kernel).
+//   KufT8[g][plane][n][k]: slices of k(z_k, x_n) / kuf_scale[g];   dot_part[v][blockIdx.y][n] = sum_k Kuf[k][n] alpha[v][k]
+// grid (Bc/64, Mp32/128, Q), block 128: warp w handles points n_base + w, w + 4, ...; lane covers the FOUR CONSECUTIVE
+// inducing indices k0 + 4 lane .. + 3, so the four bytes of a plane go out as one 32-bit store (128 B per warp).
+template <int DMAX>
+__global__ void __launch_bounds__(128) kuf8_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                   Layout lo, const double* __restrict__ X, int N, int Bp, int Mp32,
+                                                   const double* __restrict__ kuf_scale, int8_t* __restrict__ KufT,
+                                                   const double* __restrict__ alpha, double* __restrict__ dot_part, int rbn) {
+  const int g = blockIdx.z, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.y * 128 + 4 * lane;
+  const double* ls = params + lo.ls + (long long)g * D;
+  const double* Z = params + lo.Z + (long long)g * Mp * D;
+  const double kv = params[lo.kvar + g];
+  const double inv_scale = 1.0 / kuf_scale[g];
+  double il[DMAX];  // 1 / lengthscale: one FP64 division per thread instead of D per point (1 ulp from x / l)
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) il[d] = d < D ? 1.0 / ls[d] : 0.0;
+  double z[4][DMAX], zn[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int k = k0 + j;
+    zn[j] = 0.0;
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) {
+      z[j][d] = (d < D && k < Mg) ? Z[(long long)k * D + d] * il[d] : 0.0;
+      zn[j] += z[j][d] * z[j][d];
+    }
+  }
+  const int v0 = md->gvec_begin[g], nv = md->gvec_begin[g + 1] - v0;
+  int8_t* base = KufT + (long long)g * NS * Bp * Mp32;
+  const long long plane = (long long)Bp * Mp32;
+  for (int i = warp; i < 64; i += 4) {
+    const int n = blockIdx.x * 64 + i;
+    const bool valid = n < N;
+    double x[DMAX], xn = 0.0;
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) {
+      x[d] = (valid && d < D) ? X[(long long)n * D + d] * il[d] : 0.0;
+      xn += x[d] * x[d];
+    }
+    double kval[4];
+    uint32_t packed[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) packed[s] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      double dot = 0.0;
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) dot += z[j][d] * x[d];
+      const double r2 = -2.0 * dot + (zn[j] + xn);
+      kval[j] = (valid && k0 + j < Mg) ? kv * exp(-0.5 * r2) : 0.0;
+      int8_t q[NS];
+      slice8(kval[j], inv_scale, q);
+#pragma unroll
+      for (int s = 0; s < NS; s++) packed[s] |= (uint32_t)(uint8_t)q[s] << (8 * j);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) *reinterpret_cast<uint32_t*>(base + s * plane + (long long)n * Mp32 + k0) = packed[s];
+    for (int q2 = 0; q2 < nv; q2++) {
+      const int v = md->gvec[v0 + q2];
+      const double* av = alpha + (long long)v * Mp32 + k0;
+      double s = kval[0] * av[0] + kval[1] * av[1] + kval[2] * av[2] + kval[3] * av[3];
+      s = warp_sum(s);
+      if (lane == 0) dot_part[((long long)v * rbn + blockIdx.y) * Bp + n] = s;
+    }
+  }
+}
+
+}  // namespace oz
+}  // namespace mogpe

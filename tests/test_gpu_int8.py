@@ -1,0 +1,76 @@
+"""GPU parity tests of the INT8 mode: the M x M x N products of predict on the INT8 tensor cores with integer-sliced FP64
+operands and exact int32 accumulation (mogpe_b200/csrc/gemm_i8.cuh).  It is an FP64-accurate mode, so it is held to the
+float64 tolerance of BASELINE.json's north star: predictive mean / variance and mixing probabilities within 1e-8 relative
+of the oracle -- on the same ill-conditioned default specs as the FP64 path (lengthscales up to 3, jitter 1e-6)."""
+import numpy as np
+import pytest
+
+from tests._specs import make_spec
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+@pytest.mark.parametrize("flavour", ["keras", "legacy"])
+@pytest.mark.parametrize("K,F,sep,M,N,max_batch,D", [
+    (2, 1, False, 25, 333, 128, 2),     # Bernoulli gating, one row tile, 2 chunks (ragged tail)
+    (3, 1, False, 70, 300, 512, 2),     # Softmax gating
+    (2, 2, True, 150, 700, 256, 2),     # separate kernels per output, two row tiles, 3 chunks
+    (3, 2, False, 260, 520, 1024, 2),   # three row tiles
+    (2, 1, False, 512, 600, 1024, 4),   # four row tiles, D = 4
+])
+def test_int8_predict_matches_oracle(flavour, K, F, sep, M, N, max_batch, D):
+    from oracle import ref_numpy as rn
+    from tests._engine_helpers import engine_from_spec
+
+    spec, X, Y, eps = make_spec(seed=40 + K + F, N=N, D=D, F=F, K=K, M=M, flavour=flavour, separate_kernels=sep)
+    eng = engine_from_spec(spec, max_batch=max_batch, precision="int8")
+    eps_mc = np.random.default_rng(3).standard_normal((17, N, K)) if K > 2 else None
+    out = eng.predict(X, eps_mc=eps_mc)
+    pi = rn.predict_mixing_probs(spec, X, eps_mc)
+    ym, yv = rn.predict_y(spec, X, eps_mc)
+    assert _rel(out["mix_probs"], pi) < RTOL
+    assert _rel(out["y_mean"], ym) < RTOL
+    assert _rel(out["y_var"], yv) < RTOL
+    l = 0
+    for gp in spec["experts"] + [spec["gating"]]:
+        fm, fv = rn.predict_f(gp, X)
+        L = fm.shape[1]
+        assert _rel(out["f_mean"][:, l:l + L], fm) < RTOL
+        assert _rel(out["f_var"][:, l:l + L], fv) < RTOL
+        l += L
+    eng.close()
+
+
+def test_int8_engine_is_a_different_code_path_from_float64():
+    from tests._engine_helpers import engine_from_spec
+
+    spec, X, Y, eps = make_spec(seed=77, N=900, D=3, F=1, K=2, M=200)
+    e64 = engine_from_spec(spec, max_batch=512)
+    e8 = engine_from_spec(spec, max_batch=512, precision="int8")
+    a, b = e64.predict(X), e8.predict(X)
+    for k in ("f_mean", "f_var", "y_var", "y_mean", "mix_probs"):
+        assert _rel(b[k], a[k]) < RTOL, k
+    assert not np.array_equal(a["f_var"], b["f_var"])  # bitwise-identical variances would mean the flag was ignored
+    e64.close()
+    e8.close()
+
+
+def test_public_api_int8_precision():
+    from oracle import ref_numpy as rn
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=61, N=300, D=2, F=1, K=2, M=40)
+    model = model_from_spec(spec)
+    model.set_precision("int8")
+    d = model.predict_y(X)
+    ym, yv = rn.predict_y(spec, X)
+    assert _rel(d.mean(), ym) < RTOL and _rel(d.variance(), yv) < RTOL
+    val = model.maximum_log_likelihood_objective((X, Y), eps=eps)  # training stays on the FP64 DMMA path
+    assert abs(val - rn.elbo(spec, X, Y, eps)) <= RTOL * abs(val)
