@@ -159,7 +159,7 @@ static cudaError_t dalloc(T** p, size_t n) {
   return cudaMalloc((void**)p, n * sizeof(T));
 }
 
-extern "C" const char* mogpe_version(void) { return "mogpe_b200 0.2 (sm_100a: fp64 DMMA, tf32 tcgen05)"; }
+extern "C" const char* mogpe_version(void) { return "mogpe_b200 0.3 (sm_100a: fp64 DMMA; tcgen05 tf32x3 and int8-sliced)"; }
 
 extern "C" const char* mogpe_last_error(const mogpe_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 

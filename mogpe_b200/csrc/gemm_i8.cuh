@@ -205,20 +205,35 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
     const double oinv = p.out ? 1.0 / p.out_scale[batch] : 0.0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; c++) {
+      // sum_d T_d 128^-d, exactly: two int64 Horner sums (T_0..T_3 and T_4..T_7; |sum| < 2^50), two int -> double
+      // conversions per element instead of eight
       double v[32];
-#pragma unroll
-      for (int i = 0; i < 32; i++) v[i] = 0.0;
-      double w = 1.0;
-#pragma unroll 1
-      for (int d = 0; d < NS; d++) {
+      {
+        long long acc[32];
         int t[32];
-        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), t);
+        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), t);
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = fma((double)t[i], w, v[i]);
-        w *= 1.0 / 128.0;
+        for (int i = 0; i < 32; i++) acc[i] = t[i];
+#pragma unroll 1
+        for (int d = 1; d < 4; d++) {
+          tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), t);
+#pragma unroll
+          for (int i = 0; i < 32; i++) acc[i] = acc[i] * 128 + t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = (double)acc[i] * (1.0 / 2097152.0);  // 128^-3
+        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * BN + c * 32), t);
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[i] = t[i];
+#pragma unroll 1
+        for (int d = 5; d < 8; d++) {
+          tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), t);
+#pragma unroll
+          for (int i = 0; i < 32; i++) acc[i] = acc[i] * 128 + t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = fma((double)acc[i], 1.0 / 562949953421312.0 /* 128^-7 */, v[i]) * rs;
       }
-#pragma unroll
-      for (int i = 0; i < 32; i++) v[i] *= rs;
       if (p.out) {
 #pragma unroll
         for (int i = 0; i < 32; i++) {
@@ -226,10 +241,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
           int8_t* o = ocol + (long long)(c * 32 + i) * p.ldo;
 #pragma unroll
           for (int s = 0; s < NS; s++) {
+            // round to nearest with the 1.5 * 2^52 trick: the low word of y holds the integer, no conversion instructions
             const double tt = r * 128.0;
-            const int qv = __double2int_rn(tt);
-            r = tt - (double)qv;
-            o[(long long)s * p.out_plane_stride] = (int8_t)qv;
+            const double y = tt + 6755399441055744.0;
+            r = tt - (y - 6755399441055744.0);
+            o[(long long)s * p.out_plane_stride] = (int8_t)__double2loint(y);
           }
         }
       }

@@ -155,8 +155,9 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    for (int variant = 0; variant < 2; variant++) {
-      p.out = variant ? O8 : nullptr;
+    for (int variant = 0; variant < 3; variant++) {
+      p.out = variant == 1 ? O8 : nullptr;
+      p.ss_part = variant == 2 ? nullptr : ss;
       oz::launch(mapA, mapB, p, N / oz::BN, batch, 0);
       cudaEventRecord(e0);
       for (int r = 0; r < reps; r++) oz::launch(mapA, mapB, p, N / oz::BN, batch, 0);
@@ -167,7 +168,7 @@ int main(int argc, char** argv) {
       const double frac = kmode == 0 ? 1.0 : 0.5;
       const double flops = 2.0 * M * (double)K * N * batch * frac;
       printf("%s: %.3f ms/launch, %.1f TFLOP/s FP64-equivalent algorithmic (x%d INT8 MMAs: %.0f TOP/s)\n",
-             variant ? "with re-sliced output" : "stats only", ms / reps, flops / (ms / reps * 1e-3) * 1e-12, oz::NS * (oz::NS + 1) / 2,
+             variant == 1 ? "with re-sliced output" : variant == 2 ? "no epilogue outputs (main loop + TMEM read + combine only)" : "stats only", ms / reps, flops / (ms / reps * 1e-3) * 1e-12, oz::NS * (oz::NS + 1) / 2,
              oz::NS * (oz::NS + 1) / 2 * flops / (ms / reps * 1e-3) * 1e-12);
     }
   }
