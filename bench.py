@@ -202,6 +202,55 @@ class ClockSampler:
         return out
 
 
+def run_predict_modes(device, n_points=262144, M=1024):
+    """The other data path of the north star (BASELINE config 5: predict_y + predict_mixing_probs, K = 8, G = 8, M = 1024) on a
+    bounded sample of test points, once per arithmetic mode of the dense products: FP64 DMMA, INT8 tensor cores with
+    integer-sliced operands (FP64-accurate), 3xTF32 tensor cores.  Points are generated on the device; CUDA-event time."""
+    import torch
+
+    from mogpe_b200 import _lib
+    from mogpe_b200.device import DeviceBuffer
+    from mogpe_b200.engine import Engine
+
+    wl = dict(D=4, F=1, K=8, M=M, batch=65536, num_data=n_points, sep=False)
+    spec = synth_model(wl, seed=4)
+    experts, gating = blocks_from_spec(spec)
+    lib = _lib.load()
+    out = {"workload": f"C5 sample: predict_y + predict_mixing_probs, D=4 K=8 G=8 M={M}, {n_points} test points in 65536-point "
+                       "chunks, 100 Softmax Monte-Carlo draws per point from the library stream", "unit": "points/s"}
+    ref = None
+    for precision in ("float64", "int8", "tf32"):
+        eng = Engine(experts, gating, flavour="keras", max_batch=65536, precision=precision, device=device)
+        X = DeviceBuffer((n_points, 4), device, zero=False)
+        eng.fill_normal(X, seed=4)
+        ym, yv, mix = (DeviceBuffer(s, device, zero=False) for s in ((n_points, 1), (n_points, 1), (n_points, 8)))
+
+        def run():
+            _lib.check(lib.mogpe_predict(eng.h, X.ptr, n_points, eng.params.ptr, None, None, mix.ptr, ym.ptr, yv.ptr,
+                                         None, 100, None), eng.h)
+
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        eng.set_seed(0)  # same Monte-Carlo draws for the accuracy comparison below
+        run()
+        got = np.concatenate([ym.numpy(), yv.numpy()], 1)
+        if ref is None:
+            ref = got
+        flops = 16 * 2.0 * M * M * n_points  # (P_e + P_g) * 2 M^2 per point (SURVEY 8d)
+        out[precision] = {"value": n_points / (ms * 1e-3), "ms": ms, "algorithmic_tflops": flops / ms * 1e-9,
+                          "frac_of_fp64_tensor_peak": flops / ms * 1e-9 / FP64_TENSOR_PEAK_TFLOPS,
+                          "max_rel_diff_vs_float64": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))}
+        eng.close()
+        del X, ym, yv, mix
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,6 +259,7 @@ def main():
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-predict", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -389,6 +439,8 @@ def main():
         k: {"us_per_step": 1e3 * ms_k / steps, "achieved": by / (ms_k * 1e-3) * 1e-9, "peak": hbm, "unit": "GB/s",
             "frac": by / (ms_k * 1e-3) * 1e-9 / hbm}
         for k, (ms_k, by) in stream_prof.items() if ms_k > 0}
+    if world == 1 and not args.no_predict:
+        line["predict"] = run_predict_modes(local_rank)
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = run_cpu_reference(wl, spec, 3, 1, wl["cpu_rows"])
         line["cpu_baseline"] = cb
