@@ -74,3 +74,24 @@ def test_public_api_int8_precision():
     assert _rel(d.mean(), ym) < RTOL and _rel(d.variance(), yv) < RTOL
     val = model.maximum_log_likelihood_objective((X, Y), eps=eps)  # training stays on the FP64 DMMA path
     assert abs(val - rn.elbo(spec, X, Y, eps)) <= RTOL * abs(val)
+
+
+@pytest.mark.parametrize("precision,rtol", [("int8", 1e-8), ("tf32", 1e-3)])
+@pytest.mark.parametrize("N,M,D,max_batch", [
+    (1, 3, 1, 16),        # a single test point, three inducing points (one padded row tile)
+    (256, 128, 8, 256),   # exactly one full column tile / one full row tile, D = 8
+    (513, 129, 3, 256),   # one point and one inducing point past the tile boundaries
+])
+def test_tensor_core_modes_edge_shapes(precision, rtol, N, M, D, max_batch):
+    from oracle import ref_numpy as rn
+    from tests._engine_helpers import engine_from_spec
+
+    spec, X, Y, eps = make_spec(seed=90 + N, N=max(N, M), D=D, F=1, K=2, M=M, ls_range=(0.3, 1.0))
+    X = X[:N]
+    eng = engine_from_spec(spec, max_batch=max_batch, precision=precision)
+    out = eng.predict(X)
+    ym, yv = rn.predict_y(spec, X)
+    pi = rn.predict_mixing_probs(spec, X)
+    assert out["y_mean"].shape == (N, 1) and out["mix_probs"].shape == (N, 2)
+    assert _rel(out["y_mean"], ym) < rtol and _rel(out["y_var"], yv) < rtol and _rel(out["mix_probs"], pi) < rtol
+    eng.close()
