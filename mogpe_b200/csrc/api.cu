@@ -455,6 +455,16 @@ static mogpe_status set_mode(mogpe_handle* h, int bound, int S, cudaStream_t st)
   return MOGPE_OK;
 }
 
+// Split-K factor for the [M x M] (lower-triangular) results that are reduced over the Bc minibatch columns: with small M
+// there are too few output tiles to fill the machine (C3: 50 CTAs, C2: 18), so the reduction is cut across CTAs until about
+// 148 SMs x 4 resident CTAs are busy, keeping at least 8 k-tiles of 32 per piece.
+static int reduce_ksplit(int Mp, int batch, int Bc) {
+  const int t = Mp / 64, tiles = t * (t + 1) / 2 * batch;
+  if (tiles >= 400) return 1;
+  const int want = (592 + tiles - 1) / tiles, cap = std::max(1, Bc / 256);
+  return std::max(1, std::min(want, cap));
+}
+
 static GemmParams gp_init() {
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -774,6 +784,8 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.B = h->A; p.sB = (long long)Mp * Bp; p.ldb = Bp;
     p.C = h->Lbar; p.sC = (long long)Mp * Mp; p.ldc = Mp;
     p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = -1.0;
+    p.ksplit = reduce_ksplit(Mp, Q, Bc);
+    if (p.ksplit > 1) H_CUDA(h, cudaMemsetAsync(h->Lbar, 0, sizeof(double) * (size_t)Q * Mp * Mp, st));
     H_CUDA(h, hgemm(h, p, Q, false, true, st, (double)Q * Mp * Mp * Bc));
   }
   if (md.nlta > 0) {
@@ -784,6 +796,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.C = grads + lo.q_sqrt; p.sC = (long long)Mp * Mp; p.ldc = Mp; p.mapC = h->d_lta_latent;
     p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = 2.0; p.beta = 1.0;
     p.kscale = h->dfvar; p.sks = Bp; p.mapK = h->d_lta_latent;
+    p.ksplit = reduce_ksplit(Mp, md.nlta, Bc);  // beta = 1: the partial sums are added onto the KL gradient already there
     H_CUDA(h, hgemm(h, p, md.nlta, false, true, st, (double)md.nlta * Mp * Mp * Bc));
   }
   q_grads_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, lo, h->dV, eps_u, S, grads);

@@ -54,6 +54,10 @@ struct GemmParams {
   // and statistics row-block indices are absolute).  row_base must be a multiple of the row tile.
   int row_base;
   int M_total;              // 0 -> M
+  // split-K: the k range of every output tile is cut into `ksplit` pieces handled by different CTAs, which ADD
+  // alpha * partial into C with FP64 atomics (C must hold the beta-scaled prior value: zeros for beta = 0, set by the
+  // launcher).  For [M x M] results reduced over the batch dimension when M is small: 50 CTAs cannot fill 148 SMs.
+  int ksplit;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -135,14 +139,15 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
   static_assert(Cfg::MI % 4 == 0, "fragment quarters");
   extern __shared__ __align__(16) double smem[];
 
-  const int batch = blockIdx.z;
+  const int ks = p.ksplit > 1 ? p.ksplit : 1;
+  const int batch = blockIdx.z / ks, split = blockIdx.z % ks;
   // heavier (lower) row blocks first for lower-triangular left operands
   const int brow = (p.kmode & KM_LEFT_LOWER) ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
   const int bcol = blockIdx.x;
   const int row0 = p.row_base + brow * BM, col0 = bcol * BN;
   if (p.tril_out && col0 > row0 + BM - 1) {
     // strictly-upper tile of a lower-triangular result: exact zeros (consumers read whole tiles)
-    if (p.beta == 0.0) {
+    if (p.beta == 0.0 && ks == 1) {
       double* Cz = p.C + (long long)(p.mapC ? p.mapC[batch] : batch) * p.sC;
       for (int t = threadIdx.x; t < BM * BN; t += blockDim.x)
         Cz[(long long)(row0 + t / BN) * p.ldc + col0 + (t % BN)] = 0.0;
@@ -156,7 +161,13 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
   if (p.kmode & KM_RIGHT_LOWER) k_begin = max(k_begin, col0);
   if (p.kmode & KM_RIGHT_UPPER) k_end = min(k_end, col0 + BN);
   k_begin = (k_begin / BK) * BK;
-  const int nk = (k_end > k_begin) ? (k_end - k_begin + BK - 1) / BK : 0;
+  int nk = (k_end > k_begin) ? (k_end - k_begin + BK - 1) / BK : 0;
+  if (ks > 1) {  // this CTA's share of the k tiles
+    const int per = (nk + ks - 1) / ks, kt0 = split * per, kt1 = min(nk, kt0 + per);
+    k_begin += kt0 * BK;
+    nk = max(0, kt1 - kt0);
+    if (nk == 0) return;
+  }
 
   const double* __restrict__ Ab = p.A + (long long)(p.mapA ? p.mapA[batch] : batch) * p.sA;
   const double* __restrict__ Bb = p.B + (long long)(p.mapB ? p.mapB[batch] : batch) * p.sB;
@@ -317,6 +328,11 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, TA, TB, STAGES>::T
       double2 v;
       v.x = p.alpha * acc[i][j][0];
       v.y = p.alpha * acc[i][j][1];
+      if (ks > 1) {
+        if (!p.tril_out || c <= r) atomicAdd(&dst->x, v.x);
+        if (!p.tril_out || c + 1 <= r) atomicAdd(&dst->y, v.y);
+        continue;
+      }
       if (p.beta != 0.0) {
         const double2 o = *dst;
         v.x += p.beta * o.x;
@@ -343,7 +359,9 @@ inline cudaError_t launch_gemm_cfg(const GemmParams& p, int batch, cudaStream_t 
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid(p.N / BN, p.M / BM, batch);
+  const int ks = p.ksplit > 1 ? p.ksplit : 1;
+  if (ks > 1 && (STATS || p.stat_ss || (p.beta != 0.0 && p.beta != 1.0))) return cudaErrorInvalidValue;
+  dim3 grid(p.N / BN, p.M / BM, batch * ks);
   GemmParams q = p;
   q.stat_rowblocks = (p.M_total ? p.M_total : p.M) / BM;
   if (p.row_base % BM) return cudaErrorInvalidValue;
