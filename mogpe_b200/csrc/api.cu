@@ -637,9 +637,11 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
   return MOGPE_OK;
 }
 
-static int lik_block(int slots) {
+// One thread per data point with a long serial body: prefer more, smaller blocks until every SM has work
+// (8192 points in 128-thread blocks are only 64 CTAs for 148 SMs).
+static int lik_block(int slots, int Bc) {
   int b = 128;
-  while (b > 32 && (size_t)slots * b * sizeof(double) > 160 * 1024) b >>= 1;
+  while (b > 32 && ((size_t)slots * b * sizeof(double) > 160 * 1024 || Bc / b < 2 * 148)) b >>= 1;
   return b;
 }
 
@@ -714,7 +716,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   la.dmean = h->dmean; la.dfvar = h->dfvar; la.out = out; la.grads = grads;
   {
     const int slots = 4 * S * md.K + md.Pe + 6 * md.K;
-    const int blk = lik_block(slots);
+    const int blk = lik_block(slots, Bc);
     const size_t smem = (size_t)slots * blk * sizeof(double);
     static size_t lik_smem_set = 0;
     if (smem > lik_smem_set) {
@@ -772,10 +774,15 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   {
     cudaStream_t ks = h->prof ? st : h->side;  // profiling: alone on the caller's stream
     sk_begin(h, SK_KUF_GRAD, ks);
+    // column slices so that at least ~6 blocks per SM are in flight (C4: 1 slice; C3: 6; C2: 8), >= 1024 columns each
+    const int blocks = (Mp / 8) * Q;
+    int nsplit = std::max(1, std::min((888 + blocks - 1) / blocks, (N + 1023) / 1024));
+    const int n_chunk = round_up((N + nsplit - 1) / nsplit, 32);
+    nsplit = (N + n_chunk - 1) / n_chunk;
     if (md.D <= 4)
-      kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+      kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q, nsplit), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads, n_chunk);
     else
-      kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads);
+      kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q, nsplit), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads, n_chunk);
     sk_end(h, SK_KUF_GRAD, ks, 8.0 * Q * (2.0 * Mp * N + (double)N * md.D));  // read W and Kuf, X
   }
   {  // Lbar = -tril(W A^T)

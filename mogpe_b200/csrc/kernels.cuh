@@ -609,11 +609,14 @@ template <int DMAX, int ROWS>
 __global__ void __launch_bounds__(256) kuf_grad_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
                                                        Layout lo, const double* __restrict__ X, int N, int Bp,
                                                        const double* __restrict__ W, const double* __restrict__ Kuf,
-                                                       double* __restrict__ grads) {
+                                                       double* __restrict__ grads, int n_chunk) {
   const int g = blockIdx.y, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = (blockIdx.x * 8 + warp) * ROWS;
   if (m0 >= Mg) return;
+  // blockIdx.z: slice of the data columns (small models have too few rows to fill the machine; every output is an
+  // atomicAdd already, so slices simply add up)
+  const int n_lo = blockIdx.z * n_chunk, n_hi = min(N, n_lo + n_chunk);
   const double* ls = params + lo.ls + (long long)g * D;
   double zz[ROWS][DMAX], a1[ROWS][DMAX], a2[ROWS][DMAX], se[ROWS];
 #pragma unroll
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(256) kuf_grad_kernel(const ModelDev* __restric
   const double* w = W + ((long long)g * Mp + m0) * Bp;
   const double* kf = Kuf + ((long long)g * Mp + m0) * Bp;
 #pragma unroll(8 / ROWS)
-  for (int n = lane; n < N; n += 32) {
+  for (int n = n_lo + lane; n < n_hi; n += 32) {
     double x[DMAX], e[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; r++) e[r] = w[(long long)r * Bp + n] * kf[(long long)r * Bp + n];  // rows >= Mg: Kuf = 0

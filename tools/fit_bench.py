@@ -14,7 +14,7 @@ B = wl["batch"]
 X, Y = bench.synth_batch(wl, B * 4, seed=1)
 X = np.concatenate([X] * ((steps + 3) // 4 + 1))[: steps * B]
 Y = np.concatenate([Y] * ((steps + 3) // 4 + 1))[: steps * B]
-for graphs in (False, True, False, True):
+for graphs in (0, 2, 0, 2):  # 0 = direct launches, 2 = always replay as a CUDA graph (1 = automatic choice)
     model = bench.build_public_model(spec, wl)
     model.set_seed(1)
     model.compile(optimizer=Adam(learning_rate=1e-3))
