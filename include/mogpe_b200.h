@@ -196,6 +196,11 @@ mogpe_status mogpe_fill_normal(mogpe_handle* h, double* dst, int64_t n, uint64_t
 mogpe_status mogpe_nccl_unique_id(char out[128]);
 mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int32_t rank, int32_t world_size);
 mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_t n, void* cuda_stream);
+/* on != 0: mogpe_elbo_fwd_bwd performs the data-parallel reduction itself and returns globally summed gradients and
+ * results -- the part of the gradient buffer that is final before the Cholesky backward (q_mu, q_sqrt, mean, noise and, when
+ * out == grads + layout.total, the 4 results: 99.9 % of the bytes) is all-reduced on a communication stream underneath
+ * the rest of the backward, the kernel-hyperparameter / Z head at the end.  The caller must not all-reduce again. */
+mogpe_status mogpe_set_dp_overlap(mogpe_handle* h, int32_t on);
 
 /* Optimiser step on the device (reference: optimizer.apply_gradients in train_step,
  * mogpe/keras/mixture_of_experts/mosvgpe.py:61-63, tf.optimizers.Adam with TF defaults).

@@ -135,6 +135,11 @@ struct mogpe_handle {
   // NCCL (dlopen'ed)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
+  // data-parallel overlap: the gradient all-reduce is issued by mogpe_elbo_fwd_bwd itself, the 99.9 % of the buffer that is
+  // final before the Cholesky backward (q_mu, q_sqrt, mean, noise, the 4 results) on a communication stream underneath it
+  bool dp_overlap = false;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_comm_fork = nullptr, ev_comm_join = nullptr;
   std::string err;
 };
 
@@ -188,6 +193,9 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_step_state) cudaFree(h->d_step_state);
   if (h->d_lr_t) cudaFree(h->d_lr_t);
   if (h->step_stage) cudaFree(h->step_stage);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->ev_comm_fork) cudaEventDestroy(h->ev_comm_fork);
+  if (h->ev_comm_join) cudaEventDestroy(h->ev_comm_join);
   if (h->Linv8) cudaFree(h->Linv8);
   if (h->ST8) cudaFree(h->ST8);
   if (h->KufT8) cudaFree(h->KufT8);
@@ -637,6 +645,8 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
   return MOGPE_OK;
 }
 
+static mogpe_status dp_allreduce(mogpe_handle* h, double* buf, size_t n, cudaStream_t st);  // defined with the NCCL loader
+
 // One thread per data point with a long serial body: prefer more, smaller blocks until every SM has work
 // (8192 points in 128-thread blocks are only 64 CTAs for 148 SMs).
 static int lik_block(int slots, int Bc) {
@@ -732,7 +742,8 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   kl_kernel<<<dim3(Mp / 8, P), 256, 0, st>>>(h->d_md, params, lo, h->kl_weight, out, grads);
   finish_elbo_kernel<<<1, 1, 0, st>>>(out);
   H_CUDA(h, cudaGetLastError());
-  if (!grads) return MOGPE_OK;
+  const bool dp = h->dp_overlap && h->nccl_comm;
+  if (!grads) return dp ? dp_allreduce(h, out, 4, st) : MOGPE_OK;
 
   // ---------------- backward ----------------
   // (a) q_sqrt gradient of marginal latents: Sbar_l = tril(A (2 LTA_l diag(dfvar_l))^T); scaling fused in the
@@ -807,6 +818,18 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     H_CUDA(h, hgemm(h, p, md.nlta, false, true, st, (double)md.nlta * Mp * Mp * Bc));
   }
   q_grads_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, lo, h->dV, eps_u, S, grads);
+  if (dp) {
+    // everything from q_mu to the end of the gradient buffer (q_mu, q_sqrt, mean, noise: 99.9 % of it) and the 4 results are
+    // final now; only the kernel-hyperparameter / Z gradients (head of the buffer) still come from the Cholesky backward and
+    // the Kuf gradients.  Reduce the final part on the communication stream underneath the rest of the backward.
+    H_CUDA(h, cudaEventRecord(h->ev_comm_fork, st));
+    H_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_comm_fork, 0));
+    const bool tail_out = out == grads + lo.total;
+    mogpe_status arc = dp_allreduce(h, grads + lo.q_mu, (size_t)(lo.total - lo.q_mu) + (tail_out ? 4 : 0), h->comm_stream);
+    if (arc == MOGPE_OK && !tail_out) arc = dp_allreduce(h, out, 4, h->comm_stream);
+    if (arc != MOGPE_OK) return arc;
+    H_CUDA(h, cudaEventRecord(h->ev_comm_join, h->comm_stream));
+  }
   // Cholesky backward: Phi = tril(L^T Lbar) with halved diagonal; Kb = Linv^T Phi Linv (symmetrised in kuu_grad)
   {
     GemmParams p = gp_init();
@@ -840,6 +863,11 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     kuu_grad_kernel<16><<<dim3(Mp / 8, Q), 256, 0, st>>>(h->d_md, params, lo, h->desc.jitter, h->Lbar, h->Kuu, grads);
   H_CUDA(h, side_join(h, st));  // Kuf gradients (side stream, launched right after W was complete)
   H_CUDA(h, cudaGetLastError());
+  if (dp) {
+    mogpe_status arc = dp_allreduce(h, grads, (size_t)lo.q_mu, st);  // the head: lengthscales, kernel variances, Z
+    if (arc != MOGPE_OK) return arc;
+    H_CUDA(h, cudaStreamWaitEvent(st, h->ev_comm_join, 0));
+  }
   return MOGPE_OK;
 }
 
@@ -1313,6 +1341,25 @@ extern "C" mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int
   int rc = fn(&h->nccl_comm, world, uid, rank);
   if (rc != 0) H_FAIL(h, MOGPE_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
   h->nccl_lib = g_nccl.lib;
+  return MOGPE_OK;
+}
+
+static mogpe_status dp_allreduce(mogpe_handle* h, double* buf, size_t n, cudaStream_t st) {
+  int rc = g_nccl.AllReduce(buf, buf, n, 8, 0, h->nccl_comm, st);  // ncclFloat64 = 8, ncclSum = 0
+  if (rc != 0) H_FAIL(h, MOGPE_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_set_dp_overlap(mogpe_handle* h, int32_t on) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (on && !h->nccl_comm) H_FAIL(h, MOGPE_ERR_NCCL, "mogpe_comm_init has not been called on this handle");
+  H_CUDA(h, cudaSetDevice(h->device));
+  if (on && !h->comm_stream) {
+    H_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    H_CUDA(h, cudaEventCreateWithFlags(&h->ev_comm_fork, cudaEventDisableTiming));
+    H_CUDA(h, cudaEventCreateWithFlags(&h->ev_comm_join, cudaEventDisableTiming));
+  }
+  h->dp_overlap = on != 0;
   return MOGPE_OK;
 }
 

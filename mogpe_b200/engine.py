@@ -310,11 +310,15 @@ class Engine:
     def set_seed(self, seed: int):
         _lib.check(self.lib.mogpe_set_seed(self.h, int(seed)), self.h)
 
-    def init_data_parallel(self, rank: int, world_size: int, unique_id: bytes):
+    def init_data_parallel(self, rank: int, world_size: int, unique_id: bytes, overlap: bool = True):
         """Join an NCCL communicator (id from Engine.nccl_unique_id() on rank 0, distributed by the caller) and
-        weight the redundantly computed KL terms by 1/world_size so that the all-reduced sums are exact."""
+        weight the redundantly computed KL terms by 1/world_size so that the all-reduced sums are exact.
+        overlap: elbo() itself all-reduces [gradients | results] (most of it underneath the Cholesky backward) and
+        allreduce(self.gbuf) becomes a no-op; False keeps the reduction a separate call after elbo()."""
         _lib.check(self.lib.mogpe_comm_init(self.h, unique_id, rank, world_size), self.h)
         _lib.check(self.lib.mogpe_set_kl_weight(self.h, 1.0 / world_size), self.h)
+        _lib.check(self.lib.mogpe_set_dp_overlap(self.h, 1 if overlap else 0), self.h)
+        self.dp_overlap = bool(overlap)
         self.world_size = world_size
 
     @staticmethod
@@ -324,6 +328,8 @@ class Engine:
         return buf.raw
 
     def allreduce(self, buf: DeviceBuffer, count=None, stream=None):
+        if getattr(self, "dp_overlap", False) and buf is self.gbuf:
+            return  # elbo() already returned the globally reduced [gradients | results]
         _lib.check(self.lib.mogpe_allreduce_sum(self.h, buf.ptr, buf.size if count is None else count, stream), self.h)
 
     def profile(self, on=True):
