@@ -321,10 +321,11 @@ __device__ __forceinline__ void slice8(double x, double inv_scale, int8_t* q) {
   double r = x * inv_scale;
 #pragma unroll
   for (int s = 0; s < NS; s++) {
+    // round to nearest with the 1.5 * 2^52 trick: the low word of y holds the integer, no conversion instructions
     const double t = r * 128.0;
-    const int v = __double2int_rn(t);
-    r = t - (double)v;
-    q[s] = (int8_t)v;
+    const double y = t + 6755399441055744.0;
+    r = t - (y - 6755399441055744.0);
+    q[s] = (int8_t)__double2loint(y);
   }
 }
 
