@@ -14,7 +14,9 @@
 //
 // Tile: D[128 x 64] per CTA, the NS accumulators T_0 .. T_7 occupy all 512 TMEM columns (8 x 64).  Pipeline stage = 64
 // k-values (64-byte rows, 64B swizzle): A [NS planes][128 rows][64 B] + B [NS][64 rows][64 B] = 96 KB, 2 stages; each stage
-// feeds 2 x 36 MMAs (>= 2300 tensor cycles), so two stages cover the TMA latency.  Same warp roles as gemm_tf32x3_kernel.
+// feeds 2 x 36 MMAs (>= 2300 tensor cycles), so two stages cover the TMA latency.  Warp roles as in gemm_tf32x3_kernel, but
+// eight epilogue warps (two per TMEM lane quarter, one 32-column half each): the epilogue cannot overlap the main loop
+// (the accumulators fill TMEM), so it is made short instead.
 // Epilogue: T_d -> FP64 (tcgen05.ld, 8 int->double conversions per element), row / column scales, column sums of squares in
 // FP64 (butterfly transpose-reduce), and optionally the tile re-sliced into NS byte planes, transposed ([n][m]), as the
 // B operand of the next product.
@@ -37,7 +39,7 @@ constexpr int B_STAGE_BYTES = NS * B_PLANE_BYTES;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int RED_BYTES = 4 * BN * 8;              // cross-warp column sums (FP64)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RED_BYTES + 1024 + 256;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two per TMEM lane quarter, 32 columns each)
 constexpr int TMEM_COLS = NS * BN;                 // 512
 
 struct Params {
@@ -203,8 +205,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
     int8_t* ocol = nullptr;
     if (p.out) ocol = p.out + (long long)batch * p.out_batch_stride + (long long)n0 * p.ldo + row;
     const double oinv = p.out ? 1.0 / p.out_scale[batch] : 0.0;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
+    {
+      const int c = (warp - 2) >> 2;  // this warp's 32-column half of the tile
       // sum_d T_d 128^-d, exactly: two int64 Horner sums (T_0..T_3 and T_4..T_7; |sum| < 2^50), two int -> double
       // conversions per element instead of eight
       double v[32];
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
     }
     tc_fence_before();
     if (p.ss_part) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
       const int tt = threadIdx.x - 64;
       if (tt < BN) {
         double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
