@@ -17,8 +17,8 @@
 // Tile: two D[128 x 256] row tiles per CTA (UMMA M = 128, N = 256, K = 8 per instruction) sharing one B stage, BK = 16 per
 // pipeline stage, 3 stages of 64 KB:  A0, A1 [plane][128 rows][16 fp32], B [plane][256 rows][16 fp32], rows of 64 B,
 // 64B-swizzled by TMA.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-// (each reads its own 32-lane TMEM quarter).  Triangular operands shorten the k loop per row tile.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+// (two per 32-lane TMEM quarter, four 32-column chunks each).  Triangular operands shorten the k loop per row tile.
 // Epilogue: column sums of squares of the tile (butterfly transpose-reduce over the 32 lanes, then over the 4 warps)
 // written as one FP64 partial per row tile (deterministic), and optionally the tile itself, TRANSPOSED ([n][m], warp-wide
 // coalesced 128-byte stores), as hi / lo planes so that it can be the K-major B operand of the next product.
@@ -38,7 +38,7 @@ constexpr int B_STAGE_BYTES = 2 * B_PLANE_BYTES;
 constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + B_STAGE_BYTES;  // two row tiles + one column tile: 64 KB
 constexpr int RED_BYTES = 2 * 4 * BN * 4;                    // cross-warp column-sum scratch, one per row tile
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RED_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;  // two 128 x 256 FP32 accumulators
 
 enum : int { K_FULL = 0, K_LOWER = 1, K_UPPER = 2 };
@@ -281,8 +281,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         ocol_hi = p.out + (long long)batch * p.out_batch_stride + (long long)n0 * p.ldo + (m0 + q * 32 + lane);
         ocol_lo = ocol_hi + p.out_plane_stride;
       }
+      const int c_lo = ((warp - 2) >> 2) * (BN / 64);  // the two warps of a lane quarter split the 8 column chunks
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
+      for (int c = c_lo; c < c_lo + BN / 64; c++) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c * 32), v);
         if (p.out) {
@@ -312,14 +313,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         }
       }
       if (p.ss_part) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
         const int tt = threadIdx.x - 64;
         double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
-#pragma unroll
-        for (int u = 0; u < BN / 128; u++) {
-          const int col = tt + u * 128;
-          dst[col] = ((double)redt[col] + (double)redt[BN + col]) + ((double)redt[2 * BN + col] + (double)redt[3 * BN + col]);
-        }
+        if (tt < BN)  // 256 epilogue threads, one column each
+          dst[tt] = ((double)redt[tt] + (double)redt[BN + tt]) + ((double)redt[2 * BN + tt] + (double)redt[3 * BN + tt]);
       }
     }
     tc_fence_before();
