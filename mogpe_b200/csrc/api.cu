@@ -59,6 +59,13 @@ struct mogpe_handle {
   double* alpha = nullptr;                        // [P][Mp32]: L^-T q_mu (FP64 means)
   CUtensorMap tm_linv, tm_st, tm_kuf, tm_at;
   bool t32_ready = false;
+  // chunk look-ahead of the tensor-core predict modes: the Kuf stage of chunk i+1 (FP64 pipe, side stream) runs underneath the
+  // products of chunk i (tensor pipe), so Kuf^T and the mean partials are double-buffered
+  void* kuf_buf2 = nullptr;          // second Kuf^T plane buffer (float or int8 planes)
+  double* dot_part2 = nullptr;       // second mean-partial buffer
+  size_t dot_part2_cap = 0;
+  CUtensorMap tm_kuf2;
+  cudaEvent_t ev_kuf[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   // INT8 mode (integer-sliced FP64-accurate products, gemm_i8.cuh): byte planes and power-of-two scales
   int8_t *Linv8 = nullptr, *ST8 = nullptr;        // [Q | P][NS][Mp32][Mp32]
   int8_t *KufT8 = nullptr, *AT8 = nullptr;        // [Q][NS][Bp][Mp32]
@@ -193,6 +200,12 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_step_state) cudaFree(h->d_step_state);
   if (h->d_lr_t) cudaFree(h->d_lr_t);
   if (h->step_stage) cudaFree(h->step_stage);
+  if (h->kuf_buf2) cudaFree(h->kuf_buf2);
+  if (h->dot_part2) cudaFree(h->dot_part2);
+  for (int i = 0; i < 2; i++) {
+    if (h->ev_kuf[i]) cudaEventDestroy(h->ev_kuf[i]);
+    if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
+  }
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->ev_comm_fork) cudaEventDestroy(h->ev_comm_fork);
   if (h->ev_comm_join) cudaEventDestroy(h->ev_comm_join);
@@ -936,7 +949,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd_host_async(mogpe_handle* h, const dou
   cudaStream_t st = (cudaStream_t)cuda_stream;
   H_CUDA(h, cudaSetDevice(h->device));
   const size_t nx = (size_t)N * md.D, ny = (size_t)N * md.F, need = (size_t)h->desc.max_batch * (md.D + md.F);
-  if (need > h->ring_cap) {
+  if (need > h->ring_cap || !h->ring_dev[0]) {  // (mogpe_train_step shares the pinned ring but not the device slots)
     H_CUDA(h, cudaStreamSynchronize(st));
     for (int i = 0; i < mogpe_handle::RING; i++) {
       if (h->ring_host[i]) cudaFreeHost(h->ring_host[i]);
@@ -983,6 +996,13 @@ static mogpe_status ensure_t32(mogpe_handle* h) {
       !t32::make_map_kmajor(&h->tm_kuf, h->KufT32, (int)Q, (int)Bp, (int)M32, t32::BN) ||
       !t32::make_map_kmajor(&h->tm_at, h->AT32, (int)Q, (int)Bp, (int)M32, t32::BN))
     H_FAIL(h, MOGPE_ERR_CUDA, "cuTensorMapEncodeTiled failed (TF32 mode needs a driver with TMA tensor maps)");
+  {
+    float* b2 = nullptr;
+    H_CUDA(h, dalloc(&b2, Q * 2 * Bp * M32));
+    h->kuf_buf2 = b2;
+    if (!t32::make_map_kmajor(&h->tm_kuf2, b2, (int)Q, (int)Bp, (int)M32, t32::BN))
+      H_FAIL(h, MOGPE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  }
   h->t32_ready = true;
   return MOGPE_OK;
 }
@@ -1003,21 +1023,31 @@ static mogpe_status t32_prepare(mogpe_handle* h, cudaStream_t st) {
 }
 
 // One chunk of test points: Kuf^T planes + FP64 mean partials, then the two variance products on the tensor cores.
-static mogpe_status conditional_fwd_t32(mogpe_handle* h, const double* params, const double* X, int N, int Bc,
-                                        cudaStream_t st) {
+// Kuf stage of one chunk into plane buffer `buf` (0 / 1): Kuf^T planes + FP64 mean partials.
+static mogpe_status kuf_stage_t32(mogpe_handle* h, const double* params, const double* X, int N, int Bc, int buf,
+                                  cudaStream_t st) {
   const ModelDev& md = h->md_host;
   const int Q = md.Q, M32 = h->Mp32, m_tiles = M32 / t32::BM;
+  float* kt = buf ? (float*)h->kuf_buf2 : h->KufT32;
+  double* dp = buf ? h->dot_part2 : h->dot_part;
   const dim3 kg(Bc / 64, M32 / 128, Q);
   if (md.D <= 2)
-    t32::kuf32_kernel<2><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->KufT32, h->alpha, h->dot_part, m_tiles);
+    t32::kuf32_kernel<2><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, kt, h->alpha, dp, m_tiles);
   else if (md.D <= 4)
-    t32::kuf32_kernel<4><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->KufT32, h->alpha, h->dot_part, m_tiles);
+    t32::kuf32_kernel<4><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, kt, h->alpha, dp, m_tiles);
   else if (md.D <= 8)
-    t32::kuf32_kernel<8><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->KufT32, h->alpha, h->dot_part, m_tiles);
+    t32::kuf32_kernel<8><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, kt, h->alpha, dp, m_tiles);
   else
-    t32::kuf32_kernel<16><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->KufT32, h->alpha, h->dot_part, m_tiles);
+    t32::kuf32_kernel<16><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, kt, h->alpha, dp, m_tiles);
   KCOUNT(h, 1);
   H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+// The two variance products of one chunk on the tensor cores + the statistics finish.
+static mogpe_status products_t32(mogpe_handle* h, const double* params, int Bc, int buf, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, M32 = h->Mp32, m_tiles = M32 / t32::BM;
   t32::Params p;
   memset(&p, 0, sizeof(p));
   p.m_tiles = m_tiles; p.K = M32; p.kmode = t32::K_LOWER;
@@ -1026,7 +1056,7 @@ static mogpe_status conditional_fwd_t32(mogpe_handle* h, const double* params, c
     p.out = h->AT32; p.out_batch_stride = (long long)2 * h->Bp * M32; p.out_plane_stride = (long long)h->Bp * M32; p.ldo = M32;
   }
   for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = g;
-  H_CUDA(h, t32::launch(h->tm_linv, h->tm_kuf, p, Bc / t32::BN, Q, st));  // A^T planes + sum_m A^2 partials
+  H_CUDA(h, t32::launch(h->tm_linv, buf ? h->tm_kuf2 : h->tm_kuf, p, Bc / t32::BN, Q, st));  // A^T planes + sum_m A^2 partials
   h->gemm_launches++;
   KCOUNT(h, 1);
   if (md.nlta > 0) {
@@ -1042,7 +1072,7 @@ static mogpe_status conditional_fwd_t32(mogpe_handle* h, const double* params, c
     KCOUNT(h, 1);
   }
   KCOUNT(h, 1);  // stats_finish
-  stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + md.nlta), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, h->dot_part,
+  stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + md.nlta), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, buf ? h->dot_part2 : h->dot_part,
                                                                            h->lta_part, m_tiles, h->Bp, h->var0ss, h->mean,
                                                                            h->varq);
   H_CUDA(h, cudaGetLastError());
@@ -1072,6 +1102,13 @@ static mogpe_status ensure_i8(mogpe_handle* h) {
       !oz::make_map_i8(&h->tm_kuf, h->KufT8, (int)Q, (int)Bp, (int)M32, oz::BN) ||
       !oz::make_map_i8(&h->tm_at, h->AT8, (int)Q, (int)Bp, (int)M32, oz::BN))
     H_FAIL(h, MOGPE_ERR_CUDA, "cuTensorMapEncodeTiled failed (INT8 mode needs a driver with TMA tensor maps)");
+  {
+    int8_t* b2 = nullptr;
+    H_CUDA(h, dalloc(&b2, Q * NS * Bp * M32));
+    h->kuf_buf2 = b2;
+    if (!oz::make_map_i8(&h->tm_kuf2, b2, (int)Q, (int)Bp, (int)M32, oz::BN))
+      H_FAIL(h, MOGPE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  }
   h->i8_ready = true;
   return MOGPE_OK;
 }
@@ -1097,21 +1134,29 @@ static mogpe_status i8_prepare(mogpe_handle* h, const double* params, cudaStream
   return MOGPE_OK;
 }
 
-static mogpe_status conditional_fwd_i8(mogpe_handle* h, const double* params, const double* X, int N, int Bc,
-                                       cudaStream_t st) {
+static mogpe_status kuf_stage_i8(mogpe_handle* h, const double* params, const double* X, int N, int Bc, int buf,
+                                 cudaStream_t st) {
   const ModelDev& md = h->md_host;
   const int Q = md.Q, M32 = h->Mp32, m_tiles = M32 / oz::BM;
+  int8_t* kt = buf ? (int8_t*)h->kuf_buf2 : h->KufT8;
+  double* dp = buf ? h->dot_part2 : h->dot_part;
   const dim3 kg(Bc / 64, M32 / 128, Q);
   if (md.D <= 2)
-    oz::kuf8_kernel<2><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, h->KufT8, h->alpha, h->dot_part, m_tiles);
+    oz::kuf8_kernel<2><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles);
   else if (md.D <= 4)
-    oz::kuf8_kernel<4><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, h->KufT8, h->alpha, h->dot_part, m_tiles);
+    oz::kuf8_kernel<4><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles);
   else if (md.D <= 8)
-    oz::kuf8_kernel<8><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, h->KufT8, h->alpha, h->dot_part, m_tiles);
+    oz::kuf8_kernel<8><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles);
   else
-    oz::kuf8_kernel<16><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, h->KufT8, h->alpha, h->dot_part, m_tiles);
+    oz::kuf8_kernel<16><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles);
   KCOUNT(h, 1);
   H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+static mogpe_status products_i8(mogpe_handle* h, const double* params, int Bc, int buf, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, M32 = h->Mp32, m_tiles = M32 / oz::BM;
   oz::Params p;
   memset(&p, 0, sizeof(p));
   p.m_tiles = m_tiles; p.K = M32; p.kmode = t32::K_LOWER;
@@ -1122,7 +1167,7 @@ static mogpe_status conditional_fwd_i8(mogpe_handle* h, const double* params, co
     p.out_scale = h->aout_scale;
   }
   for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = g;
-  H_CUDA(h, oz::launch(h->tm_linv, h->tm_kuf, p, Bc / oz::BN, Q, st));  // A^T byte planes + sum_m A^2 partials
+  H_CUDA(h, oz::launch(h->tm_linv, buf ? h->tm_kuf2 : h->tm_kuf, p, Bc / oz::BN, Q, st));  // A^T byte planes + sum_m A^2 partials
   h->gemm_launches++;
   KCOUNT(h, 1);
   if (md.nlta > 0) {
@@ -1139,7 +1184,7 @@ static mogpe_status conditional_fwd_i8(mogpe_handle* h, const double* params, co
     KCOUNT(h, 1);
   }
   KCOUNT(h, 1);
-  stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + md.nlta), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, h->dot_part,
+  stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + md.nlta), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, buf ? h->dot_part2 : h->dot_part,
                                                                            h->lta_part, m_tiles, h->Bp, h->var0ss, h->mean,
                                                                            h->varq);
   H_CUDA(h, cudaGetLastError());
@@ -1174,12 +1219,50 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
     if (rc == MOGPE_OK && i8) rc = i8_prepare(h, params, st);
     if (rc != MOGPE_OK) return rc;
   }
-  for (int64_t n0 = 0; n0 < N; n0 += chunk_max) {
+  const bool tc = tf32 || i8;
+  auto kuf_stage = [&](int64_t n0, int buf) -> mogpe_status {
+    // Kuf stage of the chunk starting at n0 on the side stream, once plane buffer `buf` has been consumed
     const int nc = (int)std::min<int64_t>(chunk_max, N - n0);
-    const int Bc = round_up(nc, (tf32 || i8) ? t32::BN : 128);
-    rc = tf32 ? conditional_fwd_t32(h, params, X + n0 * md.D, nc, Bc, st)
-         : i8 ? conditional_fwd_i8(h, params, X + n0 * md.D, nc, Bc, st)
-              : conditional_fwd(h, params, X + n0 * md.D, nc, Bc, st, n0 == 0);
+    const int Bc = round_up(nc, t32::BN);
+    H_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_free[buf], 0));
+    mogpe_status r = tf32 ? kuf_stage_t32(h, params, X + n0 * md.D, nc, Bc, buf, h->side)
+                          : kuf_stage_i8(h, params, X + n0 * md.D, nc, Bc, buf, h->side);
+    if (r != MOGPE_OK) return r;
+    H_CUDA(h, cudaEventRecord(h->ev_kuf[buf], h->side));
+    return MOGPE_OK;
+  };
+  if (tc) {
+    for (int i = 0; i < 2; i++) {
+      if (!h->ev_kuf[i]) H_CUDA(h, cudaEventCreateWithFlags(&h->ev_kuf[i], cudaEventDisableTiming));
+      if (!h->ev_free[i]) H_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+      H_CUDA(h, cudaEventRecord(h->ev_free[i], st));  // both buffers are free once the preparation on `st` is done
+    }
+    const size_t need = (size_t)md.NV * (h->Mp32 / 128) * h->Bp;
+    if (need > h->dot_part2_cap) {
+      if (h->dot_part2) cudaFree(h->dot_part2);
+      h->dot_part2 = nullptr;
+      H_CUDA(h, dalloc(&h->dot_part2, need));
+      h->dot_part2_cap = need;
+    }
+    rc = kuf_stage(0, 0);
+    if (rc != MOGPE_OK) return rc;
+  }
+  int chunk_i = 0;
+  for (int64_t n0 = 0; n0 < N; n0 += chunk_max, chunk_i++) {
+    const int nc = (int)std::min<int64_t>(chunk_max, N - n0);
+    const int Bc = round_up(nc, tc ? t32::BN : 128);
+    if (tc) {
+      // look-ahead: the kernel matrices of the NEXT chunk (FP64 exp, side stream) run underneath this chunk's products
+      const int buf = chunk_i & 1;
+      if (n0 + chunk_max < N) {
+        rc = kuf_stage(n0 + chunk_max, buf ^ 1);
+        if (rc != MOGPE_OK) return rc;
+      }
+      H_CUDA(h, cudaStreamWaitEvent(st, h->ev_kuf[buf], 0));
+      rc = tf32 ? products_t32(h, params, Bc, buf, st) : products_i8(h, params, Bc, buf, st);
+    } else {
+      rc = conditional_fwd(h, params, X + n0 * md.D, nc, Bc, st, n0 == 0);
+    }
     if (rc != MOGPE_OK) return rc;
     PredArgs pa;
     pa.md = h->d_md; pa.params = params; pa.lo = h->lo; pa.mean = h->mean; pa.var0ss = h->var0ss; pa.varq = h->varq;
@@ -1205,6 +1288,7 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
     KCOUNT(h, 1);
     predict_out_kernel<<<(nc + blk - 1) / blk, blk, (size_t)2 * md.K * blk * sizeof(double), st>>>(pa);
     H_CUDA(h, cudaGetLastError());
+    if (tc) H_CUDA(h, cudaEventRecord(h->ev_free[chunk_i & 1], st));
   }
   if (lib_mc) h->rng_counter += ((unsigned long long)num_mc * N * md.K + 1) / 2 * 2;
   return MOGPE_OK;
