@@ -177,3 +177,22 @@ def test_mixture_distribution_matches_tfp_formulas():
                        for k in range(3)))
     np.testing.assert_allclose(d.log_prob(y), joint, rtol=1e-12)
     assert d.sample(4, rng).shape == (4, 5, 2)
+
+
+def test_parameter_versions_track_every_change_and_arrays_are_read_only():
+    """fit() skips re-packing / re-uploading parameters whose version stamp did not change (MixtureCore._stamp): every
+    mutation must therefore go through the setter, and in-place writes must fail loudly instead of being missed."""
+    from mogpe_b200.gpflow_lite import Parameter, positive
+
+    p = Parameter(np.array([1.0, 2.0]), transform=positive())
+    v0 = p.version
+    p.assign(np.array([3.0, 4.0]))
+    v1 = p.version
+    p.assign_unconstrained(p.unconstrained + 1.0)
+    v2 = p.version
+    p.unconstrained = np.zeros(2)
+    assert v0 < v1 < v2 < p.version
+    with pytest.raises(ValueError):
+        p.unconstrained[0] = 5.0  # read-only view: cannot bypass the version counter
+    q = Parameter(1.0)
+    assert q.version > p.version  # one global clock: stamps of different parameters never collide
