@@ -44,6 +44,8 @@ constexpr int TMEM_COLS = NS * BN;                 // 512
 
 struct Params {
   int m_tiles;  // row tiles of 128
+  int n_tiles;  // column tiles of 64 (set by launch)
+  int batch;    // (set by launch)
   int K;        // reduction length (multiple of 64)
   int kmode;    // t32::K_FULL / K_LOWER / K_UPPER
   const double* a_scale;     // [A batches][m_tiles * 128]: 2^ea of each operand row
@@ -102,7 +104,33 @@ __device__ __forceinline__ void tmem_ld32_i(uint32_t taddr, int* v) {
       : "memory");
 }
 
-// grid (m_tiles, n_tiles, batch): the row tiles of one column tile are neighbours in launch order (they share the B tile in L2)
+// Tile decode shared by the three warp roles.  Tiles are numbered with the row tile fastest, so the CTAs that run at the
+// same time work on neighbouring tiles and share their B tiles in L2.
+struct TileInfo {
+  int m_tile, n_tile, batch, m0, n0, k_begin, num_kb;
+};
+__device__ __forceinline__ TileInfo decode_tile(const Params& p, int t) {
+  using namespace t32;
+  TileInfo ti;
+  const int mr = t % p.m_tiles, rest = t / p.m_tiles;
+  ti.m_tile = (p.kmode == K_UPPER) ? mr : p.m_tiles - 1 - mr;
+  ti.n_tile = rest % p.n_tiles;
+  ti.batch = rest / p.n_tiles;
+  ti.m0 = ti.m_tile * BM;
+  ti.n0 = ti.n_tile * BN;
+  int k_begin = 0, k_end = p.K;
+  if (p.kmode == K_LOWER) k_end = min(p.K, ti.m0 + BM);
+  if (p.kmode == K_UPPER) k_begin = ti.m0 / BKB * BKB;
+  ti.k_begin = k_begin;
+  ti.num_kb = (k_end - k_begin) / BKB;
+  return ti;
+}
+
+// PERSISTENT kernel: gridDim.x CTAs (one per SM) loop over tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  TMEM, the
+// barriers and the tensor-map prefetch are set up once, and the TMA producer runs ahead into the next tile while the
+// epilogue of the current one drains TMEM, so the per-tile prologue (first TMA round trip: ~4k of ~25k cycles) is hidden.
+// The host picks gridDim.x coprime to m_tiles: every CTA then cycles through all row tiles (triangular operands give them
+// different k lengths) and the static schedule is balanced.
 __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                      const __grid_constant__ CUtensorMap mapB,
                                                                      const __grid_constant__ Params p) {
@@ -112,19 +140,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   double* red = reinterpret_cast<double*>(gbase + STAGES * STAGE_BYTES);  // [4][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + STAGES * STAGE_BYTES + RED_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* acc_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* full = bars;                     // [STAGES] TMA -> MMA
+  uint64_t* empty = bars + STAGES;           // [STAGES] MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;    // MMA -> epilogue: the accumulators of this tile are complete
+  uint64_t* acc_empty = bars + 2 * STAGES + 1;  // epilogue (8 warps) -> MMA: TMEM has been drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.y, batch = blockIdx.z;
-  const int m_tile = (p.kmode == K_UPPER) ? (int)blockIdx.x : p.m_tiles - 1 - (int)blockIdx.x;
-  const int m0 = m_tile * BM, n0 = n_tile * BN;
-  int k_begin = 0, k_end = p.K;
-  if (p.kmode == K_LOWER) k_end = min(p.K, m0 + BM);
-  if (p.kmode == K_UPPER) k_begin = m0 / BKB * BKB;
-  const int num_kb = (k_end - k_begin) / BKB;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.batch;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -132,6 +155,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
@@ -148,94 +172,115 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ===== TMA producer: one running stage counter across tiles =====
     if (lane == 0) {
-      const int ca = p.mapA[batch], cb = p.mapB[batch];
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1, p.err_flag);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        const int k0 = k_begin + kb * BKB;
-        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-        tma_load_4d(sa, &mapA, smem_u32(&full[s]), k0, m0, 0, ca);  // {k, m, slice, batch}: all NS planes in one copy
-        tma_load_4d(sb, &mapB, smem_u32(&full[s]), k0, n0, 0, cb);
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileInfo ti = decode_tile(p, t);
+        const int ca = p.mapA[ti.batch], cb = p.mapB[ti.batch];
+        for (int kb = 0; kb < ti.num_kb; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1, p.err_flag);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          const int k0 = ti.k_begin + kb * BKB;
+          const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          tma_load_4d(sa, &mapA, smem_u32(&full[s]), k0, ti.m0, 0, ca);  // {k, m, slice, batch}: all NS planes in one copy
+          tma_load_4d(sb, &mapB, smem_u32(&full[s]), k0, ti.n0, 0, cb);
+        }
       }
     }
   } else if (warp == 1) {
-    // the whole warp runs the loop (converged); one elected lane issues
-    for (int kb = 0; kb < num_kb; kb++) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&full[s], ph, p.err_flag);
-      tc_fence_after();
-      const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-      // K-major, 64B swizzle: 8-row groups 512 B apart; planes and the 32-byte k-step only move the start address field
-      const uint64_t ad0 = make_smem_desc(sa, 16, 8 * BKB, 4), bd0 = make_smem_desc(sb, 16, 8 * BKB, 4);
-      const uint32_t first = kb == 0 ? 0u : 1u;
-      // Slice i of A meets slices j = 0 .. NS-1-i of B, and pair (i, j) belongs to accumulator T_(i+j) = TMEM columns
-      // (i + j) * 64.  The B planes are contiguous in shared memory (plane j = rows 64 j .. 64 j + 63 of one tall K-major
-      // tile), so ONE wide MMA  A_i x [B_0; ...; B_(NS-1-i)]^T  with N = 64 (NS - i) columns starting at TMEM column 64 i
-      // covers all pairs of slice i (split in two when N > 256): 12 MMAs per k-step instead of 36, and A_i is read from
-      // shared memory once instead of NS - i times (the 36-MMA version was bound by that re-read, 63 instead of 32 cycles
-      // per 64 columns).  Slice 0 goes first and overwrites every accumulator on the very first k-step.
+    // ===== MMA issuer: the whole warp runs the loop (converged); one elected lane issues =====
+    int it = 0, tile_i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_i++) {
+      const TileInfo ti = decode_tile(p, t);
+      if (tile_i > 0) {  // the epilogue must have drained the previous tile's accumulators
+        mbar_wait(acc_empty, (uint32_t)((tile_i - 1) & 1), p.err_flag);
+        tc_fence_after();
+      }
+      for (int kb = 0; kb < ti.num_kb; kb++, it++) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph, p.err_flag);
+        tc_fence_after();
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+        // K-major, 64B swizzle: 8-row groups 512 B apart; planes and the 32-byte k-step only move the start address field
+        const uint64_t ad0 = make_smem_desc(sa, 16, 8 * BKB, 4), bd0 = make_smem_desc(sb, 16, 8 * BKB, 4);
+        const uint32_t first = kb == 0 ? 0u : 1u;
+        // Slice i of A meets slices j = 0 .. NS-1-i of B, and pair (i, j) belongs to accumulator T_(i+j) = TMEM columns
+        // (i + j) * 64.  The B planes are contiguous in shared memory (plane j = rows 64 j .. 64 j + 63 of one tall K-major
+        // tile), so ONE wide MMA  A_i x [B_0; ...; B_(NS-1-i)]^T  with N = 64 (NS - i) columns starting at TMEM column 64 i
+        // covers all pairs of slice i (split in two when N > 256): 12 MMAs per k-step instead of 36, and A_i is read from
+        // shared memory once instead of NS - i times (the 36-MMA version was bound by that re-read, 63 instead of 32 cycles
+        // per 64 columns).  Slice 0 goes first and overwrites every accumulator on the first k-step of a tile.
 #pragma unroll
-      for (int j = 0; j < BKB / UKB; j++) {
+        for (int j = 0; j < BKB / UKB; j++) {
 #pragma unroll
-        for (int i = 0; i < NS; i++) {
-          const uint64_t ad = ad0 + (uint64_t)((i * A_PLANE_BYTES + j * UKB) >> 4);
+          for (int i = 0; i < NS; i++) {
+            const uint64_t ad = ad0 + (uint64_t)((i * A_PLANE_BYTES + j * UKB) >> 4);
 #pragma unroll
-          for (int c0 = 0; c0 < BN * (NS - i); c0 += 256) {
-            const int n1 = BN * (NS - i) - c0 < 256 ? BN * (NS - i) - c0 : 256;
-            const uint64_t bd = bd0 + (uint64_t)((c0 * BKB + j * UKB) >> 4);
-            umma_i8(tmem_base + (uint32_t)(i * BN + c0), ad, bd, make_idesc_i8(n1), (j == 0 && i == 0) ? first : 1u);
+            for (int c0 = 0; c0 < BN * (NS - i); c0 += 256) {
+              const int n1 = BN * (NS - i) - c0 < 256 ? BN * (NS - i) - c0 : 256;
+              const uint64_t bd = bd0 + (uint64_t)((c0 * BKB + j * UKB) >> 4);
+              umma_i8(tmem_base + (uint32_t)(i * BN + c0), ad, bd, make_idesc_i8(n1), (j == 0 && i == 0) ? first : 1u);
+            }
           }
         }
+        __syncwarp();
+        umma_commit_elect(&empty[s]);
       }
-      __syncwarp();
-      umma_commit_elect(&empty[s]);
+      umma_commit_elect(acc_full);
     }
-    umma_commit_elect(acc_full);
   } else {
+    // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
-    mbar_wait(acc_full, 0, p.err_flag);
-    tc_fence_after();
-    const int row = m0 + q * 32 + lane;
-    // 2^(ea + eb) * 2^(-14): T_d carries 2^(-7 (d + 2))
-    const double rs = p.a_scale[(long long)p.mapA[batch] * p.a_scale_stride + row] * p.b_scale[p.mapB[batch]] * (1.0 / 16384.0);
-    int8_t* ocol = nullptr;
-    if (p.out) ocol = p.out + (long long)batch * p.out_batch_stride + (long long)n0 * p.ldo + row;
-    const double oinv = p.out ? 1.0 / p.out_scale[batch] : 0.0;
-    {
-      const int c = (warp - 2) >> 2;  // this warp's 32-column half of the tile
+    const int c = (warp - 2) >> 2;
+    int tile_i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_i++) {
+      const TileInfo ti = decode_tile(p, t);
+      const int batch = ti.batch, m_tile = ti.m_tile, n0 = ti.n0;
+      mbar_wait(acc_full, (uint32_t)(tile_i & 1), p.err_flag);
+      tc_fence_after();
+      const int row = ti.m0 + q * 32 + lane;
+      // 2^(ea + eb) * 2^(-14): T_d carries 2^(-7 (d + 2))
+      const double rs = p.a_scale[(long long)p.mapA[batch] * p.a_scale_stride + row] * p.b_scale[p.mapB[batch]] * (1.0 / 16384.0);
+      int8_t* ocol = nullptr;
+      if (p.out) ocol = p.out + (long long)batch * p.out_batch_stride + (long long)n0 * p.ldo + row;
+      const double oinv = p.out ? 1.0 / p.out_scale[batch] : 0.0;
       // sum_d T_d 128^-d, exactly: two int64 Horner sums (T_0..T_3 and T_4..T_7; |sum| < 2^50), two int -> double
       // conversions per element instead of eight
       double v[32];
       {
         long long acc[32];
-        int t[32];
-        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), t);
+        int tt[32];
+        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), tt);
 #pragma unroll
-        for (int i = 0; i < 32; i++) acc[i] = t[i];
+        for (int i = 0; i < 32; i++) acc[i] = tt[i];
 #pragma unroll 1
         for (int d = 1; d < 4; d++) {
-          tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), t);
+          tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), tt);
 #pragma unroll
-          for (int i = 0; i < 32; i++) acc[i] = acc[i] * 128 + t[i];
+          for (int i = 0; i < 32; i++) acc[i] = acc[i] * 128 + tt[i];
         }
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = (double)acc[i] * (1.0 / 2097152.0);  // 128^-3
-        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * BN + c * 32), t);
+        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * BN + c * 32), tt);
 #pragma unroll
-        for (int i = 0; i < 32; i++) acc[i] = t[i];
+        for (int i = 0; i < 32; i++) acc[i] = tt[i];
 #pragma unroll 1
         for (int d = 5; d < 8; d++) {
-          tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), t);
+          tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), tt);
 #pragma unroll
-          for (int i = 0; i < 32; i++) acc[i] = acc[i] * 128 + t[i];
+          for (int i = 0; i < 32; i++) acc[i] = acc[i] * 128 + tt[i];
         }
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = fma((double)acc[i], 1.0 / 562949953421312.0 /* 128^-7 */, v[i]) * rs;
       }
+      // every accumulator value of this warp is in registers: TMEM may be overwritten by the next tile's MMAs
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty)) : "memory");
       if (p.out) {
 #pragma unroll
         for (int i = 0; i < 32; i++) {
@@ -244,9 +289,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
 #pragma unroll
           for (int s = 0; s < NS; s++) {
             // round to nearest with the 1.5 * 2^52 trick: the low word of y holds the integer, no conversion instructions
-            const double tt = r * 128.0;
-            const double y = tt + 6755399441055744.0;
-            r = tt - (y - 6755399441055744.0);
+            const double x = r * 128.0;
+            const double y = x + 6755399441055744.0;
+            r = x - (y - 6755399441055744.0);
             o[(long long)s * p.out_plane_stride] = (int8_t)__double2loint(y);
           }
         }
@@ -264,16 +309,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
           }
         }
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // the previous tile's sums have been read by everyone
         red[q * BN + c * 32 + lane] = v[0];
-      }
-    }
-    tc_fence_before();
-    if (p.ss_part) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
-      const int tt = threadIdx.x - 64;
-      if (tt < BN) {
-        double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
-        dst[tt] = (red[tt] + red[BN + tt]) + (red[2 * BN + tt] + red[3 * BN + tt]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+        const int e = threadIdx.x - 64;
+        if (e < BN) {
+          double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
+          dst[e] = (red[e] + red[BN + e]) + (red[2 * BN + e] + red[3 * BN + e]);
+        }
       }
     }
   }
@@ -306,7 +349,22 @@ inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_i8_sliced_kernel<<<dim3(p.m_tiles, n_tiles, batch), THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 148;
+  }
+  // persistent grid: one CTA per SM, count coprime to m_tiles so that every CTA cycles through all row tiles
+  auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+  const long long total = (long long)p.m_tiles * n_tiles * batch;
+  int grid = (int)(total < sms ? total : sms);
+  while (grid > 1 && total > grid && gcd(grid, p.m_tiles) != 1) grid--;
+  Params q = p;
+  q.n_tiles = n_tiles;
+  q.batch = batch;
+  gemm_i8_sliced_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, q);
   return cudaGetLastError();
 }
 
