@@ -1,0 +1,69 @@
+"""CPU restatement of the integer-slicing scheme of the INT8 mode (mogpe_b200/csrc/gemm_i8.cuh): the slicing rule, the exact
+integer accumulation per anti-diagonal of slice pairs, and the error bound the kernel header states.  Pure numpy (int64
+arithmetic stands in for the tensor cores' exact int32 accumulation); the GPU kernel is checked against the same FP64
+products in tools/i8_gemm_test.cu and tests/test_gpu_int8.py."""
+import numpy as np
+
+NS = 8
+
+
+def pow2_scale(maxabs):
+    """2^e with maxabs / 2^e < 1/2 (oz::pow2_scale)."""
+    maxabs = np.asarray(maxabs, dtype=np.float64)
+    m, e = np.frexp(maxabs)
+    return np.where(maxabs > 0, np.ldexp(1.0, e + 1), 1.0)
+
+
+def slice8(x, scale):
+    """-> int slices q[NS, ...] with x ~= scale * sum_p q_p 2^(-7 (p + 1)), |q_p| <= 64 (oz::slice8)."""
+    r = np.asarray(x, dtype=np.float64) / scale
+    q = []
+    for _ in range(NS):
+        t = r * 128.0
+        v = np.rint(t)
+        r = t - v
+        q.append(v.astype(np.int64))
+    return np.stack(q)
+
+
+def sliced_product(A, B):
+    """D = A @ B.T through row-scaled byte slices and exact integer accumulation of the pairs with i + j < NS."""
+    sa = pow2_scale(np.max(np.abs(A), axis=1))[:, None]
+    sb = pow2_scale(np.max(np.abs(B)))
+    qa, qb = slice8(A, sa), slice8(B, sb)
+    assert np.max(np.abs(qa)) <= 64 and np.max(np.abs(qb)) <= 64
+    D = np.zeros((A.shape[0], B.shape[0]))
+    for d in range(NS):
+        T = sum(qa[i] @ qb[d - i].T for i in range(d + 1))  # exact integers
+        assert np.max(np.abs(T)) < 2**31
+        D += T.astype(np.float64) * 2.0 ** (-7 * (d + 2))
+    return D * sa * sb
+
+
+def test_slices_reconstruct_to_56_bits():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(1000) * np.exp(5 * rng.standard_normal(1000))
+    s = pow2_scale(np.max(np.abs(x)))
+    q = slice8(x, s)
+    rec = s * sum(q[p] * 2.0 ** (-7 * (p + 1)) for p in range(NS))
+    assert np.max(np.abs(q)) <= 64
+    assert np.max(np.abs(rec - x)) <= s * 2.0 ** (-7 * NS - 1) * 1.0000001
+
+
+def test_sliced_product_is_fp64_accurate_even_with_cancellation():
+    """An ill-conditioned triangular operand (rows of wildly different size, sums that cancel by 1e6): the error stays at the
+    truncation bound ~ (NS + 1) K 2^(-7 NS) rowmax(A) max(B), far below what any FP32-class accumulation gives."""
+    rng = np.random.default_rng(1)
+    M, N = 96, 40
+    L = np.tril(rng.standard_normal((M, M))) + 1e-3 * np.eye(M)
+    A = np.linalg.inv(L @ L.T + 1e-6 * np.eye(M))  # entries up to ~1e6, alternating signs
+    A = np.tril(A)
+    B = rng.random((N, M))
+    want = A @ B.T
+    got = sliced_product(A, B)
+    bound = (NS + 1) * M * 2.0 ** (-7 * NS) * 4 * np.max(np.abs(A), axis=1)[:, None] * np.max(np.abs(B))
+    assert np.all(np.abs(got - want) <= bound + 1e-15 * np.abs(want).max())
+    # relative to the row scale it is ~1e-13; a float32 product of the same operands is ~1e9 times worse
+    f32 = (A.astype(np.float32) @ B.T.astype(np.float32)).astype(np.float64)
+    rowmax = np.max(np.abs(A), axis=1)[:, None]
+    assert np.max(np.abs(got - want) / rowmax) < 1e-12 < np.max(np.abs(f32 - want) / rowmax) * 1e-3
