@@ -205,7 +205,7 @@ class ClockSampler:
 def run_predict_modes(device, n_points=262144, M=1024):
     """The other data path of the north star (BASELINE config 5: predict_y + predict_mixing_probs, K = 8, G = 8, M = 1024) on a
     bounded sample of test points, once per arithmetic mode of the dense products: FP64 DMMA, INT8 tensor cores with
-    integer-sliced operands (FP64-accurate), 3xTF32 tensor cores.  Points are generated on the device; CUDA-event time."""
+    integer-sliced operands (8 slices: FP64-accurate; 6 slices: ~1e-7), 3xTF32 tensor cores.  Points are generated on the device; CUDA-event time."""
     import torch
 
     from mogpe_b200 import _lib
@@ -219,7 +219,7 @@ def run_predict_modes(device, n_points=262144, M=1024):
     out = {"workload": f"C5 sample: predict_y + predict_mixing_probs, D=4 K=8 G=8 M={M}, {n_points} test points in 65536-point "
                        "chunks, 100 Softmax Monte-Carlo draws per point from the library stream", "unit": "points/s"}
     ref = None
-    for precision in ("float64", "int8", "tf32"):
+    for precision in ("float64", "int8", "int8x6", "tf32"):
         eng = Engine(experts, gating, flavour="keras", max_batch=65536, precision=precision, device=device)
         X = DeviceBuffer((n_points, 4), device, zero=False)
         eng.fill_normal(X, seed=4)

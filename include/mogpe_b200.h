@@ -54,8 +54,11 @@ enum { MOGPE_BOUND_FURTHER_GATING = 0, MOGPE_BOUND_TIGHT = 1, MOGPE_BOUND_FURTHE
  * (FP32-class accuracy, tolerance class 1e-4); kernel matrices, Cholesky, L^-1 and the predictive means stay FP64.
  * INT8: the same two products with every FP64 operand cut into eight signed-byte slices and multiplied on the INT8
  * tensor cores with exact int32 accumulation (integer slicing / Ozaki scheme): FP64-class accuracy (the 1e-8 tolerance
- * holds), about twice the throughput of the FP64 DMMA path.  mogpe_elbo_fwd_bwd always runs in FP64. */
-enum { MOGPE_PRECISION_F64 = 0, MOGPE_PRECISION_TF32 = 1, MOGPE_PRECISION_INT8 = 2 };
+ * holds), about twice the throughput of the FP64 DMMA path.
+ * INT8X6: the same with six slices (42 significant bits, 21 instead of 36 slice pairs): errors ~1e-7 of the largest variance
+ * even for ill-conditioned Kuu -- the fast mode that meets the 1e-4 tolerance class robustly.
+ * mogpe_elbo_fwd_bwd always runs in FP64. */
+enum { MOGPE_PRECISION_F64 = 0, MOGPE_PRECISION_TF32 = 1, MOGPE_PRECISION_INT8 = 2, MOGPE_PRECISION_INT8X6 = 3 };
 /* API flavour selects the documented numerical quirks */
 enum { MOGPE_FLAVOUR_KERAS = 0, MOGPE_FLAVOUR_LEGACY = 1 };
 

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmogpe_b200.so")
 MOGPE_OK = 0
 BOUND_IDS = {"further_gating": 0, "tight": 1, "further": 2}
 FLAVOUR_IDS = {"keras": 0, "legacy": 1}
-PRECISION_IDS = {"float64": 0, "tf32": 1, "int8": 2}
+PRECISION_IDS = {"float64": 0, "tf32": 1, "int8": 2, "int8x6": 3}
 MAX_SAMPLES = 16
 MAX_LATENTS = 64
 MAX_GROUPS = 64

@@ -72,6 +72,7 @@ struct mogpe_handle {
   double *linv_scale = nullptr, *st_scale = nullptr;      // [Q | P][Mp32] row scales
   double *kuf_scale = nullptr, *aout_scale = nullptr;     // [Q] group scales
   bool i8_ready = false;
+  int ns = 8;  // byte slices per operand: 8 (INT8, FP64-class) or 6 (INT8X6, ~1e-7-class)
   int* d_t32_err = nullptr;
   // graph-replayed training step (mogpe_train_step): launches are captured once per argument set and replayed
   struct GraphEntry {
@@ -260,7 +261,8 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (d->num_latents != d->num_experts * d->output_dim + d->num_gating) return bad("num_latents != K*F + G");
   if (d->num_latents > MAXP || d->num_groups > MAXQ || d->num_groups < 1) return bad("too many latents / groups");
   if (d->max_batch < 1) return bad("max_batch must be >= 1");
-  if (d->precision != MOGPE_PRECISION_F64 && d->precision != MOGPE_PRECISION_TF32 && d->precision != MOGPE_PRECISION_INT8)
+  if (d->precision != MOGPE_PRECISION_F64 && d->precision != MOGPE_PRECISION_TF32 && d->precision != MOGPE_PRECISION_INT8 &&
+      d->precision != MOGPE_PRECISION_INT8X6)
     return bad("unknown precision");
   if (!d->group_num_inducing || !d->latent_group) return bad("null group_num_inducing / latent_group");
   int dev_count = 0;
@@ -289,6 +291,7 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
       return bad("latent_group out of range");
     }
   h->precision = d->precision;
+  h->ns = d->precision == MOGPE_PRECISION_INT8X6 ? 6 : 8;
   h->Mp = round_up(Mmax, 64);
   h->Mp32 = round_up(h->Mp, t32::BM);
   h->Bp = round_up(d->max_batch, h->precision != MOGPE_PRECISION_F64 ? t32::BN : 128);
@@ -1083,7 +1086,7 @@ static mogpe_status products_t32(mogpe_handle* h, const double* params, int Bc, 
 static mogpe_status ensure_i8(mogpe_handle* h) {
   if (h->i8_ready) return MOGPE_OK;
   const ModelDev& md = h->md_host;
-  const size_t Q = md.Q, P = md.P, M32 = h->Mp32, Bp = h->Bp, NS = oz::NS;
+  const size_t Q = md.Q, P = md.P, M32 = h->Mp32, Bp = h->Bp, NS = h->ns;
   H_CUDA(h, dalloc(&h->Linv8, Q * NS * M32 * M32));
   H_CUDA(h, dalloc(&h->ST8, P * NS * M32 * M32));
   H_CUDA(h, dalloc(&h->KufT8, Q * NS * Bp * M32));
@@ -1097,16 +1100,16 @@ static mogpe_status ensure_i8(mogpe_handle* h) {
     H_CUDA(h, dalloc(&h->d_t32_err, 1));
     H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
   }
-  if (!oz::make_map_i8(&h->tm_linv, h->Linv8, (int)Q, (int)M32, (int)M32, oz::BM) ||
-      !oz::make_map_i8(&h->tm_st, h->ST8, (int)P, (int)M32, (int)M32, oz::BM) ||
-      !oz::make_map_i8(&h->tm_kuf, h->KufT8, (int)Q, (int)Bp, (int)M32, oz::BN) ||
-      !oz::make_map_i8(&h->tm_at, h->AT8, (int)Q, (int)Bp, (int)M32, oz::BN))
+  if (!oz::make_map_i8(&h->tm_linv, h->Linv8, (int)Q, (int)M32, (int)M32, oz::BM, h->ns) ||
+      !oz::make_map_i8(&h->tm_st, h->ST8, (int)P, (int)M32, (int)M32, oz::BM, h->ns) ||
+      !oz::make_map_i8(&h->tm_kuf, h->KufT8, (int)Q, (int)Bp, (int)M32, oz::BN, h->ns) ||
+      !oz::make_map_i8(&h->tm_at, h->AT8, (int)Q, (int)Bp, (int)M32, oz::BN, h->ns))
     H_FAIL(h, MOGPE_ERR_CUDA, "cuTensorMapEncodeTiled failed (INT8 mode needs a driver with TMA tensor maps)");
   {
     int8_t* b2 = nullptr;
     H_CUDA(h, dalloc(&b2, Q * NS * Bp * M32));
     h->kuf_buf2 = b2;
-    if (!oz::make_map_i8(&h->tm_kuf2, b2, (int)Q, (int)Bp, (int)M32, oz::BN))
+    if (!oz::make_map_i8(&h->tm_kuf2, b2, (int)Q, (int)Bp, (int)M32, oz::BN, h->ns))
       H_FAIL(h, MOGPE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   }
   h->i8_ready = true;
@@ -1118,14 +1121,21 @@ static mogpe_status i8_prepare(mogpe_handle* h, const double* params, cudaStream
   const ModelDev& md = h->md_host;
   const int Q = md.Q, Mp = h->Mp, M32 = h->Mp32;
   oz::row_scale_kernel<<<dim3(M32, Q), 128, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1, h->linv_scale, M32);
-  oz::slice_square_kernel<<<dim3(M32 / 32, M32 / 32, Q), dim3(32, 8), 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1,
-                                                                              h->linv_scale, h->Linv8, M32);
+  if (h->ns == 6)
+    oz::slice_square_kernel<6><<<dim3(M32 / 32, M32 / 32, Q), dim3(32, 8), 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0,
+                                                                                   1, h->linv_scale, h->Linv8, M32);
+  else
+    oz::slice_square_kernel<8><<<dim3(M32 / 32, M32 / 32, Q), dim3(32, 8), 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0,
+                                                                                   1, h->linv_scale, h->Linv8, M32);
   if (md.nlta > 0) {
     oz::row_scale_kernel<<<dim3(M32, md.nlta), 128, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0,
                                                               h->st_scale, M32);
-    oz::slice_square_kernel<<<dim3(M32 / 32, M32 / 32, md.nlta), dim3(32, 8), 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp,
-                                                                                      h->d_lta_latent, 1, 0, h->st_scale,
-                                                                                      h->ST8, M32);
+    if (h->ns == 6)
+      oz::slice_square_kernel<6><<<dim3(M32 / 32, M32 / 32, md.nlta), dim3(32, 8), 0, st>>>(
+          h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0, h->st_scale, h->ST8, M32);
+    else
+      oz::slice_square_kernel<8><<<dim3(M32 / 32, M32 / 32, md.nlta), dim3(32, 8), 0, st>>>(
+          h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0, h->st_scale, h->ST8, M32);
   }
   oz::group_scales_kernel<<<1, MAXQ, 0, st>>>(h->d_md, params, h->lo, h->kuf_scale, h->aout_scale);
   t32::alpha_kernel<<<dim3(M32 / 128, md.NV), 128, 0, st>>>(h->d_md, h->Linv, h->V, M32, h->alpha);
@@ -1141,14 +1151,14 @@ static mogpe_status kuf_stage_i8(mogpe_handle* h, const double* params, const do
   int8_t* kt = buf ? (int8_t*)h->kuf_buf2 : h->KufT8;
   double* dp = buf ? h->dot_part2 : h->dot_part;
   const dim3 kg(Bc / 64, M32 / 128, Q);
-  if (md.D <= 2)
-    oz::kuf8_kernel<2><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles);
-  else if (md.D <= 4)
-    oz::kuf8_kernel<4><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles);
-  else if (md.D <= 8)
-    oz::kuf8_kernel<8><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles);
-  else
-    oz::kuf8_kernel<16><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles);
+#define MOGPE_KUF8(DM, NSV) \
+  oz::kuf8_kernel<DM, NSV><<<kg, 128, 0, st>>>(h->d_md, params, h->lo, X, N, h->Bp, M32, h->kuf_scale, kt, h->alpha, dp, m_tiles)
+  if (h->ns == 6) {
+    if (md.D <= 2) MOGPE_KUF8(2, 6); else if (md.D <= 4) MOGPE_KUF8(4, 6); else if (md.D <= 8) MOGPE_KUF8(8, 6); else MOGPE_KUF8(16, 6);
+  } else {
+    if (md.D <= 2) MOGPE_KUF8(2, 8); else if (md.D <= 4) MOGPE_KUF8(4, 8); else if (md.D <= 8) MOGPE_KUF8(8, 8); else MOGPE_KUF8(16, 8);
+  }
+#undef MOGPE_KUF8
   KCOUNT(h, 1);
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
@@ -1163,11 +1173,12 @@ static mogpe_status products_i8(mogpe_handle* h, const double* params, int Bc, i
   p.a_scale = h->linv_scale; p.a_scale_stride = M32; p.b_scale = h->kuf_scale;
   p.ss_part = h->ss_part; p.ld_ss = h->Bp; p.err_flag = h->d_t32_err;
   if (md.nlta > 0) {
-    p.out = h->AT8; p.out_batch_stride = (long long)oz::NS * h->Bp * M32; p.out_plane_stride = (long long)h->Bp * M32; p.ldo = M32;
+    p.out = h->AT8; p.out_batch_stride = (long long)h->ns * h->Bp * M32; p.out_plane_stride = (long long)h->Bp * M32; p.ldo = M32;
     p.out_scale = h->aout_scale;
   }
   for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = g;
-  H_CUDA(h, oz::launch(h->tm_linv, buf ? h->tm_kuf2 : h->tm_kuf, p, Bc / oz::BN, Q, st));  // A^T byte planes + sum_m A^2 partials
+  H_CUDA(h, h->ns == 6 ? oz::launch<6>(h->tm_linv, buf ? h->tm_kuf2 : h->tm_kuf, p, Bc / oz::BN, Q, st)
+                       : oz::launch<8>(h->tm_linv, buf ? h->tm_kuf2 : h->tm_kuf, p, Bc / oz::BN, Q, st));  // A^T planes + sum A^2
   h->gemm_launches++;
   KCOUNT(h, 1);
   if (md.nlta > 0) {
@@ -1179,7 +1190,8 @@ static mogpe_status products_i8(mogpe_handle* h, const double* params, int Bc, i
       p.mapA[slot] = slot;
       p.mapB[slot] = md.lta_group[slot];
     }
-    H_CUDA(h, oz::launch(h->tm_st, h->tm_at, p, Bc / oz::BN, md.nlta, st));  // sum_m (q_sqrt^T A)^2 partials
+    H_CUDA(h, h->ns == 6 ? oz::launch<6>(h->tm_st, h->tm_at, p, Bc / oz::BN, md.nlta, st)
+                         : oz::launch<8>(h->tm_st, h->tm_at, p, Bc / oz::BN, md.nlta, st));  // sum_m (q_sqrt^T A)^2 partials
     h->gemm_launches++;
     KCOUNT(h, 1);
   }
@@ -1208,7 +1220,8 @@ extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t 
   mogpe_status rc = set_mode(h, -1, 1, st);
   if (rc != MOGPE_OK) return rc;
   const int chunk_max = h->desc.max_batch;
-  const bool tf32 = h->precision == MOGPE_PRECISION_TF32, i8 = h->precision == MOGPE_PRECISION_INT8;
+  const bool tf32 = h->precision == MOGPE_PRECISION_TF32;
+  const bool i8 = h->precision == MOGPE_PRECISION_INT8 || h->precision == MOGPE_PRECISION_INT8X6;
   {
     const int nc0 = (int)std::min<int64_t>(chunk_max, N);
     if (tf32) rc = ensure_t32(h);

@@ -30,17 +30,23 @@
 namespace mogpe {
 namespace oz {
 
-constexpr int NS = 8;                 // byte slices per operand
+// NS = byte slices per operand (template parameter): 8 -> 56 significant bits, FP64-class (the 1e-8 tolerance); 6 -> 42 bits,
+// ~1e-7-class (the 1e-4 "fast mode" tolerance with a wide margin even for cond(L) ~ 1e3) at 21 instead of 36 slice pairs.
+constexpr int MAX_NS = 8;
 constexpr int BM = 128, BN = 64, BKB = 64, UKB = 32, STAGES = 2;
 constexpr int A_PLANE_BYTES = BM * BKB;            // 8 KB
 constexpr int B_PLANE_BYTES = BN * BKB;            // 4 KB
-constexpr int A_STAGE_BYTES = NS * A_PLANE_BYTES;  // 64 KB
-constexpr int B_STAGE_BYTES = NS * B_PLANE_BYTES;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int RED_BYTES = 4 * BN * 8;              // cross-warp column sums (FP64)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RED_BYTES + 1024 + 256;
+template <int NS>
+struct Cfg {
+  static constexpr int A_STAGE_BYTES = NS * A_PLANE_BYTES;  // 64 KB for NS = 8
+  static constexpr int B_STAGE_BYTES = NS * B_PLANE_BYTES;  // 32 KB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RED_BYTES + 1024 + 256;
+  static constexpr int H = NS / 2;  // accumulators T_0 .. T_(H-1) and T_H .. T_(NS-1) are combined in two int64 Horner sums
+};
 constexpr int THREADS = 320;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two per TMEM lane quarter, 32 columns each)
-constexpr int TMEM_COLS = NS * BN;                 // 512
+constexpr int TMEM_COLS = 512;  // NS accumulators of 64 columns (allocations are powers of two)
 
 struct Params {
   int m_tiles;  // row tiles of 128
@@ -131,10 +137,12 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int t) {
 // epilogue of the current one drains TMEM, so the per-tile prologue (first TMA round trip: ~4k of ~25k cycles) is hidden.
 // The host picks gridDim.x coprime to m_tiles: every CTA then cycles through all row tiles (triangular operands give them
 // different k lengths) and the static schedule is balanced.
+template <int NS>
 __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                      const __grid_constant__ CUtensorMap mapB,
                                                                      const __grid_constant__ Params p) {
   using namespace t32;
+  constexpr int A_STAGE_BYTES = Cfg<NS>::A_STAGE_BYTES, STAGE_BYTES = Cfg<NS>::STAGE_BYTES, H = Cfg<NS>::H;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -258,24 +266,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
 #pragma unroll
         for (int i = 0; i < 32; i++) acc[i] = tt[i];
 #pragma unroll 1
-        for (int d = 1; d < 4; d++) {
+        for (int d = 1; d < H; d++) {
           tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), tt);
 #pragma unroll
           for (int i = 0; i < 32; i++) acc[i] = acc[i] * 128 + tt[i];
         }
+        constexpr double W_HI = 1.0 / (double)(1ull << (7 * (H - 1)));   // 128^-(H-1)
+        constexpr double W_LO = 1.0 / (double)(1ull << (7 * (NS - 1)));  // 128^-(NS-1)
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = (double)acc[i] * (1.0 / 2097152.0);  // 128^-3
-        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * BN + c * 32), tt);
+        for (int i = 0; i < 32; i++) v[i] = (double)acc[i] * W_HI;
+        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(H * BN + c * 32), tt);
 #pragma unroll
         for (int i = 0; i < 32; i++) acc[i] = tt[i];
 #pragma unroll 1
-        for (int d = 5; d < 8; d++) {
+        for (int d = H + 1; d < NS; d++) {
           tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), tt);
 #pragma unroll
           for (int i = 0; i < 32; i++) acc[i] = acc[i] * 128 + tt[i];
         }
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = fma((double)acc[i], 1.0 / 562949953421312.0 /* 128^-7 */, v[i]) * rs;
+        for (int i = 0; i < 32; i++) v[i] = fma((double)acc[i], W_LO, v[i]) * rs;
       }
       // every accumulator value of this warp is in registers: TMEM may be overwritten by the next tile's MMAs
       tc_fence_before();
@@ -329,23 +339,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
 }
 
 // byte planes [batch][NS][rows][cols] (cols = k contiguous): box {64 k, box_rows, NS planes, 1}, 64B swizzle
-inline bool make_map_i8(CUtensorMap* map, const int8_t* ptr, int batch, int rows, int cols, int box_rows) {
+inline bool make_map_i8(CUtensorMap* map, const int8_t* ptr, int batch, int rows, int cols, int box_rows, int NS = MAX_NS) {
   t32::EncodeTiledFn fn = t32::encode_fn();
   if (!fn) return false;
   cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)NS, (cuuint64_t)batch};
   cuuint64_t strides[3] = {(cuuint64_t)cols, (cuuint64_t)rows * cols, (cuuint64_t)NS * rows * cols};
-  cuuint32_t box[4] = {BKB, (cuuint32_t)box_rows, NS, 1};
+  cuuint32_t box[4] = {BKB, (cuuint32_t)box_rows, (cuuint32_t)NS, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(ptr), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <int NS = MAX_NS>
 inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& p, int n_tiles, int batch,
                           cudaStream_t st) {
+  constexpr int SMEM_BYTES = Cfg<NS>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_sliced_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -364,7 +376,7 @@ inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
   Params q = p;
   q.n_tiles = n_tiles;
   q.batch = batch;
-  gemm_i8_sliced_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, q);
+  gemm_i8_sliced_kernel<NS><<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, q);
   return cudaGetLastError();
 }
 
@@ -377,6 +389,7 @@ __host__ __device__ inline double pow2_scale(double maxabs) {
   return ldexp(1.0, e + 1);   // maxabs < 2^e  ->  maxabs / 2^(e+1) < 1/2
 }
 
+template <int NS = MAX_NS>
 __device__ __forceinline__ void slice8(double x, double inv_scale, int8_t* q) {
   double r = x * inv_scale;
 #pragma unroll
@@ -414,6 +427,7 @@ __global__ void __launch_bounds__(128) row_scale_kernel(const double* __restrict
 
 // dst [batch][NS][n_p][n_p] byte planes of the operand (r, c) -> src(r, c) or src(c, r) (transposed), zero padded, each
 // row sliced against its own scale.   grid (n_p/32, n_p/32, batch), block (32, 8)
+template <int NS>
 __global__ void slice_square_kernel(const double* __restrict__ src, int n, long long src_batch_stride, int src_ld,
                                     const int* __restrict__ map, int transposed, int lower_only,
                                     const double* __restrict__ scale, int8_t* __restrict__ dst, int n_p) {
@@ -433,7 +447,7 @@ __global__ void slice_square_kernel(const double* __restrict__ src, int n, long 
     const int r = r0 + j, c = c0 + threadIdx.x;
     const double x = transposed ? tile[threadIdx.x][j] : tile[j][threadIdx.x];
     int8_t qv[NS];
-    slice8(x, 1.0 / scale[(long long)b * n_p + r], qv);
+    slice8<NS>(x, 1.0 / scale[(long long)b * n_p + r], qv);
     int8_t* d = dst + ((long long)b * NS * n_p + r) * n_p + c;
 #pragma unroll
     for (int p2 = 0; p2 < NS; p2++) d[(long long)p2 * n_p * n_p] = qv[p2];

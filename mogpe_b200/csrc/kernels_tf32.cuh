@@ -135,7 +135,7 @@ __global__ void group_scales_kernel(const ModelDev* __restrict__ md, const doubl
 //   KufT8[g][plane][n][k]: slices of k(z_k, x_n) / kuf_scale[g];   dot_part[v][blockIdx.y][n] = sum_k Kuf[k][n] alpha[v][k]
 // grid (Bc/64, Mp32/128, Q), block 128: warp w handles points n_base + w, w + 4, ...; lane covers the FOUR CONSECUTIVE
 // inducing indices k0 + 4 lane .. + 3, so the four bytes of a plane go out as one 32-bit store (128 B per warp).
-template <int DMAX>
+template <int DMAX, int NS>
 __global__ void __launch_bounds__(128) kuf8_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
                                                    Layout lo, const double* __restrict__ X, int N, int Bp, int Mp32,
                                                    const double* __restrict__ kuf_scale, int8_t* __restrict__ KufT,
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) kuf8_kernel(const ModelDev* __restrict__ 
       const double r2 = -2.0 * dot + (zn[j] + xn);
       kval[j] = (valid && k0 + j < Mg) ? kv * exp(-0.5 * r2) : 0.0;
       int8_t q[NS];
-      slice8(kval[j], inv_scale, q);
+      slice8<NS>(kval[j], inv_scale, q);
 #pragma unroll
       for (int s = 0; s < NS; s++) packed[s] |= (uint32_t)(uint8_t)q[s] << (8 * j);
     }

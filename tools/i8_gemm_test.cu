@@ -22,17 +22,19 @@ using namespace mogpe;
   } while (0)
 
 // dst [batch][NS][rows][cols] <- src [batch][rows][cols] with one fixed scale
+template <int NSL>
 __global__ void slice_fixed_kernel(const double* __restrict__ src, long long n_per_batch, double inv_scale,
                                    int8_t* __restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (i >= n_per_batch) return;
-  int8_t q[oz::NS];
-  oz::slice8(src[(long long)b * n_per_batch + i], inv_scale, q);
-  for (int s = 0; s < oz::NS; s++) dst[((long long)b * oz::NS + s) * n_per_batch + i] = q[s];
+  int8_t q[NSL];
+  oz::slice8<NSL>(src[(long long)b * n_per_batch + i], inv_scale, q);
+  for (int s = 0; s < NSL; s++) dst[((long long)b * NSL + s) * n_per_batch + i] = q[s];
 }
 
-int main(int argc, char** argv) {
+template <int NSL>
+int run(int argc, char** argv) {
   const int kmode = argc > 1 ? atoi(argv[1]) : 0;
   const int M = argc > 2 ? atoi(argv[2]) : 256;
   const int N = argc > 3 ? atoi(argv[3]) : 256;
@@ -41,7 +43,7 @@ int main(int argc, char** argv) {
   const bool check = reps >= 0;
   if (reps < 0) reps = -reps;
   const int K = M;
-  printf("int8-sliced gemm test: kmode=%d M=K=%d N=%d batch=%d NS=%d\n", kmode, M, N, batch, oz::NS);
+  printf("int8-sliced gemm test: kmode=%d M=K=%d N=%d batch=%d NS=%d\n", kmode, M, N, batch, NSL);
   std::mt19937_64 rng(99);
   std::normal_distribution<double> nd(0.0, 1.0);
   std::vector<double> A((size_t)batch * M * K), B((size_t)batch * N * K);
@@ -63,19 +65,19 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dA, A.size() * 8));
   CK(cudaMalloc(&dB, B.size() * 8));
   CK(cudaMalloc(&dScale, (size_t)batch * M * 8));
-  CK(cudaMalloc(&A8, A.size() * oz::NS));
-  CK(cudaMalloc(&B8, B.size() * oz::NS));
-  CK(cudaMalloc(&O8, (size_t)batch * oz::NS * N * M));
+  CK(cudaMalloc(&A8, A.size() * NSL));
+  CK(cudaMalloc(&B8, B.size() * NSL));
+  CK(cudaMalloc(&O8, (size_t)batch * NSL * N * M));
   CK(cudaMalloc(&ss, (size_t)batch * (M / 128) * N * 8));
   CK(cudaMalloc(&err, 4));
   CK(cudaMemset(err, 0, 4));
-  CK(cudaMemset(O8, 0x7f, (size_t)batch * oz::NS * N * M));
+  CK(cudaMemset(O8, 0x7f, (size_t)batch * NSL * N * M));
   CK(cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, B.data(), B.size() * 8, cudaMemcpyHostToDevice));
   oz::row_scale_kernel<<<dim3(M, batch), 128>>>(dA, M, (long long)M * K, K, nullptr, 0, 0, dScale, M);
-  oz::slice_square_kernel<<<dim3(M / 32, M / 32, batch), dim3(32, 8)>>>(dA, M, (long long)M * K, K, nullptr, 0, 0, dScale, A8, M);
+  oz::slice_square_kernel<NSL><<<dim3(M / 32, M / 32, batch), dim3(32, 8)>>>(dA, M, (long long)M * K, K, nullptr, 0, 0, dScale, A8, M);
   const double bscale = oz::pow2_scale(bmax);
-  slice_fixed_kernel<<<dim3((unsigned)(((long long)N * K + 255) / 256), batch), 256>>>(dB, (long long)N * K, 1.0 / bscale, B8);
+  slice_fixed_kernel<NSL><<<dim3((unsigned)(((long long)N * K + 255) / 256), batch), 256>>>(dB, (long long)N * K, 1.0 / bscale, B8);
   CK(cudaGetLastError());
   // output scale: |D| <= rowmax(A) * bmax * K is far too pessimistic for slicing; the test uses the true max of D
   std::vector<double> Dref((size_t)batch * M * N);
@@ -94,13 +96,13 @@ int main(int argc, char** argv) {
   }
   const double oscale = oz::pow2_scale(dmax);
   CUtensorMap mapA, mapB;
-  if (!oz::make_map_i8(&mapA, A8, batch, M, K, oz::BM)) { printf("tensor map A failed\n"); return 3; }
-  if (!oz::make_map_i8(&mapB, B8, batch, N, K, oz::BN)) { printf("tensor map B failed\n"); return 3; }
+  if (!oz::make_map_i8(&mapA, A8, batch, M, K, oz::BM, NSL)) { printf("tensor map A failed\n"); return 3; }
+  if (!oz::make_map_i8(&mapB, B8, batch, N, K, oz::BN, NSL)) { printf("tensor map B failed\n"); return 3; }
   oz::Params p;
   memset(&p, 0, sizeof(p));
   p.m_tiles = M / 128; p.K = K; p.kmode = kmode;
   p.a_scale = dScale; p.a_scale_stride = M;
-  p.out = O8; p.out_batch_stride = (long long)oz::NS * N * M; p.out_plane_stride = (long long)N * M; p.ldo = M;
+  p.out = O8; p.out_batch_stride = (long long)NSL * N * M; p.out_plane_stride = (long long)N * M; p.ldo = M;
   p.ss_part = ss; p.ld_ss = N; p.err_flag = err;
   std::vector<double> hs(2 * batch);
   for (int b = 0; b < batch; b++) {
@@ -110,12 +112,12 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dsc, hs.size() * 8));
   CK(cudaMemcpy(dsc, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
   p.b_scale = dsc; p.out_scale = dsc + batch;
-  CK(oz::launch(mapA, mapB, p, N / oz::BN, batch, 0));
+  CK(oz::launch<NSL>(mapA, mapB, p, N / oz::BN, batch, 0));
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(se)); return 4; }
   bool pass = true;
   if (check) {
-    std::vector<int8_t> O((size_t)batch * oz::NS * N * M);
+    std::vector<int8_t> O((size_t)batch * NSL * N * M);
     std::vector<double> SS((size_t)batch * (M / 128) * N);
     CK(cudaMemcpy(O.data(), O8, O.size(), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(SS.data(), ss, SS.size() * 8, cudaMemcpyDeviceToHost));
@@ -128,14 +130,16 @@ int main(int argc, char** argv) {
         for (int k = 0; k < K; k++) arow = fmax(arow, fabs(A[((size_t)(batch - 1 - b) * M + m) * K + k]));
         for (int n = 0; n < N; n++) {
           double got = 0, w = 1.0 / 128.0;
-          for (int s = 0; s < oz::NS; s++) { got += w * (double)O[(((size_t)b * oz::NS + s) * N + n) * M + m]; w /= 128.0; }
+          for (int s = 0; s < NSL; s++) { got += w * (double)O[(((size_t)b * NSL + s) * N + n) * M + m]; w /= 128.0; }
           got *= oscale;
           const double want = Dref[((size_t)b * M + m) * N + n];
           // error unit: the slicing resolution of the OUTPUT planes (2^-57 oscale) plus the product error bound
           const double rel = fabs(got - want) / (arow * bmax * K + 1e-300);
           if (rel > max_rel) max_rel = rel;
-          if (!(fabs(got - want) <= 1e-12 * arow * bmax * K + oscale * 1e-15) && bad < 6) {
-            printf("  bad b=%d m=%d n=%d got=%.17g want=%.17g\n", b, m, n, got, want);
+          const double tol = NSL == 8 ? 1e-12 : 3e-8;  // product truncation ~ (NS+1) K 2^(-7 NS), relative to the row scale
+          if (!(fabs(got - want) <= tol * arow * bmax * K + oscale * (NSL == 8 ? 1e-15 : 1e-11))) {
+            if (bad < 6)
+              printf("  bad b=%d m=%d n=%d got=%.17g want=%.17g\n", b, m, n, got, want);
             bad++;
           }
           colss[(size_t)(m / 128) * N + n] += want * want;
@@ -148,7 +152,7 @@ int main(int argc, char** argv) {
     }
     printf("max |err| / (rowmax(A) max(B) K) = %.3e (re-sliced output)   max rel err of column sums of squares = %.3e\n", max_rel,
            max_ss_rel);
-    pass = bad == 0 && max_ss_rel < 1e-10;
+    pass = bad == 0 && max_ss_rel < (NSL == 8 ? 1e-10 : 1e-6);
     printf(pass ? "PASS\n" : "FAIL\n");
   }
   if (reps > 0) {
@@ -158,9 +162,9 @@ int main(int argc, char** argv) {
     for (int variant = 0; variant < 3; variant++) {
       p.out = variant == 1 ? O8 : nullptr;
       p.ss_part = variant == 2 ? nullptr : ss;
-      oz::launch(mapA, mapB, p, N / oz::BN, batch, 0);
+      oz::launch<NSL>(mapA, mapB, p, N / oz::BN, batch, 0);
       cudaEventRecord(e0);
-      for (int r = 0; r < reps; r++) oz::launch(mapA, mapB, p, N / oz::BN, batch, 0);
+      for (int r = 0; r < reps; r++) oz::launch<NSL>(mapA, mapB, p, N / oz::BN, batch, 0);
       cudaEventRecord(e1);
       CK(cudaDeviceSynchronize());
       float ms;
@@ -168,9 +172,14 @@ int main(int argc, char** argv) {
       const double frac = kmode == 0 ? 1.0 : 0.5;
       const double flops = 2.0 * M * (double)K * N * batch * frac;
       printf("%s: %.3f ms/launch, %.1f TFLOP/s FP64-equivalent algorithmic (x%d INT8 MMAs: %.0f TOP/s)\n",
-             variant == 1 ? "with re-sliced output" : variant == 2 ? "no epilogue outputs (main loop + TMEM read + combine only)" : "stats only", ms / reps, flops / (ms / reps * 1e-3) * 1e-12, oz::NS * (oz::NS + 1) / 2,
-             oz::NS * (oz::NS + 1) / 2 * flops / (ms / reps * 1e-3) * 1e-12);
+             variant == 1 ? "with re-sliced output" : variant == 2 ? "no epilogue outputs (main loop + TMEM read + combine only)" : "stats only", ms / reps, flops / (ms / reps * 1e-3) * 1e-12, NSL * (NSL + 1) / 2,
+             NSL * (NSL + 1) / 2 * flops / (ms / reps * 1e-3) * 1e-12);
     }
   }
   return pass ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+  const int ns = getenv("I8_NS") ? atoi(getenv("I8_NS")) : 8;
+  return ns == 6 ? run<6>(argc, argv) : run<8>(argc, argv);
 }
