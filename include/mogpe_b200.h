@@ -57,7 +57,8 @@ enum { MOGPE_BOUND_FURTHER_GATING = 0, MOGPE_BOUND_TIGHT = 1, MOGPE_BOUND_FURTHE
  * holds), about twice the throughput of the FP64 DMMA path.
  * INT8X6: the same with six slices (42 significant bits, 21 instead of 36 slice pairs): errors ~1e-7 of the largest variance
  * even for ill-conditioned Kuu -- the fast mode that meets the 1e-4 tolerance class robustly.
- * mogpe_elbo_fwd_bwd always runs in FP64. */
+ * mogpe_elbo_fwd_bwd uses the mode only when it is called WITHOUT gradients (evaluation: test_step / elbo()); a call with
+ * gradients always runs in FP64. */
 enum { MOGPE_PRECISION_F64 = 0, MOGPE_PRECISION_TF32 = 1, MOGPE_PRECISION_INT8 = 2, MOGPE_PRECISION_INT8X6 = 3 };
 /* API flavour selects the documented numerical quirks */
 enum { MOGPE_FLAVOUR_KERAS = 0, MOGPE_FLAVOUR_LEGACY = 1 };

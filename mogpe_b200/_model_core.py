@@ -122,7 +122,8 @@ class MixtureCore:
         """"float64" (default, gpflow's default_float); "int8" / "int8x6": predict_* run their M x M x N products on the INT8
         tensor cores with integer-sliced operands and exact accumulation (8 slices: float64-accurate, ~1.7x; 6 slices: ~1e-7,
         ~2.4x the FP64 throughput at M = 1024); "tf32": 3xTF32 on the tcgen05 tensor cores (FP32-class accuracy, ~4x).
-        The ELBO always runs in FP64."""
+        Gradient-free ELBO evaluations (test_step, elbo()) use the mode too; anything with gradients (fit, train_step)
+        always runs in FP64."""
         from . import _lib
 
         if precision not in _lib.PRECISION_IDS:

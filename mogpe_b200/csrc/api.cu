@@ -662,6 +662,9 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
 }
 
 static mogpe_status dp_allreduce(mogpe_handle* h, double* buf, size_t n, cudaStream_t st);  // defined with the NCCL loader
+// forward conditional (statistics + means) through the tensor-core products of the handle's precision mode
+static mogpe_status forward_tensor_core(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X,
+                                        int N, cudaStream_t st);
 
 // One thread per data point with a long serial body: prefer more, smaller blocks until every SM has work
 // (8192 points in 128-thread blocks are only 64 CTAs for 148 SMs).
@@ -729,11 +732,18 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   if (grads) H_CUDA(h, cudaMemsetAsync(grads, 0, lo.total * sizeof(double), st));
 
   // ---------------- forward ----------------
-  rc = factorise(h, params, eps_u, S, X, N, Bc, st);
-  if (rc != MOGPE_OK) return rc;
+  if (!grads && h->precision != MOGPE_PRECISION_F64) {
+    // evaluation only (test_step / elbo()): the conditional runs in the handle's tensor-core mode; a call that wants
+    // gradients always takes the FP64 path below
+    rc = forward_tensor_core(h, params, eps_u, S, X, N, st);
+    if (rc != MOGPE_OK) return rc;
+  } else {
+    rc = factorise(h, params, eps_u, S, X, N, Bc, st);
+    if (rc != MOGPE_OK) return rc;
+    rc = conditional_fwd(h, params, X, N, Bc, st, true);
+    if (rc != MOGPE_OK) return rc;
+  }
   KCOUNT(h, 3);  // lik, kl, finish
-  rc = conditional_fwd(h, params, X, N, Bc, st, true);
-  if (rc != MOGPE_OK) return rc;
 
   LikArgs la;
   la.md = h->d_md; la.params = params; la.lo = lo; la.mean = h->mean; la.var0ss = h->var0ss; la.varq = h->varq;
@@ -1201,6 +1211,20 @@ static mogpe_status products_i8(mogpe_handle* h, const double* params, int Bc, i
                                                                            h->varq);
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
+}
+
+static mogpe_status forward_tensor_core(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X,
+                                        int N, cudaStream_t st) {
+  const bool tf32 = h->precision == MOGPE_PRECISION_TF32;
+  mogpe_status rc = tf32 ? ensure_t32(h) : ensure_i8(h);
+  if (rc != MOGPE_OK) return rc;
+  rc = factorise(h, params, eps_u, S, X, N, round_up(N, 128), st, false);
+  if (rc == MOGPE_OK) rc = tf32 ? t32_prepare(h, st) : i8_prepare(h, params, st);
+  if (rc != MOGPE_OK) return rc;
+  const int Bc = round_up(N, t32::BN);
+  rc = tf32 ? kuf_stage_t32(h, params, X, N, Bc, 0, st) : kuf_stage_i8(h, params, X, N, Bc, 0, st);
+  if (rc == MOGPE_OK) rc = tf32 ? products_t32(h, params, Bc, 0, st) : products_i8(h, params, Bc, 0, st);
+  return rc;
 }
 
 extern "C" mogpe_status mogpe_predict(mogpe_handle* h, const double* X, int64_t N, const double* params,

@@ -61,7 +61,8 @@ class ElboResult:
 class Engine:
     def __init__(self, experts: List[GPBlock], gating: GPBlock, flavour="keras", max_batch=1024, device=0,
                  jitter=DEFAULT_JITTER, precision="float64"):
-        """precision of predict()'s M x M x N products (the ELBO always runs in FP64): "float64" (gpflow default_float; FP64
+        """precision of the M x M x N products of predict() and of gradient-free elbo() calls (calls with gradients always run
+        in FP64): "float64" (gpflow default_float; FP64
         DMMA), "int8" / "int8x6" (INT8 tensor cores, integer-sliced operands with exact accumulation: 8 slices are
         float64-accurate, 6 slices ~1e-7), "tf32" (3xTF32 on the tcgen05 tensor cores, FP32-class accuracy)."""
         self.lib = _lib.load()

@@ -124,3 +124,24 @@ def test_int8x6_fast_mode_meets_the_1e4_class_on_ill_conditioned_models(K, F, se
         assert _rel(out["f_var"][:, l:l + L], fv) < 1e-5
         l += L
     eng.close()
+
+
+@pytest.mark.parametrize("bound", ["further_gating", "tight", "further"])
+@pytest.mark.parametrize("precision,rtol", [("int8", 1e-8), ("int8x6", 1e-5), ("tf32", 2e-3)])
+def test_forward_only_elbo_uses_the_tensor_core_mode(bound, precision, rtol):
+    """elbo() without gradients (the reference's test_step / validation loss) evaluates the conditional in the engine's
+    tensor-core mode: inducing-sample means for every sample, marginal variances with the q_sqrt term where the bound needs
+    them.  With gradients the same engine stays on the FP64 path (checked to 1e-8)."""
+    from oracle import ref_numpy as rn
+    from tests._engine_helpers import engine_from_spec, run_engine_elbo
+
+    spec, X, Y, eps = make_spec(seed=12, N=300, D=2, F=2, K=2, M=60, S=3, bound=bound, num_data=3000, separate_kernels=True)
+    eng = engine_from_spec(spec, max_batch=300, precision=precision)
+    ref = rn.elbo(spec, X, Y, eps)
+    fwd = run_engine_elbo(eng, spec, X, Y, eps, want_grads=False)
+    assert abs(fwd.elbo - ref) <= rtol * abs(ref)
+    full = run_engine_elbo(eng, spec, X, Y, eps, want_grads=True)
+    assert abs(full.elbo - ref) <= 1e-8 * abs(ref)
+    if precision != "int8":
+        assert fwd.elbo != full.elbo  # a different arithmetic really ran
+    eng.close()

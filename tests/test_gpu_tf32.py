@@ -97,7 +97,7 @@ def test_tf32_and_float64_engines_agree_and_tf32_is_not_float64():
     e32.close()
 
 
-def test_tf32_elbo_still_runs_in_float64():
+def test_tf32_elbo_with_gradients_still_runs_in_float64():
     from oracle import ref_numpy as rn
     from tests._engine_helpers import engine_from_spec, run_engine_elbo
 
@@ -119,8 +119,8 @@ def test_unknown_precision_is_rejected():
 
 @pytest.mark.parametrize("flavour", ["keras", "legacy"])
 def test_public_api_set_precision(flavour):
-    """model.set_precision("tf32") switches predict_y / predict_mixing_probs to the tcgen05 path and back; training
-    (fit / maximum_log_likelihood_objective) stays float64 in both modes."""
+    """model.set_precision("tf32") switches predict_y / predict_mixing_probs (and gradient-free ELBO evaluations) to the
+    tcgen05 path and back; training (fit / train_step / elbo_and_gradients) stays float64 in both modes."""
     from oracle import ref_numpy as rn
     from tests._model_helpers import model_from_spec
 
@@ -133,8 +133,11 @@ def test_public_api_set_precision(flavour):
     d32 = model.predict_y(X)
     assert _rel(d32.mean(), ym) < RTOL_TF32 and _rel(d32.variance(), yv) < RTOL_TF32
     assert not np.array_equal(np.asarray(d32.variance()), np.asarray(d64.variance()))
-    val = model.maximum_log_likelihood_objective((X, Y), eps=eps)
-    assert abs(val - rn.elbo(spec, X, Y, eps)) <= RTOL_F64 * abs(val)
+    ref = rn.elbo(spec, X, Y, eps)
+    val = model.maximum_log_likelihood_objective((X, Y), eps=eps)  # evaluation only: runs in the tensor-core mode too
+    assert abs(val - ref) <= RTOL_TF32 * abs(ref)
+    val_g, _ = model.elbo_and_gradients((X, Y), eps=eps)           # with gradients: always the FP64 path
+    assert abs(val_g - ref) <= RTOL_F64 * abs(ref)
     model.set_precision("float64")
     d64b = model.predict_y(X)
     assert np.array_equal(np.asarray(d64b.variance()), np.asarray(d64.variance()))
