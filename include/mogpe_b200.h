@@ -200,6 +200,11 @@ mogpe_status mogpe_fill_normal(mogpe_handle* h, double* dst, int64_t n, uint64_t
 mogpe_status mogpe_nccl_unique_id(char out[128]);
 mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int32_t rank, int32_t world_size);
 mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_t n, void* cuda_stream);
+/* The two [M x M] results of the backward that are reduced over the minibatch (Lbar = -tril(W A^T), Sbar = 2 tril(A diag(d)
+ * LTA^T)) run on the INT8 tensor cores with integer-sliced operands and exact accumulation (FP64-class accuracy, section 4c of
+ * DESIGN.md) when M is a multiple of 128, M >= 256 and the batch has >= 2048 rows; on (default) / off selects it. */
+mogpe_status mogpe_set_int8_backward(mogpe_handle* h, int32_t on);
+
 /* on != 0: mogpe_elbo_fwd_bwd performs the data-parallel reduction itself and returns globally summed gradients and
  * results -- the part of the gradient buffer that is final before the Cholesky backward (q_mu, q_sqrt, mean, noise and, when
  * out == grads + layout.total, the 4 results: 99.9 % of the bytes) is all-reduced on a communication stream underneath

@@ -72,6 +72,12 @@ struct mogpe_handle {
   double *linv_scale = nullptr, *st_scale = nullptr;      // [Q | P][Mp32] row scales
   double *kuf_scale = nullptr, *aout_scale = nullptr;     // [Q] group scales
   bool i8_ready = false;
+  // INT8 products inside the FP64 backward: the two [M x M] results reduced over the minibatch (Lbar = -tril(W A^T),
+  // Sbar = 2 tril(A diag(d) LTA^T)) on the INT8 tensor cores with integer-sliced operands (exact accumulation: FP64-class)
+  int8_t *bW8 = nullptr, *bA8 = nullptr, *bLD8 = nullptr;   // [Q | Q | P][8][Mp][Bp] byte planes, n contiguous
+  double *bw_scale = nullptr, *ba_scale = nullptr, *bld_scale = nullptr;  // [Q | Q | P][Mp] row scales
+  CUtensorMap tm_bw, tm_ba64, tm_ba128, tm_bld;
+  bool i8_bwd_ready = false, i8_bwd_on = true;
   int ns = 8;  // byte slices per operand: 8 (INT8, FP64-class) or 6 (INT8X6, ~1e-7-class)
   int* d_t32_err = nullptr;
   // graph-replayed training step (mogpe_train_step): launches are captured once per argument set and replayed
@@ -210,6 +216,12 @@ static void free_ws(mogpe_handle* h) {
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->ev_comm_fork) cudaEventDestroy(h->ev_comm_fork);
   if (h->ev_comm_join) cudaEventDestroy(h->ev_comm_join);
+  if (h->bW8) cudaFree(h->bW8);
+  if (h->bA8) cudaFree(h->bA8);
+  if (h->bLD8) cudaFree(h->bLD8);
+  if (h->bw_scale) cudaFree(h->bw_scale);
+  if (h->ba_scale) cudaFree(h->ba_scale);
+  if (h->bld_scale) cudaFree(h->bld_scale);
   if (h->Linv8) cudaFree(h->Linv8);
   if (h->ST8) cudaFree(h->ST8);
   if (h->KufT8) cudaFree(h->KufT8);
@@ -662,6 +674,8 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
 }
 
 static mogpe_status dp_allreduce(mogpe_handle* h, double* buf, size_t n, cudaStream_t st);  // defined with the NCCL loader
+// Lbar and Sbar of the backward on the INT8 tensor cores (returns MOGPE_ERR_UNSUPPORTED when the shape does not qualify)
+static mogpe_status int8_backward_products(mogpe_handle* h, const double* params, double* grads, int Bc, int N, cudaStream_t st);
 // forward conditional (statistics + means) through the tensor-core products of the handle's precision mode
 static mogpe_status forward_tensor_core(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X,
                                         int N, cudaStream_t st);
@@ -822,26 +836,35 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
       kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q, nsplit), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads, n_chunk);
     sk_end(h, SK_KUF_GRAD, ks, 8.0 * Q * (2.0 * Mp * N + (double)N * md.D));  // read W and Kuf, X
   }
-  {  // Lbar = -tril(W A^T)
-    GemmParams p = gp_init();
-    p.A = h->W; p.sA = (long long)Mp * Bp; p.lda = Bp;
-    p.B = h->A; p.sB = (long long)Mp * Bp; p.ldb = Bp;
-    p.C = h->Lbar; p.sC = (long long)Mp * Mp; p.ldc = Mp;
-    p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = -1.0;
-    p.ksplit = reduce_ksplit(Mp, Q, Bc);
-    if (p.ksplit > 1) H_CUDA(h, cudaMemsetAsync(h->Lbar, 0, sizeof(double) * (size_t)Q * Mp * Mp, st));
-    H_CUDA(h, hgemm(h, p, Q, false, true, st, (double)Q * Mp * Mp * Bc));
+  // Lbar = -tril(W A^T) and Sbar_l = 2 tril(A diag(dfvar_l) LTA_l^T): [M x M] results reduced over the minibatch
+  bool reduced_on_int8 = false;
+  if (h->i8_bwd_on && Mp % 128 == 0 && Mp >= 256 && Bc >= 2048) {
+    mogpe_status irc = int8_backward_products(h, params, grads, Bc, N, st);
+    if (irc == MOGPE_OK) reduced_on_int8 = true;
+    else if (irc != MOGPE_ERR_UNSUPPORTED) return irc;
   }
-  if (md.nlta > 0) {
-    // Sbar_l = 2 tril(A_g diag(dfvar_l) LTA_l^T): diag(dfvar_l) is applied to the A-operand fragments per k
-    GemmParams p = gp_init();
-    p.A = h->A;   p.sA = (long long)Mp * Bp; p.lda = Bp; p.mapA = h->d_lta_group;
-    p.B = h->LTA; p.sB = (long long)Mp * Bp; p.ldb = Bp;
-    p.C = grads + lo.q_sqrt; p.sC = (long long)Mp * Mp; p.ldc = Mp; p.mapC = h->d_lta_latent;
-    p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = 2.0; p.beta = 1.0;
-    p.kscale = h->dfvar; p.sks = Bp; p.mapK = h->d_lta_latent;
-    p.ksplit = reduce_ksplit(Mp, md.nlta, Bc);  // beta = 1: the partial sums are added onto the KL gradient already there
-    H_CUDA(h, hgemm(h, p, md.nlta, false, true, st, (double)md.nlta * Mp * Mp * Bc));
+  if (!reduced_on_int8) {
+    {  // Lbar = -tril(W A^T)
+      GemmParams p = gp_init();
+      p.A = h->W; p.sA = (long long)Mp * Bp; p.lda = Bp;
+      p.B = h->A; p.sB = (long long)Mp * Bp; p.ldb = Bp;
+      p.C = h->Lbar; p.sC = (long long)Mp * Mp; p.ldc = Mp;
+      p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = -1.0;
+      p.ksplit = reduce_ksplit(Mp, Q, Bc);
+      if (p.ksplit > 1) H_CUDA(h, cudaMemsetAsync(h->Lbar, 0, sizeof(double) * (size_t)Q * Mp * Mp, st));
+      H_CUDA(h, hgemm(h, p, Q, false, true, st, (double)Q * Mp * Mp * Bc));
+    }
+    if (md.nlta > 0) {
+      // Sbar_l = 2 tril(A_g diag(dfvar_l) LTA_l^T): diag(dfvar_l) is applied to the A-operand fragments per k
+      GemmParams p = gp_init();
+      p.A = h->A;   p.sA = (long long)Mp * Bp; p.lda = Bp; p.mapA = h->d_lta_group;
+      p.B = h->LTA; p.sB = (long long)Mp * Bp; p.ldb = Bp;
+      p.C = grads + lo.q_sqrt; p.sC = (long long)Mp * Mp; p.ldc = Mp; p.mapC = h->d_lta_latent;
+      p.M = Mp; p.N = Mp; p.K = Bc; p.tril_out = 1; p.alpha = 2.0; p.beta = 1.0;
+      p.kscale = h->dfvar; p.sks = Bp; p.mapK = h->d_lta_latent;
+      p.ksplit = reduce_ksplit(Mp, md.nlta, Bc);  // beta = 1: the partial sums are added onto the KL gradient already there
+      H_CUDA(h, hgemm(h, p, md.nlta, false, true, st, (double)md.nlta * Mp * Mp * Bc));
+    }
   }
   q_grads_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, st>>>(h->d_md, lo, h->dV, eps_u, S, grads);
   if (dp) {
@@ -1213,6 +1236,93 @@ static mogpe_status products_i8(mogpe_handle* h, const double* params, int Bc, i
   return MOGPE_OK;
 }
 
+static mogpe_status int8_backward_products(mogpe_handle* h, const double* params, double* grads, int Bc, int N,
+                                           cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;
+  constexpr int NS = 8;
+  if (!h->i8_bwd_ready) {
+    if (!t32::encode_fn()) return MOGPE_ERR_UNSUPPORTED;  // no TMA tensor maps: stay on the DMMA path
+    const size_t plane = (size_t)NS * Mp * Bp;
+    H_CUDA(h, dalloc(&h->bW8, Q * plane));
+    H_CUDA(h, dalloc(&h->bA8, Q * plane));
+    H_CUDA(h, dalloc(&h->bLD8, P * plane));
+    H_CUDA(h, dalloc(&h->bw_scale, (size_t)Q * Mp));
+    H_CUDA(h, dalloc(&h->ba_scale, (size_t)Q * Mp));
+    H_CUDA(h, dalloc(&h->bld_scale, (size_t)P * Mp));
+    if (!h->kuf_scale) H_CUDA(h, dalloc(&h->kuf_scale, (size_t)Q));
+    if (!h->aout_scale) H_CUDA(h, dalloc(&h->aout_scale, (size_t)Q));
+    if (!h->d_t32_err) {
+      H_CUDA(h, dalloc(&h->d_t32_err, 1));
+      H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
+    }
+    if (!oz::make_map_i8(&h->tm_bw, h->bW8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_ba64, h->bA8, Q, Mp, Bp, oz::BN, NS) ||
+        !oz::make_map_i8(&h->tm_ba128, h->bA8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_bld, h->bLD8, P, Mp, Bp, oz::BN, NS))
+      return MOGPE_ERR_UNSUPPORTED;
+    h->graphs_dirty = true;
+    h->i8_bwd_ready = true;
+  }
+  const int m_tiles = Mp / oz::BM, n_tiles = Mp / oz::BN;
+  const dim3 sg((Bp / 4 + 255) / 256, Mp, 1);
+  // operands: A with its group bound |A| <= sqrt(kvar) as the scale of every row, W with measured row maxima
+  oz::group_scales_kernel<<<1, MAXQ, 0, st>>>(h->d_md, params, h->lo, h->kuf_scale, h->aout_scale);
+  oz::fill_row_scale_kernel<<<dim3((Mp + 127) / 128, Q), 128, 0, st>>>(h->aout_scale, nullptr, h->ba_scale, Mp);
+  oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, Q), 256, 0, st>>>(h->A, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
+                                                                 h->ba_scale, h->bA8, Mp);
+  oz::row_scale_n_kernel<<<dim3(Mp, Q), 256, 0, st>>>(h->W, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
+                                                      h->bw_scale, Mp);
+  oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, Q), 256, 0, st>>>(h->W, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
+                                                                 h->bw_scale, h->bW8, Mp);
+  KCOUNT(h, 5);
+  H_CUDA(h, cudaGetLastError());
+  auto ksplit_for = [&](int batch) {
+    const int tiles = batch * (m_tiles * (m_tiles + 1));  // lower-triangular 128 x 64 tiles: sum_t 2 (t + 1)
+    return std::max(1, std::min((8 * 148 + tiles - 1) / tiles, Bc / 1024));  // ~8 pieces per CTA smooth the static schedule
+  };
+  {
+    H_CUDA(h, cudaMemsetAsync(h->Lbar, 0, sizeof(double) * (size_t)Q * Mp * Mp, st));
+    oz::Params p;
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = m_tiles; p.K = Bc; p.kmode = t32::K_FULL;
+    p.a_scale = h->bw_scale; p.a_scale_stride = Mp;
+    p.b_row_scale = h->ba_scale; p.b_row_scale_stride = Mp;
+    p.out64 = h->Lbar; p.out64_batch_stride = (long long)Mp * Mp; p.ld64 = Mp; p.alpha64 = -1.0; p.tril64 = 1;
+    p.ksplit = ksplit_for(Q);
+    p.err_flag = h->d_t32_err;
+    for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
+    H_CUDA(h, oz::launch<NS>(h->tm_bw, h->tm_ba64, p, n_tiles, Q, st));
+    h->gemm_launches++;
+    KCOUNT(h, 1);
+  }
+  if (md.nlta > 0) {
+    const int nl = md.nlta;
+    // B operand: LTA_l diag(dfvar_l), rows scaled by their own maxima
+    oz::row_scale_n_kernel<<<dim3(Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
+                                                       h->d_lta_latent, h->bld_scale, Mp);
+    oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
+                                                                    h->d_lta_latent, h->bld_scale, h->bLD8, Mp);
+    KCOUNT(h, 2);
+    oz::Params p;
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = m_tiles; p.K = Bc; p.kmode = t32::K_FULL;
+    p.a_scale = h->ba_scale; p.a_scale_stride = Mp;
+    p.b_row_scale = h->bld_scale; p.b_row_scale_stride = Mp;
+    p.out64 = grads + h->lo.q_sqrt; p.out64_batch_stride = (long long)Mp * Mp; p.ld64 = Mp; p.alpha64 = 2.0; p.tril64 = 1;
+    p.ksplit = ksplit_for(nl);
+    p.err_flag = h->d_t32_err;
+    for (int slot = 0; slot < nl; slot++) {
+      p.mapA[slot] = md.lta_group[slot];
+      p.mapB[slot] = slot;
+      p.mapC[slot] = md.lta_latent[slot];
+    }
+    H_CUDA(h, oz::launch<NS>(h->tm_ba128, h->tm_bld, p, n_tiles, nl, st));
+    h->gemm_launches++;
+    KCOUNT(h, 1);
+  }
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
 static mogpe_status forward_tensor_core(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X,
                                         int N, cudaStream_t st) {
   const bool tf32 = h->precision == MOGPE_PRECISION_TF32;
@@ -1468,6 +1578,13 @@ extern "C" mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int
 static mogpe_status dp_allreduce(mogpe_handle* h, double* buf, size_t n, cudaStream_t st) {
   int rc = g_nccl.AllReduce(buf, buf, n, 8, 0, h->nccl_comm, st);  // ncclFloat64 = 8, ncclSum = 0
   if (rc != 0) H_FAIL(h, MOGPE_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_set_int8_backward(mogpe_handle* h, int32_t on) {
+  if (!h) return MOGPE_ERR_INVALID;
+  h->i8_bwd_on = on != 0;
+  h->graphs_dirty = true;
   return MOGPE_OK;
 }
 

@@ -63,8 +63,19 @@ struct Params {
   const double* out_scale;   // [batch] (device): 2^e of the re-sliced result (|D| / 2^e <= 1/2)
   double* ss_part;           // optional [batch][m_tiles][ld_ss] column sums of squares per row tile
   int ld_ss;
+  // optional FP64 result, ADDED (atomicAdd) into out64[mapC[batch]][m][n] (not transposed): the caller pre-sets it (zeros, or
+  // the value to accumulate onto).  tril64: only elements with n <= m; tiles wholly above the diagonal are skipped.
+  // ksplit > 1: the k range of every tile is cut into pieces handled as separate tiles (few large-K tiles otherwise).
+  double* out64;
+  long long out64_batch_stride;
+  int ld64;
+  double alpha64;
+  int tril64;
+  int ksplit;
+  const double* b_row_scale;       // optional [B batches][b_row_scale_stride]: 2^e per ROW of the B operand (instead of b_scale)
+  long long b_row_scale_stride;
   int* err_flag;
-  int mapA[64], mapB[64];
+  int mapA[64], mapB[64], mapC[64];
 };
 
 __device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
@@ -114,21 +125,45 @@ __device__ __forceinline__ void tmem_ld32_i(uint32_t taddr, int* v) {
 // same time work on neighbouring tiles and share their B tiles in L2.
 struct TileInfo {
   int m_tile, n_tile, batch, m0, n0, k_begin, num_kb;
+  bool skip;  // tile wholly above the diagonal of a lower-triangular result
 };
 __device__ __forceinline__ TileInfo decode_tile(const Params& p, int t) {
   using namespace t32;
   TileInfo ti;
-  const int mr = t % p.m_tiles, rest = t / p.m_tiles;
-  ti.m_tile = (p.kmode == K_UPPER) ? mr : p.m_tiles - 1 - mr;
-  ti.n_tile = rest % p.n_tiles;
-  ti.batch = rest / p.n_tiles;
+  const int ks = p.ksplit > 1 ? p.ksplit : 1;
+  const int split = t % ks;
+  t /= ks;
+  if (p.tril64) {
+    // lower-triangular result: only the (row tile m, column tile n) pairs with 64 n <= 128 m + 127, i.e. n <= 2 m + 1, are
+    // enumerated: pair index j in [0, m_tiles (m_tiles + 1)), row tile m holds 2 (m + 1) column tiles
+    const int per_batch = p.m_tiles * (p.m_tiles + 1);
+    const int j = t % per_batch;
+    int m = (int)((sqrtf(4.0f * (float)j + 1.0f) - 1.0f) * 0.5f);
+    while (m * (m + 1) > j) m--;
+    while ((m + 1) * (m + 2) <= j) m++;
+    ti.m_tile = m;
+    ti.n_tile = j - m * (m + 1);
+    ti.batch = t / per_batch;
+  } else {
+    const int mr = t % p.m_tiles, rest = t / p.m_tiles;
+    ti.m_tile = (p.kmode == K_UPPER) ? mr : p.m_tiles - 1 - mr;
+    ti.n_tile = rest % p.n_tiles;
+    ti.batch = rest / p.n_tiles;
+  }
   ti.m0 = ti.m_tile * BM;
   ti.n0 = ti.n_tile * BN;
   int k_begin = 0, k_end = p.K;
   if (p.kmode == K_LOWER) k_end = min(p.K, ti.m0 + BM);
   if (p.kmode == K_UPPER) k_begin = ti.m0 / BKB * BKB;
+  int nkb = (k_end - k_begin) / BKB;
+  if (ks > 1) {  // this piece of the k range
+    const int per = (nkb + ks - 1) / ks, b0 = split * per, b1 = min(nkb, b0 + per);
+    k_begin += b0 * BKB;
+    nkb = max(0, b1 - b0);
+  }
   ti.k_begin = k_begin;
-  ti.num_kb = (k_end - k_begin) / BKB;
+  ti.num_kb = nkb;
+  ti.skip = nkb == 0;
   return ti;
 }
 
@@ -155,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.batch;
+  const int total_tiles = (p.tril64 ? p.m_tiles * (p.m_tiles + 1) : p.m_tiles * p.n_tiles) * p.batch * (p.ksplit > 1 ? p.ksplit : 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -185,6 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileInfo ti = decode_tile(p, t);
+        if (ti.skip) continue;
         const int ca = p.mapA[ti.batch], cb = p.mapB[ti.batch];
         for (int kb = 0; kb < ti.num_kb; kb++, it++) {
           const int s = it % STAGES;
@@ -200,9 +236,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop (converged); one elected lane issues =====
-    int it = 0, tile_i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_i++) {
+    int it = 0, tile_i = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileInfo ti = decode_tile(p, t);
+      if (ti.skip) continue;
+      tile_i++;
       if (tile_i > 0) {  // the epilogue must have drained the previous tile's accumulators
         mbar_wait(acc_empty, (uint32_t)((tile_i - 1) & 1), p.err_flag);
         tc_fence_after();
@@ -244,15 +282,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
     // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
     const int c = (warp - 2) >> 2;
-    int tile_i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_i++) {
+    int tile_i = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileInfo ti = decode_tile(p, t);
+      if (ti.skip) continue;
+      tile_i++;
       const int batch = ti.batch, m_tile = ti.m_tile, n0 = ti.n0;
       mbar_wait(acc_full, (uint32_t)(tile_i & 1), p.err_flag);
       tc_fence_after();
       const int row = ti.m0 + q * 32 + lane;
       // 2^(ea + eb) * 2^(-14): T_d carries 2^(-7 (d + 2))
-      const double rs = p.a_scale[(long long)p.mapA[batch] * p.a_scale_stride + row] * p.b_scale[p.mapB[batch]] * (1.0 / 16384.0);
+      const double rs = p.a_scale[(long long)p.mapA[batch] * p.a_scale_stride + row] *
+                        (p.b_row_scale ? 1.0 : p.b_scale[p.mapB[batch]]) * (1.0 / 16384.0);
       int8_t* ocol = nullptr;
       if (p.out) ocol = p.out + (long long)batch * p.out_batch_stride + (long long)n0 * p.ldo + row;
       const double oinv = p.out ? 1.0 / p.out_scale[batch] : 0.0;
@@ -291,6 +332,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty)) : "memory");
+      if (p.b_row_scale) {
+        const double* bs = p.b_row_scale + (long long)p.mapB[batch] * p.b_row_scale_stride + n0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] *= bs[i];
+      }
+      if (p.out64) {
+        double* o = p.out64 + (long long)p.mapC[batch] * p.out64_batch_stride + (long long)row * p.ld64 + n0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+          if (!p.tril64 || n0 + c * 32 + i <= row) atomicAdd(o + i, p.alpha64 * v[i]);
+      }
       if (p.out) {
 #pragma unroll
         for (int i = 0; i < 32; i++) {
@@ -370,7 +422,7 @@ inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
   }
   // persistent grid: one CTA per SM, count coprime to m_tiles so that every CTA cycles through all row tiles
   auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
-  const long long total = (long long)p.m_tiles * n_tiles * batch;
+  const long long total = (long long)(p.tril64 ? p.m_tiles * (p.m_tiles + 1) : p.m_tiles * n_tiles) * batch * (p.ksplit > 1 ? p.ksplit : 1);
   int grid = (int)(total < sms ? total : sms);
   while (grid > 1 && total > grid && gcd(grid, p.m_tiles) != 1) grid--;
   Params q = p;
@@ -452,6 +504,77 @@ __global__ void slice_square_kernel(const double* __restrict__ src, int n, long 
 #pragma unroll
     for (int p2 = 0; p2 < NS; p2++) d[(long long)p2 * n_p * n_p] = qv[p2];
   }
+}
+
+}  // namespace oz
+}  // namespace mogpe
+
+// ---- slicing of [rows][n] matrices along n (the reduction index of the M x M results of the backward) -------------------
+namespace mogpe {
+namespace oz {
+
+// scale[b][r] = pow2_scale(max_n |src[b][r][n] * cs[n]|) for n < N (cs optional column scale, batch via cs_map); padded rows 1.
+// grid (rows_p, batch), block 256
+__global__ void __launch_bounds__(256) row_scale_n_kernel(const double* __restrict__ src, int rows, int N,
+                                                          long long src_batch_stride, int ld, const int* __restrict__ map,
+                                                          const double* __restrict__ cs, long long cs_stride,
+                                                          const int* __restrict__ cs_map, double* __restrict__ scale,
+                                                          int rows_p) {
+  __shared__ double red[8];
+  const int r = blockIdx.x, b = blockIdx.y, sb = map ? map[b] : b;
+  double m = 0.0;
+  if (r < rows) {
+    const double* s = src + (long long)sb * src_batch_stride + (long long)r * ld;
+    const double* c = cs ? cs + (long long)(cs_map ? cs_map[b] : b) * cs_stride : nullptr;
+    for (int n = threadIdx.x; n < N; n += 256) m = fmax(m, fabs(c ? s[n] * c[n] : s[n]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) m = fmax(m, red[w]);
+    scale[(long long)b * rows_p + r] = pow2_scale(fmax(m, red[0]));
+  }
+}
+
+// dst[b][plane][r][n] byte planes of src[b][r][n] * cs[n] / scale[b][r]  (zero for r >= rows or n >= N); every thread slices
+// four consecutive n and stores one 32-bit word per plane (coalesced 128 B per warp).  grid (ld/1024, rows_p, batch), block 256
+template <int NS>
+__global__ void __launch_bounds__(256) slice_rows_n_kernel(const double* __restrict__ src, int rows, int N,
+                                                           long long src_batch_stride, int ld, const int* __restrict__ map,
+                                                           const double* __restrict__ cs, long long cs_stride,
+                                                           const int* __restrict__ cs_map, const double* __restrict__ scale,
+                                                           int8_t* __restrict__ dst, int rows_p) {
+  const int n4 = (blockIdx.x * 256 + threadIdx.x) * 4, r = blockIdx.y, b = blockIdx.z, sb = map ? map[b] : b;
+  if (n4 >= ld) return;
+  uint32_t packed[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) packed[s] = 0;
+  if (r < rows && n4 < N) {
+    const double* sp = src + (long long)sb * src_batch_stride + (long long)r * ld + n4;
+    const double* c = cs ? cs + (long long)(cs_map ? cs_map[b] : b) * cs_stride + n4 : nullptr;
+    const double inv = 1.0 / scale[(long long)b * rows_p + r];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      double x = (n4 + j < N) ? sp[j] : 0.0;
+      if (c) x *= c[j];
+      int8_t q[NS];
+      slice8<NS>(x, inv, q);
+#pragma unroll
+      for (int s = 0; s < NS; s++) packed[s] |= (uint32_t)(uint8_t)q[s] << (8 * j);
+    }
+  }
+  int8_t* d = dst + (((long long)b * NS) * rows_p + r) * ld + n4;
+#pragma unroll
+  for (int s = 0; s < NS; s++) *reinterpret_cast<uint32_t*>(d + (long long)s * rows_p * ld) = packed[s];
+}
+
+// scale[b][r] = group_scale[map[b]] for every row (operands whose bound is known per group, e.g. |A| <= sqrt(kvar))
+__global__ void fill_row_scale_kernel(const double* __restrict__ group_scale, const int* __restrict__ map,
+                                      double* __restrict__ scale, int rows_p) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (r < rows_p) scale[(long long)b * rows_p + r] = group_scale[map ? map[b] : b];
 }
 
 }  // namespace oz

@@ -385,6 +385,11 @@ class Engine:
                                              float(scale), self.out_ptr, out_pinned_ptr, self.grads_ptr, self.u.ptr, float(lr),
                                              float(beta_1), float(beta_2), float(epsilon), int(t), int(use_graph)), self.h)
 
+    def set_int8_backward(self, on: bool):
+        """Lbar / Sbar of the backward on the INT8 tensor cores (integer-sliced, exact accumulation) when the shape qualifies
+        (default on); off keeps them on the FP64 DMMA pipe."""
+        _lib.check(self.lib.mogpe_set_int8_backward(self.h, 1 if on else 0), self.h)
+
     def graph_stats(self):
         """-> (captured training-step graphs, capture disabled after a failure)."""
         n, d = C.c_int32(), C.c_int32()

@@ -305,3 +305,32 @@ def test_predict_softmax_library_draws_are_chunking_independent_and_close_to_exp
     big = a.predict(X, want=("mix_probs",), num_mc=4000)["mix_probs"]
     ref = a.predict(X, want=("mix_probs",), eps_mc=np.random.default_rng(0).standard_normal((4000, N, K)))["mix_probs"]
     assert np.max(np.abs(big - ref)) < 0.03  # two independent 4000-draw estimates: std <= 0.5 / sqrt(4000) each
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+@pytest.mark.parametrize("bound", ["further_gating", "further"])
+def test_int8_backward_products_match_oracle_gradients(flavour, bound):
+    """At M >= 256 (multiple of 128) and >= 2048 rows the two minibatch-reduced [M x M] results of the backward (Lbar, Sbar) run
+    on the INT8 tensor cores (integer-sliced operands, exact accumulation).  Gradients must still meet the float64 tolerance
+    against the oracle, agree with the FP64 DMMA path, and really come from a different code path."""
+    from oracle import ref_torch as rt
+    from tests._engine_helpers import engine_from_spec, engine_grads_named, oracle_grads_constrained, run_engine_elbo
+
+    spec, X, Y, eps = make_spec(seed=17, N=2048, D=2, F=1, K=2, M=256, S=1, flavour=flavour, bound=bound, num_data=20000)
+    eng = engine_from_spec(spec, max_batch=2048)
+    ref, grads_u = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    want = oracle_grads_constrained(spec, grads_u)
+    res = run_engine_elbo(eng, spec, X, Y, eps)
+    assert abs(res.elbo - ref) <= RTOL_VALUE * abs(ref)
+    got = engine_grads_named(res, spec)
+    for name, g in want.items():
+        assert np.max(np.abs(np.asarray(got[name]) - g)) <= RTOL_GRAD * max(1.0, np.max(np.abs(g))), name
+    eng.set_int8_backward(False)
+    got64 = engine_grads_named(run_engine_elbo(eng, spec, X, Y, eps), spec)
+    differs = False
+    for name, g in got64.items():
+        a, b = np.asarray(got[name]), np.asarray(g)
+        assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b))), name
+        differs = differs or not np.array_equal(a, b)
+    assert differs
+    eng.close()
