@@ -202,7 +202,7 @@ mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int32_t rank, 
 mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_t n, void* cuda_stream);
 /* The two [M x M] results of the backward that are reduced over the minibatch (Lbar = -tril(W A^T), Sbar = 2 tril(A diag(d)
  * LTA^T)) run on the INT8 tensor cores with integer-sliced operands and exact accumulation (FP64-class accuracy, section 4c of
- * DESIGN.md) when M is a multiple of 128, M >= 256 and the batch has >= 2048 rows; on (default) / off selects it. */
+ * DESIGN.md) when M is a multiple of 128, M >= 512 and the batch has >= 2048 rows; on (default) / off selects it. */
 mogpe_status mogpe_set_int8_backward(mogpe_handle* h, int32_t on);
 
 /* on != 0: mogpe_elbo_fwd_bwd performs the data-parallel reduction itself and returns globally summed gradients and

@@ -838,7 +838,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   }
   // Lbar = -tril(W A^T) and Sbar_l = 2 tril(A diag(dfvar_l) LTA_l^T): [M x M] results reduced over the minibatch
   bool reduced_on_int8 = false;
-  if (h->i8_bwd_on && Mp % 128 == 0 && Mp >= 256 && Bc >= 2048) {
+  if (h->i8_bwd_on && Mp % 128 == 0 && Mp >= 512 && Bc >= 2048) {  // measured: M = 256 is faster on DMMA + split-K
     mogpe_status irc = int8_backward_products(h, params, grads, Bc, N, st);
     if (irc == MOGPE_OK) reduced_on_int8 = true;
     else if (irc != MOGPE_ERR_UNSUPPORTED) return irc;

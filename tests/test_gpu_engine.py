@@ -310,13 +310,13 @@ def test_predict_softmax_library_draws_are_chunking_independent_and_close_to_exp
 @pytest.mark.parametrize("flavour", FLAVOURS)
 @pytest.mark.parametrize("bound", ["further_gating", "further"])
 def test_int8_backward_products_match_oracle_gradients(flavour, bound):
-    """At M >= 256 (multiple of 128) and >= 2048 rows the two minibatch-reduced [M x M] results of the backward (Lbar, Sbar) run
+    """At M >= 512 (multiple of 128) and >= 2048 rows the two minibatch-reduced [M x M] results of the backward (Lbar, Sbar) run
     on the INT8 tensor cores (integer-sliced operands, exact accumulation).  Gradients must still meet the float64 tolerance
     against the oracle, agree with the FP64 DMMA path, and really come from a different code path."""
     from oracle import ref_torch as rt
     from tests._engine_helpers import engine_from_spec, engine_grads_named, oracle_grads_constrained, run_engine_elbo
 
-    spec, X, Y, eps = make_spec(seed=17, N=2048, D=2, F=1, K=2, M=256, S=1, flavour=flavour, bound=bound, num_data=20000)
+    spec, X, Y, eps = make_spec(seed=17, N=2048, D=2, F=1, K=2, M=512, S=1, flavour=flavour, bound=bound, num_data=20000)
     eng = engine_from_spec(spec, max_batch=2048)
     ref, grads_u = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
     want = oracle_grads_constrained(spec, grads_u)
