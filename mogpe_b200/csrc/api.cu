@@ -178,7 +178,7 @@ static cudaError_t dalloc(T** p, size_t n) {
   return cudaMalloc((void**)p, n * sizeof(T));
 }
 
-extern "C" const char* mogpe_version(void) { return "mogpe_b200 0.3 (sm_100a: fp64 DMMA; tcgen05 tf32x3 and int8-sliced)"; }
+extern "C" const char* mogpe_version(void) { return "mogpe_b200 0.4 (sm_100a: fp64 DMMA + int8-sliced tcgen05 in the step; tcgen05 tf32x3 / int8 predict modes)"; }
 
 extern "C" const char* mogpe_last_error(const mogpe_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -1024,7 +1024,7 @@ static mogpe_status ensure_t32(mogpe_handle* h) {
   H_CUDA(h, dalloc(&h->ST32, P * 2 * M32 * M32));
   H_CUDA(h, dalloc(&h->KufT32, Q * 2 * Bp * M32));
   H_CUDA(h, dalloc(&h->AT32, Q * 2 * Bp * M32));
-  H_CUDA(h, dalloc(&h->alpha, P * M32));
+  H_CUDA(h, dalloc(&h->alpha, P * MOGPE_MAX_SAMPLES * M32));  // one vector per (latent, sample): NV <= P * S
   H_CUDA(h, dalloc(&h->d_t32_err, 1));
   H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
   if (!t32::make_map_kmajor(&h->tm_linv, h->Linv32, (int)Q, (int)M32, (int)M32, t32::BM) ||
@@ -1128,7 +1128,7 @@ static mogpe_status ensure_i8(mogpe_handle* h) {
   H_CUDA(h, dalloc(&h->st_scale, P * M32));
   H_CUDA(h, dalloc(&h->kuf_scale, Q));
   H_CUDA(h, dalloc(&h->aout_scale, Q));
-  if (!h->alpha) H_CUDA(h, dalloc(&h->alpha, P * M32));
+  if (!h->alpha) H_CUDA(h, dalloc(&h->alpha, P * MOGPE_MAX_SAMPLES * M32));  // one vector per (latent, sample): NV <= P * S
   if (!h->d_t32_err) {
     H_CUDA(h, dalloc(&h->d_t32_err, 1));
     H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));

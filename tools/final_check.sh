@@ -1,5 +1,4 @@
-# final verification of the round: full GPU suite, smoke, default bench line, C5 at full size in the three modes
+# final verification of the round: full GPU suite, smoke, default bench line (C5 at full size: tools/predict_bench.py)
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
 timeout 400 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -1 gpurun_out/bench_default.err; python tools/show_bench.py gpurun_out/bench_default.json
-for p in int8 tf32; do timeout 600 python tools/predict_bench.py 100000000 1024 $p 2>&1 | grep "predict_y +"; done
