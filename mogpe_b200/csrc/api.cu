@@ -1126,8 +1126,8 @@ static mogpe_status ensure_i8(mogpe_handle* h) {
   H_CUDA(h, dalloc(&h->AT8, Q * NS * Bp * M32));
   H_CUDA(h, dalloc(&h->linv_scale, Q * M32));
   H_CUDA(h, dalloc(&h->st_scale, P * M32));
-  H_CUDA(h, dalloc(&h->kuf_scale, Q));
-  H_CUDA(h, dalloc(&h->aout_scale, Q));
+  if (!h->kuf_scale) H_CUDA(h, dalloc(&h->kuf_scale, Q));  // (shared with the INT8 products of the backward)
+  if (!h->aout_scale) H_CUDA(h, dalloc(&h->aout_scale, Q));
   if (!h->alpha) H_CUDA(h, dalloc(&h->alpha, P * MOGPE_MAX_SAMPLES * M32));  // one vector per (latent, sample): NV <= P * S
   if (!h->d_t32_err) {
     H_CUDA(h, dalloc(&h->d_t32_err, 1));
