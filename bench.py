@@ -426,6 +426,9 @@ def main():
             "profiled_pass_ms_per_step": ms_prof / steps,
             "gemm_launches_per_step": prof["gemm_launches"] / steps,
             "step_model_tflops": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12,
+            "note": "DMMA launches only: for M >= 512 the two minibatch-reduced [M x M] products of the backward (Lbar, Sbar) run on "
+                    "the INT8 tensor cores (integer-sliced operands, exact accumulation: gemm_i8_sliced_kernel) and are not part of "
+                    "`achieved`; step_model_tflops counts the whole step's algorithmic FLOPs (SURVEY 8d) against the step time",
             "traffic": 1.071e9,
             "traffic_note": "dram read+write of the largest launch (A = Linv*Kuf, 16 groups) from profiles/gemm_ncu_full_r01f.csv; "
                             "its algorithmic bytes are 2 * Q*M*B*8 = 1.074e9 (read Kuf, write A): no re-reads",
