@@ -196,3 +196,17 @@ def test_parameter_versions_track_every_change_and_arrays_are_read_only():
         p.unconstrained[0] = 5.0  # read-only view: cannot bypass the version counter
     q = Parameter(1.0)
     assert q.version > p.version  # one global clock: stamps of different parameters never collide
+
+
+def test_ctypes_prototypes_have_the_header_arity():
+    """Every entry point is bound with as many ctypes argument types as the header declares parameters (ABI drift between
+    include/mogpe_b200.h and mogpe_b200/_lib.py would otherwise only show up as corrupted arguments on the GPU box)."""
+    header = open(os.path.join(ROOT, "include", "mogpe_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decls = dict(re.findall(r"\b(mogpe_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert len(decls) >= 40
+    for name, args in decls.items():
+        args = " ".join(args.split())
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        restype, argtypes = _lib._PROTOS[name]
+        assert len(argtypes) == n, (name, n, len(argtypes))
