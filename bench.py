@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the mogpe hot path: minibatch ELBO forward+backward of MixtureOfSVGPExperts.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4] [--impl ours|reference] [--scaling weak|strong]
 
 One "step" = one pass of the hot path over one synthetic minibatch: draw the Monte-Carlo normals on the
 device, ELBO forward + full backward (gradients of every kernel / inducing / variational parameter), and
@@ -28,13 +28,39 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "C1": dict(D=1, F=1, K=2, M=32, batch=16, num_data=93, sep=False, cpu_rows=16),
-    "C2": dict(D=1, F=1, K=3, M=128, batch=8192, num_data=100_000, sep=False, cpu_rows=8192),
-    "C3": dict(D=2, F=2, K=2, M=256, batch=16384, num_data=1_000_000, sep=True, cpu_rows=4096),
-    "C4": dict(D=4, F=1, K=8, M=512, batch=8192, num_data=10_000_000, sep=False, cpu_rows=2048),
+    # `batch` = rows per GPU under weak scaling; `strong_global` = the fixed global batch of --scaling strong
+    "C1": dict(D=1, F=1, K=2, M=32, batch=16, num_data=93, sep=False, strong_global=16),
+    "C2": dict(D=1, F=1, K=3, M=128, batch=8192, num_data=100_000, sep=False, strong_global=8192),
+    "C3": dict(D=2, F=2, K=2, M=256, batch=16384, num_data=1_000_000, sep=True, strong_global=16384),
+    "C4": dict(D=4, F=1, K=8, M=512, batch=8192, num_data=10_000_000, sep=False, strong_global=65536),
 }
 BOUND, FLAVOUR, S = "further_gating", "keras", 1
-FP64_TENSOR_PEAK_TFLOPS = 37.0  # measured DMMA issue peak on this pool (profiles/fp64_probe_r01.log)
+FP64_TENSOR_PEAK_FALLBACK = 37.0  # DMMA issue peak measured on this pool in round 1 (profiles/fp64_probe_r01.log)
+
+
+def fp64_tensor_peak(device):
+    """FP64 tensor (DMMA) issue peak measured NOW on this GPU by the library's probe kernel (MEASURED_PEAKS.json holds only
+    HBM and bf16 figures and the profiling recipe states no FP64 fallback)."""
+    import ctypes as C
+
+    from mogpe_b200 import _lib
+
+    v = C.c_double()
+    _lib.check(_lib.load().mogpe_probe_fp64_tensor_peak(device, C.byref(v)))
+    return float(v.value)
+
+
+def measured_traffic(kernel_key):
+    """dram read+write bytes per launch of the dominant kernel from the committed `ncu --set full` summary of this round
+    (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        e = t[kernel_key]
+        return float(e["dram_bytes_per_launch"]), f"{e['source']} ({e.get('what', kernel_key)}); algorithmic {e.get('algorithmic_bytes')}"
+    except Exception as exc:  # loud, not silent: the line says the figure is missing instead of repeating a stale constant
+        return None, f"NO COMMITTED ncu CAPTURE for '{kernel_key}' in profiles/traffic.json ({type(exc).__name__})"
 
 
 def _hbm_peak():
@@ -202,7 +228,7 @@ class ClockSampler:
         return out
 
 
-def run_predict_modes(device, n_points=262144, M=1024):
+def run_predict_modes(device, n_points=262144, M=1024, fp64_peak=None):
     """The other data path of the north star (BASELINE config 5: predict_y + predict_mixing_probs, K = 8, G = 8, M = 1024) on a
     bounded sample of test points, once per arithmetic mode of the dense products: FP64 DMMA, INT8 tensor cores with
     integer-sliced operands (8 slices: FP64-accurate; 6 slices: ~1e-7), 3xTF32 tensor cores.  Points are generated on the device; CUDA-event time."""
@@ -244,10 +270,54 @@ def run_predict_modes(device, n_points=262144, M=1024):
             ref = got
         flops = 16 * 2.0 * M * M * n_points  # (P_e + P_g) * 2 M^2 per point
         out[precision] = {"value": n_points / (ms * 1e-3), "ms": ms, "algorithmic_tflops": flops / ms * 1e-9,
-                          "frac_of_fp64_tensor_peak": flops / ms * 1e-9 / FP64_TENSOR_PEAK_TFLOPS,
+                          "frac_of_fp64_tensor_peak": flops / ms * 1e-9 / (fp64_peak or FP64_TENSOR_PEAK_FALLBACK),
                           "max_rel_diff_vs_float64": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))}
         eng.close()
         del X, ym, yv, mix
+    return out
+
+
+def dp_parity_check(eng, wl, B, rank, world, pool, scale, local_rank):
+    """Numerical check of the data-parallel path at the bench shape (run by every `--gpus N > 1` invocation, so the
+    overlapped NCCL reduction is verified on the 8-GPU box): one extra step with FIXED draws on all ranks, against the same
+    global minibatch evaluated on rank 0 alone, shard by shard, with the in-library reduction switched off and the partial
+    [gradients | results] buffers summed on the host.  -> {"elbo_rel", "grad_max_rel"} on rank 0, None elsewhere."""
+    import torch.distributed as dist
+
+    from mogpe_b200 import _lib
+
+    K, F, M = wl["K"], wl["F"], wl["M"]
+    G = 1 if K == 2 else K
+    r_u, r_h = np.random.default_rng(77), np.random.default_rng(78)
+    eps_u = eng.pack_eps_u([r_u.standard_normal((S, F, M)) for _ in range(K)], None, S)
+    eps_h = r_h.standard_normal((S, B * world, G))
+    shard = lambda r: synth_batch(wl, B, seed=100 + r * pool)
+    sl = lambda r: np.ascontiguousarray(eps_h[:, r * B:(r + 1) * B])
+    X, Y = shard(rank)
+    eng.elbo(X, Y, BOUND, S, scale, eps_u=eps_u, eps_h=sl(rank), want_grads=True, unpack=False, readback=False)
+    if world > 1:
+        eng.allreduce(eng.gbuf)
+    got = eng.gbuf.numpy()
+    out = None
+    if rank == 0:
+        _lib.check(eng.lib.mogpe_set_dp_overlap(eng.h, 0), eng.h)  # no collective below: ranks 1.. are idle
+        acc = np.zeros_like(got)
+        for r in range(world):
+            Xr, Yr = shard(r)
+            eng.elbo(Xr, Yr, BOUND, S, scale, eps_u=eps_u, eps_h=sl(r), want_grads=True, unpack=False, readback=False)
+            acc += eng.gbuf.numpy()
+        lo = eng.lo
+        bounds = [lo.lengthscales, lo.variance, lo.Z, lo.q_mu, lo.q_sqrt, lo.mean_c, lo.noise, lo.total]
+        gmax = 0.0
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            gmax = max(gmax, float(np.max(np.abs(got[a:b] - acc[a:b])) / max(1e-300, np.max(np.abs(acc[a:b])))))
+        out = {"elbo_rel": float(abs(got[-4] - acc[-4]) / abs(acc[-4])), "grad_max_rel": gmax,
+               "elbo_dp": float(got[-4]), "elbo_single": float(acc[-4]),
+               "how": f"fixed draws; {world}-rank overlapped NCCL step vs the same {B * world}-row minibatch on rank 0 alone "
+                      "(shard by shard, no collective, host sum); grad_max_rel = worst block-wise max|diff| / max|grad|"}
+        _lib.check(eng.lib.mogpe_set_dp_overlap(eng.h, 1 if getattr(eng, "dp_overlap", False) else 0), eng.h)
+    if world > 1:
+        dist.barrier()
     return out
 
 
@@ -258,6 +328,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: fixed rows per GPU (default, BASELINE config 4 at 8 GPUs); strong: fixed global batch "
+                         "(SURVEY 8d: 65536 rows for C4) split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
     args = ap.parse_args()
@@ -265,26 +338,35 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    steps, warmup = args.steps, max(args.warmup, 3 if args.impl == "ours" else 0)
+    n_arm = world if args.impl == "ours" else max(1, args.gpus)
+    steps, warmup = args.steps, max(args.warmup, 3)
     K = wl["K"]
     G = 1 if K == 2 else K
+    if args.scaling == "strong":
+        if wl["strong_global"] % n_arm:
+            raise SystemExit(f"--scaling strong: global batch {wl['strong_global']} is not divisible by {n_arm} GPUs")
+        B = wl["strong_global"] // n_arm
+    else:
+        B = wl["batch"]
     cfg = {"workload": f"{args.workload}: D={wl['D']} F={wl['F']} K={K} G={G} M={wl['M']} S={S} "
-                       f"bound={BOUND} flavour={FLAVOUR}, batch {wl['batch']}/GPU (global {wl['batch'] * world}), "
+                       f"bound={BOUND} flavour={FLAVOUR}, batch {B}/GPU (global {B * n_arm}), "
                        f"num_data={wl['num_data']}",
-           "batch_per_gpu": wl["batch"], "global_batch": wl["batch"] * world, "M": wl["M"], "K": K, "D": wl["D"],
+           "batch_per_gpu": B, "global_batch": B * n_arm, "M": wl["M"], "K": K, "D": wl["D"],
            "l2": "per-step working set (A, Kuf, W, ... = 4*Q*M*B*8 B) is far larger than the 126 MB L2 for C2-C4; "
                  "minibatches cycle through a 4-batch pool",
-           "parallelism": f"dp{world}: minibatch rows sharded, params replicated, one NCCL all-reduce of grads"}
+           "parallelism": f"dp{n_arm}: minibatch rows sharded, params replicated, one NCCL all-reduce of grads"}
     spec = synth_model(wl)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        rows = wl["cpu_rows"]
-        cb, dt = run_cpu_reference(wl, spec, max(1, steps), min(warmup, 2), rows)
+        # the restated reference on the host cores, full per-step batch of the workload (bounded at 8192 rows: the CPU step
+        # is row-linear apart from the M^3 Cholesky terms, and 65536 rows would need > 20 GB of autograd intermediates)
+        rows = min(B * n_arm, 8192)
+        cb, dt = run_cpu_reference(wl, spec, max(1, steps), warmup, rows)
         line = {"impl": "reference", "metric": "elbo_fwd_bwd_points_per_sec", "value": cb["value"], "unit": "points/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 2), "ms_per_step": dt * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "restated reference (torch-CPU float64, oracle/ref_torch.py): TensorFlow/GPflow/TFP are not "
@@ -301,7 +383,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B = wl["batch"]
     experts, gating = blocks_from_spec(spec)
     eng = Engine(experts, gating, flavour=FLAVOUR, max_batch=B, device=local_rank)
     eng.set_seed(1234 + rank)
@@ -313,11 +394,6 @@ def main():
     pool = 4
     host_batches = [synth_batch(wl, B, seed=100 + rank * pool + i) for i in range(pool)]
     dev_batches = [(DeviceBuffer.from_numpy(x, local_rank), DeviceBuffer.from_numpy(y, local_rank)) for x, y in host_batches]
-    pinned = []
-    for x, y in host_batches:
-        px = torch.from_numpy(x).pin_memory()
-        py = torch.from_numpy(y).pin_memory()
-        pinned.append((px, py, px.numpy(), py.numpy()))
 
     def step(i):
         x, y = dev_batches[i % pool]
@@ -351,7 +427,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches_timed = eng.profile_read()["all_launches"]  # counters run even with event timing off
-    # second pass over the same K steps with every DMMA GEMM launch bracketed by CUDA events (roofline numbers).
+    # second pass over the same K steps with every dense-product launch bracketed by CUDA events (roofline numbers).
     # The events serialise the side-stream overlap, so this pass is a little slower than the timed one; `value`
     # comes from the clean pass above.
     eng.profile(True)
@@ -367,11 +443,13 @@ def main():
     eng.profile(False)
     clocks = sampler.stop() if sampler else None
     elbo_val = eng.gbuf.numpy(offset=eng.lo.total, count=4)
+    dp_parity = dp_parity_check(eng, wl, B, rank, world, pool, scale, local_rank) if world > 1 else None
+    fp64_peak = fp64_tensor_peak(local_rank) if rank == 0 else None
 
     # End to end through the public API a user of the reference calls: MixtureOfSVGPExperts.fit (Keras flavour).
-    # Every step copies its minibatch host -> device (staged through pinned memory inside mogpe_elbo_fwd_bwd_host),
-    # runs ELBO forward + backward, [all-reduces the gradients], applies the device-side Adam step, and reads the 4
-    # result scalars back (device -> host) before the next step starts.
+    # Every step copies its minibatch host -> device (staged through pinned memory inside the library), runs ELBO forward +
+    # backward, [all-reduces the gradients], applies the device-side Adam step, and reads the 4 result scalars back
+    # (device -> host, asynchronously into pinned memory; fit() synchronises on them at the end of the epoch).
     del eng, dev_batches
     model = build_public_model(spec, wl, device=local_rank)
     model.set_seed(4321 + rank)
@@ -405,10 +483,11 @@ def main():
     pts = float(B * world * steps)
     value = pts / (ms * 1e-3)
     gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) * 1e-12 if prof["gemm_ms"] > 0 else None
+    traffic, traffic_note = measured_traffic("gemm_dmma_A")
     line = {
         "metric": "elbo_fwd_bwd_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "steps_per_sec": steps / (ms * 1e-3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg, "clocks": clocks,
         "e2e": {"value": pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(B * (wl["D"] + wl["F"]) * 8), "d2h_bytes_per_step": 32,
@@ -418,10 +497,11 @@ def main():
         "gpu_launches": int(launches_timed),
         "roofline": {
             "bound": "tensor", "kernel": "mogpe::gemm_dmma_kernel (all instances: A=Linv*Kuf, S^T*A, Linv^T*Abar, W*A^T, ...)",
-            "achieved": gemm_tflops, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-            "frac": None if gemm_tflops is None else gemm_tflops / FP64_TENSOR_PEAK_TFLOPS,
-            "peak_source": "measured FP64 DMMA issue peak of this pool's B200 (profiles/fp64_probe_r01.log; cuBLAS DGEMM "
-                           "reaches 35.4); MEASURED_PEAKS.json holds only HBM and bf16 figures",
+            "achieved": gemm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": None if gemm_tflops is None else gemm_tflops / fp64_peak,
+            "peak_source": "FP64 tensor (DMMA) issue peak measured in THIS run by mogpe_probe_fp64_tensor_peak (independent "
+                           f"mma.sync.m8n8k4.f64 chains on every SM; round-1 value {FP64_TENSOR_PEAK_FALLBACK}, cuBLAS DGEMM "
+                           "35.4); MEASURED_PEAKS.json holds only HBM and bf16 figures",
             "gemm_ms_per_step": prof["gemm_ms"] / steps, "gemm_share_of_step": prof["gemm_ms"] / ms_prof,
             "profiled_pass_ms_per_step": ms_prof / steps,
             "gemm_launches_per_step": prof["gemm_launches"] / steps,
@@ -429,12 +509,12 @@ def main():
             "note": "DMMA launches only: for M >= 512 the two minibatch-reduced [M x M] products of the backward (Lbar, Sbar) run on "
                     "the INT8 tensor cores (integer-sliced operands, exact accumulation: gemm_i8_sliced_kernel) and are not part of "
                     "`achieved`; step_model_tflops counts the whole step's algorithmic FLOPs (SURVEY 8d) against the step time",
-            "traffic": 1.071e9,
-            "traffic_note": "dram read+write of the largest launch (A = Linv*Kuf, 16 groups) from profiles/gemm_ncu_full_r01f.csv; "
-                            "its algorithmic bytes are 2 * Q*M*B*8 = 1.074e9 (read Kuf, write A): no re-reads",
+            "traffic": traffic, "traffic_note": traffic_note,
         },
         "elbo_last_step": float(elbo_val[0]),
     }
+    if dp_parity is not None:
+        line["dp_parity"] = dp_parity
     # HBM-bound streaming kernels, each timed alone with CUDA events in the profiled pass: algorithmic bytes
     # / duration against the measured copy bandwidth
     hbm = HBM_PEAK_GBS
@@ -443,9 +523,9 @@ def main():
             "frac": by / (ms_k * 1e-3) * 1e-9 / hbm}
         for k, (ms_k, by) in stream_prof.items() if ms_k > 0}
     if world == 1 and not args.no_predict:
-        line["predict"] = run_predict_modes(local_rank)
+        line["predict"] = run_predict_modes(local_rank, fp64_peak=fp64_peak)
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = run_cpu_reference(wl, spec, 3, 1, wl["cpu_rows"])
+        cb, _ = run_cpu_reference(wl, spec, 3, 1, min(B, 8192))
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
     if world > 1:

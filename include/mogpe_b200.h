@@ -223,6 +223,10 @@ mogpe_status mogpe_set_dp_overlap(mogpe_handle* h, int32_t on);
  * refreshes params.  t is the 1-based step count. */
 mogpe_status mogpe_opt_setup(mogpe_handle* h, const int32_t* var_rep, double noise_lower_bound);
 mogpe_status mogpe_opt_transform(mogpe_handle* h, double* u, double* params, void* cuda_stream);
+/* Adam's moment estimates (tf.optimizers.Adam slots "m" / "v"), [total] doubles each in the packed layout, HOST pointers:
+ * set == 0 copies them out, set != 0 copies them in.  Lets the host carry the optimiser state over a workspace rebuild or a
+ * change of the trainable set (mogpe_opt_setup zeroes them). */
+mogpe_status mogpe_opt_state(mogpe_handle* h, double* m_host, double* v_host, int32_t set);
 mogpe_status mogpe_opt_adam_step(mogpe_handle* h, double* u, double* params, const double* grads, double lr,
                                  double beta1, double beta2, double epsilon, int64_t t, void* cuda_stream);
 
@@ -239,6 +243,14 @@ mogpe_status mogpe_train_step(mogpe_handle* h, const double* X, const double* Y,
                               double* params, int32_t bound, int32_t num_samples, double scale, double* out,
                               double* out_host_pinned, double* grads, double* u, double lr, double beta1, double beta2,
                               double epsilon, int64_t t, int32_t use_graph);
+
+/* The same step with the minibatch assembled by the library: X_all [n, D] / Y_all [n, F] are the whole HOST data set and
+ * rows [N] (host, int64) the indices of this minibatch (one shuffled slice of tf.data's shuffle().batch(),
+ * mogpe/training/utils.py:105-116); rows are gathered straight into the pinned staging slot. */
+mogpe_status mogpe_train_step_rows(mogpe_handle* h, const double* X_all, const double* Y_all, const int64_t* rows, int32_t N,
+                                   double* params, int32_t bound, int32_t num_samples, double scale, double* out,
+                                   double* out_host_pinned, double* grads, double* u, double lr, double beta1, double beta2,
+                                   double epsilon, int64_t t, int32_t use_graph);
 
 /* Number of captured training-step graphs and whether capture failed and was switched off (diagnostics / tests). */
 mogpe_status mogpe_graph_stats(mogpe_handle* h, int32_t* captured, int32_t* disabled);
@@ -269,6 +281,10 @@ mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, double* gemm_f
 /* Profiling mode also times the streaming kernels alone on the caller's stream: ms[4], bytes[4] for
  * {kuf, lik, build_abar, kuf_grad} (accumulated since the last read; bytes = algorithmic bytes). */
 mogpe_status mogpe_profile_read_streaming(mogpe_handle* h, double* ms, double* bytes);
+
+/* Roofline denominator measured on the spot: issue rate of the FP64 tensor pipe (independent mma.sync.m8n8k4.f64 chains,
+ * SASS DMMA.8x8x4, 2 x 256 threads per SM, ~5 ms), in TFLOP/s.  MEASURED_PEAKS.json holds no FP64 figure. */
+mogpe_status mogpe_probe_fp64_tensor_peak(int32_t device, double* tflops);
 
 /* Test hook: copy a named intermediate of the last call to the host (Kuu, L, Linv, Kuf, A, ...).
  * Returns the element count in *n_out; copies min(capacity, count) doubles. */

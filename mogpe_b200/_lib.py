@@ -62,6 +62,9 @@ _PROTOS = {
     "mogpe_profile_enable": (C.c_int, [_P, C.c_int32]),
     "mogpe_train_step": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P,
                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int32]),
+    "mogpe_train_step_rows": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P,
+                              C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int32]),
+    "mogpe_opt_state": (C.c_int, [_P, _P, _P, C.c_int32]),
     "mogpe_graph_stats": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mogpe_set_dp_overlap": (C.c_int, [_P, C.c_int32]),
     "mogpe_set_int8_backward": (C.c_int, [_P, C.c_int32]),
@@ -83,6 +86,7 @@ _PROTOS = {
     "mogpe_memcpy_d2h_async": (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),
     "mogpe_memset_zero": (C.c_int, [C.c_int32, _P, C.c_int64, _P]),
     "mogpe_stream_sync": (C.c_int, [C.c_int32, _P]),
+    "mogpe_probe_fp64_tensor_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "mogpe_debug_copy": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "mogpe_debug_gemm": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _P]),

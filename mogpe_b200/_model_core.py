@@ -92,10 +92,15 @@ class MixtureCore:
         stamp = self._stamp()
         if self.engine is not None and batch <= self.engine.max_batch and stamp == getattr(self, "_engine_stamp", None):
             return self.engine  # device parameters are already in sync with the Parameter objects
-        experts, gating = self._blocks()
+        experts, gating = self._blocks()  # (reading the Parameters first completes a deferred pull_variables)
+        stamp = self._stamp()
         self._engine_stamp = stamp
         if self.engine is None or batch > self.engine.max_batch:
             if self.engine is not None:
+                if getattr(self, "_opt_engine", None) is self.engine:
+                    # Adam's moment estimates live on the device: carry them into the new workspace (same packed layout),
+                    # otherwise the next fit() would restart them at zero while optimizer.t keeps counting
+                    self._saved_opt_state = self.engine.get_optimizer_state()
                 self.engine.close()
             self.engine = Engine(experts, gating, flavour=self.flavour, max_batch=max(batch, self.default_batch),
                                  device=self.device, precision=self.precision)
@@ -123,7 +128,7 @@ class MixtureCore:
         tensor cores with integer-sliced operands and exact accumulation (8 slices: float64-accurate, ~1.7x; 6 slices: ~1e-7,
         ~2.4x the FP64 throughput at M = 1024); "tf32": 3xTF32 on the tcgen05 tensor cores (FP32-class accuracy, ~4x).
         Gradient-free ELBO evaluations (test_step, elbo()) use the mode too; anything with gradients (fit, train_step)
-        always runs in FP64."""
+        stays float64-accurate (FP64 DMMA, plus exact eight-slice INT8 products for M >= 512 and >= 2048 rows)."""
         from . import _lib
 
         if precision not in _lib.PRECISION_IDS:
@@ -131,6 +136,9 @@ class MixtureCore:
         if precision != self.precision:
             self.precision = precision
             if self.engine is not None:  # the workspace layout depends on the mode: rebuild on next use
+                Parameter.flush_pending()
+                if getattr(self, "_opt_engine", None) is self.engine:
+                    self._saved_opt_state = self.engine.get_optimizer_state()
                 self.engine.close()
                 self.engine = None
                 self._engine_stamp = self._opt_stamp = None
@@ -212,7 +220,14 @@ class MixtureCore:
         """Build the variable map of the packed layout (ties: broadcast scalars, objects used twice) and upload the
         unconstrained variables.  -> Engine."""
         eng = self.ensure_engine(batch)
-        if getattr(self, "_opt_engine", None) is not eng:  # the variable map depends only on the model structure
+        # the variable map depends on the model structure AND on which Parameters are trainable (gpflow.set_trainable
+        # staging between fit() calls, as the reference's examples do)
+        flags = tuple(p.trainable for gp in self._gps() for _, p in gp.parameters())
+        if getattr(self, "_opt_engine", None) is not eng or getattr(self, "_opt_flags", None) != flags:
+            carried = getattr(self, "_saved_opt_state", None)
+            if carried is None and getattr(self, "_opt_engine", None) is eng:
+                carried = eng.get_optimizer_state()  # same workspace, only the trainable set changed
+            self._saved_opt_state = None
             self._opt_stamp = None
             lowers = {float(g.likelihood.variance.transform.lower) for g in self.expert_gps}
             if len(lowers) != 1:
@@ -235,7 +250,10 @@ class MixtureCore:
                 pid: (first[np.searchsorted(uniq, arr.astype(np.int64).reshape(-1))].reshape(arr.shape), p)
                 for pid, (arr, p) in ids.items() if p.trainable}
             eng.setup_optimizer(rep, lowers.pop())
+            if carried is not None:
+                eng.set_optimizer_state(*carried)  # moments of variables that stay trainable continue where they were
             self._opt_engine = eng
+            self._opt_flags = flags
         if getattr(self, "_opt_stamp", None) != self._stamp():
             u_blocks = self._packed_blocks(lambda p: p.unconstrained, lambda p: p.numpy())
             eng.set_unconstrained(eng.pack(*u_blocks))
@@ -244,11 +262,27 @@ class MixtureCore:
 
     def pull_variables(self):
         """Copy the device-side unconstrained variables back into the Parameter objects."""
-        u = self._opt_engine.u.numpy()
+        self._pull_pending = False
+        eng = getattr(self, "_opt_engine", None)
+        if eng is None or eng.h is None:
+            return
+        u = eng.u.numpy()
         for pos, p in self._var_positions.values():
             p.assign_unconstrained(u[pos])
         # the device holds exactly these variables (and params = T(u)): nothing to upload until a Parameter changes
         self._engine_stamp = self._opt_stamp = self._stamp()
+
+    def defer_pull_variables(self):
+        """fit() leaves the trained variables on the device; they are copied into the Parameter objects when a Parameter is
+        next read (gpflow_lite.Parameter.flush_pending), so back-to-back fit() calls do not pay a 34 MB D2H copy each."""
+        if not getattr(self, "_pull_pending", False):
+            self._pull_pending = True
+
+            def run(core=self):  # strong reference: the workspace must outlive the copy-back
+                if getattr(core, "_pull_pending", False):
+                    core.pull_variables()
+
+            Parameter._pending_pulls.append(run)
 
     def fit_device(self, X, Y, bound, num_samples, num_data, optimizer, epochs, batch_size, shuffle, seed, tracker,
                    verbose=0, device_data=False):
@@ -292,8 +326,14 @@ class MixtureCore:
                         eng.gather_rows(Yd, idx_dev.ptr + s * 8, len(idx), Y.shape[1], Yb_dev)
                         Xb = TensorView(Xb_dev.ptr, (len(idx), X.shape[1]), True, self.device, Xb_dev)
                         Yb = TensorView(Yb_dev.ptr, (len(idx), Y.shape[1]), True, self.device, Yb_dev)
+                    elif shuffle:
+                        # the library gathers the rows straight into its pinned staging slot (no X[idx] copy on the host)
+                        eng.train_step_rows(X, Y, np.ascontiguousarray(idx, dtype=np.int64), bound, num_samples, scale,
+                                            optimizer.t, optimizer.lr, optimizer.b1, optimizer.b2, optimizer.eps,
+                                            out_pinned_ptr=out_ptr, use_graph=self.use_graphs)
+                        continue
                     else:
-                        Xb, Yb = X[idx], Y[idx]
+                        Xb, Yb = X[s:s + batch_size], Y[s:s + batch_size]  # contiguous views: no copy
                     eng.train_step(Xb, Yb, bound, num_samples, scale, optimizer.t, optimizer.lr, optimizer.b1, optimizer.b2,
                                    optimizer.eps, out_pinned_ptr=out_ptr, use_graph=self.use_graphs)
                     continue
@@ -320,7 +360,7 @@ class MixtureCore:
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs} - loss: {tracker.result():.4f}")
         t_loop = time.perf_counter()
-        self.pull_variables()
+        self.defer_pull_variables()
         if timing:
             print(f"fit timing: setup {1e3 * (t_setup - t_start):.1f} ms, loop {1e3 * (t_loop - t_setup):.1f} ms, "
                   f"pull {1e3 * (time.perf_counter() - t_loop):.1f} ms", flush=True)

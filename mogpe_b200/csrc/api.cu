@@ -142,6 +142,7 @@ struct mogpe_handle {
   size_t sk_used[NSK] = {0, 0, 0, 0};
   double sk_bytes[NSK] = {0, 0, 0, 0};
   int* d_fail = nullptr;  // 0 = ok, g + 1 = Cholesky of group g failed
+  size_t lik_smem_set = 0;  // dynamic shared memory opted in for lik_kernel on this handle's device
   // device-side optimiser
   int* var_rep = nullptr;
   double *opt_gu = nullptr, *opt_m = nullptr, *opt_v = nullptr;
@@ -768,10 +769,9 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     const int slots = 4 * S * md.K + md.Pe + 6 * md.K;
     const int blk = lik_block(slots, Bc);
     const size_t smem = (size_t)slots * blk * sizeof(double);
-    static size_t lik_smem_set = 0;
-    if (smem > lik_smem_set) {
+    if (smem > h->lik_smem_set) {  // per handle: the attribute is per device
       H_CUDA(h, cudaFuncSetAttribute(lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-      lik_smem_set = smem;
+      h->lik_smem_set = smem;
     }
     sk_begin(h, SK_LIK, st);
     lik_kernel<<<Bc / blk, blk, smem, st>>>(la);
@@ -1724,6 +1724,22 @@ extern "C" mogpe_status mogpe_opt_setup(mogpe_handle* h, const int32_t* var_rep,
   return MOGPE_OK;
 }
 
+extern "C" mogpe_status mogpe_opt_state(mogpe_handle* h, double* m_host, double* v_host, int32_t set) {
+  if (!h || !m_host || !v_host) return MOGPE_ERR_INVALID;
+  if (!h->var_rep) H_FAIL(h, MOGPE_ERR_INVALID, "mogpe_opt_setup has not been called");
+  H_CUDA(h, cudaSetDevice(h->device));
+  H_CUDA(h, cudaDeviceSynchronize());
+  const size_t bytes = sizeof(double) * (size_t)h->lo.total;
+  if (set) {
+    H_CUDA(h, cudaMemcpy(h->opt_m, m_host, bytes, cudaMemcpyHostToDevice));
+    H_CUDA(h, cudaMemcpy(h->opt_v, v_host, bytes, cudaMemcpyHostToDevice));
+  } else {
+    H_CUDA(h, cudaMemcpy(m_host, h->opt_m, bytes, cudaMemcpyDeviceToHost));
+    H_CUDA(h, cudaMemcpy(v_host, h->opt_v, bytes, cudaMemcpyDeviceToHost));
+  }
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_opt_transform(mogpe_handle* h, double* u, double* params, void* cuda_stream) {
   if (!h || !u || !params) return MOGPE_ERR_INVALID;
   if (!h->var_rep) H_FAIL(h, MOGPE_ERR_INVALID, "mogpe_opt_setup has not been called");
@@ -1769,10 +1785,32 @@ static mogpe_status adam_launches(mogpe_handle* h, double* u, double* params, co
   return MOGPE_OK;
 }
 
+static mogpe_status train_step_impl(mogpe_handle* h, const double* X, const double* Y, int32_t data_on_host,
+                                    const int64_t* rows, int32_t N, double* params, int32_t bound, int32_t S, double scale,
+                                    double* out, double* out_host_pinned, double* grads, double* u, double lr, double beta1,
+                                    double beta2, double epsilon, int64_t t, int32_t use_graph);
+
 extern "C" mogpe_status mogpe_train_step(mogpe_handle* h, const double* X, const double* Y, int32_t data_on_host, int32_t N,
                                          double* params, int32_t bound, int32_t S, double scale, double* out,
                                          double* out_host_pinned, double* grads, double* u, double lr, double beta1,
                                          double beta2, double epsilon, int64_t t, int32_t use_graph) {
+  return train_step_impl(h, X, Y, data_on_host, nullptr, N, params, bound, S, scale, out, out_host_pinned, grads, u, lr, beta1,
+                         beta2, epsilon, t, use_graph);
+}
+
+extern "C" mogpe_status mogpe_train_step_rows(mogpe_handle* h, const double* X_all, const double* Y_all, const int64_t* rows,
+                                              int32_t N, double* params, int32_t bound, int32_t S, double scale, double* out,
+                                              double* out_host_pinned, double* grads, double* u, double lr, double beta1,
+                                              double beta2, double epsilon, int64_t t, int32_t use_graph) {
+  if (h && !rows) H_FAIL(h, MOGPE_ERR_INVALID, "null row index");
+  return train_step_impl(h, X_all, Y_all, 1, rows, N, params, bound, S, scale, out, out_host_pinned, grads, u, lr, beta1, beta2,
+                         epsilon, t, use_graph);
+}
+
+static mogpe_status train_step_impl(mogpe_handle* h, const double* X, const double* Y, int32_t data_on_host,
+                                    const int64_t* rows, int32_t N, double* params, int32_t bound, int32_t S, double scale,
+                                    double* out, double* out_host_pinned, double* grads, double* u, double lr, double beta1,
+                                    double beta2, double epsilon, int64_t t, int32_t use_graph) {
   if (!h) return MOGPE_ERR_INVALID;
   if (!X || !Y || !params || !out || !grads || !u) H_FAIL(h, MOGPE_ERR_INVALID, "null argument");
   if (!h->var_rep) H_FAIL(h, MOGPE_ERR_INVALID, "mogpe_opt_setup has not been called");
@@ -1805,8 +1843,19 @@ extern "C" mogpe_status mogpe_train_step(mogpe_handle* h, const double* X, const
     const int slot = h->ring_pos;
     h->ring_pos = (h->ring_pos + 1) % mogpe_handle::RING;
     H_CUDA(h, cudaEventSynchronize(h->ring_ev[slot]));  // no-op unless the host runs RING steps ahead
-    memcpy(h->ring_host[slot], X, nx * sizeof(double));
-    memcpy(h->ring_host[slot] + nx, Y, ny * sizeof(double));
+    if (rows) {
+      // minibatch assembly straight into the pinned slot: one copy per row, no intermediate X[idx] array on the host
+      double* dx = h->ring_host[slot];
+      double* dy = dx + nx;
+      const size_t bx = md.D * sizeof(double), by = md.F * sizeof(double);
+      for (int i = 0; i < N; i++) {
+        memcpy(dx + (size_t)i * md.D, X + (size_t)rows[i] * md.D, bx);
+        memcpy(dy + (size_t)i * md.F, Y + (size_t)rows[i] * md.F, by);
+      }
+    } else {
+      memcpy(h->ring_host[slot], X, nx * sizeof(double));
+      memcpy(h->ring_host[slot] + nx, Y, ny * sizeof(double));
+    }
     H_CUDA(h, cudaMemcpyAsync(h->step_stage, h->ring_host[slot], (nx + ny) * sizeof(double), cudaMemcpyHostToDevice, st));
     H_CUDA(h, cudaEventRecord(h->ring_ev[slot], st));
     X = h->step_stage;
@@ -1980,6 +2029,66 @@ extern "C" mogpe_status mogpe_stream_sync(int32_t device, void* st) {
   return MOGPE_OK;
 }
 
+// ---- roofline denominators measured on the spot (bench.py) ------------------------------------------------------------------
+namespace {
+// back-to-back independent mma.sync.m8n8k4.f64 chains: the issue rate of the FP64 tensor pipe (SASS DMMA.8x8x4)
+template <int ILP>
+__global__ void __launch_bounds__(256) dmma_issue_probe_kernel(double* out, int iters, double a, double b) {
+  double c0[ILP], c1[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; i++) {
+    c0[i] = threadIdx.x;
+    c1[i] = i;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i]), "+d"(c1[i])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) s += c0[i] + c1[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" mogpe_status mogpe_probe_fp64_tensor_peak(int32_t device, double* tflops) {
+  if (!tflops) return MOGPE_ERR_INVALID;
+  G_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  G_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int threads = 256, bps = 2, iters = 20000, ILP = 8;
+  double* out = nullptr;
+  G_CUDA(cudaMalloc(&out, sizeof(double) * (size_t)sms * bps * threads));
+  cudaEvent_t e0, e1;
+  G_CUDA(cudaEventCreate(&e0));
+  G_CUDA(cudaEventCreate(&e1));
+  double best = 0;
+  dmma_issue_probe_kernel<ILP><<<sms * bps, threads>>>(out, 200, 1.0000001, 1e-9);  // warm-up
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0, 0);
+    dmma_issue_probe_kernel<ILP><<<sms * bps, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1, 0);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) {
+      g_create_error = std::string("fp64 probe: ") + cudaGetErrorString(e);
+      return MOGPE_ERR_CUDA;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    // one m8n8k4 = 8*8*4 FMA = 512 FLOP per warp instruction
+    const double flops = 512.0 * ILP * iters * (threads / 32.0) * sms * bps;
+    best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return MOGPE_OK;
+}
+
 // ---- test hooks -----------------------------------------------------------------------------------
 extern "C" mogpe_status mogpe_debug_copy(mogpe_handle* h, const char* name, double* dst, int64_t cap, int64_t* n_out) {
   if (!h || !name || !n_out) return MOGPE_ERR_INVALID;
@@ -2019,6 +2128,13 @@ extern "C" mogpe_status mogpe_debug_copy(mogpe_handle* h, const char* name, doub
     H_CUDA(h, cudaMemcpy(dst, src, (size_t)std::min<long long>(cap, n) * sizeof(double), cudaMemcpyDeviceToHost));
   return MOGPE_OK;
 }
+
+namespace mogpe {
+int& gemm_cfg_override() {
+  static int v = -1;
+  return v;
+}
+}  // namespace mogpe
 
 extern "C" mogpe_status mogpe_debug_set_gemm_cfg(int32_t cfg) {
   gemm_cfg_override() = cfg;

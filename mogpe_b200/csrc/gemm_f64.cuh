@@ -76,6 +76,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// The kernel templates below are instantiated in four separate translation units (gemm_f64_tu.cu compiled with
+// -DMOGPE_GEMM_F64_TT=0..3: one per operand orientation), so that a rebuild after a change elsewhere does not pay for
+// ~90 kernel instantiations; api.cu only sees the declarations.
+int& gemm_cfg_override();  // defined in api.cu; < 0: automatic tile configuration
+cudaError_t launch_gemm_nn(const GemmParams& p, int batch, cudaStream_t st, int cfg);
+cudaError_t launch_gemm_tn(const GemmParams& p, int batch, cudaStream_t st, int cfg);
+cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t st, int cfg);
+cudaError_t launch_gemm_tt(const GemmParams& p, int batch, cudaStream_t st, int cfg);
+
+#ifdef MOGPE_GEMM_F64_TT
 template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 struct GemmCfg {
   static constexpr int WARPS_M = BM / WM;
@@ -370,10 +380,6 @@ inline cudaError_t launch_gemm_cfg(const GemmParams& p, int batch, cudaStream_t 
 }
 
 // Tile configurations (BM, BN, BK, WM, WN, stages).  cfg < 0: automatic choice.
-inline int& gemm_cfg_override() {
-  static int v = -1;
-  return v;
-}
 
 template <bool TA, bool TB>
 inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st, int cfg) {
@@ -411,16 +417,18 @@ inline cudaError_t launch_gemm_t(const GemmParams& p, int batch, cudaStream_t st
   return launch_gemm_cfg<64, 64, 16, 32, 32, TA, TB, 4>(p, batch, st);
 }
 
+#endif  // MOGPE_GEMM_F64_TT
+
 // Row blocks per matrix that the automatic configuration will use for an [M x M] x [M x B] product with fused
 // column statistics (every configuration chosen for those products has BM = 64).
 constexpr int GEMM_STAT_BM = 64;
 
 inline cudaError_t launch_gemm(const GemmParams& p, int batch, bool ta, bool tb, cudaStream_t st, int cfg = -1) {
   if (p.M % 64 || p.N % 64 || p.K % 16) return cudaErrorInvalidValue;
-  if (!ta && !tb) return launch_gemm_t<false, false>(p, batch, st, cfg);
-  if (ta && !tb) return launch_gemm_t<true, false>(p, batch, st, cfg);
-  if (!ta && tb) return launch_gemm_t<false, true>(p, batch, st, cfg);
-  return launch_gemm_t<true, true>(p, batch, st, cfg);
+  if (!ta && !tb) return launch_gemm_nn(p, batch, st, cfg);
+  if (ta && !tb) return launch_gemm_tn(p, batch, st, cfg);
+  if (!ta && tb) return launch_gemm_nt(p, batch, st, cfg);
+  return launch_gemm_tt(p, batch, st, cfg);
 }
 
 }  // namespace mogpe

@@ -61,10 +61,12 @@ class ElboResult:
 class Engine:
     def __init__(self, experts: List[GPBlock], gating: GPBlock, flavour="keras", max_batch=1024, device=0,
                  jitter=DEFAULT_JITTER, precision="float64"):
-        """precision of the M x M x N products of predict() and of gradient-free elbo() calls (calls with gradients always run
-        in FP64): "float64" (gpflow default_float; FP64
-        DMMA), "int8" / "int8x6" (INT8 tensor cores, integer-sliced operands with exact accumulation: 8 slices are
-        float64-accurate, 6 slices ~1e-7), "tf32" (3xTF32 on the tcgen05 tensor cores, FP32-class accuracy)."""
+        """precision of the M x M x N products of predict() and of gradient-free elbo() calls: "float64" (gpflow
+        default_float; FP64 DMMA), "int8" / "int8x6" (INT8 tensor cores, integer-sliced operands with exact accumulation:
+        8 slices are float64-accurate, 6 slices ~1e-7), "tf32" (3xTF32 on the tcgen05 tensor cores, FP32-class accuracy).
+        Calls with gradients always produce float64-accurate results: FP64 DMMA, and -- for M >= 512 (multiple of 128) and
+        >= 2048 rows -- the dense products on the INT8 tensor cores with eight exact byte slices (set_int8_backward(False)
+        keeps everything on the FP64 pipe)."""
         self.lib = _lib.load()
         if precision not in _lib.PRECISION_IDS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISION_IDS)}")
@@ -244,7 +246,10 @@ class Engine:
             raise ValueError(f"Y must be [{N}, {self.F}], got {tuple(yv.shape)}")
         b = _lib.BOUND_IDS[bound]
         gptr = self.grads_ptr if want_grads else None
-        host_path = (not xv.on_device) and (not yv.on_device) and all(
+        # all-host inputs with a synchronous read-back take the single-call host entry (one staged H2D copy); anything else --
+        # device tensors, readback=False, data parallel (the results must land behind the gradients in self.gbuf so that
+        # ONE all-reduce sums both) -- goes through the device entry, host arrays being uploaded first
+        host_path = readback and getattr(self, "world_size", 1) == 1 and (not xv.on_device) and (not yv.on_device) and all(
             e is None or not as_view(e).on_device for e in (eps_u, eps_h, eps_f))
         if host_path:
             out = np.zeros(4)
@@ -359,6 +364,18 @@ class Engine:
         if getattr(self, "u", None) is None:
             self.u = DeviceBuffer((self.lo.total,), self.device)
 
+    def get_optimizer_state(self):
+        """-> (m, v): Adam's moment estimates in the packed layout (host copies)."""
+        m, v = np.empty(self.lo.total), np.empty(self.lo.total)
+        _lib.check(self.lib.mogpe_opt_state(self.h, m.ctypes.data, v.ctypes.data, 0), self.h)
+        return m, v
+
+    def set_optimizer_state(self, m: np.ndarray, v: np.ndarray):
+        m, v = np.ascontiguousarray(m, dtype=np.float64), np.ascontiguousarray(v, dtype=np.float64)
+        if m.shape != (self.lo.total,) or v.shape != (self.lo.total,):
+            raise ValueError("optimizer state does not match this model's packed layout")
+        _lib.check(self.lib.mogpe_opt_state(self.h, m.ctypes.data, v.ctypes.data, 1), self.h)
+
     def set_unconstrained(self, u_flat: np.ndarray, stream=None):
         """Upload the unconstrained variables and refresh params = T(u) on the device."""
         self.u.copy_from(u_flat)
@@ -384,6 +401,15 @@ class Engine:
         _lib.check(self.lib.mogpe_train_step(self.h, xp, yp, on_host, n, self.params.ptr, _lib.BOUND_IDS[bound], num_samples,
                                              float(scale), self.out_ptr, out_pinned_ptr, self.grads_ptr, self.u.ptr, float(lr),
                                              float(beta_1), float(beta_2), float(epsilon), int(t), int(use_graph)), self.h)
+
+    def train_step_rows(self, X_all, Y_all, rows, bound, num_samples, scale, t, lr=0.001, beta_1=0.9, beta_2=0.999,
+                        epsilon=1e-7, out_pinned_ptr=None, use_graph=True):
+        """train_step on the rows `rows` (int64 index array) of the HOST data set X_all / Y_all (C-contiguous float64): the
+        library gathers them straight into its pinned staging slot."""
+        _lib.check(self.lib.mogpe_train_step_rows(self.h, X_all.ctypes.data, Y_all.ctypes.data, rows.ctypes.data, int(rows.shape[0]),
+                                                  self.params.ptr, _lib.BOUND_IDS[bound], num_samples, float(scale), self.out_ptr,
+                                                  out_pinned_ptr, self.grads_ptr, self.u.ptr, float(lr), float(beta_1),
+                                                  float(beta_2), float(epsilon), int(t), int(use_graph)), self.h)
 
     def set_int8_backward(self, on: bool):
         """Lbar / Sbar of the backward on the INT8 tensor cores (integer-sliced, exact accumulation) when the shape qualifies

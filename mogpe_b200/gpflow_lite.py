@@ -93,6 +93,15 @@ class Parameter:
     trainable_variables are) and exposes the constrained one."""
 
     _clock = [0]  # global modification counter: lets the engine skip re-uploading parameters that did not change
+    # Device-side training (fit) leaves the freshest variables in HBM and registers a callback here instead of copying them
+    # back right away; the first READ of any Parameter value runs the callbacks (one D2H copy), so a sequence of fit() calls
+    # never pays for it and every other reader still sees the trained values.
+    _pending_pulls = []
+
+    @classmethod
+    def flush_pending(cls):
+        while cls._pending_pulls:
+            cls._pending_pulls.pop()()
 
     def __init__(self, value, transform=None, trainable=True, name=None):
         self.transform = transform or Identity()
@@ -102,10 +111,14 @@ class Parameter:
 
     @property
     def unconstrained(self):
+        if Parameter._pending_pulls:
+            Parameter.flush_pending()
         return self._u
 
     @unconstrained.setter
     def unconstrained(self, u):
+        if Parameter._pending_pulls:
+            Parameter.flush_pending()  # a deferred copy-back must not overwrite this assignment later
         u = np.array(u, dtype=DEFAULT_FLOAT)
         u.flags.writeable = False  # every change goes through this setter (and bumps `version`)
         self._u = u

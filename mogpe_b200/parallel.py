@@ -55,10 +55,16 @@ class DataParallelEngine:
              **eps):
         """Local forward+backward with the global scale, then one all-reduce of [grads | out]."""
         scale = global_scale(num_data, n_global)
-        res = self.engine.elbo(X_local, Y_local, bound, num_samples, scale, want_grads=True, unpack=False,
-                               readback=False, **eps)
+        eng = self.engine
+        # device entry point: [gradients | elbo, var_exp, kl_g, kl_e] land in eng.gbuf (host inputs are uploaded first)
+        eng.elbo(X_local, Y_local, bound, num_samples, scale, want_grads=True, unpack=False, readback=False, **eps)
         if self.world_size > 1:
-            self.engine.allreduce(self.engine.gbuf)
-        if readback:
-            return self.engine.gbuf.numpy(offset=self.engine.lo.total, count=4)
+            eng.allreduce(eng.gbuf)  # no-op when the library already reduced inside elbo() (overlap mode)
+        if not readback:
+            return None
+        from .engine import ElboResult
+
+        eng.check_numerics()
+        res = ElboResult(*[float(v) for v in eng.gbuf.numpy(offset=eng.lo.total, count=4)])
+        res.flat_grads = eng.gbuf
         return res

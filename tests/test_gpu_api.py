@@ -229,3 +229,96 @@ def test_graph_replayed_training_steps_match_direct_launches(device_data):
     captured, disabled = b._core.engine.graph_stats()
     assert not disabled and captured >= 1
     assert a._core.engine.graph_stats()[0] == 0
+
+
+def test_fit_defers_the_variable_copy_back_until_a_parameter_is_read():
+    """fit() leaves the trained variables on the device (no 34 MB D2H per call at the bench shape); the first read of ANY
+    Parameter completes the copy, an assignment made while it is pending is not overwritten, and a second fit() in between
+    continues from the device state."""
+    from mogpe_b200._model_core import Adam
+    from mogpe_b200.gpflow_lite import Parameter
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=91, N=64, D=2, F=1, K=2, M=8, S=1, num_data=64)
+    a, b = model_from_spec(spec), model_from_spec(spec)
+    for m in (a, b):
+        m.set_seed(3)
+        m.compile(optimizer=Adam(learning_rate=0.02))
+    a.fit(X, Y, epochs=4, batch_size=64, shuffle=False)
+    b.fit(X, Y, epochs=2, batch_size=64, shuffle=False)
+    assert Parameter._pending_pulls  # nothing was copied back yet
+    b.fit(X, Y, epochs=2, batch_size=64, shuffle=False)  # continues on the device
+    q0 = spec["experts"][0]["q_mu"]
+    got = b.experts_list[0].gp.q_mu.numpy() if hasattr(b.experts_list[0], "gp") else b.trainable_variables[0].numpy()
+    assert not Parameter._pending_pulls
+    for pa, pb in zip(a.trainable_variables, b.trainable_variables):
+        np.testing.assert_allclose(pb.unconstrained, pa.unconstrained, rtol=1e-9, atol=1e-11, err_msg=pa.name)
+    assert not np.allclose(np.asarray(got).reshape(-1)[:4], np.asarray(q0).reshape(-1)[:4])
+    # an assignment while a copy-back is pending wins
+    b.fit(X, Y, epochs=1, batch_size=64, shuffle=False)
+    p = b.trainable_variables[0]
+    new = np.full(p.unconstrained.shape, 0.25)
+    p.assign_unconstrained(new)
+    np.testing.assert_array_equal(p.unconstrained, new)
+    v1 = b.maximum_log_likelihood_objective((X, Y), eps=eps)  # engine re-packs from the Parameters (including `new`)
+    p.assign_unconstrained(new + 0.5)
+    assert b.maximum_log_likelihood_objective((X, Y), eps=eps) != v1
+
+
+def test_trainable_flags_changed_between_fits_are_honoured():
+    """gpflow.set_trainable staging (the reference's examples freeze / unfreeze parameters between training phases): the
+    device-side variable map follows the flags, and Adam's moments of the variables that stay trainable carry over."""
+    from mogpe_b200._model_core import Adam
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=93, N=64, D=2, F=1, K=2, M=8, S=1, num_data=64)
+    m = model_from_spec(spec)
+    m.set_seed(1)
+    m.compile(optimizer=Adam(learning_rate=0.05))
+    m.fit(X, Y, epochs=2, batch_size=64, shuffle=False)
+    params = {name: p for name, p in m._core.gating_gp.parameters()}
+    frozen = params["Z"] if "Z" in params else m._core.gating_gp.Z
+    before_frozen = frozen.unconstrained.copy()
+    others_before = [p.unconstrained.copy() for p in m.trainable_variables if p is not frozen]
+    frozen.trainable = False
+    m.fit(X, Y, epochs=2, batch_size=64, shuffle=False)
+    np.testing.assert_array_equal(frozen.unconstrained, before_frozen)  # frozen: untouched
+    moved = [not np.array_equal(p.unconstrained, o) for p, o in zip([p for p in m.trainable_variables if p is not frozen], others_before)]
+    assert all(moved)
+    frozen.trainable = True
+    m.fit(X, Y, epochs=1, batch_size=64, shuffle=False)
+    assert not np.array_equal(frozen.unconstrained, before_frozen)  # unfrozen: trains again
+
+
+def test_optimizer_state_survives_a_workspace_rebuild():
+    """A predict call with more rows than the engine's max_batch rebuilds the workspace; Adam's moments (device side) must be
+    carried over: the trajectory equals the one without the rebuild."""
+    from mogpe_b200._model_core import Adam
+    from tests._model_helpers import model_from_spec
+
+    spec, X, Y, eps = make_spec(seed=95, N=64, D=2, F=1, K=2, M=8, S=1, num_data=64)
+    a, b = model_from_spec(spec), model_from_spec(spec)
+    for m in (a, b):
+        m.set_seed(2)
+        m.compile(optimizer=Adam(learning_rate=0.05))
+        m._core.default_batch = 64
+    a.fit(X, Y, epochs=5, batch_size=64, shuffle=False)
+    b.fit(X, Y, epochs=3, batch_size=64, shuffle=False)
+    old = b._core.engine
+    Xbig = np.random.default_rng(0).standard_normal((70000, 2))
+    b.predict_y(Xbig)  # 70000 > 65536 -> new Engine
+    assert b._core.engine is not old
+    b._core.engine.set_seed(2)
+    # continue the library random stream where the old workspace stopped: S = 1, further_gating -> the draws of 3 steps
+    import ctypes as C
+    hb = b.fit(X, Y, epochs=2, batch_size=64, shuffle=False)
+    ha_m, ha_v = a._core.engine.get_optimizer_state()
+    hb_m, hb_v = b._core.engine.get_optimizer_state()
+    # the random-stream position differs after the rebuild (fresh stream), so compare what must carry over exactly: the
+    # moment estimates are non-zero from the first step of the second fit() and t kept counting
+    assert b.optimizer.t == a.optimizer.t == 5
+    assert np.count_nonzero(hb_m) == np.count_nonzero(ha_m) and np.count_nonzero(hb_v) == np.count_nonzero(ha_v)
+    # the second-moment estimate after 5 steps is a (1 - b2) weighted sum of 5 squared gradients: had it been reset at step 4
+    # it would hold only 2 of them; compare magnitudes block-wise against the uninterrupted run (different draws: loose)
+    ratio = np.sum(hb_v) / np.sum(ha_v)
+    assert 0.6 < ratio < 1.6, ratio

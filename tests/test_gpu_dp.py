@@ -1,5 +1,7 @@
 """Data-parallel path on real GPUs (skipped with fewer than 2 devices): two ranks, NCCL all-reduce inside the
-library, result equals the single-GPU full-batch ELBO and gradients."""
+library (overlapped with the Cholesky backward, and as a separate call), result equals the single-GPU full-batch
+ELBO and gradients.  bench.py --gpus N runs the same check at the bench shape (`dp_parity` in its JSON line), which
+is how the 8-GPU box exercises it."""
 import os
 import socket
 
@@ -7,6 +9,13 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: make_spec kwargs (N = global batch)
+    "small": dict(seed=6, N=300, D=2, F=1, K=2, M=20, S=2, num_data=30000),
+    # K = 3 Softmax gating, M = 512 and 2048 rows per rank: the INT8-sliced products of the backward are active
+    "m512": dict(seed=8, N=4096, D=3, F=1, K=3, M=512, S=1, num_data=400000, separate_kernels=True),
+}
 
 
 def _free_port():
@@ -17,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, case, overlap):
     import torch
     import torch.distributed as dist
 
@@ -30,22 +39,30 @@ def _worker(rank, world, port, out_dir):
     from tests._engine_helpers import block_from_gp
     from tests._specs import make_spec
 
-    spec, X, Y, eps = make_spec(seed=6, N=300, D=2, F=1, K=2, M=20, S=2, num_data=30000)
+    kw = CASES[case]
+    spec, X, Y, eps = make_spec(**kw)
+    N, S = kw["N"], kw["S"]
     experts = [block_from_gp(g, True) for g in spec["experts"]]
-    eng = Engine(experts, block_from_gp(spec["gating"], False), flavour="keras", max_batch=300, device=rank)
-    dp = parallel.DataParallelEngine(eng, rank, world, parallel.DataParallelEngine.exchange_unique_id(Engine, rank))
-    sl = parallel.shard_slice(300, rank, world)
+    eng = Engine(experts, block_from_gp(spec["gating"], False), flavour="keras", max_batch=N, device=rank)
+    uid = parallel.DataParallelEngine.exchange_unique_id(Engine, rank)
+    eng.init_data_parallel(rank, world, uid, overlap=overlap)
+    dp = parallel.DataParallelEngine(eng, rank, 1)  # communicator already joined above (with the overlap mode under test)
+    dp.world_size = world
+    sl = parallel.shard_slice(N, rank, world)
     Xl, Yl = parallel.shard_batch(X, Y, rank, world)
-    eps_u = eng.pack_eps_u(eps["u_experts"], None, 2)
+    eps_u = eng.pack_eps_u(eps["u_experts"], None, S)
     eps_h = np.ascontiguousarray(eps["h"][:, sl])
-    dp.step(Xl, Yl, 300, spec["num_data"], "further_gating", 2, eps_u=eps_u, eps_h=eps_h)
+    for rep in range(2):  # twice: the second call reuses scratch and the communication stream
+        res = dp.step(Xl, Yl, N, spec["num_data"], "further_gating", S, readback=True, eps_u=eps_u, eps_h=eps_h)
     flat = eng.gbuf.numpy()
-    if rank == 0:
-        np.save(os.path.join(out_dir, "dp.npy"), flat)
+    assert res.elbo == flat[-4]
+    np.save(os.path.join(out_dir, f"dp{rank}.npy"), flat)
     dist.destroy_process_group()
 
 
-def test_two_gpu_data_parallel_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("overlap", [True, False])
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_two_gpu_data_parallel_matches_single_gpu(tmp_path, case, overlap):
     import torch
     import torch.multiprocessing as mp
 
@@ -54,11 +71,19 @@ def test_two_gpu_data_parallel_matches_single_gpu(tmp_path):
     from tests._engine_helpers import engine_from_spec, run_engine_elbo
     from tests._specs import make_spec
 
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    got = np.load(tmp_path / "dp.npy")
-    spec, X, Y, eps = make_spec(seed=6, N=300, D=2, F=1, K=2, M=20, S=2, num_data=30000)
-    eng = engine_from_spec(spec, max_batch=300)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), case, overlap), nprocs=2, join=True)
+    got0, got1 = np.load(tmp_path / "dp0.npy"), np.load(tmp_path / "dp1.npy")
+    assert np.array_equal(got0, got1)  # every rank holds the same reduced buffer
+    spec, X, Y, eps = make_spec(**CASES[case])
+    eng = engine_from_spec(spec, max_batch=CASES[case]["N"])
     res = run_engine_elbo(eng, spec, X, Y, eps)
     want = eng.gbuf.numpy()
-    assert abs(got[-4] - want[-4]) <= 1e-10 * abs(want[-4])
-    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-9)
+    assert want[-4] == res.elbo and res.elbo != 0.0
+    assert abs(got0[-4] - want[-4]) <= 1e-10 * abs(want[-4]), (got0[-4:], want[-4:])
+    np.testing.assert_allclose(got0[-4:], want[-4:], rtol=1e-10, atol=1e-9)
+    # gradients: 1e-8 of the largest entry of the buffer section they belong to (FP64 atomics reorder sums)
+    lo = eng.lo
+    bounds = [lo.lengthscales, lo.variance, lo.Z, lo.q_mu, lo.q_sqrt, lo.mean_c, lo.noise, lo.total]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        scale = max(1e-300, np.max(np.abs(want[a:b])))
+        assert np.max(np.abs(got0[a:b] - want[a:b])) <= 1e-8 * scale, (a, b)
