@@ -76,7 +76,7 @@ def test_two_gpu_data_parallel_matches_single_gpu(tmp_path, case, overlap):
     assert np.array_equal(got0, got1)  # every rank holds the same reduced buffer
     spec, X, Y, eps = make_spec(**CASES[case])
     eng = engine_from_spec(spec, max_batch=CASES[case]["N"])
-    res = run_engine_elbo(eng, spec, X, Y, eps)
+    res = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=True)  # device entry: results land behind the gradients
     want = eng.gbuf.numpy()
     assert want[-4] == res.elbo and res.elbo != 0.0
     assert abs(got0[-4] - want[-4]) <= 1e-10 * abs(want[-4]), (got0[-4:], want[-4:])
