@@ -204,6 +204,12 @@ mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_t n, void* 
  * LTA^T)) run on the INT8 tensor cores with integer-sliced operands and exact accumulation (FP64-class accuracy, section 4c of
  * DESIGN.md) when M is a multiple of 128, M >= 512 and the batch has >= 2048 rows; on (default) / off selects it. */
 mogpe_status mogpe_set_int8_backward(mogpe_handle* h, int32_t on);
+/* The WHOLE gradient step on the INT8 tensor cores under the same shape conditions (default on; needs the INT8 backward on):
+ * A = L^-1 Kuf, S^T A, S (S^T A) and W = L^-T Abar also run as integer-sliced products (tcgen05 kind::i8, eight exact byte
+ * slices, FP64-class results: same tolerances as the FP64 path); operands are exchanged between the kernels as byte planes
+ * and Kuf / A / Abar are never written in FP64.  Replaces the conditional + backward of gpflow's SVGP.predict_f under
+ * tf.GradientTape (mogpe/keras/gps.py:31-48, mogpe/keras/mixture_of_experts/mosvgpe.py:57-69). */
+mogpe_status mogpe_set_int8_step(mogpe_handle* h, int32_t on);
 
 /* on != 0: mogpe_elbo_fwd_bwd performs the data-parallel reduction itself and returns globally summed gradients and
  * results -- the part of the gradient buffer that is final before the Cholesky backward (q_mu, q_sqrt, mean, noise and, when
@@ -278,6 +284,9 @@ mogpe_status mogpe_stream_sync(int32_t device, void* cuda_stream);
 mogpe_status mogpe_profile_enable(mogpe_handle* h, int32_t on);
 mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches,
                                 int64_t* all_launches);
+/* INT8-sliced product launches (gemm_i8_sliced_kernel) of the step since the last read: device time (ms), ALGORITHMIC
+ * FP64-equivalent FLOPs (every such FLOP costs 36 INT8 slice-pair MACs), launch count. */
+mogpe_status mogpe_profile_read_int8(mogpe_handle* h, double* ms, double* flops, int64_t* launches);
 /* Profiling mode also times the streaming kernels alone on the caller's stream: ms[4], bytes[4] for
  * {kuf, lik, build_abar, kuf_grad} (accumulated since the last read; bytes = algorithmic bytes). */
 mogpe_status mogpe_profile_read_streaming(mogpe_handle* h, double* ms, double* bytes);

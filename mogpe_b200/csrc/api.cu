@@ -17,6 +17,7 @@
 #include "gemm_f64.cuh"
 #include "kernels.cuh"
 #include "kernels_tf32.cuh"
+#include "kernels_i8.cuh"
 #include "lik.cuh"
 #include "model_dev.cuh"
 
@@ -79,6 +80,28 @@ struct mogpe_handle {
   CUtensorMap tm_bw, tm_ba64, tm_ba128, tm_bld;
   bool i8_bwd_ready = false, i8_bwd_on = true;
   int ns = 8;  // byte slices per operand: 8 (INT8, FP64-class) or 6 (INT8X6, ~1e-7-class)
+  // The WHOLE training step on the INT8 tensor cores (eight exact byte slices, FP64-class): A = L^-1 Kuf, LTA = S^T A,
+  // S LTA, W = L^-T Abar as well as Lbar / Sbar; every operand lives in byte planes, the only FP64 [M x B] matrices left are
+  // LTA, S LTA and W (read once each by a slicing / gradient kernel).  Same shape conditions as the INT8 backward products.
+  bool i8_step_on = true, i8_step_ready = false;
+  int8_t *t8_Linv = nullptr, *t8_LinvT = nullptr;          // [Q][8][Mp][Mp]: L^-1 (K_LOWER operand) and its transpose (K_UPPER)
+  int8_t *t8_ST = nullptr, *t8_S = nullptr;                // [P][8][Mp][Mp] per LTA slot: tril(q_sqrt)^T and tril(q_sqrt)
+  int8_t *t8_KufT = nullptr, *t8_AT = nullptr, *t8_AbarT = nullptr;  // [Q][8][Bp][Mp]: point index n = row
+  int8_t* t8_LTAT = nullptr;                               // [P][8][Bp][Mp] per LTA slot
+  double *t8_linv_scale = nullptr, *t8_linvT_scale = nullptr;  // [Q][Mp] row scales
+  double *t8_st_scale = nullptr, *t8_s_scale = nullptr;        // [P][Mp]
+  double *t8_lta_scale = nullptr, *t8_srowmax = nullptr, *t8_vmax = nullptr;  // [P] (slot), [P] (latent), [NVcap]
+  double* t8_nscale = nullptr;                             // [Q][Bp] column scales of Abar
+  double* t8_P2 = nullptr;                                 // [P][Mp][Bp] FP64: S_l LTA_l per LTA slot
+  unsigned long long* t8_wmax = nullptr;                   // [Q][Mp] row maxima of W (bit patterns)
+  unsigned long long* t8_bound_bits = nullptr;             // [2 P + NVcap] atomicMax scratch of bounds_kernel
+  int t8_vmax_cap = 0;
+  CUtensorMap tmt_linv, tmt_linvT, tmt_st, tmt_s, tmt_kuf, tmt_at, tmt_abart, tmt_ltat;
+  // INT8 product timing in profiling mode (bench.py roofline of gemm_i8_sliced_kernel)
+  std::vector<cudaEvent_t> ev8;
+  size_t ev8_used = 0;
+  double prof8_flops = 0;
+  long long i8_launches = 0;
   int* d_t32_err = nullptr;
   // graph-replayed training step (mogpe_train_step): launches are captured once per argument set and replayed
   struct GraphEntry {
@@ -217,6 +240,13 @@ static void free_ws(mogpe_handle* h) {
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->ev_comm_fork) cudaEventDestroy(h->ev_comm_fork);
   if (h->ev_comm_join) cudaEventDestroy(h->ev_comm_join);
+  for (void* q : {(void*)h->t8_Linv, (void*)h->t8_LinvT, (void*)h->t8_ST, (void*)h->t8_S, (void*)h->t8_KufT, (void*)h->t8_AT,
+                  (void*)h->t8_AbarT, (void*)h->t8_LTAT, (void*)h->t8_linv_scale, (void*)h->t8_linvT_scale, (void*)h->t8_st_scale,
+                  (void*)h->t8_s_scale, (void*)h->t8_lta_scale, (void*)h->t8_srowmax, (void*)h->t8_vmax, (void*)h->t8_nscale,
+                  (void*)h->t8_P2, (void*)h->t8_wmax, (void*)h->t8_bound_bits})
+    if (q) cudaFree(q);
+  for (auto e : h->ev8) cudaEventDestroy(e);
+  h->ev8.clear();
   if (h->bW8) cudaFree(h->bW8);
   if (h->bA8) cudaFree(h->bA8);
   if (h->bLD8) cudaFree(h->bLD8);
@@ -676,7 +706,13 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
 
 static mogpe_status dp_allreduce(mogpe_handle* h, double* buf, size_t n, cudaStream_t st);  // defined with the NCCL loader
 // Lbar and Sbar of the backward on the INT8 tensor cores (returns MOGPE_ERR_UNSUPPORTED when the shape does not qualify)
-static mogpe_status int8_backward_products(mogpe_handle* h, const double* params, double* grads, int Bc, int N, cudaStream_t st);
+static mogpe_status int8_backward_products(mogpe_handle* h, const double* params, double* grads, int Bc, int N, cudaStream_t st,
+                                           bool a8_ready, int w_state);
+static mogpe_status ensure_i8_step(mogpe_handle* h);
+static bool i8_step_shape_ok(const mogpe_handle* h, int Bc);
+static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X, int N,
+                                    int Bc, cudaStream_t st);
+static mogpe_status i8_step_backward_to_W(mogpe_handle* h, int N, int Bc, cudaStream_t st);
 // forward conditional (statistics + means) through the tensor-core products of the handle's precision mode
 static mogpe_status forward_tensor_core(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X,
                                         int N, cudaStream_t st);
@@ -747,10 +783,19 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   if (grads) H_CUDA(h, cudaMemsetAsync(grads, 0, lo.total * sizeof(double), st));
 
   // ---------------- forward ----------------
+  // The whole step on the INT8 tensor cores (eight exact byte slices: FP64-class results) when the shape qualifies
+  bool i8_step = false;
+  if (grads && h->i8_step_on && h->i8_bwd_on && i8_step_shape_ok(h, Bc)) {
+    const mogpe_status erc = ensure_i8_step(h);
+    if (erc == MOGPE_OK) i8_step = true;
+    else if (erc != MOGPE_ERR_UNSUPPORTED) return erc;
+  }
   if (!grads && h->precision != MOGPE_PRECISION_F64) {
-    // evaluation only (test_step / elbo()): the conditional runs in the handle's tensor-core mode; a call that wants
-    // gradients always takes the FP64 path below
+    // evaluation only (test_step / elbo()): the conditional runs in the handle's tensor-core mode
     rc = forward_tensor_core(h, params, eps_u, S, X, N, st);
+    if (rc != MOGPE_OK) return rc;
+  } else if (i8_step) {
+    rc = i8_step_forward(h, params, eps_u, S, X, N, Bc, st);
     if (rc != MOGPE_OK) return rc;
   } else {
     rc = factorise(h, params, eps_u, S, X, N, Bc, st);
@@ -789,11 +834,16 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   // (a) q_sqrt gradient of marginal latents: Sbar_l = tril(A (2 LTA_l diag(dfvar_l))^T); scaling fused in the
   //     epilogue via alpha and into the B operand... done as: Sbar_l = 2 * tril(A_g diag(dfvar_l) LTA_l^T)
   //     => scale LTA in place first (it is also the B operand of Abar += S_l dLTA_l).
+  KCOUNT(h, 4);  // q_grads, halve_diag, kuu_grad, kuf_grad
+  if (i8_step) {
+    rc = i8_step_backward_to_W(h, N, Bc, st);
+    if (rc != MOGPE_OK) return rc;
+  } else {
   H_CUDA(h, cudaMemsetAsync(h->dV, 0, (size_t)md.NV * Mp * sizeof(double), st));
   sk_begin(h, SK_ABAR, st);
   build_abar_kernel<<<dim3(Bc / 128, Mp / 32, Q), 128, 0, st>>>(h->d_md, h->A, h->V, h->dmean, h->dfvar, Bp, h->Abar, h->dV);
   sk_end(h, SK_ABAR, st, 8.0 * Q * 2.0 * Mp * N);  // read A, write Abar
-  KCOUNT(h, 5);  // build_abar (+dV), q_grads, halve_diag, kuu_grad, kuf_grad
+  KCOUNT(h, 1);
   H_CUDA(h, cudaGetLastError());
   if (md.nlta > 0) {
     // Abar[g(l)] += S_l (2 LTA_l diag(dfvar_l))   -- column scaling fused into the B-operand load.
@@ -819,6 +869,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     p.M = Mp; p.N = Bc; p.K = Mp; p.kmode = KM_LEFT_UPPER;
     H_CUDA(h, hgemm(h, p, Q, true, false, st, (double)Q * Mp * Mp * Bc));
   }
+  }  // !i8_step
   // Kuf-bar = W is complete: its kernel-hyperparameter / Z gradients only read W, Kuf, X -> side stream, overlapping
   // the GEMMs of the Cholesky backward below (different gradient entries except kvar / ls, which are atomics)
   H_CUDA(h, side_fork(h, st));
@@ -830,16 +881,35 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
     int nsplit = std::max(1, std::min((888 + blocks - 1) / blocks, (N + 1023) / 1024));
     const int n_chunk = round_up((N + nsplit - 1) / nsplit, 32);
     nsplit = (N + n_chunk - 1) / n_chunk;
-    if (md.D <= 4)
+    static const bool kgs_fused = getenv("MOGPE_KGS") ? atoi(getenv("MOGPE_KGS")) != 0 : true;  // tuning switch
+    if (i8_step && !kgs_fused) {  // Kuf re-evaluated from X and Z; W is sliced by a separate pass (int8_backward_products)
+      if (md.D <= 4)
+        kuf_grad_kernel<4, 1, true><<<dim3(Mp / 8, Q, nsplit), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, nullptr, grads, n_chunk);
+      else
+        kuf_grad_kernel<16, 1, true><<<dim3(Mp / 8, Q, nsplit), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, nullptr, grads, n_chunk);
+    } else if (i8_step) {
+      // one pass over W: Kuf gradients (Kuf re-evaluated from X and Z) + the byte planes of W for Lbar; it feeds the Lbar
+      // product, so it runs on the caller's stream (the persistent INT8 kernels fill every SM: nothing to overlap with)
+      ks = st;
+      const int n_chunk8 = round_up((Bc + nsplit - 1) / nsplit, 128);
+      const int nsplit8 = (Bc + n_chunk8 - 1) / n_chunk8;
+      const dim3 kgrid(Mp / 8, Q, nsplit8);
+      if (md.D <= 4)
+        oz::kuf_grad_slice_kernel<4, 8><<<kgrid, 256, 0, ks>>>(h->d_md, params, lo, X, N, Bc, Bp, h->W, h->t8_wmax, grads, h->bW8, h->bw_scale, n_chunk8);
+      else
+        oz::kuf_grad_slice_kernel<16, 8><<<kgrid, 256, 0, ks>>>(h->d_md, params, lo, X, N, Bc, Bp, h->W, h->t8_wmax, grads, h->bW8, h->bw_scale, n_chunk8);
+    } else if (md.D <= 4)
       kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q, nsplit), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads, n_chunk);
     else
       kuf_grad_kernel<16, 1><<<dim3(Mp / 8, Q, nsplit), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads, n_chunk);
-    sk_end(h, SK_KUF_GRAD, ks, 8.0 * Q * (2.0 * Mp * N + (double)N * md.D));  // read W and Kuf, X
+    // algorithmic bytes: read W (and Kuf unless it is re-evaluated), X
+    sk_end(h, SK_KUF_GRAD, ks, 8.0 * Q * (2.0 * Mp * N + (double)N * md.D));  // (INT8 step: W in, W byte planes out)
   }
   // Lbar = -tril(W A^T) and Sbar_l = 2 tril(A diag(dfvar_l) LTA_l^T): [M x M] results reduced over the minibatch
   bool reduced_on_int8 = false;
   if (h->i8_bwd_on && Mp % 128 == 0 && Mp >= 512 && Bc >= 2048) {  // measured: M = 256 is faster on DMMA + split-K
-    mogpe_status irc = int8_backward_products(h, params, grads, Bc, N, st);
+    static const bool kgs_fused2 = getenv("MOGPE_KGS") ? atoi(getenv("MOGPE_KGS")) != 0 : true;
+    mogpe_status irc = int8_backward_products(h, params, grads, Bc, N, st, i8_step, i8_step ? (kgs_fused2 ? 2 : 1) : 0);
     if (irc == MOGPE_OK) reduced_on_int8 = true;
     else if (irc != MOGPE_ERR_UNSUPPORTED) return irc;
   }
@@ -1236,44 +1306,112 @@ static mogpe_status products_i8(mogpe_handle* h, const double* params, int Bc, i
   return MOGPE_OK;
 }
 
-static mogpe_status int8_backward_products(mogpe_handle* h, const double* params, double* grads, int Bc, int N,
-                                           cudaStream_t st) {
+// INT8 product launch through the handle: counts launches and, with profiling on, brackets it with CUDA events.
+// `flops` = ALGORITHMIC FP64-equivalent work (triangular operands / results counted as triangular).
+static cudaError_t h_i8_launch(mogpe_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const oz::Params& p, int n_tiles,
+                               int batch, cudaStream_t st, double flops) {
+  h->gemm_launches++;
+  h->i8_launches++;
+  h->all_launches++;
+  static const int dbg = getenv("MOGPE_I8_DBG") ? atoi(getenv("MOGPE_I8_DBG")) : 0;  // tuning switches of the epilogue (tools)
+  if (dbg) {
+    oz::Params q = p;
+    q.dbg = dbg;
+    if (!h->prof) return oz::launch<8>(ma, mb, q, n_tiles, batch, st);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    cudaError_t rc = oz::launch<8>(ma, mb, q, n_tiles, batch, st);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "i8 product dbg=%d batch=%d kmode=%d K=%d: %.1f us\n", dbg, batch, p.kmode, p.K, ms * 1e3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+  }
+  if (!h->prof) return oz::launch<8>(ma, mb, p, n_tiles, batch, st);
+  if (h->ev8_used + 2 > h->ev8.size())
+    for (int i = 0; i < 32; i++) {
+      cudaEvent_t e;
+      cudaError_t ce = cudaEventCreate(&e);
+      if (ce != cudaSuccess) return ce;
+      h->ev8.push_back(e);
+    }
+  h->prof_stream = st;
+  cudaEventRecord(h->ev8[h->ev8_used], st);
+  cudaError_t rc = oz::launch<8>(ma, mb, p, n_tiles, batch, st);
+  cudaEventRecord(h->ev8[h->ev8_used + 1], st);
+  h->ev8_used += 2;
+  h->prof8_flops += flops;
+  return rc;
+}
+
+static mogpe_status ensure_i8_bwd(mogpe_handle* h) {
+  if (h->i8_bwd_ready) return MOGPE_OK;
   const ModelDev& md = h->md_host;
   const int Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;
   constexpr int NS = 8;
-  if (!h->i8_bwd_ready) {
-    if (!t32::encode_fn()) return MOGPE_ERR_UNSUPPORTED;  // no TMA tensor maps: stay on the DMMA path
-    const size_t plane = (size_t)NS * Mp * Bp;
-    H_CUDA(h, dalloc(&h->bW8, Q * plane));
-    H_CUDA(h, dalloc(&h->bA8, Q * plane));
-    H_CUDA(h, dalloc(&h->bLD8, P * plane));
-    H_CUDA(h, dalloc(&h->bw_scale, (size_t)Q * Mp));
-    H_CUDA(h, dalloc(&h->ba_scale, (size_t)Q * Mp));
-    H_CUDA(h, dalloc(&h->bld_scale, (size_t)P * Mp));
-    if (!h->kuf_scale) H_CUDA(h, dalloc(&h->kuf_scale, (size_t)Q));
-    if (!h->aout_scale) H_CUDA(h, dalloc(&h->aout_scale, (size_t)Q));
-    if (!h->d_t32_err) {
-      H_CUDA(h, dalloc(&h->d_t32_err, 1));
-      H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
-    }
-    if (!oz::make_map_i8(&h->tm_bw, h->bW8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_ba64, h->bA8, Q, Mp, Bp, oz::BN, NS) ||
-        !oz::make_map_i8(&h->tm_ba128, h->bA8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_bld, h->bLD8, P, Mp, Bp, oz::BN, NS))
-      return MOGPE_ERR_UNSUPPORTED;
-    h->graphs_dirty = true;
-    h->i8_bwd_ready = true;
+  if (!t32::encode_fn()) return MOGPE_ERR_UNSUPPORTED;  // no TMA tensor maps: stay on the DMMA path
+  const size_t plane = (size_t)NS * Mp * Bp;
+  H_CUDA(h, dalloc(&h->bW8, Q * plane));
+  H_CUDA(h, dalloc(&h->bA8, Q * plane));
+  H_CUDA(h, dalloc(&h->bLD8, P * plane));
+  H_CUDA(h, dalloc(&h->bw_scale, (size_t)Q * Mp));
+  H_CUDA(h, dalloc(&h->ba_scale, (size_t)Q * Mp));
+  H_CUDA(h, dalloc(&h->bld_scale, (size_t)P * Mp));
+  if (!h->kuf_scale) H_CUDA(h, dalloc(&h->kuf_scale, (size_t)Q));
+  if (!h->aout_scale) H_CUDA(h, dalloc(&h->aout_scale, (size_t)Q));
+  if (!h->d_t32_err) {
+    H_CUDA(h, dalloc(&h->d_t32_err, 1));
+    H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
   }
+  if (!oz::make_map_i8(&h->tm_bw, h->bW8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_ba64, h->bA8, Q, Mp, Bp, oz::BN, NS) ||
+      !oz::make_map_i8(&h->tm_ba128, h->bA8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_bld, h->bLD8, P, Mp, Bp, oz::BN, NS))
+    return MOGPE_ERR_UNSUPPORTED;
+  h->graphs_dirty = true;
+  h->i8_bwd_ready = true;
+  return MOGPE_OK;
+}
+
+// Lbar = -tril(W A^T) and Sbar_l = 2 tril(A diag(dfvar_l) LTA_l^T) on the INT8 tensor cores.
+//   a8_ready:   the [m][n] byte planes of A (bA8, scale aout_scale per group) were written by the epilogue of the A product
+//   w_state: 0 = slice W here (row maxima measured here), 1 = row maxima collected by the epilogue of the W product
+//            (t8_wmax), 2 = byte planes and row scales already written by kuf_grad_slice_kernel
+// otherwise both operands are sliced here from their FP64 copies.
+static mogpe_status int8_backward_products(mogpe_handle* h, const double* params, double* grads, int Bc, int N,
+                                           cudaStream_t st, bool a8_ready, int w_state) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, Mp = h->Mp, Bp = h->Bp;
+  constexpr int NS = 8;
+  mogpe_status erc = ensure_i8_bwd(h);
+  if (erc != MOGPE_OK) return erc;
   const int m_tiles = Mp / oz::BM, n_tiles = Mp / oz::BN;
   const dim3 sg((Bp / 4 + 255) / 256, Mp, 1);
   // operands: A with its group bound |A| <= sqrt(kvar) as the scale of every row, W with measured row maxima
-  oz::group_scales_kernel<<<1, MAXQ, 0, st>>>(h->d_md, params, h->lo, h->kuf_scale, h->aout_scale);
+  if (!a8_ready) {
+    oz::group_scales_kernel<<<1, MAXQ, 0, st>>>(h->d_md, params, h->lo, h->kuf_scale, h->aout_scale);
+    KCOUNT(h, 1);
+  }
   oz::fill_row_scale_kernel<<<dim3((Mp + 127) / 128, Q), 128, 0, st>>>(h->aout_scale, nullptr, h->ba_scale, Mp);
-  oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, Q), 256, 0, st>>>(h->A, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
-                                                                 h->ba_scale, h->bA8, Mp);
-  oz::row_scale_n_kernel<<<dim3(Mp, Q), 256, 0, st>>>(h->W, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
-                                                      h->bw_scale, Mp);
-  oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, Q), 256, 0, st>>>(h->W, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
-                                                                 h->bw_scale, h->bW8, Mp);
-  KCOUNT(h, 5);
+  KCOUNT(h, 1);
+  if (!a8_ready) {
+    oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, Q), 256, 0, st>>>(h->A, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
+                                                                   h->ba_scale, h->bA8, Mp);
+    KCOUNT(h, 1);
+  }
+  if (w_state != 2) {  // (2: kuf_grad_slice_kernel already wrote the W planes and their row scales)
+    if (w_state == 1)
+      oz::max_to_scale_kernel<<<(Q * Mp + 255) / 256, 256, 0, st>>>(h->t8_wmax, h->bw_scale, (long long)Q * Mp);
+    else
+      oz::row_scale_n_kernel<<<dim3(Mp, Q), 256, 0, st>>>(h->W, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
+                                                          h->bw_scale, Mp);
+    oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, Q), 256, 0, st>>>(h->W, Mp, N, (long long)Mp * Bp, Bp, nullptr, nullptr, 0, nullptr,
+                                                                   h->bw_scale, h->bW8, Mp);
+    KCOUNT(h, 2);
+  }
   H_CUDA(h, cudaGetLastError());
   auto ksplit_for = [&](int batch) {
     const int tiles = batch * (m_tiles * (m_tiles + 1));  // lower-triangular 128 x 64 tiles: sum_t 2 (t + 1)
@@ -1290,9 +1428,7 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
     p.ksplit = ksplit_for(Q);
     p.err_flag = h->d_t32_err;
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
-    H_CUDA(h, oz::launch<NS>(h->tm_bw, h->tm_ba64, p, n_tiles, Q, st));
-    h->gemm_launches++;
-    KCOUNT(h, 1);
+    H_CUDA(h, h_i8_launch(h, h->tm_bw, h->tm_ba64, p, n_tiles, Q, st, (double)Q * Mp * Mp * Bc));
   }
   if (md.nlta > 0) {
     const int nl = md.nlta;
@@ -1315,11 +1451,195 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
       p.mapB[slot] = slot;
       p.mapC[slot] = md.lta_latent[slot];
     }
-    H_CUDA(h, oz::launch<NS>(h->tm_ba128, h->tm_bld, p, n_tiles, nl, st));
-    h->gemm_launches++;
-    KCOUNT(h, 1);
+    H_CUDA(h, h_i8_launch(h, h->tm_ba128, h->tm_bld, p, n_tiles, nl, st, (double)nl * Mp * Mp * Bc));
   }
   H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+// ---- the whole training step on the INT8 tensor cores -------------------------------------------------------------------
+static mogpe_status ensure_i8_step(mogpe_handle* h) {
+  const ModelDev& md = h->md_host;
+  if (md.NV > h->t8_vmax_cap) {
+    if (h->t8_vmax) cudaFree(h->t8_vmax);
+    if (h->t8_bound_bits) cudaFree(h->t8_bound_bits);
+    h->t8_vmax = nullptr;
+    h->t8_bound_bits = nullptr;
+    H_CUDA(h, dalloc(&h->t8_vmax, (size_t)md.NV));
+    H_CUDA(h, dalloc(&h->t8_bound_bits, 2 * (size_t)md.P + md.NV));
+    h->t8_vmax_cap = md.NV;
+    h->graphs_dirty = true;
+  }
+  if (h->i8_step_ready) return MOGPE_OK;
+  mogpe_status rc = ensure_i8_bwd(h);
+  if (rc != MOGPE_OK) return rc;
+  const size_t Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;
+  constexpr size_t NS = 8;
+  H_CUDA(h, dalloc(&h->t8_Linv, Q * NS * Mp * Mp));
+  H_CUDA(h, dalloc(&h->t8_LinvT, Q * NS * Mp * Mp));
+  H_CUDA(h, dalloc(&h->t8_ST, P * NS * Mp * Mp));
+  H_CUDA(h, dalloc(&h->t8_S, P * NS * Mp * Mp));
+  H_CUDA(h, dalloc(&h->t8_KufT, Q * NS * Bp * Mp));
+  H_CUDA(h, dalloc(&h->t8_AT, Q * NS * Bp * Mp));
+  H_CUDA(h, dalloc(&h->t8_AbarT, Q * NS * Bp * Mp));
+  H_CUDA(h, dalloc(&h->t8_LTAT, P * NS * Bp * Mp));
+  H_CUDA(h, dalloc(&h->t8_linv_scale, Q * Mp));
+  H_CUDA(h, dalloc(&h->t8_linvT_scale, Q * Mp));
+  H_CUDA(h, dalloc(&h->t8_st_scale, P * Mp));
+  H_CUDA(h, dalloc(&h->t8_s_scale, P * Mp));
+  H_CUDA(h, dalloc(&h->t8_lta_scale, P));
+  H_CUDA(h, dalloc(&h->t8_srowmax, P));
+  H_CUDA(h, dalloc(&h->t8_nscale, Q * Bp));
+  H_CUDA(h, dalloc(&h->t8_P2, P * Mp * Bp));
+  H_CUDA(h, dalloc(&h->t8_wmax, Q * Mp));
+  if (!h->alpha) H_CUDA(h, dalloc(&h->alpha, P * MOGPE_MAX_SAMPLES * (size_t)h->Mp32));
+  const int q = (int)Q, pp = (int)P, m = (int)Mp, b = (int)Bp;
+  if (!oz::make_map_i8(&h->tmt_linv, h->t8_Linv, q, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_linvT, h->t8_LinvT, q, m, m, oz::BM) ||
+      !oz::make_map_i8(&h->tmt_st, h->t8_ST, pp, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_s, h->t8_S, pp, m, m, oz::BM) ||
+      !oz::make_map_i8(&h->tmt_kuf, h->t8_KufT, q, b, m, oz::BN) || !oz::make_map_i8(&h->tmt_at, h->t8_AT, q, b, m, oz::BN) ||
+      !oz::make_map_i8(&h->tmt_abart, h->t8_AbarT, q, b, m, oz::BN) || !oz::make_map_i8(&h->tmt_ltat, h->t8_LTAT, pp, b, m, oz::BN))
+    return MOGPE_ERR_UNSUPPORTED;
+  h->graphs_dirty = true;
+  h->i8_step_ready = true;
+  return MOGPE_OK;
+}
+
+static bool i8_step_shape_ok(const mogpe_handle* h, int Bc) {
+  return h->Mp % 128 == 0 && h->Mp >= 512 && Bc >= 2048 && h->Mp32 == h->Mp;
+}
+
+// Forward of the INT8 step: chain -> operand planes -> Kuf^T planes (+ FP64 means) -> A product (statistics, A^T planes for
+// LTA, A planes for the backward) -> LTA product (statistics, LTA^T planes for S LTA, FP64 LTA for Sbar) -> statistics.
+static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X, int N,
+                                    int Bc, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, Mp = h->Mp, Bp = h->Bp, m_tiles = Mp / oz::BM, nl = md.nlta;
+  constexpr int NS = 8;
+  // Kuf^T planes do not depend on the factorisation: they are produced on the side stream underneath the latency-bound
+  // Cholesky chain (factorise forks / joins the side stream; the planes are queued there first)
+  oz::group_scales_kernel<<<1, MAXQ, 0, st>>>(h->d_md, params, h->lo, h->kuf_scale, h->aout_scale);
+  KCOUNT(h, 1);
+  const bool kuf_aside = !h->prof;  // profiling: timed alone on the caller's stream
+  auto launch_kuf8 = [&](cudaStream_t ks) {
+    sk_begin(h, SK_KUF, ks);
+    const dim3 kg(Bc / 64, Mp / 128, Q);
+#define MOGPE_KUF8T(DM) \
+  oz::kuf8_kernel<DM, NS><<<kg, 128, 0, ks>>>(h->d_md, params, h->lo, X, N, Bp, Mp, h->kuf_scale, h->t8_KufT, nullptr, h->dot_part, m_tiles)
+    if (md.D <= 2) MOGPE_KUF8T(2); else if (md.D <= 4) MOGPE_KUF8T(4); else if (md.D <= 8) MOGPE_KUF8T(8); else MOGPE_KUF8T(16);
+#undef MOGPE_KUF8T
+    // algorithmic bytes: Kuf as byte planes (8 B per element, as FP64), X and Z in
+    sk_end(h, SK_KUF, ks, 8.0 * Q * ((double)Mp * N + (double)N * md.D + (double)Mp * md.D));
+    KCOUNT(h, 1);
+  };
+  if (kuf_aside) {
+    H_CUDA(h, side_fork(h, st));  // after group_scales; factorise() forks again (harmless) and joins
+    launch_kuf8(h->side);
+  }
+  mogpe_status rc = factorise(h, params, eps_u, S, X, N, Bc, st, false);
+  if (rc != MOGPE_OK) return rc;
+  if (!kuf_aside) launch_kuf8(st);
+  const dim3 sq(Mp / 32, Mp / 32, Q), sb(32, 8);
+  oz::row_scale_kernel<<<dim3(Mp, Q), 128, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1, h->t8_linv_scale, Mp);
+  oz::slice_square_kernel<NS><<<sq, sb, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1, h->t8_linv_scale, h->t8_Linv, Mp);
+  oz::row_scale_kernel<<<dim3(Mp, Q), 128, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 1, 0, h->t8_linvT_scale, Mp);
+  oz::slice_square_kernel<NS><<<sq, sb, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 1, 0, h->t8_linvT_scale, h->t8_LinvT, Mp);
+  KCOUNT(h, 4);
+  if (nl > 0) {
+    const dim3 sl(Mp / 32, Mp / 32, nl);
+    oz::row_scale_kernel<<<dim3(Mp, nl), 128, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0, h->t8_st_scale, Mp);
+    oz::slice_square_kernel<NS><<<sl, sb, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0, h->t8_st_scale, h->t8_ST, Mp);
+    oz::row_scale_kernel<<<dim3(Mp, nl), 128, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 0, 1, h->t8_s_scale, Mp);
+    oz::slice_square_kernel<NS><<<sl, sb, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 0, 1, h->t8_s_scale, h->t8_S, Mp);
+    KCOUNT(h, 4);
+  }
+  {
+    unsigned long long* bb = h->t8_bound_bits;  // [P] column norms | [P] row norms | [NVcap] vector maxima
+    H_CUDA(h, cudaMemsetAsync(bb, 0, sizeof(unsigned long long) * (2 * (size_t)md.P + h->t8_vmax_cap), st));
+    oz::bounds_kernel<<<dim3(Mp / 32, nl + md.NV), 256, 0, st>>>(h->d_md, h->Sc, h->V, bb, bb + md.P, bb + 2 * md.P);
+    oz::bounds_finish_kernel<<<1, 256, 0, st>>>(h->d_md, params, h->lo, bb, bb + md.P, bb + 2 * md.P, h->t8_lta_scale,
+                                                h->t8_srowmax, h->t8_vmax);
+    KCOUNT(h, 2);
+  }
+  H_CUDA(h, cudaGetLastError());
+  {  // A = L^-1 Kuf
+    oz::Params p;
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = m_tiles; p.K = Mp; p.kmode = t32::K_LOWER;
+    p.a_scale = h->t8_linv_scale; p.a_scale_stride = Mp; p.b_scale = h->kuf_scale;
+    p.ss_part = h->ss_part; p.ld_ss = Bp; p.err_flag = h->d_t32_err;
+    // the means A^T v of every vector of the group, from the same tile (no alpha = L^-T v, no second pass)
+    p.dot_part = h->dot_part; p.dotV = h->V; p.dotV_ld = Mp;
+    p.dvec_begin = reinterpret_cast<const int*>(reinterpret_cast<const char*>(h->d_md) + offsetof(ModelDev, gvec_begin));
+    p.dvec = reinterpret_cast<const int*>(reinterpret_cast<const char*>(h->d_md) + offsetof(ModelDev, gvec));
+    p.out_scale = h->aout_scale;
+    if (nl > 0) {  // A^T planes only for the groups that have a marginal latent (B operand of S^T A)
+      p.out = h->t8_AT; p.out_batch_stride = (long long)NS * Bp * Mp; p.out_plane_stride = (long long)Bp * Mp; p.ldo = Mp;
+      for (int slot = 0; slot < nl; slot++) p.out_mask |= 1ull << md.lta_group[slot];
+    }
+    p.outn = h->bA8; p.outn_batch_stride = (long long)NS * Mp * Bp; p.outn_plane_stride = (long long)Mp * Bp; p.ldn = Bp;
+    for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
+    H_CUDA(h, h_i8_launch(h, h->tmt_linv, h->tmt_kuf, p, Bc / oz::BN, Q, st, (double)Q * Mp * Mp * Bc));
+  }
+  if (nl > 0) {  // LTA_l = S_l^T A
+    oz::Params p;
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = m_tiles; p.K = Mp; p.kmode = t32::K_UPPER;
+    p.a_scale = h->t8_st_scale; p.a_scale_stride = Mp; p.b_scale = h->aout_scale;
+    p.ss_part = h->lta_part; p.ld_ss = Bp; p.err_flag = h->d_t32_err;
+    p.out = h->t8_LTAT; p.out_batch_stride = (long long)NS * Bp * Mp; p.out_plane_stride = (long long)Bp * Mp; p.ldo = Mp;
+    p.out_scale = h->t8_lta_scale;
+    p.out64 = h->LTA; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
+    for (int slot = 0; slot < nl; slot++) {
+      p.mapA[slot] = slot;
+      p.mapB[slot] = md.lta_group[slot];
+      p.mapC[slot] = slot;
+    }
+    H_CUDA(h, h_i8_launch(h, h->tmt_st, h->tmt_at, p, Bc / oz::BN, nl, st, (double)nl * Mp * Mp * Bc));
+  }
+  KCOUNT(h, 1);
+  stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + nl), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, h->dot_part, h->lta_part,
+                                                                      m_tiles, Bp, h->var0ss, h->mean, h->varq);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
+// Backward of the INT8 step up to W = Kuf-bar:  P2_l = S_l LTA_l  ->  Abar planes (abar8_kernel, + dV)  ->  W = L^-T Abar
+// (FP64 for the Kuf gradients, row maxima for its slicing).
+static mogpe_status i8_step_backward_to_W(mogpe_handle* h, int N, int Bc, cudaStream_t st) {
+  const ModelDev& md = h->md_host;
+  const int Q = md.Q, Mp = h->Mp, Bp = h->Bp, m_tiles = Mp / oz::BM, nl = md.nlta;
+  constexpr int NS = 8;
+  H_CUDA(h, cudaMemsetAsync(h->dV, 0, (size_t)md.NV * Mp * sizeof(double), st));
+  H_CUDA(h, cudaMemsetAsync(h->t8_wmax, 0, (size_t)Q * Mp * sizeof(unsigned long long), st));
+  if (nl > 0) {
+    oz::Params p;
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = m_tiles; p.K = Mp; p.kmode = t32::K_LOWER;
+    p.a_scale = h->t8_s_scale; p.a_scale_stride = Mp; p.b_scale = h->t8_lta_scale;
+    p.err_flag = h->d_t32_err;
+    p.out64 = h->t8_P2; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
+    for (int slot = 0; slot < nl; slot++) p.mapA[slot] = p.mapB[slot] = p.mapC[slot] = slot;
+    H_CUDA(h, h_i8_launch(h, h->tmt_s, h->tmt_ltat, p, Bc / oz::BN, nl, st, (double)nl * Mp * Mp * Bc));
+  }
+  sk_begin(h, SK_ABAR, st);
+  oz::abar8_kernel<NS><<<dim3(Bc / 64, Mp / 64, Q), 256, 0, st>>>(h->d_md, h->bA8, h->aout_scale, h->V, h->dmean, h->dfvar, h->var0ss,
+                                                                 h->varq, h->t8_P2, h->t8_vmax, h->t8_srowmax, N, Bp, h->t8_AbarT,
+                                                                 h->t8_nscale, h->dV);
+  sk_end(h, SK_ABAR, st, 8.0 * (2.0 * Q + nl) * Mp * N);  // read the A planes (and S LTA), write the Abar planes
+  KCOUNT(h, 1);
+  H_CUDA(h, cudaGetLastError());
+  {  // W = L^-T Abar
+    oz::Params p;
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = m_tiles; p.K = Mp; p.kmode = t32::K_UPPER;
+    p.a_scale = h->t8_linvT_scale; p.a_scale_stride = Mp;
+    p.b_row_scale = h->t8_nscale; p.b_row_scale_stride = Bp;
+    p.err_flag = h->d_t32_err;
+    p.out64 = h->W; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
+    p.rowmax64 = h->t8_wmax; p.rowmax64_stride = Mp;
+    for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
+    H_CUDA(h, h_i8_launch(h, h->tmt_linvT, h->tmt_abart, p, Bc / oz::BN, Q, st, (double)Q * Mp * Mp * Bc));
+  }
   return MOGPE_OK;
 }
 
@@ -1588,6 +1908,13 @@ extern "C" mogpe_status mogpe_set_int8_backward(mogpe_handle* h, int32_t on) {
   return MOGPE_OK;
 }
 
+extern "C" mogpe_status mogpe_set_int8_step(mogpe_handle* h, int32_t on) {
+  if (!h) return MOGPE_ERR_INVALID;
+  h->i8_step_on = on != 0;
+  h->graphs_dirty = true;
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_set_dp_overlap(mogpe_handle* h, int32_t on) {
   if (!h) return MOGPE_ERR_INVALID;
   if (on && !h->nccl_comm) H_FAIL(h, MOGPE_ERR_NCCL, "mogpe_comm_init has not been called on this handle");
@@ -1656,6 +1983,9 @@ extern "C" mogpe_status mogpe_profile_enable(mogpe_handle* h, int32_t on) {
   h->prof = on != 0;
   h->ev_used = 0;
   h->prof_flops = 0;
+  h->ev8_used = 0;
+  h->prof8_flops = 0;
+  h->i8_launches = 0;
   for (int i = 0; i < mogpe_handle::NSK; i++) {
     h->sk_used[i] = 0;
     h->sk_bytes[i] = 0;
@@ -1682,6 +2012,25 @@ extern "C" mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, dou
   h->ev_used = 0;
   h->prof_flops = 0;
   h->gemm_launches = h->all_launches = 0;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_profile_read_int8(mogpe_handle* h, double* ms_out, double* flops, int64_t* launches) {
+  if (!h) return MOGPE_ERR_INVALID;
+  H_CUDA(h, cudaSetDevice(h->device));
+  if (h->prof_stream || h->ev8_used) H_CUDA(h, cudaStreamSynchronize(h->prof_stream));
+  double ms = 0;
+  for (size_t i = 0; i + 1 < h->ev8_used; i += 2) {
+    float t = 0;
+    H_CUDA(h, cudaEventElapsedTime(&t, h->ev8[i], h->ev8[i + 1]));
+    ms += t;
+  }
+  if (ms_out) *ms_out = ms;
+  if (flops) *flops = h->prof8_flops;
+  if (launches) *launches = h->i8_launches;
+  h->ev8_used = 0;
+  h->prof8_flops = 0;
+  h->i8_launches = 0;
   return MOGPE_OK;
 }
 

@@ -605,7 +605,9 @@ __global__ void q_grads_kernel(const ModelDev* __restrict__ md, Layout lo, const
 // One warp per ROWS rows m (coalesced over n; x_n is loaded once for the ROWS rows).
 // grid (Mp/(8*ROWS), Q), block 256.  D <= DMAX.
 // ------------------------------------------------------------------------------------------------
-template <int DMAX, int ROWS>
+// REGEN: Kuf is not read but re-evaluated from X and Z (the INT8-sliced step never materialises it in FP64): one FP64 exp
+// per element in exchange for half of the kernel's HBM reads.
+template <int DMAX, int ROWS, bool REGEN = false>
 __global__ void __launch_bounds__(256) kuf_grad_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
                                                        Layout lo, const double* __restrict__ X, int N, int Bp,
                                                        const double* __restrict__ W, const double* __restrict__ Kuf,
@@ -629,14 +631,40 @@ __global__ void __launch_bounds__(256) kuf_grad_kernel(const ModelDev* __restric
     }
   }
   const double* w = W + ((long long)g * Mp + m0) * Bp;
-  const double* kf = Kuf + ((long long)g * Mp + m0) * Bp;
+  const double* kf = REGEN ? nullptr : Kuf + ((long long)g * Mp + m0) * Bp;
+  double il[DMAX], zn[ROWS];  // REGEN: 1 / lengthscale and |z / l|^2 (the forward's expanded squared-distance form)
+  const double kvar = params[lo.kvar + g];
+  if (REGEN) {
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) il[d] = d < D ? 1.0 / ls[d] : 0.0;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      zn[r] = 0.0;
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) zn[r] += (zz[r][d] * il[d]) * (zz[r][d] * il[d]);
+    }
+  }
 #pragma unroll(8 / ROWS)
   for (int n = n_lo + lane; n < n_hi; n += 32) {
     double x[DMAX], e[ROWS];
 #pragma unroll
-    for (int r = 0; r < ROWS; r++) e[r] = w[(long long)r * Bp + n] * kf[(long long)r * Bp + n];  // rows >= Mg: Kuf = 0
-#pragma unroll
     for (int d = 0; d < DMAX; d++) x[d] = (d < D) ? X[(long long)n * D + d] : 0.0;
+    if (REGEN) {
+      double xn = 0.0;
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) xn += (x[d] * il[d]) * (x[d] * il[d]);
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        double dot = 0.0;
+#pragma unroll
+        for (int d = 0; d < DMAX; d++) dot += (zz[r][d] * il[d]) * (x[d] * il[d]);
+        const double r2 = -2.0 * dot + (zn[r] + xn);
+        e[r] = (m0 + r < Mg) ? w[(long long)r * Bp + n] * (kvar * exp(-0.5 * r2)) : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) e[r] = w[(long long)r * Bp + n] * kf[(long long)r * Bp + n];  // rows >= Mg: Kuf = 0
+    }
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
       se[r] += e[r];

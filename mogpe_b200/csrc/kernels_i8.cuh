@@ -1,0 +1,344 @@
+// Streaming kernels of the INT8-sliced TRAINING step (gemm_i8.cuh products inside mogpe_elbo_fwd_bwd): operand bounds,
+// the fused build-Abar + transpose + slice pass, and row-maximum -> scale conversion.
+//
+// Every FP64 operand of a sliced product is written as 2^e * sum_p q_p 2^(-7 (p + 1)) with |x| <= 2^(e-1).  Where the scale
+// 2^e of an operand cannot be measured without an extra pass over it, a rigorous a-priori BOUND is used instead: eight byte
+// slices carry 56 bits, the tolerance of the path needs ~35, so a bound that is loose by a factor 2^5 .. 2^10 costs nothing.
+#pragma once
+#include "gemm_i8.cuh"
+#include "model_dev.cuh"
+
+namespace mogpe {
+namespace oz {
+
+// Bounds of the sliced operands that are known before the products run (S = tril(q_sqrt), V = mean vectors):
+//   cmax2[slot] = max_m |S[:, m]|_2^2,  rmax2[slot] = max_m |S[m, :]|_2^2   (per marginal-latent slot),
+//   vmax[v]     = max_m |V[v][m]|                                           (per mean vector),
+// accumulated with atomicMax on the bit patterns of non-negative doubles (the buffers are zeroed by the caller).
+// Block (x, slot) sweeps the 32-column block x of S (column norms, rows >= 32 x) and the 32-row slab x (row norms).
+// grid (Mp/32, nlta + NV), block 256
+__global__ void __launch_bounds__(256) bounds_kernel(const ModelDev* __restrict__ md, const double* __restrict__ Sc,
+                                                     const double* __restrict__ V, unsigned long long* __restrict__ cmax2,
+                                                     unsigned long long* __restrict__ rmax2,
+                                                     unsigned long long* __restrict__ vmax_bits) {
+  __shared__ double colp[8][33];
+  const int Mp = md->Mp, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cb = blockIdx.x * 32;
+  if ((int)blockIdx.y < md->nlta) {
+    const int slot = blockIdx.y, l = md->lta_latent[slot];
+    const double* S = Sc + (long long)l * Mp * Mp;
+    double cs = 0.0;
+    for (int r = cb + warp; r < Mp; r += 8) {
+      const double x = S[(long long)r * Mp + cb + lane];  // exact zeros above the diagonal (clean copy)
+      cs += x * x;
+    }
+    colp[warp][lane] = cs;
+    double rmax = 0.0;
+    for (int r = cb + warp; r < cb + 32; r += 8) {
+      double s2 = 0.0;
+      for (int c = lane; c <= r; c += 32) {
+        const double x = S[(long long)r * Mp + c];
+        s2 += x * x;
+      }
+      rmax = fmax(rmax, warp_sum(s2));
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; w++) t += colp[w][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+      if (lane == 0) atomicMax(cmax2 + slot, (unsigned long long)__double_as_longlong(t));
+    }
+    if (lane == 0) atomicMax(rmax2 + slot, (unsigned long long)__double_as_longlong(rmax));
+  } else {
+    const int v = blockIdx.y - md->nlta;
+    if (tid < 32) {
+      double m = fabs(V[(long long)v * Mp + cb + tid]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (tid == 0) atomicMax(vmax_bits + v, (unsigned long long)__double_as_longlong(m));
+    }
+  }
+}
+
+// lta_scale[slot] = pow2_scale(max_m |S[:, m]|_2 sqrt(kvar_g))  (|LTA[m][n]| = |S[:, m] . a_n| <= |S[:, m]|_2 |a_n|_2 and
+// |a_n|_2^2 = sum_m A[m][n]^2 <= kvar);  srowmax[latent] = max_m |S[m, :]|_2  (bound of S LTA);  vmax[v] as doubles.
+// one block, 256 threads
+__global__ void bounds_finish_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
+                                     const unsigned long long* __restrict__ cmax2, const unsigned long long* __restrict__ rmax2,
+                                     const unsigned long long* __restrict__ vmax_bits, double* __restrict__ lta_scale,
+                                     double* __restrict__ srowmax, double* __restrict__ vmax) {
+  for (int i = threadIdx.x; i < md->nlta; i += blockDim.x) {
+    const int l = md->lta_latent[i], g = md->latent_group[l];
+    lta_scale[i] = pow2_scale(1.0001 * sqrt(__longlong_as_double((long long)cmax2[i])) * sqrt(params[lo.kvar + g]));
+    srowmax[l] = 1.0001 * sqrt(__longlong_as_double((long long)rmax2[i]));
+  }
+  for (int i = threadIdx.x; i < md->NV; i += blockDim.x) vmax[i] = __longlong_as_double((long long)vmax_bits[i]);
+}
+
+// scale[i] = pow2_scale(max[i]) from the bit patterns accumulated by atomicMax (non-negative doubles order like integers)
+__global__ void max_to_scale_kernel(const unsigned long long* __restrict__ mx, double* __restrict__ scale, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scale[i] = pow2_scale(__longlong_as_double((long long)mx[i]));
+}
+
+// Backward, fused: Abar (never materialised in FP64) -> transposed byte planes, the B operand of W = L^-T Abar.
+//   Abar[g][m][n] = -2 A[m][n] sum_{l in g} dfvar[l][n] + sum_{v in g} V[v][m] dmean[v][n]
+//                   + sum_{marginal l in g} 2 dfvar[l][n] (S_l LTA_l)[m][n]                 (P2[slot(l)] = S_l LTA_l)
+//   dV[v][m]     += sum_n A[g][m][n] dmean[v][n]                                            (dV zero-initialised)
+// A comes from its [m][n] byte planes (written by the epilogue of the A product; 2^e = a_scale[g]); the result is sliced
+// against a per-COLUMN scale from a rigorous bound (|A[m][n]| <= sqrt(var0ss[n]), |P2[m][n]| <= max_m |S[m, :]|_2 sqrt(varq[n]),
+// |V[v][m]| <= vmax[v]) -- a column scale commutes with the left multiplication by L^-T (gemm_i8 b_row_scale) -- and goes out
+// as AbarT8[g][plane][n][m] through a shared-memory transpose.        grid (Bc/64, Mp/64, Q), block 256
+// sign-extended byte J of w
+template <int J>
+__device__ __forceinline__ int sbyte(uint32_t w) {
+  return (int)(w << (24 - 8 * J)) >> 24;
+}
+
+// value of element J (0..3) of four consecutive columns from the NS plane words w[s] (byte J of every word), in units of
+// the operand scale:  sum_s d_s 2^(-7 (s + 1)),  exact (two integers of 28 bits, combined in FP64)
+template <int NS, int J>
+__device__ __forceinline__ double unslice(const uint32_t (&w)[NS]) {
+  constexpr int H = NS / 2;
+  int hi = sbyte<J>(w[0]), lo = sbyte<J>(w[H]);
+#pragma unroll
+  for (int k = 1; k < H; k++) {
+    hi = hi * 128 + sbyte<J>(w[k]);
+    lo = lo * 128 + sbyte<J>(w[H + k]);
+  }
+  constexpr double P1 = 1.0 / (double)(1 << (7 * H));
+  return fma(int_to_double(lo), P1, int_to_double(hi)) * P1;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__ md, const int8_t* __restrict__ A8,
+                                                    const double* __restrict__ a_scale, const double* __restrict__ V,
+                                                    const double* __restrict__ dmean, const double* __restrict__ dfvar,
+                                                    const double* __restrict__ var0ss, const double* __restrict__ varq,
+                                                    const double* __restrict__ P2, const double* __restrict__ vmax,
+                                                    const double* __restrict__ srowmax, int N, int Bp,
+                                                    int8_t* __restrict__ AbarT8, double* __restrict__ nscale,
+                                                    double* __restrict__ dV) {
+  constexpr int PITCH = 65;  // words per [n] row of the staging tile (64 m + 1: column groups of a warp spread over the banks)
+  __shared__ uint32_t stage[2][64][PITCH];  // [slice half][n][m]: the four digit bytes of planes 4 half .. 4 half + 3
+  __shared__ double s_inv[64], s_dv[64];
+  const int g = blockIdx.z, Mp = md->Mp, m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  const int lb = md->glat_begin[g], le = md->glat_begin[g + 1], vb = md->gvec_begin[g], ve = md->gvec_begin[g + 1];
+  if (tid < 64) {
+    const int n = n0 + tid;
+    double dv = 0.0, b = 0.0;
+    if (n < N) {
+      for (int q = lb; q < le; q++) {
+        const int l = md->glat[q];
+        const double d = dfvar[(long long)l * Bp + n];
+        dv += d;
+        if (md->marg[l]) b += 2.0 * fabs(d) * srowmax[l] * sqrt(fmax(varq[(long long)l * Bp + n], 0.0));
+      }
+      b += 2.0 * fabs(dv) * sqrt(fmax(var0ss[(long long)g * Bp + n], 0.0));
+      for (int q = vb; q < ve; q++) {
+        const int v = md->gvec[q];
+        b += vmax[v] * fabs(dmean[(long long)v * Bp + n]);
+      }
+    }
+    const double sc = pow2_scale(1.001 * b);
+    s_inv[tid] = 1.0 / sc;
+    s_dv[tid] = dv;
+    if (blockIdx.y == 0) nscale[(long long)g * Bp + n] = sc;
+  }
+  __syncthreads();
+  const int c4 = (tid & 15) * 4, r = tid >> 4;
+  const long long plane = (long long)Mp * Bp;
+  const int8_t* Ag = A8 + (long long)g * NS * plane;
+  const double asc = a_scale[g];
+  const bool live = n0 + c4 < N;  // N is not required to be a multiple of 4: columns >= N hold zero planes and zero adjoints
+#pragma unroll 2
+  for (int pass = 0; pass < 4; pass++) {
+    const int ml = pass * 16 + r, m = m0 + ml;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    if (live) {
+      uint32_t w[NS];
+#pragma unroll
+      for (int s = 0; s < NS; s++) w[s] = *reinterpret_cast<const uint32_t*>(Ag + s * plane + (long long)m * Bp + n0 + c4);
+      a[0] = unslice<NS, 0>(w) * asc;
+      a[1] = unslice<NS, 1>(w) * asc;
+      a[2] = unslice<NS, 2>(w) * asc;
+      a[3] = unslice<NS, 3>(w) * asc;
+    }
+    double ab[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) ab[j] = -2.0 * s_dv[c4 + j] * a[j];
+    for (int q = vb; q < ve; q++) {
+      const int v = md->gvec[q];
+      const double vm = V[(long long)v * Mp + m];
+      double part = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double dm = (n0 + c4 + j < N) ? dmean[(long long)v * Bp + n0 + c4 + j] : 0.0;
+        ab[j] += vm * dm;
+        part += a[j] * dm;
+      }
+      // the 16 threads of one tile row are 16 consecutive lanes
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 8);
+      if ((tid & 15) == 0) atomicAdd(dV + (long long)v * Mp + m, part);
+    }
+    for (int q = lb; q < le; q++) {
+      const int l = md->glat[q];
+      if (!md->marg[l]) continue;
+      const double* p2 = P2 + ((long long)md->lta_slot[l] * Mp + m) * Bp + n0 + c4;
+      const double* dl = dfvar + (long long)l * Bp + n0 + c4;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (n0 + c4 + j < N) ab[j] += 2.0 * dl[j] * p2[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t wh, wl;
+      slice_words<NS>(ab[j] * s_inv[c4 + j], wh, wl);
+      stage[0][c4 + j][ml] = wh;
+      stage[1][c4 + j][ml] = wl;
+    }
+  }
+  __syncthreads();
+  // read back 16 consecutive m of one (half, n), transpose the digit bytes into plane words and store 16 bytes per plane
+  int8_t* Og = AbarT8 + (long long)g * NS * Bp * Mp;
+  for (int u = tid; u < 2 * 64 * 4; u += 256) {
+    const int half = u >> 8, n = (u >> 2) & 63, mg = u & 3;
+    const uint32_t* sp = &stage[half][n][mg * 16];
+    uint32_t o4[4][4];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; k4++) {
+      uint32_t tr[4];
+      transpose4x4_bytes(sp[4 * k4], sp[4 * k4 + 1], sp[4 * k4 + 2], sp[4 * k4 + 3], tr);
+#pragma unroll
+      for (int b4 = 0; b4 < 4; b4++) o4[b4][k4] = tr[b4];
+    }
+    int8_t* ob = Og + (long long)(n0 + n) * Mp + m0 + mg * 16;
+#pragma unroll
+    for (int b4 = 4 - NS / 2; b4 < 4; b4++) {  // byte b4 of a slice word = digit 3 - b4 of its half
+      const int pl = half * (NS / 2) + 3 - b4;
+      *reinterpret_cast<uint4*>(ob + (long long)pl * Bp * Mp) = make_uint4(o4[b4][0], o4[b4][1], o4[b4][2], o4[b4][3]);
+    }
+  }
+}
+
+}  // namespace oz
+}  // namespace mogpe
+
+namespace mogpe {
+namespace oz {
+
+__device__ __forceinline__ void ld_global_256(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+// Kuf-bar (= W) consumer of the INT8 step, ONE pass over W [g][m][n]:
+//   (a) kernel-hyperparameter and Z gradients  E = W .* Kuf,  dZ[m,d] = -sum_n E (z_md - x_nd) / l_d^2,
+//       dl_d = sum_mn E (z_md - x_nd)^2 / l_d^3,  dvar = sum E / var   (as kuf_grad_kernel) with Kuf RE-EVALUATED from X and Z
+//       (the step holds it only as byte planes; one FP64 exp per element instead of a second 8-byte read), and
+//   (b) the [m][n] byte planes of W for Lbar = -tril(W A^T), sliced against the exact row maxima that the epilogue of the
+//       W product collected (wmax, bit patterns) -- no separate slicing pass over W.
+// One warp per row m, every lane four consecutive columns per step (128 columns per warp step: 1 KB of W, 128 B per byte
+// plane).  n_chunk must be a multiple of 128.       grid (Mp/8, Q, nsplit), block 256
+template <int DMAX, int NS>
+__global__ void __launch_bounds__(256) kuf_grad_slice_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
+                                                             Layout lo, const double* __restrict__ X, int N, int Bc, int Bp,
+                                                             const double* __restrict__ W,
+                                                             const unsigned long long* __restrict__ wmax,
+                                                             double* __restrict__ grads, int8_t* __restrict__ W8,
+                                                             double* __restrict__ w_scale, int n_chunk) {
+  const int g = blockIdx.y, Mp = md->Mp, D = md->D, Mg = md->group_M[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  const int n_lo = blockIdx.z * n_chunk, n_hi = min(Bc, n_lo + n_chunk);
+  const double* ls = params + lo.ls + (long long)g * D;
+  const double kvar = params[lo.kvar + g];
+  const bool live = m < Mg;  // padded rows: Kuf = 0 (no gradient), W planes are still written (zeros in, zeros out)
+  double il[DMAX], zs[DMAX], zz[DMAX], a1[DMAX], a2[DMAX], zn = 0.0, se = 0.0;
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) {
+    il[d] = d < D ? 1.0 / ls[d] : 0.0;
+    zz[d] = (d < D && live) ? params[lo.Z + ((long long)g * Mp + m) * D + d] : 0.0;
+    zs[d] = zz[d] * il[d];
+    zn += zs[d] * zs[d];
+    a1[d] = a2[d] = 0.0;
+  }
+  const double sc = pow2_scale(__longlong_as_double((long long)wmax[(long long)g * Mp + m]));
+  const double inv = 1.0 / sc;
+  if (lane == 0 && blockIdx.z == 0) w_scale[(long long)g * Mp + m] = sc;
+  const double* w = W + ((long long)g * Mp + m) * Bp;
+  int8_t* o8 = W8 + ((long long)g * NS * Mp + m) * Bp;
+  const long long plane = (long long)Mp * Bp;
+  for (int n4 = n_lo + lane * 4; n4 < n_hi; n4 += 128) {
+    double wv[4];
+    ld_global_256(w + n4, wv);
+    uint32_t wh[4], wl[4];
+    double ev[4], xv[4][DMAX];
+    // branch-free over the four columns (independent exp chains in flight); columns >= N contribute nothing (mask)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      slice_words<NS>(wv[j] * inv, wh[j], wl[j]);
+      const bool ok = live && n4 + j < N;
+      const long long xi = (long long)(ok ? n4 + j : 0) * D;
+      if (DMAX == 4) {
+        if (D == 4) ld_global_256(X + xi, *reinterpret_cast<double(*)[4]>(&xv[j][0]));
+        else
+#pragma unroll
+          for (int d = 0; d < DMAX; d++) xv[j][d] = d < D ? X[xi + d] : 0.0;
+      } else {
+#pragma unroll
+        for (int d = 0; d < DMAX; d++) xv[j][d] = d < D ? X[xi + d] : 0.0;
+      }
+      double dot = 0.0, xn = 0.0;
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) {
+        const double xs = xv[j][d] * il[d];
+        xn += xs * xs;
+        dot += zs[d] * xs;
+      }
+      const double r2 = -2.0 * dot + (zn + xn);
+      ev[j] = ok ? wv[j] * (kvar * exp(-0.5 * r2)) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      se += ev[j];
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) {
+        const double df = zz[d] - xv[j][d];
+        a1[d] += ev[j] * df;
+        a2[d] += ev[j] * df * df;
+      }
+    }
+    uint32_t th[4], tl[4];
+    transpose4x4_bytes(wh[0], wh[1], wh[2], wh[3], th);
+    transpose4x4_bytes(wl[0], wl[1], wl[2], wl[3], tl);
+#pragma unroll
+    for (int b4 = 4 - NS / 2; b4 < 4; b4++) {  // byte b4 of a slice word = digit 3 - b4 of its half
+      *reinterpret_cast<uint32_t*>(o8 + (long long)(3 - b4) * plane + n4) = th[b4];
+      *reinterpret_cast<uint32_t*>(o8 + (long long)(NS / 2 + 3 - b4) * plane + n4) = tl[b4];
+    }
+  }
+  if (!live) return;
+  se = warp_sum(se);
+  double dls[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) {
+    dls[d] = 0.0;
+    if (d < D) {
+      const double s1 = warp_sum(a1[d]);
+      dls[d] = warp_sum(a2[d]);
+      if (lane == 0) atomicAdd(grads + lo.Z + ((long long)g * Mp + m) * D + d, -s1 / (ls[d] * ls[d]));
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(grads + lo.kvar + g, se / kvar);
+    for (int d = 0; d < D && d < DMAX; d++) atomicAdd(grads + lo.ls + (long long)g * D + d, dls[d] / (ls[d] * ls[d] * ls[d]));
+  }
+}
+
+}  // namespace oz
+}  // namespace mogpe

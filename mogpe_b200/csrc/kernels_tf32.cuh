@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) kuf8_kernel(const ModelDev* __restrict__ 
     }
 #pragma unroll
     for (int s = 0; s < NS; s++) *reinterpret_cast<uint32_t*>(base + s * plane + (long long)n * Mp32 + k0) = packed[s];
-    for (int q2 = 0; q2 < nv; q2++) {
+    for (int q2 = 0; q2 < nv && alpha != nullptr; q2++) {  // (alpha == nullptr: the means come from the A product's epilogue)
       const int v = md->gvec[v0 + q2];
       const double* av = alpha + (long long)v * Mp32 + k0;
       double s = kval[0] * av[0] + kval[1] * av[1] + kval[2] * av[2] + kval[3] * av[3];

@@ -416,6 +416,16 @@ class Engine:
         (default on); off keeps them on the FP64 DMMA pipe."""
         _lib.check(self.lib.mogpe_set_int8_backward(self.h, 1 if on else 0), self.h)
 
+    def set_int8_step(self, on: bool):
+        """The whole gradient step (all six dense products) on the INT8 tensor cores when the shape qualifies (default on;
+        requires set_int8_backward(True)); off keeps the forward / Abar / W products on the FP64 DMMA pipe."""
+        _lib.check(self.lib.mogpe_set_int8_step(self.h, 1 if on else 0), self.h)
+
+    def profile_read_int8(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(self.lib.mogpe_profile_read_int8(self.h, C.byref(ms), C.byref(fl), C.byref(n)), self.h)
+        return {"ms": ms.value, "flops": fl.value, "launches": n.value}
+
     def graph_stats(self):
         """-> (captured training-step graphs, capture disabled after a failure)."""
         n, d = C.c_int32(), C.c_int32()

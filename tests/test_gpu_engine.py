@@ -307,6 +307,38 @@ def test_predict_softmax_library_draws_are_chunking_independent_and_close_to_exp
     assert np.max(np.abs(big - ref)) < 0.03  # two independent 4000-draw estimates: std <= 0.5 / sqrt(4000) each
 
 
+@pytest.mark.parametrize("K,F,S,sep", [(3, 1, 2, True), (2, 2, 1, False)])
+@pytest.mark.parametrize("bound", BOUNDS)
+def test_int8_step_general_structures_match_oracle(bound, K, F, S, sep):
+    """The INT8-sliced step on model structures the bench never sees: several samples, a shared kernel with two latents per
+    group (two marginal latents accumulate into one Abar), Softmax gating with separate kernels, every bound (tight: no
+    marginal latent at all; further: the experts are marginal too), inducing counts below the padded size."""
+    from oracle import ref_torch as rt
+    from tests._engine_helpers import engine_from_spec, engine_grads_named, oracle_grads_constrained, run_engine_elbo
+
+    N = 2100  # not a multiple of 64: ragged last column tile
+    spec, X, Y, eps = make_spec(seed=23 + K, N=N, D=3, F=F, K=K, M=400, S=S, flavour="keras", bound=bound, num_data=30000,
+                                separate_kernels=sep, M_gating=512, gating_mean_c=0.1)
+    if bound == "tight" and K > 2:
+        eps["mc"] = np.random.default_rng(3).standard_normal((S, 7, N, K))
+    eng = engine_from_spec(spec, max_batch=N)
+    ref, grads_u = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    want = oracle_grads_constrained(spec, grads_u)
+    eng.profile(True)
+    res = run_engine_elbo(eng, spec, X, Y, eps)
+    assert eng.profile_read_int8()["launches"] >= 3
+    eng.profile(False)
+    assert abs(res.elbo - ref) <= RTOL_VALUE * abs(ref), (res.elbo, ref)
+    got = engine_grads_named(res, spec)
+    bad = {}
+    for name, g in want.items():
+        err = np.max(np.abs(np.asarray(got[name]) - g))
+        if err > RTOL_GRAD * max(1.0, np.max(np.abs(g))):
+            bad[name] = err / max(1.0, np.max(np.abs(g)))
+    assert not bad, bad
+    eng.close()
+
+
 @pytest.mark.parametrize("flavour", FLAVOURS)
 @pytest.mark.parametrize("bound", ["further_gating", "further"])
 def test_int8_backward_products_match_oracle_gradients(flavour, bound):
@@ -325,6 +357,12 @@ def test_int8_backward_products_match_oracle_gradients(flavour, bound):
     got = engine_grads_named(res, spec)
     for name, g in want.items():
         assert np.max(np.abs(np.asarray(got[name]) - g)) <= RTOL_GRAD * max(1.0, np.max(np.abs(g))), name
+    eng.set_int8_step(False)  # hybrid: only Lbar / Sbar on the INT8 tensor cores
+    res_h = run_engine_elbo(eng, spec, X, Y, eps)
+    assert abs(res_h.elbo - ref) <= RTOL_VALUE * abs(ref)
+    got_h = engine_grads_named(res_h, spec)
+    for name, g in want.items():
+        assert np.max(np.abs(np.asarray(got_h[name]) - g)) <= RTOL_GRAD * max(1.0, np.max(np.abs(g))), name
     eng.set_int8_backward(False)
     got64 = engine_grads_named(run_engine_elbo(eng, spec, X, Y, eps), spec)
     differs = False

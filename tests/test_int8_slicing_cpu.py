@@ -15,14 +15,21 @@ def pow2_scale(maxabs):
 
 
 def slice8(x, scale):
-    """-> int slices q[NS, ...] with x ~= scale * sum_p q_p 2^(-7 (p + 1)), |q_p| <= 64 (oz::slice8)."""
+    """-> int slices q[NS, ...] with x ~= scale * sum_p q_p 2^(-7 (p + 1)), |q_p| <= 64 (oz::slice_digits): two rounds of
+    round-to-nearest to 28 bits, each split into four balanced base-128 digits."""
     r = np.asarray(x, dtype=np.float64) / scale
-    q = []
-    for _ in range(NS):
-        t = r * 128.0
-        v = np.rint(t)
-        r = t - v
-        q.append(v.astype(np.int64))
+    H = NS // 2
+    P = float(1 << (7 * H))
+    x1 = r * P
+    hi = np.rint(x1)
+    lo = np.rint((x1 - hi) * P)
+    q = [None] * NS
+    for base, v in ((0, hi.astype(np.int64)), (H, lo.astype(np.int64))):
+        for k in range(H - 1, 0, -1):
+            d = ((v + 64) & 127) - 64  # low 7 bits, sign-extended
+            q[base + k] = d
+            v = (v - d) >> 7
+        q[base] = v
     return np.stack(q)
 
 

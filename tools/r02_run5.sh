@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out/r02
+( time python -m pytest tests/test_gpu_bench_shapes.py tests/test_gpu_engine.py tests/test_gpu_int8.py -m gpu -q -x -k "c4 or int8" ) > gpurun_out/r02/pytest_i8step.log 2>&1
+tail -8 gpurun_out/r02/pytest_i8step.log
+bash tools/r02_ncu_launches.sh ${1:-i8step_v3} | head -24
+python bench.py --steps 20 --warmup 5 --no-predict --no-cpu-baseline > gpurun_out/r02/bench_5.json 2> gpurun_out/r02/bench_5.err
+python tools/show_bench.py gpurun_out/r02/bench_5.json
