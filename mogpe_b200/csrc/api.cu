@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -625,12 +626,14 @@ static void launch_kuf(mogpe_handle* h, const double* params, const double* X, i
 // not depend on the factorisation: the clean q_sqrt copies, the mean vectors V (u-samples) and Kuf of the first
 // chunk.  The Cholesky chain is a sequence of short latency-bound launches that leave most SMs idle.
 static mogpe_status factorise(mogpe_handle* h, const double* params, const double* eps_u, int S, const double* X, int N,
-                              int Bc, cudaStream_t st, bool fp64_products = true) {
+                              int Bc, cudaStream_t st, bool fp64_products = true,
+                              const std::function<void(cudaStream_t)>& side_extra = nullptr) {
   const ModelDev& md = h->md_host;
   const int Q = md.Q, P = md.P, Mp = h->Mp;
   H_CUDA(h, side_fork(h, st));
   prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, h->side>>>(h->d_md, params, h->lo, h->Sc);
   make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, h->side>>>(h->d_md, params, h->lo, h->Sc, eps_u, S, h->V);
+  if (side_extra) side_extra(h->side);  // more work that needs q_sqrt / V but not the factorisation
   if (fp64_products && !h->prof) launch_kuf(h, params, X, N, Bc, h->side);
   kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
   // Launch j of the chain completes block row j of L^-1.  A = L^-1 Kuf only needs rows [64 i, 64 i + 64) of L^-1 for
@@ -1535,31 +1538,33 @@ static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const
     H_CUDA(h, side_fork(h, st));  // after group_scales; factorise() forks again (harmless) and joins
     launch_kuf8(h->side);
   }
-  mogpe_status rc = factorise(h, params, eps_u, S, X, N, Bc, st, false);
+  const dim3 sq(Mp / 32, Mp / 32, Q), sb(32, 8);
+  // operand planes of tril(q_sqrt) (both orientations) and the a-priori bounds: no dependence on the factorisation either ->
+  // side stream, after the clean q_sqrt copies / mean vectors that factorise() queues there
+  auto s_prep = [&](cudaStream_t ss) {
+    if (nl > 0) {
+      const dim3 sl(Mp / 32, Mp / 32, nl);
+      oz::row_scale_kernel<<<dim3(Mp, nl), 128, 0, ss>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0, h->t8_st_scale, Mp);
+      oz::slice_square_kernel<NS><<<sl, sb, 0, ss>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0, h->t8_st_scale, h->t8_ST, Mp);
+      oz::row_scale_kernel<<<dim3(Mp, nl), 128, 0, ss>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 0, 1, h->t8_s_scale, Mp);
+      oz::slice_square_kernel<NS><<<sl, sb, 0, ss>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 0, 1, h->t8_s_scale, h->t8_S, Mp);
+      KCOUNT(h, 4);
+    }
+    unsigned long long* bb = h->t8_bound_bits;  // [P] column norms | [P] row norms | [NVcap] vector maxima
+    cudaMemsetAsync(bb, 0, sizeof(unsigned long long) * (2 * (size_t)md.P + h->t8_vmax_cap), ss);
+    oz::bounds_kernel<<<dim3(Mp / 32, nl + md.NV), 256, 0, ss>>>(h->d_md, h->Sc, h->V, bb, bb + md.P, bb + 2 * md.P);
+    oz::bounds_finish_kernel<<<1, 256, 0, ss>>>(h->d_md, params, h->lo, bb, bb + md.P, bb + 2 * md.P, h->t8_lta_scale,
+                                                h->t8_srowmax, h->t8_vmax);
+    KCOUNT(h, 2);
+  };
+  mogpe_status rc = factorise(h, params, eps_u, S, X, N, Bc, st, false, s_prep);
   if (rc != MOGPE_OK) return rc;
   if (!kuf_aside) launch_kuf8(st);
-  const dim3 sq(Mp / 32, Mp / 32, Q), sb(32, 8);
   oz::row_scale_kernel<<<dim3(Mp, Q), 128, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1, h->t8_linv_scale, Mp);
   oz::slice_square_kernel<NS><<<sq, sb, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1, h->t8_linv_scale, h->t8_Linv, Mp);
   oz::row_scale_kernel<<<dim3(Mp, Q), 128, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 1, 0, h->t8_linvT_scale, Mp);
   oz::slice_square_kernel<NS><<<sq, sb, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 1, 0, h->t8_linvT_scale, h->t8_LinvT, Mp);
   KCOUNT(h, 4);
-  if (nl > 0) {
-    const dim3 sl(Mp / 32, Mp / 32, nl);
-    oz::row_scale_kernel<<<dim3(Mp, nl), 128, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0, h->t8_st_scale, Mp);
-    oz::slice_square_kernel<NS><<<sl, sb, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 1, 0, h->t8_st_scale, h->t8_ST, Mp);
-    oz::row_scale_kernel<<<dim3(Mp, nl), 128, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 0, 1, h->t8_s_scale, Mp);
-    oz::slice_square_kernel<NS><<<sl, sb, 0, st>>>(h->Sc, Mp, (long long)Mp * Mp, Mp, h->d_lta_latent, 0, 1, h->t8_s_scale, h->t8_S, Mp);
-    KCOUNT(h, 4);
-  }
-  {
-    unsigned long long* bb = h->t8_bound_bits;  // [P] column norms | [P] row norms | [NVcap] vector maxima
-    H_CUDA(h, cudaMemsetAsync(bb, 0, sizeof(unsigned long long) * (2 * (size_t)md.P + h->t8_vmax_cap), st));
-    oz::bounds_kernel<<<dim3(Mp / 32, nl + md.NV), 256, 0, st>>>(h->d_md, h->Sc, h->V, bb, bb + md.P, bb + 2 * md.P);
-    oz::bounds_finish_kernel<<<1, 256, 0, st>>>(h->d_md, params, h->lo, bb, bb + md.P, bb + 2 * md.P, h->t8_lta_scale,
-                                                h->t8_srowmax, h->t8_vmax);
-    KCOUNT(h, 2);
-  }
   H_CUDA(h, cudaGetLastError());
   {  // A = L^-1 Kuf
     oz::Params p;

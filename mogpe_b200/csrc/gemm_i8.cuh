@@ -193,8 +193,11 @@ __device__ __forceinline__ void slice_words(double r, uint32_t& wh, uint32_t& wl
                       (H == 4 ? (hi & 0x7fu) : 0x40u);
   const uint32_t sl = ((lo << (3 + SH)) & 0xff000000u) | ((lo << (2 + SH)) & 0x007f0000u) | ((lo << (1 + SH)) & 0x00007f00u) |
                       (H == 4 ? (lo & 0x7fu) : 0x40u);
-  wh = __vsub4(sh, 0x40404040u);
-  wl = __vsub4(sl, 0x40404040u);
+  // per-byte u - 64 = u + 0xC0 (mod 256) without carries between the bytes, in three integer instructions (__vsub4 is
+  // emulated with ~10 on this architecture): add the low seven bits, then fix bit 7 (0xC0 has it set, so it flips unless
+  // the byte's own bit 7 is set, i.e. u = 128)
+  wh = ((sh & 0x7f7f7f7fu) + 0x40404040u) ^ (~sh & 0x80808080u);
+  wl = ((sl & 0x7f7f7f7fu) + 0x40404040u) ^ (~sl & 0x80808080u);
 }
 
 // Called by ALL lanes of the (converged) MMA warp: elect.sync picks the issuing lane, so the SASS is one predicated UTCIMMA

@@ -11,6 +11,10 @@
 namespace mogpe {
 namespace oz {
 
+__device__ __forceinline__ void ld_global_256(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
 // Bounds of the sliced operands that are known before the products run (S = tril(q_sqrt), V = mean vectors):
 //   cmax2[slot] = max_m |S[:, m]|_2^2,  rmax2[slot] = max_m |S[m, :]|_2^2   (per marginal-latent slot),
 //   vmax[v]     = max_m |V[v][m]|                                           (per mean vector),
@@ -152,32 +156,33 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
   const long long plane = (long long)Mp * Bp;
   const int8_t* Ag = A8 + (long long)g * NS * plane;
   const double asc = a_scale[g];
-  const bool live = n0 + c4 < N;  // N is not required to be a multiple of 4: columns >= N hold zero planes and zero adjoints
+  // Columns in [N, Bc) need no special case: their A / LTA planes are zero (zero Kuf^T rows) and the likelihood kernel wrote
+  // zero adjoints there, so every term below vanishes.
+  const int nn = n0 + c4;
 #pragma unroll 2
   for (int pass = 0; pass < 4; pass++) {
     const int ml = pass * 16 + r, m = m0 + ml;
-    double a[4] = {0.0, 0.0, 0.0, 0.0};
-    if (live) {
-      uint32_t w[NS];
+    uint32_t w[NS];
 #pragma unroll
-      for (int s = 0; s < NS; s++) w[s] = *reinterpret_cast<const uint32_t*>(Ag + s * plane + (long long)m * Bp + n0 + c4);
-      a[0] = unslice<NS, 0>(w) * asc;
-      a[1] = unslice<NS, 1>(w) * asc;
-      a[2] = unslice<NS, 2>(w) * asc;
-      a[3] = unslice<NS, 3>(w) * asc;
-    }
+    for (int s2 = 0; s2 < NS; s2++) w[s2] = *reinterpret_cast<const uint32_t*>(Ag + s2 * plane + (long long)m * Bp + nn);
+    double a[4];
+    a[0] = unslice<NS, 0>(w) * asc;
+    a[1] = unslice<NS, 1>(w) * asc;
+    a[2] = unslice<NS, 2>(w) * asc;
+    a[3] = unslice<NS, 3>(w) * asc;
     double ab[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) ab[j] = -2.0 * s_dv[c4 + j] * a[j];
     for (int q = vb; q < ve; q++) {
       const int v = md->gvec[q];
       const double vm = V[(long long)v * Mp + m];
+      double dm[4];
+      ld_global_256(dmean + (long long)v * Bp + nn, dm);
       double part = 0.0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const double dm = (n0 + c4 + j < N) ? dmean[(long long)v * Bp + n0 + c4 + j] : 0.0;
-        ab[j] += vm * dm;
-        part += a[j] * dm;
+        ab[j] += vm * dm[j];
+        part += a[j] * dm[j];
       }
       // the 16 threads of one tile row are 16 consecutive lanes
       part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -189,11 +194,11 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
     for (int q = lb; q < le; q++) {
       const int l = md->glat[q];
       if (!md->marg[l]) continue;
-      const double* p2 = P2 + ((long long)md->lta_slot[l] * Mp + m) * Bp + n0 + c4;
-      const double* dl = dfvar + (long long)l * Bp + n0 + c4;
+      double p2[4], dl[4];
+      ld_global_256(P2 + ((long long)md->lta_slot[l] * Mp + m) * Bp + nn, p2);
+      ld_global_256(dfvar + (long long)l * Bp + nn, dl);
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (n0 + c4 + j < N) ab[j] += 2.0 * dl[j] * p2[j];
+      for (int j = 0; j < 4; j++) ab[j] += 2.0 * dl[j] * p2[j];
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -231,10 +236,6 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
 
 namespace mogpe {
 namespace oz {
-
-__device__ __forceinline__ void ld_global_256(const double* p, double (&v)[4]) {
-  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
 
 // Kuf-bar (= W) consumer of the INT8 step, ONE pass over W [g][m][n]:
 //   (a) kernel-hyperparameter and Z gradients  E = W .* Kuf,  dZ[m,d] = -sum_n E (z_md - x_nd) / l_d^2,

@@ -103,15 +103,30 @@ _kDLCPU, _kDLCUDA, _kDLCUDAHost = 1, 2, 3
 class TensorView:
     """Borrowed view of a float64 tensor: pointer + shape + where it lives.  Keeps its owner alive."""
 
+    __slots__ = ("ptr", "shape", "on_device", "device_id", "_owner", "__weakref__")
+
     def __init__(self, ptr, shape, on_device, device_id, owner):
         self.ptr, self.shape, self.on_device, self.device_id, self._owner = ptr, tuple(shape), on_device, device_id, owner
 
 
+_USED_NAME = b"used_dltensor"  # module-level: PyCapsule_SetName keeps the pointer, not a copy
+_DELETER = C.CFUNCTYPE(None, C.c_void_p)
+
+
 def _from_dlpack_capsule(capsule, owner):
-    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
-    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
-    p = C.pythonapi.PyCapsule_GetPointer(capsule, b"dltensor")
-    t = C.cast(p, C.POINTER(_DLManagedTensor)).contents.dl_tensor
+    """Consume a DLPack capsule (the protocol of `__dlpack__`): read the DLManagedTensor, rename the capsule to
+    "used_dltensor" so that its own destructor no longer frees the tensor, and call the producer's deleter when the returned
+    view is garbage collected.  Zero-copy: the view points at the producer's memory."""
+    import weakref
+
+    api = C.pythonapi
+    api.PyCapsule_GetPointer.restype = C.c_void_p
+    api.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    api.PyCapsule_SetName.restype = C.c_int
+    api.PyCapsule_SetName.argtypes = [C.py_object, C.c_char_p]
+    p = api.PyCapsule_GetPointer(capsule, b"dltensor")
+    managed = C.cast(p, C.POINTER(_DLManagedTensor)).contents
+    t = managed.dl_tensor
     if not (t.dtype.code == 2 and t.dtype.bits == 64 and t.dtype.lanes == 1):
         raise TypeError("mogpe_b200 expects float64 tensors (the reference runs in float64)")
     shape = [t.shape[i] for i in range(t.ndim)]
@@ -124,8 +139,12 @@ def _from_dlpack_capsule(capsule, owner):
     on_dev = t.device.device_type == _kDLCUDA
     if not on_dev and t.device.device_type not in (_kDLCPU, _kDLCUDAHost):
         raise TypeError(f"unsupported DLPack device type {t.device.device_type}")
-    # the capsule (kept as owner) holds the producer's reference until it is garbage collected
-    return TensorView(t.data + t.byte_offset, shape, on_dev, t.device.device_id, (capsule, owner))
+    view = TensorView(t.data + t.byte_offset, shape, on_dev, t.device.device_id, (capsule, owner))
+    deleter = managed.deleter
+    api.PyCapsule_SetName(capsule, _USED_NAME)  # consumed: from here on WE release the tensor
+    if deleter:
+        weakref.finalize(view, _DELETER(deleter), p)
+    return view
 
 
 def as_view(x):

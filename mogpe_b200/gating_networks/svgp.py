@@ -32,12 +32,25 @@ class SVGPGatingNetwork(SVGPModel, GatingNetworkBase):
         return f_mean, f_var
 
     def predict_mixing_probs(self, Xnew, num_inducing_samples: Optional[int] = None, full_cov: Optional[bool] = False,
-                             eps_mc=None):
+                             eps_mc=None, eps_u=None, rng=None):
         """[N, K]: Bernoulli [p, 1 - p] analytic; Softmax Monte-Carlo (gating_networks/svgp.py:69-105)."""
         if num_inducing_samples is not None:
-            raise NotImplementedError("predict_mixing_probs(num_inducing_samples=...) is only used inside the tight "
-                                      "bound, which the engine evaluates internally")
+            # [S, N, K]: gating functions given inducing samples (CUDA), likelihood expectation per sample
+            h_mean, h_var = self.predict_f(Xnew, num_inducing_samples, full_cov=full_cov, eps_u=eps_u)
+            return self.predict_mixing_probs_given_h(h_mean, np.broadcast_to(h_var, h_mean.shape), eps_mc=eps_mc, rng=rng)
         return self._require_model()._predict_mixing_probs(Xnew, eps_mc)
 
-    def predict_mixing_probs_given_h(self, h_mean, h_var=None):
-        raise NotImplementedError("evaluated inside the fused likelihood kernel; use predict_mixing_probs / the bounds")
+    def predict_mixing_probs_given_h(self, h_mean, h_var=None, eps_mc=None, rng=None):
+        """gating_networks/svgp.py:85-105: Pr(alpha = k | h) (h_var None) or its expectation under N(h_mean, h_var); K = 2
+        returns [p, 1 - p].  Elementwise on values the caller holds, so it runs on the host (the bounds evaluate the same maps
+        inside the fused likelihood kernel)."""
+        lik = self.likelihood
+        if h_var is None:
+            p = lik.conditional_mean(h_mean)
+        elif isinstance(lik, Softmax):
+            p = lik.predict_mean_and_var(h_mean, h_var, eps=eps_mc, rng=rng)[0]
+        else:
+            p = lik.predict_mean_and_var(h_mean, h_var)[0]
+        if self.num_gating_functions == 1:
+            p = np.concatenate([p, 1.0 - p], -1)
+        return p

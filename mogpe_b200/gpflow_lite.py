@@ -274,11 +274,32 @@ class Gaussian(Likelihood):
         self.name = name
 
 
+def inv_probit(x):
+    """gpflow.likelihoods.utils.inv_probit: 0.5 (1 + erf(x / sqrt 2)) (1 - 2e-3) + 1e-3."""
+    from math import sqrt
+
+    try:
+        from scipy.special import erf
+    except ImportError:  # pragma: no cover
+        erf = np.vectorize(math.erf)
+    return 0.5 * (1.0 + erf(np.asarray(x, dtype=DEFAULT_FLOAT) / sqrt(2.0))) * (1.0 - 2e-3) + 1e-3
+
+
 class Bernoulli(Likelihood):
-    """Probit link with gpflow's 1e-3 jitter."""
+    """Probit link with gpflow's 1e-3 jitter.  The two maps below act elementwise on gating-function
+    values the caller already holds on the host (predict_mixing_probs_given_h); everything that starts from inputs X runs
+    in the CUDA library."""
 
     def __init__(self, name=None):
         self.name = name
+
+    def conditional_mean(self, F):
+        return inv_probit(F)
+
+    def predict_mean_and_var(self, Fmu, Fvar):
+        """gpflow Bernoulli.predict_mean_and_var (probit link, analytic): p = inv_probit(mu / sqrt(1 + var)), p - p^2."""
+        p = inv_probit(np.asarray(Fmu, dtype=DEFAULT_FLOAT) / np.sqrt(1.0 + np.asarray(Fvar, dtype=DEFAULT_FLOAT)))
+        return p, p - p * p
 
 
 class Softmax(Likelihood):
@@ -286,6 +307,22 @@ class Softmax(Likelihood):
         self.num_classes = int(num_classes)
         self.num_monte_carlo_points = 100  # gpflow MonteCarloLikelihood default
         self.name = name
+
+    def conditional_mean(self, F):
+        F = np.asarray(F, dtype=DEFAULT_FLOAT)
+        e = np.exp(F - F.max(-1, keepdims=True))
+        return e / e.sum(-1, keepdims=True)
+
+    def predict_mean_and_var(self, Fmu, Fvar, eps=None, rng=None):
+        """gpflow MonteCarloLikelihood.predict_mean_and_var: mean (and variance) of softmax(mu + sqrt(var) eps) over
+        num_monte_carlo_points standard-normal draws; eps [R, ..., K] makes it deterministic (the reference draws from the
+        global TF RNG)."""
+        Fmu, Fvar = np.asarray(Fmu, dtype=DEFAULT_FLOAT), np.asarray(Fvar, dtype=DEFAULT_FLOAT)
+        if eps is None:
+            eps = (rng or np.random.default_rng()).standard_normal((self.num_monte_carlo_points,) + Fmu.shape)
+        p = self.conditional_mean(Fmu[None] + np.sqrt(Fvar)[None] * np.asarray(eps, dtype=DEFAULT_FLOAT))
+        mean = p.mean(0)
+        return mean, (p * p).mean(0) - mean * mean
 
 
 # ---- mean functions ---------------------------------------------------------------------------------------

@@ -84,11 +84,12 @@ class SVGPGatingNetwork(GatingNetworkBase):
         return h_mean, h_var
 
     def predict_mixing_probs(self, Xnew, num_inducing_samples: Optional[int] = None, full_cov: Optional[bool] = False,
-                             eps_mc=None):
+                             eps_mc=None, eps_u=None, rng=None):
         """Pr(alpha = k | Xnew) [N, K] (gating_networks.py:173-186): Bernoulli analytic, Softmax Monte-Carlo."""
         if num_inducing_samples:
-            raise NotImplementedError("predict_mixing_probs(num_inducing_samples=...) is only used inside the tight "
-                                      "bound, which the engine evaluates internally")
+            # [S, N, K]: gating functions given inducing samples (CUDA), likelihood expectation per sample (gating_networks.py:173-186)
+            h_mean, h_var = self.predict_h(Xnew, num_inducing_samples=num_inducing_samples, eps_u=eps_u)
+            return self.predict_mixing_probs_given_h(h_mean, np.broadcast_to(h_var, h_mean.shape), eps_mc=eps_mc, rng=rng)
         return self._require_model()._predict_mixing_probs(Xnew, eps_mc)
 
     def predict_categorical_dist(self, Xnew, **kw):
@@ -106,11 +107,30 @@ class SVGPGatingNetwork(GatingNetworkBase):
             h = np.concatenate([h, -h], -1)
         return h
 
-    def predict_mixing_probs_given_h(self, h_mean, h_var=None):
-        raise NotImplementedError("evaluated inside the fused likelihood kernel; use predict_mixing_probs / the bounds")
+    def predict_mixing_probs_given_h(self, h_mean, h_var=None, eps_mc=None, rng=None):
+        """gating_networks.py:228-249: Pr(alpha = k | h = h_mean), or its expectation under N(h_mean, h_var) when h_var is
+        given (Bernoulli: analytic probit; Softmax: gpflow's Monte-Carlo mean, eps_mc [R, ..., K] for explicit draws).
+        Elementwise on gating-function values the caller holds (for K = 2 they are the [h, -h] pairs of predict_h), so it
+        runs on the host; the bounds evaluate the same maps inside the fused likelihood kernel."""
+        lik = self.gp.likelihood
+        if h_var is None:
+            return lik.conditional_mean(h_mean)
+        if isinstance(lik, Softmax):
+            return lik.predict_mean_and_var(h_mean, h_var, eps=eps_mc, rng=rng)[0]
+        return lik.predict_mean_and_var(h_mean, h_var)[0]
 
-    def predict_categorical_dist_given_h_samples(self, Xnew, num_h_samples: Optional[int] = 1):
-        raise NotImplementedError("evaluated inside the fused likelihood kernel; use the model's bounds")
+    def predict_categorical_dist_given_h_samples(self, Xnew, num_h_samples: Optional[int] = 1, eps_h=None, rng=None):
+        """gating_networks.py:145-157: Categorical over the expert indicator for every gating-function sample, batch shape
+        [S, N] (the posterior h comes from the CUDA predict path, the samples and the link are elementwise)."""
+        h = self.predict_h_samples(Xnew, num_samples=num_h_samples, eps_h=eps_h, rng=rng)
+        return Categorical(self.predict_mixing_probs_given_h(h))
+
+    def predict_categorical_dist_given_inducing_samples(self, Xnew, num_inducing_samples: Optional[int] = 1, eps_u=None,
+                                                        eps_mc=None, rng=None):
+        """gating_networks.py:159-171: h given inducing samples (CUDA: mogpe_predict_f_inducing_samples), then the likelihood
+        expectation."""
+        h_mean, h_var = self.predict_h(Xnew, num_inducing_samples=num_inducing_samples, eps_u=eps_u)
+        return Categorical(self.predict_mixing_probs_given_h(h_mean, np.broadcast_to(h_var, h_mean.shape), eps_mc=eps_mc, rng=rng))
 
     def prior_kl(self):
         return self._require_model()._prior_kl(self)

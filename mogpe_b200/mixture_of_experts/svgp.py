@@ -126,7 +126,18 @@ class MixtureOfSVGPExperts(MixtureOfExperts):
     def predict_y(self, Xnew, eps_mc=None, **kwargs) -> MixtureDistribution:
         """MixtureSameFamily(Categorical(probs), Normal(mus, sqrt(vars))) (base.py:90-115)."""
         if kwargs.get("num_inducing_samples") is not None:
-            raise NotImplementedError("predict_y(num_inducing_samples=...) is not on the accelerated path")
+            # base.py:90-115 with kwargs forwarded to the gating network and the experts: everything gets a leading sample
+            # axis.  The conditionals given inducing samples run in the CUDA library (mogpe_predict_f_inducing_samples); the
+            # mixture moments are an elementwise O(S N F K) combination of the returned arrays.
+            S = int(kwargs["num_inducing_samples"])
+            probs = self.gating_network.predict_mixing_probs(Xnew, num_inducing_samples=S, eps_mc=eps_mc, eps_u=kwargs.get("eps_u"),
+                                                             rng=kwargs.get("rng"))                      # [S, N, K]
+            mus, vs = self.experts.predict_ys(Xnew, num_inducing_samples=S)                               # [S, N, F, K] / [.., N, F, K]
+            vs = np.broadcast_to(vs, mus.shape)
+            w = probs[..., None, :]
+            mean = (w * mus).sum(-1)
+            var = (w * (vs + mus * mus)).sum(-1) - mean * mean
+            return MixtureDistribution(probs, mus, np.sqrt(vs), mean, var)
         out = self._core.predict(Xnew, ("f_mean", "f_var", "mix_probs", "y_mean", "y_var"), eps_mc=eps_mc)
         sl = self._core.latent_slices()
         mus = np.stack([out["f_mean"][:, s] for s in sl[:-1]], -1)

@@ -60,7 +60,16 @@ def parse_likelihood(likelihood_cfg, output_dim):
     if likelihood_cfg is None or likelihood_cfg.get("name") != "gaussian":
         raise NotImplementedError("This likelihood cannot be instantiated using toml config")
     var = _get(likelihood_cfg, "params.variance", None, "No variance found for Gaussian likelihood")
-    return gl.Gaussian() if var is None else gl.Gaussian(variance=float(var))
+    if var is None:
+        return gl.Gaussian()
+    # the reference wraps the TOML value in a list (parse_variance, model_parsers.py:30-35): a scalar becomes a [1] variable,
+    # a per-output list such as `variance = [0.0011, 0.0011]` (examples/quadcopter/configs/*.toml) a [1, output_dim] one
+    v = np.asarray(var, dtype=np.float64)
+    if v.ndim == 0:
+        return gl.Gaussian(variance=float(v))
+    if v.size not in (1, output_dim):
+        raise ValueError(f"likelihood.params.variance has {v.size} entries for {output_dim} outputs")
+    return gl.Gaussian(variance=v.reshape(1, -1))
 
 
 def parse_mean_function(svgp_cfg):

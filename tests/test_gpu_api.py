@@ -322,3 +322,103 @@ def test_optimizer_state_survives_a_workspace_rebuild():
     # it would hold only 2 of them; compare magnitudes block-wise against the uninterrupted run (different draws: loose)
     ratio = np.sum(hb_v) / np.sum(ha_v)
     assert 0.6 < ratio < 1.6, ratio
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+@pytest.mark.parametrize("K", [2, 3])
+def test_gating_methods_given_h_and_inducing_samples(flavour, K):
+    """The gating-network methods of SURVEY 8b that take gating-function values (predict_mixing_probs_given_h,
+    predict_categorical_dist_given_h_samples, predict_mixing_probs(num_inducing_samples=...)) and
+    predict_y(num_inducing_samples=...) of the legacy flavour: consistent with the device-computed mixing probabilities
+    and with the oracle's conditional given inducing samples."""
+    from oracle import ref_numpy as rn
+    from tests._model_helpers import model_from_spec
+
+    N, S = 50, 3
+    spec, X, Y, eps = make_spec(seed=70 + K, N=N, D=2, F=1, K=K, M=11, S=S, flavour=flavour)
+    model = model_from_spec(spec)
+    gn = model.gating_network
+    G = 1 if K == 2 else K
+    rng = np.random.default_rng(5)
+    eps_mc = rng.standard_normal((19, N, K)) if K > 2 else None
+    pi = model.predict_mixing_probs(X, eps_mc=eps_mc) if hasattr(model, "predict_mixing_probs") else gn.predict_mixing_probs(X, eps_mc=eps_mc)
+    # (1) analytic / Monte-Carlo expectation from the posterior moments equals the device result
+    if flavour == "keras":
+        h_mean, h_var = gn.predict_h(X)
+    else:
+        h_mean, h_var = gn.predict_f(X)
+    emc = None
+    if K > 2:
+        emc = eps_mc
+    got = gn.predict_mixing_probs_given_h(h_mean, h_var, eps_mc=emc)
+    np.testing.assert_allclose(got, pi, rtol=1e-9, atol=1e-12)
+    # (2) no variance: the link itself; rows sum to one
+    p0 = gn.predict_mixing_probs_given_h(h_mean)
+    assert p0.shape == (N, K)
+    np.testing.assert_allclose(p0.sum(-1), 1.0, rtol=1e-12)
+    # (3) given inducing samples: [S, N, K], against the oracle's conditional given the same u-samples
+    eps_u = rng.standard_normal((S, G, 11))
+    ps = gn.predict_mixing_probs(X, num_inducing_samples=S, eps_u=eps_u, eps_mc=None if K == 2 else rng.standard_normal((23, S, N, K)))
+    assert ps.shape == (S, N, K)
+    np.testing.assert_allclose(ps.sum(-1), 1.0, rtol=1e-9)
+    fm, fv = rn.predict_f_given_inducing_samples(spec["gating"], X, eps_u)
+    if K == 2:
+        lik = gn.gp.likelihood if flavour == "keras" else gn.likelihood
+        want = lik.predict_mean_and_var(fm, np.broadcast_to(fv, fm.shape))[0]
+        np.testing.assert_allclose(ps[..., :1], want, rtol=1e-8)
+    if flavour == "keras":
+        cat = gn.predict_categorical_dist_given_h_samples(X, num_h_samples=4, rng=np.random.default_rng(2))
+        assert cat.probs.shape == (4, N, K)
+        np.testing.assert_allclose(cat.probs.sum(-1), 1.0, rtol=1e-12)
+    else:
+        dist = model.predict_y(X, num_inducing_samples=S, eps_u=eps_u, eps_mc=None if K == 2 else rng.standard_normal((23, S, N, K)))
+        assert dist.mean().shape == (S, N, 1) and np.all(dist.variance() > 0)
+
+
+def test_dlpack_only_producer_is_consumed_zero_copy():
+    """north_star: "DLPack zero-copy from TF tensors".  An object that exposes ONLY __dlpack__ (no __cuda_array_interface__,
+    no .numpy) goes through the capsule path: same device pointer (zero copy), the capsule is renamed "used_dltensor" as the
+    protocol requires, the producer's deleter runs exactly once when the view is dropped, and the ELBO computed from such
+    inputs equals the one from host arrays."""
+    import ctypes as C
+    import gc
+
+    import torch
+
+    from mogpe_b200 import device as dev
+    from tests._engine_helpers import engine_from_spec, run_engine_elbo
+
+    class OnlyDLPack:
+        def __init__(self, t):
+            self.t = t
+            self.capsules = []
+
+        def __dlpack__(self, stream=None):
+            cap = self.t.__dlpack__()
+            self.capsules.append(cap)
+            return cap
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    t = torch.arange(12, dtype=torch.float64, device="cuda").reshape(3, 4)
+    w = OnlyDLPack(t)
+    assert not hasattr(w, "__cuda_array_interface__") and not hasattr(w, "numpy")
+    v = dev.as_view(w)
+    assert v.on_device and v.ptr == t.data_ptr() and v.shape == (3, 4)
+    C.pythonapi.PyCapsule_GetName.restype = C.c_char_p
+    C.pythonapi.PyCapsule_GetName.argtypes = [C.py_object]
+    assert C.pythonapi.PyCapsule_GetName(w.capsules[0]) == b"used_dltensor"
+    del v
+    gc.collect()  # the deleter has run: torch's tensor is still alive (it holds its own reference) and intact
+    assert torch.equal(t.cpu(), torch.arange(12, dtype=torch.float64).reshape(3, 4))
+    with pytest.raises(TypeError):
+        dev.as_view(OnlyDLPack(torch.zeros(3, device="cuda", dtype=torch.float32)))
+    # end to end: the hot path on DLPack-only inputs
+    spec, X, Y, eps = make_spec(seed=97, N=40, D=2, F=1, K=2, M=6, S=1, num_data=400)
+    eng = engine_from_spec(spec, max_batch=40)
+    ref = run_engine_elbo(eng, spec, X, Y, eps, want_grads=False)
+    eps_u = eng.pack_eps_u(eps["u_experts"], None, 1)
+    d = lambda a: OnlyDLPack(torch.as_tensor(np.ascontiguousarray(a), device="cuda"))
+    got = eng.elbo(d(X), d(Y), "further_gating", 1, 400 / 40, d(eps_u), d(eps["h"]), None, want_grads=False)
+    assert got.elbo == pytest.approx(ref.elbo, rel=1e-13)

@@ -210,3 +210,68 @@ def test_ctypes_prototypes_have_the_header_arity():
         n = 0 if args in ("", "void") else args.count(",") + 1
         restype, argtypes = _lib._PROTOS[name]
         assert len(argtypes) == n, (name, n, len(argtypes))
+
+
+def test_gating_likelihood_maps_closed_forms():
+    """Host-side link functions behind predict_mixing_probs_given_h (gpflow Bernoulli / Softmax)."""
+    from math import erf, sqrt
+
+    from mogpe_b200 import gpflow_lite as gl
+
+    b = gl.Bernoulli()
+    assert b.conditional_mean(0.0) == pytest.approx(0.5, abs=1e-15)
+    h = np.array([-30.0, -1.3, 0.2, 30.0])
+    want = np.array([0.5 * (1 + erf(x / sqrt(2))) * (1 - 2e-3) + 1e-3 for x in h])
+    np.testing.assert_allclose(b.conditional_mean(h), want, rtol=1e-14)
+    assert b.conditional_mean(h).min() >= 1e-3 and b.conditional_mean(h).max() <= 1 - 1e-3
+    np.testing.assert_allclose(b.conditional_mean(h) + b.conditional_mean(-h), 1.0, rtol=1e-14)  # [h, -h] pairs sum to one
+    mu, var = np.array([0.7, -0.4]), np.array([2.0, 0.0])
+    p, v = b.predict_mean_and_var(mu, var)
+    np.testing.assert_allclose(p, b.conditional_mean(mu / np.sqrt(1 + var)), rtol=1e-15)
+    np.testing.assert_allclose(v, p - p * p, rtol=1e-15)
+    s = gl.Softmax(3)
+    F = np.random.default_rng(0).standard_normal((5, 3)) * 4
+    pm = s.conditional_mean(F)
+    np.testing.assert_allclose(pm.sum(-1), 1.0, rtol=1e-15)
+    np.testing.assert_allclose(pm, np.exp(F) / np.exp(F).sum(-1, keepdims=True), rtol=1e-13)
+    eps = np.random.default_rng(1).standard_normal((7, 5, 3))
+    m, v = s.predict_mean_and_var(F, np.full((5, 3), 0.3), eps=eps)
+    ref = np.stack([s.conditional_mean(F + np.sqrt(0.3) * e) for e in eps])
+    np.testing.assert_allclose(m, ref.mean(0), rtol=1e-14)
+    np.testing.assert_allclose(v, ref.var(0), rtol=1e-10, atol=1e-15)
+    np.testing.assert_allclose(s.predict_mean_and_var(F, np.zeros((5, 3)), eps=eps)[0], pm, rtol=1e-14)  # zero variance
+
+
+def test_dlpack_capsule_is_consumed_per_protocol_on_the_host():
+    """device.as_view on a producer that exposes only __dlpack__ (here: numpy's CPU capsule): zero-copy pointer, capsule
+    renamed to "used_dltensor", producer's deleter called once when the view dies (numpy then drops its reference)."""
+    import ctypes as C
+    import gc
+    import sys
+
+    from mogpe_b200 import device as dev
+
+    class OnlyDLPack:
+        def __init__(self, a):
+            self.a, self.capsules = a, []
+
+        def __dlpack__(self, stream=None):
+            self.capsules.append(self.a.__dlpack__())
+            return self.capsules[-1]
+
+    a = np.arange(6, dtype=np.float64).reshape(2, 3)
+    base_refs = sys.getrefcount(a)
+    w = OnlyDLPack(a)
+    v = dev.as_view(w)
+    assert not v.on_device and v.ptr == a.ctypes.data and v.shape == (2, 3)
+    C.pythonapi.PyCapsule_GetName.restype = C.c_char_p
+    C.pythonapi.PyCapsule_GetName.argtypes = [C.py_object]
+    assert C.pythonapi.PyCapsule_GetName(w.capsules[0]) == b"used_dltensor"
+    assert sys.getrefcount(a) > base_refs  # the managed tensor holds the array
+    del v
+    gc.collect()
+    assert sys.getrefcount(a) <= base_refs + 1  # ... and released it through the deleter (w.a is the +1)
+    with pytest.raises(TypeError, match="float64"):
+        dev.as_view(OnlyDLPack(np.zeros(3, dtype=np.float32)))
+    with pytest.raises(ValueError, match="contiguous"):
+        dev.as_view(OnlyDLPack(np.zeros((4, 4))[:, ::2]))
