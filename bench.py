@@ -50,6 +50,18 @@ def fp64_tensor_peak(device):
     return float(v.value)
 
 
+def int8_tensor_peak(device):
+    """INT8 tensor-pipe issue peak (TOP/s) measured NOW by the library's probe: back-to-back tcgen05.mma.kind::i8 128x256x32
+    from shared-memory operands, one issuing warp per SM."""
+    import ctypes as C
+
+    from mogpe_b200 import _lib
+
+    v = C.c_double()
+    _lib.check(_lib.load().mogpe_probe_int8_tensor_peak(device, C.byref(v)))
+    return float(v.value)
+
+
 def measured_traffic(kernel_key):
     """dram read+write bytes per launch of the dominant kernel from the committed `ncu --set full` summary of this round
     (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when no capture is committed."""
@@ -354,7 +366,9 @@ def main():
            "batch_per_gpu": B, "global_batch": B * n_arm, "M": wl["M"], "K": K, "D": wl["D"],
            "l2": "per-step working set (A, Kuf, W, ... = 4*Q*M*B*8 B) is far larger than the 126 MB L2 for C2-C4; "
                  "minibatches cycle through a 4-batch pool",
-           "parallelism": f"dp{n_arm}: minibatch rows sharded, params replicated, one NCCL all-reduce of grads"}
+           "parallelism": f"dp{n_arm}: minibatch rows sharded, params replicated, one NCCL all-reduce of grads",
+           "arithmetic": "float64 results (1e-8 / 1e-6 parity); for M >= 512 the dense products run as exact integer-sliced "
+                         "INT8 tensor-core products (8 byte slices), FP64 DMMA otherwise"}
     spec = synth_model(wl)
 
     if args.impl == "reference":
@@ -439,12 +453,14 @@ def main():
     barrier()
     ms_prof = p0.elapsed_time(p1)
     prof = eng.profile_read()
+    prof8 = eng.profile_read_int8()
     stream_prof = eng.profile_read_streaming()
     eng.profile(False)
     clocks = sampler.stop() if sampler else None
     elbo_val = eng.gbuf.numpy(offset=eng.lo.total, count=4)
     dp_parity = dp_parity_check(eng, wl, B, rank, world, pool, scale, local_rank) if world > 1 else None
     fp64_peak = fp64_tensor_peak(local_rank) if rank == 0 else None
+    i8_peak = int8_tensor_peak(local_rank) if rank == 0 else None
 
     # End to end through the public API a user of the reference calls: MixtureOfSVGPExperts.fit (Keras flavour).
     # Every step copies its minibatch host -> device (staged through pinned memory inside the library), runs ELBO forward +
@@ -483,7 +499,52 @@ def main():
     pts = float(B * world * steps)
     value = pts / (ms * 1e-3)
     gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) * 1e-12 if prof["gemm_ms"] > 0 else None
-    traffic, traffic_note = measured_traffic("gemm_dmma_A")
+    i8_on = prof8["ms"] > 0
+    # INT8-sliced products: every FP64-equivalent multiply-add is 36 signed-byte slice-pair multiply-adds (8 x 8 slices, the
+    # pairs with i + j < 8), so the tensor pipe executes 36 operations per algorithmic FLOP
+    i8_eq_tflops = prof8["flops"] / (prof8["ms"] * 1e-3) * 1e-12 if i8_on else None
+    i8_tops = 36.0 * i8_eq_tflops if i8_on else None
+    dmma = {"kernel": "mogpe::gemm_dmma_kernel (FP64 DMMA: the M^3 products of the Cholesky backward; every dense product when "
+                      "the INT8 step does not apply)",
+            "achieved": gemm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": None if gemm_tflops is None else gemm_tflops / fp64_peak,
+            "ms_per_step": prof["gemm_ms"] / steps, "launches_per_step": prof["gemm_launches"] / steps - (prof8["launches"] / steps if i8_on else 0)}
+    if i8_on:
+        traffic, traffic_note = measured_traffic("gemm_i8_A")
+        roof = {
+            "bound": "tensor", "kernel": "mogpe::oz::gemm_i8_sliced_kernel<8> (tcgen05.mma kind::i8 + TMA + TMEM; the six dense "
+                                         "products of a step: A = L^-1 Kuf, S^T A, S S^T A, W = L^-T Abar, Lbar, Sbar)",
+            "achieved": i8_tops, "peak": i8_peak, "unit": "TOP/s", "frac": i8_tops / i8_peak,
+            "peak_source": "INT8 tensor-pipe issue peak measured in THIS run by mogpe_probe_int8_tensor_peak (back-to-back "
+                           "tcgen05.mma.kind::i8 128x256x32 from shared-memory operands on every SM; nominal dense INT8: 4500); "
+                           "MEASURED_PEAKS.json holds only HBM and bf16 figures",
+            "achieved_note": "36 INT8 slice-pair operations per algorithmic FP64 FLOP (triangular operands / results counted as "
+                             "triangular) / device time of the launches (CUDA events around every launch, profiled pass)",
+            "fp64_equivalent_tflops": i8_eq_tflops,
+            "fp64_equivalent_vs_fp64_tensor_peak": i8_eq_tflops / fp64_peak,
+            "kernel_ms_per_step": prof8["ms"] / steps, "kernel_share_of_step": prof8["ms"] / ms_prof,
+            "kernel_launches_per_step": prof8["launches"] / steps,
+            "profiled_pass_ms_per_step": ms_prof / steps,
+            "step_model_tflops": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12,
+            "step_model_vs_fp64_tensor_peak": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12 / fp64_peak,
+            "what_bounds_it": "per 64-wide k-block a CTA ingests 96 KB of operand planes by TMA and the MMAs read 208 KB from "
+                              "shared memory for 2438 tensor cycles: the main loop sits at the shared-memory / L2->SM bandwidth "
+                              "(DESIGN.md section 4c); short triangular tiles (K <= 512) add the TMEM drain per tile",
+            "traffic": traffic, "traffic_note": traffic_note,
+            "fp64_dmma": dmma, "fp64_tensor_peak_tflops": fp64_peak,
+        }
+    else:
+        traffic, traffic_note = measured_traffic("gemm_dmma_A")
+        roof = dict(dmma)
+        roof.update({
+            "bound": "tensor",
+            "peak_source": "FP64 tensor (DMMA) issue peak measured in THIS run by mogpe_probe_fp64_tensor_peak (independent "
+                           f"mma.sync.m8n8k4.f64 chains on every SM; round-1 value {FP64_TENSOR_PEAK_FALLBACK}, cuBLAS DGEMM "
+                           "35.4); MEASURED_PEAKS.json holds only HBM and bf16 figures",
+            "gemm_ms_per_step": prof["gemm_ms"] / steps, "gemm_share_of_step": prof["gemm_ms"] / ms_prof,
+            "profiled_pass_ms_per_step": ms_prof / steps,
+            "step_model_tflops": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12,
+            "traffic": traffic, "traffic_note": traffic_note})
     line = {
         "metric": "elbo_fwd_bwd_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "steps_per_sec": steps / (ms * 1e-3),
@@ -495,22 +556,7 @@ def main():
                        "minibatch, ELBO fwd+bwd, [NCCL all-reduce], device-side Adam, D2H of the result",
                 "final_loss": float(hist["loss"][-1])},
         "gpu_launches": int(launches_timed),
-        "roofline": {
-            "bound": "tensor", "kernel": "mogpe::gemm_dmma_kernel (all instances: A=Linv*Kuf, S^T*A, Linv^T*Abar, W*A^T, ...)",
-            "achieved": gemm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": None if gemm_tflops is None else gemm_tflops / fp64_peak,
-            "peak_source": "FP64 tensor (DMMA) issue peak measured in THIS run by mogpe_probe_fp64_tensor_peak (independent "
-                           f"mma.sync.m8n8k4.f64 chains on every SM; round-1 value {FP64_TENSOR_PEAK_FALLBACK}, cuBLAS DGEMM "
-                           "35.4); MEASURED_PEAKS.json holds only HBM and bf16 figures",
-            "gemm_ms_per_step": prof["gemm_ms"] / steps, "gemm_share_of_step": prof["gemm_ms"] / ms_prof,
-            "profiled_pass_ms_per_step": ms_prof / steps,
-            "gemm_launches_per_step": prof["gemm_launches"] / steps,
-            "step_model_tflops": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12,
-            "note": "DMMA launches only: for M >= 512 the two minibatch-reduced [M x M] products of the backward (Lbar, Sbar) run on "
-                    "the INT8 tensor cores (integer-sliced operands, exact accumulation: gemm_i8_sliced_kernel) and are not part of "
-                    "`achieved`; step_model_tflops counts the whole step's algorithmic FLOPs (SURVEY 8d) against the step time",
-            "traffic": traffic, "traffic_note": traffic_note,
-        },
+        "roofline": roof,
         "elbo_last_step": float(elbo_val[0]),
     }
     if dp_parity is not None:

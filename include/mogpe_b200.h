@@ -294,6 +294,10 @@ mogpe_status mogpe_profile_read_streaming(mogpe_handle* h, double* ms, double* b
 /* Roofline denominator measured on the spot: issue rate of the FP64 tensor pipe (independent mma.sync.m8n8k4.f64 chains,
  * SASS DMMA.8x8x4, 2 x 256 threads per SM, ~5 ms), in TFLOP/s.  MEASURED_PEAKS.json holds no FP64 figure. */
 mogpe_status mogpe_probe_fp64_tensor_peak(int32_t device, double* tflops);
+/* The same for the INT8 tensor pipe (tcgen05.mma kind::i8, 128 x 256 x 32 from shared-memory operands, one issuing warp per
+ * SM), in TOP/s (2 operations per multiply-accumulate): the denominator for gemm_i8_sliced_kernel, whose 36 slice-pair
+ * products per FP64-equivalent multiply-add run on this pipe. */
+mogpe_status mogpe_probe_int8_tensor_peak(int32_t device, double* tops);
 
 /* Test hook: copy a named intermediate of the last call to the host (Kuu, L, Linv, Kuf, A, ...).
  * Returns the element count in *n_out; copies min(capacity, count) doubles. */

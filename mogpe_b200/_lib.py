@@ -89,6 +89,7 @@ _PROTOS = {
     "mogpe_memset_zero": (C.c_int, [C.c_int32, _P, C.c_int64, _P]),
     "mogpe_stream_sync": (C.c_int, [C.c_int32, _P]),
     "mogpe_probe_fp64_tensor_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
+    "mogpe_probe_int8_tensor_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "mogpe_debug_copy": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "mogpe_debug_gemm": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _P]),

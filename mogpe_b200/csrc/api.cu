@@ -166,6 +166,8 @@ struct mogpe_handle {
   size_t sk_used[NSK] = {0, 0, 0, 0};
   double sk_bytes[NSK] = {0, 0, 0, 0};
   int* d_fail = nullptr;  // 0 = ok, g + 1 = Cholesky of group g failed
+  unsigned* d_chain_sync = nullptr;  // [MAXQ] step counters of the single-launch factorisation
+  int chain_capacity = -1;           // co-resident CTAs of chol_inv_chain_kernel on this device (-1: not queried yet)
   size_t lik_smem_set = 0;  // dynamic shared memory opted in for lik_kernel on this handle's device
   // device-side optimiser
   int* var_rep = nullptr;
@@ -225,6 +227,7 @@ static void free_ws(mogpe_handle* h) {
   if (h->d_round_group) cudaFree(h->d_round_group);
   if (h->var_rep) cudaFree(h->var_rep);
   if (h->d_fail) cudaFree(h->d_fail);
+  if (h->d_chain_sync) cudaFree(h->d_chain_sync);
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   h->graphs.clear();
@@ -405,6 +408,9 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (e == cudaSuccess) e = cudaMemset(h->varq, 0, (size_t)P * h->Bp * sizeof(double));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(chol_inv_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(chol_inv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM_BYTES);
+  if (e == cudaSuccess) e = dalloc(&h->d_chain_sync, (size_t)MAXQ);
   if (e == cudaSuccess && 8 * Mp * sizeof(double) > 48 * 1024)
     e = cudaFuncSetAttribute(a_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * Mp * sizeof(double)));
   if (e != cudaSuccess) {
@@ -631,11 +637,11 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, const doubl
   const ModelDev& md = h->md_host;
   const int Q = md.Q, P = md.P, Mp = h->Mp;
   H_CUDA(h, side_fork(h, st));
+  kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
   prep_qsqrt_kernel<<<dim3(Mp / 16, Mp / 16, P), dim3(16, 16), 0, h->side>>>(h->d_md, params, h->lo, h->Sc);
   make_V_kernel<<<dim3(Mp / 8, md.NV), 256, 0, h->side>>>(h->d_md, params, h->lo, h->Sc, eps_u, S, h->V);
   if (side_extra) side_extra(h->side);  // more work that needs q_sqrt / V but not the factorisation
   if (fp64_products && !h->prof) launch_kuf(h, params, X, N, Bc, h->side);
-  kuu_kernel<<<dim3(Mp / 16, Mp / 16, Q), dim3(16, 16), 0, st>>>(h->d_md, params, h->lo, h->desc.jitter, h->Kuu);
   // Launch j of the chain completes block row j of L^-1.  A = L^-1 Kuf only needs rows [64 i, 64 i + 64) of L^-1 for
   // its row block i, so the A-GEMM is issued in 64-row slices on the side stream, each waiting for the chain launch
   // that completes its rows: the DMMA work fills the SMs that the latency-bound chain leaves idle.
@@ -645,7 +651,25 @@ static mogpe_status factorise(mogpe_handle* h, const double* params, const doubl
     H_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->ev_rows.push_back(e);
   }
-  const bool pipeline = !h->prof && fp64_products;  // per-GEMM event timing needs the GEMMs alone on the device
+  const bool pipeline = !h->prof && fp64_products && Mp > 256;  // per-GEMM event timing needs the GEMMs alone on the device
+  // The whole chain in ONE launch when nothing is interleaved with its steps and every CTA of the grid can be resident at
+  // once (the CTAs of a group synchronise through a counter in global memory between steps).
+  if (h->chain_capacity < 0) {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_inv_chain_kernel, 256, CHOL_SMEM_BYTES);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    h->chain_capacity = getenv("MOGPE_CHAIN_STEPS") ? 0 : per_sm * sms;
+  }
+  if (!pipeline && (Mp / 32) * Q <= h->chain_capacity) {
+    H_CUDA(h, cudaMemsetAsync(h->d_chain_sync, 0, sizeof(unsigned) * MAXQ, st));
+    chol_inv_chain_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, h->d_fail, h->d_chain_sync);
+    h->a_done_in_factorise = false;
+    KCOUNT(h, 4);
+    H_CUDA(h, cudaGetLastError());
+    H_CUDA(h, side_join(h, st));
+    if (fp64_products && h->prof) launch_kuf(h, params, X, N, Bc, st);  // timed alone on the caller's stream
+    return MOGPE_OK;
+  }
   for (int j = -1; j < Mp / 32; j++) {
     chol_inv_step_kernel<<<dim3(Mp / 32, Q), 256, CHOL_SMEM_BYTES, st>>>(h->Kuu, h->L, h->Linv, Mp, j, h->d_fail);
     if (pipeline && j >= 0 && (j & 1)) {
@@ -1949,6 +1973,13 @@ extern "C" mogpe_status mogpe_check_numerics(mogpe_handle* h, void* cuda_stream)
   int flag = 0;
   H_CUDA(h, cudaMemcpyAsync(&flag, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
   H_CUDA(h, cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  if (flag >= 1000) {
+    H_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), (cudaStream_t)cuda_stream));
+    h->chain_capacity = 0;  // use per-step launches from now on
+    H_FAIL(h, MOGPE_ERR_CUDA,
+           "the single-launch factorisation could not synchronise its thread blocks (the grid was not co-resident: is the "
+           "GPU shared?); this call's results are invalid, later calls use one launch per step");
+  }
   if (flag != 0) {
     H_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), (cudaStream_t)cuda_stream));
     H_FAIL(h, MOGPE_ERR_NUMERIC,
@@ -2440,6 +2471,42 @@ extern "C" mogpe_status mogpe_probe_fp64_tensor_peak(int32_t device, double* tfl
   cudaEventDestroy(e1);
   cudaFree(out);
   *tflops = best;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_probe_int8_tensor_peak(int32_t device, double* tops) {
+  if (!tops) return MOGPE_ERR_INVALID;
+  G_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  G_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int smem = 64 * 1024 + 1024, iters = 20000;
+  G_CUDA(cudaFuncSetAttribute(oz::i8_issue_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int* sink = nullptr;
+  G_CUDA(cudaMalloc(&sink, sizeof(int)));
+  G_CUDA(cudaMemset(sink, 0, sizeof(int)));
+  cudaEvent_t e0, e1;
+  G_CUDA(cudaEventCreate(&e0));
+  G_CUDA(cudaEventCreate(&e1));
+  oz::i8_issue_probe_kernel<<<sms, 64, smem>>>(200, sink);  // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0, 0);
+    oz::i8_issue_probe_kernel<<<sms, 64, smem>>>(iters, sink);
+    cudaEventRecord(e1, 0);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) {
+      g_create_error = std::string("int8 probe: ") + cudaGetErrorString(e);
+      return MOGPE_ERR_CUDA;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double ops = 2.0 * 128 * 256 * 32 * (double)iters * sms;
+    best = std::max(best, ops / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tops = best;
   return MOGPE_OK;
 }
 

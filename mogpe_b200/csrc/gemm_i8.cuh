@@ -597,6 +597,43 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
   }
 }
 
+// Issue-rate probe of the INT8 tensor pipe (roofline denominator of gemm_i8_sliced_kernel): one CTA per SM, one warp issues
+// `iters` back-to-back tcgen05.mma.kind::i8 of shape 128 x 256 x 32 on (uninitialised) shared-memory operands laid out like a
+// pipeline stage of the real kernel, accumulating into TMEM; nothing is loaded or stored.  OP = 2 * 128 * 256 * 32 per MMA.
+__global__ void __launch_bounds__(64, 1) i8_issue_probe_kernel(int iters, int* sink) {
+  using namespace t32;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 1) {
+    const uint64_t ad = make_smem_desc(base, 16, 8 * BKB, 4), bd = make_smem_desc(base + 32768, 16, 8 * BKB, 4);
+    for (int it = 0; it < iters; it++) umma_i8(tmem_base, ad, bd, make_idesc_i8(256), it > 0 ? 1u : 0u);
+    __syncwarp();
+    umma_commit_elect(&bar);
+    mbar_wait(&bar, 0u, sink);
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
 // byte planes [batch][NS][rows][cols] (cols = k contiguous): box {64 k, box_rows, NS planes, 1}, 64B swizzle
 inline bool make_map_i8(CUtensorMap* map, const int8_t* ptr, int batch, int rows, int cols, int box_rows, int NS = MAX_NS) {
   t32::EncodeTiledFn fn = t32::encode_fn();
@@ -757,14 +794,20 @@ __global__ void __launch_bounds__(256) slice_rows_n_kernel(const double* __restr
     const double* sp = src + (long long)sb * src_batch_stride + (long long)r * ld + n4;
     const double* c = cs ? cs + (long long)(cs_map ? cs_map[b] : b) * cs_stride + n4 : nullptr;
     const double inv = 1.0 / scale[(long long)b * rows_p + r];
+    uint32_t wh[4], wl[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       double x = (n4 + j < N) ? sp[j] : 0.0;
       if (c) x *= c[j];
-      int8_t q[NS];
-      slice8<NS>(x, inv, q);
+      slice_words<NS>(x * inv, wh[j], wl[j]);
+    }
+    uint32_t th[4], tl[4];
+    transpose4x4_bytes(wh[0], wh[1], wh[2], wh[3], th);
+    transpose4x4_bytes(wl[0], wl[1], wl[2], wl[3], tl);
 #pragma unroll
-      for (int s = 0; s < NS; s++) packed[s] |= (uint32_t)(uint8_t)q[s] << (8 * j);
+    for (int b4 = 4 - NS / 2; b4 < 4; b4++) {  // byte b4 of a slice word = digit 3 - b4 of its half
+      packed[3 - b4] = th[b4];
+      packed[NS / 2 + 3 - b4] = tl[b4];
     }
   }
   int8_t* d = dst + (((long long)b * NS) * rows_p + r) * ld + n4;

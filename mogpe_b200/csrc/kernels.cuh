@@ -185,18 +185,18 @@ __device__ __forceinline__ void trsm32_rows_warp(const double (*T)[33], const do
 // The 32x32 outputs are split over the 8 warps (fragment row i = warp/2, fragment columns 2*(warp%2) + {0,1}):
 // no cross-warp reduction, deterministic, 8 accumulator registers per product.
 // The only sequential work per launch is one block product + one 32x32 factor/invert by ONE CTA per group.
-__global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
-                                                                double* __restrict__ Linv, int Mp, int j,
-                                                                int* __restrict__ fail_flag) {
-  extern __shared__ __align__(16) double chol_smem[];  // Pa | Pb/Pc (never live together) | Dg | Cg
-  __shared__ double rdiag[32];
+// One step of the chain for CTA (bx, g); shared by the per-step kernel and the single-launch chain kernel (where blocks of
+// L / L^-1 written by OTHER CTAs earlier in the same launch are read through the L2: cp.async.cg and ld.global.cg).
+__device__ __forceinline__ void chol_inv_step(const double* __restrict__ Kuu, double* __restrict__ L, double* __restrict__ Linv,
+                                              int Mp, int j, int* __restrict__ fail_flag, int bx, int g, double* chol_smem,
+                                              double* rdiag) {
   double(*Pa)[CHOL_PA] = reinterpret_cast<double(*)[CHOL_PA]>(chol_smem);
   double(*Pb)[CHOL_PA] = reinterpret_cast<double(*)[CHOL_PA]>(chol_smem + 32 * CHOL_PA);
   double(*Pc)[CHOL_PC] = reinterpret_cast<double(*)[CHOL_PC]>(chol_smem + 32 * CHOL_PA);  // Linv[k, b] chunk (k rows)
   double(*Dg)[33] = reinterpret_cast<double(*)[33]>(chol_smem + 32 * CHOL_PA + CHOL_CH * CHOL_PC);
   double(*Cg)[33] = Dg + 32;
-  const int g = blockIdx.y, nb = Mp / 32;
-  const int b = (blockIdx.x + j + 1) % nb;  // the look-ahead CTA (critical path) is scheduled first
+  const int nb = Mp / 32;
+  const int b = (bx + j + 1) % nb;  // the look-ahead CTA (critical path) is scheduled first
   const double* Kg = Kuu + (long long)g * Mp * Mp;
   double* Lg = L + (long long)g * Mp * Mp;
   double* Xg = Linv + (long long)g * Mp * Mp;
@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __r
       Cg[r][c + 1] = ((b == j && r == c + 1) ? 1.0 : base.y) - accC[u][1];
     }
     for (int t = tid; t < 1024; t += 256)
-      Dg[t >> 5][t & 31] = Lg[(long long)(j * 32 + (t >> 5)) * Mp + j * 32 + (t & 31)];  // Ljj (previous launch)
-    if (tid < 32) rdiag[tid] = 1.0 / Lg[(long long)(j * 32 + tid) * Mp + j * 32 + tid];
+      Dg[t >> 5][t & 31] = __ldcg(Lg + (long long)(j * 32 + (t >> 5)) * Mp + j * 32 + (t & 31));  // Ljj (previous step)
+    if (tid < 32) rdiag[tid] = 1.0 / __ldcg(Lg + (long long)(j * 32 + tid) * Mp + j * 32 + tid);
     __syncthreads();
     // one warp solves against Ljj (every CTA in parallel; nothing waits for an explicit Ljj^-1):
     //   b > j : X Ljj^T = C      b < j : Ljj Y = -R
@@ -309,6 +309,52 @@ __global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __r
   for (int t = tid; t < 1024; t += 256) {
     const int r = t >> 5, c = t & 31;
     Lg[(long long)(d * 32 + r) * Mp + d * 32 + c] = Dg[r][c];
+  }
+}
+
+
+__global__ void __launch_bounds__(256, 2) chol_inv_step_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
+                                                                double* __restrict__ Linv, int Mp, int j,
+                                                                int* __restrict__ fail_flag) {
+  extern __shared__ __align__(16) double chol_smem[];  // Pa | Pb/Pc (never live together) | Dg | Cg
+  __shared__ double rdiag[32];
+  chol_inv_step(Kuu, L, Linv, Mp, j, fail_flag, blockIdx.x, blockIdx.y, chol_smem, rdiag);
+}
+
+// The whole chain in ONE launch: every CTA loops over the steps j = -1 .. Mp/32 - 1 and the Mp/32 CTAs of a group meet at a
+// counter in global memory between steps (release: __threadfence + atomicAdd; acquire: ld.acquire.gpu spin by one thread).
+// All CTAs of the grid must be co-resident (the host checks the occupancy and falls back to per-step launches otherwise); a
+// bounded spin turns an impossible wait into a reported failure instead of a hang.
+// grid (Mp/32, Q), block 256; sync [Q] zero-initialised.
+__global__ void __launch_bounds__(256, 2) chol_inv_chain_kernel(const double* __restrict__ Kuu, double* __restrict__ L,
+                                                                 double* __restrict__ Linv, int Mp,
+                                                                 int* __restrict__ fail_flag, unsigned* __restrict__ sync) {
+  extern __shared__ __align__(16) double chol_smem[];
+  __shared__ double rdiag[32];
+  __shared__ int s_abort;
+  const int g = blockIdx.y, nb = Mp / 32;
+  if (threadIdx.x == 0) s_abort = 0;
+  for (int j = -1; j < nb; j++) {
+    chol_inv_step(Kuu, L, Linv, Mp, j, fail_flag, blockIdx.x, g, chol_smem, rdiag);
+    if (j == nb - 1) break;  // nothing reads after the last step inside this launch
+    __syncthreads();          // every thread's stores of this step are issued
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(sync + g, 1u);
+      const unsigned target = (unsigned)nb * (unsigned)(j + 2);
+      unsigned seen;
+      long long spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync + g) : "memory");
+        if (++spins > 400000000LL) {  // ~ a second: the grid is not co-resident
+          s_abort = 1;
+          atomicMax(fail_flag, 1000 + g);
+          break;
+        }
+      } while (seen < target);
+    }
+    __syncthreads();
+    if (s_abort) return;
   }
 }
 

@@ -174,9 +174,7 @@ __global__ void __launch_bounds__(128) kuf8_kernel(const ModelDev* __restrict__ 
       xn += x[d] * x[d];
     }
     double kval[4];
-    uint32_t packed[NS];
-#pragma unroll
-    for (int s = 0; s < NS; s++) packed[s] = 0;
+    uint32_t wh[4], wl[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       double dot = 0.0;
@@ -184,13 +182,18 @@ __global__ void __launch_bounds__(128) kuf8_kernel(const ModelDev* __restrict__ 
       for (int d = 0; d < DMAX; d++) dot += z[j][d] * x[d];
       const double r2 = -2.0 * dot + (zn[j] + xn);
       kval[j] = (valid && k0 + j < Mg) ? kv * exp(-0.5 * r2) : 0.0;
-      int8_t q[NS];
-      slice8<NS>(kval[j], inv_scale, q);
-#pragma unroll
-      for (int s = 0; s < NS; s++) packed[s] |= (uint32_t)(uint8_t)q[s] << (8 * j);
+      slice_words<NS>(kval[j] * inv_scale, wh[j], wl[j]);
     }
+    {  // four consecutive inducing indices -> one word per byte plane (4 x 4 byte transposes)
+      uint32_t th[4], tl[4];
+      transpose4x4_bytes(wh[0], wh[1], wh[2], wh[3], th);
+      transpose4x4_bytes(wl[0], wl[1], wl[2], wl[3], tl);
 #pragma unroll
-    for (int s = 0; s < NS; s++) *reinterpret_cast<uint32_t*>(base + s * plane + (long long)n * Mp32 + k0) = packed[s];
+      for (int b4 = 4 - NS / 2; b4 < 4; b4++) {  // byte b4 of a slice word = digit 3 - b4 of its half
+        *reinterpret_cast<uint32_t*>(base + (3 - b4) * plane + (long long)n * Mp32 + k0) = th[b4];
+        *reinterpret_cast<uint32_t*>(base + (NS / 2 + 3 - b4) * plane + (long long)n * Mp32 + k0) = tl[b4];
+      }
+    }
     for (int q2 = 0; q2 < nv && alpha != nullptr; q2++) {  // (alpha == nullptr: the means come from the A product's epilogue)
       const int v = md->gvec[v0 + q2];
       const double* av = alpha + (long long)v * Mp32 + k0;
