@@ -96,6 +96,7 @@ struct mogpe_handle {
   double* t8_P2 = nullptr;                                 // [P][Mp][Bp] FP64: S_l LTA_l per LTA slot
   unsigned long long* t8_wmax = nullptr;                   // [Q][Mp] row maxima of W (bit patterns)
   unsigned long long* t8_bound_bits = nullptr;             // [2 P + NVcap] atomicMax scratch of bounds_kernel
+  unsigned long long* t8_ltamax = nullptr;                 // [P][Mp] row maxima of LTA | [P] maxima of |dfvar| per latent
   int t8_vmax_cap = 0;
   CUtensorMap tmt_linv, tmt_linvT, tmt_st, tmt_s, tmt_kuf, tmt_at, tmt_abart, tmt_ltat;
   // INT8 product timing in profiling mode (bench.py roofline of gemm_i8_sliced_kernel)
@@ -247,7 +248,7 @@ static void free_ws(mogpe_handle* h) {
   for (void* q : {(void*)h->t8_Linv, (void*)h->t8_LinvT, (void*)h->t8_ST, (void*)h->t8_S, (void*)h->t8_KufT, (void*)h->t8_AT,
                   (void*)h->t8_AbarT, (void*)h->t8_LTAT, (void*)h->t8_linv_scale, (void*)h->t8_linvT_scale, (void*)h->t8_st_scale,
                   (void*)h->t8_s_scale, (void*)h->t8_lta_scale, (void*)h->t8_srowmax, (void*)h->t8_vmax, (void*)h->t8_nscale,
-                  (void*)h->t8_P2, (void*)h->t8_wmax, (void*)h->t8_bound_bits})
+                  (void*)h->t8_P2, (void*)h->t8_wmax, (void*)h->t8_bound_bits, (void*)h->t8_ltamax})
     if (q) cudaFree(q);
   for (auto e : h->ev8) cudaEventDestroy(e);
   h->ev8.clear();
@@ -1460,8 +1461,13 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
   if (md.nlta > 0) {
     const int nl = md.nlta;
     // B operand: LTA_l diag(dfvar_l), rows scaled by their own maxima
-    oz::row_scale_n_kernel<<<dim3(Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
-                                                       h->d_lta_latent, h->bld_scale, Mp);
+    if (a8_ready) {  // INT8 step: a bound from the row maxima of LTA (epilogue of its product) and max |dfvar| -- no pass over LTA
+      unsigned long long* dmax = h->t8_ltamax + (size_t)md.P * Mp;
+      oz::absmax_rows_kernel<<<dim3((N + 1023) / 1024, md.P), 256, 0, st>>>(h->dfvar, N, Bp, dmax);
+      oz::lta_d_scale_kernel<<<dim3((Mp + 127) / 128, nl), 128, 0, st>>>(h->d_md, h->t8_ltamax, dmax, Mp, h->bld_scale);
+    } else
+      oz::row_scale_n_kernel<<<dim3(Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
+                                                         h->d_lta_latent, h->bld_scale, Mp);
     oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
                                                                     h->d_lta_latent, h->bld_scale, h->bLD8, Mp);
     KCOUNT(h, 2);
@@ -1519,6 +1525,7 @@ static mogpe_status ensure_i8_step(mogpe_handle* h) {
   H_CUDA(h, dalloc(&h->t8_nscale, Q * Bp));
   H_CUDA(h, dalloc(&h->t8_P2, P * Mp * Bp));
   H_CUDA(h, dalloc(&h->t8_wmax, Q * Mp));
+  H_CUDA(h, dalloc(&h->t8_ltamax, P * Mp + P));
   if (!h->alpha) H_CUDA(h, dalloc(&h->alpha, P * MOGPE_MAX_SAMPLES * (size_t)h->Mp32));
   const int q = (int)Q, pp = (int)P, m = (int)Mp, b = (int)Bp;
   if (!oz::make_map_i8(&h->tmt_linv, h->t8_Linv, q, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_linvT, h->t8_LinvT, q, m, m, oz::BM) ||
@@ -1618,6 +1625,8 @@ static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const
     p.out = h->t8_LTAT; p.out_batch_stride = (long long)NS * Bp * Mp; p.out_plane_stride = (long long)Bp * Mp; p.ldo = Mp;
     p.out_scale = h->t8_lta_scale;
     p.out64 = h->LTA; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
+    H_CUDA(h, cudaMemsetAsync(h->t8_ltamax, 0, sizeof(unsigned long long) * ((size_t)md.P * Mp + md.P), st));
+    p.rowmax64 = h->t8_ltamax; p.rowmax64_stride = Mp;  // for the row scales of LTA diag(dfvar) in the backward
     for (int slot = 0; slot < nl; slot++) {
       p.mapA[slot] = slot;
       p.mapB[slot] = md.lta_group[slot];

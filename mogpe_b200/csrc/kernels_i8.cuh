@@ -80,6 +80,29 @@ __global__ void bounds_finish_kernel(const ModelDev* __restrict__ md, const doub
   for (int i = threadIdx.x; i < md->NV; i += blockDim.x) vmax[i] = __longlong_as_double((long long)vmax_bits[i]);
 }
 
+// out_bits[b] = max_n |v[b][n]| (n < N) as bit patterns (zero-initialised by the caller).  grid (ceil(N/1024), batch), block 256
+__global__ void __launch_bounds__(256) absmax_rows_kernel(const double* __restrict__ v, int N, long long stride,
+                                                          unsigned long long* __restrict__ out_bits) {
+  const int b = blockIdx.y;
+  double m = 0.0;
+  for (int n = blockIdx.x * 1024 + threadIdx.x; n < min(N, (int)(blockIdx.x + 1) * 1024); n += 256)
+    m = fmax(m, fabs(v[(long long)b * stride + n]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits + b, (unsigned long long)__double_as_longlong(m));
+}
+
+// Row scales of LTA_l diag(dfvar_l) from a bound instead of a pass over the matrix:
+//   scale[slot][m] = pow2_scale(max_n |LTA[slot][m][n]| * max_n |dfvar[latent(slot)][n]|)
+// (row maxima of LTA collected by the epilogue of the LTA product, the adjoint maxima by absmax_rows_kernel).
+__global__ void lta_d_scale_kernel(const ModelDev* __restrict__ md, const unsigned long long* __restrict__ lta_rowmax,
+                                   const unsigned long long* __restrict__ dmax, int Mp, double* __restrict__ scale) {
+  const int slot = blockIdx.y, m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mp) return;
+  const double d = __longlong_as_double((long long)dmax[md->lta_latent[slot]]);
+  scale[(long long)slot * Mp + m] = pow2_scale(1.0000001 * __longlong_as_double((long long)lta_rowmax[(long long)slot * Mp + m]) * d);
+}
+
 // scale[i] = pow2_scale(max[i]) from the bit patterns accumulated by atomicMax (non-negative doubles order like integers)
 __global__ void max_to_scale_kernel(const unsigned long long* __restrict__ mx, double* __restrict__ scale, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,6 +260,33 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
 namespace mogpe {
 namespace oz {
 
+// exp(x) for x <= 0 to ~1e-14 relative (17 FP64 instructions instead of the ~40 of the correctly rounded library routine):
+// k = round(x log2 e) by the 2^52 trick, f = x - k ln 2 in two pieces (|f| <= 0.347), a degree-11 Taylor polynomial, and
+// 2^k assembled in the exponent field (flushed to zero below the normal range).  Used ONLY where Kuf is re-evaluated for the
+// gradient kernels (tolerance 1e-6); the forward Kuf keeps the library exp.
+__device__ __forceinline__ double exp_neg_fast(double x) {
+  const double C = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, 1.4426950408889634074, C);
+  const int k = __double2loint(t);
+  const double kd = t - C;
+  double f = fma(kd, -6.93147180369123816490e-01, x);  // ln2 high part (gpflow-independent constants of fdlibm)
+  f = fma(kd, -1.90821492927058770002e-10, f);         // ln2 low part
+  double p = 1.0 / 39916800.0;
+  p = fma(p, f, 1.0 / 3628800.0);
+  p = fma(p, f, 1.0 / 362880.0);
+  p = fma(p, f, 1.0 / 40320.0);
+  p = fma(p, f, 1.0 / 5040.0);
+  p = fma(p, f, 1.0 / 720.0);
+  p = fma(p, f, 1.0 / 120.0);
+  p = fma(p, f, 1.0 / 24.0);
+  p = fma(p, f, 1.0 / 6.0);
+  p = fma(p, f, 0.5);
+  p = fma(p, f, 1.0);
+  p = fma(p, f, 1.0);
+  const double s = k > -1022 ? __hiloint2double((k + 1023) << 20, 0) : 0.0;
+  return p * s;
+}
+
 // Kuf-bar (= W) consumer of the INT8 step, ONE pass over W [g][m][n]:
 //   (a) kernel-hyperparameter and Z gradients  E = W .* Kuf,  dZ[m,d] = -sum_n E (z_md - x_nd) / l_d^2,
 //       dl_d = sum_mn E (z_md - x_nd)^2 / l_d^3,  dvar = sum E / var   (as kuf_grad_kernel) with Kuf RE-EVALUATED from X and Z
@@ -302,7 +352,7 @@ __global__ void __launch_bounds__(256) kuf_grad_slice_kernel(const ModelDev* __r
         dot += zs[d] * xs;
       }
       const double r2 = -2.0 * dot + (zn + xn);
-      ev[j] = ok ? wv[j] * (kvar * exp(-0.5 * r2)) : 0.0;
+      ev[j] = ok ? wv[j] * (kvar * exp_neg_fast(fmin(-0.5 * r2, 0.0))) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
