@@ -847,7 +847,17 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
       h->lik_smem_set = smem;
     }
     sk_begin(h, SK_LIK, st);
-    lik_kernel<<<Bc / blk, blk, smem, st>>>(la);
+    static const bool lik_fast = getenv("MOGPE_LIK_GENERIC") == nullptr;  // (tuning / test switch)
+    if (lik_fast && bound == MOGPE_BOUND_FURTHER_GATING && S <= LIK_FG_SMAX && md.K <= 32) {
+      // the default bound: KT lanes per data point (lane = expert), adjoints written once, block-level gradient reductions
+      const size_t fsm = (size_t)8 * 3 * md.P * sizeof(double);
+      if (md.K <= 2) lik_fg_kernel<2><<<Bc / 128, 256, fsm, st>>>(la);
+      else if (md.K <= 4) lik_fg_kernel<4><<<Bc / 64, 256, fsm, st>>>(la);
+      else if (md.K <= 8) lik_fg_kernel<8><<<Bc / 32, 256, fsm, st>>>(la);
+      else if (md.K <= 16) lik_fg_kernel<16><<<Bc / 16, 256, fsm, st>>>(la);
+      else lik_fg_kernel<32><<<Bc / 8, 256, fsm, st>>>(la);
+    } else
+      lik_kernel<<<Bc / blk, blk, smem, st>>>(la);
     // algorithmic bytes: per point the means / variances of every latent in and their adjoints out, Y, draws
     sk_end(h, SK_LIK, st, 8.0 * N * (2.0 * md.Pe + 2.0 * (md.P - md.Pe) + md.F + (double)S * md.G + 1.0));
     H_CUDA(h, cudaGetLastError());

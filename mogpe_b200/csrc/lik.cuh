@@ -417,6 +417,223 @@ __global__ void lik_kernel(const LikArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast path of lik_kernel for bound = further_gating -- the reference's DEFAULT bound (mosvgpe.py:109-168, legacy
+// svgp.py:129-230) and the one bench.py times: experts via inducing samples, gating via marginal h samples -- with up to
+// LIK_FG_SMAX samples.  Same arithmetic as lik_kernel, different decomposition: KT = 2^ceil(log2 K) lanes work on ONE data
+// point, lane k owns expert k (its F latents) and, with Softmax gating, gating latent k (Bernoulli: the single gating latent
+// is evaluated by lanes 0 and 1); the log-sum-exp over experts, the softmax and the adjoint sums are shuffle reductions
+// inside the lane group, every adjoint is written exactly once (no zero + read-modify-write sweeps over dmean / dfvar), and
+// the per-latent reductions over the data points (mean-function, kernel-variance and noise gradients) go through shared
+// memory: one atomic per latent and block.  lik_kernel's one-thread-per-point body took 54 us for 8192 points (latency-bound:
+// ~2 warps per SM, every intermediate through a shared-memory scratch and dozens of dependent global read-modify-writes).
+// grid (ceil(Bc / (256 / KT))), block 256.
+// ------------------------------------------------------------------------------------------------
+constexpr int LIK_FG_SMAX = 4;
+
+template <int KT>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = KT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int KT>
+__device__ __forceinline__ double group_max(double v) {
+#pragma unroll
+  for (int o = KT / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// sum over the data points of a warp for the lanes that own the same expert index (lanes k, k + KT, ...)
+template <int KT>
+__device__ __forceinline__ double points_sum(double v) {
+#pragma unroll
+  for (int o = 16; o >= KT; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256) lik_fg_kernel(const LikArgs a) {
+  constexpr int PTS = 256 / KT;  // data points per block
+  constexpr int WARPS = 8;
+  // per-latent block reductions: [mean_c | kvar | noise] x up to MOGPE_MAX_LATENTS, one slot per warp
+  extern __shared__ double red_sm[];  // [WARPS][3][P]
+  const ModelDev* md = a.md;
+  const int S = md->S, K = md->K, F = md->F, G = md->G, Pe = md->Pe, P = md->P;
+  const bool keras = md->flavour == MOGPE_FLAVOUR_KERAS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kk = lane & (KT - 1);
+  const int n = blockIdx.x * PTS + tid / KT;
+  const bool valid = n < a.N, act = kk < K;
+  const bool want = a.grads != nullptr;
+  const long long Bp = a.Bp;
+  for (int i = tid; i < WARPS * 3 * P; i += 256) red_sm[i] = 0.0;
+  __syncthreads();
+  double* red = red_sm + (long long)warp * 3 * P;
+
+  // ---- gating: log pi_k[s] from marginal h samples --------------------------------------------------------------
+  double lpi[LIK_FG_SMAX], eh[LIK_FG_SMAX];
+  double g_sd = 1.0, g_hm = 0.0;
+  const int gl = (G == 1) ? Pe : Pe + kk;  // gating latent evaluated by this lane
+  const bool g_act = (G == 1) ? (kk < 2) : act;
+  if (valid && g_act) {
+    const int gg = md->latent_group[gl];
+    g_hm = a.mean[(long long)md->voff[gl] * Bp + n];
+    const double hv = a.params[a.lo.kvar + gg] - a.var0ss[(long long)gg * Bp + n] + a.varq[(long long)gl * Bp + n];
+    g_sd = keras ? sqrt(hv) : hv;  // quirk 2: the legacy flavour samples with scale = variance
+  }
+#pragma unroll
+  for (int s = 0; s < LIK_FG_SMAX; s++) {
+    lpi[s] = 0.0;
+    eh[s] = 0.0;
+    if (s < S) {
+      if (valid && g_act) eh[s] = a.eps_h[((long long)s * a.N + n) * G + (G == 1 ? 0 : kk)];
+      const double h = g_hm + g_sd * eh[s];
+      if (G == 1) {
+        const double p0 = inv_probit(h);
+        const double p1 = keras ? inv_probit(-h) : 1.0 - p0;
+        lpi[s] = log(kk == 0 ? p0 : p1);
+      } else {
+        const double hh = act ? h : -1e300;
+        const double mx = group_max<KT>(hh);
+        const double se = group_sum<KT>(act ? exp(hh - mx) : 0.0);
+        lpi[s] = hh - (mx + log(se));
+      }
+    }
+  }
+  // ---- expert log densities lp_k[s] = sum_f log N(y_f; mean, scale) ------------------------------------------------
+  double lp[LIK_FG_SMAX];
+#pragma unroll
+  for (int s = 0; s < LIK_FG_SMAX; s++) lp[s] = 0.0;
+  if (valid && act)
+    for (int f = 0; f < F; f++) {
+      const int l = kk * F + f, g = md->latent_group[l];
+      const double yv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * Bp + n] + a.params[a.lo.noise + l];
+      const double sc = keras ? yv : sqrt(yv);  // quirk 1: the Keras flavour uses the predictive variance as the scale
+      const double y = a.Y[(long long)n * F + f], lsc = log(sc) + 0.5 * MOGPE_LOG_2PI;
+#pragma unroll
+      for (int s = 0; s < LIK_FG_SMAX; s++)
+        if (s < S) {
+          const double z = (y - a.mean[(long long)(md->voff[l] + s) * Bp + n]) / sc;
+          lp[s] += -0.5 * z * z - lsc;
+        }
+    }
+  // ---- marginalise the indicator, average the S x S sample pairs ----------------------------------------------------
+  double dlp[LIK_FG_SMAX], dlpi[LIK_FG_SMAX], val = 0.0;
+#pragma unroll
+  for (int s = 0; s < LIK_FG_SMAX; s++) dlp[s] = dlpi[s] = 0.0;
+  const double w = a.scale / ((double)S * S);
+#pragma unroll
+  for (int s1 = 0; s1 < LIK_FG_SMAX; s1++)
+#pragma unroll
+    for (int s2 = 0; s2 < LIK_FG_SMAX; s2++)
+      if (s1 < S && s2 < S) {
+        const double t = act ? lp[s1] + lpi[s2] : -1e300;
+        const double mx = group_max<KT>(t);
+        const double se = group_sum<KT>(act ? exp(t - mx) : 0.0);
+        const double lse = mx + log(se);
+        if (valid && kk == 0) val += w * lse;
+        if (want && valid && act) {
+          const double r = w * exp(t - lse);
+          dlp[s1] += r;
+          dlpi[s2] += r;
+        }
+      }
+  // ---- adjoints of the expert latents (written once; every lane runs the loop so that the shuffles stay convergent) ---------
+  for (int f = 0; f < F; f++) {
+    const int l = act ? kk * F + f : 0;
+    double dyv = 0.0, dc = 0.0;
+    if (valid && act) {
+      const int g = md->latent_group[l];
+      const double yv = a.params[a.lo.kvar + g] - a.var0ss[(long long)g * Bp + n] + a.params[a.lo.noise + l];
+      const double sc = keras ? yv : sqrt(yv);
+      const double y = a.Y[(long long)n * F + f];
+#pragma unroll
+      for (int s = 0; s < LIK_FG_SMAX; s++)
+        if (s < S) {
+          const double z = (y - a.mean[(long long)(md->voff[l] + s) * Bp + n]) / sc;
+          const double dm = dlp[s] * z / sc;
+          a.dmean[(long long)(md->voff[l] + s) * Bp + n] = dm;
+          dc += dm;
+          dyv += dlp[s] * (z * z - 1.0) / sc * (keras ? 1.0 : 0.5 / sc);
+        }
+    } else if (act) {
+      for (int s = 0; s < S; s++) a.dmean[(long long)(md->voff[l] + s) * Bp + n] = 0.0;
+    }
+    if (act) a.dfvar[(long long)l * Bp + n] = dyv;
+    if (want) {
+      const double sc_ = points_sum<KT>(dc), sk = points_sum<KT>(dyv);
+      if (lane < KT && act) {
+        red[0 * P + l] += sc_;
+        red[1 * P + l] += sk;
+        red[2 * P + l] += sk;  // d / d noise = d / d y_var
+      }
+    }
+  }
+  // ---- adjoints of the gating latents --------------------------------------------------------------------------------------
+  {
+    double dhm = 0.0, dhv = 0.0;
+    if (G == 1) {
+#pragma unroll
+      for (int s = 0; s < LIK_FG_SMAX; s++)
+        if (s < S) {
+          const double other = __shfl_xor_sync(0xffffffffu, dlpi[s], 1);  // lane 0 <-> lane 1 of the group
+          const double d0 = kk == 0 ? dlpi[s] : other, d1 = kk == 0 ? other : dlpi[s];
+          const double h = g_hm + g_sd * eh[s];
+          const double gp = inv_probit_grad(h);
+          const double p0 = inv_probit(h), p1 = keras ? inv_probit(-h) : 1.0 - p0;
+          const double dh = d0 * gp / p0 - d1 * gp / p1;
+          dhm += dh;
+          dhv += dh * eh[s] * (keras ? 0.5 / g_sd : 1.0);
+        }
+    } else {
+#pragma unroll
+      for (int s = 0; s < LIK_FG_SMAX; s++)
+        if (s < S) {
+          const double sd_all = group_sum<KT>(dlpi[s]);
+          const double dh = act ? dlpi[s] - exp(lpi[s]) * sd_all : 0.0;
+          dhm += dh;
+          dhv += dh * eh[s] * (keras ? 0.5 / g_sd : 1.0);
+        }
+    }
+    const bool owner = (G == 1) ? (kk == 0) : act;
+    if (owner) {
+      if (!valid) dhm = dhv = 0.0;
+      a.dmean[(long long)md->voff[gl] * Bp + n] = dhm;
+      a.dfvar[(long long)gl * Bp + n] = dhv;
+    }
+    if (want) {
+      const double sm = points_sum<KT>(owner ? dhm : 0.0), sv = points_sum<KT>(owner ? dhv : 0.0);
+      if (lane < KT && owner) {
+        red[0 * P + gl] += sm;
+        red[1 * P + gl] += sv;
+      }
+    }
+  }
+  // ---- block reductions -> one atomic per latent -------------------------------------------------------------------------
+  val = warp_sum(val);
+  __syncthreads();
+  if (want)
+    for (int i = tid; i < 3 * P; i += 256) {
+      double t = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < WARPS; wq++) t += red_sm[(long long)wq * 3 * P + i];
+      const int which = i / P, l = i % P;
+      if (t != 0.0) {
+        if (which == 0) atomicAdd(a.grads + a.lo.mean_c + l, t);
+        else if (which == 1) atomicAdd(a.grads + a.lo.kvar + md->latent_group[l], t);
+        else if (l < Pe) atomicAdd(a.grads + a.lo.noise + l, t);
+      }
+    }
+  __shared__ double vred[WARPS];
+  if (lane == 0) vred[warp] = val;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int wq = 0; wq < WARPS; wq++) t += vred[wq];
+    atomicAdd(a.out + 1, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Prediction outputs (Appendix A.6-A.7).  One thread per test point.
 // ------------------------------------------------------------------------------------------------
 struct PredArgs {
