@@ -399,7 +399,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     experts, gating = blocks_from_spec(spec)
     eng = Engine(experts, gating, flavour=FLAVOUR, max_batch=B, device=local_rank)
-    eng.set_seed(1234 + rank)
+    eng.set_seed(1234)  # one seed for the job: inducing draws are shared between the ranks, per-point draws are per rank
     if world > 1:
         ids = [Engine.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -468,7 +468,7 @@ def main():
     # (device -> host, asynchronously into pinned memory; fit() synchronises on them at the end of the epoch).
     del eng, dev_batches
     model = build_public_model(spec, wl, device=local_rank)
-    model.set_seed(4321 + rank)
+    model.set_seed(4321)
     if world > 1:
         ids2 = [Engine.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids2, src=0)

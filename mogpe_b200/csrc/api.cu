@@ -143,6 +143,11 @@ struct mogpe_handle {
   bool a_done_in_factorise = false;
   // library-owned random stream
   uint64_t seed = 0x6d6f677065ULL, rng_counter = 0;
+  // data parallel: the inducing-point draws (eps_u) must be IDENTICAL on every rank (they belong to the shared parameters),
+  // the per-point draws (eps_h, eps_f, Softmax MC) independent between the shards: a second counter for the former (it
+  // advances by the same amount on every rank whatever the shard sizes) and a rank offset in the counter space for the latter
+  uint64_t rng_counter_u = 0;
+  int dp_rank = 0, dp_world = 1;
   double *eps_u_int = nullptr, *eps_h_int = nullptr, *eps_f_int = nullptr;
   size_t eps_u_cap = 0, eps_h_cap = 0, eps_f_cap = 0;
   const double *last_eps_u = nullptr, *last_eps_h = nullptr, *last_eps_f = nullptr;
@@ -782,11 +787,19 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
         cap = n;
       }
       const long long pairs = ((long long)n + 1) / 2;
-      fill_normal_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(buf, (long long)n, h->seed,
-                                                                          h->rng_counter - h->capture_rng_start,
+      unsigned long long offset = h->rng_counter - h->capture_rng_start;
+      if (h->dp_world > 1) {  // (graph capture is never used with a communicator)
+        if (&buf == &h->eps_u_int) {
+          offset = (1ull << 62) + h->rng_counter_u;  // shared stream: the same eps_u on every rank
+          h->rng_counter_u += (n + 1) / 2 * 2;
+        } else {
+          offset = ((unsigned long long)(h->dp_rank + 1) << 48) + h->rng_counter;  // this rank's own stream
+        }
+      }
+      fill_normal_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(buf, (long long)n, h->seed, offset,
                                                                           h->capturing ? h->d_step_state : nullptr);
       KCOUNT(h, 1);
-      h->rng_counter += (n + 1) / 2 * 2;
+      if (!(h->dp_world > 1 && &buf == &h->eps_u_int)) h->rng_counter += (n + 1) / 2 * 2;
       eps = buf;
       return MOGPE_OK;
     };
@@ -1940,6 +1953,8 @@ extern "C" mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int
   int rc = fn(&h->nccl_comm, world, uid, rank);
   if (rc != 0) H_FAIL(h, MOGPE_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
   h->nccl_lib = g_nccl.lib;
+  h->dp_rank = rank;
+  h->dp_world = world;
   return MOGPE_OK;
 }
 
@@ -2021,6 +2036,7 @@ extern "C" mogpe_status mogpe_set_seed(mogpe_handle* h, uint64_t seed) {
   if (!h) return MOGPE_ERR_INVALID;
   h->seed = seed;
   h->rng_counter = 0;
+  h->rng_counter_u = 0;
   h->graphs_dirty = true;  // the seed is a kernel argument of the captured launches
   return MOGPE_OK;
 }

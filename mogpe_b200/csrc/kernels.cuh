@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256, 2) chol_inv_chain_kernel(const double* __
       long long spins = 0;
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync + g) : "memory");
-        if (++spins > 400000000LL) {  // ~ a second: the grid is not co-resident
+        if (++spins > 4000000LL) {  // seconds of L2 round trips: the grid is not co-resident
           s_abort = 1;
           atomicMax(fail_flag, 1000 + g);
           break;

@@ -320,6 +320,9 @@ class Engine:
     def init_data_parallel(self, rank: int, world_size: int, unique_id: bytes, overlap: bool = True):
         """Join an NCCL communicator (id from Engine.nccl_unique_id() on rank 0, distributed by the caller) and
         weight the redundantly computed KL terms by 1/world_size so that the all-reduced sums are exact.
+        Random draws the caller does not supply: use the SAME seed on every rank -- the inducing-point draws (eps_u) then
+        come from a shared stream (identical on all ranks, as one process would draw them) and the per-point draws (eps_h,
+        eps_f, Softmax Monte-Carlo) from a per-rank stream, so the shards are independent.
         overlap: elbo() itself all-reduces [gradients | results] (most of it underneath the Cholesky backward) and
         allreduce(self.gbuf) becomes a no-op; False keeps the reduction a separate call after elbo()."""
         _lib.check(self.lib.mogpe_comm_init(self.h, unique_id, rank, world_size), self.h)

@@ -1,7 +1,9 @@
 """Data parallelism over the minibatch rows: the bound is a sum over data points, so each rank
 evaluates a contiguous slice with the GLOBAL scale num_data / N_global, the redundantly computed KL terms are
 weighted 1 / world_size, and ONE all-reduce(sum) of the packed [gradients | elbo, var_exp, kl_g, kl_e] buffer
-gives every rank the single-process result.  NCCL runs inside the CUDA library (mogpe_allreduce_sum);
+gives every rank the single-process result (exactly so when the draws are passed explicitly; with library-drawn noise
+the ranks share the inducing-point draws and draw their per-point noise from independent per-rank streams, which is one
+valid realisation of the single-process estimator).  NCCL runs inside the CUDA library (mogpe_allreduce_sum);
 torch.distributed is only the plumbing that distributes the NCCL unique id.
 """
 from typing import Tuple

@@ -87,3 +87,48 @@ def test_two_gpu_data_parallel_matches_single_gpu(tmp_path, case, overlap):
     for a, b in zip(bounds[:-1], bounds[1:]):
         scale = max(1e-300, np.max(np.abs(want[a:b])))
         assert np.max(np.abs(got0[a:b] - want[a:b])) <= 1e-8 * scale, (a, b)
+
+
+def _rng_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mogpe_b200 import parallel
+    from mogpe_b200.engine import Engine
+    from tests._engine_helpers import block_from_gp
+    from tests._specs import make_spec
+
+    spec, X, Y, eps = make_spec(**CASES["small"])
+    experts = [block_from_gp(g, True) for g in spec["experts"]]
+    eng = Engine(experts, block_from_gp(spec["gating"], False), flavour="keras", max_batch=300, device=rank)
+    eng.set_seed(99)  # the same seed on every rank
+    eng.init_data_parallel(rank, world, parallel.DataParallelEngine.exchange_unique_id(Engine, rank))
+    Xl, Yl = parallel.shard_batch(X[:299], Y[:299], rank, world)  # 150 + 149 rows: unequal shards
+    out = {}
+    for step in range(2):
+        eng.elbo(Xl, Yl, "further_gating", 2, 100.0, want_grads=True, unpack=False, readback=False)
+        out[f"u{step}"] = eng.debug("eps_u")
+        out[f"h{step}"] = eng.debug("eps_h")
+    np.savez(os.path.join(out_dir, f"rng{rank}.npz"), **out)
+    dist.destroy_process_group()
+
+
+def test_library_draws_in_data_parallel_mode(tmp_path):
+    """Library-drawn noise with one seed for the job: the inducing-point draws are identical on every rank in every step
+    (also with unequal shards), the per-point draws of the shards are different streams."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_rng_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "rng0.npz"), np.load(tmp_path / "rng1.npz")
+    for step in range(2):
+        assert np.array_equal(a[f"u{step}"], b[f"u{step}"]) and np.any(a[f"u{step}"] != 0)
+        n = min(a[f"h{step}"].size, b[f"h{step}"].size)
+        assert not np.array_equal(a[f"h{step}"][:n], b[f"h{step}"][:n])
+    assert not np.array_equal(a["u0"], a["u1"])  # and the shared stream advances between steps
