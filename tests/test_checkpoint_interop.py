@@ -117,3 +117,75 @@ def test_cuda_path_at_reference_trained_parameters():
     fm, fv = model.experts.experts_list[0].predict_f(X)
     assert np.max(np.abs(fm - g["expert0/f_mean"])) <= 1e-8 * np.max(np.abs(g["expert0/f_mean"]))
     assert np.max(np.abs(fv - g["expert0/f_var"])) <= 1e-8 * np.max(np.abs(g["expert0/f_var"]))
+
+
+def test_writer_primitives_are_pinned_by_the_reference_checkpoint():
+    """CRC-32C + masking, the string-tensor encoding and the block trailer of the writer reproduce the bytes of the
+    reference's own checkpoint; the object graph generated from the variable keys places every variable on the same path of
+    child names as TensorFlow's graph does."""
+    import struct
+
+    from mogpe_b200.training import tf_checkpoint as tc
+
+    pre = os.path.join(CKPT_DIR, "ckpt-200")
+    buf = open(pre + ".index", "rb").read()
+    data = open(pre + ".data-00000-of-00001", "rb").read()
+    assert tc.crc32c(b"123456789") == 0xE3069283  # the CRC-32C check value
+    footer = buf[-48:]
+    _, p = tc._varint(footer, 0)
+    _, p = tc._varint(footer, p)
+    ioff, p = tc._varint(footer, p)
+    isize, p = tc._varint(footer, p)
+    graph_payload, n_tensors = None, 0
+    for _, handle in tc._block_entries(buf, ioff, isize):
+        boff, q = tc._varint(handle, 0)
+        bsize, q = tc._varint(handle, q)
+        block, trailer = buf[boff:boff + bsize], buf[boff + bsize:boff + bsize + 5]
+        assert struct.unpack("<I", trailer[1:])[0] == tc.mask_crc(tc.crc32c(block + trailer[:1]))
+        for key, value in tc._block_entries(buf, boff, bsize):
+            if key == b"":
+                assert value == tc._pb_varint(1, 1) + tc._pb_bytes(3, tc._pb_varint(1, 1))  # BundleHeaderProto
+                continue
+            m = tc._parse_proto(value)
+            raw = data[m.get(4, [0])[0]:m.get(4, [0])[0] + m[5][0]]
+            if m[1][0] == 7:
+                ln, pp = tc._varint(raw, 0)
+                graph_payload = raw[pp + 4:]
+                enc, crc = tc.encode_string_tensor(graph_payload)
+                assert enc == raw and crc == m[6][0]
+            else:
+                assert tc.mask_crc(tc.crc32c(raw)) == m[6][0]
+                shape = tc._shape(m[2][0]) if 2 in m else ()
+                assert value == tc._entry_proto(m[1][0], shape, m.get(4, [0])[0], m[5][0], m[6][0])  # same message bytes
+                n_tensors += 1
+    assert n_tensors == 24
+    theirs = tc.parse_object_graph(graph_payload)
+    keys = [k for k in tc.read_index(pre) if k != "_CHECKPOINTABLE_OBJECT_GRAPH"]
+    mine = tc.parse_object_graph(tc.object_graph_proto(keys))
+    assert mine == theirs and len(mine) == 24
+
+
+def test_checkpoint_round_trip_through_the_writer(tmp_path):
+    """Reference checkpoint -> model -> CheckpointManager.save -> fresh model: identical variables; the written files parse
+    as a tensor bundle with the reference's variable names, and max_to_keep prunes old files."""
+    from mogpe_b200.training.tf_checkpoint import read_index, read_tf_checkpoint
+    from mogpe_b200.training.utils import init_checkpoint_manager, update_model_from_checkpoint
+
+    a = update_model_from_checkpoint(_model(), CKPT_DIR)
+    mgr = init_checkpoint_manager(a, str(tmp_path / "log"), num_ckpts=2)
+    for _ in range(3):
+        prefix = mgr.save()
+    assert os.path.basename(prefix) == "ckpt-3" and not os.path.exists(str(tmp_path / "log" / "ckpt-1.index"))
+    ref = read_tf_checkpoint(os.path.join(CKPT_DIR, "ckpt-200"))
+    got = read_tf_checkpoint(prefix)
+    assert set(got) == set(ref)
+    for k in ref:
+        if k.startswith("save_counter"):
+            assert int(np.asarray(got[k]).reshape(-1)[0]) == 3
+            continue
+        assert got[k].shape == ref[k].shape and got[k].dtype == ref[k].dtype
+        np.testing.assert_array_equal(got[k], ref[k])  # unconstrained variables survive bit for bit
+    assert "_CHECKPOINTABLE_OBJECT_GRAPH" in read_index(prefix)
+    b = update_model_from_checkpoint(_model(), str(tmp_path / "log"))
+    for pa, pb in zip(a.trainable_variables, b.trainable_variables):
+        np.testing.assert_array_equal(pa.unconstrained, pb.unconstrained)

@@ -161,9 +161,14 @@ def test_elbo_and_gradients_match_oracle(flavour, bound, case):
     bad = {}
     for name, g_ref in want.items():
         r = _rel(got[name], g_ref)
+        g_ref = np.asarray(g_ref, dtype=float)
+        diff = np.asarray(got[name], dtype=float) - g_ref
         scale = max(1.0, float(np.max(np.abs(g_ref))))
-        if np.max(np.abs(np.asarray(got[name]) - g_ref)) > RTOL_GRAD * scale:
-            bad[name] = r
+        # max-norm against the block's largest entry AND the relative L2 norm of the whole block (the max-norm alone leaves
+        # the small entries of a large block unconstrained); blocks that are numerically zero are held to the absolute bound
+        l2 = float(np.linalg.norm(diff.ravel()) / max(np.linalg.norm(g_ref.ravel()), 1.0))
+        if np.max(np.abs(diff)) > RTOL_GRAD * scale or l2 > RTOL_GRAD:
+            bad[name] = (r, l2)
     assert not bad, bad
 
 

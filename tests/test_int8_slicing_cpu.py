@@ -74,3 +74,38 @@ def test_sliced_product_is_fp64_accurate_even_with_cancellation():
     f32 = (A.astype(np.float32) @ B.T.astype(np.float32)).astype(np.float64)
     rowmax = np.max(np.abs(A), axis=1)[:, None]
     assert np.max(np.abs(got - want) / rowmax) < 1e-12 < np.max(np.abs(f32 - want) / rowmax) * 1e-3
+
+
+def test_word_slicing_restatement_matches_the_digit_rule():
+    """oz::slice_words (gemm_i8.cuh): bias every base-128 digit by 64, spread the bit fields of the two 7 NS / 2-bit integers
+    into byte lanes, remove the bias with a carry-free per-byte add.  The bytes must equal the balanced digits of slice8 for
+    eight and for six slices, including the end points |r| = 1/2."""
+    global NS
+    keep = NS
+    rng = np.random.default_rng(0)
+    try:
+        for ns in (8, 6):
+            NS = ns
+            H = ns // 2
+            r = np.concatenate([rng.uniform(-0.5, 0.5, 100000), [0.5, -0.5, 0.0, 2.0**-30, -2.0**-30, 0.4999999999999999]])
+            q = slice8(r, 1.0)
+            P = float(1 << (7 * H))
+            x1 = r * P
+            hi = np.rint(x1)
+            lo = np.rint((x1 - hi) * P)
+            bias = sum(64 << (7 * k) for k in range(H))
+            out = np.zeros((ns, r.size), dtype=np.int64)
+            for half, v in ((0, hi.astype(np.int64)), (1, lo.astype(np.int64))):
+                u = v + bias
+                assert np.all(u >= 0)
+                sh = 0 if H == 4 else 7
+                w = ((u << (3 + sh)) & 0xFF000000) | ((u << (2 + sh)) & 0x7F0000) | ((u << (1 + sh)) & 0x7F00) | ((u & 0x7F) if H == 4 else 0x40)
+                w = ((w & 0x7F7F7F7F) + 0x40404040) ^ (~w & 0x80808080)  # per-byte u - 64 without carries
+                for b in range(4 - H, 4):
+                    byte = (w >> (8 * b)) & 0xFF
+                    out[half * H + 3 - b] = np.where(byte > 127, byte - 256, byte)
+            assert np.array_equal(out, q)
+            rec = sum(out[p] * 2.0 ** (-7 * (p + 1)) for p in range(ns))
+            assert np.max(np.abs(rec - r)) <= 2.0 ** (-7 * ns - 1)
+    finally:
+        NS = keep
