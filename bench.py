@@ -503,7 +503,7 @@ def main():
     # INT8-sliced products: every FP64-equivalent multiply-add is 36 signed-byte slice-pair multiply-adds (8 x 8 slices, the
     # pairs with i + j < 8), so the tensor pipe executes 36 operations per algorithmic FLOP
     i8_eq_tflops = prof8["flops"] / (prof8["ms"] * 1e-3) * 1e-12 if i8_on else None
-    i8_tops = 36.0 * i8_eq_tflops if i8_on else None
+    i8_tops = prof8["tensor_ops"] / (prof8["ms"] * 1e-3) * 1e-12 if i8_on else None
     dmma = {"kernel": "mogpe::gemm_dmma_kernel (FP64 DMMA: the M^3 products of the Cholesky backward; every dense product when "
                       "the INT8 step does not apply)",
             "achieved": gemm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -518,8 +518,9 @@ def main():
             "peak_source": "INT8 tensor-pipe issue peak measured in THIS run by mogpe_probe_int8_tensor_peak (back-to-back "
                            "tcgen05.mma.kind::i8 128x256x32 from shared-memory operands on every SM; nominal dense INT8: 4500); "
                            "MEASURED_PEAKS.json holds only HBM and bf16 figures",
-            "achieved_note": "36 INT8 slice-pair operations per algorithmic FP64 FLOP (triangular operands / results counted as "
-                             "triangular) / device time of the launches (CUDA events around every launch, profiled pass)",
+            "achieved_note": "INT8 slice-pair operations (36 per algorithmic FP64 FLOP for the two forward products with eight "
+                             "slices, 28 for the four gradient-only products with seven; triangular operands / results counted "
+                             "as triangular) / device time of the launches (CUDA events around every launch, profiled pass)",
             "fp64_equivalent_tflops": i8_eq_tflops,
             "fp64_equivalent_vs_fp64_tensor_peak": i8_eq_tflops / fp64_peak,
             "kernel_ms_per_step": prof8["ms"] / steps, "kernel_share_of_step": prof8["ms"] / ms_prof,

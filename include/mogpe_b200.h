@@ -210,6 +210,10 @@ mogpe_status mogpe_set_int8_backward(mogpe_handle* h, int32_t on);
  * and Kuf / A / Abar are never written in FP64.  Replaces the conditional + backward of gpflow's SVGP.predict_f under
  * tf.GradientTape (mogpe/keras/gps.py:31-48, mogpe/keras/mixture_of_experts/mosvgpe.py:57-69). */
 mogpe_status mogpe_set_int8_step(mogpe_handle* h, int32_t on);
+/* Byte slices loaded by the GRADIENT-ONLY products of the INT8 step (S LTA, W = L^-T Abar, Lbar, Sbar): 7 (default: the
+ * seven most significant planes, 49 bits, 28 slice pairs) or 8 (56 bits, 36 pairs).  The forward products, whose results
+ * enter the ELBO (1e-8), always use eight. */
+mogpe_status mogpe_set_int8_grad_slices(mogpe_handle* h, int32_t slices);
 
 /* on != 0: mogpe_elbo_fwd_bwd performs the data-parallel reduction itself and returns globally summed gradients and
  * results -- the part of the gradient buffer that is final before the Cholesky backward (q_mu, q_sqrt, mean, noise and, when
@@ -285,8 +289,9 @@ mogpe_status mogpe_profile_enable(mogpe_handle* h, int32_t on);
 mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches,
                                 int64_t* all_launches);
 /* INT8-sliced product launches (gemm_i8_sliced_kernel) of the step since the last read: device time (ms), ALGORITHMIC
- * FP64-equivalent FLOPs (every such FLOP costs 36 INT8 slice-pair MACs), launch count. */
-mogpe_status mogpe_profile_read_int8(mogpe_handle* h, double* ms, double* flops, int64_t* launches);
+ * FP64-equivalent FLOPs, launch count, and the INT8 tensor operations behind them (36 slice-pair operations per FLOP with
+ * eight slices, 28 with seven). */
+mogpe_status mogpe_profile_read_int8(mogpe_handle* h, double* ms, double* flops, int64_t* launches, double* tensor_ops);
 /* Profiling mode also times the streaming kernels alone on the caller's stream: ms[4], bytes[4] for
  * {kuf, lik, build_abar, kuf_grad} (accumulated since the last read; bytes = algorithmic bytes). */
 mogpe_status mogpe_profile_read_streaming(mogpe_handle* h, double* ms, double* bytes);

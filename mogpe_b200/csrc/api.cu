@@ -99,6 +99,12 @@ struct mogpe_handle {
   unsigned long long* t8_ltamax = nullptr;                 // [P][Mp] row maxima of LTA | [P] maxima of |dfvar| per latent
   int t8_vmax_cap = 0;
   CUtensorMap tmt_linv, tmt_linvT, tmt_st, tmt_s, tmt_kuf, tmt_at, tmt_abart, tmt_ltat;
+  // the gradient-only products (S LTA, W, Lbar, Sbar) may load only the seven most significant planes of their operands
+  // (49 bits: 28 instead of 36 slice pairs; the 1e-6 gradient tolerance has ~4 decimal digits to spare)
+  int grad_ns = 7;
+  int grad_maps_bwd_ns = 0, grad_maps_step_ns = 0;  // slice count the partial-load tensor maps were built for
+  CUtensorMap tm7_linvT, tm7_s, tm7_abart, tm7_ltat, tm7_bw, tm7_ba64, tm7_ba128, tm7_bld;
+  double prof8_ops = 0;  // INT8 tensor operations of the timed launches (36 or 28 per algorithmic FLOP)
   // INT8 product timing in profiling mode (bench.py roofline of gemm_i8_sliced_kernel)
   std::vector<cudaEvent_t> ev8;
   size_t ev8_used = 0;
@@ -1359,8 +1365,14 @@ static mogpe_status products_i8(mogpe_handle* h, const double* params, int Bc, i
 
 // INT8 product launch through the handle: counts launches and, with profiling on, brackets it with CUDA events.
 // `flops` = ALGORITHMIC FP64-equivalent work (triangular operands / results counted as triangular).
+static cudaError_t i8_launch_ns(int ns, const CUtensorMap& ma, const CUtensorMap& mb, const oz::Params& p, int n_tiles, int batch,
+                                cudaStream_t st) {
+  if (ns == 6) return oz::launch<6>(ma, mb, p, n_tiles, batch, st);
+  return ns == 7 ? oz::launch<7>(ma, mb, p, n_tiles, batch, st) : oz::launch<8>(ma, mb, p, n_tiles, batch, st);
+}
+
 static cudaError_t h_i8_launch(mogpe_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const oz::Params& p, int n_tiles,
-                               int batch, cudaStream_t st, double flops) {
+                               int batch, cudaStream_t st, double flops, int ns = 8) {
   h->gemm_launches++;
   h->i8_launches++;
   h->all_launches++;
@@ -1368,22 +1380,22 @@ static cudaError_t h_i8_launch(mogpe_handle* h, const CUtensorMap& ma, const CUt
   if (dbg) {
     oz::Params q = p;
     q.dbg = dbg;
-    if (!h->prof) return oz::launch<8>(ma, mb, q, n_tiles, batch, st);
+    if (!h->prof) return i8_launch_ns(ns, ma, mb, q, n_tiles, batch, st);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
-    cudaError_t rc = oz::launch<8>(ma, mb, q, n_tiles, batch, st);
+    cudaError_t rc = i8_launch_ns(ns, ma, mb, q, n_tiles, batch, st);
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    fprintf(stderr, "i8 product dbg=%d batch=%d kmode=%d K=%d: %.1f us\n", dbg, batch, p.kmode, p.K, ms * 1e3);
+    fprintf(stderr, "i8 product dbg=%d ns=%d batch=%d kmode=%d K=%d: %.1f us\n", dbg, ns, batch, p.kmode, p.K, ms * 1e3);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return rc;
   }
-  if (!h->prof) return oz::launch<8>(ma, mb, p, n_tiles, batch, st);
+  if (!h->prof) return i8_launch_ns(ns, ma, mb, p, n_tiles, batch, st);
   if (h->ev8_used + 2 > h->ev8.size())
     for (int i = 0; i < 32; i++) {
       cudaEvent_t e;
@@ -1393,37 +1405,46 @@ static cudaError_t h_i8_launch(mogpe_handle* h, const CUtensorMap& ma, const CUt
     }
   h->prof_stream = st;
   cudaEventRecord(h->ev8[h->ev8_used], st);
-  cudaError_t rc = oz::launch<8>(ma, mb, p, n_tiles, batch, st);
+  cudaError_t rc = i8_launch_ns(ns, ma, mb, p, n_tiles, batch, st);
   cudaEventRecord(h->ev8[h->ev8_used + 1], st);
   h->ev8_used += 2;
   h->prof8_flops += flops;
+  h->prof8_ops += flops * (ns == 6 ? 21.0 : ns == 7 ? 28.0 : 36.0);
   return rc;
 }
 
 static mogpe_status ensure_i8_bwd(mogpe_handle* h) {
-  if (h->i8_bwd_ready) return MOGPE_OK;
+  if (h->i8_bwd_ready && h->grad_maps_bwd_ns == h->grad_ns) return MOGPE_OK;
   const ModelDev& md = h->md_host;
   const int Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;
   constexpr int NS = 8;
   if (!t32::encode_fn()) return MOGPE_ERR_UNSUPPORTED;  // no TMA tensor maps: stay on the DMMA path
-  const size_t plane = (size_t)NS * Mp * Bp;
-  H_CUDA(h, dalloc(&h->bW8, Q * plane));
-  H_CUDA(h, dalloc(&h->bA8, Q * plane));
-  H_CUDA(h, dalloc(&h->bLD8, P * plane));
-  H_CUDA(h, dalloc(&h->bw_scale, (size_t)Q * Mp));
-  H_CUDA(h, dalloc(&h->ba_scale, (size_t)Q * Mp));
-  H_CUDA(h, dalloc(&h->bld_scale, (size_t)P * Mp));
-  if (!h->kuf_scale) H_CUDA(h, dalloc(&h->kuf_scale, (size_t)Q));
-  if (!h->aout_scale) H_CUDA(h, dalloc(&h->aout_scale, (size_t)Q));
-  if (!h->d_t32_err) {
-    H_CUDA(h, dalloc(&h->d_t32_err, 1));
-    H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
+  if (!h->i8_bwd_ready) {
+    const size_t plane = (size_t)NS * Mp * Bp;
+    H_CUDA(h, dalloc(&h->bW8, Q * plane));
+    H_CUDA(h, dalloc(&h->bA8, Q * plane));
+    H_CUDA(h, dalloc(&h->bLD8, P * plane));
+    H_CUDA(h, dalloc(&h->bw_scale, (size_t)Q * Mp));
+    H_CUDA(h, dalloc(&h->ba_scale, (size_t)Q * Mp));
+    H_CUDA(h, dalloc(&h->bld_scale, (size_t)P * Mp));
+    if (!h->kuf_scale) H_CUDA(h, dalloc(&h->kuf_scale, (size_t)Q));
+    if (!h->aout_scale) H_CUDA(h, dalloc(&h->aout_scale, (size_t)Q));
+    if (!h->d_t32_err) {
+      H_CUDA(h, dalloc(&h->d_t32_err, 1));
+      H_CUDA(h, cudaMemset(h->d_t32_err, 0, sizeof(int)));
+    }
+    if (!oz::make_map_i8(&h->tm_bw, h->bW8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_ba64, h->bA8, Q, Mp, Bp, oz::BN, NS) ||
+        !oz::make_map_i8(&h->tm_ba128, h->bA8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_bld, h->bLD8, P, Mp, Bp, oz::BN, NS))
+      return MOGPE_ERR_UNSUPPORTED;
+    h->i8_bwd_ready = true;
   }
-  if (!oz::make_map_i8(&h->tm_bw, h->bW8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_ba64, h->bA8, Q, Mp, Bp, oz::BN, NS) ||
-      !oz::make_map_i8(&h->tm_ba128, h->bA8, Q, Mp, Bp, oz::BM, NS) || !oz::make_map_i8(&h->tm_bld, h->bLD8, P, Mp, Bp, oz::BN, NS))
+  // maps that load only the grad_ns most significant planes of the same buffers (gradient-only products)
+  const int gs = h->grad_ns;
+  if (!oz::make_map_i8(&h->tm7_bw, h->bW8, Q, Mp, Bp, oz::BM, gs, NS) || !oz::make_map_i8(&h->tm7_ba64, h->bA8, Q, Mp, Bp, oz::BN, gs, NS) ||
+      !oz::make_map_i8(&h->tm7_ba128, h->bA8, Q, Mp, Bp, oz::BM, gs, NS) || !oz::make_map_i8(&h->tm7_bld, h->bLD8, P, Mp, Bp, oz::BN, gs, NS))
     return MOGPE_ERR_UNSUPPORTED;
+  h->grad_maps_bwd_ns = gs;
   h->graphs_dirty = true;
-  h->i8_bwd_ready = true;
   return MOGPE_OK;
 }
 
@@ -1479,7 +1500,9 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
     p.ksplit = ksplit_for(Q);
     p.err_flag = h->d_t32_err;
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
-    H_CUDA(h, h_i8_launch(h, h->tm_bw, h->tm_ba64, p, n_tiles, Q, st, (double)Q * Mp * Mp * Bc));
+    const bool g7 = h->grad_ns < 8;
+    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_bw : h->tm_bw, g7 ? h->tm7_ba64 : h->tm_ba64, p, n_tiles, Q, st, (double)Q * Mp * Mp * Bc,
+                          h->grad_ns));
   }
   if (md.nlta > 0) {
     const int nl = md.nlta;
@@ -1507,7 +1530,9 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
       p.mapB[slot] = slot;
       p.mapC[slot] = md.lta_latent[slot];
     }
-    H_CUDA(h, h_i8_launch(h, h->tm_ba128, h->tm_bld, p, n_tiles, nl, st, (double)nl * Mp * Mp * Bc));
+    const bool g7 = h->grad_ns < 8;
+    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_ba128 : h->tm_ba128, g7 ? h->tm7_bld : h->tm_bld, p, n_tiles, nl, st,
+                          (double)nl * Mp * Mp * Bc, h->grad_ns));
   }
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
@@ -1526,38 +1551,45 @@ static mogpe_status ensure_i8_step(mogpe_handle* h) {
     h->t8_vmax_cap = md.NV;
     h->graphs_dirty = true;
   }
-  if (h->i8_step_ready) return MOGPE_OK;
   mogpe_status rc = ensure_i8_bwd(h);
   if (rc != MOGPE_OK) return rc;
+  if (h->i8_step_ready && h->grad_maps_step_ns == h->grad_ns) return MOGPE_OK;
   const size_t Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;
   constexpr size_t NS = 8;
-  H_CUDA(h, dalloc(&h->t8_Linv, Q * NS * Mp * Mp));
-  H_CUDA(h, dalloc(&h->t8_LinvT, Q * NS * Mp * Mp));
-  H_CUDA(h, dalloc(&h->t8_ST, P * NS * Mp * Mp));
-  H_CUDA(h, dalloc(&h->t8_S, P * NS * Mp * Mp));
-  H_CUDA(h, dalloc(&h->t8_KufT, Q * NS * Bp * Mp));
-  H_CUDA(h, dalloc(&h->t8_AT, Q * NS * Bp * Mp));
-  H_CUDA(h, dalloc(&h->t8_AbarT, Q * NS * Bp * Mp));
-  H_CUDA(h, dalloc(&h->t8_LTAT, P * NS * Bp * Mp));
-  H_CUDA(h, dalloc(&h->t8_linv_scale, Q * Mp));
-  H_CUDA(h, dalloc(&h->t8_linvT_scale, Q * Mp));
-  H_CUDA(h, dalloc(&h->t8_st_scale, P * Mp));
-  H_CUDA(h, dalloc(&h->t8_s_scale, P * Mp));
-  H_CUDA(h, dalloc(&h->t8_lta_scale, P));
-  H_CUDA(h, dalloc(&h->t8_srowmax, P));
-  H_CUDA(h, dalloc(&h->t8_nscale, Q * Bp));
-  H_CUDA(h, dalloc(&h->t8_P2, P * Mp * Bp));
-  H_CUDA(h, dalloc(&h->t8_wmax, Q * Mp));
-  H_CUDA(h, dalloc(&h->t8_ltamax, P * Mp + P));
-  if (!h->alpha) H_CUDA(h, dalloc(&h->alpha, P * MOGPE_MAX_SAMPLES * (size_t)h->Mp32));
   const int q = (int)Q, pp = (int)P, m = (int)Mp, b = (int)Bp;
-  if (!oz::make_map_i8(&h->tmt_linv, h->t8_Linv, q, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_linvT, h->t8_LinvT, q, m, m, oz::BM) ||
-      !oz::make_map_i8(&h->tmt_st, h->t8_ST, pp, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_s, h->t8_S, pp, m, m, oz::BM) ||
-      !oz::make_map_i8(&h->tmt_kuf, h->t8_KufT, q, b, m, oz::BN) || !oz::make_map_i8(&h->tmt_at, h->t8_AT, q, b, m, oz::BN) ||
-      !oz::make_map_i8(&h->tmt_abart, h->t8_AbarT, q, b, m, oz::BN) || !oz::make_map_i8(&h->tmt_ltat, h->t8_LTAT, pp, b, m, oz::BN))
+  if (!h->i8_step_ready) {
+    H_CUDA(h, dalloc(&h->t8_Linv, Q * NS * Mp * Mp));
+    H_CUDA(h, dalloc(&h->t8_LinvT, Q * NS * Mp * Mp));
+    H_CUDA(h, dalloc(&h->t8_ST, P * NS * Mp * Mp));
+    H_CUDA(h, dalloc(&h->t8_S, P * NS * Mp * Mp));
+    H_CUDA(h, dalloc(&h->t8_KufT, Q * NS * Bp * Mp));
+    H_CUDA(h, dalloc(&h->t8_AT, Q * NS * Bp * Mp));
+    H_CUDA(h, dalloc(&h->t8_AbarT, Q * NS * Bp * Mp));
+    H_CUDA(h, dalloc(&h->t8_LTAT, P * NS * Bp * Mp));
+    H_CUDA(h, dalloc(&h->t8_linv_scale, Q * Mp));
+    H_CUDA(h, dalloc(&h->t8_linvT_scale, Q * Mp));
+    H_CUDA(h, dalloc(&h->t8_st_scale, P * Mp));
+    H_CUDA(h, dalloc(&h->t8_s_scale, P * Mp));
+    H_CUDA(h, dalloc(&h->t8_lta_scale, P));
+    H_CUDA(h, dalloc(&h->t8_srowmax, P));
+    H_CUDA(h, dalloc(&h->t8_nscale, Q * Bp));
+    H_CUDA(h, dalloc(&h->t8_P2, P * Mp * Bp));
+    H_CUDA(h, dalloc(&h->t8_wmax, Q * Mp));
+    H_CUDA(h, dalloc(&h->t8_ltamax, P * Mp + P));
+    if (!h->alpha) H_CUDA(h, dalloc(&h->alpha, P * MOGPE_MAX_SAMPLES * (size_t)h->Mp32));
+    if (!oz::make_map_i8(&h->tmt_linv, h->t8_Linv, q, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_linvT, h->t8_LinvT, q, m, m, oz::BM) ||
+        !oz::make_map_i8(&h->tmt_st, h->t8_ST, pp, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_s, h->t8_S, pp, m, m, oz::BM) ||
+        !oz::make_map_i8(&h->tmt_kuf, h->t8_KufT, q, b, m, oz::BN) || !oz::make_map_i8(&h->tmt_at, h->t8_AT, q, b, m, oz::BN) ||
+        !oz::make_map_i8(&h->tmt_abart, h->t8_AbarT, q, b, m, oz::BN) || !oz::make_map_i8(&h->tmt_ltat, h->t8_LTAT, pp, b, m, oz::BN))
+      return MOGPE_ERR_UNSUPPORTED;
+    h->i8_step_ready = true;
+  }
+  const int gs = h->grad_ns;
+  if (!oz::make_map_i8(&h->tm7_linvT, h->t8_LinvT, q, m, m, oz::BM, gs, 8) || !oz::make_map_i8(&h->tm7_s, h->t8_S, pp, m, m, oz::BM, gs, 8) ||
+      !oz::make_map_i8(&h->tm7_abart, h->t8_AbarT, q, b, m, oz::BN, gs, 8) || !oz::make_map_i8(&h->tm7_ltat, h->t8_LTAT, pp, b, m, oz::BN, gs, 8))
     return MOGPE_ERR_UNSUPPORTED;
+  h->grad_maps_step_ns = gs;
   h->graphs_dirty = true;
-  h->i8_step_ready = true;
   return MOGPE_OK;
 }
 
@@ -1680,7 +1712,9 @@ static mogpe_status i8_step_backward_to_W(mogpe_handle* h, int N, int Bc, cudaSt
     p.err_flag = h->d_t32_err;
     p.out64 = h->t8_P2; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
     for (int slot = 0; slot < nl; slot++) p.mapA[slot] = p.mapB[slot] = p.mapC[slot] = slot;
-    H_CUDA(h, h_i8_launch(h, h->tmt_s, h->tmt_ltat, p, Bc / oz::BN, nl, st, (double)nl * Mp * Mp * Bc));
+    const bool g7 = h->grad_ns < 8;
+    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_s : h->tmt_s, g7 ? h->tm7_ltat : h->tmt_ltat, p, Bc / oz::BN, nl, st,
+                          (double)nl * Mp * Mp * Bc, h->grad_ns));
   }
   sk_begin(h, SK_ABAR, st);
   oz::abar8_kernel<NS><<<dim3(Bc / 64, Mp / 64, Q), 256, 0, st>>>(h->d_md, h->bA8, h->aout_scale, h->V, h->dmean, h->dfvar, h->var0ss,
@@ -1699,7 +1733,9 @@ static mogpe_status i8_step_backward_to_W(mogpe_handle* h, int N, int Bc, cudaSt
     p.out64 = h->W; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
     p.rowmax64 = h->t8_wmax; p.rowmax64_stride = Mp;
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
-    H_CUDA(h, h_i8_launch(h, h->tmt_linvT, h->tmt_abart, p, Bc / oz::BN, Q, st, (double)Q * Mp * Mp * Bc));
+    const bool g7 = h->grad_ns < 8;
+    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_linvT : h->tmt_linvT, g7 ? h->tm7_abart : h->tmt_abart, p, Bc / oz::BN, Q, st,
+                          (double)Q * Mp * Mp * Bc, h->grad_ns));
   }
   return MOGPE_OK;
 }
@@ -1978,6 +2014,14 @@ extern "C" mogpe_status mogpe_set_int8_step(mogpe_handle* h, int32_t on) {
   return MOGPE_OK;
 }
 
+extern "C" mogpe_status mogpe_set_int8_grad_slices(mogpe_handle* h, int32_t slices) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (slices < 6 || slices > 8) H_FAIL(h, MOGPE_ERR_INVALID, "gradient-only INT8 products use 6, 7 or 8 byte slices");
+  h->grad_ns = slices;
+  h->graphs_dirty = true;
+  return MOGPE_OK;
+}
+
 extern "C" mogpe_status mogpe_set_dp_overlap(mogpe_handle* h, int32_t on) {
   if (!h) return MOGPE_ERR_INVALID;
   if (on && !h->nccl_comm) H_FAIL(h, MOGPE_ERR_NCCL, "mogpe_comm_init has not been called on this handle");
@@ -2056,6 +2100,7 @@ extern "C" mogpe_status mogpe_profile_enable(mogpe_handle* h, int32_t on) {
   h->prof_flops = 0;
   h->ev8_used = 0;
   h->prof8_flops = 0;
+  h->prof8_ops = 0;
   h->i8_launches = 0;
   for (int i = 0; i < mogpe_handle::NSK; i++) {
     h->sk_used[i] = 0;
@@ -2086,7 +2131,8 @@ extern "C" mogpe_status mogpe_profile_read(mogpe_handle* h, double* gemm_ms, dou
   return MOGPE_OK;
 }
 
-extern "C" mogpe_status mogpe_profile_read_int8(mogpe_handle* h, double* ms_out, double* flops, int64_t* launches) {
+extern "C" mogpe_status mogpe_profile_read_int8(mogpe_handle* h, double* ms_out, double* flops, int64_t* launches,
+                                                double* tensor_ops) {
   if (!h) return MOGPE_ERR_INVALID;
   H_CUDA(h, cudaSetDevice(h->device));
   if (h->prof_stream || h->ev8_used) H_CUDA(h, cudaStreamSynchronize(h->prof_stream));
@@ -2099,8 +2145,10 @@ extern "C" mogpe_status mogpe_profile_read_int8(mogpe_handle* h, double* ms_out,
   if (ms_out) *ms_out = ms;
   if (flops) *flops = h->prof8_flops;
   if (launches) *launches = h->i8_launches;
+  if (tensor_ops) *tensor_ops = h->prof8_ops;
   h->ev8_used = 0;
   h->prof8_flops = 0;
+  h->prof8_ops = 0;
   h->i8_launches = 0;
   return MOGPE_OK;
 }

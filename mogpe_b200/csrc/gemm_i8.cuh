@@ -30,7 +30,8 @@
 namespace mogpe {
 namespace oz {
 
-// NS = byte slices per operand (template parameter): 8 -> 56 significant bits, FP64-class (the 1e-8 tolerance); 6 -> 42 bits,
+// NS = byte slices per operand (template parameter): 8 -> 56 significant bits, FP64-class (the 1e-8 tolerance); 7 -> 49 bits
+// (gradient-only products of the training step: 28 instead of 36 slice pairs, no plane outputs); 6 -> 42 bits,
 // ~1e-7-class (the 1e-4 "fast mode" tolerance with a wide margin even for cond(L) ~ 1e3) at 21 instead of 36 slice pairs.
 constexpr int MAX_NS = 8;
 constexpr int BM = 128, BN = 64, BKB = 64, UKB = 32, STAGES = 2;
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
         for (int i = 0; i < 32; i++)
           if (!p.tril64 || n0 + c * 32 + i <= row) atomicAdd(o + i, p.alpha64 * v[i]);
       }
+      if constexpr (NS % 2 == 0)
       if ((p.out || p.outn) && !(p.dbg & 4)) {
         // Re-slicing of the tile into byte planes, once for both layouts.  Every element becomes two words of four signed
         // digit bytes (planes 0..3 and 4..7, byte 3 = the more significant plane); 4 x 4 byte transposes (PRMT) turn four
@@ -635,11 +637,14 @@ __global__ void __launch_bounds__(64, 1) i8_issue_probe_kernel(int iters, int* s
 }
 
 // byte planes [batch][NS][rows][cols] (cols = k contiguous): box {64 k, box_rows, NS planes, 1}, 64B swizzle
-inline bool make_map_i8(CUtensorMap* map, const int8_t* ptr, int batch, int rows, int cols, int box_rows, int NS = MAX_NS) {
+// planes_total: byte planes the buffer holds per batch (0 = NS); a product may load only the NS most significant of them
+inline bool make_map_i8(CUtensorMap* map, const int8_t* ptr, int batch, int rows, int cols, int box_rows, int NS = MAX_NS,
+                        int planes_total = 0) {
   t32::EncodeTiledFn fn = t32::encode_fn();
   if (!fn) return false;
+  if (planes_total <= 0) planes_total = NS;
   cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)NS, (cuuint64_t)batch};
-  cuuint64_t strides[3] = {(cuuint64_t)cols, (cuuint64_t)rows * cols, (cuuint64_t)NS * rows * cols};
+  cuuint64_t strides[3] = {(cuuint64_t)cols, (cuuint64_t)rows * cols, (cuuint64_t)planes_total * rows * cols};
   cuuint32_t box[4] = {BKB, (cuuint32_t)box_rows, (cuuint32_t)NS, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(ptr), dims, strides, box, es,

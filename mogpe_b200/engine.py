@@ -425,9 +425,13 @@ class Engine:
         _lib.check(self.lib.mogpe_set_int8_step(self.h, 1 if on else 0), self.h)
 
     def profile_read_int8(self):
-        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
-        _lib.check(self.lib.mogpe_profile_read_int8(self.h, C.byref(ms), C.byref(fl), C.byref(n)), self.h)
-        return {"ms": ms.value, "flops": fl.value, "launches": n.value}
+        ms, fl, n, ops = C.c_double(), C.c_double(), C.c_int64(), C.c_double()
+        _lib.check(self.lib.mogpe_profile_read_int8(self.h, C.byref(ms), C.byref(fl), C.byref(n), C.byref(ops)), self.h)
+        return {"ms": ms.value, "flops": fl.value, "launches": n.value, "tensor_ops": ops.value}
+
+    def set_int8_grad_slices(self, slices: int):
+        """Byte slices of the gradient-only INT8 products (S LTA, W, Lbar, Sbar): 7 (default) or 8."""
+        _lib.check(self.lib.mogpe_set_int8_grad_slices(self.h, int(slices)), self.h)
 
     def graph_stats(self):
         """-> (captured training-step graphs, capture disabled after a failure)."""

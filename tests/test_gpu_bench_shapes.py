@@ -77,22 +77,25 @@ def test_mid_size_bench_shapes_match_oracle(name, oracle_cache):
     eng.close()
 
 
-@pytest.mark.parametrize("mode", ["int8_step", "int8_backward", "fp64"])
+@pytest.mark.parametrize("mode", ["int8_step", "int8_step_8", "int8_step_6", "int8_backward", "fp64"])
 def test_c4_bench_shape_matches_oracle(mode, oracle_cache):
     """C4 (the headline workload): D = 4, K = 8, G = 8 Softmax, 16 kernel groups, M = 512, 8192 rows, in the three arithmetic
-    modes of a gradient step: every dense product on the INT8 tensor cores (what bench.py times), only the two
-    minibatch-reduced products of the backward there, and all-FP64 DMMA."""
+    modes of a gradient step: every dense product on the INT8 tensor cores (what bench.py times; the four gradient-only products
+    with the default seven byte slices, with eight and with six), only the two minibatch-reduced products of the backward there,
+    and all-FP64 DMMA."""
     from tests._engine_helpers import engine_from_spec, run_engine_elbo
 
     wl, spec, X, Y, eps, val, grads_u = _oracle("C4", oracle_cache)
     eng = engine_from_spec(spec, max_batch=wl["batch"])
-    eng.set_int8_step(mode == "int8_step")
+    eng.set_int8_step(mode.startswith("int8_step"))
     eng.set_int8_backward(mode != "fp64")
+    if mode.startswith("int8_step_"):  # byte slices of the gradient-only products (default 7)
+        eng.set_int8_grad_slices(int(mode[-1]))
     eng.profile(True)
     res = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=True)
     i8 = eng.profile_read_int8()["launches"]
     eng.profile(False)
-    assert i8 == {"int8_step": 6, "int8_backward": 2, "fp64": 0}[mode]  # the mode under test really ran
+    assert i8 == {"int8_step": 6, "int8_step_8": 6, "int8_step_6": 6, "int8_backward": 2, "fp64": 0}[mode]  # the mode under test really ran
     _compare(spec, res, val, grads_u, f"C4 {mode}")
     # a second call on the same handle (scratch reuse, second random-stream position) reproduces the result to rounding
     res2 = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=True)
