@@ -345,6 +345,8 @@ def main():
                          "(SURVEY 8d: 65536 rows for C4) split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
+    ap.add_argument("--fast", action="store_true",
+                    help="fast training mode (north_star's 1e-4 class): six byte slices in every INT8 product; NOT the headline")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -399,6 +401,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     experts, gating = blocks_from_spec(spec)
     eng = Engine(experts, gating, flavour=FLAVOUR, max_batch=B, device=local_rank)
+    if args.fast:
+        eng.set_int8_forward_slices(6)
+        cfg["arithmetic"] = "fast mode: six byte slices (42 bits) in every INT8 product -- the 1e-4 class, not float64 parity"
     eng.set_seed(1234)  # one seed for the job: inducing draws are shared between the ranks, per-point draws are per rank
     if world > 1:
         ids = [Engine.nccl_unique_id() if rank == 0 else None]
@@ -469,6 +474,8 @@ def main():
     del eng, dev_batches
     model = build_public_model(spec, wl, device=local_rank)
     model.set_seed(4321)
+    if args.fast:
+        model.set_fast_training(True)
     if world > 1:
         ids2 = [Engine.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids2, src=0)

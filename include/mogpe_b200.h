@@ -211,9 +211,17 @@ mogpe_status mogpe_set_int8_backward(mogpe_handle* h, int32_t on);
  * tf.GradientTape (mogpe/keras/gps.py:31-48, mogpe/keras/mixture_of_experts/mosvgpe.py:57-69). */
 mogpe_status mogpe_set_int8_step(mogpe_handle* h, int32_t on);
 /* Byte slices loaded by the GRADIENT-ONLY products of the INT8 step (S LTA, W = L^-T Abar, Lbar, Sbar): 7 (default: the
- * seven most significant planes, 49 bits, 28 slice pairs) or 8 (56 bits, 36 pairs).  The forward products, whose results
- * enter the ELBO (1e-8), always use eight. */
+ * seven most significant planes, 49 bits, 28 slice pairs), 8 (56 bits, 36 pairs) or 6; never more than the forward products
+ * load (mogpe_set_int8_forward_slices). */
 mogpe_status mogpe_set_int8_grad_slices(mogpe_handle* h, int32_t slices);
+/* Byte slices loaded by the two FORWARD products of the INT8 step (A = L^-1 Kuf, S^T A), whose results enter the ELBO:
+ * 8 (default: 56 bits, 36 slice pairs), 7 (49 bits, 28 pairs: still float64-class -- ELBO within 1.1e-10, gradients within
+ * 1.6e-8 of the FP64 step on the ill-conditioned stress model of tests/test_gpu_engine.py -- but only 0.07 ms faster at the
+ * bench shape, so opt-in), or 6 = FAST TRAINING MODE, the "1e-4 class" BASELINE.json's north_star allows beside float64:
+ * 42 bits, 21 slice pairs, and the gradient-only products are capped at six as well (4.55 instead of 5.1 ms/step at C4).
+ * Measured in fast mode: ELBO within 4e-9, gradients within 1.1e-6 of the float64 step
+ * (profiles/i8_grad_slices_accuracy_r02.log); tests/test_gpu_bench_shapes.py holds it to 1e-5 / 1e-4. */
+mogpe_status mogpe_set_int8_forward_slices(mogpe_handle* h, int32_t slices);
 
 /* on != 0: mogpe_elbo_fwd_bwd performs the data-parallel reduction itself and returns globally summed gradients and
  * results -- the part of the gradient buffer that is final before the Cholesky backward (q_mu, q_sqrt, mean, noise and, when

@@ -71,6 +71,7 @@ _PROTOS = {
     "mogpe_set_int8_step": (C.c_int, [_P, C.c_int32]),
     "mogpe_profile_read_int8": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "mogpe_set_int8_grad_slices": (C.c_int, [_P, C.c_int32]),
+    "mogpe_set_int8_forward_slices": (C.c_int, [_P, C.c_int32]),
     "mogpe_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mogpe_profile_read_streaming": (C.c_int, [_P, _P, _P]),
     "mogpe_opt_setup": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_double]),

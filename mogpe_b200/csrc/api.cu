@@ -92,6 +92,7 @@ struct mogpe_handle {
   double *t8_linv_scale = nullptr, *t8_linvT_scale = nullptr;  // [Q][Mp] row scales
   double *t8_st_scale = nullptr, *t8_s_scale = nullptr;        // [P][Mp]
   double *t8_lta_scale = nullptr, *t8_srowmax = nullptr, *t8_vmax = nullptr;  // [P] (slot), [P] (latent), [NVcap]
+  double* t8_xs = nullptr;                                 // [Q][Bp][4 | 16] inputs in every group's length scales
   double* t8_nscale = nullptr;                             // [Q][Bp] column scales of Abar
   double* t8_P2 = nullptr;                                 // [P][Mp][Bp] FP64: S_l LTA_l per LTA slot
   unsigned long long* t8_wmax = nullptr;                   // [Q][Mp] row maxima of W (bit patterns)
@@ -104,6 +105,13 @@ struct mogpe_handle {
   int grad_ns = 7;
   int grad_maps_bwd_ns = 0, grad_maps_step_ns = 0;  // slice count the partial-load tensor maps were built for
   CUtensorMap tm7_linvT, tm7_s, tm7_abart, tm7_ltat, tm7_bw, tm7_ba64, tm7_ba128, tm7_bld;
+  // slices loaded by the two forward products (A = L^-1 Kuf, S^T A): 8 by default; 7 is measured float64-class as well (ELBO
+  // 1e-10, gradients 1.6e-8 of the FP64 step on the ill-conditioned stress model) but buys only 0.07 ms at C4 for 16x less
+  // gradient margin, so it is opt-in; 6 = fast training mode (the "1e-4 class" of north_star), which also caps the
+  // gradient-only products at six
+  int fwd_ns = 8, fwd_maps_ns = 0;
+  CUtensorMap tmf_linv, tmf_kuf, tmf_st, tmf_at;
+  int gns() const { return grad_ns < fwd_ns ? grad_ns : fwd_ns; }
   double prof8_ops = 0;  // INT8 tensor operations of the timed launches (36 or 28 per algorithmic FLOP)
   // INT8 product timing in profiling mode (bench.py roofline of gemm_i8_sliced_kernel)
   std::vector<cudaEvent_t> ev8;
@@ -259,7 +267,7 @@ static void free_ws(mogpe_handle* h) {
   for (void* q : {(void*)h->t8_Linv, (void*)h->t8_LinvT, (void*)h->t8_ST, (void*)h->t8_S, (void*)h->t8_KufT, (void*)h->t8_AT,
                   (void*)h->t8_AbarT, (void*)h->t8_LTAT, (void*)h->t8_linv_scale, (void*)h->t8_linvT_scale, (void*)h->t8_st_scale,
                   (void*)h->t8_s_scale, (void*)h->t8_lta_scale, (void*)h->t8_srowmax, (void*)h->t8_vmax, (void*)h->t8_nscale,
-                  (void*)h->t8_P2, (void*)h->t8_wmax, (void*)h->t8_bound_bits, (void*)h->t8_ltamax})
+                  (void*)h->t8_P2, (void*)h->t8_wmax, (void*)h->t8_bound_bits, (void*)h->t8_ltamax, (void*)h->t8_xs})
     if (q) cudaFree(q);
   for (auto e : h->ev8) cudaEventDestroy(e);
   h->ev8.clear();
@@ -951,10 +959,11 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
       const int n_chunk8 = round_up((Bc + nsplit - 1) / nsplit, 128);
       const int nsplit8 = (Bc + n_chunk8 - 1) / n_chunk8;
       const dim3 kgrid(Mp / 8, Q, nsplit8);
+      // (t8_xs: the inputs in every group's length scales, written by xs_prep_kernel in the forward of this step)
       if (md.D <= 4)
-        oz::kuf_grad_slice_kernel<4, 8><<<kgrid, 256, 0, ks>>>(h->d_md, params, lo, X, N, Bc, Bp, h->W, h->t8_wmax, grads, h->bW8, h->bw_scale, n_chunk8);
+        oz::kuf_grad_slice_kernel<4, 8><<<kgrid, 256, 0, ks>>>(h->d_md, params, lo, h->t8_xs, Bc, Bp, h->W, h->t8_wmax, grads, h->bW8, h->bw_scale, n_chunk8);
       else
-        oz::kuf_grad_slice_kernel<16, 8><<<kgrid, 256, 0, ks>>>(h->d_md, params, lo, X, N, Bc, Bp, h->W, h->t8_wmax, grads, h->bW8, h->bw_scale, n_chunk8);
+        oz::kuf_grad_slice_kernel<16, 8><<<kgrid, 256, 0, ks>>>(h->d_md, params, lo, h->t8_xs, Bc, Bp, h->W, h->t8_wmax, grads, h->bW8, h->bw_scale, n_chunk8);
     } else if (md.D <= 4)
       kuf_grad_kernel<4, 1><<<dim3(Mp / 8, Q, nsplit), 256, 0, ks>>>(h->d_md, params, lo, X, N, Bp, h->W, h->Kuf, grads, n_chunk);
     else
@@ -1414,7 +1423,7 @@ static cudaError_t h_i8_launch(mogpe_handle* h, const CUtensorMap& ma, const CUt
 }
 
 static mogpe_status ensure_i8_bwd(mogpe_handle* h) {
-  if (h->i8_bwd_ready && h->grad_maps_bwd_ns == h->grad_ns) return MOGPE_OK;
+  if (h->i8_bwd_ready && h->grad_maps_bwd_ns == h->gns()) return MOGPE_OK;
   const ModelDev& md = h->md_host;
   const int Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;
   constexpr int NS = 8;
@@ -1439,7 +1448,7 @@ static mogpe_status ensure_i8_bwd(mogpe_handle* h) {
     h->i8_bwd_ready = true;
   }
   // maps that load only the grad_ns most significant planes of the same buffers (gradient-only products)
-  const int gs = h->grad_ns;
+  const int gs = h->gns();
   if (!oz::make_map_i8(&h->tm7_bw, h->bW8, Q, Mp, Bp, oz::BM, gs, NS) || !oz::make_map_i8(&h->tm7_ba64, h->bA8, Q, Mp, Bp, oz::BN, gs, NS) ||
       !oz::make_map_i8(&h->tm7_ba128, h->bA8, Q, Mp, Bp, oz::BM, gs, NS) || !oz::make_map_i8(&h->tm7_bld, h->bLD8, P, Mp, Bp, oz::BN, gs, NS))
     return MOGPE_ERR_UNSUPPORTED;
@@ -1500,9 +1509,9 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
     p.ksplit = ksplit_for(Q);
     p.err_flag = h->d_t32_err;
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
-    const bool g7 = h->grad_ns < 8;
+    const bool g7 = h->gns() < 8;
     H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_bw : h->tm_bw, g7 ? h->tm7_ba64 : h->tm_ba64, p, n_tiles, Q, st, (double)Q * Mp * Mp * Bc,
-                          h->grad_ns));
+                          h->gns()));
   }
   if (md.nlta > 0) {
     const int nl = md.nlta;
@@ -1530,9 +1539,9 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
       p.mapB[slot] = slot;
       p.mapC[slot] = md.lta_latent[slot];
     }
-    const bool g7 = h->grad_ns < 8;
+    const bool g7 = h->gns() < 8;
     H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_ba128 : h->tm_ba128, g7 ? h->tm7_bld : h->tm_bld, p, n_tiles, nl, st,
-                          (double)nl * Mp * Mp * Bc, h->grad_ns));
+                          (double)nl * Mp * Mp * Bc, h->gns()));
   }
   H_CUDA(h, cudaGetLastError());
   return MOGPE_OK;
@@ -1553,7 +1562,7 @@ static mogpe_status ensure_i8_step(mogpe_handle* h) {
   }
   mogpe_status rc = ensure_i8_bwd(h);
   if (rc != MOGPE_OK) return rc;
-  if (h->i8_step_ready && h->grad_maps_step_ns == h->grad_ns) return MOGPE_OK;
+  if (h->i8_step_ready && h->grad_maps_step_ns == h->gns() && h->fwd_maps_ns == h->fwd_ns) return MOGPE_OK;
   const size_t Q = md.Q, P = md.P, Mp = h->Mp, Bp = h->Bp;
   constexpr size_t NS = 8;
   const int q = (int)Q, pp = (int)P, m = (int)Mp, b = (int)Bp;
@@ -1573,6 +1582,7 @@ static mogpe_status ensure_i8_step(mogpe_handle* h) {
     H_CUDA(h, dalloc(&h->t8_lta_scale, P));
     H_CUDA(h, dalloc(&h->t8_srowmax, P));
     H_CUDA(h, dalloc(&h->t8_nscale, Q * Bp));
+    H_CUDA(h, dalloc(&h->t8_xs, Q * Bp * (md.D <= 4 ? 4 : 16)));
     H_CUDA(h, dalloc(&h->t8_P2, P * Mp * Bp));
     H_CUDA(h, dalloc(&h->t8_wmax, Q * Mp));
     H_CUDA(h, dalloc(&h->t8_ltamax, P * Mp + P));
@@ -1584,11 +1594,29 @@ static mogpe_status ensure_i8_step(mogpe_handle* h) {
       return MOGPE_ERR_UNSUPPORTED;
     h->i8_step_ready = true;
   }
-  const int gs = h->grad_ns;
+  const int gs = h->gns();
   if (!oz::make_map_i8(&h->tm7_linvT, h->t8_LinvT, q, m, m, oz::BM, gs, 8) || !oz::make_map_i8(&h->tm7_s, h->t8_S, pp, m, m, oz::BM, gs, 8) ||
       !oz::make_map_i8(&h->tm7_abart, h->t8_AbarT, q, b, m, oz::BN, gs, 8) || !oz::make_map_i8(&h->tm7_ltat, h->t8_LTAT, pp, b, m, oz::BN, gs, 8))
     return MOGPE_ERR_UNSUPPORTED;
   h->grad_maps_step_ns = gs;
+  if (h->fwd_maps_ns != h->fwd_ns) {
+    const int fs = h->fwd_ns;
+    if (fs < 8) {
+      if (!oz::make_map_i8(&h->tmf_linv, h->t8_Linv, q, m, m, oz::BM, fs, 8) || !oz::make_map_i8(&h->tmf_st, h->t8_ST, pp, m, m, oz::BM, fs, 8) ||
+          !oz::make_map_i8(&h->tmf_kuf, h->t8_KufT, q, b, m, oz::BN, fs, 8) || !oz::make_map_i8(&h->tmf_at, h->t8_AT, q, b, m, oz::BN, fs, 8))
+        return MOGPE_ERR_UNSUPPORTED;
+    }
+    if (fs == 6) {
+      // a six-slice product writes six planes of its re-sliced result; the consumers read eight-plane operands, so the two least
+      // significant planes are cleared once here and stay zero for as long as this mode is on
+      H_CUDA(h, cudaDeviceSynchronize());
+      H_CUDA(h, cudaMemset(h->t8_AT, 0, Q * NS * Bp * Mp));
+      H_CUDA(h, cudaMemset(h->t8_LTAT, 0, P * NS * Bp * Mp));
+      H_CUDA(h, cudaMemset(h->bA8, 0, Q * NS * Mp * Bp));
+      H_CUDA(h, cudaDeviceSynchronize());
+    }
+    h->fwd_maps_ns = h->fwd_ns;
+  }
   h->graphs_dirty = true;
   return MOGPE_OK;
 }
@@ -1618,7 +1646,10 @@ static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const
 #undef MOGPE_KUF8T
     // algorithmic bytes: Kuf as byte planes (8 B per element, as FP64), X and Z in
     sk_end(h, SK_KUF, ks, 8.0 * Q * ((double)Mp * N + (double)N * md.D + (double)Mp * md.D));
-    KCOUNT(h, 1);
+    // the inputs in every group's length scales, for the Kuf gradients of the backward (kuf_grad_slice_kernel)
+    if (md.D <= 4) oz::xs_prep_kernel<4><<<dim3((Bp + 255) / 256, Q), 256, 0, ks>>>(h->d_md, params, h->lo, X, N, Bp, h->t8_xs);
+    else oz::xs_prep_kernel<16><<<dim3((Bp + 255) / 256, Q), 256, 0, ks>>>(h->d_md, params, h->lo, X, N, Bp, h->t8_xs);
+    KCOUNT(h, 2);
   };
   if (kuf_aside) {
     H_CUDA(h, side_fork(h, st));  // after group_scales; factorise() forks again (harmless) and joins
@@ -1669,7 +1700,9 @@ static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const
     }
     p.outn = h->bA8; p.outn_batch_stride = (long long)NS * Mp * Bp; p.outn_plane_stride = (long long)Mp * Bp; p.ldn = Bp;
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
-    H_CUDA(h, h_i8_launch(h, h->tmt_linv, h->tmt_kuf, p, Bc / oz::BN, Q, st, (double)Q * Mp * Mp * Bc));
+    const bool f6 = h->fwd_ns < 8;
+    H_CUDA(h, h_i8_launch(h, f6 ? h->tmf_linv : h->tmt_linv, f6 ? h->tmf_kuf : h->tmt_kuf, p, Bc / oz::BN, Q, st,
+                          (double)Q * Mp * Mp * Bc, h->fwd_ns));
   }
   if (nl > 0) {  // LTA_l = S_l^T A
     oz::Params p;
@@ -1687,7 +1720,9 @@ static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const
       p.mapB[slot] = md.lta_group[slot];
       p.mapC[slot] = slot;
     }
-    H_CUDA(h, h_i8_launch(h, h->tmt_st, h->tmt_at, p, Bc / oz::BN, nl, st, (double)nl * Mp * Mp * Bc));
+    const bool f6 = h->fwd_ns < 8;
+    H_CUDA(h, h_i8_launch(h, f6 ? h->tmf_st : h->tmt_st, f6 ? h->tmf_at : h->tmt_at, p, Bc / oz::BN, nl, st,
+                          (double)nl * Mp * Mp * Bc, h->fwd_ns));
   }
   KCOUNT(h, 1);
   stats_finish_kernel<<<dim3(Bc / 128, Q + md.NV + nl), 128, 0, st>>>(h->d_md, params, h->lo, h->ss_part, h->dot_part, h->lta_part,
@@ -1712,9 +1747,9 @@ static mogpe_status i8_step_backward_to_W(mogpe_handle* h, int N, int Bc, cudaSt
     p.err_flag = h->d_t32_err;
     p.out64 = h->t8_P2; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
     for (int slot = 0; slot < nl; slot++) p.mapA[slot] = p.mapB[slot] = p.mapC[slot] = slot;
-    const bool g7 = h->grad_ns < 8;
+    const bool g7 = h->gns() < 8;
     H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_s : h->tmt_s, g7 ? h->tm7_ltat : h->tmt_ltat, p, Bc / oz::BN, nl, st,
-                          (double)nl * Mp * Mp * Bc, h->grad_ns));
+                          (double)nl * Mp * Mp * Bc, h->gns()));
   }
   sk_begin(h, SK_ABAR, st);
   oz::abar8_kernel<NS><<<dim3(Bc / 64, Mp / 64, Q), 256, 0, st>>>(h->d_md, h->bA8, h->aout_scale, h->V, h->dmean, h->dfvar, h->var0ss,
@@ -1733,9 +1768,9 @@ static mogpe_status i8_step_backward_to_W(mogpe_handle* h, int N, int Bc, cudaSt
     p.out64 = h->W; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
     p.rowmax64 = h->t8_wmax; p.rowmax64_stride = Mp;
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
-    const bool g7 = h->grad_ns < 8;
+    const bool g7 = h->gns() < 8;
     H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_linvT : h->tmt_linvT, g7 ? h->tm7_abart : h->tmt_abart, p, Bc / oz::BN, Q, st,
-                          (double)Q * Mp * Mp * Bc, h->grad_ns));
+                          (double)Q * Mp * Mp * Bc, h->gns()));
   }
   return MOGPE_OK;
 }
@@ -2018,6 +2053,14 @@ extern "C" mogpe_status mogpe_set_int8_grad_slices(mogpe_handle* h, int32_t slic
   if (!h) return MOGPE_ERR_INVALID;
   if (slices < 6 || slices > 8) H_FAIL(h, MOGPE_ERR_INVALID, "gradient-only INT8 products use 6, 7 or 8 byte slices");
   h->grad_ns = slices;
+  h->graphs_dirty = true;
+  return MOGPE_OK;
+}
+
+extern "C" mogpe_status mogpe_set_int8_forward_slices(mogpe_handle* h, int32_t slices) {
+  if (!h) return MOGPE_ERR_INVALID;
+  if (slices < 6 || slices > 8) H_FAIL(h, MOGPE_ERR_INVALID, "the forward INT8 products use 6, 7 or 8 byte slices");
+  h->fwd_ns = slices;
   h->graphs_dirty = true;
   return MOGPE_OK;
 }

@@ -467,8 +467,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
         for (int i = 0; i < 32; i++)
           if (!p.tril64 || n0 + c * 32 + i <= row) atomicAdd(o + i, p.alpha64 * v[i]);
       }
-      if constexpr (NS % 2 == 0)
       if ((p.out || p.outn) && !(p.dbg & 4)) {
+        // (ONS planes: eight for a product that loaded seven -- the consumers read eight-plane operands, and a 49-bit result
+        // written as eight digits costs the same stores -- otherwise as many as were loaded)
+        constexpr int ONS = NS == 6 ? 6 : 8;
         // Re-slicing of the tile into byte planes, once for both layouts.  Every element becomes two words of four signed
         // digit bytes (planes 0..3 and 4..7, byte 3 = the more significant plane); 4 x 4 byte transposes (PRMT) turn four
         // consecutive columns into the [m][n] plane words (`outn`, 16-byte stores of this thread's row), and the transposed
@@ -479,12 +481,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
         int8_t* orow = nullptr;  // [m][n] planes: this thread's row, 32 consecutive columns
         if (p.outn) orow = p.outn + (long long)batch * p.outn_batch_stride + (long long)row * p.ldn + n0 + c * 32;
         const int e = threadIdx.x;  // 0 .. 255 over the eight epilogue warps
-        uint32_t pn[NS][8];              // outn: this thread's 32 consecutive columns of every plane
+        uint32_t pn[ONS][8];              // outn: this thread's 32 consecutive columns of every plane
 #pragma unroll
         for (int pass = 0; pass < 4; pass++) {
           uint32_t wh[8], wl[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) slice_words<NS>(v[pass * 8 + j] * oinv, wh[j], wl[j]);
+          for (int j = 0; j < 8; j++) slice_words<ONS>(v[pass * 8 + j] * oinv, wh[j], wl[j]);
           if (want_n) {
 #pragma unroll
             for (int g4 = 0; g4 < 2; g4++) {
@@ -492,14 +494,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
               transpose4x4_bytes(wh[4 * g4], wh[4 * g4 + 1], wh[4 * g4 + 2], wh[4 * g4 + 3], th);
               transpose4x4_bytes(wl[4 * g4], wl[4 * g4 + 1], wl[4 * g4 + 2], wl[4 * g4 + 3], tl);
 #pragma unroll
-              for (int b4 = 4 - NS / 2; b4 < 4; b4++) {  // byte b4 of a slice word = digit 3 - b4 of its half
+              for (int b4 = 4 - ONS / 2; b4 < 4; b4++) {  // byte b4 of a slice word = digit 3 - b4 of its half
                 pn[3 - b4][pass * 2 + g4] = th[b4];
-                pn[NS / 2 + 3 - b4][pass * 2 + g4] = tl[b4];
+                pn[ONS / 2 + 3 - b4][pass * 2 + g4] = tl[b4];
               }
             }
             if (pass == 3) {
 #pragma unroll
-              for (int s2 = 0; s2 < NS; s2++) st_global_256(orow + (long long)s2 * p.outn_plane_stride, pn[s2]);
+              for (int s2 = 0; s2 < ONS; s2++) st_global_256(orow + (long long)s2 * p.outn_plane_stride, pn[s2]);
             }
           }
           if (want_t) {  // uniform over the CTA (depends on the batch only)
@@ -525,8 +527,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
             const int ncol = n0 + (slot >> 3) * 32 + pass * 8 + (slot & 7);
             int8_t* ob = p.out + (long long)batch * p.out_batch_stride + (long long)ncol * p.ldo + ti.m0 + mg * 16;
 #pragma unroll
-            for (int b4 = 4 - NS / 2; b4 < 4; b4++) {  // byte b4 = digit 3 - b4 of its half (the top bytes are unused for NS = 6)
-              const int plane = hh * (NS / 2) + 3 - b4;
+            for (int b4 = 4 - ONS / 2; b4 < 4; b4++) {  // byte b4 = digit 3 - b4 of its half (the top bytes are unused for six)
+              const int plane = hh * (ONS / 2) + 3 - b4;
               *reinterpret_cast<uint4*>(ob + (long long)plane * p.out_plane_stride) =
                   make_uint4(o4[b4][0], o4[b4][1], o4[b4][2], o4[b4][3]);
             }

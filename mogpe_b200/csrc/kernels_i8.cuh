@@ -287,17 +287,33 @@ __device__ __forceinline__ double exp_neg_fast(double x) {
   return p * s;
 }
 
+// Inputs of a kernel group in ITS length scales, once per step:  xs[g][n][d] = x_nd / l_gd  (zero padded to DMAX; columns
+// n >= N get 1e150 in d = 0, which drives their kernel value to exactly zero in kuf_grad_slice_kernel).   grid (Bp/256, Q)
+template <int DMAX>
+__global__ void xs_prep_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params, Layout lo,
+                               const double* __restrict__ X, int N, int Bp, double* __restrict__ xs) {
+  const int g = blockIdx.y, D = md->D;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Bp) return;
+  const double* ls = params + lo.ls + (long long)g * D;
+  double* o = xs + ((long long)g * Bp + n) * DMAX;
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) o[d] = (n < N) ? (d < D ? X[(long long)n * D + d] / ls[d] : 0.0) : (d == 0 ? 1e150 : 0.0);
+}
+
 // Kuf-bar (= W) consumer of the INT8 step, ONE pass over W [g][m][n]:
 //   (a) kernel-hyperparameter and Z gradients  E = W .* Kuf,  dZ[m,d] = -sum_n E (z_md - x_nd) / l_d^2,
-//       dl_d = sum_mn E (z_md - x_nd)^2 / l_d^3,  dvar = sum E / var   (as kuf_grad_kernel) with Kuf RE-EVALUATED from X and Z
-//       (the step holds it only as byte planes; one FP64 exp per element instead of a second 8-byte read), and
+//       dl_d = sum_mn E (z_md - x_nd)^2 / l_d^3,  dvar = sum E / var   (as kuf_grad_kernel) with Kuf RE-EVALUATED from the scaled
+//       inputs of xs_prep_kernel and Z (the step holds it only as byte planes; one FP64 exp per element instead of a second
+//       8-byte read): with u = (z - x) / l,  r2 = |u|^2 directly (no |x|^2 + |z|^2 - 2 x.z cancellation), and the same u give
+//       the gradient sums  sum E u  (-> dZ = -. / l)  and  sum E u^2  (-> dl = . / l);
 //   (b) the [m][n] byte planes of W for Lbar = -tril(W A^T), sliced against the exact row maxima that the epilogue of the
 //       W product collected (wmax, bit patterns) -- no separate slicing pass over W.
 // One warp per row m, every lane four consecutive columns per step (128 columns per warp step: 1 KB of W, 128 B per byte
 // plane).  n_chunk must be a multiple of 128.       grid (Mp/8, Q, nsplit), block 256
 template <int DMAX, int NS>
 __global__ void __launch_bounds__(256) kuf_grad_slice_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
-                                                             Layout lo, const double* __restrict__ X, int N, int Bc, int Bp,
+                                                             Layout lo, const double* __restrict__ XS, int Bc, int Bp,
                                                              const double* __restrict__ W,
                                                              const unsigned long long* __restrict__ wmax,
                                                              double* __restrict__ grads, int8_t* __restrict__ W8,
@@ -308,60 +324,44 @@ __global__ void __launch_bounds__(256) kuf_grad_slice_kernel(const ModelDev* __r
   const int n_lo = blockIdx.z * n_chunk, n_hi = min(Bc, n_lo + n_chunk);
   const double* ls = params + lo.ls + (long long)g * D;
   const double kvar = params[lo.kvar + g];
-  const bool live = m < Mg;  // padded rows: Kuf = 0 (no gradient), W planes are still written (zeros in, zeros out)
-  double il[DMAX], zs[DMAX], zz[DMAX], a1[DMAX], a2[DMAX], zn = 0.0, se = 0.0;
+  const bool live = m < Mg;  // padded rows: no gradient (sums discarded below), W planes are still written (zeros in, zeros out)
+  double zs[DMAX], a1[DMAX], a2[DMAX], se = 0.0;
 #pragma unroll
   for (int d = 0; d < DMAX; d++) {
-    il[d] = d < D ? 1.0 / ls[d] : 0.0;
-    zz[d] = (d < D && live) ? params[lo.Z + ((long long)g * Mp + m) * D + d] : 0.0;
-    zs[d] = zz[d] * il[d];
-    zn += zs[d] * zs[d];
+    zs[d] = (d < D && live) ? params[lo.Z + ((long long)g * Mp + m) * D + d] / ls[d] : 0.0;
     a1[d] = a2[d] = 0.0;
   }
   const double sc = pow2_scale(__longlong_as_double((long long)wmax[(long long)g * Mp + m]));
   const double inv = 1.0 / sc;
   if (lane == 0 && blockIdx.z == 0) w_scale[(long long)g * Mp + m] = sc;
   const double* w = W + ((long long)g * Mp + m) * Bp;
+  const double* xg = XS + (long long)g * Bp * DMAX;
   int8_t* o8 = W8 + ((long long)g * NS * Mp + m) * Bp;
   const long long plane = (long long)Mp * Bp;
   for (int n4 = n_lo + lane * 4; n4 < n_hi; n4 += 128) {
     double wv[4];
     ld_global_256(w + n4, wv);
     uint32_t wh[4], wl[4];
-    double ev[4], xv[4][DMAX];
-    // branch-free over the four columns (independent exp chains in flight); columns >= N contribute nothing (mask)
+    // branch-free over the four columns (independent exp chains in flight); padding columns have r2 ~ 1e300 -> E = 0
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       slice_words<NS>(wv[j] * inv, wh[j], wl[j]);
-      const bool ok = live && n4 + j < N;
-      const long long xi = (long long)(ok ? n4 + j : 0) * D;
-      if (DMAX == 4) {
-        if (D == 4) ld_global_256(X + xi, *reinterpret_cast<double(*)[4]>(&xv[j][0]));
-        else
+      double u[DMAX];
 #pragma unroll
-          for (int d = 0; d < DMAX; d++) xv[j][d] = d < D ? X[xi + d] : 0.0;
-      } else {
-#pragma unroll
-        for (int d = 0; d < DMAX; d++) xv[j][d] = d < D ? X[xi + d] : 0.0;
-      }
-      double dot = 0.0, xn = 0.0;
+      for (int d4 = 0; d4 < DMAX; d4 += 4) ld_global_256(xg + (long long)(n4 + j) * DMAX + d4, *reinterpret_cast<double(*)[4]>(&u[d4]));
+      double r2 = 0.0;
 #pragma unroll
       for (int d = 0; d < DMAX; d++) {
-        const double xs = xv[j][d] * il[d];
-        xn += xs * xs;
-        dot += zs[d] * xs;
+        u[d] = zs[d] - u[d];
+        r2 = fma(u[d], u[d], r2);
       }
-      const double r2 = -2.0 * dot + (zn + xn);
-      ev[j] = ok ? wv[j] * (kvar * exp_neg_fast(fmin(-0.5 * r2, 0.0))) : 0.0;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      se += ev[j];
+      const double ev = wv[j] * (kvar * exp_neg_fast(fmax(-0.5 * r2, -1000.0)));
+      se += ev;
 #pragma unroll
       for (int d = 0; d < DMAX; d++) {
-        const double df = zz[d] - xv[j][d];
-        a1[d] += ev[j] * df;
-        a2[d] += ev[j] * df * df;
+        const double t = ev * u[d];
+        a1[d] += t;
+        a2[d] = fma(t, u[d], a2[d]);
       }
     }
     uint32_t th[4], tl[4];
@@ -382,12 +382,12 @@ __global__ void __launch_bounds__(256) kuf_grad_slice_kernel(const ModelDev* __r
     if (d < D) {
       const double s1 = warp_sum(a1[d]);
       dls[d] = warp_sum(a2[d]);
-      if (lane == 0) atomicAdd(grads + lo.Z + ((long long)g * Mp + m) * D + d, -s1 / (ls[d] * ls[d]));
+      if (lane == 0) atomicAdd(grads + lo.Z + ((long long)g * Mp + m) * D + d, -s1 / ls[d]);
     }
   }
   if (lane == 0) {
     atomicAdd(grads + lo.kvar + g, se / kvar);
-    for (int d = 0; d < D && d < DMAX; d++) atomicAdd(grads + lo.ls + (long long)g * D + d, dls[d] / (ls[d] * ls[d] * ls[d]));
+    for (int d = 0; d < D && d < DMAX; d++) atomicAdd(grads + lo.ls + (long long)g * D + d, dls[d] / ls[d]);
   }
 }
 

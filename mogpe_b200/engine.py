@@ -430,8 +430,15 @@ class Engine:
         return {"ms": ms.value, "flops": fl.value, "launches": n.value, "tensor_ops": ops.value}
 
     def set_int8_grad_slices(self, slices: int):
-        """Byte slices of the gradient-only INT8 products (S LTA, W, Lbar, Sbar): 7 (default) or 8."""
+        """Byte slices of the gradient-only INT8 products (S LTA, W, Lbar, Sbar): 7 (default), 8 or 6; capped by the forward
+        products' count (set_int8_forward_slices)."""
         _lib.check(self.lib.mogpe_set_int8_grad_slices(self.h, int(slices)), self.h)
+
+    def set_int8_forward_slices(self, slices: int):
+        """Byte slices of the two forward INT8 products (A = L^-1 Kuf, S^T A): 8 (default) or 7 -- both float64-accurate at the
+        1e-8 / 1e-6 tolerances -- or 6: fast training mode, every product of the step loads six slices (42 bits; ELBO ~1e-9,
+        gradients ~1e-6 of the float64 step: the "1e-4 class" of BASELINE.json)."""
+        _lib.check(self.lib.mogpe_set_int8_forward_slices(self.h, int(slices)), self.h)
 
     def graph_stats(self):
         """-> (captured training-step graphs, capture disabled after a failure)."""

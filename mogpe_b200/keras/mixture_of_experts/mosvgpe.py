@@ -62,6 +62,10 @@ class MixtureOfSVGPExperts(MixtureOfExpertsBase):
     def set_seed(self, seed: int):
         self._core.set_seed(seed)
 
+    def set_fast_training(self, on: bool = True):
+        """Gradient steps in the "1e-4 class" (six-slice INT8 products; see ModelCore.set_fast_training)."""
+        self._core.set_fast_training(on)
+
     def set_precision(self, precision: str):
         """"float64" (default) or "tf32" (prediction on the tcgen05 tensor cores; new capability)."""
         self._core.set_precision(precision)

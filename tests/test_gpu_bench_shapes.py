@@ -77,25 +77,30 @@ def test_mid_size_bench_shapes_match_oracle(name, oracle_cache):
     eng.close()
 
 
-@pytest.mark.parametrize("mode", ["int8_step", "int8_step_8", "int8_step_6", "int8_backward", "fp64"])
+@pytest.mark.parametrize("mode", ["int8_step", "int8_step_8", "int8_step_7", "int8_step_6", "int8_backward", "fp64"])
 def test_c4_bench_shape_matches_oracle(mode, oracle_cache):
     """C4 (the headline workload): D = 4, K = 8, G = 8 Softmax, 16 kernel groups, M = 512, 8192 rows, in the three arithmetic
-    modes of a gradient step: every dense product on the INT8 tensor cores (what bench.py times; the four gradient-only products
-    with the default seven byte slices, with eight and with six), only the two minibatch-reduced products of the backward there,
-    and all-FP64 DMMA."""
+    modes of a gradient step: every dense product on the INT8 tensor cores (what bench.py times: eight byte slices per operand in
+    the two forward products, seven in the four gradient-only ones; eight everywhere; seven everywhere; six in the gradient-only
+    products), only the two minibatch-reduced products of the backward
+    there, and all-FP64 DMMA."""
     from tests._engine_helpers import engine_from_spec, run_engine_elbo
 
     wl, spec, X, Y, eps, val, grads_u = _oracle("C4", oracle_cache)
     eng = engine_from_spec(spec, max_batch=wl["batch"])
     eng.set_int8_step(mode.startswith("int8_step"))
     eng.set_int8_backward(mode != "fp64")
-    if mode.startswith("int8_step_"):  # byte slices of the gradient-only products (default 7)
-        eng.set_int8_grad_slices(int(mode[-1]))
+    if mode == "int8_step_8":  # byte slices loaded by the products (default: eight forward, seven gradient-only)
+        eng.set_int8_grad_slices(8)
+    elif mode == "int8_step_7":
+        eng.set_int8_forward_slices(7)
+    elif mode == "int8_step_6":  # six in the four gradient-only products
+        eng.set_int8_grad_slices(6)
     eng.profile(True)
     res = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=True)
     i8 = eng.profile_read_int8()["launches"]
     eng.profile(False)
-    assert i8 == {"int8_step": 6, "int8_step_8": 6, "int8_step_6": 6, "int8_backward": 2, "fp64": 0}[mode]  # the mode under test really ran
+    assert i8 == {"int8_step": 6, "int8_step_8": 6, "int8_step_7": 6, "int8_step_6": 6, "int8_backward": 2, "fp64": 0}[mode]  # the mode under test really ran
     _compare(spec, res, val, grads_u, f"C4 {mode}")
     # a second call on the same handle (scratch reuse, second random-stream position) reproduces the result to rounding
     res2 = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=True)
@@ -117,4 +122,31 @@ def test_c4_predict_matches_oracle(oracle_cache):
     pi = rn.predict_mixing_probs(spec, Xs, eps_mc)
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
     assert rel(out["y_mean"], ym) < RTOL_VALUE and rel(out["y_var"], yv) < RTOL_VALUE and rel(out["mix_probs"], pi) < RTOL_VALUE
+    eng.close()
+
+
+def test_c4_fast_training_mode_is_in_the_1e4_class(oracle_cache):
+    """BASELINE.json's north_star allows a "1e-4" arithmetic class beside float64: with six byte slices in every product of the
+    INT8 step (Engine.set_int8_forward_slices(6)) the ELBO stays within 1e-5 and every gradient block within 1e-4 of the
+    oracle (measured: ~1e-7 / ~1e-6), and switching back to eight slices restores the float64-accurate step on the same handle."""
+    from tests._engine_helpers import engine_from_spec, engine_grads_named, oracle_grads_constrained, run_engine_elbo
+
+    wl, spec, X, Y, eps, val, grads_u = _oracle("C4", oracle_cache)
+    eng = engine_from_spec(spec, max_batch=wl["batch"])
+    eng.set_int8_forward_slices(6)
+    eng.profile(True)
+    res = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=True)
+    info = eng.profile_read_int8()
+    eng.profile(False)
+    assert info["launches"] == 6 and abs(info["tensor_ops"] / info["flops"] - 21.0) < 1e-9  # 21 slice pairs everywhere
+    assert abs(res.elbo - val) <= 1e-5 * abs(val), (res.elbo, val)
+    want = oracle_grads_constrained(spec, grads_u)
+    got = engine_grads_named(res, spec)
+    for name, g in want.items():
+        a, g = np.asarray(got[name], dtype=float), np.asarray(g, dtype=float)
+        assert np.max(np.abs(a - g)) <= 1e-4 * np.max(np.abs(g)), name
+        assert np.linalg.norm((a - g).ravel()) <= 1e-4 * np.linalg.norm(g.ravel()), name
+    eng.set_int8_forward_slices(8)
+    res8 = run_engine_elbo(eng, spec, X, Y, eps, device_inputs=True)
+    _compare(spec, res8, val, grads_u, "C4 back to eight slices")
     eng.close()
