@@ -152,7 +152,9 @@ struct mogpe_handle {
   // side stream: work that does not depend on the Cholesky chain (Kuf, q_sqrt prep, mean vectors; Kuf gradients in
   // the backward) overlaps the latency-bound factorisation launches
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ld8 = nullptr, ev_linvT = nullptr;
+  bool linvT_pending = false;
+  bool ld8_pending = false;  // LTA diag(dfvar) planes queued on the side stream, ev_ld8 marks them ready
   std::vector<cudaEvent_t> ev_rows;  // ev_rows[i]: rows [64 i, 64 i + 64) of L^-1 are complete (Cholesky chain progress)
   bool a_done_in_factorise = false;
   // library-owned random stream
@@ -308,6 +310,8 @@ static void free_ws(mogpe_handle* h) {
   for (auto e : h->ev_rows) cudaEventDestroy(e);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_ld8) cudaEventDestroy(h->ev_ld8);
+  if (h->ev_linvT) cudaEventDestroy(h->ev_linvT);
   if (h->side) cudaStreamDestroy(h->side);
 }
 
@@ -423,6 +427,8 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_ld8, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_linvT, cudaEventDisableTiming);
   if (e == cudaSuccess)
     e = cudaMemcpy(h->d_latent_group, md.latent_group, sizeof(int) * MAXP, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(h->varq, 0, (size_t)P * h->Bp * sizeof(double));
@@ -751,6 +757,29 @@ static mogpe_status conditional_fwd(mogpe_handle* h, const double* params, const
   return MOGPE_OK;
 }
 
+static mogpe_status ensure_i8_bwd(mogpe_handle* h);
+
+// Byte planes of LTA_l diag(dfvar_l) (the B operand of Sbar), rows scaled by a bound or their measured maxima.  DRAM-bound and
+// small in registers (32 x 256 per block), so in the INT8 step it is queued on the side stream right after the likelihood
+// kernel, where it shares the SMs with the persistent tensor-core products of the backward (their CTAs leave ~11 K registers).
+static mogpe_status lta_d_planes(mogpe_handle* h, int Bc, int N, cudaStream_t st, bool a8_ready) {
+  const ModelDev& md = h->md_host;
+  const int Mp = h->Mp, Bp = h->Bp, nl = md.nlta;
+  const dim3 sg((Bp / 4 + 255) / 256, Mp, 1);
+  if (a8_ready) {  // INT8 step: a bound from the row maxima of LTA (epilogue of its product) and max |dfvar| -- no pass over LTA
+    unsigned long long* dmax = h->t8_ltamax + (size_t)md.P * Mp;
+    oz::absmax_rows_kernel<<<dim3((N + 1023) / 1024, md.P), 256, 0, st>>>(h->dfvar, N, Bp, dmax);
+    oz::lta_d_scale_kernel<<<dim3((Mp + 127) / 128, nl), 128, 0, st>>>(h->d_md, h->t8_ltamax, dmax, Mp, h->bld_scale);
+  } else
+    oz::row_scale_n_kernel<<<dim3(Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
+                                                       h->d_lta_latent, h->bld_scale, Mp);
+  oz::slice_rows_n_kernel<8><<<dim3(sg.x, Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
+                                                                 h->d_lta_latent, h->bld_scale, h->bLD8, Mp);
+  KCOUNT(h, 2);
+  H_CUDA(h, cudaGetLastError());
+  return MOGPE_OK;
+}
+
 static mogpe_status dp_allreduce(mogpe_handle* h, double* buf, size_t n, cudaStream_t st);  // defined with the NCCL loader
 // Lbar and Sbar of the backward on the INT8 tensor cores (returns MOGPE_ERR_UNSUPPORTED when the shape does not qualify)
 static mogpe_status int8_backward_products(mogpe_handle* h, const double* params, double* grads, int Bc, int N, cudaStream_t st,
@@ -901,6 +930,15 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   //     => scale LTA in place first (it is also the B operand of Abar += S_l dLTA_l).
   KCOUNT(h, 4);  // q_grads, halve_diag, kuu_grad, kuf_grad
   if (i8_step) {
+    if (md.nlta > 0 && !h->prof && h->i8_bwd_on) {  // (profiling: every kernel alone on the caller's stream)
+      rc = ensure_i8_bwd(h);
+      if (rc != MOGPE_OK) return rc;
+      H_CUDA(h, side_fork(h, st));
+      rc = lta_d_planes(h, Bc, N, h->side, true);
+      if (rc != MOGPE_OK) return rc;
+      H_CUDA(h, cudaEventRecord(h->ev_ld8, h->side));
+      h->ld8_pending = true;
+    }
     rc = i8_step_backward_to_W(h, N, Bc, st);
     if (rc != MOGPE_OK) return rc;
   } else {
@@ -1516,16 +1554,13 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
   if (md.nlta > 0) {
     const int nl = md.nlta;
     // B operand: LTA_l diag(dfvar_l), rows scaled by their own maxima
-    if (a8_ready) {  // INT8 step: a bound from the row maxima of LTA (epilogue of its product) and max |dfvar| -- no pass over LTA
-      unsigned long long* dmax = h->t8_ltamax + (size_t)md.P * Mp;
-      oz::absmax_rows_kernel<<<dim3((N + 1023) / 1024, md.P), 256, 0, st>>>(h->dfvar, N, Bp, dmax);
-      oz::lta_d_scale_kernel<<<dim3((Mp + 127) / 128, nl), 128, 0, st>>>(h->d_md, h->t8_ltamax, dmax, Mp, h->bld_scale);
-    } else
-      oz::row_scale_n_kernel<<<dim3(Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
-                                                         h->d_lta_latent, h->bld_scale, Mp);
-    oz::slice_rows_n_kernel<NS><<<dim3(sg.x, Mp, nl), 256, 0, st>>>(h->LTA, Mp, N, (long long)Mp * Bp, Bp, nullptr, h->dfvar, Bp,
-                                                                    h->d_lta_latent, h->bld_scale, h->bLD8, Mp);
-    KCOUNT(h, 2);
+    if (h->ld8_pending) {  // already queued on the side stream at the start of the backward (underneath the products before)
+      H_CUDA(h, cudaStreamWaitEvent(st, h->ev_ld8, 0));
+      h->ld8_pending = false;
+    } else {
+      mogpe_status lrc = lta_d_planes(h, Bc, N, st, a8_ready);
+      if (lrc != MOGPE_OK) return lrc;
+    }
     oz::Params p;
     memset(&p, 0, sizeof(p));
     p.m_tiles = m_tiles; p.K = Bc; p.kmode = t32::K_FULL;
@@ -1679,8 +1714,19 @@ static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const
   if (!kuf_aside) launch_kuf8(st);
   oz::row_scale_kernel<<<dim3(Mp, Q), 128, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1, h->t8_linv_scale, Mp);
   oz::slice_square_kernel<NS><<<sq, sb, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 0, 1, h->t8_linv_scale, h->t8_Linv, Mp);
-  oz::row_scale_kernel<<<dim3(Mp, Q), 128, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 1, 0, h->t8_linvT_scale, Mp);
-  oz::slice_square_kernel<NS><<<sq, sb, 0, st>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 1, 0, h->t8_linvT_scale, h->t8_LinvT, Mp);
+  {  // L^-T planes: only W = L^-T Abar of the backward reads them -> side stream, underneath the A product
+    cudaStream_t ts = st;
+    if (!h->prof) {
+      H_CUDA(h, side_fork(h, st));
+      ts = h->side;
+    }
+    oz::row_scale_kernel<<<dim3(Mp, Q), 128, 0, ts>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 1, 0, h->t8_linvT_scale, Mp);
+    oz::slice_square_kernel<NS><<<sq, sb, 0, ts>>>(h->Linv, Mp, (long long)Mp * Mp, Mp, nullptr, 1, 0, h->t8_linvT_scale, h->t8_LinvT, Mp);
+    if (!h->prof) {
+      H_CUDA(h, cudaEventRecord(h->ev_linvT, h->side));
+      h->linvT_pending = true;
+    }
+  }
   KCOUNT(h, 4);
   H_CUDA(h, cudaGetLastError());
   {  // A = L^-1 Kuf
@@ -1758,6 +1804,10 @@ static mogpe_status i8_step_backward_to_W(mogpe_handle* h, int N, int Bc, cudaSt
   sk_end(h, SK_ABAR, st, 8.0 * (2.0 * Q + nl) * Mp * N);  // read the A planes (and S LTA), write the Abar planes
   KCOUNT(h, 1);
   H_CUDA(h, cudaGetLastError());
+  if (h->linvT_pending) {  // the L^-T planes were queued on the side stream in the forward
+    H_CUDA(h, cudaStreamWaitEvent(st, h->ev_linvT, 0));
+    h->linvT_pending = false;
+  }
   {  // W = L^-T Abar
     oz::Params p;
     memset(&p, 0, sizeof(p));
