@@ -138,6 +138,33 @@ __device__ __forceinline__ double unslice(const uint32_t (&w)[NS]) {
   return fma(int_to_double(lo), P1, int_to_double(hi)) * P1;
 }
 
+// The same for all four columns at once, with byte-wise SIMD: flipping the sign bits turns the signed digits into unsigned bytes
+// d + 128, a 4 x 4 byte transpose gathers the digits of one element into one word, two DP4A with the weights (128, 1) pair
+// them up and one IMAD joins the pairs; the bias 128 * sum 128^k rides in the accumulator input of the second DP4A.
+// 12 integer instructions per element instead of 22.
+template <int NS>
+__device__ __forceinline__ void unslice4(const uint32_t (&w)[NS], double (&a)[4]) {
+  constexpr int H = NS / 2;
+  static_assert(H == 3 || H == 4, "six or eight slices");
+  constexpr unsigned BIAS = H == 4 ? 128u * 2113665u : 128u * 16513u;
+  int half[2][4];
+#pragma unroll
+  for (int h2 = 0; h2 < 2; h2++) {
+    uint32_t t[4];
+    transpose4x4_bytes(w[h2 * H] ^ 0x80808080u, w[h2 * H + 1] ^ 0x80808080u, w[h2 * H + 2] ^ 0x80808080u,
+                       H == 4 ? (w[h2 * H + H - 1] ^ 0x80808080u) : 0u, t);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned top = __dp4a(t[j], 0x00000180u, 0u);  // u0 * 128 + u1
+      const unsigned low = __dp4a(t[j], H == 4 ? 0x01800000u : 0x00010000u, 0u - BIAS);  // u2 * 128 + u3 (or u2) - bias
+      half[h2][j] = (int)(top * (H == 4 ? 16384u : 128u) + low);
+    }
+  }
+  constexpr double P1 = 1.0 / (double)(1 << (7 * H));
+#pragma unroll
+  for (int j = 0; j < 4; j++) a[j] = fma(int_to_double(half[1][j]), P1, int_to_double(half[0][j])) * P1;
+}
+
 template <int NS>
 __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__ md, const int8_t* __restrict__ A8,
                                                     const double* __restrict__ a_scale, const double* __restrict__ V,
@@ -170,8 +197,9 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
       }
     }
     const double sc = pow2_scale(1.001 * b);
-    s_inv[tid] = 1.0 / sc;
-    s_dv[tid] = dv;
+    // column n = 4 i + j lives at [16 j + i]: the 16 lanes of a tile row read consecutive words (no bank conflicts)
+    s_inv[(tid & 3) * 16 + (tid >> 2)] = 1.0 / sc;
+    s_dv[(tid & 3) * 16 + (tid >> 2)] = dv;
     if (blockIdx.y == 0) nscale[(long long)g * Bp + n] = sc;
   }
   __syncthreads();
@@ -189,13 +217,12 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
 #pragma unroll
     for (int s2 = 0; s2 < NS; s2++) w[s2] = *reinterpret_cast<const uint32_t*>(Ag + s2 * plane + (long long)m * Bp + nn);
     double a[4];
-    a[0] = unslice<NS, 0>(w) * asc;
-    a[1] = unslice<NS, 1>(w) * asc;
-    a[2] = unslice<NS, 2>(w) * asc;
-    a[3] = unslice<NS, 3>(w) * asc;
+    unslice4<NS>(w, a);
+#pragma unroll
+    for (int j = 0; j < 4; j++) a[j] *= asc;
     double ab[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) ab[j] = -2.0 * s_dv[c4 + j] * a[j];
+    for (int j = 0; j < 4; j++) ab[j] = -2.0 * s_dv[j * 16 + (tid & 15)] * a[j];
     for (int q = vb; q < ve; q++) {
       const int v = md->gvec[q];
       const double vm = V[(long long)v * Mp + m];
@@ -226,7 +253,7 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t wh, wl;
-      slice_words<NS>(ab[j] * s_inv[c4 + j], wh, wl);
+      slice_words<NS>(ab[j] * s_inv[j * 16 + (tid & 15)], wh, wl);
       stage[0][c4 + j][ml] = wh;
       stage[1][c4 + j][ml] = wl;
     }
@@ -234,8 +261,10 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
   __syncthreads();
   // read back 16 consecutive m of one (half, n), transpose the digit bytes into plane words and store 16 bytes per plane
   int8_t* Og = AbarT8 + (long long)g * NS * Bp * Mp;
+  // (a warp covers 16 columns x 2 groups of 16 m: with the odd pitch the 32 row starts fall into 32 different banks)
   for (int u = tid; u < 2 * 64 * 4; u += 256) {
-    const int half = u >> 8, n = (u >> 2) & 63, mg = u & 3;
+    const int half = u >> 8, wq = (u >> 5) & 7, l = u & 31;
+    const int n = (l >> 1) + 16 * (wq >> 1), mg = (l & 1) + 2 * (wq & 1);
     const uint32_t* sp = &stage[half][n][mg * 16];
     uint32_t o4[4][4];
 #pragma unroll

@@ -3,6 +3,7 @@ integer accumulation per anti-diagonal of slice pairs, and the error bound the k
 arithmetic stands in for the tensor cores' exact int32 accumulation); the GPU kernel is checked against the same FP64
 products in tools/i8_gemm_test.cu and tests/test_gpu_int8.py."""
 import numpy as np
+import pytest
 
 NS = 8
 
@@ -109,3 +110,21 @@ def test_word_slicing_restatement_matches_the_digit_rule():
             assert np.max(np.abs(rec - r)) <= 2.0 ** (-7 * ns - 1)
     finally:
         NS = keep
+
+
+@pytest.mark.parametrize("H", [3, 4])
+def test_unslice4_dp4a_restatement(H):
+    """kernels_i8.cuh: unslice4 rebuilds a half (H signed base-128 digits) as  (u0 128 + u1) 128^(H-2) + (u2 128 + u3 | u2) - bias
+    with u = digit ^ 0x80 as an unsigned byte (two DP4A with weights (128, 1), the bias in the accumulator): exact, and every
+    intermediate stays below 2^32."""
+    rng = np.random.default_rng(H)
+    d = rng.integers(-64, 65, size=(200000, H))
+    d[0], d[1] = -64, 64
+    u = (d.astype(np.int8).view(np.uint8) ^ 0x80).astype(np.int64)
+    bias = 128 * sum(128 ** k for k in range(H))
+    top = u[:, 0] * 128 + u[:, 1]
+    low = u[:, 2] * 128 + u[:, 3] if H == 4 else u[:, 2]
+    val = top * (16384 if H == 4 else 128) + low
+    assert val.max() < 2 ** 32
+    ref = sum(d[:, k] * 128 ** (H - 1 - k) for k in range(H))
+    assert np.array_equal(val - bias, ref)
