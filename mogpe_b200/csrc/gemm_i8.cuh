@@ -237,6 +237,66 @@ __device__ __forceinline__ void tmem_ld32_i(uint32_t taddr, int* v) {
       : "memory");
 }
 
+// 16 columns of one accumulator, WITHOUT waiting: the data are valid after tmem_ld_wait, which names the destination registers
+// as read-write operands so that the compiler keeps every consumer behind it.
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]),
+                 "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :
+               : "memory");
+}
+
+// sum_d T_d 128^-d of this thread's 32 columns when every k-sum is at most 512 long.  Then |T_d| <= (d + 1) 512 * 2^12, so two
+// neighbouring accumulators combine EXACTLY in int32 (|128 T_d + T_(d+1)| <= 2^21 (129 d + 130) < 2^31 for d <= 6): half the
+// int -> double conversions and FP64 multiply-adds of the plain recurrence.  The loads are software pipelined in units of
+// (pair, 16 columns): the tcgen05.ld of the next unit is in flight while the current one is combined.
+// Result: v[i] = (sum_d T_d 128^-d) * (NS odd ? 1 : 128)   -- the caller folds the factor into its scale.
+template <int NS>
+__device__ __forceinline__ void horner_pairs(uint32_t trow, double (&v)[32]) {
+  constexpr int ODD = NS & 1, NP = NS / 2, U = 2 * (NP + ODD);  // units: pairs from the top, then (NS odd) T_0 alone; two halves each
+  uint32_t ba[2][16], bb[2][16];
+  auto issue = [&](int u, int par) {
+    const int pi = u >> 1, h = u & 1;
+    if (pi < NP) {
+      const int d = 2 * (NP - 1 - pi) + ODD;  // pair (d, d + 1)
+      tmem_ld16_nowait(trow + (uint32_t)(d * BN + h * 16), ba[par]);
+      tmem_ld16_nowait(trow + (uint32_t)((d + 1) * BN + h * 16), bb[par]);
+    } else {
+      tmem_ld16_nowait(trow + (uint32_t)(h * 16), ba[par]);
+    }
+  };
+  issue(0, 0);
+  tmem_ld_wait(ba[0], bb[0]);
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int par = u & 1, pi = u >> 1, h = u & 1;
+    if (u + 1 < U) issue(u + 1, par ^ 1);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int idx = h * 16 + i;
+      if (pi < NP) {
+        const int cmb = (int)ba[par][i] * 128 + (int)bb[par][i];
+        v[idx] = pi == 0 ? int_to_double(cmb) : fma(v[idx], 1.0 / 16384.0, int_to_double(cmb));
+      } else {
+        v[idx] = fma(v[idx], 1.0 / 16384.0, int_to_double((int)ba[par][i]));
+      }
+    }
+    if (u + 1 < U) tmem_ld_wait(ba[par ^ 1], bb[par ^ 1]);
+  }
+}
+
 // Tile decode shared by the three warp roles.  Tiles are numbered with the row tile fastest, so the CTAs that run at the
 // same time work on neighbouring tiles and share their B tiles in L2.
 struct TileInfo {
@@ -417,14 +477,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       // accumulator value instead of ~5 for the 64-bit integer recurrence; the rounding of the recurrence is 2^-53 of the
       // running sum, far below the 2^-57 grid of the operands.
       double v[32];
-      {
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      if (ti.num_kb * BKB <= 512 && !(p.dbg & 64)) {  // (uniform) every k-sum short enough for the exact int32 pair combination
+        horner_pairs<NS>(trow, v);
+        const double rs2 = (NS & 1) ? rs : rs * (1.0 / 128.0);
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] *= rs2;
+      } else {
         int tt[32];
-        tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((NS - 1) * BN + c * 32), tt);
+        tmem_ld32_i(trow + (uint32_t)((NS - 1) * BN), tt);
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = int_to_double(tt[i]);
 #pragma unroll 1
         for (int d = NS - 2; d >= 0; d--) {
-          tmem_ld32_i(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 32), tt);
+          tmem_ld32_i(trow + (uint32_t)(d * BN), tt);
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] = fma(v[i], 1.0 / 128.0, int_to_double(tt[i]));
         }
