@@ -1414,6 +1414,15 @@ static mogpe_status products_i8(mogpe_handle* h, const double* params, int Bc, i
 // `flops` = ALGORITHMIC FP64-equivalent work (triangular operands / results counted as triangular).
 static cudaError_t i8_launch_ns(int ns, const CUtensorMap& ma, const CUtensorMap& mb, const oz::Params& p, int n_tiles, int batch,
                                 cudaStream_t st) {
+  // epilogue warps: 16 for the short-K products whose epilogue stores FP64 results (measured at C4: S^T A 437 -> 420 us, S LTA
+  // 271 -> 250, W 578 -> 517), 8 for A = L^-1 Kuf (both plane layouts + statistics: 880 us with 8 warps, 1011 with 16) and for
+  // the minibatch-reduced products (K = 8192: atomics into [M x M]); MOGPE_I8_EW = 8 / 16 forces one (tuning switch)
+  static const int ew_env = getenv("MOGPE_I8_EW") ? atoi(getenv("MOGPE_I8_EW")) : 0;
+  const bool wide = ew_env ? ew_env == 16 : (p.K <= 512 && !p.tril64 && !p.outn);
+  if (wide) {
+    if (ns == 6) return oz::launch<6, 16>(ma, mb, p, n_tiles, batch, st);
+    return ns == 7 ? oz::launch<7, 16>(ma, mb, p, n_tiles, batch, st) : oz::launch<8, 16>(ma, mb, p, n_tiles, batch, st);
+  }
   if (ns == 6) return oz::launch<6>(ma, mb, p, n_tiles, batch, st);
   return ns == 7 ? oz::launch<7>(ma, mb, p, n_tiles, batch, st) : oz::launch<8>(ma, mb, p, n_tiles, batch, st);
 }

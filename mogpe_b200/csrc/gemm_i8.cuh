@@ -258,17 +258,33 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16], uint32_t (&b)[16
                : "memory");
 }
 
-// sum_d T_d 128^-d of this thread's 32 columns when every k-sum is at most 512 long.  Then |T_d| <= (d + 1) 512 * 2^12, so two
+__device__ __forceinline__ void tmem_ld16_i(uint32_t taddr, int* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void st_global_128(void* p, const uint32_t (&w)[4]) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+
+// sum_d T_d 128^-d of this thread's CW (32 or 16) columns when every k-sum is at most 512 long.  Then |T_d| <= (d + 1) 512 * 2^12, so two
 // neighbouring accumulators combine EXACTLY in int32 (|128 T_d + T_(d+1)| <= 2^21 (129 d + 130) < 2^31 for d <= 6): half the
 // int -> double conversions and FP64 multiply-adds of the plain recurrence.  The loads are software pipelined in units of
 // (pair, 16 columns): the tcgen05.ld of the next unit is in flight while the current one is combined.
 // Result: v[i] = (sum_d T_d 128^-d) * (NS odd ? 1 : 128)   -- the caller folds the factor into its scale.
-template <int NS>
-__device__ __forceinline__ void horner_pairs(uint32_t trow, double (&v)[32]) {
-  constexpr int ODD = NS & 1, NP = NS / 2, U = 2 * (NP + ODD);  // units: pairs from the top, then (NS odd) T_0 alone; two halves each
+template <int NS, int CW>
+__device__ __forceinline__ void horner_pairs(uint32_t trow, double (&v)[CW]) {
+  constexpr int HV = CW / 16;  // 16-column halves per accumulator
+  constexpr int ODD = NS & 1, NP = NS / 2, U = HV * (NP + ODD);  // units: pairs from the top, then (NS odd) T_0 alone
   uint32_t ba[2][16], bb[2][16];
   auto issue = [&](int u, int par) {
-    const int pi = u >> 1, h = u & 1;
+    const int pi = u / HV, h = u % HV;
     if (pi < NP) {
       const int d = 2 * (NP - 1 - pi) + ODD;  // pair (d, d + 1)
       tmem_ld16_nowait(trow + (uint32_t)(d * BN + h * 16), ba[par]);
@@ -281,7 +297,7 @@ __device__ __forceinline__ void horner_pairs(uint32_t trow, double (&v)[32]) {
   tmem_ld_wait(ba[0], bb[0]);
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    const int par = u & 1, pi = u >> 1, h = u & 1;
+    const int par = u & 1, pi = u / HV, h = u % HV;
     if (u + 1 < U) issue(u + 1, par ^ 1);
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -348,12 +364,16 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int t) {
 // epilogue of the current one drains TMEM, so the per-tile prologue (first TMA round trip: ~4k of ~25k cycles) is hidden.
 // The host picks gridDim.x coprime to m_tiles: every CTA then cycles through all row tiles (triangular operands give them
 // different k lengths) and the static schedule is balanced.
-template <int NS>
-__global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                     const __grid_constant__ CUtensorMap mapB,
-                                                                     const __grid_constant__ Params p) {
+// EW = epilogue warps: 8 (two per TMEM lane quarter, 32 columns each) or 16 (four per quarter, 16 columns each: twice the warps to
+// hide the latencies of the epilogue, which is what bounds the K = 512 products; ~96 registers per thread).
+template <int NS, int EW = 8>
+__global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                           const __grid_constant__ CUtensorMap mapB,
+                                                                           const __grid_constant__ Params p) {
   using namespace t32;
   constexpr int A_STAGE_BYTES = Cfg<NS>::A_STAGE_BYTES, STAGE_BYTES = Cfg<NS>::STAGE_BYTES, H = Cfg<NS>::H;
+  constexpr int TMA_W = EW, MMA_W = EW + 1, ETH = EW * 32;  // warp roles (the issuing warps keep the highest ids)
+  constexpr int CW = 256 / EW, PC = CW / 4;                 // columns per epilogue thread; columns per slicing pass
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -375,12 +395,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 8);
+    mbar_init(acc_empty, EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
   }
-  if (warp == MMA_WARP) {
+  if (warp == MMA_W) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)TMEM_COLS)
                  : "memory");
@@ -391,7 +411,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == TMA_WARP) {
+  if (warp == TMA_W) {
     // ===== TMA producer: one running stage counter across tiles =====
     if (lane == 0) {
       int it = 0;
@@ -411,7 +431,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
         }
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == MMA_W) {
     // ===== MMA issuer: the whole warp runs the loop (converged); one elected lane issues =====
     int it = 0, tile_i = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -456,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       umma_commit_elect(acc_full);
     }
   } else {
-    // ===== epilogue: warps 0..7, TMEM lane quarter = warp % 4, column half = warp / 4 =====
+    // ===== epilogue: warps 0..EW-1, TMEM lane quarter = warp % 4, column group (CW columns) = warp / 4 =====
     const int q = warp & 3;
     const int c = warp >> 2;
     int tile_i = -1;
@@ -468,6 +488,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       mbar_wait(acc_full, (uint32_t)(tile_i & 1), p.err_flag);
       tc_fence_after();
       const int row = ti.m0 + q * 32 + lane;
+      const int col0 = n0 + c * CW;  // first of this thread's CW consecutive columns
       // 2^(ea + eb) * 2^(-14): T_d carries 2^(-7 (d + 2))
       const double rs = p.a_scale[(long long)p.mapA[batch] * p.a_scale_stride + row] *
                         (p.b_row_scale ? 1.0 : p.b_scale[p.mapB[batch]]) * (1.0 / 16384.0);
@@ -476,26 +497,28 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       // conversions use the 2^52 trick (one LOP3 + one DADD on the FP64 pipe, no conversion unit) -- 3 instructions per
       // accumulator value instead of ~5 for the 64-bit integer recurrence; the rounding of the recurrence is 2^-53 of the
       // running sum, far below the 2^-57 grid of the operands.
-      double v[32];
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      double v[CW];
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * CW);
       if (ti.num_kb * BKB <= 512 && !(p.dbg & 64)) {  // (uniform) every k-sum short enough for the exact int32 pair combination
-        horner_pairs<NS>(trow, v);
+        horner_pairs<NS, CW>(trow, v);
         const double rs2 = (NS & 1) ? rs : rs * (1.0 / 128.0);
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] *= rs2;
+        for (int i = 0; i < CW; i++) v[i] *= rs2;
       } else {
-        int tt[32];
-        tmem_ld32_i(trow + (uint32_t)((NS - 1) * BN), tt);
+        int tt[CW];
+        if constexpr (CW == 32) tmem_ld32_i(trow + (uint32_t)((NS - 1) * BN), tt);
+        else tmem_ld16_i(trow + (uint32_t)((NS - 1) * BN), tt);
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = int_to_double(tt[i]);
+        for (int i = 0; i < CW; i++) v[i] = int_to_double(tt[i]);
 #pragma unroll 1
         for (int d = NS - 2; d >= 0; d--) {
-          tmem_ld32_i(trow + (uint32_t)(d * BN), tt);
+          if constexpr (CW == 32) tmem_ld32_i(trow + (uint32_t)(d * BN), tt);
+          else tmem_ld16_i(trow + (uint32_t)(d * BN), tt);
 #pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = fma(v[i], 1.0 / 128.0, int_to_double(tt[i]));
+          for (int i = 0; i < CW; i++) v[i] = fma(v[i], 1.0 / 128.0, int_to_double(tt[i]));
         }
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] *= rs;
+        for (int i = 0; i < CW; i++) v[i] *= rs;
       }
       // every accumulator value of this warp is in registers: TMEM may be overwritten by the next tile's MMAs
       tc_fence_before();
@@ -503,20 +526,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty)) : "memory");
       if (p.dbg & 32) continue;
       if (p.b_row_scale) {
-        const double2* bs = reinterpret_cast<const double2*>(p.b_row_scale + (long long)p.mapB[batch] * p.b_row_scale_stride + n0 + c * 32);
+        const double2* bs = reinterpret_cast<const double2*>(p.b_row_scale + (long long)p.mapB[batch] * p.b_row_scale_stride + col0);
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
+        for (int i = 0; i < CW / 2; i++) {
           const double2 b2 = bs[i];
           v[2 * i] *= b2.x;
           v[2 * i + 1] *= b2.y;
         }
       }
       if (p.out64 && p.store64) {
-        double* o = p.out64 + (long long)p.mapC[batch] * p.out64_batch_stride + (long long)row * p.ld64 + n0 + c * 32;
-        const double* cs = p.col64 ? p.col64 + (long long)p.mapS64[batch] * p.col64_stride + n0 + c * 32 : nullptr;
+        double* o = p.out64 + (long long)p.mapC[batch] * p.out64_batch_stride + (long long)row * p.ld64 + col0;
+        const double* cs = p.col64 ? p.col64 + (long long)p.mapS64[batch] * p.col64_stride + col0 : nullptr;
         double mx = 0.0;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < CW; i += 4) {
           double w[4];
 #pragma unroll
           for (int j = 0; j < 4; j++) {
@@ -528,10 +551,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
         if (p.rowmax64)
           atomicMax(p.rowmax64 + (long long)p.mapC[batch] * p.rowmax64_stride + row, (unsigned long long)__double_as_longlong(mx));
       } else if (p.out64) {
-        double* o = p.out64 + (long long)p.mapC[batch] * p.out64_batch_stride + (long long)row * p.ld64 + n0 + c * 32;
+        double* o = p.out64 + (long long)p.mapC[batch] * p.out64_batch_stride + (long long)row * p.ld64 + col0;
 #pragma unroll
-        for (int i = 0; i < 32; i++)
-          if (!p.tril64 || n0 + c * 32 + i <= row) atomicAdd(o + i, p.alpha64 * v[i]);
+        for (int i = 0; i < CW; i++)
+          if (!p.tril64 || col0 + i <= row) atomicAdd(o + i, p.alpha64 * v[i]);
       }
       if ((p.out || p.outn) && !(p.dbg & 4)) {
         // (ONS planes: eight for a product that loaded seven -- the consumers read eight-plane operands, and a 49-bit result
@@ -539,80 +562,94 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
         constexpr int ONS = NS == 6 ? 6 : 8;
         // Re-slicing of the tile into byte planes, once for both layouts.  Every element becomes two words of four signed
         // digit bytes (planes 0..3 and 4..7, byte 3 = the more significant plane); 4 x 4 byte transposes (PRMT) turn four
-        // consecutive columns into the [m][n] plane words (`outn`, 16-byte stores of this thread's row), and the transposed
-        // [n][m] planes (`out`) go through a 16 KB shared-memory staging tile: 8 columns of either column half per pass,
-        // read back as 64-byte runs along m and written as coalesced 16-byte stores.
+        // consecutive columns into the [m][n] plane words (`outn`, one wide store of this thread's row per plane), and the
+        // transposed [n][m] planes (`out`) go through a 16 KB shared-memory staging tile: PC columns of every column group per
+        // pass (16 column slots), read back as 64-byte runs along m and written as coalesced 16-byte stores.
         const bool want_t = p.out != nullptr && (p.out_mask == 0ull || ((p.out_mask >> batch) & 1ull)) && !(p.dbg & 1);
         const bool want_n = p.outn != nullptr && !(p.dbg & 2);
-        int8_t* orow = nullptr;  // [m][n] planes: this thread's row, 32 consecutive columns
-        if (p.outn) orow = p.outn + (long long)batch * p.outn_batch_stride + (long long)row * p.ldn + n0 + c * 32;
-        const int e = threadIdx.x;  // 0 .. 255 over the eight epilogue warps
-        uint32_t pn[ONS][8];              // outn: this thread's 32 consecutive columns of every plane
+        int8_t* orow = nullptr;  // [m][n] planes: this thread's row, CW consecutive columns
+        if (p.outn) orow = p.outn + (long long)batch * p.outn_batch_stride + (long long)row * p.ldn + col0;
+        const int e = threadIdx.x;  // 0 .. ETH - 1 over the epilogue warps
+        uint32_t pn[ONS][CW / 4];   // outn: this thread's CW consecutive columns of every plane
 #pragma unroll
         for (int pass = 0; pass < 4; pass++) {
-          uint32_t wh[8], wl[8];
+          uint32_t wh[PC], wl[PC];
 #pragma unroll
-          for (int j = 0; j < 8; j++) slice_words<ONS>(v[pass * 8 + j] * oinv, wh[j], wl[j]);
+          for (int j = 0; j < PC; j++) slice_words<ONS>(v[pass * PC + j] * oinv, wh[j], wl[j]);
           if (want_n) {
 #pragma unroll
-            for (int g4 = 0; g4 < 2; g4++) {
+            for (int g4 = 0; g4 < PC / 4; g4++) {
               uint32_t th[4], tl[4];
               transpose4x4_bytes(wh[4 * g4], wh[4 * g4 + 1], wh[4 * g4 + 2], wh[4 * g4 + 3], th);
               transpose4x4_bytes(wl[4 * g4], wl[4 * g4 + 1], wl[4 * g4 + 2], wl[4 * g4 + 3], tl);
 #pragma unroll
               for (int b4 = 4 - ONS / 2; b4 < 4; b4++) {  // byte b4 of a slice word = digit 3 - b4 of its half
-                pn[3 - b4][pass * 2 + g4] = th[b4];
-                pn[ONS / 2 + 3 - b4][pass * 2 + g4] = tl[b4];
+                pn[3 - b4][pass * (PC / 4) + g4] = th[b4];
+                pn[ONS / 2 + 3 - b4][pass * (PC / 4) + g4] = tl[b4];
               }
             }
             if (pass == 3) {
 #pragma unroll
-              for (int s2 = 0; s2 < ONS; s2++) st_global_256(orow + (long long)s2 * p.outn_plane_stride, pn[s2]);
+              for (int s2 = 0; s2 < ONS; s2++) {
+                if constexpr (CW == 32) st_global_256(orow + (long long)s2 * p.outn_plane_stride, pn[s2]);
+                else st_global_128(orow + (long long)s2 * p.outn_plane_stride, pn[s2]);
+              }
             }
           }
           if (want_t) {  // uniform over the CTA (depends on the batch only)
-            // staging[half][column slot 0..15][m 0..127]: slots 0..7 = columns 8 pass + j of column half 0, 8..15 of half 1
-            asm volatile("bar.sync 3, 256;" ::: "memory");  // the previous pass has been read back
+            // staging[half][column slot 0..15][m 0..127]: slot = PC * column group + j  <->  column CW * group + PC * pass + j
+            asm volatile("bar.sync 3, %0;" ::"n"(ETH) : "memory");  // the previous pass has been read back
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              stage[(0 * 16 + c * 8 + j) * 128 + q * 32 + lane] = wh[j];
-              stage[(1 * 16 + c * 8 + j) * 128 + q * 32 + lane] = wl[j];
+            for (int j = 0; j < PC; j++) {
+              stage[(0 * 16 + c * PC + j) * 128 + q * 32 + lane] = wh[j];
+              stage[(1 * 16 + c * PC + j) * 128 + q * 32 + lane] = wl[j];
             }
-            asm volatile("bar.sync 3, 256;" ::: "memory");
-            const int hh = e >> 7, slot = (e >> 3) & 15, mg = e & 7;
-            const uint4* sp = reinterpret_cast<const uint4*>(stage + (hh * 16 + slot) * 128 + mg * 16);
-            uint32_t o4[4][4];  // [byte of the slice word][m group of four]
+            asm volatile("bar.sync 3, %0;" ::"n"(ETH) : "memory");
+            if (e < 256) {  // 2 halves x 16 slots x 8 groups of 16 rows
+              const int hh = e >> 7, slot = (e >> 3) & 15, mg = e & 7;
+              const uint4* sp = reinterpret_cast<const uint4*>(stage + (hh * 16 + slot) * 128 + mg * 16);
+              uint32_t o4[4][4];  // [byte of the slice word][m group of four]
 #pragma unroll
-            for (int k4 = 0; k4 < 4; k4++) {
-              const uint4 w4 = sp[k4];
-              uint32_t tr[4];
-              transpose4x4_bytes(w4.x, w4.y, w4.z, w4.w, tr);
+              for (int k4 = 0; k4 < 4; k4++) {
+                const uint4 w4 = sp[k4];
+                uint32_t tr[4];
+                transpose4x4_bytes(w4.x, w4.y, w4.z, w4.w, tr);
 #pragma unroll
-              for (int b4 = 0; b4 < 4; b4++) o4[b4][k4] = tr[b4];
-            }
-            const int ncol = n0 + (slot >> 3) * 32 + pass * 8 + (slot & 7);
-            int8_t* ob = p.out + (long long)batch * p.out_batch_stride + (long long)ncol * p.ldo + ti.m0 + mg * 16;
+                for (int b4 = 0; b4 < 4; b4++) o4[b4][k4] = tr[b4];
+              }
+              const int ncol = n0 + (slot / PC) * CW + pass * PC + (slot % PC);
+              int8_t* ob = p.out + (long long)batch * p.out_batch_stride + (long long)ncol * p.ldo + ti.m0 + mg * 16;
 #pragma unroll
-            for (int b4 = 4 - ONS / 2; b4 < 4; b4++) {  // byte b4 = digit 3 - b4 of its half (the top bytes are unused for six)
-              const int plane = hh * (ONS / 2) + 3 - b4;
-              *reinterpret_cast<uint4*>(ob + (long long)plane * p.out_plane_stride) =
-                  make_uint4(o4[b4][0], o4[b4][1], o4[b4][2], o4[b4][3]);
+              for (int b4 = 4 - ONS / 2; b4 < 4; b4++) {  // byte b4 = digit 3 - b4 of its half (the top bytes are unused for six)
+                const int plane = hh * (ONS / 2) + 3 - b4;
+                *reinterpret_cast<uint4*>(ob + (long long)plane * p.out_plane_stride) =
+                    make_uint4(o4[b4][0], o4[b4][1], o4[b4][2], o4[b4][3]);
+              }
             }
           }
         }
       }
+      // Column sums over the 32 rows of a warp by a butterfly transpose-reduce: stage o halves the values a lane holds and
+      // doubles the rows they cover; lane l ends with the sum of column (l mod CW).  (CW = 16: the two half-warps are summed
+      // first, both then hold the same 16 values.)
       if (p.dot_part && !(p.dbg & 8)) {
         const int vb = p.dvec_begin[batch], ve = p.dvec_begin[batch + 1];
         for (int qv = vb; qv < ve; qv++) {
           const int vec = p.dvec[qv];
           const double vm = p.dotV[(long long)vec * p.dotV_ld + row];
           double w[16];
-          {  // first butterfly stage on the fly: only 16 temporaries live
+          if constexpr (CW == 32) {  // first butterfly stage on the fly: only 16 temporaries live
             const bool up = (lane & 16) != 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
               const double a = v[i] * vm, b = v[i + 16] * vm;
               w[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const double a = v[i] * vm;
+              w[i] = a + __shfl_xor_sync(0xffffffffu, a, 16);
             }
           }
 #pragma unroll
@@ -625,9 +662,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
               w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
           }
-          asm volatile("bar.sync 2, 256;" ::: "memory");  // the previous use of `red` has been read by everyone
-          red[q * BN + c * 32 + lane] = w[0];
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 2, %0;" ::"n"(ETH) : "memory");  // the previous use of `red` has been read by everyone
+          if (lane < CW) red[q * BN + c * CW + lane] = w[0];
+          asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
           if (threadIdx.x < BN) {
             const int e = threadIdx.x;
             double* dst = p.dot_part + ((long long)vec * p.m_tiles + m_tile) * p.ld_ss + n0;
@@ -637,9 +674,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
       }
       if (p.ss_part && !(p.dbg & 8)) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] *= v[i];
+        for (int i = 0; i < CW; i++) v[i] *= v[i];
+        if constexpr (CW == 16) {
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
+          for (int i = 0; i < 16; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+        }
+#pragma unroll
+        for (int o = CW == 32 ? 16 : 8; o >= 1; o >>= 1) {
           const bool up = (lane & o) != 0;
 #pragma unroll
           for (int i = 0; i < o; i++) {
@@ -648,9 +689,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
           }
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");  // the previous tile's sums have been read by everyone
-        red[q * BN + c * 32 + lane] = v[0];
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+        asm volatile("bar.sync 2, %0;" ::"n"(ETH) : "memory");  // the previous tile's sums have been read by everyone
+        if (lane < CW) red[q * BN + c * CW + lane] = v[0];
+        asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");  // the epilogue warps only
         const int e = threadIdx.x;
         if (e < BN) {
           double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
@@ -660,7 +701,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_i8_sliced_kernel(const __grid
     }
   }
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == MMA_W) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
@@ -720,13 +761,13 @@ inline bool make_map_i8(CUtensorMap* map, const int8_t* ptr, int batch, int rows
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NS = MAX_NS>
+template <int NS = MAX_NS, int EW = 8>
 inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& p, int n_tiles, int batch,
                           cudaStream_t st) {
   constexpr int SMEM_BYTES = Cfg<NS>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_sliced_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_sliced_kernel<NS, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -745,7 +786,7 @@ inline cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
   Params q = p;
   q.n_tiles = n_tiles;
   q.batch = batch;
-  gemm_i8_sliced_kernel<NS><<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, q);
+  gemm_i8_sliced_kernel<NS, EW><<<grid, (EW + 2) * 32, SMEM_BYTES, st>>>(mapA, mapB, q);
   return cudaGetLastError();
 }
 
