@@ -111,6 +111,8 @@ struct mogpe_handle {
   // gradient-only products at six
   int fwd_ns = 8, fwd_maps_ns = 0;
   CUtensorMap tmf_linv, tmf_kuf, tmf_st, tmf_at;
+  // blocked-layout maps of the step (gns() planes): A planes as B operand of Lbar / A operand of Sbar, Abar^T planes for W
+  CUtensorMap tmb_ba64, tmb_ba128, tmb_abart;
   int gns() const { return grad_ns < fwd_ns ? grad_ns : fwd_ns; }
   double prof8_ops = 0;  // INT8 tensor operations of the timed launches (36 or 28 per algorithmic FLOP)
   // INT8 product timing in profiling mode (bench.py roofline of gemm_i8_sliced_kernel)
@@ -1557,8 +1559,9 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
     p.err_flag = h->d_t32_err;
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
     const bool g7 = h->gns() < 8;
-    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_bw : h->tm_bw, g7 ? h->tm7_ba64 : h->tm_ba64, p, n_tiles, Q, st, (double)Q * Mp * Mp * Bc,
-                          h->gns()));
+    p.b_blk = a8_ready ? 1 : 0;  // INT8 step: the A planes come from the A product's epilogue in the blocked layout
+    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_bw : h->tm_bw, a8_ready ? h->tmb_ba64 : (g7 ? h->tm7_ba64 : h->tm_ba64), p, n_tiles, Q, st,
+                          (double)Q * Mp * Mp * Bc, h->gns()));
   }
   if (md.nlta > 0) {
     const int nl = md.nlta;
@@ -1584,7 +1587,8 @@ static mogpe_status int8_backward_products(mogpe_handle* h, const double* params
       p.mapC[slot] = md.lta_latent[slot];
     }
     const bool g7 = h->gns() < 8;
-    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_ba128 : h->tm_ba128, g7 ? h->tm7_bld : h->tm_bld, p, n_tiles, nl, st,
+    p.a_blk = a8_ready ? 1 : 0;
+    H_CUDA(h, h_i8_launch(h, a8_ready ? h->tmb_ba128 : (g7 ? h->tm7_ba128 : h->tm_ba128), g7 ? h->tm7_bld : h->tm_bld, p, n_tiles, nl, st,
                           (double)nl * Mp * Mp * Bc, h->gns()));
   }
   H_CUDA(h, cudaGetLastError());
@@ -1640,7 +1644,10 @@ static mogpe_status ensure_i8_step(mogpe_handle* h) {
   }
   const int gs = h->gns();
   if (!oz::make_map_i8(&h->tm7_linvT, h->t8_LinvT, q, m, m, oz::BM, gs, 8) || !oz::make_map_i8(&h->tm7_s, h->t8_S, pp, m, m, oz::BM, gs, 8) ||
-      !oz::make_map_i8(&h->tm7_abart, h->t8_AbarT, q, b, m, oz::BN, gs, 8) || !oz::make_map_i8(&h->tm7_ltat, h->t8_LTAT, pp, b, m, oz::BN, gs, 8))
+      !oz::make_map_i8(&h->tm7_ltat, h->t8_LTAT, pp, b, m, oz::BN, gs, 8) ||
+      !oz::make_map_i8_blocked(&h->tmb_abart, h->t8_AbarT, q, b, m, oz::BN, gs, 8) ||
+      !oz::make_map_i8_blocked(&h->tmb_ba64, h->bA8, q, m, b, oz::BN, gs, 8) ||
+      !oz::make_map_i8_blocked(&h->tmb_ba128, h->bA8, q, m, b, oz::BM, gs, 8))
     return MOGPE_ERR_UNSUPPORTED;
   h->grad_maps_step_ns = gs;
   if (h->fwd_maps_ns != h->fwd_ns) {
@@ -1754,6 +1761,7 @@ static mogpe_status i8_step_forward(mogpe_handle* h, const double* params, const
       for (int slot = 0; slot < nl; slot++) p.out_mask |= 1ull << md.lta_group[slot];
     }
     p.outn = h->bA8; p.outn_batch_stride = (long long)NS * Mp * Bp; p.outn_plane_stride = (long long)Mp * Bp; p.ldn = Bp;
+    p.outn_blk_rows = Mp;  // blocked layout [n / 64][m][64]: read by abar8_kernel and by the Lbar / Sbar products
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
     const bool f6 = h->fwd_ns < 8;
     H_CUDA(h, h_i8_launch(h, f6 ? h->tmf_linv : h->tmt_linv, f6 ? h->tmf_kuf : h->tmt_kuf, p, Bc / oz::BN, Q, st,
@@ -1827,8 +1835,9 @@ static mogpe_status i8_step_backward_to_W(mogpe_handle* h, int N, int Bc, cudaSt
     p.out64 = h->W; p.out64_batch_stride = (long long)Mp * Bp; p.ld64 = Bp; p.alpha64 = 1.0; p.store64 = 1;
     p.rowmax64 = h->t8_wmax; p.rowmax64_stride = Mp;
     for (int g = 0; g < Q; g++) p.mapA[g] = p.mapB[g] = p.mapC[g] = g;
+    p.b_blk = 1;  // Abar^T planes: blocked layout (abar8_kernel)
     const bool g7 = h->gns() < 8;
-    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_linvT : h->tmt_linvT, g7 ? h->tm7_abart : h->tmt_abart, p, Bc / oz::BN, Q, st,
+    H_CUDA(h, h_i8_launch(h, g7 ? h->tm7_linvT : h->tmt_linvT, h->tmb_abart, p, Bc / oz::BN, Q, st,
                           (double)Q * Mp * Mp * Bc, h->gns()));
   }
   return MOGPE_OK;

@@ -105,6 +105,12 @@ struct Params {
   int8_t* outn;
   long long outn_batch_stride, outn_plane_stride;  // bytes
   int ldn;
+  // BLOCKED plane layout  [batch][plane][k / 64][row][64 bytes]  (make_map_i8_blocked): a 64-byte k-block of all rows is one
+  // contiguous run, so a tile of the operand is contiguous in HBM for the TMA loads of the consuming product and for the
+  // streaming kernels that read / write it.  a_blk / b_blk: the A / B operand of THIS product is stored that way (5-D tensor map);
+  // outn_blk_rows > 0: `outn` is written that way, with this many rows per k-block (ldn is then unused).
+  int a_blk, b_blk;
+  int outn_blk_rows;
   int* err_flag;
   int dbg;  // tuning switches (tools only): 1 skip `out` stores, 2 skip `outn` stores, 4 skip slicing, 8 skip ss, 16 skip FP64 stores, 32 skip all
   int mapA[64], mapB[64], mapC[64];
@@ -426,8 +432,11 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
           mbar_expect_tx(&full[s], STAGE_BYTES);
           const int k0 = ti.k_begin + kb * BKB;
           const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-          tma_load_4d(sa, &mapA, smem_u32(&full[s]), k0, ti.m0, 0, ca);  // {k, m, slice, batch}: all NS planes in one copy
-          tma_load_4d(sb, &mapB, smem_u32(&full[s]), k0, ti.n0, 0, cb);
+          // {k, m, slice, batch}: all NS planes in one copy  (blocked layout: {k in block, m, k block, slice, batch})
+          if (p.a_blk) tma_load_5d(sa, &mapA, smem_u32(&full[s]), 0, ti.m0, k0 / BKB, 0, ca);
+          else tma_load_4d(sa, &mapA, smem_u32(&full[s]), k0, ti.m0, 0, ca);
+          if (p.b_blk) tma_load_5d(sb, &mapB, smem_u32(&full[s]), 0, ti.n0, k0 / BKB, 0, cb);
+          else tma_load_4d(sb, &mapB, smem_u32(&full[s]), k0, ti.n0, 0, cb);
         }
       }
     }
@@ -568,7 +577,10 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
         const bool want_t = p.out != nullptr && (p.out_mask == 0ull || ((p.out_mask >> batch) & 1ull)) && !(p.dbg & 1);
         const bool want_n = p.outn != nullptr && !(p.dbg & 2);
         int8_t* orow = nullptr;  // [m][n] planes: this thread's row, CW consecutive columns
-        if (p.outn) orow = p.outn + (long long)batch * p.outn_batch_stride + (long long)row * p.ldn + col0;
+        if (p.outn)
+          orow = p.outn + (long long)batch * p.outn_batch_stride +
+                 (p.outn_blk_rows > 0 ? ((long long)(col0 / BKB) * p.outn_blk_rows + row) * BKB + (col0 % BKB)
+                                      : (long long)row * p.ldn + col0);
         const int e = threadIdx.x;  // 0 .. ETH - 1 over the epilogue warps
         uint32_t pn[ONS][CW / 4];   // outn: this thread's CW consecutive columns of every plane
 #pragma unroll
@@ -757,6 +769,21 @@ inline bool make_map_i8(CUtensorMap* map, const int8_t* ptr, int batch, int rows
   cuuint32_t box[4] = {BKB, (cuuint32_t)box_rows, (cuuint32_t)NS, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// the same planes in the BLOCKED layout [batch][planes_total][cols / 64][rows][64]: box {64, box_rows, 1 k-block, NS planes, 1}
+inline bool make_map_i8_blocked(CUtensorMap* map, const int8_t* ptr, int batch, int rows, int cols, int box_rows, int NS = MAX_NS,
+                                int planes_total = 0) {
+  t32::EncodeTiledFn fn = t32::encode_fn();
+  if (!fn || cols % BKB != 0) return false;
+  if (planes_total <= 0) planes_total = NS;
+  cuuint64_t dims[5] = {(cuuint64_t)BKB, (cuuint64_t)rows, (cuuint64_t)(cols / BKB), (cuuint64_t)NS, (cuuint64_t)batch};
+  cuuint64_t strides[4] = {(cuuint64_t)BKB, (cuuint64_t)rows * BKB, (cuuint64_t)rows * cols, (cuuint64_t)planes_total * rows * cols};
+  cuuint32_t box[5] = {BKB, (cuuint32_t)box_rows, 1, (cuuint32_t)NS, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<int8_t*>(ptr), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

@@ -116,7 +116,8 @@ __global__ void max_to_scale_kernel(const unsigned long long* __restrict__ mx, d
 // A comes from its [m][n] byte planes (written by the epilogue of the A product; 2^e = a_scale[g]); the result is sliced
 // against a per-COLUMN scale from a rigorous bound (|A[m][n]| <= sqrt(var0ss[n]), |P2[m][n]| <= max_m |S[m, :]|_2 sqrt(varq[n]),
 // |V[v][m]| <= vmax[v]) -- a column scale commutes with the left multiplication by L^-T (gemm_i8 b_row_scale) -- and goes out
-// as AbarT8[g][plane][n][m] through a shared-memory transpose.        grid (Bc/64, Mp/64, Q), block 256
+// as AbarT8[g][plane][m / 64][n][64] (the blocked plane layout of gemm_i8.cuh, like the A planes it reads) through a
+// shared-memory transpose.        grid (Bc/64, Mp/64, Q), block 256
 // sign-extended byte J of w
 template <int J>
 __device__ __forceinline__ int sbyte(uint32_t w) {
@@ -215,7 +216,9 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
     const int ml = pass * 16 + r, m = m0 + ml;
     uint32_t w[NS];
 #pragma unroll
-    for (int s2 = 0; s2 < NS; s2++) w[s2] = *reinterpret_cast<const uint32_t*>(Ag + s2 * plane + (long long)m * Bp + nn);
+    // (A planes in the blocked layout [n / 64][m][64]: the 64 x 64 tile of a plane is one contiguous 4 KB run)
+    for (int s2 = 0; s2 < NS; s2++)
+      w[s2] = *reinterpret_cast<const uint32_t*>(Ag + s2 * plane + ((long long)blockIdx.x * Mp + m) * 64 + c4);
     double a[4];
     unslice4<NS>(w, a);
 #pragma unroll
@@ -274,7 +277,8 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
 #pragma unroll
       for (int b4 = 0; b4 < 4; b4++) o4[b4][k4] = tr[b4];
     }
-    int8_t* ob = Og + (long long)(n0 + n) * Mp + m0 + mg * 16;
+    // (blocked over m: [m / 64][n][64] -- the tile is contiguous again)
+    int8_t* ob = Og + ((long long)blockIdx.y * Bp + n0 + n) * 64 + mg * 16;
 #pragma unroll
     for (int b4 = 4 - NS / 2; b4 < 4; b4++) {  // byte b4 of a slice word = digit 3 - b4 of its half
       const int pl = half * (NS / 2) + 3 - b4;
