@@ -519,7 +519,7 @@ def main():
     if i8_on:
         traffic, traffic_note = measured_traffic("gemm_i8_A")
         roof = {
-            "bound": "tensor", "kernel": "mogpe::oz::gemm_i8_sliced_kernel<8> (tcgen05.mma kind::i8 + TMA + TMEM; the six dense "
+            "bound": "tensor", "kernel": "mogpe::oz::gemm_i8_sliced_kernel<NS, EW> (tcgen05.mma kind::i8 + TMA + TMEM; the six dense "
                                          "products of a step: A = L^-1 Kuf, S^T A, S S^T A, W = L^-T Abar, Lbar, Sbar)",
             "achieved": i8_tops, "peak": i8_peak, "unit": "TOP/s", "frac": i8_tops / i8_peak,
             "peak_source": "INT8 tensor-pipe issue peak measured in THIS run by mogpe_probe_int8_tensor_peak (back-to-back "
@@ -536,8 +536,9 @@ def main():
             "step_model_tflops": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12,
             "step_model_vs_fp64_tensor_peak": step_flops(wl, B) * steps / (ms * 1e-3) * 1e-12 / fp64_peak,
             "what_bounds_it": "per 64-wide k-block a CTA ingests 96 KB of operand planes by TMA and the MMAs read 208 KB from "
-                              "shared memory for 2438 tensor cycles: the main loop sits at the shared-memory / L2->SM bandwidth "
-                              "(DESIGN.md section 4c); short triangular tiles (K <= 512) add the TMEM drain per tile",
+                              "shared memory for 2438 tensor cycles: the main loop sits at the shared-memory bandwidth (~60 % of the "
+                              "issue peak); at K <= 512 the period of a tile is TMEM drain + max(main loop, rest of the epilogue) "
+                              "and the epilogue (FP64 re-slicing, statistics, plane stores) is the longer one (DESIGN.md 4d)",
             "traffic": traffic, "traffic_note": traffic_note,
             "fp64_dmma": dmma, "fp64_tensor_peak_tflops": fp64_peak,
         }
