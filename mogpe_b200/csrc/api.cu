@@ -871,6 +871,7 @@ extern "C" mogpe_status mogpe_elbo_fwd_bwd(mogpe_handle* h, const double* X, con
   // ---------------- forward ----------------
   // The whole step on the INT8 tensor cores (eight exact byte slices: FP64-class results) when the shape qualifies
   bool i8_step = false;
+  h->ld8_pending = h->linvT_pending = false;  // (a call that failed half-way must not leave a stale hand-over behind)
   if (grads && h->i8_step_on && h->i8_bwd_on && i8_step_shape_ok(h, Bc)) {
     const mogpe_status erc = ensure_i8_step(h);
     if (erc == MOGPE_OK) i8_step = true;
