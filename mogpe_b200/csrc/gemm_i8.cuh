@@ -183,18 +183,12 @@ __device__ __forceinline__ void transpose4x4_bytes(uint32_t w0, uint32_t w1, uin
 // adding 64 to every base-128 digit turns the balanced digits of the signed 7 NS / 2-bit integer into the plain bit fields of
 // a non-negative one (the top field runs to 128), three shift-and-mask steps spread the fields to byte lanes, and one
 // per-byte subtraction removes the bias.
+// hi, lo: the two signed 7 NS / 2-bit halves of round(r 2^(7 NS))  ->  the digit words
 template <int NS>
-__device__ __forceinline__ void slice_words(double r, uint32_t& wh, uint32_t& wl) {
-  static_assert(NS == 8 || NS == 6, "eight or six slices");
+__device__ __forceinline__ void halves_to_words(int hi_i, int lo_i, uint32_t& wh, uint32_t& wl) {
   constexpr int H = NS / 2;
-  constexpr double P = (double)(1 << (7 * H));
-  constexpr double C = 6755399441055744.0;  // 1.5 * 2^52
-  const double x1 = r * P;
-  const double y1 = x1 + C;
-  const double rem = x1 - (y1 - C);
-  const double y2 = fma(rem, P, C);
   constexpr int BIAS = H == 4 ? 64 * (1 + 128 + 16384 + 2097152) : 64 * (1 + 128 + 16384);
-  const uint32_t hi = (uint32_t)(__double2loint(y1) + BIAS), lo = (uint32_t)(__double2loint(y2) + BIAS);
+  const uint32_t hi = (uint32_t)(hi_i + BIAS), lo = (uint32_t)(lo_i + BIAS);
   constexpr int SH = H == 4 ? 0 : 7;  // H = 3: the 21-bit value sits one field lower
   const uint32_t sh = ((hi << (3 + SH)) & 0xff000000u) | ((hi << (2 + SH)) & 0x007f0000u) | ((hi << (1 + SH)) & 0x00007f00u) |
                       (H == 4 ? (hi & 0x7fu) : 0x40u);
@@ -205,6 +199,43 @@ __device__ __forceinline__ void slice_words(double r, uint32_t& wh, uint32_t& wl
   // the byte's own bit 7 is set, i.e. u = 128)
   wh = ((sh & 0x7f7f7f7fu) + 0x40404040u) ^ (~sh & 0x80808080u);
   wl = ((sl & 0x7f7f7f7fu) + 0x40404040u) ^ (~sl & 0x80808080u);
+}
+
+template <int NS>
+__device__ __forceinline__ void slice_words(double r, uint32_t& wh, uint32_t& wl) {
+  static_assert(NS == 8 || NS == 6, "eight or six slices");
+  constexpr int H = NS / 2;
+  constexpr double P = (double)(1 << (7 * H));
+  constexpr double C = 6755399441055744.0;  // 1.5 * 2^52
+  const double x1 = r * P;
+  const double y1 = x1 + C;
+  const double rem = x1 - (y1 - C);
+  const double y2 = fma(rem, P, C);
+  halves_to_words<NS>(__double2loint(y1), __double2loint(y2), wh, wl);
+}
+
+// The same digits of r = v * 2^eo (|r| <= 1/2) WITHOUT a single FP64 instruction: R = round(r 2^(7 NS)) is a rounded shift of
+// v's 53-bit mantissa, and its two balanced halves are a sign extension and a subtraction.  ~25 integer instructions instead of
+// 6 FP64 ones -- for the epilogue of gemm_i8_sliced_kernel, whose FP64 instructions after the TMEM drain share the issue pipe
+// with the tensor instructions of the next tile and stall on it (ncu: 44 % of the A product's warp samples were `stall_math`
+// on the five FP64 instructions of slice_words).  Rounds half away from zero where slice_words rounds half to even: a
+// difference of one unit of the last digit (2^-57) in exact ties only.
+template <int NS>
+__device__ __forceinline__ void slice_words_int(double v, int eo, uint32_t& wh, uint32_t& wl) {
+  static_assert(NS == 8 || NS == 6, "eight or six slices");
+  constexpr int B = 7 * (NS / 2), TB = 2 * B;
+  const int hiw = __double2hiint(v);
+  const int ef = (hiw >> 20) & 0x7ff;  // biased exponent: v = (-1)^s M 2^(ef - 1075), M = mantissa with the implicit one
+  unsigned long long M = ((unsigned long long)(uint32_t)((hiw & 0xfffff) | 0x100000) << 32) | (uint32_t)__double2loint(v);
+  if (ef == 0) M = 0;
+  // R = M 2^(ef - 1075 + eo + TB);  |r| <= 1/2 bounds the exponent by TB - 53 <= 3, so with M << 3 the shift is to the right
+  int t = 3 - (ef - 1075 + eo + TB);
+  t = t < 0 ? 0 : (t > 63 ? 63 : t);
+  const unsigned long long Ru = ((M << 3) + ((1ull << t) >> 1)) >> t;
+  const long long R = hiw < 0 ? -(long long)Ru : (long long)Ru;
+  const int lo = (int)((uint32_t)R << (32 - B)) >> (32 - B);  // balanced low half: sign-extended low B bits
+  const int hi = (int)((R - (long long)lo) >> B);
+  halves_to_words<NS>(hi, lo, wh, wl);
 }
 
 // Called by ALL lanes of the (converged) MMA warp: elect.sync picks the issuing lane, so the SASS is one predicated UTCIMMA
@@ -501,7 +532,10 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
       // 2^(ea + eb) * 2^(-14): T_d carries 2^(-7 (d + 2))
       const double rs = p.a_scale[(long long)p.mapA[batch] * p.a_scale_stride + row] *
                         (p.b_row_scale ? 1.0 : p.b_scale[p.mapB[batch]]) * (1.0 / 16384.0);
-      const double oinv = (p.out || p.outn) ? 1.0 / p.out_scale[batch] : 0.0;
+      // plane outputs are sliced against out_scale[batch] = 2^e (a power of two: only its exponent is needed)
+      const double oscale = (p.out || p.outn) ? p.out_scale[batch] : 1.0;
+      const double oinv = 1.0 / oscale;
+      const int oexp = 1023 - ((__double2hiint(oscale) >> 20) & 0x7ff);
       // sum_d T_d 128^-d by a Horner recurrence in FP64 from the least significant accumulator: the int32 -> double
       // conversions use the 2^52 trick (one LOP3 + one DADD on the FP64 pipe, no conversion unit) -- 3 instructions per
       // accumulator value instead of ~5 for the 64-bit integer recurrence; the rounding of the recurrence is 2^-53 of the
@@ -587,7 +621,11 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
         for (int pass = 0; pass < 4; pass++) {
           uint32_t wh[PC], wl[PC];
 #pragma unroll
-          for (int j = 0; j < PC; j++) slice_words<ONS>(v[pass * PC + j] * oinv, wh[j], wl[j]);
+          for (int j = 0; j < PC; j++) {
+            // eight epilogue warps: integer slicing (A: 850 -> 800 us); sixteen (96 registers): the FP64 version is faster
+            if constexpr (EW == 8) slice_words_int<ONS>(v[pass * PC + j], oexp, wh[j], wl[j]);
+            else slice_words<ONS>(v[pass * PC + j] * oinv, wh[j], wl[j]);
+          }
           if (want_n) {
 #pragma unroll
             for (int g4 = 0; g4 < PC / 4; g4++) {

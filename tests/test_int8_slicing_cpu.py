@@ -128,3 +128,35 @@ def test_unslice4_dp4a_restatement(H):
     assert val.max() < 2 ** 32
     ref = sum(d[:, k] * 128 ** (H - 1 - k) for k in range(H))
     assert np.array_equal(val - bias, ref)
+
+
+@pytest.mark.parametrize("NS", [6, 8])
+def test_integer_slicing_restatement(NS):
+    """gemm_i8.cuh: slice_words_int -- the digits of r = v 2^eo from v's bit pattern with integer operations only: R =
+    round(r 2^(7 NS)) as a rounded right shift of the mantissa (M << 3), the balanced low half by sign extension, the high half
+    by subtraction.  R must equal the correctly rounded value (ties away from zero) and the halves must be balanced."""
+    import struct
+
+    B, TB = 7 * (NS // 2), 7 * NS
+    rng = np.random.default_rng(NS)
+    vals = np.concatenate([rng.uniform(-0.5, 0.5, 20000) * 2.0 ** rng.integers(-60, 1, 20000),
+                           [0.0, 0.5, -0.5, 2.0 ** -57, -(2.0 ** -58), 0.5 - 2.0 ** -54, 1.5 * 2.0 ** -57]])
+    for r in vals:
+        eo = int(rng.integers(-40, 41))
+        v = float(r) * 2.0 ** (-eo)  # the kernel sees v and the exponent of the output scale
+        bits = struct.unpack("<q", struct.pack("<d", v))[0]
+        hiw = (bits >> 32) & 0xFFFFFFFF
+        ef = (hiw >> 20) & 0x7FF
+        M = ((((hiw & 0xFFFFF) | 0x100000) << 32) | (bits & 0xFFFFFFFF)) if ef else 0
+        t = min(max(3 - (ef - 1075 + eo + TB), 0), 63)
+        Ru = (((M << 3) + ((1 << t) >> 1)) & (2 ** 64 - 1)) >> t
+        R = -Ru if bits < 0 else Ru
+        lo = ((R & (2 ** B - 1)) ^ (1 << (B - 1))) - (1 << (B - 1))  # sign-extended low B bits
+        hi = (R - lo) >> B
+        # exact reference: round half away from zero of r 2^TB in integer arithmetic
+        from fractions import Fraction
+
+        x = Fraction(float(r)) * 2 ** TB
+        want = int(abs(x) + Fraction(1, 2)) * (1 if x >= 0 else -1)
+        assert R == want, (r, eo, R, want)
+        assert hi * 2 ** B + lo == R and -(2 ** (B - 1)) <= lo < 2 ** (B - 1) and abs(hi) <= 2 ** (B - 1)
