@@ -530,8 +530,10 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
       const int row = ti.m0 + q * 32 + lane;
       const int col0 = n0 + c * CW;  // first of this thread's CW consecutive columns
       // 2^(ea + eb) * 2^(-14): T_d carries 2^(-7 (d + 2))
+      // (the factor of an accumulated FP64 result rides along: such a product has no other output)
       const double rs = p.a_scale[(long long)p.mapA[batch] * p.a_scale_stride + row] *
-                        (p.b_row_scale ? 1.0 : p.b_scale[p.mapB[batch]]) * (1.0 / 16384.0);
+                        (p.b_row_scale ? 1.0 : p.b_scale[p.mapB[batch]]) * (1.0 / 16384.0) *
+                        ((p.out64 && !p.store64) ? p.alpha64 : 1.0);
       // plane outputs are sliced against out_scale[batch] = 2^e (a power of two: only its exponent is needed)
       const double oscale = (p.out || p.outn) ? p.out_scale[batch] : 1.0;
       const double oinv = 1.0 / oscale;
@@ -563,11 +565,8 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
 #pragma unroll
         for (int i = 0; i < CW; i++) v[i] *= rs;
       }
-      // every accumulator value of this warp is in registers: TMEM may be overwritten by the next tile's MMAs
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty)) : "memory");
-      if (p.dbg & 32) continue;
+      // FP64 work is cheapest HERE: after the release below the next tile's tensor instructions own the issue pipe that FP64
+      // shares with them, and every DMUL / DADD of this warp waits for a gap (stall_math)
       if (p.b_row_scale) {
         const double2* bs = reinterpret_cast<const double2*>(p.b_row_scale + (long long)p.mapB[batch] * p.b_row_scale_stride + col0);
 #pragma unroll
@@ -577,27 +576,111 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
           v[2 * i + 1] *= b2.y;
         }
       }
+      auto do_dot = [&]() {
+        const int vb = p.dvec_begin[batch], ve = p.dvec_begin[batch + 1];
+        for (int qv = vb; qv < ve; qv++) {
+          const int vec = p.dvec[qv];
+          const double vm = p.dotV[(long long)vec * p.dotV_ld + row];
+          double w[16];
+          if constexpr (CW == 32) {  // first butterfly stage on the fly: only 16 temporaries live
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const double a = v[i] * vm, b = v[i + 16] * vm;
+              w[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const double a = v[i] * vm;
+              w[i] = a + __shfl_xor_sync(0xffffffffu, a, 16);
+            }
+          }
+#pragma unroll
+          for (int o = 8; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; i++) {
+              const double send = up ? w[i] : w[i + o];
+              const double keep = up ? w[i + o] : w[i];
+              w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(ETH) : "memory");  // the previous use of `red` has been read by everyone
+          if (lane < CW) red[q * BN + c * CW + lane] = w[0];
+          asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+          if (threadIdx.x < BN) {
+            const int e = threadIdx.x;
+            double* dst = p.dot_part + ((long long)vec * p.m_tiles + m_tile) * p.ld_ss + n0;
+            dst[e] = (red[e] + red[BN + e]) + (red[2 * BN + e] + red[3 * BN + e]);
+          }
+        }
+            };
+      auto do_ss = [&]() {  // column sums of squares; v is left intact (16 temporaries)
+        double w[16];
+        if constexpr (CW == 32) {
+          const bool up = (lane & 16) != 0;
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const double a = v[i] * v[i], b = v[i + 16] * v[i + 16];
+            w[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const double a = v[i] * v[i];
+            w[i] = a + __shfl_xor_sync(0xffffffffu, a, 16);
+          }
+        }
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < o; i++) {
+            const double send = up ? w[i] : w[i + o];
+            const double keep = up ? w[i + o] : w[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(ETH) : "memory");  // the previous use of `red` has been read by everyone
+        if (lane < CW) red[q * BN + c * CW + lane] = w[0];
+        asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");  // the epilogue warps only
+        const int e = threadIdx.x;
+        if (e < BN) {
+          double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
+          dst[e] = (red[e] + red[BN + e]) + (red[2 * BN + e] + red[3 * BN + e]);
+        }
+      };
+      // the statistics (FP64 multiplies and adds) belong before the release for the same reason: A 830 -> 800 us (same-box A / B)
+      if (p.dot_part && !(p.dbg & 8)) do_dot();
+      if (p.ss_part && !(p.dbg & 8)) do_ss();
+      // every accumulator value of this warp is in registers: TMEM may be overwritten by the next tile's MMAs
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty)) : "memory");
+      if (p.dbg & 32) continue;
       if (p.out64 && p.store64) {
         double* o = p.out64 + (long long)p.mapC[batch] * p.out64_batch_stride + (long long)row * p.ld64 + col0;
         const double* cs = p.col64 ? p.col64 + (long long)p.mapS64[batch] * p.col64_stride + col0 : nullptr;
-        double mx = 0.0;
+        const bool plain = p.alpha64 == 1.0 && cs == nullptr;  // (uniform) nothing to multiply: no FP64 instruction at all
+        unsigned long long mxb = 0ull;  // max |w| as a bit pattern (non-negative doubles order like their bit patterns)
 #pragma unroll
         for (int i = 0; i < CW; i += 4) {
           double w[4];
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            w[j] = p.alpha64 * v[i + j] * (cs ? cs[i + j] : 1.0);
-            mx = fmax(mx, fabs(w[j]));
+            w[j] = plain ? v[i + j] : p.alpha64 * v[i + j] * (cs ? cs[i + j] : 1.0);
+            const unsigned long long b = (unsigned long long)__double_as_longlong(w[j]) & 0x7fffffffffffffffull;
+            mxb = b > mxb ? b : mxb;
           }
           if (!(p.dbg & 16)) st_global_256(o + i, w[0], w[1], w[2], w[3]);
         }
-        if (p.rowmax64)
-          atomicMax(p.rowmax64 + (long long)p.mapC[batch] * p.rowmax64_stride + row, (unsigned long long)__double_as_longlong(mx));
+        if (p.rowmax64) atomicMax(p.rowmax64 + (long long)p.mapC[batch] * p.rowmax64_stride + row, mxb);
       } else if (p.out64) {
         double* o = p.out64 + (long long)p.mapC[batch] * p.out64_batch_stride + (long long)row * p.ld64 + col0;
 #pragma unroll
         for (int i = 0; i < CW; i++)
-          if (!p.tril64 || col0 + i <= row) atomicAdd(o + i, p.alpha64 * v[i]);
+          if (!p.tril64 || col0 + i <= row) atomicAdd(o + i, v[i]);  // (alpha64 is part of rs)
       }
       if ((p.out || p.outn) && !(p.dbg & 4)) {
         // (ONS planes: eight for a product that loaded seven -- the consumers read eight-plane operands, and a 49-bit result
@@ -622,7 +705,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
           uint32_t wh[PC], wl[PC];
 #pragma unroll
           for (int j = 0; j < PC; j++) {
-            // eight epilogue warps: integer slicing (A: 850 -> 800 us); sixteen (96 registers): the FP64 version is faster
+            // eight epilogue warps: integer slicing (A: 850 -> 800 us); sixteen (96 registers): no difference, FP64 kept
             if constexpr (EW == 8) slice_words_int<ONS>(v[pass * PC + j], oexp, wh[j], wl[j]);
             else slice_words<ONS>(v[pass * PC + j] * oinv, wh[j], wl[j]);
           }
@@ -682,72 +765,6 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_i8_sliced_kernel(const 
       // Column sums over the 32 rows of a warp by a butterfly transpose-reduce: stage o halves the values a lane holds and
       // doubles the rows they cover; lane l ends with the sum of column (l mod CW).  (CW = 16: the two half-warps are summed
       // first, both then hold the same 16 values.)
-      if (p.dot_part && !(p.dbg & 8)) {
-        const int vb = p.dvec_begin[batch], ve = p.dvec_begin[batch + 1];
-        for (int qv = vb; qv < ve; qv++) {
-          const int vec = p.dvec[qv];
-          const double vm = p.dotV[(long long)vec * p.dotV_ld + row];
-          double w[16];
-          if constexpr (CW == 32) {  // first butterfly stage on the fly: only 16 temporaries live
-            const bool up = (lane & 16) != 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-              const double a = v[i] * vm, b = v[i + 16] * vm;
-              w[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-              const double a = v[i] * vm;
-              w[i] = a + __shfl_xor_sync(0xffffffffu, a, 16);
-            }
-          }
-#pragma unroll
-          for (int o = 8; o >= 1; o >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < o; i++) {
-              const double send = up ? w[i] : w[i + o];
-              const double keep = up ? w[i + o] : w[i];
-              w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-            }
-          }
-          asm volatile("bar.sync 2, %0;" ::"n"(ETH) : "memory");  // the previous use of `red` has been read by everyone
-          if (lane < CW) red[q * BN + c * CW + lane] = w[0];
-          asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
-          if (threadIdx.x < BN) {
-            const int e = threadIdx.x;
-            double* dst = p.dot_part + ((long long)vec * p.m_tiles + m_tile) * p.ld_ss + n0;
-            dst[e] = (red[e] + red[BN + e]) + (red[2 * BN + e] + red[3 * BN + e]);
-          }
-        }
-      }
-      if (p.ss_part && !(p.dbg & 8)) {
-#pragma unroll
-        for (int i = 0; i < CW; i++) v[i] *= v[i];
-        if constexpr (CW == 16) {
-#pragma unroll
-          for (int i = 0; i < 16; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-        }
-#pragma unroll
-        for (int o = CW == 32 ? 16 : 8; o >= 1; o >>= 1) {
-          const bool up = (lane & o) != 0;
-#pragma unroll
-          for (int i = 0; i < o; i++) {
-            const double send = up ? v[i] : v[i + o];
-            const double keep = up ? v[i + o] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-          }
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(ETH) : "memory");  // the previous tile's sums have been read by everyone
-        if (lane < CW) red[q * BN + c * CW + lane] = v[0];
-        asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");  // the epilogue warps only
-        const int e = threadIdx.x;
-        if (e < BN) {
-          double* dst = p.ss_part + ((long long)batch * p.m_tiles + m_tile) * p.ld_ss + n0;
-          dst[e] = (red[e] + red[BN + e]) + (red[2 * BN + e] + red[3 * BN + e]);
-        }
-      }
     }
   }
   __syncthreads();
