@@ -99,12 +99,12 @@ struct mogpe_handle {
   unsigned long long* t8_bound_bits = nullptr;             // [2 P + NVcap] atomicMax scratch of bounds_kernel
   unsigned long long* t8_ltamax = nullptr;                 // [P][Mp] row maxima of LTA | [P] maxima of |dfvar| per latent
   int t8_vmax_cap = 0;
-  CUtensorMap tmt_linv, tmt_linvT, tmt_st, tmt_s, tmt_kuf, tmt_at, tmt_abart, tmt_ltat;
+  CUtensorMap tmt_linv, tmt_linvT, tmt_st, tmt_s, tmt_kuf, tmt_at, tmt_ltat;
   // the gradient-only products (S LTA, W, Lbar, Sbar) may load only the seven most significant planes of their operands
   // (49 bits: 28 instead of 36 slice pairs; the 1e-6 gradient tolerance has ~4 decimal digits to spare)
   int grad_ns = 7;
   int grad_maps_bwd_ns = 0, grad_maps_step_ns = 0;  // slice count the partial-load tensor maps were built for
-  CUtensorMap tm7_linvT, tm7_s, tm7_abart, tm7_ltat, tm7_bw, tm7_ba64, tm7_ba128, tm7_bld;
+  CUtensorMap tm7_linvT, tm7_s, tm7_ltat, tm7_bw, tm7_ba64, tm7_ba128, tm7_bld;
   // slices loaded by the two forward products (A = L^-1 Kuf, S^T A): 8 by default; 7 is measured float64-class as well (ELBO
   // 1e-10, gradients 1.6e-8 of the FP64 step on the ill-conditioned stress model) but buys only 0.07 ms at C4 for 16x less
   // gradient margin, so it is opt-in; 6 = fast training mode (the "1e-4 class" of north_star), which also caps the
@@ -1639,7 +1639,7 @@ static mogpe_status ensure_i8_step(mogpe_handle* h) {
     if (!oz::make_map_i8(&h->tmt_linv, h->t8_Linv, q, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_linvT, h->t8_LinvT, q, m, m, oz::BM) ||
         !oz::make_map_i8(&h->tmt_st, h->t8_ST, pp, m, m, oz::BM) || !oz::make_map_i8(&h->tmt_s, h->t8_S, pp, m, m, oz::BM) ||
         !oz::make_map_i8(&h->tmt_kuf, h->t8_KufT, q, b, m, oz::BN) || !oz::make_map_i8(&h->tmt_at, h->t8_AT, q, b, m, oz::BN) ||
-        !oz::make_map_i8(&h->tmt_abart, h->t8_AbarT, q, b, m, oz::BN) || !oz::make_map_i8(&h->tmt_ltat, h->t8_LTAT, pp, b, m, oz::BN))
+        !oz::make_map_i8(&h->tmt_ltat, h->t8_LTAT, pp, b, m, oz::BN))
       return MOGPE_ERR_UNSUPPORTED;
     h->i8_step_ready = true;
   }
