@@ -365,7 +365,8 @@ extern "C" mogpe_status mogpe_create(const mogpe_desc* d, mogpe_handle** out) {
     }
   h->precision = d->precision;
   h->ns = d->precision == MOGPE_PRECISION_INT8X6 ? 6 : 8;
-  h->Mp = round_up(Mmax, 64);
+  // (above 512 inducing points the padded size is a multiple of the 128-row tensor-core tile, so that the INT8 step applies)
+  h->Mp = Mmax > 512 ? round_up(Mmax, 128) : round_up(Mmax, 64);
   h->Mp32 = round_up(h->Mp, t32::BM);
   h->Bp = round_up(d->max_batch, h->precision != MOGPE_PRECISION_F64 ? t32::BN : 128);
   h->Pe = d->num_experts * d->output_dim;

@@ -344,6 +344,33 @@ def test_int8_step_general_structures_match_oracle(bound, K, F, S, sep):
     eng.close()
 
 
+def test_int8_step_applies_above_512_inducing_points():
+    """M = 520 is padded to 640 (a multiple of the 128-row tile), so the step runs on the INT8 tensor cores; the 120 padding
+    rows / columns of every operand must stay inert (unit diagonal in Kuu, zero elsewhere)."""
+    from oracle import ref_torch as rt
+    from tests._engine_helpers import engine_from_spec, engine_grads_named, oracle_grads_constrained, run_engine_elbo
+
+    N = 2048
+    spec, X, Y, eps = make_spec(seed=77, N=N, D=2, F=1, K=2, M=520, S=1, flavour="keras", bound="further_gating", num_data=40000)
+    eng = engine_from_spec(spec, max_batch=N)
+    assert eng.Mp == 640
+    ref, grads_u = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    want = oracle_grads_constrained(spec, grads_u)
+    eng.profile(True)
+    res = run_engine_elbo(eng, spec, X, Y, eps)
+    assert eng.profile_read_int8()["launches"] == 6
+    eng.profile(False)
+    assert abs(res.elbo - ref) <= RTOL_VALUE * abs(ref), (res.elbo, ref)
+    got = engine_grads_named(res, spec)
+    bad = {}
+    for name, g in want.items():
+        err = np.max(np.abs(np.asarray(got[name]) - g))
+        if err > RTOL_GRAD * max(1.0, np.max(np.abs(g))):
+            bad[name] = err / max(1.0, np.max(np.abs(g)))
+    assert not bad, bad
+    eng.close()
+
+
 @pytest.mark.parametrize("D", [1, 6])
 def test_int8_step_input_dimensions_match_oracle(D):
     """The INT8 step for input dimensions on either side of the bench's D = 4: D = 1 (kuf8_kernel<2>, padded 4-wide records of
