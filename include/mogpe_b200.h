@@ -202,7 +202,7 @@ mogpe_status mogpe_comm_init(mogpe_handle* h, const char id[128], int32_t rank, 
 mogpe_status mogpe_allreduce_sum(mogpe_handle* h, double* buf, int64_t n, void* cuda_stream);
 /* The two [M x M] results of the backward that are reduced over the minibatch (Lbar = -tril(W A^T), Sbar = 2 tril(A diag(d)
  * LTA^T)) run on the INT8 tensor cores with integer-sliced operands and exact accumulation (FP64-class accuracy, section 4c of
- * DESIGN.md) when M is a multiple of 128, M >= 512 and the batch has >= 2048 rows; on (default) / off selects it. */
+ * DESIGN.md) when the padded M is >= 512 (M > 448; above 512 the library pads to multiples of 128) and the batch has >= 2048 rows; on (default) / off selects it. */
 mogpe_status mogpe_set_int8_backward(mogpe_handle* h, int32_t on);
 /* The WHOLE gradient step on the INT8 tensor cores under the same shape conditions (default on; needs the INT8 backward on):
  * A = L^-1 Kuf, S^T A, S (S^T A) and W = L^-T Abar also run as integer-sliced products (tcgen05 kind::i8, eight exact byte

@@ -64,7 +64,7 @@ class Engine:
         """precision of the M x M x N products of predict() and of gradient-free elbo() calls: "float64" (gpflow
         default_float; FP64 DMMA), "int8" / "int8x6" (INT8 tensor cores, integer-sliced operands with exact accumulation:
         8 slices are float64-accurate, 6 slices ~1e-7), "tf32" (3xTF32 on the tcgen05 tensor cores, FP32-class accuracy).
-        Calls with gradients always produce float64-accurate results: FP64 DMMA, and -- for M >= 512 (multiple of 128) and
+        Calls with gradients always produce float64-accurate results: FP64 DMMA, and -- for more than 448 inducing points and
         >= 2048 rows -- the dense products on the INT8 tensor cores with eight exact byte slices (set_int8_backward(False)
         keeps everything on the FP64 pipe)."""
         self.lib = _lib.load()
