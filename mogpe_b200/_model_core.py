@@ -23,6 +23,13 @@ def _lib_check(status):
     _lib.check(status)
 
 
+def _active_dims(gp: SVGP):
+    """Per latent kernel: the input columns it reads (gpflow active_dims), or None when every kernel reads all of them."""
+    D = int(np.asarray(gp.Z.numpy()).shape[1])
+    cols = [k.active_columns(D) if hasattr(k, "active_columns") else None for k in gp.latent_kernel_list]
+    return None if all(c is None for c in cols) else cols
+
+
 def svgp_to_block(gp: SVGP, is_expert: bool) -> GPBlock:
     L = gp.num_latent_gps
     mean_c = None
@@ -41,6 +48,7 @@ def svgp_to_block(gp: SVGP, is_expert: bool) -> GPBlock:
         q_sqrt=gp.q_sqrt.numpy(),
         mean_c=mean_c,
         noise=noise,
+        active_dims=_active_dims(gp),
     )
 
 
@@ -224,7 +232,7 @@ class MixtureCore:
                 variances=[float(np.asarray(value_of(k.variance))) for k in gp.latent_kernel_list],
                 q_mu=np.asarray(value_of(gp.q_mu), dtype=np.float64),
                 q_sqrt=np.asarray(tri_of(gp.q_sqrt), dtype=np.float64),
-                mean_c=mean_c, noise=noise))
+                mean_c=mean_c, noise=noise, active_dims=_active_dims(gp)))
         return blocks[:-1], blocks[-1]
 
     def setup_device_optimizer(self, batch: int):
@@ -253,7 +261,7 @@ class MixtureCore:
                 return ids[id(p)][0] if p.trainable else np.zeros(p.unconstrained.shape)
 
             tri = lambda p: p.transform.forward(ids_of(p))  # FillTriangular of the id vector: ids land where the values do
-            flat_ids = eng.pack(*self._packed_blocks(ids_of, tri)).astype(np.int64)
+            flat_ids = eng.pack(*self._packed_blocks(ids_of, tri), inactive=0.0).astype(np.int64)
             uniq, first, inv = np.unique(flat_ids, return_index=True, return_inverse=True)
             rep = first[inv].astype(np.int32)
             rep[flat_ids == 0] = -1
@@ -267,7 +275,7 @@ class MixtureCore:
             self._opt_flags = flags
         if getattr(self, "_opt_stamp", None) != self._stamp():
             u_blocks = self._packed_blocks(lambda p: p.unconstrained, lambda p: p.numpy())
-            eng.set_unconstrained(eng.pack(*u_blocks))
+            eng.set_unconstrained(eng.pack(*u_blocks, inactive=0.0))
             self._opt_stamp = self._stamp()
         return eng
 

@@ -12,6 +12,8 @@ from . import _lib
 from .device import DeviceBuffer, as_view
 
 DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
+# lengthscale of the input columns outside a kernel's active_dims: x / l and z / l vanish, so does every gradient through them
+INACTIVE_LENGTHSCALE = 1e150
 
 
 @dataclass
@@ -26,6 +28,10 @@ class GPBlock:
     q_sqrt: np.ndarray  # [L, M, M]
     mean_c: Optional[np.ndarray] = None  # [L] or None (Zero mean function)
     noise: Optional[np.ndarray] = None  # [L] Gaussian likelihood variance (experts only)
+    active_dims: Optional[List[Optional[np.ndarray]]] = None  # per kernel: input columns it reads (None: all)
+
+    def active(self, i):
+        return None if self.active_dims is None or self.active_dims[i] is None else np.asarray(self.active_dims[i], dtype=np.int64)
 
     @property
     def M(self):
@@ -128,7 +134,9 @@ class Engine:
             pass
 
     # ---- packing ---------------------------------------------------------------------------------
-    def pack(self, experts: List[GPBlock], gating: GPBlock) -> np.ndarray:
+    def pack(self, experts: List[GPBlock], gating: GPBlock, inactive: float = INACTIVE_LENGTHSCALE) -> np.ndarray:
+        """-> the packed buffer.  `inactive`: what the lengthscale slots outside a kernel's active_dims receive (the huge
+        lengthscale for parameter values; 0 when variable ids / unconstrained values are packed: those slots are no variables)."""
         lo, Mp, D = self.lo, self.Mp, self.D
         flat = np.zeros(lo.total)
         ls = flat[lo.lengthscales:lo.lengthscales + self.Q * D].reshape(self.Q, D)
@@ -140,7 +148,12 @@ class Engine:
         nz = flat[lo.noise:lo.noise + self.Pe]
         for gp, (g0, nk, l0, L, M) in zip(list(experts) + [gating], self.blocks_meta):
             for i in range(nk):
-                ls[g0 + i] = np.broadcast_to(np.asarray(gp.lengthscales[i], dtype=np.float64), (D,))
+                ad = gp.active(i)
+                if ad is None:
+                    ls[g0 + i] = np.broadcast_to(np.asarray(gp.lengthscales[i], dtype=np.float64), (D,))
+                else:
+                    ls[g0 + i] = inactive
+                    ls[g0 + i, ad] = np.broadcast_to(np.asarray(gp.lengthscales[i], dtype=np.float64), (ad.size,))
                 kv[g0 + i] = float(gp.variances[i])
                 Z[g0 + i, :M] = gp.Z
             qm[l0:l0 + L, :M] = np.asarray(gp.q_mu).T
@@ -153,6 +166,7 @@ class Engine:
 
     def set_params(self, experts, gating):
         self._ls_shapes = [[np.shape(ls) for ls in gp.lengthscales] for gp in list(experts) + [gating]]
+        self._ls_active = [[gp.active(i) for i in range(len(gp.lengthscales))] for gp in list(experts) + [gating]]
         self.params.copy_from(self.pack(experts, gating))
 
     def unpack_grads(self, flat: np.ndarray):
@@ -168,8 +182,9 @@ class Engine:
         for bi, (g0, nk, l0, L, M) in enumerate(self.blocks_meta):
             gl = []
             for i in range(nk):
-                shp = self._ls_shapes[bi][i]
-                gl.append(ls[g0 + i].sum() if shp == () else ls[g0 + i].copy())
+                shp, ad = self._ls_shapes[bi][i], self._ls_active[bi][i]
+                row = ls[g0 + i] if ad is None else ls[g0 + i][ad]
+                gl.append(row.sum() if shp == () else row.copy())
             out.append(GPGrads(
                 Z=Z[g0:g0 + nk, :M].sum(0),
                 lengthscales=gl,

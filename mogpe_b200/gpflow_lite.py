@@ -192,11 +192,30 @@ class SquaredExponential(Kernel):
     """k(x, z) = variance * exp(-0.5 |x/l - z/l|^2); lengthscales scalar or [D] (ARD)."""
 
     def __init__(self, variance=1.0, lengthscales=1.0, active_dims=None, name=None):
-        if active_dims is not None:
-            raise NotImplementedError("active_dims is not supported by the CUDA path yet")
         self.variance = Parameter(variance, transform=positive(), name="variance")
         self.lengthscales = Parameter(lengthscales, transform=positive(), name="lengthscales")
         self.name = name
+        # gpflow.kernels.Kernel(active_dims=...): the kernel acts on these input columns only (a slice or a list of column
+        # indices; None = all).  The CUDA path keeps the full-width layout and gives the other columns an effectively infinite
+        # lengthscale (engine.INACTIVE_LENGTHSCALE), which is the same function and has the same gradients.
+        self.active_dims = active_dims
+        if active_dims is not None and not isinstance(active_dims, slice):
+            ad = np.asarray(active_dims, dtype=np.int64).reshape(-1)
+            if ad.size == 0 or np.any(ad < 0) or len(set(ad.tolist())) != ad.size:
+                raise ValueError("active_dims must be distinct non-negative column indices")
+            if self.lengthscales.unconstrained.ndim > 0 and self.lengthscales.unconstrained.size != ad.size:
+                raise ValueError("ARD lengthscales need one entry per active dimension")
+            self.active_dims = ad
+
+    def active_columns(self, input_dim: int):
+        """Column indices this kernel reads for inputs with `input_dim` columns (None: all of them)."""
+        ad = self.active_dims
+        if ad is None:
+            return None
+        cols = np.arange(input_dim)[ad] if isinstance(ad, slice) else np.asarray(ad)
+        if cols.size == 0 or cols.max() >= input_dim:
+            raise ValueError(f"active_dims {ad} do not fit inputs with {input_dim} columns")
+        return None if (cols.size == input_dim and np.array_equal(cols, np.arange(input_dim))) else cols
 
     @property
     def ard(self):

@@ -39,11 +39,13 @@ def parse_single_kernel(kernel_cfg, input_dim):
     if name != "rbf":
         raise NotImplementedError(f"Kernel name {name} is not on the CUDA path (only 'rbf'; the reference also parses "
                                   "'cosine' and 'product')")
-    if _get(kernel_cfg, "active_dims") is not None:
-        raise NotImplementedError("active_dims is not supported by the CUDA path yet")
+    active_dims = _get(kernel_cfg, "active_dims")  # reference parse_active_dims / parse_lengthscale (model_parsers.py:18-44, 287-292)
+    n_ls = input_dim if active_dims is None else len(active_dims)
     ls = _get(kernel_cfg, "params.lengthscale", 1.0, "No lengthscale in config so setting it to 1.0")
     var = _get(kernel_cfg, "params.variance", 1.0, "No variance in config so setting it to 1.0")
-    return gl.RBF(lengthscales=np.full((input_dim,), float(ls)), variance=float(var))  # ARD vector, as the reference builds
+    # ARD vector (one entry per active dimension), as the reference builds
+    return gl.RBF(lengthscales=np.full((n_ls,), float(ls)), variance=float(var),
+                  active_dims=None if active_dims is None else [int(d) for d in active_dims])
 
 
 def parse_kernel(kernels_cfg, input_dim, output_dim):
@@ -121,7 +123,9 @@ def parse_gating_network(cfg, X, rng):
     if g is None:
         raise NotImplementedError("gating_network not specified in toml config")
     if g.get("active_dims") is not None:
-        raise NotImplementedError("gating_network.active_dims is not supported by the CUDA path yet")
+        raise NotImplementedError("gating_network.active_dims (the reference slices the gating inducing inputs but not the "
+                                  "gating kernel's view of X, model_parsers.py:331-336) is not supported: put active_dims on "
+                                  "the gating kernel instead")
     if "num_experts" not in cfg:
         raise NotImplementedError("num_experts not specified in toml config")
     K = int(cfg["num_experts"])

@@ -20,7 +20,7 @@ A model is described by a plain ``spec`` dict (constrained-space values, all flo
       "gating": gp,                             # G = 1 (Bernoulli, K=2) or G = K (Softmax)
     }
     gp = {
-      "Z": [M, D], "kernels": [ {"lengthscales": [D] or scalar, "variance": scalar}, ... ],
+      "Z": [M, D], "kernels": [ {"lengthscales": [D] or scalar, "variance": scalar[, "active_dims": column indices]}, ... ],
             # one kernel shared by all L latents, or L kernels (SeparateIndependent, shared Z)
       "q_mu": [M, L], "q_sqrt": [L, M, M] (lower-triangular), "mean_c": None | [L],
       "noise_variance": [L]   (experts only; Gaussian likelihood variance per output)
@@ -94,7 +94,14 @@ def _lengthscales(kern, D):
     return np.broadcast_to(ls, (D,)) if ls.ndim == 0 else ls
 
 
+def _slice(kern, X):
+    """gpflow Kernel.slice: a kernel built with active_dims sees only those input columns."""
+    ad = kern.get("active_dims")
+    return X if ad is None or X is None else X[..., np.asarray(ad, dtype=np.int64)]
+
+
 def rbf_K(kern, X, X2=None):
+    X, X2 = _slice(kern, X), _slice(kern, X2)
     D = X.shape[-1]
     ls = _lengthscales(kern, D)
     Xs = X / ls

@@ -68,7 +68,10 @@ class SVGP:
         self.Z = Z.clone().requires_grad_(True)
         self.ard = []
         self.ls_u, self.kvar_u = [], []
+        self.active = []  # per kernel: the input columns it reads (gpflow active_dims) or None
         for k in gp["kernels"]:
+            ad = k.get("active_dims")
+            self.active.append(None if ad is None else torch.as_tensor(list(ad), dtype=torch.long))
             ls = _t(k["lengthscales"])
             self.ls_u.append(softplus_inverse(ls).clone().requires_grad_(True))
             self.kvar_u.append(softplus_inverse(_t(k["variance"])).clone().requires_grad_(True))
@@ -110,6 +113,10 @@ class SVGP:
     # gpflow arithmetic ------------------------------------------------------------------------
     def K(self, l, X, X2=None):
         ls, var = self.kernel(l)
+        ad = self.active[0 if len(self.ls_u) == 1 else l]
+        if ad is not None:  # gpflow Kernel.slice
+            X = X[:, ad]
+            X2 = None if X2 is None else X2[:, ad]
         Xs = X / ls
         if X2 is None:
             sq = (Xs * Xs).sum(-1, keepdim=True)

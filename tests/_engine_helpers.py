@@ -14,6 +14,8 @@ def block_from_gp(gp, is_expert):
         q_sqrt=np.asarray(gp["q_sqrt"], dtype=np.float64),
         mean_c=None if gp.get("mean_c") is None else np.asarray(gp["mean_c"], dtype=np.float64),
         noise=np.broadcast_to(np.asarray(gp["noise_variance"], dtype=np.float64).reshape(-1), (L,)).copy() if is_expert else None,
+        active_dims=([k.get("active_dims") for k in gp["kernels"]] if any(k.get("active_dims") is not None for k in gp["kernels"])
+                     else None),
     )
 
 

@@ -5,7 +5,8 @@ from mogpe_b200 import gpflow_lite as gl
 
 
 def _kernel(gp, L):
-    ks = [gl.RBF(variance=k["variance"], lengthscales=np.asarray(k["lengthscales"], dtype=float)) for k in gp["kernels"]]
+    ks = [gl.RBF(variance=k["variance"], lengthscales=np.asarray(k["lengthscales"], dtype=float), active_dims=k.get("active_dims"))
+          for k in gp["kernels"]]
     if len(ks) == 1:
         return ks[0] if L == 1 else gl.SharedIndependent(ks[0], L)
     return gl.SeparateIndependent(ks)

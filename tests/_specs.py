@@ -70,3 +70,17 @@ def make_spec(seed=0, N=24, D=2, F=1, K=2, M=8, S=1, flavour="keras", bound="fur
 
 FLAVOURS = ["keras", "legacy"]
 BOUNDS = ["further_gating", "tight", "further"]
+
+
+def restrict_active_dims(spec, expert_dims, gating_dims):
+    """Give every kernel of the spec gpflow `active_dims` (column indices) and cut its ARD lengthscales down to them."""
+    def cut(gp, dims):
+        for k in gp["kernels"]:
+            k["active_dims"] = list(dims)
+            ls = np.asarray(k["lengthscales"], dtype=float)
+            if ls.ndim:
+                k["lengthscales"] = ls[list(dims)].copy()
+    for gp in spec["experts"]:
+        cut(gp, expert_dims)
+    cut(spec["gating"], gating_dims)
+    return spec

@@ -219,3 +219,19 @@ def test_every_mixture_config_of_the_reference_examples_loads():
                                 "config_svgp_m_32_full.toml"]
     assert "cosine" in rejected["config_2_experts.toml"]
     assert all("gating_network" in rejected[k] for k in rejected if k != "config_2_experts.toml")
+
+
+def test_toml_kernel_active_dims(tmp_path):
+    """`active_dims` on a kernel table (reference parse_active_dims / parse_lengthscale, model_parsers.py:18-44, 287-292): the
+    kernel reads those input columns only and gets one ARD lengthscale per active dimension."""
+    from mogpe_b200.training import MixtureOfSVGPExperts_from_toml
+
+    rng = np.random.default_rng(0)
+    X, Y = rng.standard_normal((80, 3)), rng.standard_normal((80, 1))
+    p = tmp_path / "active.toml"
+    p.write_text(TOML.replace('name = "rbf"\n', 'name = "rbf"\nactive_dims = [0, 2]\n', 1))  # first expert's kernel table
+    model = MixtureOfSVGPExperts_from_toml(str(p), (X, Y), seed=1)
+    e0, e1 = model.experts.experts_list
+    assert e0.kernel.active_columns(3).tolist() == [0, 2] and e0.kernel.lengthscales.numpy().shape == (2,)
+    assert e1.kernel.active_columns(3) is None and e1.kernel.lengthscales.numpy().shape == (3,)
+    assert e0.Z.numpy().shape == (32, 3)  # the inducing inputs keep every column, as in gpflow

@@ -422,3 +422,35 @@ def test_dlpack_only_producer_is_consumed_zero_copy():
     d = lambda a: OnlyDLPack(torch.as_tensor(np.ascontiguousarray(a), device="cuda"))
     got = eng.elbo(d(X), d(Y), "further_gating", 1, 400 / 40, d(eps_u), d(eps["h"]), None, want_grads=False)
     assert got.elbo == pytest.approx(ref.elbo, rel=1e-13)
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+def test_kernels_with_active_dims(flavour):
+    """gpflow kernels built with active_dims (experts on columns 0 and 2, the gating network on column 1 of 3-D inputs): the
+    objective, the gradients of every variable (the inducing inputs keep all three columns; the inactive ones get zero
+    gradient) and the device-side optimiser (whose variable map must skip the lengthscale slots of inactive columns)."""
+    from oracle import ref_torch as rt
+    from mogpe_b200._model_core import Adam
+    from tests._model_helpers import model_from_spec, oracle_grads_in_model_order
+    from tests._specs import restrict_active_dims
+
+    spec, X, Y, eps = make_spec(seed=91, N=120, D=3, F=1, K=2, M=12, S=2, flavour=flavour, num_data=1200, gating_mean_c=0.1)
+    restrict_active_dims(spec, expert_dims=[0, 2], gating_dims=[1])
+    model = model_from_spec(spec)
+    ref, grads_u = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    val, grads = model.elbo_and_gradients((X, Y), eps=eps)
+    assert abs(val - ref) <= 1e-8 * abs(ref)
+    want = oracle_grads_in_model_order(spec, model, grads_u)
+    for p, g, w in zip(model.trainable_variables, grads, want):
+        w = np.asarray(w)
+        assert np.max(np.abs(np.asarray(g).reshape(w.shape) - w)) <= 1e-6 * max(1.0, np.max(np.abs(w))), p.name
+    # host Adam and device Adam walk the same path (the variable map of the device optimiser handles the scattered slots)
+    a, b = model_from_spec(spec), model_from_spec(spec)
+    for m in (a, b):
+        m.set_seed(7)
+        m.compile(optimizer=Adam(learning_rate=0.02))
+    for _ in range(4):
+        a.train_step((X, Y))
+    b.fit(X, Y, epochs=4, batch_size=120, shuffle=False)
+    for pa, pb in zip(a.trainable_variables, b.trainable_variables):
+        np.testing.assert_allclose(pb.unconstrained, pa.unconstrained, rtol=1e-9, atol=1e-11, err_msg=pa.name)

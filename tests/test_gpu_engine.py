@@ -344,6 +344,34 @@ def test_int8_step_general_structures_match_oracle(bound, K, F, S, sep):
     eng.close()
 
 
+def test_int8_step_with_active_dims():
+    """Kernels restricted to a subset of the input columns (gpflow active_dims) on the INT8 path: the inactive columns carry
+    the huge lengthscale of engine.INACTIVE_LENGTHSCALE through kuf8 / xs_prep / kuf_grad_slice / kuu."""
+    from oracle import ref_torch as rt
+    from tests._engine_helpers import engine_from_spec, engine_grads_named, oracle_grads_constrained, run_engine_elbo
+    from tests._specs import restrict_active_dims
+
+    N = 2048
+    spec, X, Y, eps = make_spec(seed=55, N=N, D=3, F=1, K=2, M=512, S=1, flavour="keras", bound="further_gating", num_data=30000)
+    restrict_active_dims(spec, expert_dims=[0, 2], gating_dims=[1, 2])
+    eng = engine_from_spec(spec, max_batch=N)
+    ref, grads_u = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    want = oracle_grads_constrained(spec, grads_u)
+    eng.profile(True)
+    res = run_engine_elbo(eng, spec, X, Y, eps)
+    assert eng.profile_read_int8()["launches"] == 6
+    eng.profile(False)
+    assert abs(res.elbo - ref) <= RTOL_VALUE * abs(ref), (res.elbo, ref)
+    got = engine_grads_named(res, spec)
+    bad = {}
+    for name, g in want.items():
+        err = np.max(np.abs(np.asarray(got[name]) - g))
+        if err > RTOL_GRAD * max(1.0, np.max(np.abs(g))):
+            bad[name] = err / max(1.0, np.max(np.abs(g)))
+    assert not bad, bad
+    eng.close()
+
+
 def test_int8_step_applies_above_512_inducing_points():
     """M = 520 is padded to 640 (a multiple of the 128-row tile), so the step runs on the INT8 tensor cores; the 120 padding
     rows / columns of every operand must stay inert (unit diagonal in Kuu, zero elsewhere)."""

@@ -191,3 +191,34 @@ def test_autograd_vs_finite_differences(flavour, bound, K):
             fd = (rn.elbo(_perturb(spec, name, idx, h), X, Y, eps) - rn.elbo(_perturb(spec, name, idx, -h), X, Y, eps)) / (2 * h)
             gi = g[idx] if g.shape else float(g)
             assert abs(fd - gi) <= 2e-6 * max(1.0, abs(gi), abs(val) * 1e-3), (name, idx, fd, gi)
+
+
+def test_active_dims_slice_the_kernel_inputs():
+    """gpflow Kernel.slice: a kernel with active_dims is the same function of the selected input columns; both oracle
+    implementations honour it and agree, and the inducing-input gradient of an inactive column is exactly zero."""
+    from tests._specs import restrict_active_dims
+
+    spec, X, Y, eps = make_spec(seed=12, N=24, D=3, F=1, K=2, M=6, S=2, flavour="keras", num_data=200)
+    restrict_active_dims(spec, expert_dims=[0, 2], gating_dims=[1])
+    k = spec["experts"][0]["kernels"][0]
+    Z = spec["experts"][0]["Z"]
+    plain = {"lengthscales": k["lengthscales"], "variance": k["variance"]}
+    np.testing.assert_array_equal(rn.rbf_K(k, X, Z), rn.rbf_K(plain, X[:, [0, 2]], Z[:, [0, 2]]))
+    a = rn.elbo(spec, X, Y, eps)
+    val, grads = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    assert abs(a - float(val)) <= 1e-11 * max(1.0, abs(a))
+    assert np.all(np.asarray(grads["experts/0/Z"])[:, 1] == 0.0) and np.all(np.asarray(grads["gating/Z"])[:, [0, 2]] == 0.0)
+    assert np.asarray(grads["experts/0/kernels/0/lengthscales"]).shape == (2,)
+
+
+def test_front_end_kernels_accept_active_dims():
+    """gpflow_lite.RBF(active_dims=...) (list or slice) resolves to column indices; ARD lengthscales must match their count."""
+    from mogpe_b200 import gpflow_lite as gl
+
+    assert gl.RBF(lengthscales=[1.0, 2.0], active_dims=[0, 2]).active_columns(3).tolist() == [0, 2]
+    assert gl.RBF(active_dims=slice(1, 3)).active_columns(4).tolist() == [1, 2]
+    assert gl.RBF(lengthscales=[1.0, 2.0], active_dims=[0, 1]).active_columns(2) is None  # all columns, in order
+    with pytest.raises(ValueError):
+        gl.RBF(lengthscales=[1.0, 2.0, 3.0], active_dims=[0, 2])
+    with pytest.raises(ValueError):
+        gl.RBF(active_dims=[0, 5]).active_columns(3)
