@@ -166,7 +166,8 @@ __device__ __forceinline__ void unslice4(const uint32_t (&w)[NS], double (&a)[4]
   for (int j = 0; j < 4; j++) a[j] = fma(int_to_double(half[1][j]), P1, int_to_double(half[0][j])) * P1;
 }
 
-template <int NS>
+// (ISL: integer slicing, slice_words_int -- measured same-box: 462 us against 417 with the FP64 slicing here, so off)
+template <int NS, bool ISL = false>
 __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__ md, const int8_t* __restrict__ A8,
                                                     const double* __restrict__ a_scale, const double* __restrict__ V,
                                                     const double* __restrict__ dmean, const double* __restrict__ dfvar,
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
   constexpr int PITCH = 65;  // words per [n] row of the staging tile (64 m + 1: column groups of a warp spread over the banks)
   __shared__ uint32_t stage[2][64][PITCH];  // [slice half][n][m]: the four digit bytes of planes 4 half .. 4 half + 3
   __shared__ double s_inv[64], s_dv[64];
+  __shared__ int s_ie[64];  // exponent of 1 / scale (integer slicing)
   const int g = blockIdx.z, Mp = md->Mp, m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tid = threadIdx.x;
   const int lb = md->glat_begin[g], le = md->glat_begin[g + 1], vb = md->gvec_begin[g], ve = md->gvec_begin[g + 1];
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
     const double sc = pow2_scale(1.001 * b);
     // column n = 4 i + j lives at [16 j + i]: the 16 lanes of a tile row read consecutive words (no bank conflicts)
     s_inv[(tid & 3) * 16 + (tid >> 2)] = 1.0 / sc;
+    s_ie[(tid & 3) * 16 + (tid >> 2)] = 1023 - ((__double2hiint(sc) >> 20) & 0x7ff);
     s_dv[(tid & 3) * 16 + (tid >> 2)] = dv;
     if (blockIdx.y == 0) nscale[(long long)g * Bp + n] = sc;
   }
@@ -256,7 +259,8 @@ __global__ void __launch_bounds__(256) abar8_kernel(const ModelDev* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t wh, wl;
-      slice_words<NS>(ab[j] * s_inv[j * 16 + (tid & 15)], wh, wl);
+      if constexpr (ISL) slice_words_int<NS>(ab[j], s_ie[j * 16 + (tid & 15)], wh, wl);
+      else slice_words<NS>(ab[j] * s_inv[j * 16 + (tid & 15)], wh, wl);
       stage[0][c4 + j][ml] = wh;
       stage[1][c4 + j][ml] = wl;
     }
@@ -344,7 +348,9 @@ __global__ void xs_prep_kernel(const ModelDev* __restrict__ md, const double* __
 //       W product collected (wmax, bit patterns) -- no separate slicing pass over W.
 // One warp per row m, every lane four consecutive columns per step (128 columns per warp step: 1 KB of W, 128 B per byte
 // plane).  n_chunk must be a multiple of 128.       grid (Mp/8, Q, nsplit), block 256
-template <int DMAX, int NS>
+// ISL: W is re-sliced with integer operations (slice_words_int): 455 -> 436 us same-box -- this kernel is bound by its FP64
+// instructions, and the slicing is the part of them that integer units can take over.
+template <int DMAX, int NS, bool ISL = true>
 __global__ void __launch_bounds__(256) kuf_grad_slice_kernel(const ModelDev* __restrict__ md, const double* __restrict__ params,
                                                              Layout lo, const double* __restrict__ XS, int Bc, int Bp,
                                                              const double* __restrict__ W,
@@ -366,6 +372,7 @@ __global__ void __launch_bounds__(256) kuf_grad_slice_kernel(const ModelDev* __r
   }
   const double sc = pow2_scale(__longlong_as_double((long long)wmax[(long long)g * Mp + m]));
   const double inv = 1.0 / sc;
+  const int inv_e = 1023 - ((__double2hiint(sc) >> 20) & 0x7ff);  // sc = 2^e: only the exponent is needed by the integer slicing
   if (lane == 0 && blockIdx.z == 0) w_scale[(long long)g * Mp + m] = sc;
   const double* w = W + ((long long)g * Mp + m) * Bp;
   const double* xg = XS + (long long)g * Bp * DMAX;
@@ -378,7 +385,8 @@ __global__ void __launch_bounds__(256) kuf_grad_slice_kernel(const ModelDev* __r
     // branch-free over the four columns (independent exp chains in flight); padding columns have r2 ~ 1e300 -> E = 0
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      slice_words<NS>(wv[j] * inv, wh[j], wl[j]);
+      if constexpr (ISL) slice_words_int<NS>(wv[j], inv_e, wh[j], wl[j]);
+      else slice_words<NS>(wv[j] * inv, wh[j], wl[j]);
       double u[DMAX];
 #pragma unroll
       for (int d4 = 0; d4 < DMAX; d4 += 4) ld_global_256(xg + (long long)(n4 + j) * DMAX + d4, *reinterpret_cast<double(*)[4]>(&u[d4]));
