@@ -233,7 +233,8 @@ mogpe_status mogpe_set_dp_overlap(mogpe_handle* h, int32_t on);
  * mogpe/keras/mixture_of_experts/mosvgpe.py:61-63, tf.optimizers.Adam with TF defaults).
  *   var_rep [total] (host): for every entry of the packed buffer, the index of the representative entry of the
  *     variable it belongs to (itself if untied), or -1 for entries that are not variables (padding, the strict upper
- *     triangle of q_sqrt, non-trainable parameters).
+ *     triangle of q_sqrt, non-trainable parameters).  A value r < -1 means representative -2 - r AND a positive (softplus)
+ *     parameter regardless of its position: the diagonal of a q_diag=True q_sqrt (gpflow: positive(), not FillTriangular).
  *   u [total] (device): the unconstrained variables in the packed layout (lengthscales / variances / noise hold the
  *     pre-softplus values; everything else is stored as is).
  * mogpe_opt_transform writes params = T(u); mogpe_opt_adam_step chains `grads` (d ELBO / d constrained, as returned by

@@ -45,7 +45,7 @@ def svgp_to_block(gp: SVGP, is_expert: bool) -> GPBlock:
         lengthscales=[k.lengthscales.numpy() for k in gp.latent_kernel_list],
         variances=[float(k.variance.numpy()) for k in gp.latent_kernel_list],
         q_mu=gp.q_mu.numpy(),
-        q_sqrt=gp.q_sqrt.numpy(),
+        q_sqrt=gp.q_sqrt_full(),
         mean_c=mean_c,
         noise=noise,
         active_dims=_active_dims(gp),
@@ -65,7 +65,8 @@ def accumulate_param_grads(acc: Dict[int, np.ndarray], gp: SVGP, g: GPGrads, is_
         add(k.lengthscales, np.asarray(gl))
         add(k.variance, np.asarray(gv))
     add(gp.q_mu, g.q_mu)
-    add(gp.q_sqrt, g.q_sqrt)
+    # (q_diag=True: only the diagonals of the [L, M, M] factors are variables -> [M, L])
+    add(gp.q_sqrt, np.diagonal(g.q_sqrt, axis1=-2, axis2=-1).T if gp.q_diag else g.q_sqrt)
     if isinstance(gp.mean_function, Constant):
         c = gp.mean_function.c
         gc = g.mean_c if c.unconstrained.size == g.mean_c.size else np.sum(g.mean_c)
@@ -214,8 +215,10 @@ class MixtureCore:
     def _gps(self):
         return self.expert_gps + [self.gating_gp]
 
-    def _packed_blocks(self, value_of, tri_of):
-        """GPBlocks whose arrays are produced by value_of(param) (q_sqrt: tri_of(param) -> [L, M, M])."""
+    def _packed_blocks(self, value_of, tri_of, diag_of=None):
+        """GPBlocks whose arrays are produced by value_of(param) (q_sqrt: tri_of(param) -> [L, M, M]; the [M, L] diagonal of a
+        q_diag=True GP: diag_of(param), value_of by default)."""
+        diag_of = diag_of or value_of
         blocks = []
         for i, gp in enumerate(self._gps()):
             is_expert = i < len(self.expert_gps)
@@ -231,7 +234,7 @@ class MixtureCore:
                 lengthscales=[np.asarray(value_of(k.lengthscales), dtype=np.float64) for k in gp.latent_kernel_list],
                 variances=[float(np.asarray(value_of(k.variance))) for k in gp.latent_kernel_list],
                 q_mu=np.asarray(value_of(gp.q_mu), dtype=np.float64),
-                q_sqrt=np.asarray(tri_of(gp.q_sqrt), dtype=np.float64),
+                q_sqrt=np.asarray(gp.diag_embed(diag_of(gp.q_sqrt)) if gp.q_diag else tri_of(gp.q_sqrt), dtype=np.float64),
                 mean_c=mean_c, noise=noise, active_dims=_active_dims(gp)))
         return blocks[:-1], blocks[-1]
 
@@ -265,6 +268,14 @@ class MixtureCore:
             uniq, first, inv = np.unique(flat_ids, return_index=True, return_inverse=True)
             rep = first[inv].astype(np.int32)
             rep[flat_ids == 0] = -1
+            if any(gp.q_diag for gp in self._gps()):
+                # the diagonal of a q_diag=True q_sqrt is a positive() parameter in the middle of the identity-transformed
+                # q_sqrt region of the layout: flag those entries (include/mogpe_b200.h, var_rep < -1)
+                zeros = lambda p: np.zeros(p.unconstrained.shape)
+                mask = eng.pack(*self._packed_blocks(zeros, lambda p: np.zeros(p.numpy().shape),
+                                                     lambda p: np.ones(p.unconstrained.shape)), inactive=0.0) > 0
+                sel = mask & (rep >= 0)
+                rep[sel] = -2 - rep[sel]
             self._var_positions = {
                 pid: (first[np.searchsorted(uniq, arr.astype(np.int64).reshape(-1))].reshape(arr.shape), p)
                 for pid, (arr, p) in ids.items() if p.trainable}
@@ -274,7 +285,7 @@ class MixtureCore:
             self._opt_engine = eng
             self._opt_flags = flags
         if getattr(self, "_opt_stamp", None) != self._stamp():
-            u_blocks = self._packed_blocks(lambda p: p.unconstrained, lambda p: p.numpy())
+            u_blocks = self._packed_blocks(lambda p: p.unconstrained, lambda p: p.numpy(), lambda p: p.unconstrained)
             eng.set_unconstrained(eng.pack(*u_blocks, inactive=0.0))
             self._opt_stamp = self._stamp()
         return eng

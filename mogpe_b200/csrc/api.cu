@@ -2288,9 +2288,11 @@ extern "C" mogpe_status mogpe_profile_read_streaming(mogpe_handle* h, double* ms
 extern "C" mogpe_status mogpe_opt_setup(mogpe_handle* h, const int32_t* var_rep, double noise_lower_bound) {
   if (!h || !var_rep) return MOGPE_ERR_INVALID;
   const long long n = h->lo.total;
-  for (long long i = 0; i < n; i++)
-    if (var_rep[i] >= n || (var_rep[i] >= 0 && var_rep[var_rep[i]] != var_rep[i]))
+  for (long long i = 0; i < n; i++) {
+    const int r = var_rep_index(var_rep[i]);
+    if (r >= n || (r >= 0 && var_rep_index(var_rep[r]) != r))
       H_FAIL(h, MOGPE_ERR_INVALID, "var_rep[%lld] = %d is not a representative index", i, var_rep[i]);
+  }
   H_CUDA(h, cudaSetDevice(h->device));
   if (!h->var_rep) {
     H_CUDA(h, dalloc(&h->var_rep, (size_t)n));

@@ -828,15 +828,21 @@ __device__ __forceinline__ int param_kind(long long i, Layout lo) {  // 0 identi
   return 0;                        // Z, q_mu, q_sqrt (lower triangle), mean_c
 }
 
+// var_rep encoding: r >= 0 representative index; -1 not a variable; r < -1: representative -2 - r AND the entry is a positive
+// (softplus) parameter whatever its position -- the diagonal of a q_diag=True q_sqrt, which gpflow constrains with
+// positive() where the full q_sqrt is an unconstrained FillTriangular.
+__host__ __device__ __forceinline__ int var_rep_index(int v) { return v >= -1 ? v : -2 - v; }
+__host__ __device__ __forceinline__ bool var_rep_softplus(int v) { return v < -1; }
+
 // gu[i] = dELBO/du_i (chain through the bijector); tied entries are accumulated into their representative
 __global__ void opt_chain_kernel(long long n, Layout lo, const double* __restrict__ u, const double* __restrict__ g,
                                  const int* __restrict__ var_rep, double* __restrict__ gu) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int rep = var_rep[i];
+  const int rep = var_rep_index(var_rep[i]);
   if (rep < 0) return;
   double v = g[i];
-  if (param_kind(i, lo) != 0) v *= 1.0 / (1.0 + exp(-u[i]));  // d softplus / du = sigmoid(u)
+  if (param_kind(i, lo) != 0 || var_rep_softplus(var_rep[i])) v *= 1.0 / (1.0 + exp(-u[i]));  // d softplus / du = sigmoid(u)
   if (rep == i) atomicAdd(gu + i, v);
   else atomicAdd(gu + rep, v);
 }
@@ -847,7 +853,7 @@ __global__ void opt_adam_kernel(long long n, const int* __restrict__ var_rep, co
                                 double* __restrict__ u, double* __restrict__ m, double* __restrict__ v, double lr_t,
                                 double b1, double b2, double eps, const double* __restrict__ lr_t_dev) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || var_rep[i] != i) return;
+  if (i >= n || var_rep_index(var_rep[i]) != i) return;
   if (lr_t_dev) lr_t = *lr_t_dev;
   const double gl = -gu[i];
   const double mi = m[i] + (1.0 - b1) * (gl - m[i]);
@@ -871,11 +877,11 @@ __global__ void opt_transform_kernel(long long n, Layout lo, const int* __restri
                                      double noise_lower, double* __restrict__ params) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int rep = var_rep[i];
+  const int rep = var_rep_index(var_rep[i]);
   if (rep < 0) return;
   const double ui = u[rep];
   if (rep != i) u[i] = ui;
-  const int kind = param_kind(i, lo);
+  const int kind = var_rep_softplus(var_rep[i]) ? 1 : param_kind(i, lo);
   double p = ui;
   if (kind != 0) p = (ui > 0 ? ui : 0.0) + log1p(exp(-fabs(ui))) + (kind == 2 ? noise_lower : 0.0);  // stable softplus
   params[i] = p;

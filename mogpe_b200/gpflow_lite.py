@@ -402,8 +402,6 @@ class SVGP(Module):
 
     def __init__(self, kernel, likelihood, inducing_variable, mean_function=None, num_latent_gps: int = 1,
                  q_diag: bool = False, q_mu=None, q_sqrt=None, whiten: bool = True, num_data=None):
-        if q_diag:
-            raise NotImplementedError("q_diag=True is not implemented by the CUDA path (SURVEY 8f-4)")
         if not whiten:
             raise NotImplementedError("whiten=False is not implemented by the CUDA path (SURVEY 8f-4)")
         self.kernel = kernel
@@ -417,11 +415,34 @@ class SVGP(Module):
         if q_mu.shape != (M, L):
             raise ValueError(f"q_mu must be [{M}, {L}], got {q_mu.shape}")
         self.q_mu = Parameter(q_mu, name="q_mu")
-        q_sqrt = np.tile(np.eye(M)[None], (L, 1, 1)) if q_sqrt is None else np.asarray(q_sqrt, dtype=DEFAULT_FLOAT)
-        if q_sqrt.shape != (L, M, M):
-            raise ValueError(f"q_sqrt must be [{L}, {M}, {M}], got {q_sqrt.shape}")
-        self.q_sqrt = Parameter(np.tril(q_sqrt), transform=triangular(), name="q_sqrt")
+        if q_diag:
+            # gpflow SVGP._init_variational_parameters: a diagonal covariance, q_sqrt [M, L] with the positive() transform.  The
+            # CUDA path sees L diagonal [M, M] factors (q_sqrt_full): the same conditional, KL and gradients, restricted to the
+            # diagonal entries -- the only variables of those matrices.
+            q_sqrt = np.ones((M, L)) if q_sqrt is None else np.asarray(q_sqrt, dtype=DEFAULT_FLOAT)
+            if q_sqrt.shape != (M, L):
+                raise ValueError(f"q_sqrt must be [{M}, {L}] for q_diag=True, got {q_sqrt.shape}")
+            self.q_sqrt = Parameter(q_sqrt, transform=positive(), name="q_sqrt")
+        else:
+            q_sqrt = np.tile(np.eye(M)[None], (L, 1, 1)) if q_sqrt is None else np.asarray(q_sqrt, dtype=DEFAULT_FLOAT)
+            if q_sqrt.shape != (L, M, M):
+                raise ValueError(f"q_sqrt must be [{L}, {M}, {M}], got {q_sqrt.shape}")
+            self.q_sqrt = Parameter(np.tril(q_sqrt), transform=triangular(), name="q_sqrt")
         self._kernels = latent_kernels(kernel, L)
+
+    @staticmethod
+    def diag_embed(d):
+        """[M, L] -> [L, M, M] with d[:, l] on the diagonal of matrix l."""
+        d = np.asarray(d)
+        out = np.zeros((d.shape[1], d.shape[0], d.shape[0]), dtype=d.dtype)
+        idx = np.arange(d.shape[0])
+        out[:, idx, idx] = d.T
+        return out
+
+    def q_sqrt_full(self, values=None):
+        """The [L, M, M] Cholesky factors the CUDA path works with (`values`: a stand-in for the q_sqrt entries, e.g. variable ids)."""
+        v = self.q_sqrt.numpy() if values is None else values
+        return self.diag_embed(v) if self.q_diag else v
 
     @property
     def Z(self) -> Parameter:

@@ -29,7 +29,7 @@ class SVGPModel(SVGP):
         M, L = self.q_mu.numpy().shape
         if eps_u is None:
             eps_u = (rng or np.random.default_rng()).standard_normal((S, L, M))
-        u = self.q_mu.numpy().T[None] + np.einsum("lmk,slk->slm", self.q_sqrt.numpy(), np.asarray(eps_u))
+        u = self.q_mu.numpy().T[None] + np.einsum("lmk,slk->slm", self.q_sqrt_full(), np.asarray(eps_u))
         return np.transpose(u, (0, 2, 1))
 
     def predict_f(self, Xnew, num_inducing_samples: int = None, full_cov: bool = False, full_output_cov: bool = False,

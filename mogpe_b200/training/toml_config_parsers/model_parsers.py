@@ -98,7 +98,10 @@ def parse_inducing_points(svgp_cfg, output_dim, rng):
         q_mu = mean * np.ones((M, 1)) + rng.standard_normal((M, output_dim)) * var
     if ip.get("q_sqrt") is not None and M is not None:
         q_sqrt = np.array([np.tril(ip["q_sqrt"] * np.eye(M) @ np.abs(rng.standard_normal((M, M)))) for _ in range(output_dim)])
-    return q_mu, q_sqrt, bool(ip.get("q_diag", False)), bool(ip.get("inputs_trainable", True))
+    q_diag = bool(ip.get("q_diag", False))
+    if q_diag and q_sqrt is not None:
+        q_sqrt = np.diagonal(q_sqrt, axis1=-2, axis2=-1).T.copy()  # gpflow's q_diag=True parameter is [M, L]
+    return q_mu, q_sqrt, q_diag, bool(ip.get("inputs_trainable", True))
 
 
 def parse_inducing_variable(svgp_cfg, X, rng):

@@ -22,7 +22,8 @@ A model is described by a plain ``spec`` dict (constrained-space values, all flo
     gp = {
       "Z": [M, D], "kernels": [ {"lengthscales": [D] or scalar, "variance": scalar[, "active_dims": column indices]}, ... ],
             # one kernel shared by all L latents, or L kernels (SeparateIndependent, shared Z)
-      "q_mu": [M, L], "q_sqrt": [L, M, M] (lower-triangular), "mean_c": None | [L],
+      "q_mu": [M, L], "q_sqrt": [L, M, M] (lower-triangular) -- or [M, L] with "q_diag": True (gpflow's diagonal covariance) --,
+      "mean_c": None | [L],
       "noise_variance": [L]   (experts only; Gaussian likelihood variance per output)
     }
 
@@ -122,6 +123,17 @@ def rbf_Kdiag(kern, X):
     return np.full((X.shape[0],), float(kern["variance"]))
 
 
+def q_sqrt_full(gp):
+    """[L, M, M] Cholesky factors of q(u); gpflow's q_diag=True stores their diagonals as [M, L] (SVGP._init_variational_parameters)."""
+    q = np.asarray(gp["q_sqrt"], dtype=np.float64)
+    if not gp.get("q_diag"):
+        return q
+    out = np.zeros((q.shape[1], q.shape[0], q.shape[0]))
+    idx = np.arange(q.shape[0])
+    out[:, idx, idx] = q.T
+    return out
+
+
 def _kernel_for_latent(gp, l):
     ks = gp["kernels"]
     return ks[0] if len(ks) == 1 else ks[l]
@@ -166,7 +178,7 @@ def predict_f(gp, X):
     var = np.zeros((N, L))
     for l in range(L):
         m, v = base_conditional_latent(
-            _kernel_for_latent(gp, l), X, Z, np.asarray(gp["q_mu"])[:, l : l + 1], np.asarray(gp["q_sqrt"])[l]
+            _kernel_for_latent(gp, l), X, Z, np.asarray(gp["q_mu"])[:, l : l + 1], q_sqrt_full(gp)[l]
         )
         mean[:, l] = m[:, 0]
         var[:, l] = v
@@ -176,7 +188,7 @@ def predict_f(gp, X):
 def sample_inducing(gp, eps_u):
     """u_s = q_mu[:, l] + tril(q_sqrt_l) @ eps[s, l]  (TFP MultivariateNormalTriL.sample). -> [S, M, L]."""
     q_mu = np.asarray(gp["q_mu"])
-    q_sqrt = np.asarray(gp["q_sqrt"])
+    q_sqrt = q_sqrt_full(gp)
     S, L, M = eps_u.shape
     u = np.zeros((S, M, L))
     for s in range(S):
@@ -207,7 +219,7 @@ def predict_f_given_inducing_samples(gp, X, eps_u):
 def prior_kl(gp):
     """Appendix A.5 (gauss_kl, whitened, full q_sqrt), summed over the L latents."""
     q_mu = np.asarray(gp["q_mu"])
-    q_sqrt = np.tril(np.asarray(gp["q_sqrt"]))
+    q_sqrt = np.tril(q_sqrt_full(gp))
     M, L = q_mu.shape
     mahal = np.sum(q_mu * q_mu)
     logdet = np.sum(np.log(np.square(np.diagonal(q_sqrt, axis1=-2, axis2=-1))))

@@ -77,7 +77,11 @@ class SVGP:
             self.kvar_u.append(softplus_inverse(_t(k["variance"])).clone().requires_grad_(True))
         self.q_mu = _t(gp["q_mu"]).clone().requires_grad_(True)
         self.L = self.q_mu.shape[1]
-        self.q_sqrt_u = fill_triangular_inverse(torch.tril(_t(gp["q_sqrt"]))).clone().requires_grad_(True)
+        self.q_diag = bool(gp.get("q_diag"))
+        if self.q_diag:  # gpflow: q_sqrt [M, L] with the positive() (softplus) transform
+            self.q_sqrt_u = softplus_inverse(_t(gp["q_sqrt"])).clone().requires_grad_(True)
+        else:
+            self.q_sqrt_u = fill_triangular_inverse(torch.tril(_t(gp["q_sqrt"]))).clone().requires_grad_(True)
         c = gp.get("mean_c")
         self.c = None if c is None else _t(c).reshape(-1).clone().requires_grad_(True)
         self.noise_u = None
@@ -92,6 +96,8 @@ class SVGP:
 
     @property
     def q_sqrt(self):
+        if self.q_diag:
+            return torch.diag_embed(softplus(self.q_sqrt_u).T)  # [L, M, M]
         return fill_triangular(self.q_sqrt_u)
 
     @property

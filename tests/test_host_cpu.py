@@ -76,8 +76,11 @@ def test_parameter_roundtrip_and_errors():
         gl.Parameter(-1.0, transform=gl.positive())
     with pytest.raises(ValueError):
         gl.Gaussian(variance=1e-7)  # below the 1e-6 lower bound (mogpe/gps/likelihoods.py:21)
-    with pytest.raises(NotImplementedError):
-        gl.SVGP(gl.RBF(), gl.Gaussian(), np.zeros((3, 1)), q_diag=True)
+    qd = gl.SVGP(gl.RBF(), gl.Gaussian(), np.zeros((3, 1)), q_diag=True, num_latent_gps=2)  # gpflow: q_sqrt [M, L], positive()
+    assert qd.q_sqrt.numpy().shape == (3, 2) and isinstance(qd.q_sqrt.transform, type(gl.positive()))
+    np.testing.assert_array_equal(qd.q_sqrt_full(), np.tile(np.eye(3)[None], (2, 1, 1)))
+    with pytest.raises(ValueError):
+        gl.SVGP(gl.RBF(), gl.Gaussian(), np.zeros((3, 1)), q_diag=True, q_sqrt=np.ones((1, 3, 3)))
     with pytest.raises(NotImplementedError):
         gl.SVGP(gl.RBF(), gl.Gaussian(), np.zeros((3, 1)), whiten=False)
     with pytest.raises(ValueError):

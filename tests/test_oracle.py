@@ -222,3 +222,22 @@ def test_front_end_kernels_accept_active_dims():
         gl.RBF(lengthscales=[1.0, 2.0, 3.0], active_dims=[0, 2])
     with pytest.raises(ValueError):
         gl.RBF(active_dims=[0, 5]).active_columns(3)
+
+
+def test_q_diag_is_the_diagonal_special_case():
+    """gpflow q_diag=True (q_sqrt [M, L], positive transform): the same bound as full factors that happen to be diagonal, in
+    both oracle implementations; the unconstrained q_sqrt gradient is the softplus-chained diagonal of the full one."""
+    from tests._specs import make_q_diag
+
+    spec, X, Y, eps = make_spec(seed=21, N=20, D=2, F=2, K=2, M=6, S=2, flavour="keras", bound="further", num_data=150,
+                                separate_kernels=True)
+    full = copy.deepcopy(spec)
+    make_q_diag(spec)
+    for gp in full["experts"] + [full["gating"]]:
+        d = np.abs(np.diagonal(np.asarray(gp["q_sqrt"]), axis1=-2, axis2=-1))
+        gp["q_sqrt"] = np.stack([np.diag(r) for r in d])
+    a, b = rn.elbo(spec, X, Y, eps), rn.elbo(full, X, Y, eps)
+    assert a == pytest.approx(b, rel=1e-13)
+    val, grads = rt.MixtureOfSVGPExperts(spec).elbo_and_grads(X, Y, eps)
+    assert abs(a - float(val)) <= 1e-11 * max(1.0, abs(a))
+    assert np.asarray(grads["experts/0/q_sqrt"]).shape == (6, 2) and np.asarray(grads["gating/q_sqrt"]).shape == (6, 1)
