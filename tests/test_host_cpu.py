@@ -278,3 +278,25 @@ def test_dlpack_capsule_is_consumed_per_protocol_on_the_host():
         dev.as_view(OnlyDLPack(np.zeros(3, dtype=np.float32)))
     with pytest.raises(ValueError, match="contiguous"):
         dev.as_view(OnlyDLPack(np.zeros((4, 4))[:, ::2]))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the contract's keys, no GPU needed --
+    it times the restated reference (oracle/ref_torch.py) on the host cores."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "elbo_fwd_bwd_points_per_sec" and line["unit"] == "points/s"
+    assert line["steps"] == 2 and line["warmup"] == 3 and line["value"] > 0 and "workload" in line["config"]  # (W >= 3 is enforced)
+    assert line["e2e"] == {"value": line["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
