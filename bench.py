@@ -431,8 +431,16 @@ def main():
         step(i)
     barrier()
     # keep the GPU under the same load until nvidia-smi has had time to report (its first sample takes ~0.3 s)
+    # (every step contains a collective when world > 1: the NUMBER of these extra steps must be the same on all ranks, so rank
+    # 0's clock decides and the others follow -- a per-rank time test lets one rank leave the loop a step early and deadlocks
+    # the rest in their all-reduce)
     i = warmup
-    while time.perf_counter() - t_load < 0.6:
+    while True:
+        more = [time.perf_counter() - t_load < 0.6]
+        if world > 1:
+            dist.broadcast_object_list(more, src=0)
+        if not more[0]:
+            break
         step(i)
         i += 1
         torch.cuda.synchronize()
