@@ -333,7 +333,27 @@ def dp_parity_check(eng, wl, B, rank, world, pool, scale, local_rank):
     return out
 
 
+def _arm_watchdog():
+    """A multi-rank run whose ranks disagree on a collective hangs silently; give up loudly instead (default 30 min,
+    MOGPE_BENCH_TIMEOUT seconds; 0 disables).  A default run takes a few minutes."""
+    import threading
+
+    limit = float(os.environ.get("MOGPE_BENCH_TIMEOUT", "1800"))
+    if limit <= 0:
+        return
+
+    def expire():
+        sys.stderr.write(f"bench.py: no result after {limit:.0f} s (rank {os.environ.get('RANK', '0')}): giving up\n")
+        sys.stderr.flush()
+        os._exit(3)
+
+    t = threading.Timer(limit, expire)
+    t.daemon = True
+    t.start()
+
+
 def main():
+    _arm_watchdog()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
